@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — PCG DOF·iter/s of the Static3D solve on the BASELINE config (256^3 VCSEL-like block).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path
+  python bench.py --impl reference --steps K --warmup W    the reference's CPU path (NSPCG)
+
+A *step* is one pass of the hot path over one batch of synthetic input: `--iters` PCG iterations
+(operator apply + Jacobi preconditioner + axpys + dots) on the assembled-free 27-point brick
+operator of config B, FP64.
+
+  value      DOF·iter/s with all inputs resident in HBM (CUDA-event time of K steps, max over ranks)
+  e2e        the same metric through the public solver API with HOST buffers: every step uploads the
+             heat source and the initial field from pinned host memory, runs the iterations and reads
+             the temperatures back
+  roofline   the dominant kernel (operator apply, 7 FP64 words/DOF algorithmic) against the measured
+             HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline / --impl reference
+             the reference's own NSPCG (oracle/_ref, compiled from /root/reference) — or the oracle
+             port when that is absent — on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_DOF_ITER = 112.0   # 14 FP64 words: SURVEY.md §8(d), DESIGN.md §5
+BYTES_PER_DOF_APPLY = 56.0   # operator kernel: reads r, D^-1, p_old, c_lat, c_vert; writes p_new, q
+FALLBACK_HBM_GBS = 6650.0    # /opt/skills/guides/B200_PROFILING.md
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu=0):
+        self.gpu, self.proc, self.rows = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload(n):
+    from plask_b200 import configs
+    return configs.config_B(n)
+
+
+def pinned_copy(a):
+    """numpy array backed by CUDA-pinned host memory (torch is only the allocator)."""
+    import torch
+    t = torch.empty(a.shape, dtype=getattr(torch, str(a.dtype)), pin_memory=True)
+    v = t.numpy()
+    v[...] = a
+    return v, t
+
+
+# ----------------------------------------------------------------------------------- CPU arm
+
+def cpu_pcg_sample(n_sample, iters, want_ref=True):
+    """The reference's CPU iterative path on a bounded sample: assemble config B at n_sample^3 the
+    way setMatrix does (therm3d.cpp:170-279) and run NSPCG cg+ic (PLaSK default,
+    iterative_matrix.hpp:50,73) for `iters` iterations; falls back to the oracle's Jacobi-PCG port."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import oracle_thermal
+    from oracle import oracle as orc
+    p = workload(n_sample)
+    use_ref = want_ref and orc.ref_available()
+    o = oracle_thermal(p, algorithm="iterative" if use_ref else "pcg")
+    A = orc.Sparse14(o.mesh)
+    B = np.zeros(o.mesh.N)
+    t0 = time.perf_counter()
+    o.set_matrix(A, B)
+    t_asm = time.perf_counter() - t0
+    X = o.temperatures.copy()
+    t0 = time.perf_counter()
+    if use_ref:
+        info = A.solve_nspcg(B, X, precond="ic", accel="cg", maxit=iters, maxerr=1e-30)
+    else:
+        info = A.solve_pcg(B, X, maxit=iters, tol=1e-30)
+    t_solve = time.perf_counter() - t0
+    done = max(int(info["iters"]), 1)
+    return dict(N=o.mesh.N, iters=done, t_solve=t_solve, t_assembly=t_asm, kind="reference" if use_ref else "port",
+                value=o.mesh.N * done / t_solve,
+                sample=f"config B at {n_sample}^3 ({o.mesh.N} DOF), assembly {t_asm:.2f} s + "
+                       f"{'NSPCG cg+ic (oracle/_ref)' if use_ref else 'oracle Jacobi-PCG port'} x {done} iterations "
+                       f"in {t_solve:.2f} s, 1 thread (NSPCG is serial by construction)")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for s in range(args.warmup + args.steps):
+        r = cpu_pcg_sample(args.cpu_n, args.cpu_iters)
+        if s >= args.warmup:
+            vals.append(r)
+    t = sum(v["t_solve"] for v in vals)
+    value = sum(v["N"] * v["iters"] for v in vals) / t
+    line = {
+        "impl": "reference", "metric": "pcg_dof_iter_per_s", "value": value, "unit": "DOF*iter/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(vals), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Static3D config B (VCSEL-like, k(T)), bounded CPU sample at {args.cpu_n}^3 of the 256^3 case",
+                   "iters_per_step": vals[-1]["iters"]},
+        "cpu_baseline": {"value": value, "unit": "DOF*iter/s", "cores": 1, "kind": vals[-1]["kind"], "sample": vals[-1]["sample"]},
+        "e2e": {"value": value, "unit": "DOF*iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------- GPU arm
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from plask_b200 import _lib as L
+    from plask_b200.fem import DeviceFem
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the CUDA algorithm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.n
+    p = workload(n)
+    N = p.N
+    iters = args.iters
+    f = DeviceFem(local)
+    f.set_mesh(p.axes, p.strides)
+    f.set_materials(p.elem_mat, p.T0, p.dT, p.tab_lat, p.tab_vert)
+    f.set_field(float(p.inittemp))
+    f.set_dirichlet(p.bc_nodes, p.bc_values)
+    f.set_source(p.heat)
+    f.update_conductivity_thermal()
+    opts = dict(maxit=10 ** 9, lin_tol=1e-8, variant=args.variant)
+
+    # ---- device-resident throughput: K steps of `iters` PCG iterations
+    for _ in range(args.warmup):
+        f.bench_pcg(iters, **opts)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ms, launches = [], 0
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = f.bench_pcg(iters, **opts)
+        ms.append(r["ms"])
+        launches += r["launches"]
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if rank == 0 else None
+    t_dev = sum(ms) * 1e-3
+    if world > 1:
+        t = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev = float(t.item())
+    value = world * N * iters * args.steps / t_dev
+
+    # ---- per-kernel split (events between kernels, no graph) for the roofline of the operator kernel
+    split = f.bench_pcg(min(iters, 20), split_timing=True, **opts)
+    n_split = min(iters, 20)
+    apply_ms = split["apply_ms"] / n_split
+    update_ms = split["update_ms"] / n_split
+    peak, how = measured_peak()
+    achieved = BYTES_PER_DOF_APPLY * N / (apply_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_apply_tiled (fused p-update + 27-point brick operator + p.q)" if args.variant == 0
+                else "k_apply_simple", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": how, "traffic": None, "algorithmic_bytes_per_launch": BYTES_PER_DOF_APPLY * N,
+                "avg_launch_ms": apply_ms,
+                "update_kernel": {"achieved": BYTES_PER_DOF_APPLY * N / (update_ms * 1e-3) / 1e9, "avg_launch_ms": update_ms},
+                "iteration": {"achieved": BYTES_PER_DOF_ITER * N * iters * args.steps / (sum(ms) * 1e-3) / 1e9,
+                              "frac": BYTES_PER_DOF_ITER * N * iters * args.steps / (sum(ms) * 1e-3) / 1e9 / peak}}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get("apply_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- end to end through the public API with host buffers (pinned), H2D + D2H inside the timed region
+    heat_h, _k1 = pinned_copy(np.ascontiguousarray(p.heat))
+    x0_h, _k2 = pinned_copy(np.full(N, float(p.inittemp)))
+    out_h, _k3 = pinned_copy(np.zeros(N))
+    lib = f.lib
+    o = f.opts(maxit=iters, lin_tol=1e-30, variant=args.variant)
+    st = L.Stats()
+    import ctypes as C
+
+    def e2e_step():
+        f._ck(lib.pfem_set_source(f.ctx, heat_h.ctypes.data_as(L.c_dp)))
+        f._ck(lib.pfem_set_field(f.ctx, x0_h.ctypes.data_as(L.c_dp)))
+        f._ck(lib.pfem_set_dirichlet(f.ctx, p.bc_nodes.size, p.bc_nodes.ctypes.data_as(L._szp), p.bc_values.ctypes.data_as(L.c_dp)))
+        f._ck(lib.pfem_update_conductivity_thermal(f.ctx))
+        f._ck(lib.pfem_solve_linear(f.ctx, C.byref(o), C.byref(st)))
+        f._ck(lib.pfem_get_field(f.ctx, out_h.ctypes.data_as(L.c_dp)))
+        return st.last_iters
+
+    for _ in range(min(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_iters = 0
+    for _ in range(args.steps):
+        e2e_iters += e2e_step()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e = {"value": world * N * e2e_iters / t_e2e, "unit": "DOF*iter/s",
+           "h2d_bytes_per_step": int(heat_h.nbytes + x0_h.nbytes + p.bc_nodes.nbytes + p.bc_values.nbytes),
+           "d2h_bytes_per_step": int(out_h.nbytes), "ms_per_step": 1e3 * t_e2e / args.steps,
+           "api": "pfem_set_source + pfem_set_field + pfem_set_dirichlet + pfem_solve_linear + pfem_get_field (host buffers)"}
+
+    # ---- time to solution of the full nonlinear Static3D solve (reported, not the metric)
+    tts = None
+    if args.tts and rank == 0:
+        from plask_b200.solvers import Static3D
+        s = Static3D("bench")
+        s.problem = p
+        s.variant = args.variant
+        s.iterative.maxerr = args.lin_tol
+        s.iterative.maxit = args.tts_maxit
+        t0 = time.perf_counter()
+        try:
+            s.compute(args.tts_loops)
+            st_ = s.stats
+            tts = {"seconds": time.perf_counter() - t0, "outer_loops": st_["outer_loops"], "pcg_iterations": st_["lin_iters"],
+                   "converged": st_["converged"], "lin_relres": st_["lin_relres"], "maxT": st_["maxval"],
+                   "loop_err_K": st_["err"], "lin_tol": args.lin_tol, "includes": "H2D of all inputs + device solve"}
+        except Exception as ex:  # keep the bench line even if the long solve fails
+            tts = {"error": str(ex)}
+        s.invalidate()
+
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_baseline:
+        c = cpu_pcg_sample(args.cpu_n, args.cpu_iters)
+        cpu = {"value": c["value"], "unit": "DOF*iter/s", "cores": 1, "kind": c["kind"], "sample": c["sample"],
+               "assembly_s": c["t_assembly"]}
+
+    if rank == 0:
+        line = {
+            "metric": "pcg_dof_iter_per_s", "value": value, "unit": "DOF*iter/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"Static3D config B: {n}^3 VCSEL-like layered block, nonlinear k(T) tables, "
+                                   f"{N} DOF per GPU, Jacobi-PCG", "iters_per_step": iters,
+                       "l2": "working set >> L2 (each of the 7+7 vectors per iteration is %.0f MB)" % (N * 8 / 1e6),
+                       "order": p.order, "kernel_variant": args.variant,
+                       "multi_gpu": "independent replicas" if world > 1 else "single device"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "time_to_solution": tts, "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line))
+    f.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=256, help="nodes per axis of config B")
+    ap.add_argument("--iters", type=int, default=50, help="PCG iterations per step")
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--cpu-n", type=int, default=96)
+    ap.add_argument("--cpu-iters", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-tts", dest="tts", action="store_false")
+    ap.add_argument("--tts-loops", type=int, default=0)
+    ap.add_argument("--tts-maxit", type=int, default=200000)
+    ap.add_argument("--lin-tol", type=float, default=1e-8)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

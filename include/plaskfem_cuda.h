@@ -1,0 +1,199 @@
+/* plaskfem_cuda.h — C ABI of libplaskfem_cuda.so: the B200 (sm_100a, FP64) replacement for
+ * the hot path of PLaSK's thermal.static.Static3D and electrical.shockley.Shockley3D.
+ *
+ * What it replaces (paths relative to the PLaSK source tree):
+ *   - the pair setMatrix(A,B,...) + A.solve(B,X) inside the nonlinear do..while of
+ *     ThermalFem3DSolver::compute      solvers/thermal/static/therm3d.cpp:311-334
+ *     ElectricalFem3DSolver::compute   solvers/electrical/shockley/electr3d.cpp:383-433
+ *     i.e. element stiffness assembly (therm3d.cpp:186-276, electr3d.cpp:281-342), Dirichlet
+ *     elimination (plask/common/fem/matrix.hpp:111-118, iterative_matrix.hpp:462-485) and
+ *     the SPD solve (iterative_matrix.hpp:141-339 -> extlib/nspcg, or cholesky_matrix.hpp:90-111);
+ *   - the conductivity updates around it (therm3d.cpp:204-220, electr3d.cpp:203-225,246-274,
+ *     beta.hpp:43-46), the loop error reductions (therm3d.cpp:318-326, electr3d.cpp:387-425)
+ *     and the element post-processing (therm3d.cpp:342-384, electr3d.cpp:444-478).
+ * The solver plugin selects it with a new FemMatrixAlgorithm value (fem_solver.hpp:25-29);
+ * see INTEGRATION.md for the plugin-side binding.
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary: every call returns a pfem_status
+ *     (0 = ok, < 0 = error, > 0 = completed with a condition the caller maps to its
+ *     `noconv` policy, iterative_matrix.hpp:299-314).
+ *   - every pointer argument is HOST memory owned by the caller and is copied during the
+ *     call (DataVector<T>::data(), plask/data.hpp); the library owns all device memory
+ *     until pfem_destroy (solver onInvalidate, therm3d.cpp:118-122, electr3d.cpp:195-201).
+ *   - node arrays have N = n0*n1*n2 entries indexed exactly like RectangularMesh<3>
+ *     (plask/mesh/rectilinear3d.cpp:20-32); element arrays have E = (n0-1)(n1-1)(n2-1)
+ *     entries indexed like the element mesh of the same iteration order
+ *     (plask/mesh/rectangular3d.cpp:20-22).  Tensor2 / Vec<3> element arrays are interleaved
+ *     (c00,c11) / (c0,c1,c2) like DataVector<Tensor2<double>> / DataVector<Vec<3>>.
+ *   - all arithmetic is FP64.  Not thread-safe per context; no callbacks.
+ *   - there is NO CPU fallback: without a CUDA device pfem_create fails with
+ *     PFEM_ERR_NO_DEVICE.
+ */
+#ifndef PLASKFEM_CUDA_H
+#define PLASKFEM_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFEM_ABI_VERSION 1
+
+typedef struct pfem_ctx pfem_ctx;
+
+typedef enum {
+    PFEM_OK = 0,
+    PFEM_NOT_CONVERGED = 1,   /* linear solve hit maxit (NSPCG ier = 1, iterative_matrix.hpp:299) */
+    PFEM_ERR_CUDA = -1,       /* CUDA runtime error, text in pfem_last_error */
+    PFEM_ERR_NO_DEVICE = -2,  /* no usable CUDA device: the GPU path has no CPU fallback */
+    PFEM_ERR_BAD_INPUT = -3,  /* BadInput (plask/exceptions.hpp) */
+    PFEM_ERR_STATE = -4,      /* call order: mesh / materials / field not set */
+    PFEM_ERR_NOT_SPD = -5,    /* p.Ap <= 0: ComputationError "not positive definite" (ier -6/-7) */
+    PFEM_ERR_NOMEM = -6,
+    PFEM_ERR_NAN = -7         /* non-finite value met in the iteration */
+} pfem_status;
+
+/* ---- life cycle --------------------------------------------------------------------- */
+int pfem_abi_version(void);
+int pfem_device_count(void);                       /* 0 if no driver / no device */
+int pfem_create(pfem_ctx** ctx, int device);
+void pfem_destroy(pfem_ctx* ctx);
+const char* pfem_strerror(int status);
+const char* pfem_last_error(const pfem_ctx* ctx);  /* detail of the last failing call */
+
+/* ---- problem description (host arrays, copied) --------------------------------------- */
+
+/* Mesh: n[a], coordinates ax_a[0..n[a]-1] in um for the physical axes a = 0,1,2 (axis 2 is
+ * vertical); stride[a] = linear-index stride of axis a, i.e. the iteration order of
+ * RectilinearMesh3D (rectilinear3d.hpp:349; any of the 6 permutations).  Resets everything
+ * else in the context. */
+int pfem_set_mesh(pfem_ctx* ctx, const size_t n[3], const double* ax0, const double* ax1, const double* ax2,
+                  const size_t stride[3]);
+
+/* Material id per element + per-id conductivity tables c_lat/c_vert[nmat][nT] sampled by the
+ * host on the grid T0 + i*dT from material->thermk(T, thickness) (thermal, therm3d.cpp:213;
+ * ids distinguish (material, layer thickness) pairs, therm3d.cpp:81-114) or material->cond(T)
+ * (electrical, electr3d.cpp:221).  Interpolation is linear, clamped at both ends. */
+int pfem_set_materials(pfem_ctx* ctx, const uint32_t* elem_mat, uint32_t nmat, double T0, double dT, uint32_t nT,
+                       const double* c_lat, const double* c_vert);
+
+/* First-kind boundary conditions flattened in application order:
+ * for (cond : bconds) for (r : cond.place) (r, cond.value)  — matrix.hpp:111-118. */
+int pfem_set_dirichlet(pfem_ctx* ctx, size_t nd, const size_t* node, const double* value);
+
+/* Volumetric heat source per element, W/m^3 (inHeat(elementMesh), therm3d.cpp:179,223);
+ * NULL = zero load vector (electrical, electr3d.cpp:278). */
+int pfem_set_source(pfem_ctx* ctx, const double* heat_per_elem);
+
+/* Unknown field (temperatures [K] / potential [V]): initial guess and warm start
+ * (therm3d.cpp:79, electr3d.cpp:190; iterative_matrix.hpp:205-209). */
+int pfem_set_field(pfem_ctx* ctx, const double* x0);
+int pfem_fill_field(pfem_ctx* ctx, double value);
+
+/* Temperature at element midpoints for sigma(T) (inTemperature(elementMesh), electr3d.cpp:204-205);
+ * NULL = uniform `uniform_T`. */
+int pfem_set_elem_temperature(pfem_ctx* ctx, const double* T_elem, double uniform_T);
+
+/* One p-n junction, ElectricalFem3DSolver::Active (electr3d.hpp:28-78) after
+ * setupActiveRegions (electr3d.cpp:89-183): node-plane indices bottom/top along axis 2,
+ * element index ranges [left,right) along axis 1 and [back,front) along axis 0,
+ * ld = front-back, offset into the junction table, height in um. */
+typedef struct {
+    size_t bottom, top, left, right, back, front, ld;
+    ptrdiff_t offset;
+    double height;
+} pfem_junction;
+
+/* Shockley description.  elem_junc[E]: 0 = not a junction, k+1 = junction k (isActive,
+ * electr3d.hpp:148-171).  elem_role[E]: 0 none, 1 p-contact, 2 n-contact (electr3d.cpp:216-219),
+ * may be NULL.  junc_cond[ncol][2]: junction_conductivity table (electr3d.hpp:87), ncol =
+ * sum over junctions of (right-left)*(front-back).  beta_col/js_col[ncol]: Shockley
+ * parameters per table entry; the host evaluates beta(T), js(T) (beta.hpp:50-77,
+ * electr_python.cpp:67-110) at the mid-plane element temperature (electr3d.cpp:261-262).
+ * stable != 0 selects CONVERGENCE_STABLE (electr3d.cpp:263-268). */
+int pfem_set_junctions(pfem_ctx* ctx, uint32_t njunc, const pfem_junction* junc, const uint32_t* elem_junc,
+                       const uint8_t* elem_role, double pcond, double ncond, size_t ncol, const double* junc_cond,
+                       const double* beta_col, const double* js_col, int stable);
+
+/* ---- solve --------------------------------------------------------------------------- */
+
+typedef struct {
+    int maxit;        /* max PCG iterations per linear solve (iter_params.maxit)            */
+    double lin_tol;   /* stop when ||r||2 <= lin_tol*||b||2 AND ||r||_D^-1 <= lin_tol*||b||_D^-1 (b = free rows of the rhs) */
+    int precond;      /* 0 = Jacobi (NSPCG "jac"), 1 = line-Jacobi along the vertical axis  */
+    double outer_tol; /* maxerr of the nonlinear loop: K (thermal) or % (electrical)        */
+    int loops;        /* max nonlinear loops in this call, 0 = until converged              */
+    int batch;        /* PCG iterations per captured CUDA graph launch (0 = default)        */
+    int variant;      /* 0 = production kernels, 1 = simple reference kernels (tests)       */
+    int reserved[5];
+} pfem_opts;
+
+typedef struct {
+    int outer_loops;         /* loops done in this call                                     */
+    int loopno;              /* loops done since the last pfem_set_mesh (solver loopno)     */
+    long long lin_iters;     /* PCG iterations summed over the call                         */
+    int last_iters;          /* ... of the last linear solve (iter_params.iters)            */
+    int converged;           /* last linear solve converged (iter_params.converged)         */
+    double lin_relres;       /* ||r||2/||b_free||2 at exit of the last solve (iter_params.err) */
+    double err;              /* last loop error (K or %)                                    */
+    double toterr;           /* max loop error in this call (the value compute() returns)   */
+    double maxval;           /* max T (thermal) / max |j| at the junction, kA/cm2           */
+    double maxcur[3];        /* current density vector where |j| is largest (electr3d.hpp:184) */
+    double t_solve_ms;       /* device time of the call, CUDA events                        */
+    long long kernel_launches; /* kernels of this library launched during the call          */
+    double lin_relres_precond; /* sqrt(r.D^-1 r / b.D^-1 b) at exit of the last solve          */
+    double reserved[3];
+} pfem_stats;
+
+void pfem_default_opts(pfem_opts* opts);
+
+/* The whole nonlinear loop of ThermalFem3DSolver::compute (therm3d.cpp:311-334) on the device. */
+int pfem_solve_thermal(pfem_ctx* ctx, const pfem_opts* opts, pfem_stats* stats);
+/* The whole nonlinear loop of ElectricalFem3DSolver::compute (electr3d.cpp:378-435),
+ * including loadConductivity before and saveConductivity after it. */
+int pfem_solve_shockley(pfem_ctx* ctx, const pfem_opts* opts, pfem_stats* stats);
+
+/* ---- results ------------------------------------------------------------------------- */
+int pfem_get_field(pfem_ctx* ctx, double* x);  /* temperatures / potential, N doubles */
+
+typedef enum {
+    PFEM_ELEM_COND = 0,     /* conds, E x (c00,c11)  [W/m/K or S/m]                          */
+    PFEM_ELEM_CURRENT = 1,  /* current, E x 3 [kA/cm2]            (electr3d.cpp:399-411)     */
+    PFEM_ELEM_HEAT = 2,     /* Joule heat, E [W/m3]               (electr3d.cpp:444-478)     */
+    PFEM_ELEM_FLUX = 3      /* heat flux, E x 3 [W/m2]            (therm3d.cpp:342-384)      */
+} pfem_elem_field;
+/* noheat[E] (may be NULL): elements with EMPTY material or the "noheat" role get zero heat
+ * (electr3d.cpp:472); only read for PFEM_ELEM_HEAT. */
+int pfem_get_elem(pfem_ctx* ctx, int what, const uint8_t* noheat, double* out);
+int pfem_get_junction_cond(pfem_ctx* ctx, double* junc_cond /* [ncol][2] */);
+
+/* ---- building blocks exposed for parity tests and the benchmark ---------------------- */
+/* conds from the current field (thermal, therm3d.cpp:204-213) */
+int pfem_update_conductivity_thermal(pfem_ctx* ctx);
+/* conds from T_elem / junction table / contacts (loadConductivity, electr3d.cpp:203-225) */
+int pfem_update_conductivity_shockley(pfem_ctx* ctx);
+/* conds given directly, E x (c00,c11) */
+int pfem_set_conductivity(pfem_ctx* ctx, const double* cond);
+/* q = A p with A the Dirichlet-eliminated stiffness matrix of the current conds
+ * (== SparseBandMatrix::mult after applyBC, iterative_matrix.hpp:420-433,462-485) */
+int pfem_apply(pfem_ctx* ctx, const double* p, double* q, int variant);
+/* load vector after applyBC (B of therm3d.cpp:278 / electr3d.cpp:344) */
+int pfem_get_rhs(pfem_ctx* ctx, double* b);
+/* diagonal of the eliminated matrix (1 on Dirichlet rows) */
+int pfem_get_diag(pfem_ctx* ctx, double* d);
+/* one linear solve from the current field with the current conds */
+int pfem_solve_linear(pfem_ctx* ctx, const pfem_opts* opts, pfem_stats* stats);
+/* exactly `iters` PCG iterations (no convergence exit) from the current state, device
+ * resident, timed with CUDA events on the launching stream; *ms = elapsed, *apply_ms /
+ * *update_ms = summed duration of the operator kernel / the vector-update kernel when
+ * split_timing != 0 (adds event records between kernels). */
+int pfem_bench_pcg(pfem_ctx* ctx, const pfem_opts* opts, int iters, int split_timing, double* ms, double* apply_ms,
+                   double* update_ms, long long* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLASKFEM_CUDA_H */

@@ -1,0 +1,462 @@
+"""CPU oracle for the PLaSK Static3D / Shockley3D hot path — TEST INFRASTRUCTURE ONLY.
+
+Nothing under ``plask_b200/`` may import this module.  Only ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
+``bench.py`` use it, and only as the checker / the CPU arm.
+
+It drives ``liboracle.so`` (``fem3d_oracle.c``, our C restatement of the reference loops)
+and, when present, ``_ref/libnspcg_ref.so`` — the reference's own vendored NSPCG compiled
+from ``/root/reference/extlib/nspcg/nspcg.c`` — plus LAPACK ``dpbtrf/dpbtrs`` from the
+OpenBLAS that ships inside scipy (the reference links an external LAPACK,
+``plask/common/fem/cholesky_matrix.hpp:24-50``).
+
+The outer loops below follow, statement by statement,
+``solvers/thermal/static/therm3d.cpp:281-340`` and
+``solvers/electrical/shockley/electr3d.cpp:356-442``.
+"""
+import ctypes as C
+import os
+import subprocess
+import time
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+c_sz = C.c_size_t
+c_dp = C.POINTER(C.c_double)
+
+
+def build(ref=True, quiet=True):
+    """Compile liboracle.so and, if /root/reference exists, _ref/libnspcg_ref.so."""
+    out = subprocess.DEVNULL if quiet else None
+    subprocess.check_call(["make", "-C", _HERE], stdout=out)
+    if ref and os.path.isdir("/root/reference/extlib/nspcg"):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=out)
+
+
+class _Mesh(C.Structure):
+    _fields_ = [("n", c_sz * 3), ("ax", c_dp * 3), ("ns", c_sz * 3), ("es", c_sz * 3)]
+
+
+class _Active(C.Structure):
+    _fields_ = [("bottom", c_sz), ("top", c_sz), ("left", c_sz), ("right", c_sz), ("back", c_sz), ("front", c_sz),
+                ("ld", c_sz), ("offset", C.c_ssize_t), ("height", C.c_double)]
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        _lib = C.CDLL(path)
+        _lib.orc_table_at.restype = C.c_double
+        _lib.orc_shockley_currents.restype = C.c_double
+        _lib.orc_integrate_current.restype = C.c_double
+        _lib.orc_total_heat.restype = C.c_double
+        _lib.orc_total_energy.restype = C.c_double
+        _lib.orc_mesh_nodes.restype = c_sz
+        _lib.orc_mesh_elements.restype = c_sz
+    return _lib
+
+
+def ref_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libnspcg_ref.so"))
+
+
+def ref():
+    """The reference's own NSPCG (None if oracle/_ref was not built)."""
+    global _ref
+    if _ref is None and ref_available():
+        _ref = C.CDLL(os.path.join(_HERE, "_ref", "libnspcg_ref.so"))
+        _ref.ref_nspcg_new.restype = C.c_void_p
+        _ref.ref_nspcg_free.argtypes = [C.c_void_p]
+    return _ref
+
+
+def _p(a, t=C.c_double):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+ORDERS = {"012": (0, 1, 2), "021": (0, 2, 1), "102": (1, 0, 2), "120": (1, 2, 0), "201": (2, 0, 1), "210": (2, 1, 0)}
+
+
+def optimal_order(n):
+    """RectilinearMesh3D::setOptimalIterationOrder, plask/mesh/rectilinear3d.cpp:74-85."""
+    for name in ("012", "021", "102", "120", "201", "210"):
+        f, s, t = ORDERS[name]
+        if n[t] <= n[s] <= n[f]:
+            return name
+    return "210"
+
+
+class Mesh:
+    """RectangularMesh<3> (plask/mesh/rectilinear3d.hpp): three coordinate axes [um] and an
+    iteration order 'major medium minor' (:349)."""
+
+    def __init__(self, ax0, ax1, ax2, order="012"):
+        self.axes = [np.ascontiguousarray(a, dtype=np.float64) for a in (ax0, ax1, ax2)]
+        self.n = tuple(len(a) for a in self.axes)
+        if order == "optimal":
+            order = optimal_order(self.n)
+        self.order = order
+        self.c = _Mesh()
+        o = (C.c_int * 3)(*ORDERS[order])
+        lib().orc_mesh_init(C.byref(self.c), c_sz(self.n[0]), c_sz(self.n[1]), c_sz(self.n[2]), _p(self.axes[0]),
+                            _p(self.axes[1]), _p(self.axes[2]), o)
+        self.N = self.n[0] * self.n[1] * self.n[2]
+        self.E = (self.n[0] - 1) * (self.n[1] - 1) * (self.n[2] - 1)
+        self.ns = tuple(self.c.ns)
+        self.es = tuple(self.c.es)
+        s = sorted(self.ns)
+        self.minor, self.major = s[1], s[2]
+        self.icords = np.zeros(14, dtype=np.int32)
+        lib().orc_sparse14_offsets(c_sz(self.major), c_sz(self.minor), _p(self.icords, C.c_int))
+
+    @property
+    def ref(self):
+        return C.byref(self.c)
+
+    def node(self, i0, i1, i2):
+        return i0 * self.ns[0] + i1 * self.ns[1] + i2 * self.ns[2]
+
+    def nodes_grid(self):
+        """node index array of shape (n0,n1,n2)"""
+        i0, i1, i2 = np.meshgrid(*[np.arange(k) for k in self.n], indexing="ij")
+        return i0 * self.ns[0] + i1 * self.ns[1] + i2 * self.ns[2]
+
+    def elems_grid(self):
+        i0, i1, i2 = np.meshgrid(*[np.arange(k - 1) for k in self.n], indexing="ij")
+        return i0 * self.es[0] + i1 * self.es[1] + i2 * self.es[2]
+
+
+class Tables:
+    """Per-material-id conductivity tables on a uniform T grid (sampled by the host from
+    material->thermk / material->cond)."""
+
+    def __init__(self, T0, dT, lat, vert):
+        self.T0, self.dT = float(T0), float(dT)
+        self.lat = np.ascontiguousarray(lat, dtype=np.float64)
+        self.vert = np.ascontiguousarray(vert, dtype=np.float64)
+        assert self.lat.shape == self.vert.shape and self.lat.ndim == 2
+        self.nmat, self.nT = self.lat.shape
+
+
+def thickness(mesh, elem_mat):
+    out = np.empty(mesh.E)
+    lib().orc_thickness(mesh.ref, _p(elem_mat, C.c_uint32), _p(out))
+    return out
+
+
+# ----------------------------------------------------------------------------- matrices
+
+
+class Sparse14:
+    """SparseBandMatrix, plask/common/fem/iterative_matrix.hpp:347-486."""
+
+    def __init__(self, mesh):
+        self.mesh = mesh
+        self.data = np.zeros(14 * mesh.N)
+        self.state = None
+
+    def assemble(self, cond, heat, B):
+        rc = lib().orc_assemble_sparse14(self.mesh.ref, _p(cond), _p(heat) if heat is not None else None,
+                                         _p(self.data), _p(B))
+        assert rc == 0
+
+    def apply_bc(self, B, nodes, values):
+        lib().orc_apply_bc_sparse14(c_sz(self.mesh.N), _p(self.mesh.icords, C.c_int), _p(self.data), _p(B),
+                                    c_sz(len(nodes)), _p(nodes, c_sz), _p(values))
+
+    def mult(self, x):
+        y = np.zeros(self.mesh.N)
+        lib().orc_addmult_sparse14(c_sz(self.mesh.N), _p(self.mesh.icords, C.c_int), _p(self.data), _p(x), _p(y))
+        return y
+
+    def solve_nspcg(self, B, X, precond="ic", accel="cg", maxit=1000, maxerr=1e-6, nfact=10):
+        """SparseMatrix::solverhs, iterative_matrix.hpp:141-339, through the reference's NSPCG."""
+        r = ref()
+        if r is None:
+            raise RuntimeError("oracle/_ref/libnspcg_ref.so not built (needs /root/reference)")
+        if self.state is None:
+            self.state = C.c_void_p(r.ref_nspcg_new())
+        pre = ["rich", "jac", "ljac", "ljacx", "sor", "ssor", "ic", "mic", "lsp", "neu", "lsor", "lssor", "llsp",
+               "lneu", "bic", "bicx", "mbic", "mbicx"].index(precond)
+        acc = ["cg", "si", "sor", "srcg", "srsi"].index(accel)
+        iters, err = C.c_int(0), C.c_double(0)
+        tf, tt = C.c_double(0), C.c_double(0)
+        rhs = B.copy()
+        ier = r.ref_nspcg_solve(self.state, pre, acc, C.c_int(self.mesh.N), C.c_int(self.mesh.major),
+                                C.c_int(self.mesh.minor), _p(self.data), _p(self.mesh.icords, C.c_int), _p(X),
+                                _p(rhs), C.c_int(maxit), C.c_double(maxerr), C.c_int(nfact), C.byref(iters),
+                                C.byref(err), C.byref(tf), C.byref(tt))
+        # ier == -7 with a vanishing residual is exact convergence (SURVEY.md §8c gotcha)
+        if ier < 0 and ier != -7:
+            raise RuntimeError(f"NSPCG error ier={ier}")
+        return dict(ier=ier, converged=(ier != 1), iters=iters.value, err=err.value)
+
+    def solve_pcg(self, B, X, maxit=100000, tol=1e-10):
+        relres = C.c_double(0)
+        it = lib().orc_pcg_jacobi_sparse14(c_sz(self.mesh.N), _p(self.mesh.icords, C.c_int), _p(self.data), _p(B),
+                                           _p(X), C.c_int(maxit), C.c_double(tol), C.byref(relres))
+        return dict(ier=0 if it >= 0 else it, converged=(it >= 0 and relres.value <= tol * 1.01), iters=it, err=relres.value)
+
+    def __del__(self):
+        if self.state is not None and ref() is not None:
+            ref().ref_nspcg_free(self.state)
+
+
+class Dpb:
+    """DpbMatrix, plask/common/fem/cholesky_matrix.hpp:58-120 (LAPACK lower band storage)."""
+
+    def __init__(self, mesh):
+        self.mesh = mesh
+        kd, ld = c_sz(0), c_sz(0)
+        lib().orc_dpb_dims(mesh.ref, C.byref(kd), C.byref(ld))
+        self.kd, self.ld = kd.value, ld.value
+        self.data = np.zeros((mesh.N, self.ld + 1))
+
+    def assemble(self, cond, heat, B):
+        lib().orc_assemble_dpb(self.mesh.ref, _p(cond), _p(heat) if heat is not None else None, c_sz(self.ld),
+                               _p(self.data), _p(B))
+
+    def apply_bc(self, B, nodes, values):
+        lib().orc_apply_bc_dpb(c_sz(self.mesh.N), c_sz(self.kd), c_sz(self.ld), _p(self.data), _p(B),
+                               c_sz(len(nodes)), _p(nodes, c_sz), _p(values))
+
+    def solve(self, B, X, threads=None):
+        """factorize() + solverhs(): dpbtrf('L') + dpbtrs, cholesky_matrix.hpp:90-111."""
+        from scipy.linalg import lapack
+        ab = self.data.T  # Fortran-ordered (ld+1, N) view, no copy
+        c, info = lapack.dpbtrf(ab, lower=1, overwrite_ab=1)
+        if info > 0:
+            raise RuntimeError(f"leading minor of order {info} of the stiffness matrix is not positive-definite")
+        assert info == 0
+        x, info = lapack.dpbtrs(c, B, lower=1)
+        assert info == 0
+        X[:] = x
+        return dict(ier=0, converged=True, iters=0, err=0.)
+
+
+# ------------------------------------------------------------------------- Static3D
+
+
+class Static3DOracle:
+    """ThermalFem3DSolver restated (solvers/thermal/static/therm3d.cpp)."""
+
+    def __init__(self, mesh, elem_mat, tables, dirichlet_nodes, dirichlet_values, heat=None, inittemp=300.,
+                 maxerr=0.05, algorithm="cholesky", precond="ic", itmaxerr=1e-6, maxit=1000, nfact=10):
+        self.mesh = mesh
+        self.elem_mat = np.ascontiguousarray(elem_mat, dtype=np.uint32)
+        self.tables = tables
+        self.bc_nodes = np.ascontiguousarray(dirichlet_nodes, dtype=np.uintp)
+        self.bc_values = np.ascontiguousarray(dirichlet_values, dtype=np.float64)
+        self.heat = None if heat is None else np.ascontiguousarray(heat, dtype=np.float64)
+        self.inittemp, self.maxerr = inittemp, maxerr
+        self.algorithm, self.precond, self.itmaxerr, self.maxit, self.nfact = algorithm, precond, itmaxerr, maxit, nfact
+        self.temperatures = np.full(mesh.N, float(inittemp))  # onInitialize, therm3d.cpp:79
+        self.loopno = 0
+        self.converged = True
+        self.history = []
+        self.timing = dict(assembly=0., solve=0.)
+        self.conds = np.zeros((mesh.E, 2))
+        self._A = None
+
+    def _matrix(self):
+        if self._A is None:
+            self._A = Dpb(self.mesh) if self.algorithm == "cholesky" else Sparse14(self.mesh)
+        return self._A
+
+    def set_matrix(self, A, B):
+        """setMatrix, therm3d.cpp:170-279 (Dirichlet + volumetric heat only)."""
+        t = self.tables
+        lib().orc_thermal_conds(self.mesh.ref, _p(self.temperatures), _p(self.elem_mat, C.c_uint32),
+                                C.c_uint32(t.nT), C.c_double(t.T0), C.c_double(t.dT), _p(t.lat), _p(t.vert),
+                                _p(self.conds))
+        A.assemble(self.conds, self.heat if self.heat is not None else np.zeros(self.mesh.E), B)
+        A.apply_bc(B, self.bc_nodes, self.bc_values)
+
+    def compute(self, loops=0):
+        """compute, therm3d.cpp:281-340."""
+        A = self._matrix()
+        loop, toterr = 0, 0.
+        B = np.zeros(self.mesh.N)
+        while True:
+            temp0 = self.temperatures.copy()
+            t0 = time.perf_counter()
+            self.set_matrix(A, B)
+            t1 = time.perf_counter()
+            if self.algorithm == "cholesky":
+                info = A.solve(B, self.temperatures)
+            elif self.algorithm == "iterative":
+                info = A.solve_nspcg(B, self.temperatures, precond=self.precond, maxit=self.maxit,
+                                     maxerr=self.itmaxerr, nfact=self.nfact)
+            else:  # 'pcg': oracle's own Jacobi-PCG with a true-residual test
+                info = A.solve_pcg(B, self.temperatures, maxit=self.maxit, tol=self.itmaxerr)
+            t2 = time.perf_counter()
+            self.timing["assembly"] += t1 - t0
+            self.timing["solve"] += t2 - t1
+            self.converged = info["converged"]
+            err, maxT = C.c_double(0), C.c_double(0)
+            lib().orc_thermal_error(c_sz(self.mesh.N), _p(self.temperatures), _p(temp0), C.byref(err), C.byref(maxT))
+            err, self.maxT = err.value, maxT.value
+            toterr = max(toterr, err)
+            self.loopno += 1
+            loop += 1
+            self.history.append(dict(loop=loop, maxT=self.maxT, err=err, iters=info["iters"], lin_err=info["err"]))
+            if not ((not self.converged or err > self.maxerr) and (loops == 0 or loop < loops)):
+                break
+        return toterr
+
+    def heat_fluxes(self):
+        flux = np.zeros((self.mesh.E, 3))
+        lib().orc_heat_flux(self.mesh.ref, _p(self.temperatures), _p(self.conds), _p(flux))
+        return flux
+
+
+# ------------------------------------------------------------------------- Shockley3D
+
+
+class Shockley3DOracle:
+    """ElectricalFem3DSolver + BetaSolver<Geometry3D> restated
+    (solvers/electrical/shockley/electr3d.cpp, beta.hpp)."""
+
+    def __init__(self, mesh, elem_mat, tables, dirichlet_nodes, dirichlet_values, elem_junc=None, elem_role=None,
+                 beta=None, js=None, pcond=5., ncond=50., start_cond=(0., 5.), maxerr=0.05, convergence="fast",
+                 algorithm="cholesky", precond="ic", itmaxerr=1e-6, maxit=1000, nfact=10, noheat=None, eps=None):
+        self.mesh = mesh
+        E = mesh.E
+        self.elem_mat = np.ascontiguousarray(elem_mat, dtype=np.uint32)
+        self.tables = tables
+        self.bc_nodes = np.ascontiguousarray(dirichlet_nodes, dtype=np.uintp)
+        self.bc_values = np.ascontiguousarray(dirichlet_values, dtype=np.float64)
+        self.elem_junc = np.zeros(E, dtype=np.uint32) if elem_junc is None else np.ascontiguousarray(elem_junc, dtype=np.uint32)
+        self.elem_role = np.zeros(E, dtype=np.uint8) if elem_role is None else np.ascontiguousarray(elem_role, dtype=np.uint8)
+        self.noheat = None if noheat is None else np.ascontiguousarray(noheat, dtype=np.uint8)
+        self.eps = None if eps is None else np.ascontiguousarray(eps, dtype=np.float64)
+        self.pcond, self.ncond, self.maxerr = pcond, ncond, maxerr
+        self.stable = 1 if convergence == "stable" else 0
+        self.algorithm, self.precond, self.itmaxerr, self.maxit, self.nfact = algorithm, precond, itmaxerr, maxit, nfact
+        # setupActiveRegions, electr3d.cpp:89-183
+        max_act = int(self.elem_junc.max()) if E else 0
+        self.active = (_Active * max(max_act, 1))()
+        condsize = c_sz(0)
+        self.nact = lib().orc_setup_active(mesh.ref, _p(self.elem_junc, C.c_uint32), self.active, C.c_int(max_act),
+                                           C.byref(condsize))
+        if self.nact < 0:
+            raise ValueError("junction does not have top and bottom edges at constant heights")
+        self.junction_conductivity = np.tile(np.asarray(start_cond, dtype=np.float64), (max(condsize.value, 1), 1))
+        self.beta, self.js = beta, js  # per junction: float or callable(T)
+        # onInitialize, electr3d.cpp:185-193
+        self.potential = np.zeros(mesh.N)
+        self.current = np.zeros((E, 3))
+        self.conds = np.zeros((E, 2))
+        self.heat = None
+        self.loopno = 0
+        self.converged = True
+        self.history = []
+        self.maxcur = np.zeros(3)
+        self.Te = np.full(E, 300.)  # inTemperature default
+        self._A = None
+
+    def _matrix(self):
+        if self._A is None:
+            self._A = Dpb(self.mesh) if self.algorithm == "cholesky" else Sparse14(self.mesh)
+        return self._A
+
+    def _junction_params(self):
+        """beta/js per junction-table entry, evaluated at the mid-plane element temperature
+        (temperature[tidx], electr3d.cpp:261-262; python callables electr_python.cpp:103-110)."""
+        n = len(self.junction_conductivity)
+        bcol, jcol = np.ones(n), np.ones(n)
+        for k in range(self.nact):
+            a = self.active[k]
+            v = (a.top + a.bottom) // 2
+            b = self.beta[k] if isinstance(self.beta, (list, tuple)) else self.beta
+            j = self.js[k] if isinstance(self.js, (list, tuple)) else self.js
+            for t in range(a.left, a.right):
+                for l in range(a.back, a.front):
+                    T = self.Te[l * self.mesh.es[0] + t * self.mesh.es[1] + v * self.mesh.es[2]]
+                    col = a.offset + a.ld * t + l
+                    bcol[col] = b(T) if callable(b) else b
+                    jcol[col] = j(T) if callable(j) else j
+        return bcol, jcol
+
+    def load_conductivity(self):
+        t = self.tables
+        lib().orc_shockley_load_conds(self.mesh.ref, _p(self.elem_mat, C.c_uint32), _p(self.elem_junc, C.c_uint32),
+                                      _p(self.elem_role, C.c_uint8), _p(self.Te), C.c_uint32(t.nT), C.c_double(t.T0),
+                                      C.c_double(t.dT), _p(t.lat), _p(t.vert), self.active,
+                                      _p(self.junction_conductivity), C.c_double(self.pcond), C.c_double(self.ncond),
+                                      _p(self.conds))
+
+    def compute(self, loops=0):
+        """compute, electr3d.cpp:356-442."""
+        A = self._matrix()
+        loop, toterr = 0, 0.
+        rhs = np.zeros(self.mesh.N)
+        self.load_conductivity()
+        bcol, jcol = self._junction_params()
+        noactive = 1 if self.nact == 0 else 0
+        minj = 100e-7
+        self.heat = None
+        while True:
+            # setMatrix, electr3d.cpp:239-354
+            if self.loopno != 0:
+                lib().orc_shockley_junction_update(self.mesh.ref, _p(self.elem_junc, C.c_uint32), self.active,
+                                                   _p(self.potential), _p(bcol), _p(jcol), C.c_int(self.stable),
+                                                   _p(self.conds))
+            A.assemble(self.conds, None, rhs)
+            A.apply_bc(rhs, self.bc_nodes, self.bc_values)
+            if self.algorithm == "cholesky":
+                info = A.solve(rhs, self.potential)
+            elif self.algorithm == "iterative":
+                info = A.solve_nspcg(rhs, self.potential, precond=self.precond, maxit=self.maxit,
+                                     maxerr=self.itmaxerr, nfact=self.nfact)
+            else:
+                info = A.solve_pcg(rhs, self.potential, maxit=self.maxit, tol=self.itmaxerr)
+            self.converged = info["converged"]
+            mcur = C.c_double(0)
+            err = lib().orc_shockley_currents(self.mesh.ref, _p(self.elem_junc, C.c_uint32), C.c_int(noactive),
+                                              _p(self.potential), _p(self.conds), _p(self.current), C.byref(mcur),
+                                              _p(self.maxcur))
+            if (loop != 0 or mcur.value >= minj) and err > toterr:
+                toterr = err
+            self.loopno += 1
+            loop += 1
+            self.history.append(dict(loop=loop, mcur=mcur.value, err=err, iters=info["iters"]))
+            if not ((not self.converged or err > self.maxerr) and (loops == 0 or loop < loops)):
+                break
+        lib().orc_shockley_save_conds(self.mesh.ref, self.active, C.c_int(self.nact), _p(self.conds),
+                                      _p(self.junction_conductivity))
+        return toterr
+
+    def heat_density(self):
+        if self.heat is None:
+            self.heat = np.zeros(self.mesh.E)
+            lib().orc_shockley_heat(self.mesh.ref, _p(self.potential), _p(self.conds),
+                                    _p(self.noheat, C.c_uint8) if self.noheat is not None else None, _p(self.heat))
+        return self.heat
+
+    def get_total_current(self, nact=0):
+        a = self.active[nact]
+        level = (a.bottom + a.top) // 2
+        return lib().orc_integrate_current(self.mesh.ref, _p(self.elem_junc, C.c_uint32), _p(self.current),
+                                           c_sz(level), C.c_int(1))
+
+    def get_total_heat(self):
+        return lib().orc_total_heat(self.mesh.ref, _p(self.heat_density()))
+
+    def get_total_energy(self):
+        return lib().orc_total_energy(self.mesh.ref, _p(self.potential), _p(self.eps))
+
+    def get_capacitance(self):
+        """getCapacitance, electr3d.cpp:602-610 (exactly two voltage conditions)."""
+        vals = np.unique(self.bc_values)
+        assert len(vals) == 2
+        U = vals[1] - vals[0]
+        return 2e12 * self.get_total_energy() / (U * U)

@@ -1,0 +1,338 @@
+"""Synthetic problem configurations of BASELINE.json, as flat arrays.
+
+A `Problem` is exactly what the solver plugin would hand to the C ABI: axis coordinates, the
+iteration order (strides), a material id per element, conductivity tables, Dirichlet nodes,
+heat per element and (Shockley) the junction description.  Everything is deterministic; the
+randomised variants use numpy.random.default_rng(20261017).
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import materials as M
+
+ORDERS = {"012": (0, 1, 2), "021": (0, 2, 1), "102": (1, 0, 2), "120": (1, 2, 0), "201": (2, 0, 1), "210": (2, 1, 0)}
+
+
+def optimal_order(n):
+    """RectilinearMesh3D::setOptimalIterationOrder (plask/mesh/rectilinear3d.cpp:74-85)."""
+    for name in ("012", "021", "102", "120", "201", "210"):
+        f, s, t = ORDERS[name]
+        if n[t] <= n[s] <= n[f]:
+            return name
+    return "210"
+
+
+def strides_for(n, order):
+    """node and element strides of the physical axes for ORDER_<major><medium><minor>
+    (rectilinear3d.cpp:20-32; the element mesh keeps the order, rectangular3d.cpp:20-22)."""
+    mj, md, mn = ORDERS[order]
+    ns, es = [0, 0, 0], [0, 0, 0]
+    ns[mn], ns[md], ns[mj] = 1, n[mn], n[mn] * n[md]
+    es[mn], es[md], es[mj] = 1, n[mn] - 1, (n[mn] - 1) * (n[md] - 1)
+    return tuple(ns), tuple(es)
+
+
+@dataclass
+class Problem:
+    name: str
+    kind: str                      # 'thermal' | 'shockley'
+    axes: list
+    order: str
+    elem_mat: np.ndarray           # uint32 [E], reference element order
+    T0: float
+    dT: float
+    tab_lat: np.ndarray            # [nmat][nT]
+    tab_vert: np.ndarray
+    bc_nodes: np.ndarray           # uintp
+    bc_values: np.ndarray
+    heat: np.ndarray = None        # [E] W/m3 (thermal)
+    inittemp: float = 300.
+    maxerr: float = 0.05
+    # Shockley only
+    elem_junc: np.ndarray = None   # uint32 [E], 0 = none, k+1 = junction k
+    elem_role: np.ndarray = None   # uint8 [E]: 1 p-contact, 2 n-contact
+    noheat: np.ndarray = None      # uint8 [E]
+    beta: float = 11.
+    js: float = 1.
+    pcond: float = 5.
+    ncond: float = 50.
+    start_cond: tuple = (0., 5.)
+    Te: float = 300.
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def n(self):
+        return tuple(len(a) for a in self.axes)
+
+    @property
+    def N(self):
+        n = self.n
+        return n[0] * n[1] * n[2]
+
+    @property
+    def E(self):
+        n = self.n
+        return (n[0] - 1) * (n[1] - 1) * (n[2] - 1)
+
+    @property
+    def strides(self):
+        return strides_for(self.n, self.order)[0]
+
+    @property
+    def estrides(self):
+        return strides_for(self.n, self.order)[1]
+
+    def elem_index_grid(self):
+        n, es = self.n, self.estrides
+        i0, i1, i2 = np.meshgrid(*[np.arange(k - 1) for k in n], indexing="ij", sparse=True)
+        return i0 * es[0] + i1 * es[1] + i2 * es[2]
+
+    def node_index_grid(self):
+        n, ns = self.n, self.strides
+        i0, i1, i2 = np.meshgrid(*[np.arange(k) for k in n], indexing="ij", sparse=True)
+        return i0 * ns[0] + i1 * ns[1] + i2 * ns[2]
+
+    def to_elem_order(self, grid3d, dtype=None):
+        """(n0-1,n1-1,n2-1) array -> flat array in the reference element order"""
+        out = np.empty(self.E, dtype=dtype or grid3d.dtype)
+        out[self.elem_index_grid().ravel()] = np.broadcast_to(grid3d, tuple(k - 1 for k in self.n)).ravel()
+        return out
+
+
+# ------------------------------------------------------------------------------ helpers
+
+def graded_axis(n, hmin, hmax):
+    """n nodes, symmetric about 0, element sizes growing geometrically from hmin at the centre
+    to hmax at the edge (adjacent ratio constant, like DivideGenerator's `gradual` meshes)."""
+    ne = n - 1
+    half = ne // 2
+    r = (hmax / hmin) ** (1. / max(half - 1, 1))
+    side = hmin * r ** np.arange(half)
+    if ne % 2:
+        h = np.concatenate([side[::-1], [hmin], side])
+    else:
+        h = np.concatenate([side[::-1], side])
+    x = np.concatenate([[0.], np.cumsum(h)])
+    return x - 0.5 * x[-1]
+
+
+def graded_run(total, n, first):
+    """n element sizes summing to `total`, growing geometrically from about `first`."""
+    if n == 1:
+        return np.array([total])
+    lo, hi = 1.0, 50.0
+    for _ in range(200):
+        r = 0.5 * (lo + hi)
+        s = first * (r ** n - 1) / (r - 1) if abs(r - 1) > 1e-12 else first * n
+        if s < total:
+            lo = r
+        else:
+            hi = r
+    h = first * r ** np.arange(n)
+    return h * (total / h.sum())
+
+
+D_GAAS, D_ALGAAS = 0.0700, 0.0795   # DBR layer thicknesses, solvers/meta/shockley/tests/thermoelectric.xpl:26-30
+
+# material ids shared by the configurations
+GAAS, ALGAAS, QW, ALOX, AU, CU, AIR, NDBR_A, NDBR_B, PDBR_A, PDBR_B, NSUB = range(12)
+
+
+def thermal_tables(T0=250., dT=0.25, nT=1601):
+    models = [M.thermk_GaAs, lambda T: M.thermk_AlGaAs(T, 0.73), M.thermk_GaAs, M.thermk_AlOx, M.thermk_Au,
+              M.thermk_Cu, M.thermk_air,
+              M.thermk_GaAs, lambda T: M.thermk_AlGaAs(T, 0.73), M.thermk_GaAs, lambda T: M.thermk_AlGaAs(T, 0.73),
+              M.thermk_GaAs]
+    return M.sample_tables(models, T0, dT, nT)
+
+
+def electrical_tables(T0=250., dT=0.25, nT=1601):
+    models = [M.cond_GaAs, M.cond_GaAs, M.cond_GaAs, M.cond_AlOx, M.cond_Au, M.cond_Cu, M.cond_air,
+              lambda T: M.cond_doped(T, 2e18, 2000., 1.4),    # n-GaAs:Si
+              lambda T: M.cond_doped(T, 2e18, 300., 1.4),     # n-AlGaAs:Si
+              lambda T: M.cond_doped(T, 2e18, 100., 1.25),    # p-GaAs:C
+              lambda T: M.cond_doped(T, 2e18, 40., 1.25),     # p-AlGaAs:C
+              lambda T: M.cond_doped(T, 1e18, 2500., 1.4)]    # n-GaAs substrate
+    return M.sample_tables(models, T0, dT, nT)
+
+
+# --------------------------------------------------------------------------- config A
+
+def config_A(n=64, order="optimal", heat=1e15):
+    """Static3D on an n^3 GaAs/AlGaAs stack with uniform heat source (BASELINE configs[0]):
+    lateral axes uniform over n um, vertical axis = DBR layer interfaces, one element per
+    layer; T = 300 K on the bottom plane."""
+    n = (n, n, n) if np.isscalar(n) else tuple(n)
+    ax0 = np.linspace(0., float(n[0]), n[0])
+    ax1 = np.linspace(0., float(n[1]), n[1])
+    hz = np.where(np.arange(n[2] - 1) % 2 == 0, D_GAAS, D_ALGAAS)
+    ax2 = np.concatenate([[0.], np.cumsum(hz)])
+    if order == "optimal":
+        order = optimal_order(n)
+    T0, dT, lat, vert = thermal_tables()
+    p = Problem("A", "thermal", [ax0, ax1, ax2], order, None, T0, dT, lat[:2].copy(), vert[:2].copy(), None, None)
+    mat = (np.arange(n[2] - 1) % 2).astype(np.uint32)[None, None, :]
+    p.elem_mat = p.to_elem_order(mat, np.uint32)
+    p.heat = np.full(p.E, float(heat))
+    ng = p.node_index_grid()
+    bottom = np.broadcast_to(ng, n)[:, :, 0].ravel()
+    p.bc_nodes = bottom.astype(np.uintp)
+    p.bc_values = np.full(bottom.size, 300.)
+    return p
+
+
+# ----------------------------------------------------------------- VCSEL-like (B, C, D)
+
+def _vcsel_vertical(ne):
+    """Vertical layer list (bottom -> top) with exactly `ne` elements:
+    Cu sink, n-GaAs substrate, bottom DBR, cavity with QWs, oxide layer, top DBR, Au contact.
+    Returns element sizes [um] and a tag per element."""
+    n_cav = 11 if ne >= 80 else 3          # QW/barrier elements (role 'active' in config C)
+    n_ox = 1
+    n_au = 2 if ne >= 40 else 1
+    rest = ne - n_cav - n_ox - n_au
+    n_sub = max(2, rest // 8)
+    n_cu = max(1, rest // 16)
+    n_dbr = rest - n_sub - n_cu
+    nb = (n_dbr * 5) // 9
+    nt = n_dbr - nb
+    h, tag = [], []
+    for x in graded_run(200., n_cu, 2.)[::-1]:
+        h.append(x); tag.append("cu")
+    for x in graded_run(100., n_sub, 0.2)[::-1]:
+        h.append(x); tag.append("sub")
+    for k in range(nb):
+        h.append(D_ALGAAS if k % 2 == 0 else D_GAAS); tag.append("nA" if k % 2 == 0 else "nG")
+    for k in range(n_cav):
+        h.append(0.005); tag.append("qw" if k % 2 else "bar")
+    h.append(0.016); tag.append("ox")
+    for k in range(nt):
+        h.append(D_ALGAAS if k % 2 == 0 else D_GAAS); tag.append("pA" if k % 2 == 0 else "pG")
+    for k in range(n_au):
+        h.append(0.1); tag.append("au")
+    assert len(h) == ne
+    return np.array(h), tag
+
+
+def _vcsel(n, order, kind, r_ap=4., r_mesa=15., hmin=0.25, hmax=4.):
+    n = (n, n, n) if np.isscalar(n) else tuple(n)
+    ax0 = graded_axis(n[0], hmin, hmax)
+    ax1 = graded_axis(n[1], hmin, hmax)
+    hz, tag = _vcsel_vertical(n[2] - 1)
+    ax2 = np.concatenate([[0.], np.cumsum(hz)])
+    if order == "optimal":
+        order = optimal_order(n)
+    xm, ym = 0.5 * (ax0[1:] + ax0[:-1]), 0.5 * (ax1[1:] + ax1[:-1])
+    R = np.sqrt(xm[:, None] ** 2 + ym[None, :] ** 2)          # (n0-1, n1-1)
+    in_mesa, in_ap = R < r_mesa, R < r_ap
+    ring = (R > 1.5 * r_ap) & (R < 0.8 * r_mesa)
+    tagv = np.array(tag)
+    thermal_id = {"cu": CU, "sub": GAAS, "nA": ALGAAS, "nG": GAAS, "bar": GAAS, "qw": QW, "ox": ALOX, "pA": ALGAAS,
+                  "pG": GAAS, "au": AU}
+    electr_id = {"cu": CU, "sub": NSUB, "nA": NDBR_B, "nG": NDBR_A, "bar": GAAS, "qw": GAAS, "ox": ALOX, "pA": PDBR_B,
+                 "pG": PDBR_A, "au": AU}
+    ids = thermal_id if kind == "thermal" else electr_id
+    col = np.array([ids[t] for t in tag], dtype=np.uint32)     # per vertical element
+    mat = np.broadcast_to(col[None, None, :], (n[0] - 1, n[1] - 1, n[2] - 1)).copy()
+    above = np.isin(tagv, ["bar", "qw", "ox", "pA", "pG", "au"])  # the etched mesa
+    mat[np.ix_(np.arange(n[0] - 1), np.arange(n[1] - 1), np.where(above)[0])] = np.where(
+        in_mesa[:, :, None], mat[:, :, above], AIR)
+    kox = np.where(tagv == "ox")[0]
+    mat[:, :, kox] = np.where(in_ap[:, :, None], (ALGAAS if kind == "thermal" else PDBR_B),
+                              np.where(in_mesa[:, :, None], ALOX, AIR))
+    kau = np.where(tagv == "au")[0]
+    mat[:, :, kau] = np.where(ring[:, :, None], AU, AIR)
+    return n, [ax0, ax1, ax2], order, mat, tagv, dict(in_mesa=in_mesa, in_ap=in_ap, ring=ring)
+
+
+def config_B(n=256, order="optimal"):
+    """Static3D, VCSEL-like layered block with nonlinear k(T) (BASELINE configs[1], 256^3)."""
+    n, axes, order, mat, tagv, reg = _vcsel(n, order, "thermal")
+    T0, dT, lat, vert = thermal_tables()
+    p = Problem("B", "thermal", axes, order, None, T0, dT, lat, vert, None, None)
+    p.elem_mat = p.to_elem_order(mat, np.uint32)
+    heat = np.zeros(mat.shape)
+    mesa_layers = np.isin(tagv, ["bar", "qw", "ox", "pA", "pG"])
+    heat[:, :, mesa_layers] = np.where(reg["in_mesa"][:, :, None], 1e14, 0.)
+    cav = np.isin(tagv, ["bar", "qw"])
+    heat[:, :, cav] = np.where(reg["in_ap"][:, :, None], 5e16, heat[:, :, cav])
+    p.heat = p.to_elem_order(heat, np.float64)
+    bottom = np.broadcast_to(p.node_index_grid(), n)[:, :, 0].ravel()
+    p.bc_nodes = bottom.astype(np.uintp)
+    p.bc_values = np.full(bottom.size, 300.)
+    return p
+
+
+def config_C(n=(192, 192, 400), order="optimal", voltage=1.4):
+    """Shockley3D with oxide aperture and a nonlinear junction layer (BASELINE configs[2])."""
+    n, axes, order, mat, tagv, reg = _vcsel(n, order, "shockley")
+    T0, dT, lat, vert = electrical_tables()
+    p = Problem("C", "shockley", axes, order, None, T0, dT, lat, vert, None, None)
+    p.elem_mat = p.to_elem_order(mat, np.uint32)
+    junc = np.zeros(mat.shape, dtype=np.uint32)
+    cav = np.isin(tagv, ["bar", "qw"])
+    junc[:, :, cav] = np.where(reg["in_mesa"][:, :, None], 1, 0)
+    p.elem_junc = p.to_elem_order(junc, np.uint32)
+    p.elem_role = np.zeros(p.E, dtype=np.uint8)
+    p.noheat = p.to_elem_order((mat == AIR).astype(np.uint8), np.uint8)
+    p.maxerr = 0.05
+    p.beta, p.js = 11., 1.   # thermoelectric.xpl:91
+    ng = np.broadcast_to(p.node_index_grid(), n)
+    # 0 V on the bottom plane (n side), `voltage` on the top face of the Au ring (p side)
+    x, y = axes[0], axes[1]
+    Rn = np.sqrt(x[:, None] ** 2 + y[None, :] ** 2)
+    # nodes whose four surrounding top-layer elements are all Au
+    ring_e = reg["ring"]
+    ring_n = np.zeros((n[0], n[1]), dtype=bool)
+    ring_n[1:-1, 1:-1] = ring_e[:-1, :-1] & ring_e[1:, :-1] & ring_e[:-1, 1:] & ring_e[1:, 1:]
+    top = ng[:, :, -1][ring_n]
+    bottom = ng[:, :, 0].ravel()
+    p.bc_nodes = np.concatenate([top, bottom]).astype(np.uintp)
+    p.bc_values = np.concatenate([np.full(top.size, float(voltage)), np.zeros(bottom.size)])
+    p.meta["Rn"] = Rn
+    return p
+
+
+def config_E(g=1, nz_per_gpu=96, nxy=512, order="012"):
+    """Static3D weak-scaling case (BASELINE configs[4]): the config-A stack with the major axis
+    extended proportionally to the number of GPUs g.  ORDER_012: the slab axis (major = axis 0) is
+    lateral, so every GPU sees the same layer structure; the vertical axis is the minor one."""
+    n = (nz_per_gpu * g, nxy, nxy)
+    p = config_A(n, order=order)
+    p.name = f"E{g}"
+    return p
+
+
+# --------------------------------------------------------------------- junction tables
+
+def setup_active(p):
+    """setupActiveRegions (electr3d.cpp:89-183) on the flat description: returns a list of dicts
+    (pfem_junction fields) and the junction-table length."""
+    n, es = p.n, p.estrides
+    junc3 = p.elem_junc[p.elem_index_grid()] if p.elem_junc is not None else None
+    acts, tot = [], 0
+    if junc3 is None or junc3.max() == 0:
+        return acts, 0
+    junc3 = np.broadcast_to(junc3, tuple(k - 1 for k in n))
+    for num in range(1, int(junc3.max()) + 1):
+        m = junc3 == num
+        if not m.any():
+            acts.append(dict(bottom=0, top=1, left=0, right=0, back=0, front=0, ld=0, offset=0, height=1.))
+            continue
+        cols = m.any(axis=2)
+        vert = m.any(axis=(0, 1))
+        ks = np.where(vert)[0]
+        bottom, top = int(ks[0]), int(ks[-1]) + 1
+        # every active column must span exactly [bottom, top)
+        span = m[cols]
+        if not (span[:, bottom:top].all() and span.sum(axis=1).max() == top - bottom):
+            raise ValueError(f"Junction {num - 1} does not have top and bottom edges at constant heights")
+        i0 = np.where(cols.any(axis=1))[0]
+        i1 = np.where(cols.any(axis=0))[0]
+        back, front, left, right = int(i0[0]), int(i0[-1]) + 1, int(i1[0]), int(i1[-1]) + 1
+        ld = front - back
+        acts.append(dict(bottom=bottom, top=top, left=left, right=right, back=back, front=front, ld=ld,
+                         offset=tot - ld * left - back, height=float(p.axes[2][top] - p.axes[2][bottom])))
+        tot += (right - left) * (front - back)
+    return acts, tot

@@ -1,0 +1,555 @@
+// kernels_simple.cuh — straightforward one-thread-per-node / per-element FP64 kernels.
+// They are the device-side reference for the tiled production kernels (kernels_tiled.cuh)
+// and implement every non-iteration step of the path (conductivity updates, load vector,
+// diagonal, loop-error reductions, post-processing).
+#pragma once
+#include "pfem_internal.cuh"
+
+namespace pfem {
+
+#define PFEM_NODE_BLOCK_X 64
+#define PFEM_NODE_BLOCK_Y 4
+
+// ---------------------------------------------------------------- operator (simple) -----
+
+// MODE 0: out = M (A in),  partial in.out -> pq, alpha          (CG: q = A p)
+// MODE 1: out = M (f - A in)                                    (initial residual)
+// MODE 2: out = M (f - A in),  partials out.out -> bb, out.D^-1 out -> bz   (norms of the lifted rhs)
+// MODE 3: out = M (A in), no reduction, ignores sc->done        (tests: plain operator)
+// M masks Dirichlet rows (dinv == 0).  `in` must be 0 on Dirichlet nodes for MODE 0/3.
+template <int MODE>
+__global__ void __launch_bounds__(PFEM_NODE_BLOCK_X* PFEM_NODE_BLOCK_Y)
+k_apply_simple(const Grid g, const double* __restrict__ cl, const double* __restrict__ cv,
+               const double* __restrict__ in, const double* __restrict__ dinv, const double* __restrict__ f,
+               double* __restrict__ out, Scalars* sc, double* partials) {
+    __shared__ double sh[64];
+    __shared__ int sh_flag;
+    if (MODE == 0 && sc->done) return;
+    const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
+    const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
+    const int k = blockIdx.z;
+    double dot[2] = {0., 0.};
+    if (i < g.nI && j < g.nJ) {
+        const idx_t n = i + g.sJ * j + g.sK * k;
+        double P[3][3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+                for (int a = 0; a < 3; ++a) P[c][b][a] = in[n + (a - 1) + g.sJ * (b - 1) + g.sK * (c - 1)];
+        double acc = 0.;
+#pragma unroll
+        for (int dk = -1; dk <= 0; ++dk)
+#pragma unroll
+            for (int dj = -1; dj <= 0; ++dj)
+#pragma unroll
+                for (int di = -1; di <= 0; ++di) {
+                    const idx_t slot = n + di + g.sJ * dj + g.sK * dk;
+                    double kI, kJ, kK, kv[8];
+                    elem_conductances(g, cl[slot], cv[slot], i + di, j + dj, k + dk, kI, kJ, kK);
+                    elem_matrix8(kI, kJ, kK, kv);
+                    // this node is local corner (-di,-dj,-dk) of the element
+#pragma unroll
+                    for (int l = 0; l < 8; ++l) {
+                        const int bi = l & 1, bj = (l >> 1) & 1, bk = (l >> 2) & 1;
+                        const int x = ((-di) ^ bi) | (((-dj) ^ bj) << 1) | (((-dk) ^ bk) << 2);
+                        acc += kv[x] * P[dk + bk + 1][dj + bj + 1][di + bi + 1];
+                    }
+                }
+        const double dn = dinv[n];
+        const bool fixed = (dn == 0.);
+        double o;
+        if (MODE == 0 || MODE == 3) o = fixed ? 0. : acc;
+        else o = fixed ? 0. : f[n] - acc;
+        out[n] = o;
+        if (MODE == 0) dot[0] = P[1][1][1] * o;
+        if (MODE == 2) { dot[0] = o * o; dot[1] = o * o * dn; }
+    }
+    if (MODE == 1 || MODE == 3) return;
+    if (grid_reduce<2, false>(dot, partials, &sc->ticket[0], sh, &sh_flag)) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            if (MODE == 0) {
+                sc->pq = dot[0];
+                if (dot[0] > 0.) sc->alpha = sc->rho / dot[0];
+                else {
+                    sc->alpha = 0.;
+                    if (!sc->bench) { sc->done = 1; sc->status = (dot[0] == dot[0]) ? -1 : -2; }
+                }
+            } else { sc->bb = dot[0]; sc->bz = dot[1]; }
+        }
+    }
+}
+
+// Diagonal of the eliminated matrix: sum over the 8 adjacent elements of (kI+kJ+kK)/9
+// (therm3d.cpp:227); dinv = 0 marks Dirichlet rows (and rows with an empty diagonal).
+__global__ void k_diag(const Grid g, const double* __restrict__ cl, const double* __restrict__ cv,
+                       const uint8_t* __restrict__ fixed, double* __restrict__ dinv) {
+    const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
+    const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= g.nI || j >= g.nJ) return;
+    const idx_t n = i + g.sJ * j + g.sK * k;
+    double d = 0.;
+#pragma unroll
+    for (int dk = -1; dk <= 0; ++dk)
+#pragma unroll
+        for (int dj = -1; dj <= 0; ++dj)
+#pragma unroll
+            for (int di = -1; di <= 0; ++di) {
+                const idx_t slot = n + di + g.sJ * dj + g.sK * dk;
+                double kI, kJ, kK;
+                elem_conductances(g, cl[slot], cv[slot], i + di, j + dj, k + dk, kI, kJ, kK);
+                d += (kI + kJ + kK) * (1. / 9.);
+            }
+    dinv[n] = (fixed[n] || !(d > 0.)) ? 0. : 1. / d;
+}
+
+// Load vector: B[node] += 0.125e-18*dx*dy*dz*heat[e] over the 8 adjacent elements
+// (therm3d.cpp:223,274).  heat lives on the padded element lattice (0 in padding).
+__global__ void k_load_vector(const Grid g, const double* __restrict__ heat, double* __restrict__ f) {
+    const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
+    const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= g.nI || j >= g.nJ) return;
+    const idx_t n = i + g.sJ * j + g.sK * k;
+    double s = 0.;
+#pragma unroll
+    for (int dk = -1; dk <= 0; ++dk)
+#pragma unroll
+        for (int dj = -1; dj <= 0; ++dj)
+#pragma unroll
+            for (int di = -1; di <= 0; ++di) {
+                const idx_t slot = n + di + g.sJ * dj + g.sK * dk;
+                s += 0.125e-18 * g.hI[i + di] * g.hJ[j + dj] * g.hK[k + dk] * heat[slot];
+            }
+    f[n] = s;
+}
+
+// ------------------------------------------------------------ vector kernels (PCG) ------
+
+// p = dinv*r + beta*p   (simple variant only; the tiled operator kernel fuses this)
+__global__ void k_pupdate(idx_t N, const double* __restrict__ r, const double* __restrict__ dinv,
+                          double* __restrict__ p, const Scalars* sc) {
+    if (sc->done) return;
+    const double beta = sc->beta;
+    for (idx_t n = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; n < N; n += (idx_t)gridDim.x * blockDim.x)
+        p[n] = dinv[n] * r[n] + beta * p[n];
+}
+
+// x += alpha p; r -= alpha q; rho = sum r^2 dinv; rr = sum r^2; then (last block) the scalar
+// recurrences of CG (itcg, extlib/nspcg/nspcg.f:9281-9337) and the stopping test.
+// INIT = true: no update, only the two reductions and the initial scalars.
+template <bool INIT>
+__global__ void __launch_bounds__(256)
+k_update(idx_t N, double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
+         const double* __restrict__ q, const double* __restrict__ dinv, Scalars* sc, double* partials) {
+    __shared__ double sh[64];
+    __shared__ int sh_flag;
+    if (!INIT && sc->done) return;
+    const double alpha = INIT ? 0. : sc->alpha;
+    double v[2] = {0., 0.};
+    const idx_t nthreads = (idx_t)gridDim.x * blockDim.x;
+    const idx_t t = blockIdx.x * (idx_t)blockDim.x + threadIdx.x;
+    const idx_t N2 = N >> 1;  // arrays are 16-byte aligned (guard band is a multiple of 16 doubles)
+    for (idx_t m = t; m < N2; m += nthreads) {
+        double2 rr = reinterpret_cast<const double2*>(r)[m];
+        const double2 dd = reinterpret_cast<const double2*>(dinv)[m];
+        if (!INIT) {
+            const double2 pp = reinterpret_cast<const double2*>(p)[m];
+            const double2 qq = reinterpret_cast<const double2*>(q)[m];
+            double2 xx = reinterpret_cast<double2*>(x)[m];
+            xx.x += alpha * pp.x; xx.y += alpha * pp.y;
+            rr.x -= alpha * qq.x; rr.y -= alpha * qq.y;
+            reinterpret_cast<double2*>(x)[m] = xx;
+            reinterpret_cast<double2*>(r)[m] = rr;
+        }
+        v[0] += rr.x * rr.x * dd.x + rr.y * rr.y * dd.y;
+        v[1] += rr.x * rr.x + rr.y * rr.y;
+    }
+    if ((N & 1) && t == 0) {
+        const idx_t n = N - 1;
+        double rn = r[n];
+        if (!INIT) { x[n] += alpha * p[n]; rn -= alpha * q[n]; r[n] = rn; }
+        v[0] += rn * rn * dinv[n];
+        v[1] += rn * rn;
+    }
+    if (grid_reduce<2, false>(v, partials, &sc->ticket[1], sh, &sh_flag)) {
+        if (threadIdx.x == 0) {
+            if (INIT) {
+                sc->rho = v[0]; sc->rho_prev = v[0]; sc->rr = v[1];
+                sc->beta = 0.; sc->alpha = 0.; sc->pq = 0.; sc->iter = 0; sc->status = 0; sc->done = 0;
+                if (!(v[1] == v[1])) { sc->done = 1; sc->status = -2; }
+                else if (!sc->bench && v[1] <= sc->tol2 * sc->bb && v[0] <= sc->tol2 * sc->bz) { sc->done = 1; sc->status = 1; }
+            } else {
+                const double rho_old = sc->rho;
+                sc->rho_prev = rho_old; sc->rho = v[0]; sc->rr = v[1];
+                sc->beta = (rho_old > 0.) ? v[0] / rho_old : 0.;
+                const int it = sc->iter + 1;
+                sc->iter = it;
+                if (!sc->bench) {
+                    if (!(v[1] == v[1])) { sc->done = 1; sc->status = -2; }
+                    else if (v[1] <= sc->tol2 * sc->bb && v[0] <= sc->tol2 * sc->bz) { sc->done = 1; sc->status = 1; }
+                    else if (it >= sc->maxit) { sc->done = 1; sc->status = 2; }
+                }
+            }
+        }
+    }
+}
+
+// q = fixed ? x : 0  (the Dirichlet-only vector used to lift the boundary values into the rhs)
+__global__ void k_dirichlet_only(idx_t N, const double* __restrict__ x, const uint8_t* __restrict__ fixed,
+                                 double* __restrict__ out) {
+    for (idx_t n = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; n < N; n += (idx_t)gridDim.x * blockDim.x)
+        out[n] = fixed[n] ? x[n] : 0.;
+}
+// out = fixed ? a : b
+__global__ void k_select_fixed(idx_t N, const uint8_t* __restrict__ fixed, const double* __restrict__ a,
+                               const double* __restrict__ b, double* __restrict__ out) {
+    for (idx_t n = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; n < N; n += (idx_t)gridDim.x * blockDim.x)
+        out[n] = fixed[n] ? a[n] : b[n];
+}
+__global__ void k_scatter_dirichlet(size_t nd, const idx_t* __restrict__ node, const double* __restrict__ value,
+                                    double* __restrict__ x, uint8_t* __restrict__ fixed) {
+    // applied in order on one thread per *distinct* node would need sorting; the host passes a
+    // de-duplicated list (last value wins, like B[r] = val in setBC), so plain scatter is safe.
+    for (size_t m = blockIdx.x * (size_t)blockDim.x + threadIdx.x; m < nd; m += (size_t)gridDim.x * blockDim.x) {
+        x[node[m]] = value[m];
+        fixed[node[m]] = 1;
+    }
+}
+__global__ void k_fill(idx_t N, double* __restrict__ x, double v) {
+    for (idx_t n = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; n < N; n += (idx_t)gridDim.x * blockDim.x) x[n] = v;
+}
+__global__ void k_diag_from_dinv(idx_t N, const double* __restrict__ dinv, const uint8_t* __restrict__ fixed,
+                                 double* __restrict__ d) {
+    for (idx_t n = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; n < N; n += (idx_t)gridDim.x * blockDim.x)
+        d[n] = fixed[n] ? 1. : (dinv[n] != 0. ? 1. / dinv[n] : 0.);
+}
+
+// ------------------------------------------------- element lattice <-> compact order ----
+
+// Compact (ABI order: the element mesh keeps the node iteration order, so compact element
+// e = ei + (nI-1)*(ej + (nJ-1)*ek) in index space) <-> padded node-lattice slots.
+__device__ __forceinline__ idx_t compact_to_slot(const Grid& g, idx_t e) {
+    const idx_t eI = g.nI - 1, eJ = g.nJ - 1;
+    const idx_t ei = e % eI, t = e / eI;
+    const idx_t ej = t % eJ, ek = t / eJ;
+    return ei + g.sJ * ej + g.sK * ek;
+}
+__device__ __forceinline__ idx_t slot_to_compact(const Grid& g, int i, int j, int k) {
+    return i + (idx_t)(g.nI - 1) * (j + (idx_t)(g.nJ - 1) * k);
+}
+template <typename T, int NC>
+__global__ void k_elem_expand(const Grid g, const T* __restrict__ src, T* __restrict__ dst0, T* __restrict__ dst1,
+                              T* __restrict__ dst2) {
+    for (idx_t e = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; e < g.E; e += (idx_t)gridDim.x * blockDim.x) {
+        const idx_t slot = compact_to_slot(g, e);
+        dst0[slot] = src[e * NC];
+        if (NC > 1) dst1[slot] = src[e * NC + 1];
+        if (NC > 2) dst2[slot] = src[e * NC + 2];
+    }
+}
+template <typename T, int NC>
+__global__ void k_elem_compact(const Grid g, const T* __restrict__ src0, const T* __restrict__ src1,
+                               const T* __restrict__ src2, T* __restrict__ dst) {
+    for (idx_t e = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; e < g.E; e += (idx_t)gridDim.x * blockDim.x) {
+        const idx_t slot = compact_to_slot(g, e);
+        dst[e * NC] = src0[slot];
+        if (NC > 1) dst[e * NC + 1] = src1[slot];
+        if (NC > 2) dst[e * NC + 2] = src2[slot];
+    }
+}
+
+// Decode helper for per-element kernels launched over the node lattice: returns false for
+// padding slots.  (pi[a] = element index along PHYSICAL axis a.)
+__device__ __forceinline__ bool elem_slot(const Grid& g, int i, int j, int k, int (&pi)[3]) {
+    if (i >= g.nI - 1 || j >= g.nJ - 1 || k >= g.nK - 1) return false;
+    const int ii[3] = {i, j, k};
+    pi[0] = ii[g.dim_of_phys[0]];
+    pi[1] = ii[g.dim_of_phys[1]];
+    pi[2] = ii[g.dim_of_phys[2]];
+    return true;
+}
+
+// Linear table interpolation, clamped (same arithmetic as oracle table_at()).
+__device__ __forceinline__ double table_at(const double* __restrict__ tab, uint32_t mat, uint32_t nT, double T0,
+                                           double dT, double T) {
+    double t = (T - T0) / dT;
+    if (!(t > 0.)) t = 0.;
+    const double tmax = (double)(nT - 1);
+    if (t > tmax) t = tmax;
+    uint32_t i = (uint32_t)t;
+    if (i > nT - 2) i = nT - 2;
+    const double f = t - (double)i;
+    const double* row = tab + (size_t)mat * nT;
+    const double a = row[i], b = row[i + 1];
+    return __dadd_rn(a, __dmul_rn(f, __dsub_rn(b, a)));  // no FMA contraction: bit-equal to the oracle
+}
+
+// ------------------------------------------------------- conductivity updates -----------
+
+// Thermal: T_mean = 0.125 * sum of the 8 node temperatures in the reference's corner order,
+// conds = table(T_mean)   (therm3d.cpp:208-213)
+__global__ void k_cond_thermal(const Grid g, const double* __restrict__ T, const uint32_t* __restrict__ mat,
+                               uint32_t nT, double T0, double dT, const double* __restrict__ tab_lat,
+                               const double* __restrict__ tab_vert, double* __restrict__ cl, double* __restrict__ cv) {
+    const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
+    const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
+    const int k = blockIdx.z;
+    int pi[3];
+    if (!elem_slot(g, i, j, k, pi)) return;
+    const idx_t n = i + g.sJ * j + g.sK * k;
+    double temp = 0.;
+#pragma unroll
+    for (int l = 0; l < 8; ++l)
+        temp = __dadd_rn(temp, T[n + ((l & 1) ? g.ps[0] : 0) + ((l & 2) ? g.ps[1] : 0) + ((l & 4) ? g.ps[2] : 0)]);
+    temp *= 0.125;
+    const uint32_t m = mat[n];
+    cl[n] = table_at(tab_lat, m, nT, T0, dT, temp);
+    cv[n] = table_at(tab_vert, m, nT, T0, dT, temp);
+}
+
+struct JunctionDev {
+    idx_t bottom, top, left, right, back, front, ld, offset;
+    double height;
+};
+
+// loadConductivity (electr3d.cpp:203-225)
+__global__ void k_cond_shockley(const Grid g, const uint32_t* __restrict__ mat, const uint32_t* __restrict__ junc,
+                                const uint8_t* __restrict__ role, const double* __restrict__ Te, uint32_t nT, double T0,
+                                double dT, const double* __restrict__ tab_lat, const double* __restrict__ tab_vert,
+                                const JunctionDev* __restrict__ act, const double* __restrict__ junc_cond, double pcond,
+                                double ncond, double* __restrict__ cl, double* __restrict__ cv) {
+    const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
+    const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
+    const int k = blockIdx.z;
+    int pi[3];
+    if (!elem_slot(g, i, j, k, pi)) return;
+    const idx_t n = i + g.sJ * j + g.sK * k;
+    const uint32_t actn = junc ? junc[n] : 0u;
+    double c0, c1;
+    if (actn) {
+        const JunctionDev a = act[actn - 1];
+        const idx_t col = a.offset + a.ld * pi[1] + pi[0];
+        c0 = junc_cond[2 * col];
+        c1 = junc_cond[2 * col + 1];
+        if (isnan(c1) || fabs(c1) < 1e-16) c1 = 1e-16;
+    } else if (role && role[n] == 1) {
+        c0 = c1 = pcond;
+    } else if (role && role[n] == 2) {
+        c0 = c1 = ncond;
+    } else {
+        const double T = Te[n];
+        c0 = table_at(tab_lat, mat[n], nT, T0, dT, T);
+        c1 = table_at(tab_vert, mat[n], nT, T0, dT, T);
+    }
+    cl[n] = c0;
+    cv[n] = c1;
+}
+
+// Junction update (electr3d.cpp:246-274) with the Shockley law of beta.hpp:43-46.
+__global__ void k_junction_update(const Grid g, const uint32_t* __restrict__ junc, const JunctionDev* __restrict__ act,
+                                  const double* __restrict__ phi, const double* __restrict__ beta_col,
+                                  const double* __restrict__ js_col, int stable, double* __restrict__ cl,
+                                  double* __restrict__ cv) {
+    const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
+    const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
+    const int k = blockIdx.z;
+    int pi[3];
+    if (!elem_slot(g, i, j, k, pi)) return;
+    const idx_t n = i + g.sJ * j + g.sK * k;
+    const uint32_t nact = junc[n];
+    if (!nact) return;
+    const JunctionDev a = act[nact - 1];
+    const idx_t b0 = (idx_t)pi[0] * g.ps[0], f0 = b0 + g.ps[0], l1 = (idx_t)pi[1] * g.ps[1], r1 = l1 + g.ps[1];
+    const idx_t zb = a.bottom * g.ps[2], zt = a.top * g.ps[2];
+    const double U = 0.25 * (-phi[b0 + l1 + zb] - phi[f0 + l1 + zb] - phi[b0 + r1 + zb] - phi[f0 + r1 + zb] +
+                             phi[b0 + l1 + zt] + phi[f0 + l1 + zt] + phi[b0 + r1 + zt] + phi[f0 + r1 + zt]);
+    double jy = 0.1 * cv[n] * U / a.height;
+    const idx_t col = a.offset + a.ld * pi[1] + pi[0];
+    jy = fabs(jy);
+    double c0 = 0., c1 = 10. * jy * a.height * beta_col[col] / log(1e7 * jy / js_col[col] + 1.);
+    if (stable) { c0 = 0.5 * (cl[n] + c0); c1 = 0.5 * (cv[n] + c1); }
+    if (isnan(c1) || fabs(c1) < 1e-16) c1 = 1e-16;
+    cl[n] = c0;
+    cv[n] = c1;
+}
+
+// saveConductivity (electr3d.cpp:227-237): junction table <- conds of the mid-plane element
+__global__ void k_junction_save(const Grid g, const JunctionDev* __restrict__ act, int nact,
+                                const double* __restrict__ cl, const double* __restrict__ cv,
+                                double* __restrict__ junc_cond) {
+    for (int a = 0; a < nact; ++a) {
+        const JunctionDev A = act[a];
+        const idx_t v = (A.top + A.bottom) / 2;
+        const idx_t nl = A.front - A.back, nt = A.right - A.left;
+        for (idx_t m = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; m < nl * nt; m += (idx_t)gridDim.x * blockDim.x) {
+            const idx_t t = A.left + m / nl, l = A.back + m % nl;
+            const idx_t slot = l * g.ps[0] + t * g.ps[1] + v * g.ps[2];
+            const idx_t col = A.offset + A.ld * t + l;
+            junc_cond[2 * col] = cl[slot];
+            junc_cond[2 * col + 1] = cv[slot];
+        }
+    }
+}
+
+// ----------------------------------------------------- loop errors & post-processing ----
+
+// err = max|T - T_prev|, maxT (therm3d.cpp:318-325); also T_prev <- T for the next loop is done
+// by the caller with a device copy.
+__global__ void __launch_bounds__(256)
+k_thermal_error(idx_t N, const double* __restrict__ T, const double* __restrict__ Tp, Scalars* sc, double* partials) {
+    __shared__ double sh[64];
+    __shared__ int sh_flag;
+    double v[2] = {0., 0.};
+    for (idx_t n = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; n < N; n += (idx_t)gridDim.x * blockDim.x) {
+        const double t = T[n];
+        v[0] = fmax(v[0], fabs(Tp[n] - t));
+        v[1] = fmax(v[1], t);
+    }
+    if (grid_reduce<2, true>(v, partials, &sc->ticket[2], sh, &sh_flag)) {
+        if (threadIdx.x == 0) { sc->red[0] = v[0]; sc->red[1] = v[1]; }
+    }
+}
+
+// Mean gradient of a nodal field over one brick, physical axis order, exactly the sign
+// pattern of electr3d.cpp:399-410 / therm3d.cpp:372-381 (sum of 4 edge differences).
+__device__ __forceinline__ void brick_edge_sums(const Grid& g, const double* __restrict__ u, idx_t n, double& s0,
+                                                double& s1, double& s2) {
+    const double lll = u[n], ull = u[n + g.ps[0]], lul = u[n + g.ps[1]], uul = u[n + g.ps[0] + g.ps[1]];
+    const double llu = u[n + g.ps[2]], ulu = u[n + g.ps[0] + g.ps[2]], luu = u[n + g.ps[1] + g.ps[2]],
+                 uuu = u[n + g.ps[0] + g.ps[1] + g.ps[2]];
+    s0 = -lll - llu - lul - luu + ull + ulu + uul + uuu;
+    s1 = -lll - llu + lul + luu - ull - ulu + uul + uuu;
+    s2 = -lll + llu - lul + luu - ull + ulu - uul + uuu;
+}
+__device__ __forceinline__ void brick_sizes(const Grid& g, const int (&pi)[3], double& d0, double& d1, double& d2) {
+    const double* h[3] = {g.hI, g.hJ, g.hK};
+    d0 = h[g.dim_of_phys[0]][pi[0]];
+    d1 = h[g.dim_of_phys[1]][pi[1]];
+    d2 = h[g.dim_of_phys[2]][pi[2]];
+}
+
+// Element current densities + loop error (electr3d.cpp:387-425).  red[0] = max |dj|^2,
+// red[1] = max |j|^2 over junction elements (all if noactive); maxcur = j at that element
+// (first element in reference order among equal maxima).
+__global__ void __launch_bounds__(PFEM_NODE_BLOCK_X* PFEM_NODE_BLOCK_Y)
+k_currents(const Grid g, const double* __restrict__ phi, const double* __restrict__ cl, const double* __restrict__ cv,
+           const uint32_t* __restrict__ junc, int noactive, double* __restrict__ c0, double* __restrict__ c1,
+           double* __restrict__ c2, Scalars* sc, double* partials, long long* partial_idx) {
+    __shared__ double sh[64];
+    __shared__ int sh_flag;
+    __shared__ long long sh_idx[32];
+    const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
+    const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
+    const int k = blockIdx.z;
+    int pi[3];
+    double v[2] = {0., 0.};
+    long long my_idx = 0x7fffffffffffffffLL;
+    double my_cur = -1.;
+    if (elem_slot(g, i, j, k, pi)) {
+        const idx_t n = i + g.sJ * j + g.sK * k;
+        double s0, s1, s2, d0, d1, d2;
+        brick_edge_sums(g, phi, n, s0, s1, s2);
+        brick_sizes(g, pi, d0, d1, d2);
+        const double a = cl[n], b = cv[n];
+        const double j0 = -0.025 * a * s0 / d0, j1 = -0.025 * a * s1 / d1, j2 = -0.025 * b * s2 / d2;
+        if (noactive || junc[n]) {
+            my_cur = j0 * j0 + j1 * j1 + j2 * j2;
+            my_idx = slot_to_compact(g, i, j, k);
+            v[1] = my_cur;
+        }
+        const double e0 = c0[n] - j0, e1 = c1[n] - j1, e2 = c2[n] - j2;
+        v[0] = e0 * e0 + e1 * e1 + e2 * e2;
+        c0[n] = j0; c1[n] = j1; c2[n] = j2;
+    }
+    // arg-max: block max of v[1], then the smallest reference element index that attains it
+    const int tid = threadIdx.x + blockDim.x * threadIdx.y;
+    const unsigned int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    const unsigned int nblk = gridDim.x * gridDim.y * gridDim.z;
+    double bv[2] = {v[0], v[1]};
+    block_reduce<2, true>(bv, sh);
+    __shared__ double sh_max;
+    if (tid == 0) sh_max = bv[1];
+    __syncthreads();
+    long long cand = (my_cur == sh_max) ? my_idx : 0x7fffffffffffffffLL;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { long long t = __shfl_down_sync(0xffffffffu, cand, o); cand = t < cand ? t : cand; }
+    if ((tid & 31) == 0) sh_idx[tid >> 5] = cand;
+    __syncthreads();
+    if (tid == 0) {
+        long long best = sh_idx[0];
+        for (int w = 1; w < (int)((blockDim.x * blockDim.y + 31) >> 5); ++w) best = sh_idx[w] < best ? sh_idx[w] : best;
+        partials[(size_t)bid * 2] = bv[0];
+        partials[(size_t)bid * 2 + 1] = bv[1];
+        partial_idx[bid] = best;
+        __threadfence();
+        sh_flag = (atomicAdd(&sc->ticket[3], 1u) == nblk - 1);
+    }
+    __syncthreads();
+    if (!sh_flag) return;
+    __threadfence();
+    // last block: serial-in-thread strided scan, then block combine
+    double m0 = 0., m1 = -1.;
+    long long mi = 0x7fffffffffffffffLL;
+    for (unsigned int b = tid; b < nblk; b += blockDim.x * blockDim.y) {
+        const double x0 = __ldcg(partials + (size_t)b * 2), x1 = __ldcg(partials + (size_t)b * 2 + 1);
+        const long long xi = __ldcg(partial_idx + b);
+        m0 = fmax(m0, x0);
+        if (x1 > m1 || (x1 == m1 && xi < mi)) { m1 = x1; mi = xi; }
+    }
+    double w[2] = {m0, m1};
+    block_reduce<2, true>(w, sh);
+    if (tid == 0) sh_max = w[1];
+    __syncthreads();
+    cand = (m1 == sh_max) ? mi : 0x7fffffffffffffffLL;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { long long t = __shfl_down_sync(0xffffffffu, cand, o); cand = t < cand ? t : cand; }
+    if ((tid & 31) == 0) sh_idx[tid >> 5] = cand;
+    __syncthreads();
+    if (tid == 0) {
+        long long best = sh_idx[0];
+        for (int q = 1; q < (int)((blockDim.x * blockDim.y + 31) >> 5); ++q) best = sh_idx[q] < best ? sh_idx[q] : best;
+        sc->red[0] = w[0];
+        sc->red[1] = fmax(w[1], 0.);
+        sc->argidx = best;
+        sc->ticket[3] = 0u;
+    }
+}
+
+// maxcur = current at the arg-max element (compact index -> slot)
+__global__ void k_fetch_maxcur(const Grid g, const double* __restrict__ c0, const double* __restrict__ c1,
+                               const double* __restrict__ c2, Scalars* sc) {
+    const long long e = sc->argidx;
+    if (e < 0 || e >= g.E) { sc->maxcur[0] = sc->maxcur[1] = sc->maxcur[2] = 0.; return; }
+    const idx_t slot = compact_to_slot(g, e);
+    sc->maxcur[0] = c0[slot]; sc->maxcur[1] = c1[slot]; sc->maxcur[2] = c2[slot];
+}
+
+// Joule heat (electr3d.cpp:444-478) and heat flux (therm3d.cpp:342-384); o0..o2 padded outputs.
+template <bool HEAT>
+__global__ void k_gradient_fields(const Grid g, const double* __restrict__ u, const double* __restrict__ cl,
+                                  const double* __restrict__ cv, const uint8_t* __restrict__ noheat,
+                                  double* __restrict__ o0, double* __restrict__ o1, double* __restrict__ o2) {
+    const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
+    const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
+    const int k = blockIdx.z;
+    int pi[3];
+    if (!elem_slot(g, i, j, k, pi)) return;
+    const idx_t n = i + g.sJ * j + g.sK * k;
+    double s0, s1, s2, d0, d1, d2;
+    brick_edge_sums(g, u, n, s0, s1, s2);
+    brick_sizes(g, pi, d0, d1, d2);
+    const double a = cl[n], b = cv[n];
+    if (HEAT) {
+        const double dvx = -0.25e6 * s0 / d0, dvy = -0.25e6 * s1 / d1, dvz = -0.25e6 * s2 / d2;
+        o0[n] = (noheat && noheat[n]) ? 0. : a * dvx * dvx + a * dvy * dvy + b * dvz * dvz;
+    } else {
+        o0[n] = -0.25e6 * a * s0 / d0;
+        o1[n] = -0.25e6 * a * s1 / d1;
+        o2[n] = -0.25e6 * b * s2 / d2;
+    }
+}
+
+}  // namespace pfem

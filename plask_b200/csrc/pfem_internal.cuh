@@ -1,0 +1,164 @@
+// pfem_internal.cuh — device data layout, reduction helpers and the brick-element stencil core.
+//
+// Layout in HBM.  The mesh is handled in INDEX space: I = minor (fastest),
+// J = medium, K = major axis of RectangularMesh<3> (plask/mesh/rectilinear3d.cpp:20-32), so a
+// node array is exactly the reference's DataVector<double>: node (i,j,k) at i + nI*(j + nJ*k).
+// Element arrays live on the SAME lattice: element (i,j,k) is stored at the index of its
+// lowest corner node; the slots with i = nI-1, j = nJ-1 or k = nK-1 are padding and hold ZERO
+// conductivity.  Every array additionally has a zero guard band of G >= nI*nJ + nI + 2 entries
+// on both sides.  Together this makes the 27-point operator branch-free: a neighbour that does
+// not exist is reached through a padding/guard slot whose conductivity is 0.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pfem {
+
+typedef long long idx_t;
+
+struct Grid {
+    int nI, nJ, nK;      // nodes per index-space axis
+    idx_t sJ, sK;        // node strides (sI = 1)
+    idx_t N;             // nI*nJ*nK
+    idx_t G;             // guard band length (multiple of 16)
+    int vdim;            // index-space axis (0 I, 1 J, 2 K) that is the physical vertical axis 2
+    int dim_of_phys[3];  // index-space axis of physical axis a
+    idx_t ps[3];         // node stride of physical axis a
+    int pn[3];           // node count of physical axis a
+    idx_t es[3];         // element stride of physical axis a in the ABI (compact) element order
+    idx_t E;             // compact element count
+    // spacings per index-space axis and their reciprocals; each array has one guard entry in
+    // front and one behind (value 1), so h[-1] and h[n-1] are readable.
+    const double *hI, *hJ, *hK, *rI, *rJ, *rK;
+};
+
+// Scalars of the PCG iteration and of the nonlinear loop; device resident, one instance per
+// context, mirrored to pinned host memory after every graph batch.
+struct Scalars {
+    double rho;       // r.z
+    double rho_prev;
+    double pq;        // p.Ap
+    double alpha;
+    double beta;
+    double rr;        // r.r
+    double bb;        // ||b_free||^2
+    double bz;        // b_free . D^-1 b_free  (preconditioner norm of the rhs)
+    double tol2;      // lin_tol^2 (negative: never converge, benchmark mode)
+    double red[4];    // generic reduction outputs (err, max, ...)
+    long long argidx; // arg-max index of the current reduction
+    double maxcur[3];
+    int iter;
+    int maxit;
+    int done;         // 1: all iteration kernels return immediately
+    int status;       // 0 running, 1 converged, 2 maxit, -1 breakdown (p.Ap <= 0), -2 non-finite
+    int bench;        // 1: ignore breakdown / convergence
+    unsigned int ticket[8];
+};
+
+// ------------------------------------------------------------------ reductions ----------
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide reduction of NV values; result valid in thread 0.  `sh` needs 32*NV doubles.
+template <int NV, bool MAX>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], double* sh) {
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const int nthr = blockDim.x * blockDim.y * blockDim.z;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = (nthr + 31) >> 5;
+#pragma unroll
+    for (int a = 0; a < NV; ++a) v[a] = MAX ? warp_max(v[a]) : warp_sum(v[a]);
+    __syncthreads();  // protect sh from a previous use
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < NV; ++a) sh[a * 32 + warp] = v[a];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int a = 0; a < NV; ++a) {
+            double x = (lane < nwarp) ? sh[a * 32 + lane] : (MAX ? -1.7976931348623157e308 : 0.);
+            v[a] = MAX ? warp_max(x) : warp_sum(x);
+        }
+    }
+}
+
+// Grid-wide deterministic reduction ("last block done"): every block stores its NV partials,
+// the block that draws the last ticket reduces all of them in a fixed order.  Returns true in
+// ALL threads of that last block; totals valid in its thread 0.  partials: nblocks*NV doubles.
+template <int NV, bool MAX>
+__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* __restrict__ partials, unsigned int* ticket,
+                                            double* sh, int* sh_flag) {
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const int nthr = blockDim.x * blockDim.y * blockDim.z;
+    const unsigned int nblk = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    block_reduce<NV, MAX>(v, sh);
+    if (tid == 0) {
+#pragma unroll
+        for (int a = 0; a < NV; ++a) partials[(size_t)bid * NV + a] = v[a];
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        *sh_flag = (t == nblk - 1);
+    }
+    __syncthreads();
+    if (!*sh_flag) return false;
+    __threadfence();
+    double acc[NV];
+#pragma unroll
+    for (int a = 0; a < NV; ++a) acc[a] = MAX ? -1.7976931348623157e308 : 0.;
+    for (unsigned int b = tid; b < nblk; b += nthr) {
+#pragma unroll
+        for (int a = 0; a < NV; ++a) {
+            double x = __ldcg(partials + (size_t)b * NV + a);
+            acc[a] = MAX ? fmax(acc[a], x) : acc[a] + x;
+        }
+    }
+    block_reduce<NV, MAX>(acc, sh);
+    if (tid == 0) {
+#pragma unroll
+        for (int a = 0; a < NV; ++a) v[a] = acc[a];
+        *ticket = 0u;
+    }
+    return true;
+}
+
+// ------------------------------------------------------- brick element coefficients -----
+
+// Directional element conductances of the 8-node brick (therm3d.cpp:215-220,
+// electr3d.cpp:310-324): k_d = 1e-6 * c_d * h_a*h_b/h_d with c_d = c_vert on the physical
+// vertical axis and c_lat on the two lateral ones.  ei,ej,ek may be -1 or n-1 (guards).
+__device__ __forceinline__ void elem_conductances(const Grid& g, double cl, double cv, int ei, int ej, int ek,
+                                                  double& kI, double& kJ, double& kK) {
+    const double hi = g.hI[ei], hj = g.hJ[ej], hk = g.hK[ek];
+    const double cI = (g.vdim == 0 ? cv : cl) * 1e-6;
+    const double cJ = (g.vdim == 1 ? cv : cl) * 1e-6;
+    const double cK = (g.vdim == 2 ? cv : cl) * 1e-6;
+    kI = cI * (hj * hk) * g.rI[ei];
+    kJ = cJ * (hi * hk) * g.rJ[ej];
+    kK = cK * (hi * hj) * g.rK[ek];
+}
+
+// The 8 distinct entries of the element matrix indexed by the XOR of the local node numbers
+// (bit 0 = I, bit 1 = J, bit 2 = K differ); therm3d.cpp:227-237 with x,y,z -> I,J,K.
+__device__ __forceinline__ void elem_matrix8(double kI, double kJ, double kK, double (&kv)[8]) {
+    const double s = kI + kJ + kK;
+    kv[0] = s * (1. / 9.);
+    kv[1] = (s - 3. * kI) * (1. / 18.);
+    kv[2] = (s - 3. * kJ) * (1. / 18.);
+    kv[4] = (s - 3. * kK) * (1. / 18.);
+    kv[3] = (3. * kK - 2. * s) * (1. / 36.);  // I,J differ: (-2kI-2kJ+kK)/36
+    kv[5] = (3. * kJ - 2. * s) * (1. / 36.);  // I,K differ
+    kv[6] = (3. * kI - 2. * s) * (1. / 36.);  // J,K differ
+    kv[7] = -s * (1. / 36.);
+}
+
+}  // namespace pfem

@@ -1,0 +1,943 @@
+// plaskfem_cuda.cu — C ABI (include/plaskfem_cuda.h) and host-side drivers of the device path:
+// PCG loop (CUDA-graph batches, scalars device resident), the nonlinear loops of
+// ThermalFem3DSolver::compute (solvers/thermal/static/therm3d.cpp:281-340) and
+// ElectricalFem3DSolver::compute (solvers/electrical/shockley/electr3d.cpp:356-442).
+// No CPU fallback anywhere: every numeric step is a kernel of this library.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/plaskfem_cuda.h"
+#include "kernels_simple.cuh"
+#include "kernels_tiled.cuh"
+
+using namespace pfem;
+
+// ------------------------------------------------------------------------ context -------
+
+struct DevArr {
+    void* base = nullptr;  // allocation start
+    size_t bytes = 0;
+};
+
+struct pfem_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    bool have_mesh = false, have_materials = false, have_junctions = false, conds_valid = false;
+    Grid g;
+    std::vector<DevArr> allocs;
+    // node arrays (pointers already offset by the guard band)
+    double *x = nullptr, *xprev = nullptr, *r = nullptr, *p = nullptr, *p2 = nullptr, *q = nullptr, *dinv = nullptr, *f = nullptr;
+    uint8_t* fixed = nullptr;
+    // element arrays on the node lattice
+    double *cl = nullptr, *cv = nullptr, *Te = nullptr, *cur0 = nullptr, *cur1 = nullptr, *cur2 = nullptr;
+    double *aux0 = nullptr, *aux1 = nullptr, *aux2 = nullptr;
+    uint32_t *mat = nullptr, *junc = nullptr;
+    uint8_t *role = nullptr, *noheat = nullptr;
+    // small arrays
+    double* hbuf = nullptr;
+    double *tab_lat = nullptr, *tab_vert = nullptr;
+    uint32_t nmat = 0, nT = 0;
+    double T0 = 0, dT = 1;
+    JunctionDev* act = nullptr;
+    int nact = 0;
+    size_t ncol = 0;
+    double *junc_cond = nullptr, *beta_col = nullptr, *js_col = nullptr;
+    double pcond = 5., ncond = 50.;
+    int stable = 0;
+    int loopno = 0;
+    // scalars / reductions
+    Scalars* d_sc = nullptr;
+    Scalars* h_sc = nullptr;  // pinned
+    double* partials = nullptr;
+    long long* partial_idx = nullptr;
+    size_t n_partials = 0;
+    // scratch for compact <-> lattice transfers
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+    // cached CUDA graph of `graph_batch` PCG iterations
+    cudaGraphExec_t graph = nullptr;
+    int graph_batch = 0, graph_variant = -1, graph_precond = -1;
+    long long launches = 0;
+    double last_relres_pre = 0.;
+    int sm_count = 148;
+    TiledPlan plan;
+};
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            char b_[512];                                                                                \
+            snprintf(b_, sizeof b_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            ctx->err = b_;                                                                               \
+            return (e_ == cudaErrorMemoryAllocation) ? PFEM_ERR_NOMEM : PFEM_ERR_CUDA;                   \
+        }                                                                                                \
+    } while (0)
+
+#define FAIL(code, ...)                          \
+    do {                                         \
+        char b_[512];                            \
+        snprintf(b_, sizeof b_, __VA_ARGS__);    \
+        ctx->err = b_;                           \
+        return (code);                           \
+    } while (0)
+
+#define TRY(...)                   \
+    do {                           \
+        int rc_ = (__VA_ARGS__);   \
+        if (rc_ < 0) return rc_;   \
+    } while (0)
+
+static void free_all(pfem_ctx* ctx) {
+    if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
+    for (auto& a : ctx->allocs) cudaFree(a.base);
+    ctx->allocs.clear();
+    if (ctx->stage) { cudaFree(ctx->stage); ctx->stage = nullptr; ctx->stage_bytes = 0; }
+    ctx->have_mesh = ctx->have_materials = ctx->have_junctions = ctx->conds_valid = false;
+}
+
+template <typename T>
+static int dev_alloc(pfem_ctx* ctx, T** out, size_t count, size_t guard) {
+    void* base = nullptr;
+    size_t bytes = (count + 2 * guard) * sizeof(T);
+    if (bytes == 0) bytes = sizeof(T);
+    CU(cudaMalloc(&base, bytes));
+    CU(cudaMemsetAsync(base, 0, bytes, ctx->stream));
+    ctx->allocs.push_back({base, bytes});
+    *out = reinterpret_cast<T*>(base) + guard;
+    return PFEM_OK;
+}
+
+static int ensure_stage(pfem_ctx* ctx, size_t bytes) {
+    if (ctx->stage_bytes >= bytes) return PFEM_OK;
+    if (ctx->stage) { CU(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->stage); ctx->stage = nullptr; ctx->stage_bytes = 0; }
+    CU(cudaMalloc(&ctx->stage, bytes));
+    ctx->stage_bytes = bytes;
+    return PFEM_OK;
+}
+
+static inline dim3 node_block() { return dim3(PFEM_NODE_BLOCK_X, PFEM_NODE_BLOCK_Y, 1); }
+static inline dim3 node_grid(const Grid& g) {
+    return dim3((g.nI + PFEM_NODE_BLOCK_X - 1) / PFEM_NODE_BLOCK_X, (g.nJ + PFEM_NODE_BLOCK_Y - 1) / PFEM_NODE_BLOCK_Y, g.nK);
+}
+static inline int vec_blocks(const pfem_ctx* ctx) { return ctx->sm_count * 8; }
+
+#define LAUNCHED(n) (ctx->launches += (n))
+#define KCHECK() CU(cudaGetLastError())
+
+// ------------------------------------------------------------------------ life cycle ----
+
+extern "C" int pfem_abi_version(void) { return PFEM_ABI_VERSION; }
+
+extern "C" int pfem_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char* pfem_strerror(int s) {
+    switch (s) {
+        case PFEM_OK: return "ok";
+        case PFEM_NOT_CONVERGED: return "linear solver failed to converge in maxit iterations";
+        case PFEM_ERR_CUDA: return "CUDA runtime error";
+        case PFEM_ERR_NO_DEVICE: return "no usable CUDA device (the CUDA algorithm has no CPU fallback)";
+        case PFEM_ERR_BAD_INPUT: return "bad input";
+        case PFEM_ERR_STATE: return "call sequence error: mesh/materials/field not set";
+        case PFEM_ERR_NOT_SPD: return "stiffness matrix is not positive definite (p.Ap <= 0)";
+        case PFEM_ERR_NOMEM: return "out of device memory";
+        case PFEM_ERR_NAN: return "non-finite value in the iteration";
+        default: return "unknown status";
+    }
+}
+
+extern "C" const char* pfem_last_error(const pfem_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int pfem_create(pfem_ctx** out, int device) {
+    if (!out) return PFEM_ERR_BAD_INPUT;
+    *out = nullptr;
+    int n = pfem_device_count();
+    if (n <= 0 || device < 0 || device >= n) return PFEM_ERR_NO_DEVICE;
+    pfem_ctx* ctx = new pfem_ctx();
+    ctx->device = device;
+    auto bail = [&](int rc) { delete ctx; return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(PFEM_ERR_NO_DEVICE);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(PFEM_ERR_NO_DEVICE);
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PFEM_ERR_CUDA);
+    if (cudaMalloc(&ctx->d_sc, sizeof(Scalars)) != cudaSuccess) return bail(PFEM_ERR_NOMEM);
+    cudaMemset(ctx->d_sc, 0, sizeof(Scalars));
+    if (cudaMallocHost(&ctx->h_sc, sizeof(Scalars)) != cudaSuccess) return bail(PFEM_ERR_NOMEM);
+    memset(ctx->h_sc, 0, sizeof(Scalars));
+    *out = ctx;
+    return PFEM_OK;
+}
+
+extern "C" void pfem_destroy(pfem_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    free_all(ctx);
+    if (ctx->d_sc) cudaFree(ctx->d_sc);
+    if (ctx->h_sc) cudaFreeHost(ctx->h_sc);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" void pfem_default_opts(pfem_opts* o) {
+    memset(o, 0, sizeof(*o));
+    o->maxit = 10000;
+    o->lin_tol = 1e-8;
+    o->precond = 0;
+    o->outer_tol = 0.05;
+    o->loops = 0;
+    o->batch = 0;
+    o->variant = 0;
+}
+
+// ------------------------------------------------------------------------ mesh ----------
+
+extern "C" int pfem_set_mesh(pfem_ctx* ctx, const size_t n[3], const double* ax0, const double* ax1, const double* ax2,
+                             const size_t stride[3]) {
+    if (!ctx) return PFEM_ERR_BAD_INPUT;
+    CU(cudaSetDevice(ctx->device));
+    if (!n || !ax0 || !ax1 || !ax2 || !stride) FAIL(PFEM_ERR_BAD_INPUT, "null mesh argument");
+    for (int a = 0; a < 3; ++a)
+        if (n[a] < 2) FAIL(PFEM_ERR_BAD_INPUT, "axis %d needs at least 2 points", a);
+    // recover the iteration order from the strides (rectilinear3d.cpp:20-32)
+    int minor = -1, medium = -1, major = -1;
+    for (int a = 0; a < 3; ++a) if (stride[a] == 1) minor = a;
+    if (minor < 0) FAIL(PFEM_ERR_BAD_INPUT, "no axis has stride 1");
+    for (int a = 0; a < 3; ++a) if (a != minor && stride[a] == n[minor]) medium = a;
+    if (medium < 0) FAIL(PFEM_ERR_BAD_INPUT, "strides are not a RectangularMesh<3> iteration order");
+    major = 3 - minor - medium;
+    if (stride[major] != n[minor] * n[medium]) FAIL(PFEM_ERR_BAD_INPUT, "strides are not a RectangularMesh<3> iteration order");
+    const double* ax[3] = {ax0, ax1, ax2};
+    for (int a = 0; a < 3; ++a)
+        for (size_t i = 1; i < n[a]; ++i)
+            if (!(ax[a][i] > ax[a][i - 1])) FAIL(PFEM_ERR_BAD_INPUT, "axis %d is not strictly increasing at %zu", a, i);
+    double total = (double)n[0] * (double)n[1] * (double)n[2];
+    if (total > 2.0e9) FAIL(PFEM_ERR_BAD_INPUT, "mesh too large for one device context (%g nodes)", total);
+
+    CU(cudaStreamSynchronize(ctx->stream));
+    free_all(ctx);
+    Grid& g = ctx->g;
+    memset(&g, 0, sizeof(g));
+    g.nI = (int)n[minor]; g.nJ = (int)n[medium]; g.nK = (int)n[major];
+    g.sJ = g.nI; g.sK = (idx_t)g.nI * g.nJ;
+    g.N = g.sK * g.nK;
+    g.G = ((g.sK + g.sJ + 2 + 15) / 16) * 16;
+    g.dim_of_phys[minor] = 0; g.dim_of_phys[medium] = 1; g.dim_of_phys[major] = 2;
+    g.vdim = g.dim_of_phys[2];
+    for (int a = 0; a < 3; ++a) { g.ps[a] = (idx_t)stride[a]; g.pn[a] = (int)n[a]; }
+    g.es[minor] = 1; g.es[medium] = g.nI - 1; g.es[major] = (idx_t)(g.nI - 1) * (g.nJ - 1);
+    g.E = (idx_t)(g.nI - 1) * (g.nJ - 1) * (g.nK - 1);
+
+    // spacing arrays with one guard entry (value 1) on both sides
+    const int cnt[3] = {g.nI - 1, g.nJ - 1, g.nK - 1};
+    const int phys_of_dim[3] = {minor, medium, major};
+    size_t tot = 0;
+    for (int d = 0; d < 3; ++d) tot += 2 * (size_t)(cnt[d] + 2);
+    std::vector<double> hb(tot, 1.0);
+    size_t off = 0;
+    size_t hoff[3], roff[3];
+    for (int d = 0; d < 3; ++d) {
+        hoff[d] = off + 1;
+        for (int i = 0; i < cnt[d]; ++i) hb[hoff[d] + i] = ax[phys_of_dim[d]][i + 1] - ax[phys_of_dim[d]][i];
+        off += cnt[d] + 2;
+        roff[d] = off + 1;
+        for (int i = 0; i < cnt[d]; ++i) hb[roff[d] + i] = 1.0 / hb[hoff[d] + i];
+        off += cnt[d] + 2;
+    }
+    TRY(dev_alloc(ctx, &ctx->hbuf, tot, 0));
+    CU(cudaMemcpyAsync(ctx->hbuf, hb.data(), tot * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    g.hI = ctx->hbuf + hoff[0]; g.rI = ctx->hbuf + roff[0];
+    g.hJ = ctx->hbuf + hoff[1]; g.rJ = ctx->hbuf + roff[1];
+    g.hK = ctx->hbuf + hoff[2]; g.rK = ctx->hbuf + roff[2];
+
+    const size_t N = (size_t)g.N, G = (size_t)g.G;
+    TRY(dev_alloc(ctx, &ctx->x, N, G));
+    TRY(dev_alloc(ctx, &ctx->xprev, N, G));
+    TRY(dev_alloc(ctx, &ctx->r, N, G));
+    TRY(dev_alloc(ctx, &ctx->p, N, G));
+    TRY(dev_alloc(ctx, &ctx->p2, N, G));
+    TRY(dev_alloc(ctx, &ctx->q, N, G));
+    TRY(dev_alloc(ctx, &ctx->dinv, N, G));
+    TRY(dev_alloc(ctx, &ctx->f, N, G));
+    TRY(dev_alloc(ctx, &ctx->cl, N, G));
+    TRY(dev_alloc(ctx, &ctx->cv, N, G));
+    TRY(dev_alloc(ctx, &ctx->fixed, N, G));
+    TRY(dev_alloc(ctx, &ctx->mat, N, G));
+    // reduction partials: enough for the node-lattice grid and the persistent vector grid
+    dim3 ng = node_grid(g);
+    size_t nblk = (size_t)ng.x * ng.y * ng.z;
+    size_t nb2 = (size_t)vec_blocks(ctx);
+    ctx->n_partials = (nblk > nb2 ? nblk : nb2) + 1024;
+    TRY(dev_alloc(ctx, &ctx->partials, ctx->n_partials * 4, 0));
+    TRY(dev_alloc(ctx, &ctx->partial_idx, ctx->n_partials, 0));
+    CU(cudaMemsetAsync(ctx->d_sc, 0, sizeof(Scalars), ctx->stream));
+    ctx->loopno = 0;
+    ctx->plan = make_tiled_plan(g, ctx->sm_count);
+    ctx->have_mesh = true;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+
+#define NEED_MESH() \
+    do { if (!ctx) return PFEM_ERR_BAD_INPUT; if (!ctx->have_mesh) FAIL(PFEM_ERR_STATE, "pfem_set_mesh has not been called"); \
+         CU(cudaSetDevice(ctx->device)); } while (0)
+
+// upload a compact element array (NC interleaved components) onto the lattice
+template <typename T, int NC>
+static int upload_elem(pfem_ctx* ctx, const T* host, T* d0, T* d1, T* d2) {
+    const Grid& g = ctx->g;
+    size_t bytes = (size_t)g.E * NC * sizeof(T);
+    TRY(ensure_stage(ctx, bytes));
+    CU(cudaMemcpyAsync(ctx->stage, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    k_elem_expand<T, NC><<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g, (const T*)ctx->stage, d0, d1, d2);
+    KCHECK(); LAUNCHED(1);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+template <typename T, int NC>
+static int download_elem(pfem_ctx* ctx, const T* s0, const T* s1, const T* s2, T* host) {
+    const Grid& g = ctx->g;
+    size_t bytes = (size_t)g.E * NC * sizeof(T);
+    TRY(ensure_stage(ctx, bytes));
+    k_elem_compact<T, NC><<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g, s0, s1, s2, (T*)ctx->stage);
+    KCHECK(); LAUNCHED(1);
+    CU(cudaMemcpyAsync(host, ctx->stage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+
+extern "C" int pfem_set_materials(pfem_ctx* ctx, const uint32_t* elem_mat, uint32_t nmat, double T0, double dT,
+                                  uint32_t nT, const double* c_lat, const double* c_vert) {
+    NEED_MESH();
+    if (!elem_mat || !c_lat || !c_vert) FAIL(PFEM_ERR_BAD_INPUT, "null material argument");
+    if (nmat == 0 || nT < 2 || !(dT > 0.)) FAIL(PFEM_ERR_BAD_INPUT, "need nmat >= 1, nT >= 2, dT > 0");
+    for (idx_t e = 0; e < ctx->g.E; ++e)
+        if (elem_mat[e] >= nmat) FAIL(PFEM_ERR_BAD_INPUT, "element %lld has material id %u >= nmat %u", (long long)e, elem_mat[e], nmat);
+    TRY(upload_elem<uint32_t, 1>(ctx, elem_mat, ctx->mat, nullptr, nullptr));
+    size_t cnt = (size_t)nmat * nT;
+    TRY(dev_alloc(ctx, &ctx->tab_lat, cnt, 0));
+    TRY(dev_alloc(ctx, &ctx->tab_vert, cnt, 0));
+    CU(cudaMemcpyAsync(ctx->tab_lat, c_lat, cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->tab_vert, c_vert, cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->nmat = nmat; ctx->nT = nT; ctx->T0 = T0; ctx->dT = dT;
+    ctx->have_materials = true;
+    ctx->conds_valid = false;
+    return PFEM_OK;
+}
+
+extern "C" int pfem_set_dirichlet(pfem_ctx* ctx, size_t nd, const size_t* node, const double* value) {
+    NEED_MESH();
+    const Grid& g = ctx->g;
+    if (nd && (!node || !value)) FAIL(PFEM_ERR_BAD_INPUT, "null Dirichlet argument");
+    // De-duplicate keeping the LAST value per node: B[r] = val of the last condition that names
+    // r (iterative_matrix.hpp:462-464).
+    std::vector<idx_t> nn;
+    std::vector<double> vv;
+    nn.reserve(nd); vv.reserve(nd);
+    {
+        std::vector<long long> last;  // node -> position, lazily via sort-free map for big meshes
+        std::vector<std::pair<idx_t, size_t>> order(nd);
+        for (size_t m = 0; m < nd; ++m) {
+            if (node[m] >= (size_t)g.N) FAIL(PFEM_ERR_BAD_INPUT, "Dirichlet node %zu out of range", node[m]);
+            if (!(value[m] == value[m]) || isinf(value[m])) FAIL(PFEM_ERR_BAD_INPUT, "non-finite Dirichlet value");
+            order[m] = {(idx_t)node[m], m};
+        }
+        std::sort(order.begin(), order.end());
+        for (size_t m = 0; m < nd; ++m) {
+            if (m + 1 < nd && order[m + 1].first == order[m].first) continue;  // keep the last occurrence
+            nn.push_back(order[m].first);
+            vv.push_back(value[order[m].second]);
+        }
+    }
+    CU(cudaMemsetAsync(ctx->fixed, 0, (size_t)g.N, ctx->stream));
+    if (!nn.empty()) {
+        size_t bytes = nn.size() * (sizeof(idx_t) + sizeof(double));
+        TRY(ensure_stage(ctx, bytes));
+        idx_t* dn = (idx_t*)ctx->stage;
+        double* dv = (double*)(dn + nn.size());
+        CU(cudaMemcpyAsync(dn, nn.data(), nn.size() * sizeof(idx_t), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(dv, vv.data(), vv.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        int blocks = (int)((nn.size() + 255) / 256);
+        if (blocks > 4096) blocks = 4096;
+        k_scatter_dirichlet<<<blocks, 256, 0, ctx->stream>>>(nn.size(), dn, dv, ctx->x, ctx->fixed);
+        KCHECK(); LAUNCHED(1);
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+
+static int ensure_elem_arrays(pfem_ctx* ctx, bool shockley) {
+    const size_t N = (size_t)ctx->g.N, G = (size_t)ctx->g.G;
+    if (!ctx->aux0) {
+        TRY(dev_alloc(ctx, &ctx->aux0, N, G));
+        TRY(dev_alloc(ctx, &ctx->aux1, N, G));
+        TRY(dev_alloc(ctx, &ctx->aux2, N, G));
+    }
+    if (shockley && !ctx->cur0) {
+        TRY(dev_alloc(ctx, &ctx->cur0, N, G));
+        TRY(dev_alloc(ctx, &ctx->cur1, N, G));
+        TRY(dev_alloc(ctx, &ctx->cur2, N, G));
+    }
+    return PFEM_OK;
+}
+
+extern "C" int pfem_set_source(pfem_ctx* ctx, const double* heat) {
+    NEED_MESH();
+    const Grid& g = ctx->g;
+    if (!heat) {
+        CU(cudaMemsetAsync(ctx->f, 0, (size_t)g.N * sizeof(double), ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        return PFEM_OK;
+    }
+    TRY(ensure_elem_arrays(ctx, false));
+    CU(cudaMemsetAsync(ctx->aux0 - g.G, 0, (size_t)(g.N + 2 * g.G) * sizeof(double), ctx->stream));
+    TRY(upload_elem<double, 1>(ctx, heat, ctx->aux0, nullptr, nullptr));
+    k_load_vector<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->aux0, ctx->f);
+    KCHECK(); LAUNCHED(1);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+
+extern "C" int pfem_set_field(pfem_ctx* ctx, const double* x0) {
+    NEED_MESH();
+    if (!x0) FAIL(PFEM_ERR_BAD_INPUT, "null field");
+    CU(cudaMemcpyAsync(ctx->x, x0, (size_t)ctx->g.N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+
+extern "C" int pfem_fill_field(pfem_ctx* ctx, double value) {
+    NEED_MESH();
+    k_fill<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(ctx->g.N, ctx->x, value);
+    KCHECK(); LAUNCHED(1);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+
+extern "C" int pfem_set_elem_temperature(pfem_ctx* ctx, const double* T_elem, double uniform_T) {
+    NEED_MESH();
+    const Grid& g = ctx->g;
+    if (!ctx->Te) TRY(dev_alloc(ctx, &ctx->Te, (size_t)g.N, (size_t)g.G));
+    if (T_elem) {
+        TRY(upload_elem<double, 1>(ctx, T_elem, ctx->Te, nullptr, nullptr));
+    } else {
+        k_fill<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->Te, uniform_T);
+        KCHECK(); LAUNCHED(1);
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->conds_valid = false;
+    return PFEM_OK;
+}
+
+extern "C" int pfem_set_junctions(pfem_ctx* ctx, uint32_t njunc, const pfem_junction* junc, const uint32_t* elem_junc,
+                                  const uint8_t* elem_role, double pcond, double ncond, size_t ncol,
+                                  const double* junc_cond, const double* beta_col, const double* js_col, int stable) {
+    NEED_MESH();
+    const Grid& g = ctx->g;
+    if (njunc && (!junc || !elem_junc || !junc_cond || !beta_col || !js_col)) FAIL(PFEM_ERR_BAD_INPUT, "null junction argument");
+    const size_t N = (size_t)g.N, G = (size_t)g.G;
+    if (!ctx->junc) TRY(dev_alloc(ctx, &ctx->junc, N, G));
+    if (!ctx->role) TRY(dev_alloc(ctx, &ctx->role, N, G));
+    CU(cudaMemsetAsync(ctx->junc, 0, N * sizeof(uint32_t), ctx->stream));
+    CU(cudaMemsetAsync(ctx->role, 0, N, ctx->stream));
+    if (elem_junc) {
+        for (idx_t e = 0; e < g.E; ++e)
+            if (elem_junc[e] > njunc) FAIL(PFEM_ERR_BAD_INPUT, "element %lld names junction %u > njunc", (long long)e, elem_junc[e]);
+        TRY(upload_elem<uint32_t, 1>(ctx, elem_junc, ctx->junc, nullptr, nullptr));
+    }
+    if (elem_role) TRY(upload_elem<uint8_t, 1>(ctx, elem_role, ctx->role, nullptr, nullptr));
+    std::vector<JunctionDev> hj(njunc);
+    size_t need = 0;
+    for (uint32_t a = 0; a < njunc; ++a) {
+        const pfem_junction& s = junc[a];
+        if (s.top <= s.bottom || s.top >= (size_t)g.pn[2] || s.right > (size_t)g.pn[1] - 1 || s.front > (size_t)g.pn[0] - 1 ||
+            s.left > s.right || s.back > s.front || !(s.height > 0.))
+            FAIL(PFEM_ERR_BAD_INPUT, "junction %u has inconsistent extents", a);
+        hj[a] = {(idx_t)s.bottom, (idx_t)s.top, (idx_t)s.left, (idx_t)s.right, (idx_t)s.back, (idx_t)s.front, (idx_t)s.ld,
+                 (idx_t)s.offset, s.height};
+        if (s.right > s.left && s.front > s.back) {
+            size_t last = (size_t)(s.offset + (ptrdiff_t)(s.ld * (s.right - 1) + (s.front - 1))) + 1;
+            if (last > need) need = last;
+        }
+    }
+    if (need > ncol) FAIL(PFEM_ERR_BAD_INPUT, "junction table too short: need %zu entries, got %zu", need, ncol);
+    ctx->nact = (int)njunc;
+    ctx->ncol = ncol;
+    if (njunc) {
+        TRY(dev_alloc(ctx, &ctx->act, njunc, 0));
+        CU(cudaMemcpyAsync(ctx->act, hj.data(), njunc * sizeof(JunctionDev), cudaMemcpyHostToDevice, ctx->stream));
+        TRY(dev_alloc(ctx, &ctx->junc_cond, 2 * ncol, 0));
+        TRY(dev_alloc(ctx, &ctx->beta_col, ncol, 0));
+        TRY(dev_alloc(ctx, &ctx->js_col, ncol, 0));
+        CU(cudaMemcpyAsync(ctx->junc_cond, junc_cond, 2 * ncol * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->beta_col, beta_col, ncol * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->js_col, js_col, ncol * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->pcond = pcond; ctx->ncond = ncond; ctx->stable = stable;
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->have_junctions = true;
+    ctx->conds_valid = false;
+    return PFEM_OK;
+}
+
+// ------------------------------------------------------------------ conductivities ------
+
+extern "C" int pfem_update_conductivity_thermal(pfem_ctx* ctx) {
+    NEED_MESH();
+    if (!ctx->have_materials) FAIL(PFEM_ERR_STATE, "pfem_set_materials has not been called");
+    const Grid& g = ctx->g;
+    k_cond_thermal<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->x, ctx->mat, ctx->nT, ctx->T0, ctx->dT,
+                                                                    ctx->tab_lat, ctx->tab_vert, ctx->cl, ctx->cv);
+    KCHECK(); LAUNCHED(1);
+    ctx->conds_valid = true;
+    return PFEM_OK;
+}
+
+extern "C" int pfem_update_conductivity_shockley(pfem_ctx* ctx) {
+    NEED_MESH();
+    if (!ctx->have_materials) FAIL(PFEM_ERR_STATE, "pfem_set_materials has not been called");
+    const Grid& g = ctx->g;
+    if (!ctx->Te) TRY(pfem_set_elem_temperature(ctx, nullptr, 300.));  // inTemperature = 300 (electr3d.cpp:35)
+    k_cond_shockley<<<node_grid(g), node_block(), 0, ctx->stream>>>(
+        g, ctx->mat, ctx->nact ? ctx->junc : nullptr, ctx->role, ctx->Te, ctx->nT, ctx->T0, ctx->dT, ctx->tab_lat,
+        ctx->tab_vert, ctx->act, ctx->junc_cond, ctx->pcond, ctx->ncond, ctx->cl, ctx->cv);
+    KCHECK(); LAUNCHED(1);
+    ctx->conds_valid = true;
+    return PFEM_OK;
+}
+
+extern "C" int pfem_set_conductivity(pfem_ctx* ctx, const double* cond) {
+    NEED_MESH();
+    if (!cond) FAIL(PFEM_ERR_BAD_INPUT, "null conductivity");
+    TRY(upload_elem<double, 2>(ctx, cond, ctx->cl, ctx->cv, nullptr));
+    ctx->conds_valid = true;
+    return PFEM_OK;
+}
+
+// ------------------------------------------------------------------------ PCG -----------
+
+__global__ void k_set_params(Scalars* sc, double tol2, int maxit, int bench) {
+    sc->tol2 = tol2; sc->maxit = maxit; sc->bench = bench;
+}
+__global__ void k_force_running(Scalars* sc) { sc->done = 0; sc->status = 0; }
+
+static int launch_diag(pfem_ctx* ctx) {
+    const Grid& g = ctx->g;
+    k_diag<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->cl, ctx->cv, ctx->fixed, ctx->dinv);
+    KCHECK(); LAUNCHED(1);
+    return PFEM_OK;
+}
+
+// out = M (f - A in) [MODE 1/2] or M A in [MODE 3]
+template <int MODE>
+static int launch_apply_simple(pfem_ctx* ctx, const double* in, double* out) {
+    const Grid& g = ctx->g;
+    k_apply_simple<MODE><<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->cl, ctx->cv, in, ctx->dinv, ctx->f, out,
+                                                                          ctx->d_sc, ctx->partials);
+    KCHECK(); LAUNCHED(1);
+    return PFEM_OK;
+}
+
+// one PCG iteration's kernels on ctx->stream; returns the number of kernels launched.
+// The tiled operator kernel reads p_old from one buffer and writes p_new to the other
+// (halo nodes of p_old are read by neighbouring CTAs), so `parity` = iteration & 1 picks them.
+static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t* ev /* 3 events or null */) {
+    const Grid& g = ctx->g;
+    int launched = 0;
+    const double* pin = parity ? ctx->p2 : ctx->p;
+    double* pout = parity ? ctx->p : ctx->p2;
+    const double* pnew = (variant == 1) ? ctx->p : pout;
+    if (ev) cudaEventRecord(ev[0], ctx->stream);
+    if (variant == 1) {
+        k_pupdate<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->r, ctx->dinv, ctx->p, ctx->d_sc);
+        k_apply_simple<0><<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->cl, ctx->cv, ctx->p, ctx->dinv, ctx->f,
+                                                                         ctx->q, ctx->d_sc, ctx->partials);
+        launched += 2;
+    } else {
+        launch_apply_tiled(ctx->plan, g, ctx->cl, ctx->cv, ctx->r, ctx->dinv, pin, pout, ctx->q, ctx->d_sc,
+                           ctx->partials, ctx->stream);
+        launched += 1;
+    }
+    if (ev) cudaEventRecord(ev[1], ctx->stream);
+    k_update<false><<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->x, ctx->r, pnew, ctx->q, ctx->dinv, ctx->d_sc,
+                                                               ctx->partials);
+    launched += 1;
+    if (ev) cudaEventRecord(ev[2], ctx->stream);
+    return launched;
+}
+
+static int kernels_per_iteration(int variant) { return variant == 1 ? 3 : 2; }
+
+static int build_graph(pfem_ctx* ctx, int batch, int variant, int precond) {
+    if (ctx->graph && ctx->graph_batch == batch && ctx->graph_variant == variant && ctx->graph_precond == precond)
+        return PFEM_OK;
+    if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    for (int it = 0; it < batch; ++it) launch_iteration(ctx, variant, it & 1, nullptr);
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    if (e != cudaSuccess) FAIL(PFEM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&ctx->graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { ctx->graph = nullptr; FAIL(PFEM_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
+    ctx->graph_batch = batch; ctx->graph_variant = variant; ctx->graph_precond = precond;
+    return PFEM_OK;
+}
+
+static int read_scalars(pfem_ctx* ctx) {
+    CU(cudaMemcpyAsync(ctx->h_sc, ctx->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+
+// Prepare the PCG state from the current x / conds: dinv, ||b_free||^2, r0, rho0.
+static int pcg_prepare(pfem_ctx* ctx, const pfem_opts* o, int bench) {
+    const Grid& g = ctx->g;
+    if (!ctx->conds_valid) FAIL(PFEM_ERR_STATE, "conductivities have not been computed");
+    double tol2 = bench ? -1. : o->lin_tol * o->lin_tol;
+    k_set_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, tol2, o->maxit, bench);
+    LAUNCHED(1);
+    TRY(launch_diag(ctx));
+    // ||b_free||^2 with b_free = M (f - A x_D): q <- x_D, p <- b_free (scratch)
+    k_dirichlet_only<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->x, ctx->fixed, ctx->q);
+    LAUNCHED(1);
+    TRY(launch_apply_simple<2>(ctx, ctx->q, ctx->p));
+    // r0 = M (f - A x)
+    TRY(launch_apply_simple<1>(ctx, ctx->x, ctx->r));
+    k_fill<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->p, 0.);
+    LAUNCHED(1);
+    k_update<true><<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->x, ctx->r, ctx->p, ctx->q, ctx->dinv, ctx->d_sc,
+                                                              ctx->partials);
+    LAUNCHED(1);
+    KCHECK();
+    return PFEM_OK;
+}
+
+static int pcg_solve(pfem_ctx* ctx, const pfem_opts* o, int* iters, double* relres, int* converged) {
+    TRY(pcg_prepare(ctx, o, 0));
+    int batch = o->batch > 0 ? o->batch : 32;
+    batch += batch & 1;  // even: p ping-pong parity is preserved across graph launches
+    TRY(build_graph(ctx, batch, o->variant, o->precond));
+    TRY(read_scalars(ctx));
+    while (!ctx->h_sc->done) {
+        CU(cudaGraphLaunch(ctx->graph, ctx->stream));
+        LAUNCHED((long long)batch * kernels_per_iteration(o->variant));
+        TRY(read_scalars(ctx));
+    }
+    const Scalars& s = *ctx->h_sc;
+    *iters = s.iter;
+    *relres = (s.bb > 0.) ? sqrt(s.rr / s.bb) : sqrt(s.rr);
+    ctx->last_relres_pre = (s.bz > 0.) ? sqrt(s.rho / s.bz) : sqrt(s.rho);
+    *converged = (s.status == 1);
+    if (s.status == -1) FAIL(PFEM_ERR_NOT_SPD, "p.Ap = %g <= 0 at iteration %d: stiffness matrix is not positive definite", s.pq, s.iter);
+    if (s.status == -2) FAIL(PFEM_ERR_NAN, "non-finite value in the PCG iteration %d", s.iter);
+    return PFEM_OK;
+}
+
+static int check_opts(pfem_ctx* ctx, const pfem_opts* o) {
+    if (!o) FAIL(PFEM_ERR_BAD_INPUT, "null options");
+    if (o->maxit <= 0) FAIL(PFEM_ERR_BAD_INPUT, "maxit must be positive");
+    if (!(o->lin_tol > 0.)) FAIL(PFEM_ERR_BAD_INPUT, "lin_tol must be positive");
+    if (o->precond != 0) FAIL(PFEM_ERR_BAD_INPUT, "preconditioner %d is not implemented", o->precond);
+    if (o->variant != 0 && o->variant != 1) FAIL(PFEM_ERR_BAD_INPUT, "unknown kernel variant %d", o->variant);
+    if (o->variant == 0 && !ctx->plan.valid) FAIL(PFEM_ERR_STATE, "no tiled kernel plan for this mesh");
+    return PFEM_OK;
+}
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t s;
+    explicit Timer(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
+    double stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+    ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+};
+
+extern "C" int pfem_solve_linear(pfem_ctx* ctx, const pfem_opts* o, pfem_stats* st) {
+    NEED_MESH();
+    TRY(check_opts(ctx, o));
+    long long l0 = ctx->launches;
+    Timer t(ctx->stream);
+    int iters = 0, conv = 0;
+    double relres = 0;
+    TRY(pcg_solve(ctx, o, &iters, &relres, &conv));
+    if (st) {
+        memset(st, 0, sizeof(*st));
+        st->lin_iters = st->last_iters = iters;
+        st->converged = conv; st->lin_relres = relres; st->loopno = ctx->loopno;
+        st->lin_relres_precond = ctx->last_relres_pre;
+        st->t_solve_ms = t.stop();
+        st->kernel_launches = ctx->launches - l0;
+    }
+    return conv ? PFEM_OK : PFEM_NOT_CONVERGED;
+}
+
+// ------------------------------------------------------------------ nonlinear loops -----
+
+extern "C" int pfem_solve_thermal(pfem_ctx* ctx, const pfem_opts* o, pfem_stats* st) {
+    NEED_MESH();
+    TRY(check_opts(ctx, o));
+    if (!ctx->have_materials) FAIL(PFEM_ERR_STATE, "pfem_set_materials has not been called");
+    const Grid& g = ctx->g;
+    long long l0 = ctx->launches;
+    Timer t(ctx->stream);
+    int loop = 0, conv = 1, iters = 0;
+    long long total_iters = 0;
+    double err = 0., toterr = 0., maxT = 0., relres = 0.;
+    const int cap = o->loops > 0 ? o->loops : 100000;
+    do {
+        CU(cudaMemcpyAsync(ctx->xprev, ctx->x, (size_t)g.N * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        TRY(pfem_update_conductivity_thermal(ctx));           // therm3d.cpp:204-220
+        TRY(pcg_solve(ctx, o, &iters, &relres, &conv));        // setMatrix + A.solve, :314-315
+        total_iters += iters;
+        k_thermal_error<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->x, ctx->xprev, ctx->d_sc, ctx->partials);
+        KCHECK(); LAUNCHED(1);
+        TRY(read_scalars(ctx));
+        err = ctx->h_sc->red[0];
+        maxT = ctx->h_sc->red[1];
+        if (err > toterr) toterr = err;
+        ++ctx->loopno;
+        ++loop;
+    } while ((!conv || err > o->outer_tol) && loop < cap);      // :334
+    if (st) {
+        memset(st, 0, sizeof(*st));
+        st->outer_loops = loop; st->loopno = ctx->loopno; st->lin_iters = total_iters; st->last_iters = iters;
+        st->converged = conv; st->lin_relres = relres; st->err = err; st->toterr = toterr; st->maxval = maxT;
+        st->lin_relres_precond = ctx->last_relres_pre;
+        st->t_solve_ms = t.stop();
+        st->kernel_launches = ctx->launches - l0;
+    }
+    return conv ? PFEM_OK : PFEM_NOT_CONVERGED;
+}
+
+extern "C" int pfem_solve_shockley(pfem_ctx* ctx, const pfem_opts* o, pfem_stats* st) {
+    NEED_MESH();
+    TRY(check_opts(ctx, o));
+    if (!ctx->have_materials) FAIL(PFEM_ERR_STATE, "pfem_set_materials has not been called");
+    const Grid& g = ctx->g;
+    TRY(ensure_elem_arrays(ctx, true));
+    long long l0 = ctx->launches;
+    Timer t(ctx->stream);
+    TRY(pfem_update_conductivity_shockley(ctx));               // loadConductivity, electr3d.cpp:378
+    const int noactive = (ctx->nact == 0);
+    const double minj = 100e-7;                                 // :381
+    int loop = 0, conv = 1, iters = 0;
+    long long total_iters = 0;
+    double err = 0., toterr = 0., mcur = 0., relres = 0.;
+    const int cap = o->loops > 0 ? o->loops : 100000;
+    do {
+        if (ctx->loopno != 0 && ctx->nact) {                    // :246-274
+            k_junction_update<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->junc, ctx->act, ctx->x, ctx->beta_col,
+                                                                               ctx->js_col, ctx->stable, ctx->cl, ctx->cv);
+            KCHECK(); LAUNCHED(1);
+        }
+        TRY(pcg_solve(ctx, o, &iters, &relres, &conv));        // assembly + applyBC + solve, :281-344,385
+        total_iters += iters;
+        k_currents<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->x, ctx->cl, ctx->cv, ctx->junc, noactive,
+                                                                    ctx->cur0, ctx->cur1, ctx->cur2, ctx->d_sc,
+                                                                    ctx->partials, ctx->partial_idx);
+        k_fetch_maxcur<<<1, 1, 0, ctx->stream>>>(g, ctx->cur0, ctx->cur1, ctx->cur2, ctx->d_sc);
+        KCHECK(); LAUNCHED(2);
+        TRY(read_scalars(ctx));
+        mcur = sqrt(ctx->h_sc->red[1]);
+        err = 100. * sqrt(ctx->h_sc->red[0]) / (mcur > minj ? mcur : minj);   // :423-424
+        if ((loop != 0 || mcur >= minj) && err > toterr) toterr = err;         // :425
+        ++ctx->loopno;
+        ++loop;
+    } while ((!conv || err > o->outer_tol) && loop < cap);      // :433
+    if (ctx->nact) {                                            // saveConductivity, :435
+        k_junction_save<<<64, 256, 0, ctx->stream>>>(g, ctx->act, ctx->nact, ctx->cl, ctx->cv, ctx->junc_cond);
+        KCHECK(); LAUNCHED(1);
+    }
+    if (st) {
+        memset(st, 0, sizeof(*st));
+        st->outer_loops = loop; st->loopno = ctx->loopno; st->lin_iters = total_iters; st->last_iters = iters;
+        st->converged = conv; st->lin_relres = relres; st->err = err; st->toterr = toterr; st->maxval = mcur;
+        st->lin_relres_precond = ctx->last_relres_pre;
+        for (int a = 0; a < 3; ++a) st->maxcur[a] = ctx->h_sc->maxcur[a];
+        st->t_solve_ms = t.stop();
+        st->kernel_launches = ctx->launches - l0;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return conv ? PFEM_OK : PFEM_NOT_CONVERGED;
+}
+
+// ------------------------------------------------------------------------ results -------
+
+extern "C" int pfem_get_field(pfem_ctx* ctx, double* x) {
+    NEED_MESH();
+    if (!x) FAIL(PFEM_ERR_BAD_INPUT, "null output");
+    CU(cudaMemcpyAsync(x, ctx->x, (size_t)ctx->g.N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+
+extern "C" int pfem_get_elem(pfem_ctx* ctx, int what, const uint8_t* noheat, double* out) {
+    NEED_MESH();
+    if (!out) FAIL(PFEM_ERR_BAD_INPUT, "null output");
+    const Grid& g = ctx->g;
+    switch (what) {
+        case PFEM_ELEM_COND:
+            if (!ctx->conds_valid) FAIL(PFEM_ERR_STATE, "conductivities have not been computed");
+            return download_elem<double, 2>(ctx, ctx->cl, ctx->cv, nullptr, out);
+        case PFEM_ELEM_CURRENT:
+            if (!ctx->cur0) FAIL(PFEM_ERR_STATE, "no current densities: pfem_solve_shockley has not run");
+            return download_elem<double, 3>(ctx, ctx->cur0, ctx->cur1, ctx->cur2, out);
+        case PFEM_ELEM_HEAT: {
+            if (!ctx->conds_valid) FAIL(PFEM_ERR_STATE, "conductivities have not been computed");
+            TRY(ensure_elem_arrays(ctx, false));
+            const uint8_t* nh = nullptr;
+            if (noheat) {
+                if (!ctx->noheat) TRY(dev_alloc(ctx, &ctx->noheat, (size_t)g.N, (size_t)g.G));
+                TRY(upload_elem<uint8_t, 1>(ctx, noheat, ctx->noheat, nullptr, nullptr));
+                nh = ctx->noheat;
+            }
+            k_gradient_fields<true><<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->x, ctx->cl, ctx->cv, nh, ctx->aux0,
+                                                                                     ctx->aux1, ctx->aux2);
+            KCHECK(); LAUNCHED(1);
+            return download_elem<double, 1>(ctx, ctx->aux0, nullptr, nullptr, out);
+        }
+        case PFEM_ELEM_FLUX: {
+            if (!ctx->have_materials) FAIL(PFEM_ERR_STATE, "pfem_set_materials has not been called");
+            TRY(ensure_elem_arrays(ctx, false));
+            // saveHeatFluxes re-evaluates thermk at the CURRENT temperatures (therm3d.cpp:362-370)
+            TRY(pfem_update_conductivity_thermal(ctx));
+            k_gradient_fields<false><<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->x, ctx->cl, ctx->cv, nullptr,
+                                                                                      ctx->aux0, ctx->aux1, ctx->aux2);
+            KCHECK(); LAUNCHED(1);
+            return download_elem<double, 3>(ctx, ctx->aux0, ctx->aux1, ctx->aux2, out);
+        }
+        default: FAIL(PFEM_ERR_BAD_INPUT, "unknown element field %d", what);
+    }
+}
+
+extern "C" int pfem_get_junction_cond(pfem_ctx* ctx, double* junc_cond) {
+    NEED_MESH();
+    if (!ctx->nact || !junc_cond) FAIL(PFEM_ERR_BAD_INPUT, "no junctions / null output");
+    CU(cudaMemcpyAsync(junc_cond, ctx->junc_cond, 2 * ctx->ncol * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+
+// ---------------------------------------------------------------- test / bench hooks ----
+
+extern "C" int pfem_apply(pfem_ctx* ctx, const double* p, double* q, int variant) {
+    NEED_MESH();
+    if (!p || !q) FAIL(PFEM_ERR_BAD_INPUT, "null vector");
+    if (!ctx->conds_valid) FAIL(PFEM_ERR_STATE, "conductivities have not been computed");
+    const Grid& g = ctx->g;
+    TRY(launch_diag(ctx));
+    // r <- p (as given), p <- M p, q <- M A M p, then q_D <- p_D
+    CU(cudaMemcpyAsync(ctx->r, p, (size_t)g.N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    k_fill<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->q, 0.);
+    k_select_fixed<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->fixed, ctx->q, ctx->r, ctx->p);
+    LAUNCHED(2);
+    if (variant == 1) {
+        TRY(launch_apply_simple<3>(ctx, ctx->p, ctx->q));
+    } else {
+        if (!ctx->plan.valid) FAIL(PFEM_ERR_STATE, "no tiled kernel plan for this mesh");
+        launch_apply_tiled_plain(ctx->plan, g, ctx->cl, ctx->cv, ctx->dinv, ctx->p, ctx->q, ctx->stream);
+        KCHECK(); LAUNCHED(1);
+    }
+    k_select_fixed<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->fixed, ctx->r, ctx->q, ctx->q);
+    KCHECK(); LAUNCHED(1);
+    CU(cudaMemcpyAsync(q, ctx->q, (size_t)g.N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+
+extern "C" int pfem_get_rhs(pfem_ctx* ctx, double* b) {
+    NEED_MESH();
+    if (!b) FAIL(PFEM_ERR_BAD_INPUT, "null output");
+    if (!ctx->conds_valid) FAIL(PFEM_ERR_STATE, "conductivities have not been computed");
+    const Grid& g = ctx->g;
+    TRY(launch_diag(ctx));
+    k_dirichlet_only<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->x, ctx->fixed, ctx->q);
+    LAUNCHED(1);
+    TRY(launch_apply_simple<1>(ctx, ctx->q, ctx->p));
+    k_select_fixed<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->fixed, ctx->x, ctx->p, ctx->p);
+    KCHECK(); LAUNCHED(1);
+    CU(cudaMemcpyAsync(b, ctx->p, (size_t)g.N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+
+extern "C" int pfem_get_diag(pfem_ctx* ctx, double* d) {
+    NEED_MESH();
+    if (!d) FAIL(PFEM_ERR_BAD_INPUT, "null output");
+    if (!ctx->conds_valid) FAIL(PFEM_ERR_STATE, "conductivities have not been computed");
+    const Grid& g = ctx->g;
+    TRY(launch_diag(ctx));
+    k_diag_from_dinv<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->dinv, ctx->fixed, ctx->q);
+    KCHECK(); LAUNCHED(1);
+    CU(cudaMemcpyAsync(d, ctx->q, (size_t)g.N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+
+extern "C" int pfem_bench_pcg(pfem_ctx* ctx, const pfem_opts* o, int iters, int split_timing, double* ms, double* apply_ms,
+                              double* update_ms, long long* launches) {
+    NEED_MESH();
+    TRY(check_opts(ctx, o));
+    if (iters <= 0) FAIL(PFEM_ERR_BAD_INPUT, "iters must be positive");
+    long long l0 = ctx->launches;
+    TRY(pcg_prepare(ctx, o, 1));
+    CU(cudaStreamSynchronize(ctx->stream));
+    l0 = ctx->launches;
+    double t_apply = 0., t_update = 0., t_total = 0.;
+    if (split_timing) {
+        std::vector<cudaEvent_t> ev((size_t)iters * 3);
+        for (auto& e : ev) CU(cudaEventCreate(&e));
+        for (int it = 0; it < iters; ++it) LAUNCHED(launch_iteration(ctx, o->variant, it & 1, &ev[(size_t)it * 3]));
+        KCHECK();
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (int it = 0; it < iters; ++it) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, ev[(size_t)it * 3], ev[(size_t)it * 3 + 1]);
+            cudaEventElapsedTime(&b, ev[(size_t)it * 3 + 1], ev[(size_t)it * 3 + 2]);
+            t_apply += a; t_update += b;
+        }
+        float tot = 0;
+        cudaEventElapsedTime(&tot, ev[0], ev[(size_t)iters * 3 - 1]);
+        t_total = tot;
+        for (auto& e : ev) cudaEventDestroy(e);
+    } else {
+        int batch = o->batch > 0 ? o->batch : 32;
+        batch += batch & 1;
+        if (batch > iters) batch = iters & ~1;
+        if (batch < 2) batch = 2;
+        TRY(build_graph(ctx, batch, o->variant, o->precond));
+        Timer t(ctx->stream);
+        int done = 0;
+        while (done + batch <= iters) {
+            CU(cudaGraphLaunch(ctx->graph, ctx->stream));
+            LAUNCHED((long long)batch * kernels_per_iteration(o->variant));
+            done += batch;
+        }
+        for (; done < iters; ++done) LAUNCHED(launch_iteration(ctx, o->variant, done & 1, nullptr));
+        KCHECK();
+        t_total = t.stop();
+    }
+    TRY(read_scalars(ctx));
+    k_set_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, o->lin_tol * o->lin_tol, o->maxit, 0);
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_sc->iter != iters) FAIL(PFEM_ERR_CUDA, "benchmark ran %d iterations instead of %d", ctx->h_sc->iter, iters);
+    if (ms) *ms = t_total;
+    if (apply_ms) *apply_ms = t_apply;
+    if (update_ms) *update_ms = t_update;
+    if (launches) *launches = ctx->launches - l0;
+    return PFEM_OK;
+}

@@ -1,0 +1,184 @@
+"""DeviceFem — thin object wrapper over one pfem_ctx (one CUDA device, one mesh).
+
+This is the level at which the PLaSK solver plugin would talk to the library (see
+INTEGRATION.md); `plask_b200.solvers` builds the Static3D / Shockley3D mirrors on top of it.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _dp(a):
+    return a.ctypes.data_as(L.c_dp)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class DeviceFem:
+    def __init__(self, device=0):
+        self.lib = L.load()
+        self.ctx = L._vp()
+        rc = self.lib.pfem_create(C.byref(self.ctx), int(device))
+        if rc != 0:
+            self.ctx = None
+            L.check(None, rc)
+        self.N = self.E = 0
+        self.ncol = 0
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.pfem_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        return L.check(self.ctx, rc)
+
+    # ---- problem description
+    def set_mesh(self, axes, strides):
+        ax = [_f64(a) for a in axes]
+        n = (L.c_sz * 3)(*[len(a) for a in ax])
+        s = (L.c_sz * 3)(*[int(v) for v in strides])
+        self._ck(self.lib.pfem_set_mesh(self.ctx, n, _dp(ax[0]), _dp(ax[1]), _dp(ax[2]), s))
+        self.n = tuple(len(a) for a in ax)
+        self.N = self.n[0] * self.n[1] * self.n[2]
+        self.E = (self.n[0] - 1) * (self.n[1] - 1) * (self.n[2] - 1)
+
+    def set_materials(self, elem_mat, T0, dT, c_lat, c_vert):
+        m = np.ascontiguousarray(elem_mat, dtype=np.uint32)
+        a, b = _f64(c_lat), _f64(c_vert)
+        assert m.size == self.E and a.shape == b.shape and a.ndim == 2
+        self._ck(self.lib.pfem_set_materials(self.ctx, m.ctypes.data_as(L._u32p), a.shape[0], float(T0), float(dT),
+                                             a.shape[1], _dp(a), _dp(b)))
+
+    def set_dirichlet(self, nodes, values):
+        n = np.ascontiguousarray(nodes, dtype=np.uintp)
+        v = _f64(values)
+        assert n.size == v.size
+        self._ck(self.lib.pfem_set_dirichlet(self.ctx, n.size, n.ctypes.data_as(L._szp), _dp(v)))
+
+    def set_source(self, heat):
+        if heat is None:
+            self._ck(self.lib.pfem_set_source(self.ctx, None))
+        else:
+            h = _f64(heat)
+            assert h.size == self.E
+            self._ck(self.lib.pfem_set_source(self.ctx, _dp(h)))
+
+    def set_field(self, x):
+        if np.isscalar(x):
+            self._ck(self.lib.pfem_fill_field(self.ctx, float(x)))
+        else:
+            x = _f64(x)
+            assert x.size == self.N
+            self._ck(self.lib.pfem_set_field(self.ctx, _dp(x)))
+
+    def set_elem_temperature(self, Te):
+        if np.isscalar(Te):
+            self._ck(self.lib.pfem_set_elem_temperature(self.ctx, None, float(Te)))
+        else:
+            t = _f64(Te)
+            assert t.size == self.E
+            self._ck(self.lib.pfem_set_elem_temperature(self.ctx, _dp(t), 0.))
+
+    def set_junctions(self, junctions, elem_junc, elem_role, pcond, ncond, junc_cond, beta_col, js_col, stable=False):
+        nj = len(junctions)
+        arr = (L.Junction * max(nj, 1))()
+        for k, j in enumerate(junctions):
+            for name in ("bottom", "top", "left", "right", "back", "front", "ld", "offset", "height"):
+                setattr(arr[k], name, getattr(j, name) if not isinstance(j, dict) else j[name])
+        ej = np.ascontiguousarray(elem_junc, dtype=np.uint32)
+        er = None if elem_role is None else np.ascontiguousarray(elem_role, dtype=np.uint8)
+        jc, bc, jsn = _f64(junc_cond), _f64(beta_col), _f64(js_col)
+        self.ncol = bc.size
+        assert jc.size == 2 * self.ncol and jsn.size == self.ncol
+        self._ck(self.lib.pfem_set_junctions(self.ctx, nj, arr, ej.ctypes.data_as(L._u32p),
+                                             er.ctypes.data_as(L._u8p) if er is not None else None, float(pcond),
+                                             float(ncond), self.ncol, _dp(jc), _dp(bc), _dp(jsn), int(bool(stable))))
+
+    # ---- solve
+    def opts(self, **kw):
+        o = L.Opts()
+        self.lib.pfem_default_opts(C.byref(o))
+        for k, v in kw.items():
+            if not hasattr(o, k):
+                raise BadInput(f"unknown option {k}")
+            setattr(o, k, v)
+        return o
+
+    def solve_thermal(self, **kw):
+        o, st = self.opts(**kw), L.Stats()
+        rc = self._ck(self.lib.pfem_solve_thermal(self.ctx, C.byref(o), C.byref(st)))
+        return rc, st.as_dict()
+
+    def solve_shockley(self, **kw):
+        o, st = self.opts(**kw), L.Stats()
+        rc = self._ck(self.lib.pfem_solve_shockley(self.ctx, C.byref(o), C.byref(st)))
+        return rc, st.as_dict()
+
+    def solve_linear(self, **kw):
+        o, st = self.opts(**kw), L.Stats()
+        rc = self._ck(self.lib.pfem_solve_linear(self.ctx, C.byref(o), C.byref(st)))
+        return rc, st.as_dict()
+
+    def bench_pcg(self, iters, split_timing=False, **kw):
+        o = self.opts(**kw)
+        ms, a, u, n = C.c_double(0), C.c_double(0), C.c_double(0), C.c_longlong(0)
+        self._ck(self.lib.pfem_bench_pcg(self.ctx, C.byref(o), int(iters), int(split_timing), C.byref(ms), C.byref(a),
+                                         C.byref(u), C.byref(n)))
+        return dict(ms=ms.value, apply_ms=a.value, update_ms=u.value, launches=n.value)
+
+    # ---- results
+    def get_field(self):
+        x = np.empty(self.N)
+        self._ck(self.lib.pfem_get_field(self.ctx, _dp(x)))
+        return x
+
+    def get_elem(self, what, noheat=None):
+        nc = {L.ELEM_COND: 2, L.ELEM_CURRENT: 3, L.ELEM_HEAT: 1, L.ELEM_FLUX: 3}[what]
+        out = np.empty((self.E, nc))
+        nh = None if noheat is None else np.ascontiguousarray(noheat, dtype=np.uint8)
+        self._ck(self.lib.pfem_get_elem(self.ctx, what, nh.ctypes.data_as(L._u8p) if nh is not None else None, _dp(out)))
+        return out[:, 0] if nc == 1 else out
+
+    def get_junction_cond(self):
+        out = np.empty((self.ncol, 2))
+        self._ck(self.lib.pfem_get_junction_cond(self.ctx, _dp(out)))
+        return out
+
+    # ---- building blocks (tests / bench)
+    def update_conductivity_thermal(self):
+        self._ck(self.lib.pfem_update_conductivity_thermal(self.ctx))
+
+    def update_conductivity_shockley(self):
+        self._ck(self.lib.pfem_update_conductivity_shockley(self.ctx))
+
+    def set_conductivity(self, cond):
+        c = _f64(cond)
+        assert c.size == 2 * self.E
+        self._ck(self.lib.pfem_set_conductivity(self.ctx, _dp(c)))
+
+    def apply(self, p, variant=0):
+        p = _f64(p)
+        q = np.empty(self.N)
+        self._ck(self.lib.pfem_apply(self.ctx, _dp(p), _dp(q), int(variant)))
+        return q
+
+    def get_rhs(self):
+        b = np.empty(self.N)
+        self._ck(self.lib.pfem_get_rhs(self.ctx, _dp(b)))
+        return b
+
+    def get_diag(self):
+        d = np.empty(self.N)
+        self._ck(self.lib.pfem_get_diag(self.ctx, _dp(d)))
+        return d

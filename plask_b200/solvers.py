@@ -1,0 +1,283 @@
+"""Host-side mirror of the reference's solver interface for the CUDA algorithm.
+
+`Static3D` and `Shockley3D` keep the names, defaults and semantics of
+thermal.static.Static3D (solvers/thermal/static/therm3d.{hpp,cpp}, python/therm_python.cpp)
+and electrical.shockley.Shockley3D (solvers/electrical/shockley/electr3d.{hpp,cpp}, beta.hpp,
+python/electr_python.cpp): `compute(loops)`, `maxerr`, `inittemp`, `algorithm`, `iterative.*`,
+`beta`/`js`, `pcond`/`ncond`, `convergence`, `inHeat`, `inTemperature`, `outTemperature`,
+`outHeatFlux`, `outVoltage`, `outCurrentDensity`, `outHeat`, `get_total_current()` ...
+What differs is only where the geometry comes from: PLaSK's geometry tree is out of scope
+(SURVEY.md §2.2), so a solver is bound to a `configs.Problem`, the flat arrays the plugin
+extracts from geometry/mesh/materials.
+
+`algorithm` must be 'cuda' — the new FemMatrixAlgorithm value; there is no CPU path here.
+"""
+import numpy as np
+
+from . import _lib as L
+from .configs import Problem, setup_active
+from .fem import DeviceFem
+
+
+class IterativeParams:
+    """iter_params of FemSolverWithMesh (plask/common/fem/iterative_matrix.hpp:25-94), the subset
+    that has a meaning for the CUDA algorithm."""
+
+    def __init__(self):
+        self.maxit = 10000          # maxit
+        self.maxerr = 1e-8          # here: relative residual ||r||/||b_free|| (north-star tolerance)
+        self.preconditioner = "jac"
+        self.accelerator = "cg"
+        self.noconv = "warning"     # 'error' | 'warning' | 'continue'  (:88-89)
+        # outputs (:90-93)
+        self.converged = True
+        self.iters = 0
+        self.err = 0.
+
+
+class _FemSolver:
+    def __init__(self, name=""):
+        self.id = name
+        self.algorithm = "cuda"
+        self.iterative = IterativeParams()
+        self.device = 0
+        self.variant = 0            # 0 production kernels, 1 simple reference kernels
+        self._fem = None
+        self._problem = None
+        self.initialized = False
+        self.log = []
+        self.stats = None
+
+    # geometry + mesh + materials, flattened
+    @property
+    def problem(self):
+        return self._problem
+
+    @problem.setter
+    def problem(self, p):
+        assert isinstance(p, Problem)
+        self._problem = p
+        self.invalidate()
+
+    def invalidate(self):
+        """Solver::invalidate -> onInvalidate (therm3d.cpp:118-122, electr3d.cpp:195-201): drops the
+        fields and the device state."""
+        if self._fem is not None:
+            self._fem.close()
+        self._fem = None
+        self.initialized = False
+
+    def _opts(self, loops, outer_tol):
+        if self.algorithm != "cuda":
+            raise L.BadInput(f"{self.id}: algorithm '{self.algorithm}' is not provided by plask_b200 "
+                             "(cholesky/gauss/iterative live in the reference); use 'cuda'")
+        pre = {"jac": 0}.get(self.iterative.preconditioner)
+        if pre is None or self.iterative.accelerator != "cg":
+            raise L.BadInput(f"{self.id}: the CUDA algorithm implements accelerator 'cg' with preconditioner 'jac'")
+        return dict(maxit=int(self.iterative.maxit), lin_tol=float(self.iterative.maxerr), precond=pre,
+                    outer_tol=float(outer_tol), loops=int(loops), variant=int(self.variant))
+
+    def _after(self, rc, st):
+        self.stats = st
+        it = self.iterative
+        it.converged, it.iters, it.err = st["converged"], st["last_iters"], st["lin_relres"]
+        if rc == L.PFEM_NOT_CONVERGED:
+            msg = f"Failed to converge in {it.maxit} iterations (error {it.err})"
+            if it.noconv == "error":
+                raise L.ComputationError(f"{self.id}: {msg}")
+            self.log.append(("warning" if it.noconv == "warning" else "detail", msg))
+
+
+class Static3D(_FemSolver):
+    """thermal.static.Static3D with algorithm='cuda'."""
+
+    def __init__(self, name=""):
+        super().__init__(name)
+        self.inittemp = 300.     # therm3d.cpp:23
+        self.maxerr = 0.05       # therm3d.cpp:24
+        self.inHeat = None       # None -> problem.heat; scalar or [E] array (W/m3)
+        self.maxT = 0.
+        self.loopno = 0
+
+    def initialize(self):
+        p = self._problem
+        if p is None:
+            raise L.BadInput(f"{self.id}: no geometry/mesh (problem) specified")
+        f = self._fem = DeviceFem(self.device)
+        f.set_mesh(p.axes, p.strides)
+        f.set_materials(p.elem_mat, p.T0, p.dT, p.tab_lat, p.tab_vert)
+        f.set_field(float(self.inittemp))               # temperatures.reset(size, inittemp), :79
+        f.set_dirichlet(p.bc_nodes, p.bc_values)
+        self.loopno = 0
+        self.initialized = True
+
+    def compute(self, loops=0):
+        """ThermalFem3DSolver::compute (therm3d.cpp:281-340); returns the max loop error."""
+        if not self.initialized:
+            self.initialize()
+        f, p = self._fem, self._problem
+        heat = p.heat if self.inHeat is None else self.inHeat
+        if heat is not None and np.isscalar(heat):
+            heat = np.full(p.E, float(heat))
+        f.set_source(heat)
+        rc, st = f.solve_thermal(**self._opts(loops, self.maxerr))
+        self._after(rc, st)
+        self.maxT, self.loopno = st["maxval"], st["loopno"]
+        self.log.append(("result", f"Loop {st['outer_loops']}({self.loopno}): max(T) = {self.maxT:.3f} K, "
+                                   f"error = {st['err']:g} K"))
+        return st["toterr"]
+
+    # providers, on the solver's own mesh (interpolation onto other meshes is a "next" row)
+    def outTemperature(self):
+        if not self.initialized:
+            return np.full(self._problem.N, float(self.inittemp))
+        return self._fem.get_field()
+
+    def outHeatFlux(self):
+        return self._fem.get_elem(L.ELEM_FLUX)
+
+    def outThermalConductivity(self):
+        self._fem.update_conductivity_thermal()
+        return self._fem.get_elem(L.ELEM_COND)
+
+
+class Shockley3D(_FemSolver):
+    """electrical.shockley.Shockley3D with algorithm='cuda'."""
+
+    def __init__(self, name=""):
+        super().__init__(name)
+        self.maxerr = 0.05           # electr3d.cpp:26
+        self.pcond, self.ncond = 5., 50.   # :22-23
+        self.start_cond = (0., 5.)   # default_junction_conductivity, :25
+        self.convergence = "fast"    # :31
+        self.beta = None             # float | callable(T) | list per junction  (beta.hpp, electr_python.cpp)
+        self.js = None
+        self.inTemperature = 300.    # scalar or [E] array
+        self.loopno = 0
+        self.maxcur = (0., 0., 0.)
+        self._acts, self._ncol = [], 0
+        self._junc_cond = None
+
+    def initialize(self):
+        p = self._problem
+        if p is None:
+            raise L.BadInput(f"{self.id}: no geometry/mesh (problem) specified")
+        if self.beta is None:
+            self.beta = p.beta
+        if self.js is None:
+            self.js = p.js
+        f = self._fem = DeviceFem(self.device)
+        f.set_mesh(p.axes, p.strides)
+        f.set_materials(p.elem_mat, p.T0, p.dT, p.tab_lat, p.tab_vert)
+        f.set_field(0.)                                  # potential.reset(size, 0.), electr3d.cpp:190
+        f.set_dirichlet(p.bc_nodes, p.bc_values)
+        f.set_source(None)
+        self._acts, self._ncol = setup_active(p)         # setupActiveRegions, :89-183
+        if self._junc_cond is None or len(self._junc_cond) != max(self._ncol, 1):
+            self._junc_cond = np.tile(np.asarray(self.start_cond, dtype=np.float64), (max(self._ncol, 1), 1))
+        self.loopno = 0
+        self.initialized = True
+
+    def invalidate(self):
+        super().invalidate()
+        self._junc_cond = None      # junction_conductivity.reset(1, default), :200
+
+    def _per_junction(self, v, k):
+        return v[k] if isinstance(v, (list, tuple)) else v
+
+    def _junction_params(self, Te):
+        """beta(T), js(T) per junction-table entry at the mid-plane element temperature."""
+        p = self._problem
+        es = p.estrides
+        n = max(self._ncol, 1)
+        bcol, jcol = np.ones(n), np.ones(n)
+        for k, a in enumerate(self._acts):
+            b, j = self._per_junction(self.beta, k), self._per_junction(self.js, k)
+            if b is None:
+                raise L.BadInput(f"{self.id}: no beta given for junction {k}")
+            v = (a["top"] + a["bottom"]) // 2
+            t = np.arange(a["left"], a["right"])[:, None]
+            l = np.arange(a["back"], a["front"])[None, :]
+            col = (a["offset"] + a["ld"] * t + l).ravel()
+            e = (l * es[0] + t * es[1] + v * es[2]).ravel()
+            T = np.full(e.size, float(Te)) if np.isscalar(Te) else np.asarray(Te)[e]
+            bcol[col] = np.vectorize(b)(T) if callable(b) else b
+            jcol[col] = np.vectorize(j)(T) if callable(j) else j
+        return bcol, jcol
+
+    def compute(self, loops=0):
+        """ElectricalFem3DSolver::compute (electr3d.cpp:356-442)."""
+        if not self.initialized:
+            self.initialize()
+        f, p = self._fem, self._problem
+        Te = self.inTemperature
+        f.set_elem_temperature(Te if np.isscalar(Te) else np.asarray(Te, dtype=np.float64))
+        bcol, jcol = self._junction_params(Te)
+        f.set_junctions(self._acts, p.elem_junc if p.elem_junc is not None else np.zeros(p.E, np.uint32),
+                        p.elem_role, self.pcond, self.ncond, self._junc_cond, bcol, jcol,
+                        stable=(self.convergence == "stable"))
+        rc, st = f.solve_shockley(**self._opts(loops, self.maxerr))
+        self._after(rc, st)
+        self.loopno, self.maxcur = st["loopno"], st["maxcur"]
+        if self._ncol:
+            self._junc_cond = f.get_junction_cond()      # saveConductivity, :227-237
+        self.log.append(("result", f"Loop {st['outer_loops']}({self.loopno}): max(j@junc) = {st['maxval']:g} kA/cm2, "
+                                   f"error = {st['err']:g}%"))
+        return st["toterr"]
+
+    # providers on the solver's own meshes
+    def outVoltage(self):
+        return self._fem.get_field()
+
+    def outCurrentDensity(self):
+        return self._fem.get_elem(L.ELEM_CURRENT)
+
+    def outHeat(self):
+        return self._fem.get_elem(L.ELEM_HEAT, self._problem.noheat)
+
+    def outConductivity(self):
+        if not self.initialized:
+            self.initialize()
+            f = self._fem
+            f.set_elem_temperature(self.inTemperature)
+            bcol, jcol = self._junction_params(self.inTemperature)
+            f.set_junctions(self._acts, self._problem.elem_junc if self._problem.elem_junc is not None
+                            else np.zeros(self._problem.E, np.uint32), self._problem.elem_role, self.pcond, self.ncond,
+                            self._junc_cond, bcol, jcol, stable=(self.convergence == "stable"))
+        self._fem.update_conductivity_shockley()
+        return self._fem.get_elem(L.ELEM_COND)
+
+    def _elem_sizes(self):
+        p = self._problem
+        d = [np.diff(a) for a in p.axes]
+        return d
+
+    def integrate_current(self, vindex, onlyactive=False):
+        """integrateCurrent (electr3d.cpp:480-497), mA."""
+        p = self._problem
+        cur = self.outCurrentDensity()
+        es = p.estrides
+        d = self._elem_sizes()
+        i0 = np.arange(p.n[0] - 1)[:, None]
+        i1 = np.arange(p.n[1] - 1)[None, :]
+        e = i0 * es[0] + i1 * es[1] + vindex * es[2]
+        w = d[0][:, None] * d[1][None, :]
+        jz = cur[e, 2]
+        if onlyactive:
+            jz = np.where(p.elem_junc[e] > 0, jz, 0.)
+        return float((jz * w).sum() * 0.01)
+
+    def get_total_current(self, nact=0):
+        """getTotalCurrent (electr3d.cpp:499-505)."""
+        if nact >= len(self._acts):
+            raise L.BadInput(f"{self.id}: wrong active region number")
+        a = self._acts[nact]
+        return self.integrate_current((a["bottom"] + a["top"]) // 2, True)
+
+    def get_total_heat(self):
+        """getTotalHeat (electr3d.cpp:612-624), mW."""
+        p = self._problem
+        heat = self.outHeat()
+        d = self._elem_sizes()
+        vol = d[0][:, None, None] * d[1][None, :, None] * d[2][None, None, :]
+        return float((1e-15 * vol * heat[p.elem_index_grid()]).sum())

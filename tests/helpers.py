@@ -1,0 +1,90 @@
+"""Shared test helpers: build the CPU oracle objects from a plask_b200.configs.Problem."""
+import numpy as np
+
+from oracle import oracle as orc
+from plask_b200 import configs as cf
+
+
+def oracle_mesh(p):
+    return orc.Mesh(p.axes[0], p.axes[1], p.axes[2], p.order)
+
+
+def oracle_thermal(p, **kw):
+    m = oracle_mesh(p)
+    tb = orc.Tables(p.T0, p.dT, p.tab_lat, p.tab_vert)
+    return orc.Static3DOracle(m, p.elem_mat, tb, p.bc_nodes, p.bc_values, heat=p.heat, inittemp=p.inittemp,
+                              maxerr=p.maxerr, **kw)
+
+
+def oracle_shockley(p, **kw):
+    m = oracle_mesh(p)
+    tb = orc.Tables(p.T0, p.dT, p.tab_lat, p.tab_vert)
+    kw.setdefault("beta", p.beta)
+    kw.setdefault("js", p.js)
+    kw.setdefault("maxerr", p.maxerr)
+    return orc.Shockley3DOracle(m, p.elem_mat, tb, p.bc_nodes, p.bc_values, elem_junc=p.elem_junc,
+                                elem_role=p.elem_role, pcond=p.pcond, ncond=p.ncond, start_cond=p.start_cond,
+                                noheat=p.noheat, **kw)
+
+
+def random_problem(n, order, seed=20261017, nd_frac=0.08, kind="thermal"):
+    """Small mesh with jittered spacings, log-uniform conductivities per element (via one material id
+    per element would be huge; use 5 ids with anisotropic tables) and a random Dirichlet set."""
+    rng = np.random.default_rng(seed)
+    axes = []
+    for k in n:
+        h = 1. + 0.4 * (rng.random(k - 1) - 0.5)
+        h *= 10. ** rng.uniform(-1.5, 0.5)
+        axes.append(np.concatenate([[0.], np.cumsum(h)]))
+    nmat, nT = 5, 41
+    T0, dT = 250., 10.
+    base = 10. ** rng.uniform(-1, 2.6, size=(nmat, 1))
+    T = T0 + dT * np.arange(nT)
+    lat = base * (300. / T) ** rng.uniform(0., 1.5, size=(nmat, 1))
+    vert = lat * 10. ** rng.uniform(-0.5, 0.5, size=(nmat, 1))
+    p = cf.Problem("rand", kind, axes, order, None, T0, dT, lat, vert, None, None)
+    p.elem_mat = rng.integers(0, nmat, size=p.E).astype(np.uint32)
+    N = p.N
+    nd = max(1, int(nd_frac * N))
+    nodes = rng.choice(N, size=nd, replace=False)
+    p.bc_nodes = nodes.astype(np.uintp)
+    p.bc_values = rng.uniform(290., 310., size=nd)
+    p.heat = 10. ** rng.uniform(12, 16, size=p.E)
+    return p
+
+
+def shockley3d_reference_problem(order="optimal"):
+    """The structure of solvers/electrical/shockley/tests/shockley3d.py:36-60 as a Problem
+    (same arrays as tests/test_oracle_pin.py::shockley3d_reference_case)."""
+    def divide(edges, k):
+        out = [edges[0]]
+        for a, b in zip(edges[:-1], edges[1:]):
+            out += [a + (b - a) * (i + 1) / k for i in range(k)]
+        return np.array(out)
+
+    x = divide([-500., -350., 350., 500.], 3)
+    z = divide([0., 1., 301., 301.02, 601.02, 602.02], 2)
+    n = (len(x), len(x), len(z))
+    if order == "optimal":
+        order = cf.optimal_order(n)
+    gaas_cond = 1e2 * 1.60217733e-19 * 8000. * 1e16
+    sig = np.array([[1e9, 1e9], [gaas_cond, gaas_cond], [0.55e-14, 0.55e-14]])
+    p = cf.Problem("shockley3d.py", "shockley", [x, x.copy(), z], order, None, 300., 100., sig, sig.copy(), None, None)
+    xm, zm = 0.5 * (x[1:] + x[:-1]), 0.5 * (z[1:] + z[:-1])
+    X, Y, Z = np.meshgrid(xm, xm, zm, indexing="ij")
+    mat = np.zeros(X.shape, dtype=np.uint32)
+    mat[((Z < 1.) | (Z > 601.02)) & ((np.abs(X) > 350.) | (np.abs(Y) > 350.))] = 2
+    is_j = (Z > 301.) & (Z < 301.02)
+    mat[is_j] = 1
+    p.elem_mat = p.to_elem_order(mat, np.uint32)
+    p.elem_junc = p.to_elem_order(is_j.astype(np.uint32), np.uint32)
+    p.noheat = (p.elem_mat == 2).astype(np.uint8)
+    p.meta["eps"] = np.array([1., 12.9, 1.])[p.elem_mat]
+    ng = np.broadcast_to(p.node_index_grid(), n)
+    Xn, Yn = np.meshgrid(x, x, indexing="ij")
+    inc = (np.abs(Xn) <= 350. + 1e-9) & (np.abs(Yn) <= 350. + 1e-9)
+    top, bot = ng[:, :, -1][inc], ng[:, :, 0][inc]
+    p.bc_nodes = np.concatenate([top, bot]).astype(np.uintp)
+    p.bc_values = np.concatenate([np.zeros(top.size), np.ones(bot.size)])
+    p.beta, p.js, p.maxerr = 10., 1., 1e-3
+    return p

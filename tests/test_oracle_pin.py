@@ -1,0 +1,102 @@
+"""Pin the CPU oracle against the only results the reference's own tests hold for this path:
+solvers/electrical/shockley/tests/shockley3d.py:36-83 (analytic current, capacitance, heat)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+
+def shockley3d_reference_case(order="optimal"):
+    """The structure of shockley3d.py:36-60 restated as flat arrays.
+
+    Stack from the bottom: contact 700x700x1, conductor 1000x1000x300, GaAs junction 0.02
+    (role 'active'), conductor 300, contact 700x700x1; DivideGenerator(prediv=(3,3,2),
+    gradual=False) splits every geometry interval into 3,3,2 equal parts.
+    Material ids: 0 = Conductor (cond 1e9, eps 1), 1 = GaAs (junction), 2 = air.
+    """
+    def divide(edges, k):
+        out = [edges[0]]
+        for a, b in zip(edges[:-1], edges[1:]):
+            out += [a + (b - a) * (i + 1) / k for i in range(k)]
+        return np.array(out)
+
+    x = divide([-500., -350., 350., 500.], 3)
+    z = divide([0., 1., 301., 301.02, 601.02, 602.02], 2)
+    mesh = orc.Mesh(x, x.copy(), z, order)
+    xm, zm = 0.5 * (x[1:] + x[:-1]), 0.5 * (z[1:] + z[:-1])
+    X, Y, Z = np.meshgrid(xm, xm, zm, indexing="ij")
+    mat = np.zeros(X.shape, dtype=np.uint32)
+    junc = np.zeros(X.shape, dtype=np.uint32)
+    in_contact_layer = (Z < 1.) | (Z > 601.02)
+    outside = (np.abs(X) > 350.) | (np.abs(Y) > 350.)
+    mat[in_contact_layer & outside] = 2
+    is_j = (Z > 301.) & (Z < 301.02)
+    mat[is_j] = 1
+    junc[is_j] = 1
+    eg = mesh.elems_grid()
+    elem_mat = np.zeros(mesh.E, dtype=np.uint32); elem_mat[eg.ravel()] = mat.ravel()
+    elem_junc = np.zeros(mesh.E, dtype=np.uint32); elem_junc[eg.ravel()] = junc.ravel()
+    gaas_cond = 1e2 * 1.60217733e-19 * 8000. * 1e16  # GaAs.cpp:234-237 at 300 K (unused: junction)
+    sig = np.array([[1e9, 1e9], [gaas_cond, gaas_cond], [0.55e-14, 0.55e-14]])  # air.cpp:43-46
+    tables = orc.Tables(300., 100., sig, sig)
+    eps = np.array([1., 12.9, 1.])[elem_mat]  # GaAs.cpp:299-301; Conductor eps = 1 (shockley3d.py:31-32)
+    noheat = (elem_mat == 2).astype(np.uint8)  # Material::EMPTY, electr3d.cpp:472
+    ng = mesh.nodes_grid()
+    Xn, Yn = np.meshgrid(x, x, indexing="ij")
+    inc = (np.abs(Xn) <= 350. + 1e-9) & (np.abs(Yn) <= 350. + 1e-9)
+    top_nodes = ng[:, :, -1][inc]
+    bot_nodes = ng[:, :, 0][inc]
+    # voltage_boundary: TopOf(contact, top) = 0 V first, BottomOf(contact, bottom) = 1 V second
+    nodes = np.concatenate([top_nodes, bot_nodes]).astype(np.uintp)
+    values = np.concatenate([np.zeros(len(top_nodes)), np.ones(len(bot_nodes))])
+    return dict(mesh=mesh, elem_mat=elem_mat, elem_junc=elem_junc, tables=tables, eps=eps, noheat=noheat,
+                nodes=nodes, values=values)
+
+
+@pytest.mark.parametrize("algorithm,precond", [("cholesky", None), ("iterative", "ic"), ("iterative", "jac"), ("pcg", None)])
+def test_shockley3d_analytic(algorithm, precond):
+    if algorithm == "iterative" and not orc.ref_available():
+        pytest.skip("oracle/_ref not built")
+    c = shockley3d_reference_case()
+    assert c["mesh"].order == "201" and c["mesh"].n == (10, 10, 11)
+    kw = dict(itmaxerr=1e-6, maxit=1000)
+    maxerr = 1e-3                                            # shockley3d.py:56
+    if algorithm == "pcg":
+        # A noise-free solver takes ever smaller steps towards the fixed point (rate ~0.9/loop), so
+        # the step-size criterion 1e-3 % stops it ~1e-4 away from the analytic current; the
+        # reference's solvers only get closer because their round-off noise keeps the loop going.
+        kw = dict(itmaxerr=1e-14, maxit=200000)
+        maxerr = 1e-5
+    s = orc.Shockley3DOracle(c["mesh"], c["elem_mat"], c["tables"], c["nodes"], c["values"], elem_junc=c["elem_junc"],
+                             beta=10., js=1., maxerr=maxerr, algorithm=algorithm, precond=precond or "ic",
+                             noheat=c["noheat"], eps=c["eps"], **kw)
+    s.compute(1000)
+    S = 1e6
+    correct_current = 1e-9 * S * 1. * (np.exp(10.) - 1)
+    assert abs(s.get_total_current()) == pytest.approx(correct_current, abs=0.5e-3)       # shockley3d.py:64-65
+    capacitance = 8.854187817e-6 * 12.9 * S / 0.02
+    assert s.get_capacitance() == pytest.approx(capacitance, abs=0.5e-2)                  # :66-67
+    assert s.get_total_heat() == pytest.approx(correct_current * 1., abs=0.5e-3)         # :68-69
+
+
+def test_shockley3d_beta_of_T():
+    """shockley3d.py:75-83: beta as a python function of T, inTemperature 300 then 250."""
+    c = shockley3d_reference_case()
+    s = orc.Shockley3DOracle(c["mesh"], c["elem_mat"], c["tables"], c["nodes"], c["values"], elem_junc=c["elem_junc"],
+                             beta=lambda T: np.log(T * 70), js=1., maxerr=1e-3, algorithm="cholesky",
+                             noheat=c["noheat"], eps=c["eps"])
+    s.compute(1000)
+    assert abs(s.get_total_current()) == pytest.approx(1e-9 * 1e6 * (21000 - 1), abs=0.5e-3)
+    s.Te[:] = 250.
+    s.compute(1000)
+    assert abs(s.get_total_current()) == pytest.approx(1e-9 * 1e6 * (17500 - 1), abs=0.5e-3)
+
+
+def test_shockley3d_conductivity():
+    """shockley3d.py:85-91: outConductivity equals material cond(300) / (0,5) in the junction."""
+    c = shockley3d_reference_case()
+    s = orc.Shockley3DOracle(c["mesh"], c["elem_mat"], c["tables"], c["nodes"], c["values"], elem_junc=c["elem_junc"],
+                             beta=10., js=1.)
+    s.load_conductivity()
+    expect = np.where(c["elem_junc"][:, None] > 0, np.array([0., 5.]), c["tables"].lat[c["elem_mat"], 0][:, None])
+    assert np.array_equal(s.conds, expect)

@@ -84,7 +84,7 @@ k_apply_simple(const Grid g, const double* __restrict__ cl, const double* __rest
 // Diagonal of the eliminated matrix: sum over the 8 adjacent elements of (kI+kJ+kK)/9
 // (therm3d.cpp:227); dinv = 0 marks Dirichlet rows (and rows with an empty diagonal).
 __global__ void k_diag(const Grid g, const double* __restrict__ cl, const double* __restrict__ cv,
-                       const uint8_t* __restrict__ fixed, double* __restrict__ dinv) {
+                       const uint8_t* __restrict__ fixed, double* __restrict__ dinv, Scalars* sc) {
     const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
     const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
     const int k = blockIdx.z;
@@ -102,6 +102,7 @@ __global__ void k_diag(const Grid g, const double* __restrict__ cl, const double
                 elem_conductances(g, cl[slot], cv[slot], i + di, j + dj, k + dk, kI, kJ, kK);
                 d += (kI + kJ + kK) * (1. / 9.);
             }
+    if (!fixed[n] && d < 0.) sc->neg_diag = 1;
     dinv[n] = (fixed[n] || !(d > 0.)) ? 0. : 1. / d;
 }
 
@@ -137,59 +138,68 @@ __global__ void k_pupdate(idx_t N, const double* __restrict__ r, const double* _
         p[n] = dinv[n] * r[n] + beta * p[n];
 }
 
-// x += alpha p; r -= alpha q; rho = sum r^2 dinv; rr = sum r^2; then (last block) the scalar
-// recurrences of CG (itcg, extlib/nspcg/nspcg.f:9281-9337) and the stopping test.
+// x += alpha p; r -= alpha q; rho = sum r^2 dinv; rr = sum r^2; zz = sum (dinv r)^2; xx = sum x^2;
+// then (last block) the scalar recurrences of CG (itcg, extlib/nspcg/nspcg.f:9281-9337) and the
+// stopping test: ||r|| <= tol ||b||, ||r||_D^-1 <= tol ||b||_D^-1 and ||D^-1 r|| <= tol ||x||
+// (the last is NSPCG's pseudo-residual test #2, nspcg.f:26487-26518, without the eigenvalue
+// estimate; it is what makes nearly floating nodes — air pockets — converge too).
 // INIT = true: no update, only the two reductions and the initial scalars.
 template <bool INIT>
 __global__ void __launch_bounds__(256)
 k_update(idx_t N, double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
          const double* __restrict__ q, const double* __restrict__ dinv, Scalars* sc, double* partials) {
-    __shared__ double sh[64];
+    __shared__ double sh[128];
     __shared__ int sh_flag;
     if (!INIT && sc->done) return;
     const double alpha = INIT ? 0. : sc->alpha;
-    double v[2] = {0., 0.};
+    double v[4] = {0., 0., 0., 0.};
     const idx_t nthreads = (idx_t)gridDim.x * blockDim.x;
     const idx_t t = blockIdx.x * (idx_t)blockDim.x + threadIdx.x;
     const idx_t N2 = N >> 1;  // arrays are 16-byte aligned (guard band is a multiple of 16 doubles)
     for (idx_t m = t; m < N2; m += nthreads) {
         double2 rr = reinterpret_cast<const double2*>(r)[m];
         const double2 dd = reinterpret_cast<const double2*>(dinv)[m];
+        double2 xx = reinterpret_cast<double2*>(x)[m];
         if (!INIT) {
             const double2 pp = reinterpret_cast<const double2*>(p)[m];
             const double2 qq = reinterpret_cast<const double2*>(q)[m];
-            double2 xx = reinterpret_cast<double2*>(x)[m];
             xx.x += alpha * pp.x; xx.y += alpha * pp.y;
             rr.x -= alpha * qq.x; rr.y -= alpha * qq.y;
             reinterpret_cast<double2*>(x)[m] = xx;
             reinterpret_cast<double2*>(r)[m] = rr;
         }
-        v[0] += rr.x * rr.x * dd.x + rr.y * rr.y * dd.y;
+        const double zx = rr.x * dd.x, zy = rr.y * dd.y;
+        v[0] += rr.x * zx + rr.y * zy;
         v[1] += rr.x * rr.x + rr.y * rr.y;
+        v[2] += zx * zx + zy * zy;
+        v[3] += xx.x * xx.x + xx.y * xx.y;
     }
     if ((N & 1) && t == 0) {
         const idx_t n = N - 1;
-        double rn = r[n];
-        if (!INIT) { x[n] += alpha * p[n]; rn -= alpha * q[n]; r[n] = rn; }
-        v[0] += rn * rn * dinv[n];
+        double rn = r[n], xn = x[n];
+        if (!INIT) { xn += alpha * p[n]; x[n] = xn; rn -= alpha * q[n]; r[n] = rn; }
+        const double zn = rn * dinv[n];
+        v[0] += rn * zn;
         v[1] += rn * rn;
+        v[2] += zn * zn;
+        v[3] += xn * xn;
     }
-    if (grid_reduce<2, false>(v, partials, &sc->ticket[1], sh, &sh_flag)) {
+    if (grid_reduce<4, false>(v, partials, &sc->ticket[1], sh, &sh_flag)) {
         if (threadIdx.x == 0) {
             if (INIT) {
-                sc->rho = v[0]; sc->rho_prev = v[0]; sc->rr = v[1];
+                sc->rho = v[0]; sc->rho_prev = v[0]; sc->rr = v[1]; sc->zz = v[2]; sc->xx = v[3];
                 sc->beta = 0.; sc->alpha = 0.; sc->pq = 0.; sc->iter = 0; sc->status = 0; sc->done = 0;
                 if (!(v[1] == v[1])) { sc->done = 1; sc->status = -2; }
-                else if (!sc->bench && v[1] <= sc->tol2 * sc->bb && v[0] <= sc->tol2 * sc->bz) { sc->done = 1; sc->status = 1; }
+                else if (!sc->bench && v[1] <= sc->tol2 * sc->bb && v[0] <= sc->tol2 * sc->bz && v[2] <= sc->tol2 * v[3]) { sc->done = 1; sc->status = 1; }
             } else {
                 const double rho_old = sc->rho;
-                sc->rho_prev = rho_old; sc->rho = v[0]; sc->rr = v[1];
+                sc->rho_prev = rho_old; sc->rho = v[0]; sc->rr = v[1]; sc->zz = v[2]; sc->xx = v[3];
                 sc->beta = (rho_old > 0.) ? v[0] / rho_old : 0.;
                 const int it = sc->iter + 1;
                 sc->iter = it;
                 if (!sc->bench) {
                     if (!(v[1] == v[1])) { sc->done = 1; sc->status = -2; }
-                    else if (v[1] <= sc->tol2 * sc->bb && v[0] <= sc->tol2 * sc->bz) { sc->done = 1; sc->status = 1; }
+                    else if (v[1] <= sc->tol2 * sc->bb && v[0] <= sc->tol2 * sc->bz && v[2] <= sc->tol2 * v[3]) { sc->done = 1; sc->status = 1; }
                     else if (it >= sc->maxit) { sc->done = 1; sc->status = 2; }
                 }
             }
@@ -209,17 +219,21 @@ __global__ void k_select_fixed(idx_t N, const uint8_t* __restrict__ fixed, const
     for (idx_t n = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; n < N; n += (idx_t)gridDim.x * blockDim.x)
         out[n] = fixed[n] ? a[n] : b[n];
 }
+// The host passes a de-duplicated list (last value wins, like B[r] = val in setBC), so a plain
+// scatter is race free.  x and/or fixed may be null.
 __global__ void k_scatter_dirichlet(size_t nd, const idx_t* __restrict__ node, const double* __restrict__ value,
                                     double* __restrict__ x, uint8_t* __restrict__ fixed) {
-    // applied in order on one thread per *distinct* node would need sorting; the host passes a
-    // de-duplicated list (last value wins, like B[r] = val in setBC), so plain scatter is safe.
     for (size_t m = blockIdx.x * (size_t)blockDim.x + threadIdx.x; m < nd; m += (size_t)gridDim.x * blockDim.x) {
-        x[node[m]] = value[m];
-        fixed[node[m]] = 1;
+        if (x) x[node[m]] = value[m];
+        if (fixed) fixed[node[m]] = 1;
     }
 }
-__global__ void k_fill(idx_t N, double* __restrict__ x, double v) {
-    for (idx_t n = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; n < N; n += (idx_t)gridDim.x * blockDim.x) x[n] = v;
+// fill the true nodes of a pitched lattice array (pad entries stay 0)
+__global__ void k_fill_nodes(const Grid g, double* __restrict__ x, double v) {
+    const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
+    const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i < g.nI && j < g.nJ) x[i + g.sJ * j + g.sK * k] = v;
 }
 __global__ void k_diag_from_dinv(idx_t N, const double* __restrict__ dinv, const uint8_t* __restrict__ fixed,
                                  double* __restrict__ d) {

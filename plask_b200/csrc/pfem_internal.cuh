@@ -1,11 +1,13 @@
 // pfem_internal.cuh — device data layout, reduction helpers and the brick-element stencil core.
 //
 // Layout in HBM.  The mesh is handled in INDEX space: I = minor (fastest),
-// J = medium, K = major axis of RectangularMesh<3> (plask/mesh/rectilinear3d.cpp:20-32), so a
-// node array is exactly the reference's DataVector<double>: node (i,j,k) at i + nI*(j + nJ*k).
+// J = medium, K = major axis of RectangularMesh<3> (plask/mesh/rectilinear3d.cpp:20-32).  A node
+// array is the reference's DataVector<double> with the rows padded to a pitch sJ = nI rounded up
+// to 16 doubles (128-byte rows: coalescing, and the 16-byte stride rule of TMA tensor maps):
+// node (i,j,k) at i + sJ*(j + nJ*k); the pad entries are always 0.
 // Element arrays live on the SAME lattice: element (i,j,k) is stored at the index of its
-// lowest corner node; the slots with i = nI-1, j = nJ-1 or k = nK-1 are padding and hold ZERO
-// conductivity.  Every array additionally has a zero guard band of G >= nI*nJ + nI + 2 entries
+// lowest corner node; the slots with i >= nI-1, j = nJ-1 or k = nK-1 are padding and hold ZERO
+// conductivity.  Every array additionally has a zero guard band of G >= sK + sJ + 2 entries
 // on both sides.  Together this makes the 27-point operator branch-free: a neighbour that does
 // not exist is reached through a padding/guard slot whose conductivity is 0.
 #pragma once
@@ -18,8 +20,9 @@ typedef long long idx_t;
 
 struct Grid {
     int nI, nJ, nK;      // nodes per index-space axis
-    idx_t sJ, sK;        // node strides (sI = 1)
-    idx_t N;             // nI*nJ*nK
+    idx_t sJ, sK;        // node strides (sI = 1): sJ = row pitch >= nI, sK = sJ*nJ
+    idx_t N;             // nI*nJ*nK (true node count)
+    idx_t NP;            // sK*nK (length of a pitched node array)
     idx_t G;             // guard band length (multiple of 16)
     int vdim;            // index-space axis (0 I, 1 J, 2 K) that is the physical vertical axis 2
     int dim_of_phys[3];  // index-space axis of physical axis a
@@ -43,6 +46,8 @@ struct Scalars {
     double rr;        // r.r
     double bb;        // ||b_free||^2
     double bz;        // b_free . D^-1 b_free  (preconditioner norm of the rhs)
+    double zz;        // ||D^-1 r||^2  (Jacobi pseudo-residual, NSPCG's stopping quantity)
+    double xx;        // ||x||^2
     double tol2;      // lin_tol^2 (negative: never converge, benchmark mode)
     double red[4];    // generic reduction outputs (err, max, ...)
     long long argidx; // arg-max index of the current reduction
@@ -52,6 +57,7 @@ struct Scalars {
     int done;         // 1: all iteration kernels return immediately
     int status;       // 0 running, 1 converged, 2 maxit, -1 breakdown (p.Ap <= 0), -2 non-finite
     int bench;        // 1: ignore breakdown / convergence
+    int neg_diag;     // a free row has a negative diagonal (NSPCG ier = -4)
     unsigned int ticket[8];
 };
 

@@ -15,6 +15,7 @@
 #include "../../include/plaskfem_cuda.h"
 #include "kernels_simple.cuh"
 #include "kernels_tiled.cuh"
+#include "kernels_tma.cuh"
 
 using namespace pfem;
 
@@ -35,6 +36,9 @@ struct pfem_ctx {
     // node arrays (pointers already offset by the guard band)
     double *x = nullptr, *xprev = nullptr, *r = nullptr, *p = nullptr, *p2 = nullptr, *q = nullptr, *dinv = nullptr, *f = nullptr;
     uint8_t* fixed = nullptr;
+    idx_t* bc_node = nullptr;   // de-duplicated Dirichlet nodes (device lattice indices) and values
+    double* bc_val = nullptr;
+    size_t nbc = 0;
     // element arrays on the node lattice
     double *cl = nullptr, *cv = nullptr, *Te = nullptr, *cur0 = nullptr, *cur1 = nullptr, *cur2 = nullptr;
     double *aux0 = nullptr, *aux1 = nullptr, *aux2 = nullptr;
@@ -68,6 +72,7 @@ struct pfem_ctx {
     double last_relres_pre = 0.;
     int sm_count = 148;
     TiledPlan plan;
+    TmaPlan tma;
 };
 
 #define CU(call)                                                                                         \
@@ -128,6 +133,18 @@ static inline dim3 node_grid(const Grid& g) {
     return dim3((g.nI + PFEM_NODE_BLOCK_X - 1) / PFEM_NODE_BLOCK_X, (g.nJ + PFEM_NODE_BLOCK_Y - 1) / PFEM_NODE_BLOCK_Y, g.nK);
 }
 static inline int vec_blocks(const pfem_ctx* ctx) { return ctx->sm_count * 8; }
+
+// host <-> device copies of node arrays: the ABI side is dense (row length nI), the device side pitched
+static cudaError_t upload_nodes(pfem_ctx* ctx, double* dev, const double* host) {
+    const Grid& g = ctx->g;
+    return cudaMemcpy2DAsync(dev, (size_t)g.sJ * 8, host, (size_t)g.nI * 8, (size_t)g.nI * 8, (size_t)g.nJ * g.nK,
+                             cudaMemcpyHostToDevice, ctx->stream);
+}
+static cudaError_t download_nodes(pfem_ctx* ctx, double* host, const double* dev) {
+    const Grid& g = ctx->g;
+    return cudaMemcpy2DAsync(host, (size_t)g.nI * 8, dev, (size_t)g.sJ * 8, (size_t)g.nI * 8, (size_t)g.nJ * g.nK,
+                             cudaMemcpyDeviceToHost, ctx->stream);
+}
 
 #define LAUNCHED(n) (ctx->launches += (n))
 #define KCHECK() CU(cudaGetLastError())
@@ -231,12 +248,15 @@ extern "C" int pfem_set_mesh(pfem_ctx* ctx, const size_t n[3], const double* ax0
     Grid& g = ctx->g;
     memset(&g, 0, sizeof(g));
     g.nI = (int)n[minor]; g.nJ = (int)n[medium]; g.nK = (int)n[major];
-    g.sJ = g.nI; g.sK = (idx_t)g.nI * g.nJ;
-    g.N = g.sK * g.nK;
+    g.sJ = ((idx_t)g.nI + 15) / 16 * 16;   // 128-byte rows
+    g.sK = g.sJ * g.nJ;
+    g.N = (idx_t)g.nI * g.nJ * g.nK;
+    g.NP = g.sK * g.nK;
     g.G = ((g.sK + g.sJ + 2 + 15) / 16) * 16;
     g.dim_of_phys[minor] = 0; g.dim_of_phys[medium] = 1; g.dim_of_phys[major] = 2;
     g.vdim = g.dim_of_phys[2];
-    for (int a = 0; a < 3; ++a) { g.ps[a] = (idx_t)stride[a]; g.pn[a] = (int)n[a]; }
+    for (int a = 0; a < 3; ++a) g.pn[a] = (int)n[a];
+    g.ps[minor] = 1; g.ps[medium] = g.sJ; g.ps[major] = g.sK;   // strides in the pitched device layout
     g.es[minor] = 1; g.es[medium] = g.nI - 1; g.es[major] = (idx_t)(g.nI - 1) * (g.nJ - 1);
     g.E = (idx_t)(g.nI - 1) * (g.nJ - 1) * (g.nK - 1);
 
@@ -263,7 +283,7 @@ extern "C" int pfem_set_mesh(pfem_ctx* ctx, const size_t n[3], const double* ax0
     g.hJ = ctx->hbuf + hoff[1]; g.rJ = ctx->hbuf + roff[1];
     g.hK = ctx->hbuf + hoff[2]; g.rK = ctx->hbuf + roff[2];
 
-    const size_t N = (size_t)g.N, G = (size_t)g.G;
+    const size_t N = (size_t)g.NP, G = (size_t)g.G;
     TRY(dev_alloc(ctx, &ctx->x, N, G));
     TRY(dev_alloc(ctx, &ctx->xprev, N, G));
     TRY(dev_alloc(ctx, &ctx->r, N, G));
@@ -286,6 +306,10 @@ extern "C" int pfem_set_mesh(pfem_ctx* ctx, const size_t n[3], const double* ax0
     CU(cudaMemsetAsync(ctx->d_sc, 0, sizeof(Scalars), ctx->stream));
     ctx->loopno = 0;
     ctx->plan = make_tiled_plan(g, ctx->sm_count);
+    ctx->tma = make_tma_plan(g, ctx->sm_count, ctx->p, ctx->p2, ctx->r, ctx->dinv, ctx->cl, ctx->cv);
+    ctx->nbc = 0;
+    ctx->bc_node = nullptr;
+    ctx->bc_val = nullptr;
     ctx->have_mesh = true;
     CU(cudaStreamSynchronize(ctx->stream));
     return PFEM_OK;
@@ -339,6 +363,16 @@ extern "C" int pfem_set_materials(pfem_ctx* ctx, const uint32_t* elem_mat, uint3
     return PFEM_OK;
 }
 
+// x[node] = value and/or fixed[node] = 1 for the stored Dirichlet list
+static int scatter_bc(pfem_ctx* ctx, double* x, uint8_t* fixed) {
+    if (!ctx->nbc) return PFEM_OK;
+    int blocks = (int)((ctx->nbc + 255) / 256);
+    if (blocks > 4096) blocks = 4096;
+    k_scatter_dirichlet<<<blocks, 256, 0, ctx->stream>>>(ctx->nbc, ctx->bc_node, ctx->bc_val, x, fixed);
+    KCHECK(); LAUNCHED(1);
+    return PFEM_OK;
+}
+
 extern "C" int pfem_set_dirichlet(pfem_ctx* ctx, size_t nd, const size_t* node, const double* value) {
     NEED_MESH();
     const Grid& g = ctx->g;
@@ -354,7 +388,10 @@ extern "C" int pfem_set_dirichlet(pfem_ctx* ctx, size_t nd, const size_t* node, 
         for (size_t m = 0; m < nd; ++m) {
             if (node[m] >= (size_t)g.N) FAIL(PFEM_ERR_BAD_INPUT, "Dirichlet node %zu out of range", node[m]);
             if (!(value[m] == value[m]) || isinf(value[m])) FAIL(PFEM_ERR_BAD_INPUT, "non-finite Dirichlet value");
-            order[m] = {(idx_t)node[m], m};
+            // ABI index (dense rows) -> pitched lattice index
+            const idx_t r = (idx_t)node[m];
+            const idx_t i = r % g.nI, t = r / g.nI;
+            order[m] = {i + g.sJ * (t % g.nJ) + g.sK * (t / g.nJ), m};
         }
         std::sort(order.begin(), order.end());
         for (size_t m = 0; m < nd; ++m) {
@@ -363,25 +400,24 @@ extern "C" int pfem_set_dirichlet(pfem_ctx* ctx, size_t nd, const size_t* node, 
             vv.push_back(value[order[m].second]);
         }
     }
-    CU(cudaMemsetAsync(ctx->fixed, 0, (size_t)g.N, ctx->stream));
+    // The values are NOT written into the field here: like the reference (applyBC works on the
+    // matrix and B only, matrix.hpp:111-118) the field keeps its previous values until the solve,
+    // so the conductivities of the first loop are evaluated from the un-constrained field.
+    CU(cudaMemsetAsync(ctx->fixed, 0, (size_t)g.NP, ctx->stream));
+    ctx->nbc = nn.size();
     if (!nn.empty()) {
-        size_t bytes = nn.size() * (sizeof(idx_t) + sizeof(double));
-        TRY(ensure_stage(ctx, bytes));
-        idx_t* dn = (idx_t*)ctx->stage;
-        double* dv = (double*)(dn + nn.size());
-        CU(cudaMemcpyAsync(dn, nn.data(), nn.size() * sizeof(idx_t), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(dv, vv.data(), vv.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        int blocks = (int)((nn.size() + 255) / 256);
-        if (blocks > 4096) blocks = 4096;
-        k_scatter_dirichlet<<<blocks, 256, 0, ctx->stream>>>(nn.size(), dn, dv, ctx->x, ctx->fixed);
-        KCHECK(); LAUNCHED(1);
+        TRY(dev_alloc(ctx, &ctx->bc_node, nn.size(), 0));
+        TRY(dev_alloc(ctx, &ctx->bc_val, nn.size(), 0));
+        CU(cudaMemcpyAsync(ctx->bc_node, nn.data(), nn.size() * sizeof(idx_t), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->bc_val, vv.data(), vv.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        TRY(scatter_bc(ctx, nullptr, ctx->fixed));
     }
     CU(cudaStreamSynchronize(ctx->stream));
     return PFEM_OK;
 }
 
 static int ensure_elem_arrays(pfem_ctx* ctx, bool shockley) {
-    const size_t N = (size_t)ctx->g.N, G = (size_t)ctx->g.G;
+    const size_t N = (size_t)ctx->g.NP, G = (size_t)ctx->g.G;
     if (!ctx->aux0) {
         TRY(dev_alloc(ctx, &ctx->aux0, N, G));
         TRY(dev_alloc(ctx, &ctx->aux1, N, G));
@@ -399,12 +435,12 @@ extern "C" int pfem_set_source(pfem_ctx* ctx, const double* heat) {
     NEED_MESH();
     const Grid& g = ctx->g;
     if (!heat) {
-        CU(cudaMemsetAsync(ctx->f, 0, (size_t)g.N * sizeof(double), ctx->stream));
+        CU(cudaMemsetAsync(ctx->f, 0, (size_t)g.NP * sizeof(double), ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         return PFEM_OK;
     }
     TRY(ensure_elem_arrays(ctx, false));
-    CU(cudaMemsetAsync(ctx->aux0 - g.G, 0, (size_t)(g.N + 2 * g.G) * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(ctx->aux0 - g.G, 0, (size_t)(g.NP + 2 * g.G) * sizeof(double), ctx->stream));
     TRY(upload_elem<double, 1>(ctx, heat, ctx->aux0, nullptr, nullptr));
     k_load_vector<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->aux0, ctx->f);
     KCHECK(); LAUNCHED(1);
@@ -415,14 +451,14 @@ extern "C" int pfem_set_source(pfem_ctx* ctx, const double* heat) {
 extern "C" int pfem_set_field(pfem_ctx* ctx, const double* x0) {
     NEED_MESH();
     if (!x0) FAIL(PFEM_ERR_BAD_INPUT, "null field");
-    CU(cudaMemcpyAsync(ctx->x, x0, (size_t)ctx->g.N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(upload_nodes(ctx, ctx->x, x0));
     CU(cudaStreamSynchronize(ctx->stream));
     return PFEM_OK;
 }
 
 extern "C" int pfem_fill_field(pfem_ctx* ctx, double value) {
     NEED_MESH();
-    k_fill<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(ctx->g.N, ctx->x, value);
+    k_fill_nodes<<<node_grid(ctx->g), node_block(), 0, ctx->stream>>>(ctx->g, ctx->x, value);
     KCHECK(); LAUNCHED(1);
     CU(cudaStreamSynchronize(ctx->stream));
     return PFEM_OK;
@@ -431,11 +467,11 @@ extern "C" int pfem_fill_field(pfem_ctx* ctx, double value) {
 extern "C" int pfem_set_elem_temperature(pfem_ctx* ctx, const double* T_elem, double uniform_T) {
     NEED_MESH();
     const Grid& g = ctx->g;
-    if (!ctx->Te) TRY(dev_alloc(ctx, &ctx->Te, (size_t)g.N, (size_t)g.G));
+    if (!ctx->Te) TRY(dev_alloc(ctx, &ctx->Te, (size_t)g.NP, (size_t)g.G));
     if (T_elem) {
         TRY(upload_elem<double, 1>(ctx, T_elem, ctx->Te, nullptr, nullptr));
     } else {
-        k_fill<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->Te, uniform_T);
+        k_fill_nodes<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->Te, uniform_T);
         KCHECK(); LAUNCHED(1);
         CU(cudaStreamSynchronize(ctx->stream));
     }
@@ -449,7 +485,7 @@ extern "C" int pfem_set_junctions(pfem_ctx* ctx, uint32_t njunc, const pfem_junc
     NEED_MESH();
     const Grid& g = ctx->g;
     if (njunc && (!junc || !elem_junc || !junc_cond || !beta_col || !js_col)) FAIL(PFEM_ERR_BAD_INPUT, "null junction argument");
-    const size_t N = (size_t)g.N, G = (size_t)g.G;
+    const size_t N = (size_t)g.NP, G = (size_t)g.G;
     if (!ctx->junc) TRY(dev_alloc(ctx, &ctx->junc, N, G));
     if (!ctx->role) TRY(dev_alloc(ctx, &ctx->role, N, G));
     CU(cudaMemsetAsync(ctx->junc, 0, N * sizeof(uint32_t), ctx->stream));
@@ -531,13 +567,13 @@ extern "C" int pfem_set_conductivity(pfem_ctx* ctx, const double* cond) {
 // ------------------------------------------------------------------------ PCG -----------
 
 __global__ void k_set_params(Scalars* sc, double tol2, int maxit, int bench) {
-    sc->tol2 = tol2; sc->maxit = maxit; sc->bench = bench;
+    sc->tol2 = tol2; sc->maxit = maxit; sc->bench = bench; sc->neg_diag = 0;
 }
 __global__ void k_force_running(Scalars* sc) { sc->done = 0; sc->status = 0; }
 
 static int launch_diag(pfem_ctx* ctx) {
     const Grid& g = ctx->g;
-    k_diag<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->cl, ctx->cv, ctx->fixed, ctx->dinv);
+    k_diag<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->cl, ctx->cv, ctx->fixed, ctx->dinv, ctx->d_sc);
     KCHECK(); LAUNCHED(1);
     return PFEM_OK;
 }
@@ -563,24 +599,28 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
     const double* pnew = (variant == 1) ? ctx->p : pout;
     if (ev) cudaEventRecord(ev[0], ctx->stream);
     if (variant == 1) {
-        k_pupdate<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->r, ctx->dinv, ctx->p, ctx->d_sc);
+        k_pupdate<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->r, ctx->dinv, ctx->p, ctx->d_sc);
         k_apply_simple<0><<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->cl, ctx->cv, ctx->p, ctx->dinv, ctx->f,
                                                                          ctx->q, ctx->d_sc, ctx->partials);
         launched += 2;
-    } else {
+    } else if (variant == 2) {
         launch_apply_tiled(ctx->plan, g, ctx->cl, ctx->cv, ctx->r, ctx->dinv, pin, pout, ctx->q, ctx->d_sc,
                            ctx->partials, ctx->stream);
         launched += 1;
+    } else {
+        launch_tma_dispatch<true>(ctx->tma, g, ctx->tma.m_p[parity], ctx->dinv, pout, ctx->q, ctx->d_sc, ctx->partials,
+                                  ctx->stream);
+        launched += 1;
     }
     if (ev) cudaEventRecord(ev[1], ctx->stream);
-    k_update<false><<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->x, ctx->r, pnew, ctx->q, ctx->dinv, ctx->d_sc,
+    k_update<false><<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->x, ctx->r, pnew, ctx->q, ctx->dinv, ctx->d_sc,
                                                                ctx->partials);
     launched += 1;
     if (ev) cudaEventRecord(ev[2], ctx->stream);
     return launched;
 }
 
-static int kernels_per_iteration(int variant) { return variant == 1 ? 3 : 2; }
+static int kernels_per_iteration(int variant) { return variant == 1 ? 3 : 2; }  // variants 0 (TMA) and 2 (LDG tiled) fuse the p-update
 
 static int build_graph(pfem_ctx* ctx, int batch, int variant, int precond) {
     if (ctx->graph && ctx->graph_batch == batch && ctx->graph_variant == variant && ctx->graph_precond == precond)
@@ -612,15 +652,15 @@ static int pcg_prepare(pfem_ctx* ctx, const pfem_opts* o, int bench) {
     k_set_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, tol2, o->maxit, bench);
     LAUNCHED(1);
     TRY(launch_diag(ctx));
+    TRY(scatter_bc(ctx, ctx->x, nullptr));   // x_D = v_D (B[r] = val, iterative_matrix.hpp:463-464)
     // ||b_free||^2 with b_free = M (f - A x_D): q <- x_D, p <- b_free (scratch)
-    k_dirichlet_only<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->x, ctx->fixed, ctx->q);
+    k_dirichlet_only<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->x, ctx->fixed, ctx->q);
     LAUNCHED(1);
     TRY(launch_apply_simple<2>(ctx, ctx->q, ctx->p));
     // r0 = M (f - A x)
     TRY(launch_apply_simple<1>(ctx, ctx->x, ctx->r));
-    k_fill<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->p, 0.);
-    LAUNCHED(1);
-    k_update<true><<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->x, ctx->r, ctx->p, ctx->q, ctx->dinv, ctx->d_sc,
+    CU(cudaMemsetAsync(ctx->p, 0, (size_t)g.NP * sizeof(double), ctx->stream));
+    k_update<true><<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->x, ctx->r, ctx->p, ctx->q, ctx->dinv, ctx->d_sc,
                                                               ctx->partials);
     LAUNCHED(1);
     KCHECK();
@@ -633,6 +673,7 @@ static int pcg_solve(pfem_ctx* ctx, const pfem_opts* o, int* iters, double* relr
     batch += batch & 1;  // even: p ping-pong parity is preserved across graph launches
     TRY(build_graph(ctx, batch, o->variant, o->precond));
     TRY(read_scalars(ctx));
+    if (ctx->h_sc->neg_diag) FAIL(PFEM_ERR_NOT_SPD, "nonpositive diagonal element in stiffness matrix");
     while (!ctx->h_sc->done) {
         CU(cudaGraphLaunch(ctx->graph, ctx->stream));
         LAUNCHED((long long)batch * kernels_per_iteration(o->variant));
@@ -653,8 +694,9 @@ static int check_opts(pfem_ctx* ctx, const pfem_opts* o) {
     if (o->maxit <= 0) FAIL(PFEM_ERR_BAD_INPUT, "maxit must be positive");
     if (!(o->lin_tol > 0.)) FAIL(PFEM_ERR_BAD_INPUT, "lin_tol must be positive");
     if (o->precond != 0) FAIL(PFEM_ERR_BAD_INPUT, "preconditioner %d is not implemented", o->precond);
-    if (o->variant != 0 && o->variant != 1) FAIL(PFEM_ERR_BAD_INPUT, "unknown kernel variant %d", o->variant);
-    if (o->variant == 0 && !ctx->plan.valid) FAIL(PFEM_ERR_STATE, "no tiled kernel plan for this mesh");
+    if (o->variant < 0 || o->variant > 2) FAIL(PFEM_ERR_BAD_INPUT, "unknown kernel variant %d", o->variant);
+    if (o->variant == 0 && !ctx->tma.valid) FAIL(PFEM_ERR_STATE, "TMA operator kernel unavailable: %s", ctx->tma.why);
+    if (o->variant == 2 && !ctx->plan.valid) FAIL(PFEM_ERR_STATE, "no tiled kernel plan for this mesh");
     return PFEM_OK;
 }
 
@@ -699,11 +741,11 @@ extern "C" int pfem_solve_thermal(pfem_ctx* ctx, const pfem_opts* o, pfem_stats*
     double err = 0., toterr = 0., maxT = 0., relres = 0.;
     const int cap = o->loops > 0 ? o->loops : 100000;
     do {
-        CU(cudaMemcpyAsync(ctx->xprev, ctx->x, (size_t)g.N * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->xprev, ctx->x, (size_t)g.NP * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         TRY(pfem_update_conductivity_thermal(ctx));           // therm3d.cpp:204-220
         TRY(pcg_solve(ctx, o, &iters, &relres, &conv));        // setMatrix + A.solve, :314-315
         total_iters += iters;
-        k_thermal_error<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->x, ctx->xprev, ctx->d_sc, ctx->partials);
+        k_thermal_error<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->x, ctx->xprev, ctx->d_sc, ctx->partials);
         KCHECK(); LAUNCHED(1);
         TRY(read_scalars(ctx));
         err = ctx->h_sc->red[0];
@@ -780,7 +822,7 @@ extern "C" int pfem_solve_shockley(pfem_ctx* ctx, const pfem_opts* o, pfem_stats
 extern "C" int pfem_get_field(pfem_ctx* ctx, double* x) {
     NEED_MESH();
     if (!x) FAIL(PFEM_ERR_BAD_INPUT, "null output");
-    CU(cudaMemcpyAsync(x, ctx->x, (size_t)ctx->g.N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(download_nodes(ctx, x, ctx->x));
     CU(cudaStreamSynchronize(ctx->stream));
     return PFEM_OK;
 }
@@ -801,7 +843,7 @@ extern "C" int pfem_get_elem(pfem_ctx* ctx, int what, const uint8_t* noheat, dou
             TRY(ensure_elem_arrays(ctx, false));
             const uint8_t* nh = nullptr;
             if (noheat) {
-                if (!ctx->noheat) TRY(dev_alloc(ctx, &ctx->noheat, (size_t)g.N, (size_t)g.G));
+                if (!ctx->noheat) TRY(dev_alloc(ctx, &ctx->noheat, (size_t)g.NP, (size_t)g.G));
                 TRY(upload_elem<uint8_t, 1>(ctx, noheat, ctx->noheat, nullptr, nullptr));
                 nh = ctx->noheat;
             }
@@ -841,20 +883,24 @@ extern "C" int pfem_apply(pfem_ctx* ctx, const double* p, double* q, int variant
     const Grid& g = ctx->g;
     TRY(launch_diag(ctx));
     // r <- p (as given), p <- M p, q <- M A M p, then q_D <- p_D
-    CU(cudaMemcpyAsync(ctx->r, p, (size_t)g.N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    k_fill<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->q, 0.);
-    k_select_fixed<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->fixed, ctx->q, ctx->r, ctx->p);
-    LAUNCHED(2);
+    CU(upload_nodes(ctx, ctx->r, p));
+    CU(cudaMemsetAsync(ctx->q, 0, (size_t)g.NP * sizeof(double), ctx->stream));
+    k_select_fixed<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->fixed, ctx->q, ctx->r, ctx->p);
+    LAUNCHED(1);
     if (variant == 1) {
         TRY(launch_apply_simple<3>(ctx, ctx->p, ctx->q));
-    } else {
+    } else if (variant == 2) {
         if (!ctx->plan.valid) FAIL(PFEM_ERR_STATE, "no tiled kernel plan for this mesh");
-        launch_apply_tiled_plain(ctx->plan, g, ctx->cl, ctx->cv, ctx->dinv, ctx->p, ctx->q, ctx->stream);
-        KCHECK(); LAUNCHED(1);
-    }
-    k_select_fixed<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->fixed, ctx->r, ctx->q, ctx->q);
+        CU(launch_apply_tiled_plain(ctx->plan, g, ctx->cl, ctx->cv, ctx->dinv, ctx->p, ctx->q, ctx->stream));
+        LAUNCHED(1);
+    } else if (variant == 0) {
+        if (!ctx->tma.valid) FAIL(PFEM_ERR_STATE, "TMA operator kernel unavailable: %s", ctx->tma.why);
+        CU(launch_tma_dispatch<false>(ctx->tma, g, ctx->tma.m_p[0], ctx->dinv, nullptr, ctx->q, nullptr, nullptr, ctx->stream));
+        LAUNCHED(1);
+    } else FAIL(PFEM_ERR_BAD_INPUT, "unknown kernel variant %d", variant);
+    k_select_fixed<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->fixed, ctx->r, ctx->q, ctx->q);
     KCHECK(); LAUNCHED(1);
-    CU(cudaMemcpyAsync(q, ctx->q, (size_t)g.N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(download_nodes(ctx, q, ctx->q));
     CU(cudaStreamSynchronize(ctx->stream));
     return PFEM_OK;
 }
@@ -865,12 +911,13 @@ extern "C" int pfem_get_rhs(pfem_ctx* ctx, double* b) {
     if (!ctx->conds_valid) FAIL(PFEM_ERR_STATE, "conductivities have not been computed");
     const Grid& g = ctx->g;
     TRY(launch_diag(ctx));
-    k_dirichlet_only<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->x, ctx->fixed, ctx->q);
-    LAUNCHED(1);
+    // q <- v_D on Dirichlet nodes, 0 elsewhere; p <- M (f - A q); b = fixed ? v_D : p
+    CU(cudaMemsetAsync(ctx->q, 0, (size_t)g.NP * sizeof(double), ctx->stream));
+    TRY(scatter_bc(ctx, ctx->q, nullptr));
     TRY(launch_apply_simple<1>(ctx, ctx->q, ctx->p));
-    k_select_fixed<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->fixed, ctx->x, ctx->p, ctx->p);
+    k_select_fixed<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->fixed, ctx->q, ctx->p, ctx->p);
     KCHECK(); LAUNCHED(1);
-    CU(cudaMemcpyAsync(b, ctx->p, (size_t)g.N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(download_nodes(ctx, b, ctx->p));
     CU(cudaStreamSynchronize(ctx->stream));
     return PFEM_OK;
 }
@@ -881,9 +928,9 @@ extern "C" int pfem_get_diag(pfem_ctx* ctx, double* d) {
     if (!ctx->conds_valid) FAIL(PFEM_ERR_STATE, "conductivities have not been computed");
     const Grid& g = ctx->g;
     TRY(launch_diag(ctx));
-    k_diag_from_dinv<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.N, ctx->dinv, ctx->fixed, ctx->q);
+    k_diag_from_dinv<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->dinv, ctx->fixed, ctx->q);
     KCHECK(); LAUNCHED(1);
-    CU(cudaMemcpyAsync(d, ctx->q, (size_t)g.N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(download_nodes(ctx, d, ctx->q));
     CU(cudaStreamSynchronize(ctx->stream));
     return PFEM_OK;
 }

@@ -25,7 +25,7 @@ def make(p, variant=0, lin_tol=1e-12, **kw):
     return s
 
 
-@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("variant", [1, 2, 0])
 def test_reference_case_fixed_loops_vs_cholesky(variant):
     """same number of loops on both sides -> potentials, currents, junction conductivities agree"""
     p = shockley3d_reference_problem()

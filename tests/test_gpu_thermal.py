@@ -25,7 +25,7 @@ def gpu_solve(p, variant=0, loops=0, lin_tol=1e-10):
     return s, err
 
 
-@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("variant", [1, 2, 0])
 def test_config_A_small_vs_cholesky(variant):
     p = cf.config_A(20)
     o = oracle_thermal(p, algorithm="cholesky")

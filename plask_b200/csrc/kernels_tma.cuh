@@ -10,6 +10,12 @@
 // and the element conductances k_I,k_J,k_K/36 into compact shared-memory planes and (2) gather the
 // 27-point operator for their nodes.  Loads for step s+NS-1 are in flight while step s computes, so
 // HBM latency is hidden without spending registers.
+//
+// TMA constraint met here (measured with tools/tma_probe.cu on a B200): the start address of a box
+// must be 16-byte aligned, i.e. with 8-byte elements the innermost box coordinate must be EVEN —
+// an odd one faults with "illegal instruction".  Tiles start at multiples of TI (even), so the box
+// carries a TWO-node halo on the low-I side and on the high-I side (HX = 2, box width TI + 4), of
+// which one column each side is used; rows (J) and planes (K) have no such constraint.
 #pragma once
 #include <cuda.h>
 #include <stdio.h>
@@ -52,7 +58,8 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 
 template <int TI, int TJ>
 struct TmaTile {
-    static constexpr int PW = TI + 2, PH = TJ + 2;
+    static constexpr int HX = 2;                        // halo columns on each side of the tile (see header)
+    static constexpr int PW = TI + 2 * HX, PH = TJ + 2;
     static constexpr int BOX = PW * PH;                 // doubles moved per box
     static constexpr int BOXP = (BOX + 15) / 16 * 16;   // 128-byte aligned box slot
     static constexpr size_t smem_bytes(int ns, bool fused) {
@@ -71,7 +78,7 @@ k_apply_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CU
     constexpr int NT = TI * (TJ / RJ);
     constexpr int NBN = FUSED ? 3 : 1;  // node boxes per stage
     constexpr int NB = NBN + 2;         // + c_lat, c_vert
-    constexpr int PW = T::PW, BOX = T::BOX, BOXP = T::BOXP;
+    constexpr int PW = T::PW, BOX = T::BOX, BOXP = T::BOXP, HX = T::HX;
     extern __shared__ unsigned char smem_dyn[];
     double* base = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
     double* sRaw = base;                          // [NS][NB][BOXP]
@@ -98,14 +105,14 @@ k_apply_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CU
         uint64_t* bar = &bars[st];
         mbar_expect_tx(bar, (uint32_t)((NBN + (t > 0 ? 2 : 0)) * BOX * sizeof(double)));
         const int P = k0 - 1 + t;
-        tma_load_3d(dst, &tm_p, bar, i0 - 1, j0 - 1, P);
+        tma_load_3d(dst, &tm_p, bar, i0 - HX, j0 - 1, P);
         if (FUSED) {
-            tma_load_3d(dst + BOXP, &tm_r, bar, i0 - 1, j0 - 1, P);
-            tma_load_3d(dst + 2 * BOXP, &tm_d, bar, i0 - 1, j0 - 1, P);
+            tma_load_3d(dst + BOXP, &tm_r, bar, i0 - HX, j0 - 1, P);
+            tma_load_3d(dst + 2 * BOXP, &tm_d, bar, i0 - HX, j0 - 1, P);
         }
         if (t > 0) {
-            tma_load_3d(dst + NBN * BOXP, &tm_cl, bar, i0 - 1, j0 - 1, P - 1);
-            tma_load_3d(dst + (NBN + 1) * BOXP, &tm_cv, bar, i0 - 1, j0 - 1, P - 1);
+            tma_load_3d(dst + NBN * BOXP, &tm_cl, bar, i0 - HX, j0 - 1, P - 1);
+            tma_load_3d(dst + (NBN + 1) * BOXP, &tm_cv, bar, i0 - HX, j0 - 1, P - 1);
         }
     };
     // p_new of node plane P from stage st into plane buffer `buf`; owned nodes are stored to pout
@@ -119,8 +126,8 @@ k_apply_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CU
                 v = raw[2 * BOXP + m] * raw[BOXP + m] + beta * raw[m];
                 if (own_k) {
                     const int jj = m / PW, ii = m - jj * PW;
-                    const int i = i0 + ii - 1, j = j0 + jj - 1;
-                    if (ii >= 1 && ii <= TI && jj >= 1 && jj <= TJ && i < g.nI && j < g.nJ) pout[i + g.sJ * j + g.sK * P] = v;
+                    const int i = i0 + ii - HX, j = j0 + jj - 1;
+                    if (ii >= HX && ii < HX + TI && jj >= 1 && jj <= TJ && i < g.nI && j < g.nJ) pout[i + g.sJ * j + g.sK * P] = v;
                 }
             } else {
                 v = raw[m];
@@ -136,7 +143,7 @@ k_apply_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CU
         const double s = 1e-6 / 36.;
         for (int m = tid; m < BOX; m += NT) {
             const int jj = m / PW, ii = m - jj * PW;
-            const int ei = min(i0 + ii - 1, g.nI - 1), ej = min(j0 + jj - 1, g.nJ - 1);  // >= -1 by construction
+            const int ei = min(max(i0 + ii - HX, -1), g.nI - 1), ej = min(j0 + jj - 1, g.nJ - 1);  // guards of hI/hJ: -1 .. n-1
             const double a = raw[m], b = raw[BOXP + m];
             const double hi = g.hI[ei], hj = g.hJ[ej];
             const double cI = (g.vdim == 0 ? b : a) * s, cJ = (g.vdim == 1 ? b : a) * s, cK = (g.vdim == 2 ? b : a) * s;
@@ -186,15 +193,15 @@ k_apply_tma(const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CU
             for (int dj = 0; dj < 3; ++dj)
 #pragma unroll
                 for (int di = 0; di < 3; ++di) {
-                    a[dj][di] = Pa[(jl + dj) * PW + tx + di];
-                    b[dj][di] = Pb[(jl + dj) * PW + tx + di];
+                    a[dj][di] = Pa[(jl + dj) * PW + tx + di + (HX - 1)];
+                    b[dj][di] = Pb[(jl + dj) * PW + tx + di + (HX - 1)];
                 }
             double lo = 0., hi = 0., cc = 0.;
 #pragma unroll
             for (int sj = 0; sj < 2; ++sj)
 #pragma unroll
                 for (int si = 0; si < 2; ++si) {
-                    const int ce = (jl + sj) * PW + tx + si;
+                    const int ce = (jl + sj) * PW + tx + si + (HX - 1);
                     const double kI = sC[ce], kJ = sC[BOXP + ce], kK = sC[2 * BOXP + ce];
                     const int on = sj ? 2 : 0;
                     const int cn = si ? 2 : 0;
@@ -298,7 +305,7 @@ static inline TmaPlan make_tma_plan(const Grid& g, int sm_count, double* p0, dou
     p.lk = lk;
     p.chunksK = (g.nK + lk - 1) / lk;
     if ((g.sJ * 8) % 16 != 0 || (g.sK * 8) % 16 != 0) { snprintf(p.why, sizeof p.why, "row pitch is not a multiple of 16 bytes"); return p; }
-    const int bw = p.ti + 2, bh = p.tj + 2;
+    const int bw = p.ti + 4, bh = p.tj + 2;   // TmaTile::PW x PH
     bool ok = make_lattice_map(&p.m_p[0], p0, g.nI, g.nJ, g.nK, g.sJ, g.sK, bw, bh) &&
               make_lattice_map(&p.m_p[1], p1, g.nI, g.nJ, g.nK, g.sJ, g.sK, bw, bh) &&
               make_lattice_map(&p.m_r, r, g.nI, g.nJ, g.nK, g.sJ, g.sK, bw, bh) &&

@@ -127,7 +127,9 @@ typedef struct {
     double outer_tol; /* maxerr of the nonlinear loop: K (thermal) or % (electrical)        */
     int loops;        /* max nonlinear loops in this call, 0 = until converged              */
     int batch;        /* PCG iterations per captured CUDA graph launch (0 = default)        */
-    int variant;      /* 0 = production kernels, 1 = simple reference kernels (tests)       */
+    int variant;      /* 3 = production: fused single-kernel PCG iteration (default);
+                       * 0 = two-kernel iteration, TMA operator kernel; 2 = same with LDG tiles;
+                       * 1 = simple one-thread-per-node reference kernels (tests)            */
     int reserved[5];
 } pfem_opts;
 

@@ -188,7 +188,7 @@ k_update(idx_t N, double* __restrict__ x, double* __restrict__ r, const double* 
         if (threadIdx.x == 0) {
             if (INIT) {
                 sc->rho = v[0]; sc->rho_prev = v[0]; sc->rr = v[1]; sc->zz = v[2]; sc->xx = v[3];
-                sc->beta = 0.; sc->alpha = 0.; sc->pq = 0.; sc->iter = 0; sc->status = 0; sc->done = 0;
+                sc->beta = 0.; sc->alpha = 0.; sc->pq = 0.; sc->iter = 0; sc->launch = 0; sc->status = 0; sc->done = 0;
                 if (!(v[1] == v[1])) { sc->done = 1; sc->status = -2; }
                 else if (!sc->bench && v[1] <= sc->tol2 * sc->bb && v[0] <= sc->tol2 * sc->bz && v[2] <= sc->tol2 * v[3]) { sc->done = 1; sc->status = 1; }
             } else {

@@ -58,6 +58,8 @@ struct Scalars {
     int status;       // 0 running, 1 converged, 2 maxit, -1 breakdown (p.Ap <= 0), -2 non-finite
     int bench;        // 1: ignore breakdown / convergence
     int neg_diag;     // a free row has a negative diagonal (NSPCG ier = -4)
+    int launch;       // fused kernel: launches since the start of the solve (launch m has applied m-1 updates)
+    int pad_;
     unsigned int ticket[8];
 };
 

@@ -16,6 +16,7 @@
 #include "kernels_simple.cuh"
 #include "kernels_tiled.cuh"
 #include "kernels_tma.cuh"
+#include "kernels_fused.cuh"
 
 using namespace pfem;
 
@@ -34,7 +35,8 @@ struct pfem_ctx {
     Grid g;
     std::vector<DevArr> allocs;
     // node arrays (pointers already offset by the guard band)
-    double *x = nullptr, *xprev = nullptr, *r = nullptr, *p = nullptr, *p2 = nullptr, *q = nullptr, *dinv = nullptr, *f = nullptr;
+    double *x = nullptr, *xprev = nullptr, *r = nullptr, *r2 = nullptr, *p = nullptr, *p2 = nullptr, *q = nullptr, *q2 = nullptr,
+           *dinv = nullptr, *f = nullptr;
     uint8_t* fixed = nullptr;
     idx_t* bc_node = nullptr;   // de-duplicated Dirichlet nodes (device lattice indices) and values
     double* bc_val = nullptr;
@@ -73,6 +75,7 @@ struct pfem_ctx {
     int sm_count = 148;
     TiledPlan plan;
     TmaPlan tma;
+    FusedPlan fused;
 };
 
 #define CU(call)                                                                                         \
@@ -216,7 +219,7 @@ extern "C" void pfem_default_opts(pfem_opts* o) {
     o->outer_tol = 0.05;
     o->loops = 0;
     o->batch = 0;
-    o->variant = 0;
+    o->variant = 3;
 }
 
 // ------------------------------------------------------------------------ mesh ----------
@@ -290,6 +293,8 @@ extern "C" int pfem_set_mesh(pfem_ctx* ctx, const size_t n[3], const double* ax0
     TRY(dev_alloc(ctx, &ctx->p, N, G));
     TRY(dev_alloc(ctx, &ctx->p2, N, G));
     TRY(dev_alloc(ctx, &ctx->q, N, G));
+    TRY(dev_alloc(ctx, &ctx->r2, N, G));
+    TRY(dev_alloc(ctx, &ctx->q2, N, G));
     TRY(dev_alloc(ctx, &ctx->dinv, N, G));
     TRY(dev_alloc(ctx, &ctx->f, N, G));
     TRY(dev_alloc(ctx, &ctx->cl, N, G));
@@ -307,6 +312,12 @@ extern "C" int pfem_set_mesh(pfem_ctx* ctx, const size_t n[3], const double* ax0
     ctx->loopno = 0;
     ctx->plan = make_tiled_plan(g, ctx->sm_count);
     ctx->tma = make_tma_plan(g, ctx->sm_count, ctx->p, ctx->p2, ctx->r, ctx->dinv, ctx->cl, ctx->cv);
+    {
+        double* const rr[2] = {ctx->r, ctx->r2};
+        double* const qq[2] = {ctx->q, ctx->q2};
+        double* const pp[2] = {ctx->p, ctx->p2};
+        ctx->fused = make_fused_plan(g, ctx->sm_count, rr, qq, pp, ctx->dinv, ctx->cl, ctx->cv);
+    }
     ctx->nbc = 0;
     ctx->bc_node = nullptr;
     ctx->bc_val = nullptr;
@@ -598,6 +609,16 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
     double* pout = parity ? ctx->p : ctx->p2;
     const double* pnew = (variant == 1) ? ctx->p : pout;
     if (ev) cudaEventRecord(ev[0], ctx->stream);
+    if (variant == 3) {
+        // the whole iteration in one kernel: inputs r,q,p[parity] -> outputs r,q,p[1-parity], x in place
+        double* const rr[2] = {ctx->r, ctx->r2};
+        double* const qq[2] = {ctx->q, ctx->q2};
+        double* const pp[2] = {ctx->p, ctx->p2};
+        launch_fused_dispatch<true>(ctx->fused, g, parity, rr[1 - parity], qq[1 - parity], pp[1 - parity], ctx->x, ctx->d_sc,
+                                    ctx->partials, ctx->stream);
+        if (ev) { cudaEventRecord(ev[1], ctx->stream); cudaEventRecord(ev[2], ctx->stream); }
+        return 1;
+    }
     if (variant == 1) {
         k_pupdate<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->r, ctx->dinv, ctx->p, ctx->d_sc);
         k_apply_simple<0><<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->cl, ctx->cv, ctx->p, ctx->dinv, ctx->f,
@@ -620,7 +641,7 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
     return launched;
 }
 
-static int kernels_per_iteration(int variant) { return variant == 1 ? 3 : 2; }  // variants 0 (TMA) and 2 (LDG tiled) fuse the p-update
+static int kernels_per_iteration(int variant) { return variant == 1 ? 3 : (variant == 3 ? 1 : 2); }  // variants 0 (TMA) and 2 (LDG tiled) fuse the p-update
 
 static int build_graph(pfem_ctx* ctx, int batch, int variant, int precond) {
     if (ctx->graph && ctx->graph_batch == batch && ctx->graph_variant == variant && ctx->graph_precond == precond)
@@ -660,6 +681,7 @@ static int pcg_prepare(pfem_ctx* ctx, const pfem_opts* o, int bench) {
     // r0 = M (f - A x)
     TRY(launch_apply_simple<1>(ctx, ctx->x, ctx->r));
     CU(cudaMemsetAsync(ctx->p, 0, (size_t)g.NP * sizeof(double), ctx->stream));
+    CU(cudaMemsetAsync(ctx->q, 0, (size_t)g.NP * sizeof(double), ctx->stream));   // fused kernel: r' = r - 0*q on the first launch
     k_update<true><<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->x, ctx->r, ctx->p, ctx->q, ctx->dinv, ctx->d_sc,
                                                               ctx->partials);
     LAUNCHED(1);
@@ -694,7 +716,8 @@ static int check_opts(pfem_ctx* ctx, const pfem_opts* o) {
     if (o->maxit <= 0) FAIL(PFEM_ERR_BAD_INPUT, "maxit must be positive");
     if (!(o->lin_tol > 0.)) FAIL(PFEM_ERR_BAD_INPUT, "lin_tol must be positive");
     if (o->precond != 0) FAIL(PFEM_ERR_BAD_INPUT, "preconditioner %d is not implemented", o->precond);
-    if (o->variant < 0 || o->variant > 2) FAIL(PFEM_ERR_BAD_INPUT, "unknown kernel variant %d", o->variant);
+    if (o->variant < 0 || o->variant > 3) FAIL(PFEM_ERR_BAD_INPUT, "unknown kernel variant %d", o->variant);
+    if (o->variant == 3 && !ctx->fused.valid) FAIL(PFEM_ERR_STATE, "fused PCG kernel unavailable: %s", ctx->fused.why);
     if (o->variant == 0 && !ctx->tma.valid) FAIL(PFEM_ERR_STATE, "TMA operator kernel unavailable: %s", ctx->tma.why);
     if (o->variant == 2 && !ctx->plan.valid) FAIL(PFEM_ERR_STATE, "no tiled kernel plan for this mesh");
     return PFEM_OK;
@@ -892,6 +915,10 @@ extern "C" int pfem_apply(pfem_ctx* ctx, const double* p, double* q, int variant
     } else if (variant == 2) {
         if (!ctx->plan.valid) FAIL(PFEM_ERR_STATE, "no tiled kernel plan for this mesh");
         CU(launch_apply_tiled_plain(ctx->plan, g, ctx->cl, ctx->cv, ctx->dinv, ctx->p, ctx->q, ctx->stream));
+        LAUNCHED(1);
+    } else if (variant == 3) {
+        if (!ctx->fused.valid) FAIL(PFEM_ERR_STATE, "fused PCG kernel unavailable: %s", ctx->fused.why);
+        CU(launch_fused_dispatch<false>(ctx->fused, g, 0, nullptr, ctx->q, nullptr, nullptr, nullptr, nullptr, ctx->stream));
         LAUNCHED(1);
     } else if (variant == 0) {
         if (!ctx->tma.valid) FAIL(PFEM_ERR_STATE, "TMA operator kernel unavailable: %s", ctx->tma.why);

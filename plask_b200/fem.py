@@ -167,7 +167,7 @@ class DeviceFem:
         assert c.size == 2 * self.E
         self._ck(self.lib.pfem_set_conductivity(self.ctx, _dp(c)))
 
-    def apply(self, p, variant=0):
+    def apply(self, p, variant=3):
         p = _f64(p)
         q = np.empty(self.N)
         self._ck(self.lib.pfem_apply(self.ctx, _dp(p), _dp(q), int(variant)))

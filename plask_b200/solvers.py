@@ -41,7 +41,7 @@ class _FemSolver:
         self.algorithm = "cuda"
         self.iterative = IterativeParams()
         self.device = 0
-        self.variant = 0            # 0 production kernels, 1 simple reference kernels
+        self.variant = 3            # 3 production (fused single-kernel iteration); 0/2 two-kernel; 1 simple reference kernels
         self._fem = None
         self._problem = None
         self.initialized = False

@@ -48,7 +48,7 @@ def test_operator_rhs_diag_all_orders(order, n):
     v = rng.standard_normal(p.N)
     q_ref = A.mult(v)
     scale = np.abs(A.data[:p.N]).max() * np.abs(v).max()
-    for variant in (1, 2, 0):
+    for variant in (1, 2, 0, 3):
         q = f.apply(v, variant=variant)
         assert np.abs(q - q_ref).max() <= 2e-14 * scale, (variant, np.abs(q - q_ref).max() / scale)
     # load vector after applyBC and the diagonal
@@ -75,7 +75,7 @@ def test_operator_tile_edges(n, order):
     v = rng.standard_normal(p.N)
     q_ref = A.mult(v)
     scale = np.abs(A.data[:p.N]).max() * np.abs(v).max()
-    for variant in (1, 2, 0):
+    for variant in (1, 2, 0, 3):
         q = f.apply(v, variant=variant)
         assert np.abs(q - q_ref).max() <= 2e-14 * scale, (variant, np.abs(q - q_ref).max() / scale)
     f.close()
@@ -92,12 +92,13 @@ def test_operator_linearity_and_symmetry_large():
     f.update_conductivity_thermal()
     rng = np.random.default_rng(11)
     u, v = rng.standard_normal(p.N), rng.standard_normal(p.N)
-    for variant in (1, 2, 0):
+    for variant in (1, 2, 0, 3):
         Au, Av = f.apply(u, variant=variant), f.apply(v, variant=variant)
         assert abs(u @ Av - v @ Au) <= 1e-12 * (np.abs(u @ Av) + np.linalg.norm(Au) * np.linalg.norm(v) * 1e-3)
         ones = f.apply(np.ones(p.N), variant=variant)
         assert np.abs(ones).max() <= 1e-12 * np.abs(Au).max()
-    a0, a1, a2 = f.apply(u, variant=0), f.apply(u, variant=1), f.apply(u, variant=2)
+    a0, a1, a2, a3 = f.apply(u, variant=0), f.apply(u, variant=1), f.apply(u, variant=2), f.apply(u, variant=3)
     assert np.abs(a0 - a1).max() <= 1e-13 * np.abs(a1).max()
     assert np.abs(a2 - a1).max() <= 1e-13 * np.abs(a1).max()
+    assert np.abs(a3 - a1).max() <= 1e-13 * np.abs(a1).max()
     f.close()

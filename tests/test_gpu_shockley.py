@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 TOL_V = 1e-6
 
 
-def make(p, variant=0, lin_tol=1e-12, **kw):
+def make(p, variant=3, lin_tol=1e-12, **kw):
     s = Shockley3D("electrical3d")
     s.problem = p
     s.beta, s.js, s.maxerr = p.beta, p.js, p.maxerr
@@ -25,7 +25,7 @@ def make(p, variant=0, lin_tol=1e-12, **kw):
     return s
 
 
-@pytest.mark.parametrize("variant", [1, 2, 0])
+@pytest.mark.parametrize("variant", [1, 2, 0, 3])
 def test_reference_case_fixed_loops_vs_cholesky(variant):
     """same number of loops on both sides -> potentials, currents, junction conductivities agree"""
     p = shockley3d_reference_problem()

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 TOL_T = 1e-3  # K, BASELINE.json north_star
 
 
-def gpu_solve(p, variant=0, loops=0, lin_tol=1e-10):
+def gpu_solve(p, variant=3, loops=0, lin_tol=1e-10):
     s = Static3D("thermal")
     s.problem = p
     s.inittemp, s.maxerr = p.inittemp, p.maxerr
@@ -25,7 +25,7 @@ def gpu_solve(p, variant=0, loops=0, lin_tol=1e-10):
     return s, err
 
 
-@pytest.mark.parametrize("variant", [1, 2, 0])
+@pytest.mark.parametrize("variant", [1, 2, 0, 3])
 def test_config_A_small_vs_cholesky(variant):
     p = cf.config_A(20)
     o = oracle_thermal(p, algorithm="cholesky")
@@ -45,7 +45,7 @@ def test_config_B_small_all_orders_vs_cholesky(order):
     p = cf.config_B((18, 20, 44), order=order)
     o = oracle_thermal(p, algorithm="cholesky")
     o.compute(0)
-    s, err = gpu_solve(p, 0)
+    s, err = gpu_solve(p)
     T = s.outTemperature()
     assert np.abs(T - o.temperatures).max() <= TOL_T, np.abs(T - o.temperatures).max()
     assert s.stats["outer_loops"] == len(o.history)
@@ -60,7 +60,7 @@ def test_vs_reference_nspcg():
     p = cf.config_B(24)
     o = oracle_thermal(p, algorithm="iterative", precond="ic", itmaxerr=1e-10, maxit=5000)
     o.compute(0)
-    s, _ = gpu_solve(p, 0)
+    s, _ = gpu_solve(p)
     assert np.abs(s.outTemperature() - o.temperatures).max() <= TOL_T
     s.invalidate()
 
@@ -70,7 +70,7 @@ def test_random_problem_linear_solve_and_flux():
     p.maxerr = 1e-6
     o = oracle_thermal(p, algorithm="cholesky")
     o.compute(3)
-    s, _ = gpu_solve(p, 0, loops=3, lin_tol=1e-12)
+    s, _ = gpu_solve(p, 3, loops=3, lin_tol=1e-12)
     T = s.outTemperature()
     assert np.abs(T - o.temperatures).max() <= 1e-6
     # heat flux provider (therm3d.cpp:342-384): conds re-evaluated at the final temperatures
@@ -96,7 +96,7 @@ def test_manufactured_parabola():
     ng = np.broadcast_to(p.node_index_grid(), n)
     p.bc_nodes = ng[:, :, 0].ravel().astype(np.uintp)
     p.bc_values = np.full(p.bc_nodes.size, 300.)
-    s, _ = gpu_solve(p, 0, lin_tol=1e-12)
+    s, _ = gpu_solve(p, 3, lin_tol=1e-12)
     T = s.outTemperature()[ng]
     z = axes[2] * 1e-6
     exact = 300. + Q * (2 * H * 1e-6 * z - z * z) / (2 * k)
@@ -106,7 +106,7 @@ def test_manufactured_parabola():
 
 def test_warm_start_and_loops_limit():
     p = cf.config_B(20)
-    s, _ = gpu_solve(p, 0, loops=1)
+    s, _ = gpu_solve(p, 3, loops=1)
     assert s.stats["outer_loops"] == 1 and s.loopno == 1
     s.compute(1)
     assert s.loopno == 2

@@ -31,8 +31,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-BYTES_PER_DOF_ITER = 112.0   # 14 FP64 words: SURVEY.md §8(d), DESIGN.md §5
-BYTES_PER_DOF_APPLY = 56.0   # operator kernel: reads r, D^-1, p_old, c_lat, c_vert; writes p_new, q
+BYTES_PER_DOF_FUSED = 88.0   # k_fpcg, one launch = one iteration: reads r q p D^-1 x c_lat c_vert, writes r p q x
+BYTES_PER_DOF_ITER = 112.0   # two-kernel iteration (variants 0/2): 14 FP64 words, SURVEY.md §8(d)
+BYTES_PER_DOF_APPLY = 56.0   # two-kernel operator kernel: reads r, D^-1, p_old, c_lat, c_vert; writes p_new, q
 FALLBACK_HBM_GBS = 6650.0    # /opt/skills/guides/B200_PROFILING.md
 
 
@@ -46,7 +47,7 @@ def measured_peak():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -65,9 +66,14 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_first_sample(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.05)
+
+    def stop(self, window=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -76,7 +82,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons, pw = [], [], set(), []
-        for r in self.rows:
+        rows = [r for (ts, r) in self.rows if window is None or window[0] <= ts <= window[1] + 0.15]
+        if not rows:   # region shorter than one sampling period: take the samples closest to it
+            rows = [r for (ts, r) in self.rows[-3:]]
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -197,10 +206,12 @@ def run_ours(args):
     for _ in range(args.warmup):
         f.bench_pcg(iters, **opts)
     sampler = ClockSampler(local)
-    barrier()
     if rank == 0:
         sampler.start()
+        sampler.wait_first_sample()
+    barrier()
     ms, launches = [], 0
+    t_win0 = time.time()
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         r = f.bench_pcg(iters, **opts)
@@ -208,7 +219,7 @@ def run_ours(args):
         launches += r["launches"]
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop((t_win0, time.time())) if rank == 0 else None
     t_dev = sum(ms) * 1e-3
     if world > 1:
         t = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
@@ -216,26 +227,39 @@ def run_ours(args):
         t_dev = float(t.item())
     value = world * N * iters * args.steps / t_dev
 
-    # ---- per-kernel split (events between kernels, no graph) for the roofline of the operator kernel
-    split = f.bench_pcg(min(iters, 20), split_timing=True, **opts)
-    n_split = min(iters, 20)
-    apply_ms = split["apply_ms"] / n_split
-    update_ms = split["update_ms"] / n_split
+    # ---- roofline of the dominant kernel
     peak, how = measured_peak()
-    achieved = BYTES_PER_DOF_APPLY * N / (apply_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_apply_tiled (fused p-update + 27-point brick operator + p.q)" if args.variant == 0
-                else "k_apply_simple", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": how, "traffic": None, "algorithmic_bytes_per_launch": BYTES_PER_DOF_APPLY * N,
-                "avg_launch_ms": apply_ms,
-                "update_kernel": {"achieved": BYTES_PER_DOF_APPLY * N / (update_ms * 1e-3) / 1e9, "avg_launch_ms": update_ms},
-                "iteration": {"achieved": BYTES_PER_DOF_ITER * N * iters * args.steps / (sum(ms) * 1e-3) / 1e9,
-                              "frac": BYTES_PER_DOF_ITER * N * iters * args.steps / (sum(ms) * 1e-3) / 1e9 / peak}}
+    traffic = None
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get("apply_dram_bytes_per_launch")
+            traffic = json.load(open(traffic_file)).get("k_fpcg_dram_bytes_per_launch" if args.variant == 3 else "apply_dram_bytes_per_launch")
         except Exception:
             pass
+    if args.variant == 3:
+        # one kernel per iteration: its average launch duration IS the timed region / launches (CUDA events on
+        # the library's stream around the graph launches)
+        launch_ms = sum(ms) / max(launches, 1)
+        achieved = BYTES_PER_DOF_FUSED * N / (launch_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_fpcg (whole PCG iteration: update + new direction + matrix-free 27-point operator + 7 dots)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": how,
+                    "traffic": traffic, "algorithmic_bytes_per_launch": BYTES_PER_DOF_FUSED * N, "bytes_per_dof": BYTES_PER_DOF_FUSED,
+                    "avg_launch_ms": launch_ms,
+                    "note": "two-kernel formulation of SURVEY 8(d) is 112 B/DOF: the same time would read %.0f GB/s on that basis"
+                            % (BYTES_PER_DOF_ITER * N / (launch_ms * 1e-3) / 1e9)}
+    else:
+        # per-kernel split (events between kernels, no graph) for the roofline of the operator kernel
+        split = f.bench_pcg(min(iters, 20), split_timing=True, **opts)
+        n_split = min(iters, 20)
+        apply_ms = split["apply_ms"] / n_split
+        update_ms = split["update_ms"] / n_split
+        achieved = BYTES_PER_DOF_APPLY * N / (apply_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_apply_tma (p-update + 27-point brick operator + p.q)" if args.variant == 0 else "k_apply",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": how, "traffic": traffic,
+                    "algorithmic_bytes_per_launch": BYTES_PER_DOF_APPLY * N, "avg_launch_ms": apply_ms,
+                    "update_kernel": {"achieved": BYTES_PER_DOF_APPLY * N / (update_ms * 1e-3) / 1e9, "avg_launch_ms": update_ms},
+                    "iteration": {"achieved": BYTES_PER_DOF_ITER * N * iters * args.steps / (sum(ms) * 1e-3) / 1e9,
+                                  "frac": BYTES_PER_DOF_ITER * N * iters * args.steps / (sum(ms) * 1e-3) / 1e9 / peak}}
 
     # ---- end to end through the public API with host buffers (pinned), H2D + D2H inside the timed region
     heat_h, _k1 = pinned_copy(np.ascontiguousarray(p.heat))
@@ -306,7 +330,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"Static3D config B: {n}^3 VCSEL-like layered block, nonlinear k(T) tables, "
                                    f"{N} DOF per GPU, Jacobi-PCG", "iters_per_step": iters,
-                       "l2": "working set >> L2 (each of the 7+7 vectors per iteration is %.0f MB)" % (N * 8 / 1e6),
+                       "l2": "inputs >> L2: every iteration streams 11 vectors of %.0f MB each, nothing survives in the 126 MB L2" % (N * 8 / 1e6),
                        "order": p.order, "kernel_variant": args.variant,
                        "multi_gpu": "independent replicas" if world > 1 else "single device"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -325,8 +349,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=256, help="nodes per axis of config B")
-    ap.add_argument("--iters", type=int, default=50, help="PCG iterations per step")
-    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--iters", type=int, default=500, help="PCG iterations per step")
+    ap.add_argument("--variant", type=int, default=3, help="3 fused single-kernel iteration (production), 0/2 two-kernel, 1 simple")
     ap.add_argument("--cpu-n", type=int, default=96)
     ap.add_argument("--cpu-iters", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")

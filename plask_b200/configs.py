@@ -254,9 +254,11 @@ def config_B(n=256, order="optimal"):
     p.elem_mat = p.to_elem_order(mat, np.uint32)
     heat = np.zeros(mat.shape)
     mesa_layers = np.isin(tagv, ["bar", "qw", "ox", "pA", "pG"])
-    heat[:, :, mesa_layers] = np.where(reg["in_mesa"][:, :, None], 1e14, 0.)
+    # ~14 mW in the active cylinder (r < r_ap, 55 nm thick) + ~6 mW of Joule heat spread over the mesa:
+    # a 20 mW device with a temperature rise of a few tens of K, so k(T) matters but stays inside the tables
+    heat[:, :, mesa_layers] = np.where(reg["in_mesa"][:, :, None], 1e12, 0.)
     cav = np.isin(tagv, ["bar", "qw"])
-    heat[:, :, cav] = np.where(reg["in_ap"][:, :, None], 5e16, heat[:, :, cav])
+    heat[:, :, cav] = np.where(reg["in_ap"][:, :, None], 5e15, heat[:, :, cav])
     p.heat = p.to_elem_order(heat, np.float64)
     bottom = np.broadcast_to(p.node_index_grid(), n)[:, :, 0].ravel()
     p.bc_nodes = bottom.astype(np.uintp)

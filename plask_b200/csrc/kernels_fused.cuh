@@ -32,6 +32,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "kernels_tma.cuh"
 
 namespace pfem {
@@ -44,15 +46,16 @@ struct FusedTile {
     static constexpr int BOXP = (BOX + 15) / 16 * 16;
     static constexpr int PWP = TI + 2;                   // p' plane pitch, rows PH
     static constexpr int PLANE = (PWP * PH + 15) / 16 * 16;
-    static constexpr int CW = TI + 1, CH = TJ + 1;       // coefficient layer, 4 doubles per element
-    static constexpr int LAYER = (CW * CH * 4 + 15) / 16 * 16;
+    static constexpr int CW = TI + 1, CH = TJ + 1;       // coefficient layer: two double2 planes per element,
+    static constexpr int CHALF = (CW * CH * 2 + 15) / 16 * 16;   // (sij, ui) then (uj, kk): conflict-free LDS.128
+    static constexpr int LAYER = 2 * CHALF;
     static constexpr int NRED = 7;
-    static constexpr size_t smem_bytes(int ns, bool fused) {
-        return 128 + sizeof(double) * ((size_t)ns * (fused ? 6 : 4) * BOXP + 2 * PLANE + 2 * LAYER + 32 * NRED) + 16 * 8 + 16;
+    static constexpr size_t smem_bytes(int ns, bool fused, int lk) {
+        return 128 + sizeof(double) * ((size_t)ns * (fused ? 6 : 4) * BOXP + 2 * PLANE + 2 * LAYER + 32 * NRED + 2 * (size_t)(lk + 2)) +
+               16 * 8 + 16;
     }
 };
 
-struct __align__(16) Coef4 { double sij, ui, uj, kk; };
 
 template <int TJ, int RJ, int NS, int MINB, int VDIM, bool FUSED>
 __global__ void __launch_bounds__(32 * (TJ / RJ), MINB)
@@ -63,7 +66,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
        Scalars* sc, double* partials) {
     typedef FusedTile<TJ> T;
     constexpr int TI = T::TI, HX = T::HX, PW = T::PW, PH = T::PH, BOX = T::BOX, BOXP = T::BOXP, PWP = T::PWP;
-    constexpr int PLANE = T::PLANE, CW = T::CW, CH = T::CH, LAYER = T::LAYER, NRED = T::NRED;
+    constexpr int PLANE = T::PLANE, CW = T::CW, CHALF = T::CHALF, LAYER = T::LAYER, NRED = T::NRED;
     constexpr int NT = TI * (TJ / RJ);
     constexpr int NBN = FUSED ? 4 : 2;   // node boxes per stage: r q p d | p d
     constexpr int NB = NBN + 2;          // + c_lat, c_vert
@@ -78,6 +81,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
     double* const sRed = sC + 2 * LAYER;                // [32*NRED]
     uint64_t* const bars = reinterpret_cast<uint64_t*>(sRed + 32 * NRED);  // [NS]
     int* const sh_flag = reinterpret_cast<int*>(bars + 16);
+    double* const sHK = reinterpret_cast<double*>(bars + 18);   // [lk+2] hK and [lk+2] 1/hK of the element layers of this chunk
 
     if (FUSED && sc->done) return;
     const double alpha = FUSED ? sc->alpha : 0.;
@@ -156,6 +160,13 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         }
     };
 
+    // spacings of the element layers k0-2 .. k1-1 (entry t = layer of step t), staged once: a global load per
+    // step would sit on the critical path of every warp
+    for (int t = tid; t <= nsteps; t += NT) {
+        const int Lc = min(max(k0 - 2 + t, -1), g.nK - 1);
+        sHK[t] = g.hK[Lc];
+        sHK[lk + 2 + t] = g.rK[Lc];
+    }
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) mbar_init(&bars[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -166,51 +177,56 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         for (int t = 0; t < NS && t <= nsteps; ++t) issue(t);
 
     // ---- state carried along the march ----------------------------------------------------
-    double wa[RJ + 2][3];          // p' window of the plane below (registers)
-    double carry[RJ];              // contribution of the layer below to the current plane
-    double za[RJ], da[RJ];         // z and D^-1 of the own nodes of the plane below
+    // The p' windows and (z, D^-1) of the own nodes ping-pong between two register sets so that
+    // "plane above" becomes "plane below" without moves: step(t) reads set A (plane below), fills set B.
+    double w0[RJ + 2][3], w1[RJ + 2][3];
+    double zd0[2 * RJ], zd1[2 * RJ];   // z[rr], D^-1[rr]
+    double carry[RJ];                  // contribution of the layer below to the current plane
 #pragma unroll
     for (int y = 0; y < RJ + 2; ++y)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) wa[y][c] = 0.;
+        for (int c = 0; c < 3; ++c) { w0[y][c] = 0.; w1[y][c] = 0.; }
 #pragma unroll
-    for (int rr = 0; rr < RJ; ++rr) { carry[rr] = 0.; za[rr] = 0.; da[rr] = 0.; }
+    for (int rr = 0; rr < RJ; ++rr) { carry[rr] = 0.; zd0[rr] = zd0[RJ + rr] = zd1[rr] = zd1[RJ + rr] = 0.; }
     double red[NRED];              // pq, rz, qz, qdq, rr, zz, xx
 #pragma unroll
     for (int a = 0; a < NRED; ++a) red[a] = 0.;
+
+    // lattice index of the own nodes in the plane of the current step (advanced by sK per step)
+    idx_t nown[RJ];
+#pragma unroll
+    for (int rr = 0; rr < RJ; ++rr) nown[rr] = i + g.sJ * (j0 + jl0 + rr) + g.sK * (idx_t)(k0 - 1);
+    const idx_t sK = g.sK;
 
     // x of the own nodes, fetched one step ahead
     double xn[RJ];
 #pragma unroll
     for (int rr = 0; rr < RJ; ++rr) xn[rr] = 0.;
-    auto fetch_x = [&](int P) {
-        if (!FUSED) return;
-        if (P >= k0 && P < k1) {
-#pragma unroll
-            for (int rr = 0; rr < RJ; ++rr)
-                if (vj[rr]) xn[rr] = x[i + g.sJ * (j0 + jl0 + rr) + g.sK * P];
-        }
-    };
-    fetch_x(k0 - 1);
 
-    for (int t = 0; t <= nsteps; ++t) {
+    // OWN: plane P = k0-1+t is owned (store r', p', x');  NEXT_OWN: plane P+1 is owned (prefetch x)
+    // GATHER: t >= 1 (element layer P-1 exists);  FINAL: plane P-1 is owned (store q', dots)
+    auto step = [&](auto own_c, auto next_own_c, auto gather_c, auto final_c, const int t, double (&wa)[RJ + 2][3],
+                    double (&wb)[RJ + 2][3], double (&zda)[2 * RJ], double (&zdb)[2 * RJ]) {
+        constexpr bool OWN = decltype(own_c)::value, NEXT_OWN = decltype(next_own_c)::value;
+        constexpr bool GATHER = decltype(gather_c)::value, FINAL = decltype(final_c)::value;
         const int st = t % NS;
-        const int P = k0 - 1 + t;                 // node plane of this step
-        const bool own_plane = (P >= k0 && P < k1);
         const double* raw = sRaw + (size_t)st * NB * BOXP;
         double* sPb = sP + (t & 1) * PLANE;
         double* sCb = sC + (t & 1) * LAYER;
         double xcur[RJ];
+        if (FUSED && OWN) {
 #pragma unroll
-        for (int rr = 0; rr < RJ; ++rr) xcur[rr] = xn[rr];
-        fetch_x(P + 1);
-        const int L = P - 1;                      // element layer of this step (t >= 1)
-        const int Lc = min(max(L, -1), g.nK - 1);
-        const double hk = g.hK[Lc], rk = g.rK[Lc];
+            for (int rr = 0; rr < RJ; ++rr) xcur[rr] = xn[rr];
+        }
+        if (FUSED && NEXT_OWN) {
+#pragma unroll
+            for (int rr = 0; rr < RJ; ++rr)
+                if (vj[rr]) xn[rr] = x[nown[rr] + sK];
+        }
+        const double hk = sHK[t], rk = sHK[lk + 2 + t];   // element layer L = P - 1 of this step (t >= 1)
         mbar_wait(&bars[st], (uint32_t)((t / NS) & 1));
 
         // ---------------- phase 1: p' plane and coefficient layer -------------------------
-        double zb[RJ], db[RJ];
 #pragma unroll
         for (int rr = 0; rr < RJ; ++rr) {
             const int ro = (jl0 + rr + 1) * PW + tx + HX;
@@ -220,31 +236,33 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
                 const double rn = fma(-alpha, q0, r0);
                 const double z = dd * rn;
                 pn = fma(beta, p0, z);
-                zb[rr] = z; db[rr] = dd;
-                if (own_plane && vj[rr]) {
-                    const idx_t n = i + g.sJ * (j0 + jl0 + rr) + g.sK * P;
-                    const double xv = fma(alpha, p0, xcur[rr]);
-                    r_out[n] = rn;
-                    p_out[n] = pn;
-                    x[n] = xv;
-                    red[1] = fma(rn, z, red[1]);
-                    red[4] = fma(rn, rn, red[4]);
-                    red[5] = fma(z, z, red[5]);
-                    red[6] = fma(xv, xv, red[6]);
+                zdb[rr] = z; zdb[RJ + rr] = dd;
+                if (OWN) {
+                    if (vj[rr]) {
+                        const idx_t n = nown[rr];
+                        const double xv = fma(alpha, p0, xcur[rr]);
+                        r_out[n] = rn;
+                        p_out[n] = pn;
+                        x[n] = xv;
+                        red[1] = fma(rn, z, red[1]);
+                        red[4] = fma(rn, rn, red[4]);
+                        red[5] = fma(z, z, red[5]);
+                        red[6] = fma(xv, xv, red[6]);
+                    }
                 }
             } else {
                 pn = raw[B_P * BOXP + ro];
-                zb[rr] = 0.; db[rr] = raw[B_D * BOXP + ro];
+                zdb[rr] = 0.; zdb[RJ + rr] = raw[B_D * BOXP + ro];
             }
             sPb[(jl0 + rr + 1) * PWP + tx + 1] = pn;
-            if (t > 0) {
+            if (GATHER) {
                 const double a = raw[B_CL * BOXP + ro], b = raw[B_CV * BOXP + ro];
                 const double kI = ((VDIM == 0 ? b : a) * wI[rr]) * hk;
                 const double kJ = ((VDIM == 1 ? b : a) * wJ[rr]) * hk;
                 const double kK = ((VDIM == 2 ? b : a) * wK[rr]) * rk;
-                Coef4 c;
-                c.sij = kI + kJ; c.ui = fma(-2., kI, kJ); c.uj = fma(-2., kJ, kI); c.kk = kK;
-                reinterpret_cast<Coef4*>(sCb)[(jl0 + rr + 1) * CW + tx + 1] = c;
+                const int co = (jl0 + rr + 1) * CW + tx + 1;
+                reinterpret_cast<double2*>(sCb)[co] = make_double2(kI + kJ, fma(-2., kI, kJ));
+                reinterpret_cast<double2*>(sCb + CHALF)[co] = make_double2(fma(-2., kJ, kI), kK);
             }
         }
         if (ring_raw >= 0) {
@@ -258,80 +276,110 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
             }
             sPb[ring_pl] = pn;
         }
-        if (er_raw >= 0 && t > 0) {
+        if (GATHER && er_raw >= 0) {
             const double a = raw[B_CL * BOXP + er_raw], b = raw[B_CV * BOXP + er_raw];
             const double kI = ((VDIM == 0 ? b : a) * wIr) * hk;
             const double kJ = ((VDIM == 1 ? b : a) * wJr) * hk;
             const double kK = ((VDIM == 2 ? b : a) * wKr) * rk;
-            Coef4 c;
-            c.sij = kI + kJ; c.ui = fma(-2., kI, kJ); c.uj = fma(-2., kJ, kI); c.kk = kK;
-            reinterpret_cast<Coef4*>(sCb)[er_c] = c;
+            reinterpret_cast<double2*>(sCb)[er_c] = make_double2(kI + kJ, fma(-2., kI, kJ));
+            reinterpret_cast<double2*>(sCb + CHALF)[er_c] = make_double2(fma(-2., kJ, kI), kK);
         }
         __syncthreads();
         if (tid == 0 && t + NS <= nsteps) issue(t + NS);
 
         // ---------------- phase 2: gather layer L between planes a (registers) and b --------
-        double wb[RJ + 2][3];
 #pragma unroll
         for (int y = 0; y < RJ + 2; ++y)
 #pragma unroll
             for (int c = 0; c < 3; ++c) wb[y][c] = sPb[(jl0 + y) * PWP + tx + c];
-        if (t > 0) {
-            double dw[RJ + 2][3];
-#pragma unroll
-            for (int y = 0; y < RJ + 2; ++y)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) dw[y][c] = wb[y][c] - wa[y][c];
-            double La[RJ], Lb[RJ], Cc[RJ], S[RJ], Tt[RJ], A0[RJ], A1[RJ], P0[RJ], P1[RJ];
-#pragma unroll
-            for (int rr = 0; rr < RJ; ++rr) { La[rr] = Lb[rr] = Cc[rr] = S[rr] = Tt[rr] = A0[rr] = A1[rr] = P0[rr] = P1[rr] = 0.; }
+        if (GATHER) {
+            // coefficients of the RJ+1 element rows x 2 element columns around the own nodes
+            double e_sij[RJ + 1][2], e_ui[RJ + 1][2], e_uj[RJ + 1][2], e_kk[RJ + 1][2];
 #pragma unroll
             for (int ey = 0; ey <= RJ; ++ey) {          // element row between window rows ey and ey+1
-                const Coef4 e0 = reinterpret_cast<const Coef4*>(sCb)[(jl0 + ey) * CW + tx];
-                const Coef4 e1 = reinterpret_cast<const Coef4*>(sCb)[(jl0 + ey) * CW + tx + 1];
-                const double Bs = e0.uj + e1.uj, Qs = e0.kk + e1.kk, Ss = e0.sij + e1.sij;
+                const int co = (jl0 + ey) * CW + tx;
 #pragma unroll
-                for (int side = 0; side < 2; ++side) {
-                    // side 0: node rr = ey (centre row ey+1, other row ey); side 1: node rr = ey-1 (centre ey, other ey+1)
-                    const int rr = side ? ey - 1 : ey;
-                    if (rr < 0 || rr >= RJ) continue;
-                    const int yo = side ? ey + 1 : ey;
-                    La[rr] = fma(Bs, wa[yo][1], La[rr]); La[rr] = fma(-e0.sij, wa[yo][0], La[rr]); La[rr] = fma(-e1.sij, wa[yo][2], La[rr]);
-                    Lb[rr] = fma(Bs, wb[yo][1], Lb[rr]); Lb[rr] = fma(-e0.sij, wb[yo][0], Lb[rr]); Lb[rr] = fma(-e1.sij, wb[yo][2], Lb[rr]);
-                    Cc[rr] = fma(2. * Qs, dw[yo][1], Cc[rr]); Cc[rr] = fma(e0.kk, dw[yo][0], Cc[rr]); Cc[rr] = fma(e1.kk, dw[yo][2], Cc[rr]);
-                    S[rr] += Ss; Tt[rr] += Qs;
-                    A0[rr] += e0.ui; A1[rr] += e1.ui; P0[rr] += e0.kk; P1[rr] += e1.kk;
+                for (int si = 0; si < 2; ++si) {
+                    const double2 ea = reinterpret_cast<const double2*>(sCb)[co + si];
+                    const double2 eb = reinterpret_cast<const double2*>(sCb + CHALF)[co + si];
+                    e_sij[ey][si] = ea.x; e_ui[ey][si] = ea.y; e_uj[ey][si] = eb.x; e_kk[ey][si] = eb.y;
                 }
+            }
+            double Bs[RJ + 1], Qs[RJ + 1], Ss[RJ + 1];   // sums over the two elements of a row
+#pragma unroll
+            for (int ey = 0; ey <= RJ; ++ey) {
+                Bs[ey] = e_uj[ey][0] + e_uj[ey][1];
+                Qs[ey] = e_kk[ey][0] + e_kk[ey][1];
+                Ss[ey] = e_sij[ey][0] + e_sij[ey][1];
             }
 #pragma unroll
             for (int rr = 0; rr < RJ; ++rr) {
-                const int yc = rr + 1;
-                const double S2 = 2. * S[rr];
-                double la = fma(S2, wa[yc][1], La[rr]); la = fma(A0[rr], wa[yc][0], la); la = fma(A1[rr], wa[yc][2], la);
-                double lb = fma(S2, wb[yc][1], Lb[rr]); lb = fma(A0[rr], wb[yc][0], lb); lb = fma(A1[rr], wb[yc][2], lb);
-                double cc = fma(4. * Tt[rr], dw[yc][1], Cc[rr]);
-                cc = fma(2. * P0[rr], dw[yc][0], cc); cc = fma(2. * P1[rr], dw[yc][2], cc);
+                const int y0 = rr, yc = rr + 1, y2 = rr + 2;   // window rows; element rows rr (below) and rr+1 (above)
+                const double S2 = 2. * (Ss[rr] + Ss[rr + 1]);
+                const double T4 = 4. * (Qs[rr] + Qs[rr + 1]);
+                const double A0 = e_ui[rr][0] + e_ui[rr + 1][0], A1 = e_ui[rr][1] + e_ui[rr + 1][1];
+                const double P0 = 2. * (e_kk[rr][0] + e_kk[rr + 1][0]), P1 = 2. * (e_kk[rr][1] + e_kk[rr + 1][1]);
+                const double Q0 = 2. * Qs[rr], Q1 = 2. * Qs[rr + 1];
+                // in-plane stiffness of planes a and b: three independent chains each
+                double la = fma(A1, wa[yc][2], fma(A0, wa[yc][0], S2 * wa[yc][1]));
+                double la0 = fma(-e_sij[rr][1], wa[y0][2], fma(-e_sij[rr][0], wa[y0][0], Bs[rr] * wa[y0][1]));
+                double la2 = fma(-e_sij[rr + 1][1], wa[y2][2], fma(-e_sij[rr + 1][0], wa[y2][0], Bs[rr + 1] * wa[y2][1]));
+                double lb = fma(A1, wb[yc][2], fma(A0, wb[yc][0], S2 * wb[yc][1]));
+                double lb0 = fma(-e_sij[rr][1], wb[y0][2], fma(-e_sij[rr][0], wb[y0][0], Bs[rr] * wb[y0][1]));
+                double lb2 = fma(-e_sij[rr + 1][1], wb[y2][2], fma(-e_sij[rr + 1][0], wb[y2][0], Bs[rr + 1] * wb[y2][1]));
+                la += la0 + la2;
+                lb += lb0 + lb2;
+                // vertical stiffness M9 (b - a) evaluated as M9 b - M9 a (same rounding class as an assembled SpMV)
+                double ca = fma(P1, wa[yc][2], fma(P0, wa[yc][0], T4 * wa[yc][1]));
+                double ca0 = fma(e_kk[rr][1], wa[y0][2], fma(e_kk[rr][0], wa[y0][0], Q0 * wa[y0][1]));
+                double ca2 = fma(e_kk[rr + 1][1], wa[y2][2], fma(e_kk[rr + 1][0], wa[y2][0], Q1 * wa[y2][1]));
+                double cb = fma(P1, wb[yc][2], fma(P0, wb[yc][0], T4 * wb[yc][1]));
+                double cb0 = fma(e_kk[rr][1], wb[y0][2], fma(e_kk[rr][0], wb[y0][0], Q0 * wb[y0][1]));
+                double cb2 = fma(e_kk[rr + 1][1], wb[y2][2], fma(e_kk[rr + 1][0], wb[y2][0], Q1 * wb[y2][1]));
+                const double cc = (cb + (cb0 + cb2)) - (ca + (ca0 + ca2));
                 const double lo = fma(2., la, lb) - cc;
                 const double hi = fma(2., lb, la) + cc;
-                const int Pa = P - 1;
-                if (Pa >= k0 && vj[rr]) {       // finalise the plane below (always < k1 here)
-                    const double qv = (da[rr] == 0.) ? 0. : carry[rr] + lo;
-                    q_out[i + g.sJ * (j0 + jl0 + rr) + g.sK * Pa] = qv;
-                    red[0] = fma(wa[yc][1], qv, red[0]);
-                    if (FUSED) {
-                        red[2] = fma(qv, za[rr], red[2]);
-                        red[3] = fma(qv * qv, da[rr], red[3]);
+                if (FINAL) {
+                    if (vj[rr]) {       // finalise the plane below
+                        const double da = zda[RJ + rr];
+                        const double qv = (da == 0.) ? 0. : carry[rr] + lo;
+                        q_out[nown[rr] - sK] = qv;
+                        red[0] = fma(wa[yc][1], qv, red[0]);
+                        if (FUSED) {
+                            red[2] = fma(qv, zda[rr], red[2]);
+                            red[3] = fma(qv * qv, da, red[3]);
+                        }
                     }
                 }
                 carry[rr] = hi;
             }
         }
 #pragma unroll
-        for (int y = 0; y < RJ + 2; ++y)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) wa[y][c] = wb[y][c];
-#pragma unroll
-        for (int rr = 0; rr < RJ; ++rr) { za[rr] = zb[rr]; da[rr] = db[rr]; }
+        for (int rr = 0; rr < RJ; ++rr) nown[rr] += sK;
+    };
+
+    {
+        typedef std::true_type Y;
+        typedef std::false_type N;
+        // t = 0: halo plane k0-1;  t = 1: first owned plane;  t = 2 .. nsteps-1: owned planes, all flags on;
+        // t = nsteps: halo plane k1.  nsteps >= 2.  Even t fills w0 from w1, odd t fills w1 from w0.
+        step(N(), Y(), N(), N(), 0, w1, w0, zd1, zd0);
+        if (nsteps == 2) {
+            step(Y(), N(), Y(), N(), 1, w0, w1, zd0, zd1);
+        } else {
+            step(Y(), Y(), Y(), N(), 1, w0, w1, zd0, zd1);
+            int t = 2;
+            for (; t + 1 < nsteps - 1; t += 2) {
+                step(Y(), Y(), Y(), Y(), t, w1, w0, zd1, zd0);
+                step(Y(), Y(), Y(), Y(), t + 1, w0, w1, zd0, zd1);
+            }
+            // one or two owned planes left; the last owned plane (t = nsteps-1) has no owned successor
+            if (t < nsteps - 1) { step(Y(), Y(), Y(), Y(), t, w1, w0, zd1, zd0); ++t; }
+            if (t & 1) step(Y(), N(), Y(), Y(), t, w0, w1, zd0, zd1);
+            else step(Y(), N(), Y(), Y(), t, w1, w0, zd1, zd0);
+        }
+        if (nsteps & 1) step(N(), N(), Y(), Y(), nsteps, w0, w1, zd0, zd1);
+        else step(N(), N(), Y(), Y(), nsteps, w1, w0, zd1, zd0);
     }
     if (!FUSED) return;
     if (grid_reduce<NRED, false>(red, partials, &sc->ticket[0], sRed, sh_flag)) {
@@ -374,7 +422,7 @@ static inline FusedPlan make_fused_plan(const Grid& g, int sm_count, double* con
                                         double* dinv, double* cl, double* cv) {
     FusedPlan f;
     memset(&f, 0, sizeof(f));
-    f.tj = 8; f.rj = 1; f.ns = 3; f.minb = 2;
+    f.tj = 8; f.rj = 2; f.ns = 2; f.minb = 3;   // measured best on B200 at 256^3 (tools/tune_fused.py)
     int lk = 0;
     const char* env = getenv("PFEM_FUSED_TILE");  // "tj,rj,ns,minb,lk" for tuning runs
     if (env) {
@@ -386,15 +434,21 @@ static inline FusedPlan make_fused_plan(const Grid& g, int sm_count, double* con
     f.tilesI = (g.nI + 31) / 32;
     f.tilesJ = (g.nJ + f.tj - 1) / f.tj;
     if (lk <= 0) {
-        // CTAs resident per wave: 2 per SM; aim for >= 4 waves but keep >= 16 planes per CTA
+        // Planes per CTA: every chunk re-stages 2 halo planes (efficiency lk/(lk+2)) and the grid should fill
+        // whole waves of sm_count*minb resident CTAs (148 SMs on B200).  Score both and take the best.
         const long long tiles = (long long)f.tilesI * f.tilesJ;
-        const long long want = 8LL * sm_count;
-        long long chunks = (want + tiles - 1) / tiles;
-        if (chunks < 1) chunks = 1;
-        lk = (int)((g.nK + chunks - 1) / chunks);
-        if (lk < 16) lk = 16;
-        if (lk > g.nK) lk = g.nK;
+        const long long resident = (long long)sm_count * f.minb;
+        double best = -1.;
+        for (int c = 1; c <= g.nK; ++c) {
+            const int l = (g.nK + c - 1) / c;
+            if (l < 8 && c > 1) break;
+            const long long ctas = tiles * ((g.nK + l - 1) / l);
+            const long long waves = (ctas + resident - 1) / resident;
+            const double eff = (double)ctas / (double)(waves * resident) * (double)l / (double)(l + 2);
+            if (eff > best + 1e-9) { best = eff; lk = l; }
+        }
     }
+    if (lk > 510) lk = 510;   // <= 8 KB of staged layer spacings per CTA
     f.lk = lk;
     f.chunksK = (g.nK + lk - 1) / lk;
     if ((g.sJ * 8) % 16 != 0 || (g.sK * 8) % 16 != 0) { snprintf(f.why, sizeof f.why, "row pitch is not a multiple of 16 bytes"); return f; }
@@ -415,12 +469,12 @@ static inline FusedPlan make_fused_plan(const Grid& g, int sm_count, double* con
 template <int TJ, int RJ, int NS, int MINB, int VDIM, bool FUSED>
 static inline cudaError_t launch_fused_inst(const FusedPlan& f, const Grid& g, int par, double* r_out, double* q_out, double* p_out,
                                             double* x, Scalars* sc, double* partials, cudaStream_t st) {
-    const size_t smem = FusedTile<TJ>::smem_bytes(NS, FUSED);
-    static bool attr_done = false;
-    if (!attr_done) {
+    const size_t smem = FusedTile<TJ>::smem_bytes(NS, FUSED, f.lk);
+    static size_t attr_done = 0;
+    if (attr_done < smem) {
         cudaError_t e = cudaFuncSetAttribute(k_fpcg<TJ, RJ, NS, MINB, VDIM, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done = smem;
     }
     dim3 grid(f.tilesI, f.tilesJ, f.chunksK), block(32, TJ / RJ, 1);
     k_fpcg<TJ, RJ, NS, MINB, VDIM, FUSED><<<grid, block, smem, st>>>(f.m_r[par], f.m_q[par], f.m_p[par], f.m_d, f.m_cl, f.m_cv, g, f.lk,

@@ -157,7 +157,7 @@ def test_full_size_properties_256():
     p = cf.config_B(256)
     s = Static3D("B")
     s.problem = p
-    s.iterative.maxerr = 1e-8
+    s.iterative.maxerr = 1e-10     # the energy balance below sums the residual over 16.7 M rows
     s.iterative.maxit = 100000
     s.compute(1)
     T = s.outTemperature()
@@ -169,7 +169,7 @@ def test_full_size_properties_256():
     f = s._fem
     total_heat = float((p.heat * 1e-18 * _elem_volumes(p)).sum())
     f.set_dirichlet(np.zeros(0, dtype=np.uintp), np.zeros(0))   # unconstrained operator
-    AT = f.apply(T, variant=0)
+    AT = f.apply(T, variant=3)
     fixed = np.zeros(p.N, dtype=bool); fixed[p.bc_nodes] = True
     reaction = -AT[fixed].sum()
     assert reaction == pytest.approx(total_heat, rel=1e-5)

@@ -16,6 +16,11 @@ timeout 900 python bench.py --steps 3 --warmup 3 ${BENCH_ARGS:-} > gpurun_out/be
 tail -n 2 gpurun_out/bench.log
 if [ "${WITH_NCU:-1}" = "1" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-     python bench.py --steps 1 --warmup 1 --iters 10 --no-tts --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+     python bench.py --steps 2 --warmup 1 --iters 10 --no-tts --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
   echo "ncu exit $?" | tee -a gpurun_out/summary.txt
+fi
+if [ "${WITH_NCU_FULL:-1}" = "1" ]; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_fpcg' -s 30 -c 2 -f -o gpurun_out/prof_fused \
+     python bench.py --steps 1 --warmup 1 --iters 10 --no-tts --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+  echo "ncu full exit $?" | tee -a gpurun_out/summary.txt
 fi

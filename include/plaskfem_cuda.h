@@ -118,6 +118,24 @@ int pfem_set_junctions(pfem_ctx* ctx, uint32_t njunc, const pfem_junction* junc,
                        const uint8_t* elem_role, double pcond, double ncond, size_t ncol, const double* junc_cond,
                        const double* beta_col, const double* js_col, int stable);
 
+/* ---- slab mode: one context per GPU, z-slab partition along the MAJOR mesh axis ------------------------
+ * (new with this library: the reference has no domain decomposition).  The plugin gives each
+ * context the LOCAL mesh = its owned node planes along the slowest-varying index plus ONE halo plane towards each
+ * existing neighbour (all arrays of the calls above in local indexing, Dirichlet nodes of halo planes included), then
+ *     pfem_slab_configure(ctx, rank, nranks, own_lo, own_hi)       owned planes = local [own_lo, own_hi)
+ *     pfem_slab_export(ctx, blob)                                  pfem_slab_blob_size() bytes
+ *     (exchange the blobs between the processes: MPI / torch.distributed all-gather — plumbing)
+ *     pfem_slab_connect(ctx, all_blobs)                            maps the peers' memory (CUDA IPC, NVLink P2P)
+ * ONE PROCESS PER GPU.  Every solve call is then COLLECTIVE: all ranks must make the same calls in the same order.
+ * Per PCG iteration the boundary planes of r, q, p are written straight into the neighbours' halo planes by the
+ * iteration kernel and the 7 CG scalars are exchanged once through peer inboxes (no separate collective launch);
+ * all ranks obtain bit-identical scalars.  pfem_get_field returns the local field with up-to-date halo planes.
+ * Implemented for pfem_solve_thermal and pfem_solve_linear (kernel variant 3). */
+size_t pfem_slab_blob_size(void);
+int pfem_slab_configure(pfem_ctx* ctx, int rank, int nranks, size_t own_lo, size_t own_hi);
+int pfem_slab_export(pfem_ctx* ctx, void* blob);
+int pfem_slab_connect(pfem_ctx* ctx, const void* blobs);
+
 /* ---- solve --------------------------------------------------------------------------- */
 
 typedef struct {

@@ -70,6 +70,10 @@ SYMBOLS = {
     "pfem_set_elem_temperature": (C.c_int, [_vp, c_dp, C.c_double]),
     "pfem_set_junctions": (C.c_int, [_vp, C.c_uint32, C.POINTER(Junction), _u32p, _u8p, C.c_double, C.c_double, c_sz,
                                      c_dp, c_dp, c_dp, C.c_int]),
+    "pfem_slab_blob_size": (c_sz, []),
+    "pfem_slab_configure": (C.c_int, [_vp, C.c_int, C.c_int, c_sz, c_sz]),
+    "pfem_slab_export": (C.c_int, [_vp, _vp]),
+    "pfem_slab_connect": (C.c_int, [_vp, _vp]),
     "pfem_default_opts": (None, [C.POINTER(Opts)]),
     "pfem_solve_thermal": (C.c_int, [_vp, C.POINTER(Opts), C.POINTER(Stats)]),
     "pfem_solve_shockley": (C.c_int, [_vp, C.POINTER(Opts), C.POINTER(Stats)]),

@@ -215,10 +215,15 @@ def _vcsel_vertical(ne):
     return np.array(h), tag
 
 
-def _vcsel(n, order, kind, r_ap=4., r_mesa=15., hmin=0.25, hmax=4.):
+def _vcsel(n, order, kind, r_ap=4., r_mesa=15., hmin=0.25, hmax=4., rows0=None):
+    """rows0 = (lo, hi): keep only node rows lo..hi-1 of axis 0 (direct construction of one slab of a large
+    mesh without ever building the global arrays; the structure depends on the coordinates only)."""
     n = (n, n, n) if np.isscalar(n) else tuple(n)
     ax0 = graded_axis(n[0], hmin, hmax)
     ax1 = graded_axis(n[1], hmin, hmax)
+    if rows0 is not None:
+        ax0 = ax0[rows0[0]:rows0[1]]
+        n = (len(ax0), n[1], n[2])
     hz, tag = _vcsel_vertical(n[2] - 1)
     ax2 = np.concatenate([[0.], np.cumsum(hz)])
     if order == "optimal":
@@ -246,9 +251,11 @@ def _vcsel(n, order, kind, r_ap=4., r_mesa=15., hmin=0.25, hmax=4.):
     return n, [ax0, ax1, ax2], order, mat, tagv, dict(in_mesa=in_mesa, in_ap=in_ap, ring=ring)
 
 
-def config_B(n=256, order="optimal"):
+def config_B(n=256, order="optimal", rows0=None):
     """Static3D, VCSEL-like layered block with nonlinear k(T) (BASELINE configs[1], 256^3)."""
-    n, axes, order, mat, tagv, reg = _vcsel(n, order, "thermal")
+    if rows0 is not None and order == "optimal":
+        order = optimal_order((n, n, n) if np.isscalar(n) else tuple(n))
+    n, axes, order, mat, tagv, reg = _vcsel(n, order, "thermal", rows0=rows0)
     T0, dT, lat, vert = thermal_tables()
     p = Problem("B", "thermal", axes, order, None, T0, dT, lat, vert, None, None)
     p.elem_mat = p.to_elem_order(mat, np.uint32)
@@ -338,3 +345,66 @@ def setup_active(p):
                          offset=tot - ld * left - back, height=float(p.axes[2][top] - p.axes[2][bottom])))
         tot += (right - left) * (front - back)
     return acts, tot
+
+
+# ------------------------------------------------------------------------- slab partition
+
+def slab_range(nK, rank, nranks):
+    """Owned node planes [K0, K1) of `rank` along the major axis (balanced, contiguous)."""
+    base, rem = divmod(nK, nranks)
+    K0 = rank * base + min(rank, rem)
+    return K0, K0 + base + (1 if rank < rem else 0)
+
+
+def slab_local(nK, rank, nranks):
+    """(lo, hi, own_lo, own_hi): local node planes [lo, hi) of the global major axis = owned planes plus one halo
+    plane towards each neighbour, and the owned range in LOCAL plane indices."""
+    K0, K1 = slab_range(nK, rank, nranks)
+    lo, hi = K0 - (1 if rank > 0 else 0), K1 + (1 if rank < nranks - 1 else 0)
+    return lo, hi, K0 - lo, K1 - lo
+
+
+def slab_problem(p, rank, nranks):
+    """Cut the local problem of `rank` out of a global thermal Problem — what the solver plugin would do on each
+    process before calling the C ABI in slab mode.  Returns (local Problem, own_lo, own_hi, (lo, hi))."""
+    major = ORDERS[p.order][0]
+    n = p.n
+    lo, hi, own_lo, own_hi = slab_local(n[major], rank, nranks)
+    axes = [a.copy() for a in p.axes]
+    axes[major] = axes[major][lo:hi]
+    q = Problem(p.name + f"[{rank}/{nranks}]", p.kind, axes, p.order, None, p.T0, p.dT, p.tab_lat, p.tab_vert, None, None,
+                inittemp=p.inittemp, maxerr=p.maxerr)
+    esl = [slice(None)] * 3
+    esl[major] = slice(lo, hi - 1)
+    eg = p.elem_index_grid()
+    shape_e = tuple(k - 1 for k in n)
+
+    def cut_elem(a, dtype):
+        if a is None:
+            return None
+        g3 = np.asarray(a)[np.broadcast_to(eg, shape_e)][tuple(esl)]
+        return q.to_elem_order(g3, dtype)
+
+    q.elem_mat = cut_elem(p.elem_mat, np.uint32)
+    q.heat = cut_elem(p.heat, np.float64)
+    # Dirichlet nodes inside the local planes (halo planes included), in application order
+    ns = p.strides
+    order3 = sorted(range(3), key=lambda a: -ns[a])            # major, medium, minor
+    idx = np.asarray(p.bc_nodes, dtype=np.int64)
+    c = [None] * 3
+    rem = idx
+    for a in order3:
+        c[a], rem = np.divmod(rem, ns[a])
+    keep = (c[major] >= lo) & (c[major] < hi)
+    c[major] = c[major] - lo
+    qs = q.strides
+    q.bc_nodes = (c[0][keep] * qs[0] + c[1][keep] * qs[1] + c[2][keep] * qs[2]).astype(np.uintp)
+    q.bc_values = np.asarray(p.bc_values)[keep].copy()
+    return q, own_lo, own_hi, (lo, hi)
+
+
+def slab_field_owned(q, field, own_lo, own_hi):
+    """Owned part of a local node field as an array shaped (owned planes, medium, minor)."""
+    major, medium, minor = ORDERS[q.order]
+    n = q.n
+    return np.asarray(field).reshape(n[major], n[medium], n[minor])[own_lo:own_hi]

@@ -63,7 +63,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
        const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_d,
        const __grid_constant__ CUtensorMap tm_cl, const __grid_constant__ CUtensorMap tm_cv, const Grid g, const int lk,
        double* __restrict__ r_out, double* __restrict__ q_out, double* __restrict__ p_out, double* __restrict__ x,
-       Scalars* sc, double* partials) {
+       Scalars* sc, double* partials, const PeerOut po) {
     typedef FusedTile<TJ> T;
     constexpr int TI = T::TI, HX = T::HX, PW = T::PW, PH = T::PH, BOX = T::BOX, BOXP = T::BOXP, PWP = T::PWP;
     constexpr int PLANE = T::PLANE, CW = T::CW, CHALF = T::CHALF, LAYER = T::LAYER, NRED = T::NRED;
@@ -90,10 +90,13 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int tid = tx + TI * ty;
     const int i0 = blockIdx.x * TI, j0 = blockIdx.y * TJ;
-    const int k0 = blockIdx.z * lk;
-    const int k1 = min(k0 + lk, g.nK);
+    const int k0 = g.kown0 + blockIdx.z * lk;   // owned planes only (slab mode: halo planes belong to the neighbours)
+    const int k1 = min(k0 + lk, g.kown1);
     const int nsteps = k1 - k0 + 1;   // items t = 0 .. nsteps: node planes k0-1 .. k1, element layers k0-1 .. k1-1
     const int jl0 = ty * RJ;
+    // slab mode: the first / last owned plane is also stored into the neighbour's halo plane (NVLink peer stores)
+    const bool push_lo = FUSED && po.r_lo != nullptr, push_hi = FUSED && po.r_hi != nullptr;
+    const bool slab = push_lo || push_hi;
 
     // ---- per-thread constants -----------------------------------------------------------
     const int i = i0 + tx;
@@ -244,6 +247,12 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
                         r_out[n] = rn;
                         p_out[n] = pn;
                         x[n] = xv;
+                        if (slab) {
+                            const int P = k0 - 1 + t;
+                            const idx_t nip = n - sK * P;   // offset inside the plane
+                            if (push_lo && P == g.kown0) { po.r_lo[nip] = rn; po.p_lo[nip] = pn; }
+                            if (push_hi && P == g.kown1 - 1) { po.r_hi[nip] = rn; po.p_hi[nip] = pn; }
+                        }
                         red[1] = fma(rn, z, red[1]);
                         red[4] = fma(rn, rn, red[4]);
                         red[5] = fma(z, z, red[5]);
@@ -344,6 +353,12 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
                         const double da = zda[RJ + rr];
                         const double qv = (da == 0.) ? 0. : carry[rr] + lo;
                         q_out[nown[rr] - sK] = qv;
+                        if (slab) {
+                            const int Pa = k0 - 2 + t;
+                            const idx_t nip = nown[rr] - sK - sK * Pa;
+                            if (push_lo && Pa == g.kown0) po.q_lo[nip] = qv;
+                            if (push_hi && Pa == g.kown1 - 1) po.q_hi[nip] = qv;
+                        }
                         red[0] = fma(wa[yc][1], qv, red[0]);
                         if (FUSED) {
                             red[2] = fma(qv, zda[rr], red[2]);
@@ -382,7 +397,8 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         else step(N(), N(), Y(), Y(), nsteps, w1, w0, zd1, zd0);
     }
     if (!FUSED) return;
-    if (grid_reduce<NRED, false>(red, partials, &sc->ticket[0], sRed, sh_flag)) {
+    if (grid_reduce<NRED, false>(red, partials, &sc->ticket[0], sRed, sh_flag, slab)) {
+        if (sc->comm) rank_allreduce<NRED, false>(red, sc->comm, sRed);
         if (tid == 0) {
             const double pq = red[0], rho = red[1], qz = red[2], qdq = red[3], rr = red[4], zz = red[5], xx = red[6];
             const double rho_old = sc->rho;
@@ -393,7 +409,8 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
             sc->iter = it;
             bool stop = false;
             if (!sc->bench) {
-                if (!(rr == rr) || !(pq == pq)) { sc->done = 1; sc->status = -2; stop = true; }
+                if (sc->comm && sc->comm->timeout) { sc->done = 1; sc->status = -3; stop = true; }
+                else if (!(rr == rr) || !(pq == pq)) { sc->done = 1; sc->status = -2; stop = true; }
                 else if (rr <= sc->tol2 * sc->bb && rho <= sc->tol2 * sc->bz && zz <= sc->tol2 * xx) { sc->done = 1; sc->status = 1; stop = true; }
                 else if (it >= sc->maxit) { sc->done = 1; sc->status = 2; stop = true; }
                 else if (!(pq > 0.)) { sc->done = 1; sc->status = -1; stop = true; }
@@ -439,10 +456,11 @@ static inline FusedPlan make_fused_plan(const Grid& g, int sm_count, double* con
         const long long tiles = (long long)f.tilesI * f.tilesJ;
         const long long resident = (long long)sm_count * f.minb;
         double best = -1.;
-        for (int c = 1; c <= g.nK; ++c) {
-            const int l = (g.nK + c - 1) / c;
+        const int nown = g.kown1 - g.kown0;
+        for (int c = 1; c <= nown; ++c) {
+            const int l = (nown + c - 1) / c;
             if (l < 8 && c > 1) break;
-            const long long ctas = tiles * ((g.nK + l - 1) / l);
+            const long long ctas = tiles * ((nown + l - 1) / l);
             const long long waves = (ctas + resident - 1) / resident;
             const double eff = (double)ctas / (double)(waves * resident) * (double)l / (double)(l + 2);
             if (eff > best + 1e-9) { best = eff; lk = l; }
@@ -450,7 +468,7 @@ static inline FusedPlan make_fused_plan(const Grid& g, int sm_count, double* con
     }
     if (lk > 510) lk = 510;   // <= 8 KB of staged layer spacings per CTA
     f.lk = lk;
-    f.chunksK = (g.nK + lk - 1) / lk;
+    f.chunksK = (g.kown1 - g.kown0 + lk - 1) / lk;
     if ((g.sJ * 8) % 16 != 0 || (g.sK * 8) % 16 != 0) { snprintf(f.why, sizeof f.why, "row pitch is not a multiple of 16 bytes"); return f; }
     const int bw = 32 + 4, bh = f.tj + 2;
     bool ok = true;
@@ -468,7 +486,7 @@ static inline FusedPlan make_fused_plan(const Grid& g, int sm_count, double* con
 
 template <int TJ, int RJ, int NS, int MINB, int VDIM, bool FUSED>
 static inline cudaError_t launch_fused_inst(const FusedPlan& f, const Grid& g, int par, double* r_out, double* q_out, double* p_out,
-                                            double* x, Scalars* sc, double* partials, cudaStream_t st) {
+                                            double* x, Scalars* sc, double* partials, const PeerOut& po, cudaStream_t st) {
     const size_t smem = FusedTile<TJ>::smem_bytes(NS, FUSED, f.lk);
     static size_t attr_done = 0;
     if (attr_done < smem) {
@@ -478,17 +496,17 @@ static inline cudaError_t launch_fused_inst(const FusedPlan& f, const Grid& g, i
     }
     dim3 grid(f.tilesI, f.tilesJ, f.chunksK), block(32, TJ / RJ, 1);
     k_fpcg<TJ, RJ, NS, MINB, VDIM, FUSED><<<grid, block, smem, st>>>(f.m_r[par], f.m_q[par], f.m_p[par], f.m_d, f.m_cl, f.m_cv, g, f.lk,
-                                                                r_out, q_out, p_out, x, sc, partials);
+                                                                r_out, q_out, p_out, x, sc, partials, po);
     return cudaGetLastError();
 }
 
 template <int TJ, int RJ, int NS, int MINB, bool FUSED>
 static inline cudaError_t launch_fused_vdim(const FusedPlan& f, const Grid& g, int par, double* r_out, double* q_out, double* p_out,
-                                            double* x, Scalars* sc, double* partials, cudaStream_t st) {
+                                            double* x, Scalars* sc, double* partials, const PeerOut& po, cudaStream_t st) {
     switch (g.vdim) {
-        case 0: return launch_fused_inst<TJ, RJ, NS, MINB, 0, FUSED>(f, g, par, r_out, q_out, p_out, x, sc, partials, st);
-        case 1: return launch_fused_inst<TJ, RJ, NS, MINB, 1, FUSED>(f, g, par, r_out, q_out, p_out, x, sc, partials, st);
-        default: return launch_fused_inst<TJ, RJ, NS, MINB, 2, FUSED>(f, g, par, r_out, q_out, p_out, x, sc, partials, st);
+        case 0: return launch_fused_inst<TJ, RJ, NS, MINB, 0, FUSED>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st);
+        case 1: return launch_fused_inst<TJ, RJ, NS, MINB, 1, FUSED>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st);
+        default: return launch_fused_inst<TJ, RJ, NS, MINB, 2, FUSED>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st);
     }
 }
 
@@ -496,9 +514,10 @@ static inline cudaError_t launch_fused_vdim(const FusedPlan& f, const Grid& g, i
 // FUSED = false: plain q_out = M A p with p = p[par] (tests, pfem_apply).
 template <bool FUSED>
 static inline cudaError_t launch_fused_dispatch(const FusedPlan& f, const Grid& g, int par, double* r_out, double* q_out,
-                                                double* p_out, double* x, Scalars* sc, double* partials, cudaStream_t st) {
+                                                double* p_out, double* x, Scalars* sc, double* partials, const PeerOut& po,
+                                                cudaStream_t st) {
 #define PFEM_FUSED_CASE(TJ, RJ, NS, MINB) \
-    if (f.tj == TJ && f.rj == RJ && f.ns == NS && f.minb == MINB) return launch_fused_vdim<TJ, RJ, NS, MINB, FUSED>(f, g, par, r_out, q_out, p_out, x, sc, partials, st);
+    if (f.tj == TJ && f.rj == RJ && f.ns == NS && f.minb == MINB) return launch_fused_vdim<TJ, RJ, NS, MINB, FUSED>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st);
     PFEM_FUSED_CASE(8, 1, 3, 2)
     PFEM_FUSED_CASE(8, 1, 2, 2)
     PFEM_FUSED_CASE(8, 2, 3, 2)

@@ -64,10 +64,11 @@ k_apply_simple(const Grid g, const double* __restrict__ cl, const double* __rest
         else o = fixed ? 0. : f[n] - acc;
         out[n] = o;
         if (MODE == 0) dot[0] = P[1][1][1] * o;
-        if (MODE == 2) { dot[0] = o * o; dot[1] = o * o * dn; }
+        if (MODE == 2 && k >= g.kown0 && k < g.kown1) { dot[0] = o * o; dot[1] = o * o * dn; }
     }
     if (MODE == 1 || MODE == 3) return;
     if (grid_reduce<2, false>(dot, partials, &sc->ticket[0], sh, &sh_flag)) {
+        if (MODE == 2 && sc->comm) rank_allreduce<2, false>(dot, sc->comm, sh);
         if (threadIdx.x == 0 && threadIdx.y == 0) {
             if (MODE == 0) {
                 sc->pq = dot[0];
@@ -185,6 +186,7 @@ k_update(idx_t N, double* __restrict__ x, double* __restrict__ r, const double* 
         v[3] += xn * xn;
     }
     if (grid_reduce<4, false>(v, partials, &sc->ticket[1], sh, &sh_flag)) {
+        if (INIT && sc->comm) rank_allreduce<4, false>(v, sc->comm, sh);
         if (threadIdx.x == 0) {
             if (INIT) {
                 sc->rho = v[0]; sc->rho_prev = v[0]; sc->rr = v[1]; sc->zz = v[2]; sc->xx = v[3];
@@ -205,6 +207,24 @@ k_update(idx_t N, double* __restrict__ x, double* __restrict__ r, const double* 
             }
         }
     }
+}
+
+// ---- slab mode helpers ---------------------------------------------------------------------
+// copy my first / last owned plane into the halo plane of the lower / upper neighbour (peer-mapped memory)
+__global__ void k_halo_push(idx_t len, const double* __restrict__ src_lo, double* __restrict__ dst_lo,
+                            const double* __restrict__ src_hi, double* __restrict__ dst_hi) {
+    for (idx_t n = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; n < len; n += (idx_t)gridDim.x * blockDim.x) {
+        if (dst_lo) dst_lo[n] = src_lo[n];
+        if (dst_hi) dst_hi[n] = src_hi[n];
+    }
+}
+// cross-rank barrier (also publishes the halo stores of the preceding kernel); ORs a per-rank flag
+__global__ void k_rank_barrier(Scalars* sc, int flag_in) {
+    __shared__ double sh[8];
+    double v[1] = {(double)flag_in};
+    __threadfence_system();
+    rank_allreduce<1, true>(v, sc->comm, sh);
+    if (threadIdx.x == 0) sc->red[3] = v[0];
 }
 
 // q = fixed ? x : 0  (the Dirichlet-only vector used to lift the boundary values into the rhs)
@@ -423,6 +443,7 @@ k_thermal_error(idx_t N, const double* __restrict__ T, const double* __restrict_
         v[1] = fmax(v[1], t);
     }
     if (grid_reduce<2, true>(v, partials, &sc->ticket[2], sh, &sh_flag)) {
+        if (sc->comm) rank_allreduce<2, true>(v, sc->comm, sh);
         if (threadIdx.x == 0) { sc->red[0] = v[0]; sc->red[1] = v[1]; }
     }
 }

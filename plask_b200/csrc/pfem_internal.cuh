@@ -30,9 +30,30 @@ struct Grid {
     int pn[3];           // node count of physical axis a
     idx_t es[3];         // element stride of physical axis a in the ABI (compact) element order
     idx_t E;             // compact element count
+    int kown0, kown1;    // node planes [kown0, kown1) along K owned by this context (slab mode; else 0, nK)
     // spacings per index-space axis and their reciprocals; each array has one guard entry in
     // front and one behind (value 1), so h[-1] and h[n-1] are readable.
     const double *hI, *hJ, *hK, *rI, *rJ, *rK;
+};
+
+// ---- slab mode (one context per GPU, peers mapped with CUDA IPC over NVLink) ----------------
+#define PFEM_MAX_RANKS 8
+#define PFEM_COMM_NV 8
+// One per rank, in memory the rank exports: peers deposit their partial sums here.
+struct Inbox {
+    double data[2][PFEM_MAX_RANKS][PFEM_COMM_NV];
+    unsigned long long flag[2][PFEM_MAX_RANKS];
+};
+struct Comm {
+    int rank, nranks;
+    unsigned long long seq;            // cross-rank exchanges completed so far (identical on all ranks)
+    Inbox* inbox[PFEM_MAX_RANKS];      // inbox of every rank; inbox[rank] is local
+    int timeout;                       // a wait gave up: a peer died or the call sequences diverged
+};
+// Destination planes in the neighbours' arrays for the boundary planes of r', q', p' (null = no neighbour).
+struct PeerOut {
+    double *r_lo, *q_lo, *p_lo;        // upper halo plane of the lower neighbour
+    double *r_hi, *q_hi, *p_hi;        // lower halo plane of the upper neighbour
 };
 
 // Scalars of the PCG iteration and of the nonlinear loop; device resident, one instance per
@@ -61,6 +82,7 @@ struct Scalars {
     int launch;       // fused kernel: launches since the start of the solve (launch m has applied m-1 updates)
     int pad_;
     unsigned int ticket[8];
+    Comm* comm;       // null unless the context is one slab of a multi-GPU solve
 };
 
 // ------------------------------------------------------------------ reductions ----------
@@ -104,7 +126,7 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], double* sh) {
 // ALL threads of that last block; totals valid in its thread 0.  partials: nblocks*NV doubles.
 template <int NV, bool MAX>
 __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* __restrict__ partials, unsigned int* ticket,
-                                            double* sh, int* sh_flag) {
+                                            double* sh, int* sh_flag, bool peer_writes = false) {
     const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
     const int nthr = blockDim.x * blockDim.y * blockDim.z;
     const unsigned int nblk = gridDim.x * gridDim.y * gridDim.z;
@@ -113,7 +135,8 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* __restrict_
     if (tid == 0) {
 #pragma unroll
         for (int a = 0; a < NV; ++a) partials[(size_t)bid * NV + a] = v[a];
-        __threadfence();
+        if (peer_writes) __threadfence_system();   // this CTA's stores into a neighbour's halo planes go first
+        else __threadfence();
         unsigned int t = atomicAdd(ticket, 1u);
         *sh_flag = (t == nblk - 1);
     }
@@ -137,6 +160,53 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* __restrict_
         *ticket = 0u;
     }
     return true;
+}
+
+// Cross-rank all-reduce of NV <= PFEM_COMM_NV doubles through the peers' inboxes; called by ALL threads of
+// one block (the last block of a grid reduction), input/result in thread 0's v.  Every rank writes its values
+// into every inbox (its own too), raises a sequence flag after a system-scope fence, waits for all flags in its
+// own inbox and sums in rank order, so all ranks get bit-identical results.  Slots alternate with the sequence
+// number; a rank can only be one exchange ahead of the slowest, so two slots suffice.  It is also the
+// inter-iteration barrier that orders the halo-plane stores of k_fpcg (fence cumulativity).
+template <int NV, bool MAX>
+__device__ __forceinline__ void rank_allreduce(double (&v)[NV], Comm* cm, double* sh) {
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int a = 0; a < NV; ++a) sh[a] = v[a];
+    }
+    __syncthreads();
+    const unsigned long long s = *(volatile unsigned long long*)&cm->seq;
+    const int slot = (int)(s & 1ull), me = cm->rank;
+    if (tid < cm->nranks) {
+        Inbox* dst = cm->inbox[tid];
+#pragma unroll
+        for (int a = 0; a < NV; ++a) *(volatile double*)&dst->data[slot][me][a] = sh[a];
+        __threadfence_system();
+        *(volatile unsigned long long*)&dst->flag[slot][me] = s + 1ull;
+        const Inbox* mine = cm->inbox[me];
+        const long long t0 = clock64();
+        while (*(volatile const unsigned long long*)&mine->flag[slot][tid] != s + 1ull) {
+            if (clock64() - t0 > 20000000000ll) { cm->timeout = 1; break; }   // ~10 s
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const Inbox* mine = cm->inbox[me];
+#pragma unroll
+        for (int a = 0; a < NV; ++a) {
+            double acc = *(volatile const double*)&mine->data[slot][0][a];
+            for (int r = 1; r < cm->nranks; ++r) {
+                const double x = *(volatile const double*)&mine->data[slot][r][a];
+                acc = MAX ? fmax(acc, x) : acc + x;
+            }
+            v[a] = acc;
+        }
+        *(volatile unsigned long long*)&cm->seq = s + 1ull;
+    }
+    __syncthreads();
 }
 
 // ------------------------------------------------------- brick element coefficients -----

@@ -76,6 +76,27 @@ struct pfem_ctx {
     TiledPlan plan;
     TmaPlan tma;
     FusedPlan fused;
+    // slab mode (multi-GPU): this context owns node planes [kown0, kown1) of its local mesh, the rest are halo planes
+    int rank = 0, nranks = 1;
+    Comm* d_comm = nullptr;
+    Inbox* inbox = nullptr;                 // exported
+    Inbox* peer_inbox[PFEM_MAX_RANKS] = {};  // imported (null for self)
+    struct Neighbour { bool present = false; double* arr[8] = {}; long long G = 0, sK = 0, nK = 0; } nb_lo, nb_hi;
+};
+
+// arrays a neighbour may write / read: indices into pfem_ctx (order fixed by the blob layout)
+enum { SA_R = 0, SA_R2, SA_Q, SA_Q2, SA_P, SA_P2, SA_DINV, SA_X, SA_COUNT };
+static double* slab_array(pfem_ctx* ctx, int a) {
+    switch (a) {
+        case SA_R: return ctx->r; case SA_R2: return ctx->r2; case SA_Q: return ctx->q; case SA_Q2: return ctx->q2;
+        case SA_P: return ctx->p; case SA_P2: return ctx->p2; case SA_DINV: return ctx->dinv; default: return ctx->x;
+    }
+}
+struct SlabBlob {
+    cudaIpcMemHandle_t arr[SA_COUNT];
+    cudaIpcMemHandle_t inbox;
+    long long G, sK, nK;
+    int rank, nranks;
 };
 
 #define CU(call)                                                                                         \
@@ -103,8 +124,23 @@ struct pfem_ctx {
         if (rc_ < 0) return rc_;   \
     } while (0)
 
+static void slab_release(pfem_ctx* ctx) {
+    for (int r = 0; r < PFEM_MAX_RANKS; ++r)
+        if (ctx->peer_inbox[r]) { cudaIpcCloseMemHandle(ctx->peer_inbox[r]); ctx->peer_inbox[r] = nullptr; }
+    for (pfem_ctx::Neighbour* nb : {&ctx->nb_lo, &ctx->nb_hi}) {
+        if (nb->present)
+            for (int a = 0; a < SA_COUNT; ++a)
+                if (nb->arr[a]) cudaIpcCloseMemHandle(nb->arr[a] - nb->G);
+        *nb = pfem_ctx::Neighbour();
+    }
+    if (ctx->inbox) { cudaFree(ctx->inbox); ctx->inbox = nullptr; }
+    if (ctx->d_comm) { cudaFree(ctx->d_comm); ctx->d_comm = nullptr; }
+    ctx->rank = 0; ctx->nranks = 1;
+}
+
 static void free_all(pfem_ctx* ctx) {
     if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
+    slab_release(ctx);
     for (auto& a : ctx->allocs) cudaFree(a.base);
     ctx->allocs.clear();
     if (ctx->stage) { cudaFree(ctx->stage); ctx->stage = nullptr; ctx->stage_bytes = 0; }
@@ -262,6 +298,7 @@ extern "C" int pfem_set_mesh(pfem_ctx* ctx, const size_t n[3], const double* ax0
     g.ps[minor] = 1; g.ps[medium] = g.sJ; g.ps[major] = g.sK;   // strides in the pitched device layout
     g.es[minor] = 1; g.es[medium] = g.nI - 1; g.es[major] = (idx_t)(g.nI - 1) * (g.nJ - 1);
     g.E = (idx_t)(g.nI - 1) * (g.nJ - 1) * (g.nK - 1);
+    g.kown0 = 0; g.kown1 = g.nK;
 
     // spacing arrays with one guard entry (value 1) on both sides
     const int cnt[3] = {g.nI - 1, g.nJ - 1, g.nK - 1};
@@ -541,6 +578,127 @@ extern "C" int pfem_set_junctions(pfem_ctx* ctx, uint32_t njunc, const pfem_junc
     return PFEM_OK;
 }
 
+// ------------------------------------------------------------------------ slab mode -----
+// One context per GPU / process; the local mesh given to pfem_set_mesh contains the owned node planes along the
+// MAJOR axis plus one halo plane towards each existing neighbour.  Peers are mapped with CUDA IPC (NVLink P2P).
+// One process per context is required: the kernels of a collective call spin on their peers, and any implicitly
+// device-synchronising runtime call of a sibling context in the same process would dead-lock against them.
+
+extern "C" size_t pfem_slab_blob_size(void) { return sizeof(SlabBlob); }
+
+extern "C" int pfem_slab_configure(pfem_ctx* ctx, int rank, int nranks, size_t own_lo, size_t own_hi) {
+    NEED_MESH();
+    Grid& g = ctx->g;
+    if (nranks < 1 || nranks > PFEM_MAX_RANKS || rank < 0 || rank >= nranks) FAIL(PFEM_ERR_BAD_INPUT, "bad rank %d of %d (max %d)", rank, nranks, PFEM_MAX_RANKS);
+    if (own_lo >= own_hi || own_hi > (size_t)g.nK) FAIL(PFEM_ERR_BAD_INPUT, "owned plane range [%zu,%zu) outside the local mesh (%d planes)", own_lo, own_hi, g.nK);
+    if (own_lo != (rank > 0 ? 1u : 0u) || (size_t)g.nK - own_hi != (rank < nranks - 1 ? 1u : 0u))
+        FAIL(PFEM_ERR_BAD_INPUT, "the local mesh must hold exactly one halo plane towards each neighbour");
+    if (!ctx->fused.valid) FAIL(PFEM_ERR_STATE, "slab mode needs the fused PCG kernel: %s", ctx->fused.why);
+    CU(cudaStreamSynchronize(ctx->stream));
+    slab_release(ctx);
+    ctx->rank = rank; ctx->nranks = nranks;
+    g.kown0 = (int)own_lo; g.kown1 = (int)own_hi;
+    if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
+    {   // the fused plan chunks the OWNED planes
+        double* const rr[2] = {ctx->r, ctx->r2};
+        double* const qq[2] = {ctx->q, ctx->q2};
+        double* const pp[2] = {ctx->p, ctx->p2};
+        ctx->fused = make_fused_plan(g, ctx->sm_count, rr, qq, pp, ctx->dinv, ctx->cl, ctx->cv);
+    }
+    if (nranks == 1) return PFEM_OK;
+    CU(cudaMalloc(&ctx->inbox, sizeof(Inbox)));
+    CU(cudaMemset(ctx->inbox, 0, sizeof(Inbox)));
+    CU(cudaMalloc(&ctx->d_comm, sizeof(Comm)));
+    CU(cudaMemset(ctx->d_comm, 0, sizeof(Comm)));
+    return PFEM_OK;
+}
+
+extern "C" int pfem_slab_export(pfem_ctx* ctx, void* blob) {
+    NEED_MESH();
+    if (!blob) FAIL(PFEM_ERR_BAD_INPUT, "null blob");
+    if (ctx->nranks < 2 || !ctx->inbox) FAIL(PFEM_ERR_STATE, "pfem_slab_configure with nranks > 1 has not been called");
+    SlabBlob b;
+    memset(&b, 0, sizeof b);
+    for (int a = 0; a < SA_COUNT; ++a) CU(cudaIpcGetMemHandle(&b.arr[a], slab_array(ctx, a) - ctx->g.G));
+    CU(cudaIpcGetMemHandle(&b.inbox, ctx->inbox));
+    b.G = ctx->g.G; b.sK = ctx->g.sK; b.nK = ctx->g.nK; b.rank = ctx->rank; b.nranks = ctx->nranks;
+    memcpy(blob, &b, sizeof b);
+    return PFEM_OK;
+}
+
+extern "C" int pfem_slab_connect(pfem_ctx* ctx, const void* blobs) {
+    NEED_MESH();
+    if (!blobs) FAIL(PFEM_ERR_BAD_INPUT, "null blobs");
+    if (ctx->nranks < 2 || !ctx->inbox) FAIL(PFEM_ERR_STATE, "pfem_slab_configure with nranks > 1 has not been called");
+    const SlabBlob* B = reinterpret_cast<const SlabBlob*>(blobs);
+    Comm hc;
+    memset(&hc, 0, sizeof hc);
+    hc.rank = ctx->rank; hc.nranks = ctx->nranks;
+    for (int r = 0; r < ctx->nranks; ++r) {
+        if (B[r].rank != r || B[r].nranks != ctx->nranks) FAIL(PFEM_ERR_BAD_INPUT, "blob %d does not come from rank %d of %d", r, r, ctx->nranks);
+        if (B[r].sK != ctx->g.sK) FAIL(PFEM_ERR_BAD_INPUT, "rank %d has a different plane size", r);
+        if (r == ctx->rank) { hc.inbox[r] = ctx->inbox; continue; }
+        void* ptr = nullptr;
+        CU(cudaIpcOpenMemHandle(&ptr, B[r].inbox, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_inbox[r] = reinterpret_cast<Inbox*>(ptr);
+        hc.inbox[r] = ctx->peer_inbox[r];
+        pfem_ctx::Neighbour* nb = (r == ctx->rank - 1) ? &ctx->nb_lo : (r == ctx->rank + 1) ? &ctx->nb_hi : nullptr;
+        if (!nb) continue;
+        nb->G = B[r].G; nb->sK = B[r].sK; nb->nK = B[r].nK;
+        for (int a = 0; a < SA_COUNT; ++a) {
+            void* base = nullptr;
+            CU(cudaIpcOpenMemHandle(&base, B[r].arr[a], cudaIpcMemLazyEnablePeerAccess));
+            nb->arr[a] = reinterpret_cast<double*>(base) + nb->G;
+        }
+        nb->present = true;
+    }
+    CU(cudaMemcpy(ctx->d_comm, &hc, sizeof hc, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(&ctx->d_sc->comm, &ctx->d_comm, sizeof(Comm*), cudaMemcpyHostToDevice));
+    return PFEM_OK;
+}
+
+// cross-rank barrier; returns (through *any) the OR of `flag` over the ranks
+static int rank_barrier(pfem_ctx* ctx, int flag, int* any) {
+    if (ctx->nranks < 2) { if (any) *any = flag; return PFEM_OK; }
+    k_rank_barrier<<<1, 32, 0, ctx->stream>>>(ctx->d_sc, flag);
+    KCHECK(); LAUNCHED(1);
+    if (any) {
+        CU(cudaMemcpyAsync(ctx->h_sc, ctx->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        *any = ctx->h_sc->red[3] != 0.;
+    }
+    return PFEM_OK;
+}
+
+// refresh the halo planes of array `a` on both neighbours from my first / last owned plane
+static int halo_sync(pfem_ctx* ctx, int a) {
+    if (ctx->nranks < 2) return PFEM_OK;
+    const Grid& g = ctx->g;
+    const double* mine = slab_array(ctx, a);
+    double* dlo = ctx->nb_lo.present ? ctx->nb_lo.arr[a] + (ctx->nb_lo.nK - 1) * ctx->nb_lo.sK : nullptr;
+    double* dhi = ctx->nb_hi.present ? ctx->nb_hi.arr[a] : nullptr;
+    k_halo_push<<<vec_blocks(ctx) / 4, 256, 0, ctx->stream>>>(g.sK, mine + g.sK * g.kown0, dlo, mine + g.sK * (g.kown1 - 1), dhi);
+    KCHECK(); LAUNCHED(1);
+    return rank_barrier(ctx, 0, nullptr);
+}
+
+static PeerOut peer_out(pfem_ctx* ctx, int out_parity) {
+    PeerOut po;
+    memset(&po, 0, sizeof po);
+    if (ctx->nb_lo.present) {
+        const long long off = (ctx->nb_lo.nK - 1) * ctx->nb_lo.sK;
+        po.r_lo = ctx->nb_lo.arr[out_parity ? SA_R2 : SA_R] + off;
+        po.q_lo = ctx->nb_lo.arr[out_parity ? SA_Q2 : SA_Q] + off;
+        po.p_lo = ctx->nb_lo.arr[out_parity ? SA_P2 : SA_P] + off;
+    }
+    if (ctx->nb_hi.present) {
+        po.r_hi = ctx->nb_hi.arr[out_parity ? SA_R2 : SA_R];
+        po.q_hi = ctx->nb_hi.arr[out_parity ? SA_Q2 : SA_Q];
+        po.p_hi = ctx->nb_hi.arr[out_parity ? SA_P2 : SA_P];
+    }
+    return po;
+}
+
 // ------------------------------------------------------------------ conductivities ------
 
 extern "C" int pfem_update_conductivity_thermal(pfem_ctx* ctx) {
@@ -615,7 +773,7 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
         double* const qq[2] = {ctx->q, ctx->q2};
         double* const pp[2] = {ctx->p, ctx->p2};
         launch_fused_dispatch<true>(ctx->fused, g, parity, rr[1 - parity], qq[1 - parity], pp[1 - parity], ctx->x, ctx->d_sc,
-                                    ctx->partials, ctx->stream);
+                                    ctx->partials, peer_out(ctx, 1 - parity), ctx->stream);
         if (ev) { cudaEventRecord(ev[1], ctx->stream); cudaEventRecord(ev[2], ctx->stream); }
         return 1;
     }
@@ -673,6 +831,7 @@ static int pcg_prepare(pfem_ctx* ctx, const pfem_opts* o, int bench) {
     k_set_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, tol2, o->maxit, bench);
     LAUNCHED(1);
     TRY(launch_diag(ctx));
+    TRY(halo_sync(ctx, SA_DINV));            // slab mode: the diagonal of a halo plane needs the neighbour's elements
     TRY(scatter_bc(ctx, ctx->x, nullptr));   // x_D = v_D (B[r] = val, iterative_matrix.hpp:463-464)
     // ||b_free||^2 with b_free = M (f - A x_D): q <- x_D, p <- b_free (scratch)
     k_dirichlet_only<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->x, ctx->fixed, ctx->q);
@@ -680,10 +839,14 @@ static int pcg_prepare(pfem_ctx* ctx, const pfem_opts* o, int bench) {
     TRY(launch_apply_simple<2>(ctx, ctx->q, ctx->p));
     // r0 = M (f - A x)
     TRY(launch_apply_simple<1>(ctx, ctx->x, ctx->r));
+    TRY(halo_sync(ctx, SA_R));
     CU(cudaMemsetAsync(ctx->p, 0, (size_t)g.NP * sizeof(double), ctx->stream));
     CU(cudaMemsetAsync(ctx->q, 0, (size_t)g.NP * sizeof(double), ctx->stream));   // fused kernel: r' = r - 0*q on the first launch
-    k_update<true><<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->x, ctx->r, ctx->p, ctx->q, ctx->dinv, ctx->d_sc,
-                                                              ctx->partials);
+    {   // initial scalars over the OWNED planes (all planes unless this is a slab)
+        const idx_t off = g.sK * g.kown0, cnt = g.sK * (g.kown1 - g.kown0);
+        k_update<true><<<vec_blocks(ctx), 256, 0, ctx->stream>>>(cnt, ctx->x + off, ctx->r + off, ctx->p + off, ctx->q + off,
+                                                                  ctx->dinv + off, ctx->d_sc, ctx->partials);
+    }
     LAUNCHED(1);
     KCHECK();
     return PFEM_OK;
@@ -695,7 +858,9 @@ static int pcg_solve(pfem_ctx* ctx, const pfem_opts* o, int* iters, double* relr
     batch += batch & 1;  // even: p ping-pong parity is preserved across graph launches
     TRY(build_graph(ctx, batch, o->variant, o->precond));
     TRY(read_scalars(ctx));
-    if (ctx->h_sc->neg_diag) FAIL(PFEM_ERR_NOT_SPD, "nonpositive diagonal element in stiffness matrix");
+    int neg_diag = ctx->h_sc->neg_diag;
+    if (ctx->nranks > 1) { TRY(rank_barrier(ctx, neg_diag, &neg_diag)); TRY(read_scalars(ctx)); }   // all ranks fail together
+    if (neg_diag) FAIL(PFEM_ERR_NOT_SPD, "nonpositive diagonal element in stiffness matrix");
     while (!ctx->h_sc->done) {
         CU(cudaGraphLaunch(ctx->graph, ctx->stream));
         LAUNCHED((long long)batch * kernels_per_iteration(o->variant));
@@ -708,6 +873,7 @@ static int pcg_solve(pfem_ctx* ctx, const pfem_opts* o, int* iters, double* relr
     *converged = (s.status == 1);
     if (s.status == -1) FAIL(PFEM_ERR_NOT_SPD, "p.Ap = %g <= 0 at iteration %d: stiffness matrix is not positive definite", s.pq, s.iter);
     if (s.status == -2) FAIL(PFEM_ERR_NAN, "non-finite value in the PCG iteration %d", s.iter);
+    if (s.status == -3) FAIL(PFEM_ERR_CUDA, "slab mode: timed out waiting for a peer rank in PCG iteration %d", s.iter);
     return PFEM_OK;
 }
 
@@ -718,6 +884,7 @@ static int check_opts(pfem_ctx* ctx, const pfem_opts* o) {
     if (o->precond != 0) FAIL(PFEM_ERR_BAD_INPUT, "preconditioner %d is not implemented", o->precond);
     if (o->variant < 0 || o->variant > 3) FAIL(PFEM_ERR_BAD_INPUT, "unknown kernel variant %d", o->variant);
     if (o->variant == 3 && !ctx->fused.valid) FAIL(PFEM_ERR_STATE, "fused PCG kernel unavailable: %s", ctx->fused.why);
+    if (ctx->nranks > 1 && o->variant != 3) FAIL(PFEM_ERR_BAD_INPUT, "slab mode runs the fused PCG kernel only (variant 3)");
     if (o->variant == 0 && !ctx->tma.valid) FAIL(PFEM_ERR_STATE, "TMA operator kernel unavailable: %s", ctx->tma.why);
     if (o->variant == 2 && !ctx->plan.valid) FAIL(PFEM_ERR_STATE, "no tiled kernel plan for this mesh");
     return PFEM_OK;
@@ -739,6 +906,7 @@ extern "C" int pfem_solve_linear(pfem_ctx* ctx, const pfem_opts* o, pfem_stats* 
     int iters = 0, conv = 0;
     double relres = 0;
     TRY(pcg_solve(ctx, o, &iters, &relres, &conv));
+    TRY(halo_sync(ctx, SA_X));
     if (st) {
         memset(st, 0, sizeof(*st));
         st->lin_iters = st->last_iters = iters;
@@ -763,12 +931,15 @@ extern "C" int pfem_solve_thermal(pfem_ctx* ctx, const pfem_opts* o, pfem_stats*
     long long total_iters = 0;
     double err = 0., toterr = 0., maxT = 0., relres = 0.;
     const int cap = o->loops > 0 ? o->loops : 100000;
+    const idx_t own_off = g.sK * g.kown0, own_cnt = g.sK * (g.kown1 - g.kown0);
     do {
+        TRY(halo_sync(ctx, SA_X));                             // slab mode: the solve updates owned planes only
         CU(cudaMemcpyAsync(ctx->xprev, ctx->x, (size_t)g.NP * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         TRY(pfem_update_conductivity_thermal(ctx));           // therm3d.cpp:204-220
         TRY(pcg_solve(ctx, o, &iters, &relres, &conv));        // setMatrix + A.solve, :314-315
         total_iters += iters;
-        k_thermal_error<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->x, ctx->xprev, ctx->d_sc, ctx->partials);
+        k_thermal_error<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(own_cnt, ctx->x + own_off, ctx->xprev + own_off, ctx->d_sc,
+                                                                   ctx->partials);
         KCHECK(); LAUNCHED(1);
         TRY(read_scalars(ctx));
         err = ctx->h_sc->red[0];
@@ -777,6 +948,7 @@ extern "C" int pfem_solve_thermal(pfem_ctx* ctx, const pfem_opts* o, pfem_stats*
         ++ctx->loopno;
         ++loop;
     } while ((!conv || err > o->outer_tol) && loop < cap);      // :334
+    TRY(halo_sync(ctx, SA_X));
     if (st) {
         memset(st, 0, sizeof(*st));
         st->outer_loops = loop; st->loopno = ctx->loopno; st->lin_iters = total_iters; st->last_iters = iters;
@@ -792,6 +964,7 @@ extern "C" int pfem_solve_shockley(pfem_ctx* ctx, const pfem_opts* o, pfem_stats
     NEED_MESH();
     TRY(check_opts(ctx, o));
     if (!ctx->have_materials) FAIL(PFEM_ERR_STATE, "pfem_set_materials has not been called");
+    if (ctx->nranks > 1) FAIL(PFEM_ERR_BAD_INPUT, "slab mode (multi-GPU) is implemented for the thermal and the linear solve only");
     const Grid& g = ctx->g;
     TRY(ensure_elem_arrays(ctx, true));
     long long l0 = ctx->launches;
@@ -918,7 +1091,9 @@ extern "C" int pfem_apply(pfem_ctx* ctx, const double* p, double* q, int variant
         LAUNCHED(1);
     } else if (variant == 3) {
         if (!ctx->fused.valid) FAIL(PFEM_ERR_STATE, "fused PCG kernel unavailable: %s", ctx->fused.why);
-        CU(launch_fused_dispatch<false>(ctx->fused, g, 0, nullptr, ctx->q, nullptr, nullptr, nullptr, nullptr, ctx->stream));
+        PeerOut none;
+        memset(&none, 0, sizeof none);
+        CU(launch_fused_dispatch<false>(ctx->fused, g, 0, nullptr, ctx->q, nullptr, nullptr, nullptr, nullptr, none, ctx->stream));
         LAUNCHED(1);
     } else if (variant == 0) {
         if (!ctx->tma.valid) FAIL(PFEM_ERR_STATE, "TMA operator kernel unavailable: %s", ctx->tma.why);

@@ -105,6 +105,22 @@ class DeviceFem:
                                              er.ctypes.data_as(L._u8p) if er is not None else None, float(pcond),
                                              float(ncond), self.ncol, _dp(jc), _dp(bc), _dp(jsn), int(bool(stable))))
 
+    # ---- slab mode (one DeviceFem per GPU / process; see include/plaskfem_cuda.h)
+    def slab_configure(self, rank, nranks, own_lo, own_hi):
+        self._ck(self.lib.pfem_slab_configure(self.ctx, int(rank), int(nranks), int(own_lo), int(own_hi)))
+        self.slab = (int(rank), int(nranks), int(own_lo), int(own_hi))
+
+    def slab_export(self):
+        buf = C.create_string_buffer(self.lib.pfem_slab_blob_size())
+        self._ck(self.lib.pfem_slab_export(self.ctx, C.cast(buf, L._vp)))
+        return bytes(buf.raw)
+
+    def slab_connect(self, blobs):
+        n = self.lib.pfem_slab_blob_size()
+        assert all(len(b) == n for b in blobs)
+        buf = C.create_string_buffer(b"".join(blobs), n * len(blobs))
+        self._ck(self.lib.pfem_slab_connect(self.ctx, C.cast(buf, L._vp)))
+
     # ---- solve
     def opts(self, **kw):
         o = L.Opts()

@@ -47,6 +47,9 @@ class _FemSolver:
         self.initialized = False
         self.log = []
         self.stats = None
+        # slab mode (multi-GPU): dict(rank, nranks, own_lo, own_hi, allgather=callable(bytes) -> list of bytes);
+        # `problem` is then the LOCAL problem (configs.slab_problem) and compute() is collective
+        self.slab = None
 
     # geometry + mesh + materials, flattened
     @property
@@ -105,6 +108,11 @@ class Static3D(_FemSolver):
             raise L.BadInput(f"{self.id}: no geometry/mesh (problem) specified")
         f = self._fem = DeviceFem(self.device)
         f.set_mesh(p.axes, p.strides)
+        if self.slab is not None:
+            sl = self.slab
+            f.slab_configure(sl["rank"], sl["nranks"], sl["own_lo"], sl["own_hi"])
+            if sl["nranks"] > 1:
+                f.slab_connect(sl["allgather"](f.slab_export()))
         f.set_materials(p.elem_mat, p.T0, p.dT, p.tab_lat, p.tab_vert)
         f.set_field(float(self.inittemp))               # temperatures.reset(size, inittemp), :79
         f.set_dirichlet(p.bc_nodes, p.bc_values)

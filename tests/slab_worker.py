@@ -1,0 +1,116 @@
+"""Worker of the slab-mode (multi-GPU) tests, one process per rank:
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/slab_worker.py [--host-only]
+
+--host-only (CPU, gloo): checks the host-side slab logic — partition, halo planes, local Dirichlet lists, blob
+all-gather plumbing — without touching a GPU.
+Default (needs one GPU per rank): solves a small config-B problem in slab mode through the C ABI and compares it on
+rank 0 with the single-GPU solve of the global problem and with the oracle's Cholesky.
+"""
+import os
+import sys
+
+import numpy as np
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from plask_b200 import configs as cf  # noqa: E402
+
+
+def allgather_bytes(b):
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, b)
+    return out
+
+
+def main():
+    host_only = "--host-only" in sys.argv
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n = (8 * world + 3, 14, 12)                       # major axis = axis 0, uneven split
+    p = cf.config_B(n)
+    assert cf.ORDERS[p.order][0] == 0
+    q, own_lo, own_hi, (lo, hi) = cf.slab_problem(p, rank, world)
+
+    # ---- host logic: partition covers the axis, halos overlap the neighbours' owned planes
+    ranges = allgather_bytes((lo, hi, own_lo, own_hi))
+    owned = [(l + a, l + b) for (l, h, a, b) in ranges]
+    assert owned[0][0] == 0 and owned[-1][1] == n[0]
+    assert all(owned[r][1] == owned[r + 1][0] for r in range(world - 1))
+    assert own_lo == (1 if rank > 0 else 0) and (hi - lo) - own_hi == (1 if rank < world - 1 else 0)
+    # local arrays are the slices of the global ones
+    eg = np.broadcast_to(p.elem_index_grid(), tuple(k - 1 for k in n))
+    leg = np.broadcast_to(q.elem_index_grid(), tuple(k - 1 for k in q.n))
+    assert np.array_equal(q.elem_mat[leg], p.elem_mat[eg][lo:hi - 1])
+    assert np.array_equal(q.heat[leg], p.heat[eg][lo:hi - 1])
+    ng = np.broadcast_to(p.node_index_grid(), n)
+    lng = np.broadcast_to(q.node_index_grid(), q.n)
+    gfix = np.zeros(p.N, bool); gfix[p.bc_nodes] = True
+    lfix = np.zeros(q.N, bool); lfix[q.bc_nodes] = True
+    assert np.array_equal(lfix[lng], gfix[ng][lo:hi])
+    # direct construction of the slab (what bench.py does at scale) gives the same local problem
+    d = cf.config_B(n, rows0=(lo, hi))
+    assert np.array_equal(d.elem_mat, q.elem_mat) and np.array_equal(d.heat, q.heat)
+    assert np.array_equal(np.sort(d.bc_nodes), np.sort(q.bc_nodes))
+    blobs = allgather_bytes(bytes([rank]) * 64)
+    assert [b[0] for b in blobs] == list(range(world))
+    if host_only:
+        dist.barrier()
+        if rank == 0:
+            print("slab host logic ok, world", world)
+        dist.destroy_process_group()
+        return
+
+    # ---- device: collective solve in slab mode
+    import torch
+    from plask_b200.solvers import Static3D
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    assert torch.cuda.device_count() > local, "one GPU per rank is needed"
+    s = Static3D(f"slab{rank}")
+    s.device = local
+    s.problem = q
+    s.slab = dict(rank=rank, nranks=world, own_lo=own_lo, own_hi=own_hi, allgather=allgather_bytes)
+    s.iterative.maxerr = 1e-11
+    s.iterative.maxit = 50000
+    err = s.compute(0)
+    T_loc = s.outTemperature()
+    parts = allgather_bytes((cf.slab_field_owned(q, T_loc, own_lo, own_hi), s.stats, err))
+    # halo planes returned by get_field agree with the neighbours' owned planes
+    planes = T_loc.reshape(q.n[0], q.n[1], q.n[2])
+    if rank > 0:
+        assert np.array_equal(planes[0], parts[rank - 1][0][-1])
+    if rank < world - 1:
+        assert np.array_equal(planes[-1], parts[rank + 1][0][0])
+    stats = [x[1] for x in parts]
+    assert all(st["lin_iters"] == stats[0]["lin_iters"] and st["outer_loops"] == stats[0]["outer_loops"] for st in stats)
+    assert all(x[2] == parts[0][2] for x in parts)
+    s.invalidate()
+    if rank == 0:
+        from helpers import oracle_thermal
+        T = np.concatenate([x[0] for x in parts], axis=0).ravel()      # order 012: plain C order of (n0, n1, n2)
+        one = Static3D("single")
+        one.device = 0
+        one.problem = p
+        one.iterative.maxerr = 1e-11
+        one.iterative.maxit = 50000
+        one.compute(0)
+        T1 = one.outTemperature()
+        o = oracle_thermal(p, algorithm="cholesky")
+        o.compute(0)
+        d1 = float(np.abs(T - T1).max())
+        d2 = float(np.abs(T - o.temperatures).max())
+        print(f"slab x{world}: loops {stats[0]['outer_loops']}, PCG iterations {stats[0]['lin_iters']} (single GPU "
+              f"{one.stats['lin_iters']}), max|T_slab - T_single| = {d1:.3e} K, max|T_slab - T_cholesky| = {d2:.3e} K")
+        assert stats[0]["outer_loops"] == one.stats["outer_loops"] == len(o.history)
+        assert abs(stats[0]["lin_iters"] - one.stats["lin_iters"]) <= 0.02 * one.stats["lin_iters"] + 2
+        assert d1 <= 1e-6 and d2 <= 1e-3
+        one.invalidate()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,32 @@
+"""Slab mode: host logic with gloo world_size 2 on the CPU, the collective device solve on >= 2 GPUs."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WORKER = os.path.join(ROOT, "tests", "slab_worker.py")
+
+
+def _torchrun(nproc, port, *args, timeout=600):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), WORKER, *args]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_host_logic_gloo(world):
+    r = _torchrun(world, 29541 + world, "--host-only")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "slab host logic ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_slab_solve_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    r = _torchrun(2, 29551, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "max|T_slab - T_single|" in r.stdout

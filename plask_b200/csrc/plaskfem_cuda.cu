@@ -674,6 +674,9 @@ static int rank_barrier(pfem_ctx* ctx, int flag, int* any) {
 static int halo_sync(pfem_ctx* ctx, int a) {
     if (ctx->nranks < 2) return PFEM_OK;
     const Grid& g = ctx->g;
+    // Receiver-ready barrier first: the local kernels that produced array `a` also wrote (meaningless) values
+    // into their own halo planes; a neighbour that runs ahead must not push before those kernels have finished.
+    TRY(rank_barrier(ctx, 0, nullptr));
     const double* mine = slab_array(ctx, a);
     double* dlo = ctx->nb_lo.present ? ctx->nb_lo.arr[a] + (ctx->nb_lo.nK - 1) * ctx->nb_lo.sK : nullptr;
     double* dhi = ctx->nb_hi.present ? ctx->nb_hi.arr[a] : nullptr;

@@ -143,6 +143,15 @@ static void free_all(pfem_ctx* ctx) {
     slab_release(ctx);
     for (auto& a : ctx->allocs) cudaFree(a.base);
     ctx->allocs.clear();
+    // every pointer below came from dev_alloc: a later pfem_set_mesh must not see stale addresses
+    ctx->x = ctx->xprev = ctx->r = ctx->r2 = ctx->p = ctx->p2 = ctx->q = ctx->q2 = ctx->dinv = ctx->f = nullptr;
+    ctx->fixed = nullptr; ctx->bc_node = nullptr; ctx->bc_val = nullptr; ctx->nbc = 0;
+    ctx->cl = ctx->cv = ctx->Te = ctx->cur0 = ctx->cur1 = ctx->cur2 = ctx->aux0 = ctx->aux1 = ctx->aux2 = nullptr;
+    ctx->mat = ctx->junc = nullptr; ctx->role = ctx->noheat = nullptr;
+    ctx->hbuf = ctx->tab_lat = ctx->tab_vert = nullptr;
+    ctx->act = nullptr; ctx->nact = 0; ctx->ncol = 0;
+    ctx->junc_cond = ctx->beta_col = ctx->js_col = nullptr;
+    ctx->partials = nullptr; ctx->partial_idx = nullptr; ctx->n_partials = 0;
     if (ctx->stage) { cudaFree(ctx->stage); ctx->stage = nullptr; ctx->stage_bytes = 0; }
     ctx->have_mesh = ctx->have_materials = ctx->have_junctions = ctx->conds_valid = false;
 }
@@ -157,6 +166,20 @@ static int dev_alloc(pfem_ctx* ctx, T** out, size_t count, size_t guard) {
     ctx->allocs.push_back({base, bytes});
     *out = reinterpret_cast<T*>(base) + guard;
     return PFEM_OK;
+}
+
+// release one array obtained from dev_alloc with guard 0 (re-set Dirichlet lists, tables ...)
+template <typename T>
+static void dev_release(pfem_ctx* ctx, T** p) {
+    if (!*p) return;
+    for (size_t a = 0; a < ctx->allocs.size(); ++a)
+        if (ctx->allocs[a].base == (void*)*p) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(ctx->allocs[a].base);
+            ctx->allocs.erase(ctx->allocs.begin() + a);
+            break;
+        }
+    *p = nullptr;
 }
 
 static int ensure_stage(pfem_ctx* ctx, size_t bytes) {
@@ -400,6 +423,8 @@ extern "C" int pfem_set_materials(pfem_ctx* ctx, const uint32_t* elem_mat, uint3
         if (elem_mat[e] >= nmat) FAIL(PFEM_ERR_BAD_INPUT, "element %lld has material id %u >= nmat %u", (long long)e, elem_mat[e], nmat);
     TRY(upload_elem<uint32_t, 1>(ctx, elem_mat, ctx->mat, nullptr, nullptr));
     size_t cnt = (size_t)nmat * nT;
+    dev_release(ctx, &ctx->tab_lat);
+    dev_release(ctx, &ctx->tab_vert);
     TRY(dev_alloc(ctx, &ctx->tab_lat, cnt, 0));
     TRY(dev_alloc(ctx, &ctx->tab_vert, cnt, 0));
     CU(cudaMemcpyAsync(ctx->tab_lat, c_lat, cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -453,6 +478,8 @@ extern "C" int pfem_set_dirichlet(pfem_ctx* ctx, size_t nd, const size_t* node, 
     // so the conductivities of the first loop are evaluated from the un-constrained field.
     CU(cudaMemsetAsync(ctx->fixed, 0, (size_t)g.NP, ctx->stream));
     ctx->nbc = nn.size();
+    dev_release(ctx, &ctx->bc_node);
+    dev_release(ctx, &ctx->bc_val);
     if (!nn.empty()) {
         TRY(dev_alloc(ctx, &ctx->bc_node, nn.size(), 0));
         TRY(dev_alloc(ctx, &ctx->bc_val, nn.size(), 0));
@@ -561,6 +588,10 @@ extern "C" int pfem_set_junctions(pfem_ctx* ctx, uint32_t njunc, const pfem_junc
     if (need > ncol) FAIL(PFEM_ERR_BAD_INPUT, "junction table too short: need %zu entries, got %zu", need, ncol);
     ctx->nact = (int)njunc;
     ctx->ncol = ncol;
+    dev_release(ctx, &ctx->act);
+    dev_release(ctx, &ctx->junc_cond);
+    dev_release(ctx, &ctx->beta_col);
+    dev_release(ctx, &ctx->js_col);
     if (njunc) {
         TRY(dev_alloc(ctx, &ctx->act, njunc, 0));
         CU(cudaMemcpyAsync(ctx->act, hj.data(), njunc * sizeof(JunctionDev), cudaMemcpyHostToDevice, ctx->stream));

@@ -1,0 +1,318 @@
+// plaskfem_cuda.hpp — header-only C++17 host adapter over the C ABI (plaskfem_cuda.h).
+//
+// This is the code the PLaSK solver plugin compiles in: it turns what
+// ThermalFem3DSolver / ElectricalFem3DSolver hold after onInitialize() into the flat arrays of
+// the C ABI and maps status codes back to the solver's exceptions, `iter_params` outputs and
+// the `noconv` policy.  It deliberately depends on NOTHING from PLaSK (so it builds and is
+// tested in this repository); the three places where the plugin supplies PLaSK objects are
+// template parameters / callables:
+//     material_key(e)      -> an integer identifying geometry->getMaterial(elem.getMidpoint())
+//     thermk(id, T, h)     -> material->thermk(T, h)      (tabulated, no callbacks into Python
+//     cond(id, T)          -> material->cond(T)            from the device)
+//     junction_number(e)   -> isActive(elem) (electr3d.hpp:148-171)
+//
+// Reference behaviour restated here (paths relative to the PLaSK tree):
+//     layer_thickness        therm3d.cpp:81-114          (row a2 of SURVEY.md §8)
+//     setup_active_regions   electr3d.cpp:89-183         (row a12 set-up)
+//     flatten_dirichlet      plask/common/fem/matrix.hpp:111-118
+//     IterParams / noconv    plask/common/fem/iterative_matrix.hpp:25-94, 296-336
+//     Solver loops           therm3d.cpp:281-340, electr3d.cpp:356-442 (on the device)
+#ifndef PLASKFEM_CUDA_HPP
+#define PLASKFEM_CUDA_HPP
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <functional>
+#include <limits>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "plaskfem_cuda.h"
+
+namespace plaskfem {
+
+// ---- errors: the plugin re-throws these as plask::ComputationError / plask::BadInput -----------------
+
+struct ComputationError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct BadInput : std::invalid_argument { using std::invalid_argument::invalid_argument; };
+struct NoDevice : std::runtime_error { using std::runtime_error::runtime_error; };
+
+// ---- mesh description (row a1) -----------------------------------------------------------------------
+
+// Iteration orders of RectilinearMesh3D (rectilinear3d.hpp:349): ORDER_<major><medium><minor>.
+enum IterationOrder { ORDER_012, ORDER_021, ORDER_102, ORDER_120, ORDER_201, ORDER_210 };
+
+struct Mesh {
+    std::vector<double> axis[3];   // coordinates in um, axis 2 vertical
+    IterationOrder order = ORDER_012;
+
+    size_t n(int a) const { return axis[a].size(); }
+    size_t size() const { return n(0) * n(1) * n(2); }
+    size_t elements() const { return (n(0) - 1) * (n(1) - 1) * (n(2) - 1); }
+    void order_axes(int& major, int& medium, int& minor) const {
+        static const int t[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+        major = t[order][0]; medium = t[order][1]; minor = t[order][2];
+    }
+    // node strides, rectilinear3d.cpp:20-32
+    void strides(size_t s[3]) const {
+        int mj, md, mn; order_axes(mj, md, mn);
+        s[mn] = 1; s[md] = n(mn); s[mj] = n(mn) * n(md);
+    }
+    // element strides: the element mesh keeps the order (rectangular3d.cpp:20-22)
+    void elem_strides(size_t s[3]) const {
+        int mj, md, mn; order_axes(mj, md, mn);
+        s[mn] = 1; s[md] = n(mn) - 1; s[mj] = (n(mn) - 1) * (n(md) - 1);
+    }
+    size_t node(size_t i0, size_t i1, size_t i2) const { size_t s[3]; strides(s); return i0 * s[0] + i1 * s[1] + i2 * s[2]; }
+    size_t elem(size_t i0, size_t i1, size_t i2) const { size_t s[3]; elem_strides(s); return i0 * s[0] + i1 * s[1] + i2 * s[2]; }
+    // setOptimalIterationOrder, rectilinear3d.cpp:74-85
+    void set_optimal_order() {
+        static const int t[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+        for (int o = 0; o < 6; ++o)
+            if (n(t[o][2]) <= n(t[o][1]) && n(t[o][1]) <= n(t[o][0])) { order = (IterationOrder)o; return; }
+        order = ORDER_210;
+    }
+};
+
+// ---- row a2: thickness of the maximal vertical run of equal material ---------------------------------
+
+// thickness[e] = height of the maximal run of vertically adjacent elements with the same material_key
+// that contains e (therm3d.cpp:81-114).  material_key: callable (i0, i1, i2) -> comparable key.
+template <typename KeyFn>
+std::vector<double> layer_thickness(const Mesh& m, KeyFn&& material_key) {
+    const size_t e0 = m.n(0) - 1, e1 = m.n(1) - 1, e2 = m.n(2) - 1;
+    size_t es[3]; m.elem_strides(es);
+    std::vector<double> th(m.elements(), std::numeric_limits<double>::quiet_NaN());
+    for (size_t i0 = 0; i0 < e0; ++i0)
+        for (size_t i1 = 0; i1 < e1; ++i1) {
+            size_t start = 0;
+            auto key = material_key(i0, i1, (size_t)0);
+            for (size_t r = 1; r <= e2; ++r) {
+                bool brk = (r == e2);
+                decltype(key) k2 = key;
+                if (!brk) { k2 = material_key(i0, i1, r); brk = !(k2 == key); }
+                if (brk) {
+                    const double h = m.axis[2][r] - m.axis[2][start];
+                    for (size_t q = start; q < r; ++q) th[i0 * es[0] + i1 * es[1] + q * es[2]] = h;
+                    start = r; key = k2;
+                }
+            }
+        }
+    return th;
+}
+
+// Table ids: one id per distinct (material key, thickness) pair, so that thermk(T, thickness) can be
+// tabulated per id (pfem_set_materials).  Returns ids[E]; `reps` receives one representative element per id.
+template <typename Key>
+std::vector<uint32_t> material_ids(const std::vector<Key>& key_per_elem, const std::vector<double>& thickness,
+                                   std::vector<size_t>* reps = nullptr) {
+    std::map<std::pair<Key, double>, uint32_t> seen;
+    std::vector<uint32_t> ids(key_per_elem.size());
+    for (size_t e = 0; e < key_per_elem.size(); ++e) {
+        auto it = seen.find({key_per_elem[e], thickness.empty() ? 0. : thickness[e]});
+        if (it == seen.end()) {
+            it = seen.emplace(std::make_pair(key_per_elem[e], thickness.empty() ? 0. : thickness[e]), (uint32_t)seen.size()).first;
+            if (reps) reps->push_back(e);
+        }
+        ids[e] = it->second;
+    }
+    return ids;
+}
+
+// Conductivity tables on the grid T0 + i*dT: fn(id, T) -> (lateral, vertical) = Tensor2 (c00, c11).
+struct Tables {
+    double T0 = 250., dT = 0.25;
+    uint32_t nmat = 0, nT = 0;
+    std::vector<double> lat, vert;   // [nmat][nT]
+};
+template <typename Fn>
+Tables sample_tables(uint32_t nmat, Fn&& fn, double T0 = 250., double dT = 0.25, uint32_t nT = 1601) {
+    Tables t; t.T0 = T0; t.dT = dT; t.nmat = nmat; t.nT = nT;
+    t.lat.resize((size_t)nmat * nT); t.vert.resize((size_t)nmat * nT);
+    for (uint32_t id = 0; id < nmat; ++id)
+        for (uint32_t i = 0; i < nT; ++i) {
+            std::pair<double, double> c = fn(id, T0 + i * dT);
+            t.lat[(size_t)id * nT + i] = c.first; t.vert[(size_t)id * nT + i] = c.second;
+        }
+    return t;
+}
+
+// ---- row a8: BoundaryConditionsWithMesh flattened in application order (matrix.hpp:111-118) -----------
+
+struct Dirichlet {
+    std::vector<size_t> node;
+    std::vector<double> value;
+    template <typename NodeRange>
+    void add(const NodeRange& place, double v) { for (size_t r : place) { node.push_back(r); value.push_back(v); } }
+};
+
+// ---- junctions (electr3d.hpp:28-78, electr3d.cpp:89-183) ---------------------------------------------
+
+// junction_number(i0, i1, i2) -> 0 (not active) or k+1.  Throws like the reference when a junction does not
+// have flat top/bottom.  Returns the Active list; *condsize = length of junction_conductivity.
+template <typename JuncFn>
+std::vector<pfem_junction> setup_active_regions(const Mesh& m, JuncFn&& junction_number, size_t* condsize,
+                                                const std::string& solver_id = "") {
+    struct Region { size_t bottom, top, left, right, back, front; };
+    const size_t SZMAX = std::numeric_limits<size_t>::max();
+    std::map<size_t, Region> regions;
+    size_t nreg = 0;
+    const size_t p0 = m.n(0) - 1, p1 = m.n(1) - 1, p2 = m.n(2) - 1;
+    auto summarize = [&](size_t num, size_t start, size_t ver, size_t lon, size_t tra) {
+        auto found = regions.find(num);
+        if (found == regions.end()) {
+            regions[num] = Region{start, ver, SZMAX, 0, SZMAX, 0};
+            if (nreg < num) nreg = num;
+        } else {
+            Region& r = found->second;
+            if (start != r.bottom || ver != r.top)
+                throw ComputationError(solver_id + ": Junction " + std::to_string(num - 1) +
+                                       " does not have top and bottom edges at constant heights");
+            if (tra < r.left) r.left = tra;
+            if (tra >= r.right) r.right = tra + 1;
+            if (lon < r.back) r.back = lon;
+            if (lon >= r.front) r.front = lon + 1;
+        }
+    };
+    for (size_t lon = 0; lon < p0; ++lon)
+        for (size_t tra = 0; tra < p1; ++tra) {
+            size_t num = 0, start = 0;
+            for (size_t ver = 0; ver < p2; ++ver) {
+                size_t cur = junction_number(lon, tra, ver);
+                if (cur != num) {
+                    if (num) summarize(num, start, ver, lon, tra);
+                    num = cur; start = ver;
+                }
+            }
+            if (num) summarize(num, start, p2, lon, tra);
+        }
+    // NOTE (reference quirk kept): the column that CREATES a region does not widen it, so a junction made of a
+    // single column keeps left = SIZE_MAX, right = 0; real junctions span many columns and are unaffected.
+    std::vector<pfem_junction> active(nreg);
+    for (auto& a : active) { a = pfem_junction{0, 0, 0, 0, 0, 0, 0, 0, 0.}; }
+    size_t tot = 0;
+    for (auto& ir : regions) {
+        const Region& r = ir.second;
+        pfem_junction a;
+        a.bottom = r.bottom; a.top = r.top; a.left = r.left; a.right = r.right; a.back = r.back; a.front = r.front;
+        if (r.left == SZMAX || r.back == SZMAX) { a.left = a.right = a.back = a.front = 0; }
+        a.ld = a.front - a.back;
+        a.offset = (ptrdiff_t)tot - (ptrdiff_t)(a.ld * a.left) - (ptrdiff_t)a.back;
+        a.height = m.axis[2][r.top] - m.axis[2][r.bottom];
+        active[ir.first - 1] = a;
+        tot += (a.right - a.left) * (a.front - a.back);
+    }
+    if (condsize) *condsize = tot;
+    return active;
+}
+
+// ---- iter_params (iterative_matrix.hpp:25-94) ---------------------------------------------------------
+
+struct IterParams {
+    enum NoConvergenceBehavior { NO_CONVERGENCE_ERROR, NO_CONVERGENCE_WARNING, NO_CONVERGENCE_CONTINUE };
+    int maxit = 10000;
+    double maxerr = 1e-8;   // relative residual ||r||/||b_free|| (north-star criterion)
+    NoConvergenceBehavior no_convergence_behavior = NO_CONVERGENCE_WARNING;
+    // outputs (:90-93)
+    bool converged = true;
+    int iters = 0;
+    double err = 0.;
+};
+
+typedef std::function<void(int level /*0 error .. 3 result, 4 detail*/, const std::string&)> LogFn;
+
+// ---- RAII context -------------------------------------------------------------------------------------
+
+class Context {
+    pfem_ctx* ctx_ = nullptr;
+    std::string id_;
+
+    void check(int rc) const {
+        if (rc >= 0) return;
+        std::string msg = id_ + ": " + pfem_strerror(rc);
+        const char* d = pfem_last_error(ctx_);
+        if (d && *d) msg += std::string(" (") + d + ")";
+        switch (rc) {
+            case PFEM_ERR_BAD_INPUT: case PFEM_ERR_STATE: throw BadInput(msg);
+            case PFEM_ERR_NO_DEVICE: throw NoDevice(msg);
+            default: throw ComputationError(msg);
+        }
+    }
+
+  public:
+    explicit Context(int device = 0, std::string solver_id = "") : id_(std::move(solver_id)) {
+        int rc = pfem_create(&ctx_, device);
+        if (rc != PFEM_OK) { ctx_ = nullptr; throw NoDevice(id_ + ": " + pfem_strerror(rc)); }
+    }
+    ~Context() { if (ctx_) pfem_destroy(ctx_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    pfem_ctx* get() const { return ctx_; }
+
+    void set_mesh(const Mesh& m) {
+        if (m.n(0) < 2 || m.n(1) < 2 || m.n(2) < 2) throw BadInput(id_ + ": mesh needs at least 2 points per axis");
+        size_t n[3] = {m.n(0), m.n(1), m.n(2)}, s[3];
+        m.strides(s);
+        check(pfem_set_mesh(ctx_, n, m.axis[0].data(), m.axis[1].data(), m.axis[2].data(), s));
+    }
+    void set_materials(const std::vector<uint32_t>& ids, const Tables& t) {
+        check(pfem_set_materials(ctx_, ids.data(), t.nmat, t.T0, t.dT, t.nT, t.lat.data(), t.vert.data()));
+    }
+    void set_dirichlet(const Dirichlet& bc) { check(pfem_set_dirichlet(ctx_, bc.node.size(), bc.node.data(), bc.value.data())); }
+    void set_source(const double* heat_per_elem) { check(pfem_set_source(ctx_, heat_per_elem)); }
+    void set_field(const double* x0) { check(pfem_set_field(ctx_, x0)); }
+    void fill_field(double v) { check(pfem_fill_field(ctx_, v)); }
+    void set_elem_temperature(const double* Te, double uniform = 300.) { check(pfem_set_elem_temperature(ctx_, Te, uniform)); }
+    void set_junctions(const std::vector<pfem_junction>& act, const std::vector<uint32_t>& elem_junc,
+                       const std::vector<uint8_t>& elem_role, double pcond, double ncond, const std::vector<double>& junc_cond,
+                       const std::vector<double>& beta_col, const std::vector<double>& js_col, bool stable) {
+        check(pfem_set_junctions(ctx_, (uint32_t)act.size(), act.data(), elem_junc.data(), elem_role.empty() ? nullptr : elem_role.data(),
+                                 pcond, ncond, beta_col.size(), junc_cond.data(), beta_col.data(), js_col.data(), stable ? 1 : 0));
+    }
+    void get_field(double* x) { check(pfem_get_field(ctx_, x)); }
+    void get_elem(int what, double* out, const uint8_t* noheat = nullptr) { check(pfem_get_elem(ctx_, what, noheat, out)); }
+    void get_junction_cond(double* jc) { check(pfem_get_junction_cond(ctx_, jc)); }
+
+    struct LoopResult { int loops, loopno; double err, toterr, maxval; double maxcur[3]; long long lin_iters; double ms; };
+
+    // The do..while of compute() on the device.  Fills iter_params like SparseMatrix::solverhs does
+    // (iterative_matrix.hpp:330-336) and applies the noconv policy (:296-314).
+    LoopResult solve(bool thermal, IterParams& ip, double maxerr, int loops, const LogFn& log = LogFn()) {
+        pfem_opts o;
+        pfem_default_opts(&o);
+        o.maxit = ip.maxit; o.lin_tol = ip.maxerr; o.outer_tol = maxerr; o.loops = loops;
+        pfem_stats st;
+        int rc = thermal ? pfem_solve_thermal(ctx_, &o, &st) : pfem_solve_shockley(ctx_, &o, &st);
+        check(rc);
+        ip.converged = st.converged != 0; ip.iters = st.last_iters; ip.err = st.lin_relres;
+        if (rc == PFEM_NOT_CONVERGED) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "Failed to converge in %d iterations (error %g)", ip.maxit, ip.err);
+            switch (ip.no_convergence_behavior) {
+                case IterParams::NO_CONVERGENCE_ERROR: throw ComputationError(id_ + ": " + buf);
+                case IterParams::NO_CONVERGENCE_WARNING: if (log) log(1, buf); break;
+                case IterParams::NO_CONVERGENCE_CONTINUE: if (log) log(4, buf); break;
+            }
+        } else if (log) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "Conjugate gradient converged after %d iterations (error %g)", ip.iters, ip.err);
+            log(4, buf);
+        }
+        LoopResult r{st.outer_loops, st.loopno, st.err, st.toterr, st.maxval, {st.maxcur[0], st.maxcur[1], st.maxcur[2]},
+                     st.lin_iters, st.t_solve_ms};
+        if (log) {
+            char buf[200];
+            if (thermal) snprintf(buf, sizeof buf, "Loop %d(%d): max(T) = %.3f K, error = %g K", r.loops, r.loopno, r.maxval, r.err);
+            else snprintf(buf, sizeof buf, "Loop %d(%d): max(j%s) = %g kA/cm2, error = %g%%", r.loops, r.loopno, "@junc", r.maxval, r.err);
+            log(3, buf);
+        }
+        return r;
+    }
+};
+
+}  // namespace plaskfem
+#endif  // PLASKFEM_CUDA_HPP

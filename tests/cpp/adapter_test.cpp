@@ -1,0 +1,163 @@
+// adapter_test.cpp — exercises include/plaskfem_cuda.hpp the way the solver plugin would.
+//   adapter_test host   host-side logic only (no GPU): thickness, ids, junction detection, BC flattening,
+//                       NoDevice mapping when no CUDA device is usable
+//   adapter_test gpu    additionally a Static3D solve with a manufactured solution (uniform k, uniform heat,
+//                       Dirichlet bottom: T(z) = T0 + q (2Hz - z^2) / (2k), nodally exact for trilinear bricks,
+//                       SURVEY.md §8c(ii)) and a two-material k(T) problem run through Context::solve
+#include <cassert>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "plaskfem_cuda.hpp"
+
+using namespace plaskfem;
+
+#define REQUIRE(c) do { if (!(c)) { fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
+
+static Mesh make_mesh(size_t n0, size_t n1, size_t n2, IterationOrder o) {
+    Mesh m;
+    for (size_t i = 0; i < n0; ++i) m.axis[0].push_back(0.5 * i + 0.01 * i * i);
+    for (size_t i = 0; i < n1; ++i) m.axis[1].push_back(0.7 * i);
+    for (size_t i = 0; i < n2; ++i) m.axis[2].push_back(0.1 * i + 0.02 * i * i);
+    m.order = o;
+    return m;
+}
+
+static int host_tests() {
+    Mesh m = make_mesh(5, 4, 9, ORDER_012);
+    size_t s[3], es[3];
+    m.strides(s); m.elem_strides(es);
+    REQUIRE(s[2] == 1 && s[1] == 9 && s[0] == 36);
+    REQUIRE(es[2] == 1 && es[1] == 8 && es[0] == 24);
+    Mesh o = make_mesh(5, 4, 9, ORDER_012);
+    o.set_optimal_order();               // sizes 5,4,9 -> largest axis slowest: major 2, medium 0, minor 1
+    REQUIRE(o.order == ORDER_201);
+
+    // layers: rows 0-2 material 1, rows 3-4 material 2, rows 5-7 material 1; one column differs
+    auto key = [](size_t i0, size_t i1, size_t r) -> int {
+        if (i0 == 1 && i1 == 2) return r < 4 ? 7 : 1;
+        return (r < 3 || r >= 5) ? 1 : 2;
+    };
+    std::vector<double> th = layer_thickness(m, key);
+    const double* z = m.axis[2].data();
+    REQUIRE(std::fabs(th[m.elem(0, 0, 1)] - (z[3] - z[0])) < 1e-15);
+    REQUIRE(std::fabs(th[m.elem(0, 0, 3)] - (z[5] - z[3])) < 1e-15);
+    REQUIRE(std::fabs(th[m.elem(3, 2, 7)] - (z[8] - z[5])) < 1e-15);
+    REQUIRE(std::fabs(th[m.elem(1, 2, 2)] - (z[4] - z[0])) < 1e-15);
+    REQUIRE(std::fabs(th[m.elem(1, 2, 6)] - (z[8] - z[4])) < 1e-15);
+    std::vector<int> keys(m.elements());
+    for (size_t i0 = 0; i0 < 4; ++i0) for (size_t i1 = 0; i1 < 3; ++i1) for (size_t r = 0; r < 8; ++r) keys[m.elem(i0, i1, r)] = key(i0, i1, r);
+    std::vector<size_t> reps;
+    std::vector<uint32_t> ids = material_ids(keys, th, &reps);
+    // (1, z3-z0), (2, z5-z3), (1, z8-z5), (7, z4-z0), (1, z8-z4)
+    REQUIRE(reps.size() == 5);
+    REQUIRE(ids[m.elem(0, 0, 0)] == ids[m.elem(3, 1, 2)] && ids[m.elem(0, 0, 0)] != ids[m.elem(0, 0, 6)]);
+
+    // junction: rows 3..4 active in columns lon 1..2, tra 0..2
+    auto jn = [](size_t lon, size_t tra, size_t ver) -> size_t { return (lon >= 1 && lon <= 2 && ver >= 3 && ver < 5) ? 1 : 0; (void)tra; };
+    size_t condsize = 0;
+    std::vector<pfem_junction> act = setup_active_regions(m, jn, &condsize, "test");
+    REQUIRE(act.size() == 1);
+    REQUIRE(act[0].bottom == 3 && act[0].top == 5 && act[0].back == 1 && act[0].front == 3 && act[0].left == 0 && act[0].right == 3);
+    REQUIRE(act[0].ld == 2 && condsize == 6 && act[0].offset == -1);
+    REQUIRE(std::fabs(act[0].height - (z[5] - z[3])) < 1e-15);
+    bool thrown = false;
+    try {
+        auto bad = [](size_t lon, size_t, size_t ver) -> size_t { return (ver >= (lon == 0 ? 2u : 3u) && ver < 5) ? 1 : 0; };
+        setup_active_regions(m, bad, &condsize, "test");
+    } catch (const ComputationError& e) { thrown = strstr(e.what(), "constant heights") != nullptr; }
+    REQUIRE(thrown);
+
+    Dirichlet bc;
+    std::vector<size_t> bottom;
+    for (size_t i0 = 0; i0 < 5; ++i0) for (size_t i1 = 0; i1 < 4; ++i1) bottom.push_back(m.node(i0, i1, 0));
+    bc.add(bottom, 300.);
+    REQUIRE(bc.node.size() == 20 && bc.value[19] == 300.);
+
+    Tables t = sample_tables(2, [](uint32_t id, double T) { return std::make_pair(10. * (id + 1) * 300. / T, 5. * (id + 1)); }, 250., 0.5, 701);
+    REQUIRE(t.lat.size() == 1402 && std::fabs(t.lat[701 + 100] - 20. * 300. / 300.) < 1e-12);
+
+    if (pfem_device_count() == 0) {
+        bool nodev = false;
+        try { Context c(0, "nodev"); } catch (const NoDevice&) { nodev = true; }
+        REQUIRE(nodev);   // no CPU fallback: creating a context without a device must throw
+    }
+    printf("adapter host tests ok\n");
+    return 0;
+}
+
+static int gpu_tests() {
+    // ---- manufactured solution
+    for (int ord = 0; ord < 6; ++ord) {
+        Mesh m = make_mesh(9, 7, 21, (IterationOrder)ord);
+        const size_t N = m.size(), E = m.elements();
+        const double k = 44., q = 3e15, T0 = 300.;
+        Context c(0, "manufactured");
+        c.set_mesh(m);
+        std::vector<uint32_t> ids(E, 0);
+        Tables t = sample_tables(1, [&](uint32_t, double) { return std::make_pair(k, k); }, 250., 1., 400);
+        c.set_materials(ids, t);
+        c.fill_field(T0);
+        Dirichlet bc;
+        std::vector<size_t> bottom;
+        for (size_t i0 = 0; i0 < m.n(0); ++i0) for (size_t i1 = 0; i1 < m.n(1); ++i1) bottom.push_back(m.node(i0, i1, 0));
+        bc.add(bottom, T0);
+        c.set_dirichlet(bc);
+        std::vector<double> heat(E, q);
+        c.set_source(heat.data());
+        IterParams ip;
+        ip.maxerr = 1e-12; ip.maxit = 20000;
+        Context::LoopResult r = c.solve(true, ip, 0.05, 0);
+        REQUIRE(ip.converged && r.loops >= 1);
+        std::vector<double> T(N);
+        c.get_field(T.data());
+        const double H = (m.axis[2].back() - m.axis[2].front()) * 1e-6;
+        double maxd = 0.;
+        for (size_t i0 = 0; i0 < m.n(0); ++i0) for (size_t i1 = 0; i1 < m.n(1); ++i1) for (size_t i2 = 0; i2 < m.n(2); ++i2) {
+            const double z = (m.axis[2][i2] - m.axis[2][0]) * 1e-6;
+            const double ex = T0 + q * (2. * H * z - z * z) / (2. * k);
+            maxd = std::fmax(maxd, std::fabs(T[m.node(i0, i1, i2)] - ex));
+        }
+        printf("order %d: loops %d, PCG iterations %lld, max|T - T_exact| = %.3e K (max T %.3f)\n", ord, r.loops, r.lin_iters, maxd, r.maxval);
+        REQUIRE(maxd < 1e-6);
+    }
+    // ---- noconv policy
+    {
+        Mesh m = make_mesh(9, 7, 21, ORDER_012);
+        Context c(0, "noconv");
+        c.set_mesh(m);
+        std::vector<uint32_t> ids(m.elements(), 0);
+        c.set_materials(ids, sample_tables(1, [](uint32_t, double T) { return std::make_pair(45. * std::pow(300. / T, 1.28), 45. * std::pow(300. / T, 1.28)); }));
+        c.fill_field(300.);
+        Dirichlet bc;
+        std::vector<size_t> bottom;
+        for (size_t i0 = 0; i0 < m.n(0); ++i0) for (size_t i1 = 0; i1 < m.n(1); ++i1) bottom.push_back(m.node(i0, i1, 0));
+        bc.add(bottom, 300.);
+        c.set_dirichlet(bc);
+        std::vector<double> heat(m.elements(), 1e16);
+        c.set_source(heat.data());
+        IterParams ip;
+        ip.maxit = 3; ip.maxerr = 1e-12;
+        ip.no_convergence_behavior = IterParams::NO_CONVERGENCE_ERROR;
+        bool thrown = false;
+        try { c.solve(true, ip, 0.05, 1); } catch (const ComputationError& e) { thrown = strstr(e.what(), "Failed to converge") != nullptr; }
+        REQUIRE(thrown && !ip.converged && ip.iters == 3);
+        int warned = 0;
+        ip.no_convergence_behavior = IterParams::NO_CONVERGENCE_WARNING;
+        c.solve(true, ip, 0.05, 1, [&](int lvl, const std::string&) { if (lvl == 1) ++warned; });
+        REQUIRE(warned == 1);
+        bool bad = false;
+        try { c.set_source(nullptr); IterParams z; z.maxit = 0; c.solve(true, z, 0.05, 1); } catch (const BadInput&) { bad = true; }
+        REQUIRE(bad);
+    }
+    printf("adapter gpu tests ok\n");
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    int rc = host_tests();
+    if (rc) return rc;
+    if (argc > 1 && !strcmp(argv[1], "gpu")) rc = gpu_tests();
+    return rc;
+}

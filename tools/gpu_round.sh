@@ -12,8 +12,10 @@ for f in tests/test_gpu_operator.py tests/test_gpu_thermal.py tests/test_gpu_sho
 done
 timeout 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" | tee -a gpurun_out/summary.txt
 tail -n 4 gpurun_out/smoke.log
-timeout 900 python bench.py --steps 3 --warmup 3 ${BENCH_ARGS:-} > gpurun_out/bench.log 2>&1; echo "bench exit $?" | tee -a gpurun_out/summary.txt
-tail -n 2 gpurun_out/bench.log
+if [ "${WITH_BENCH:-1}" = "1" ]; then
+  timeout 900 python bench.py --steps 3 --warmup 3 ${BENCH_ARGS:-} > gpurun_out/bench.log 2>&1; echo "bench exit $?" | tee -a gpurun_out/summary.txt
+  tail -n 2 gpurun_out/bench.log
+fi
 if [ "${WITH_NCU:-1}" = "1" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
      python bench.py --steps 2 --warmup 1 --iters 10 --no-tts --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1

@@ -185,10 +185,26 @@ typedef enum {
     PFEM_ELEM_HEAT = 2,     /* Joule heat, E [W/m3]               (electr3d.cpp:444-478)     */
     PFEM_ELEM_FLUX = 3      /* heat flux, E x 3 [W/m2]            (therm3d.cpp:342-384)      */
 } pfem_elem_field;
-/* noheat[E] (may be NULL): elements with EMPTY material or the "noheat" role get zero heat
- * (electr3d.cpp:472); only read for PFEM_ELEM_HEAT. */
+/* noheat[E] (may be NULL = keep what pfem_set_noheat stored): elements with EMPTY material or the "noheat" role
+ * get zero heat (electr3d.cpp:472); only read for PFEM_ELEM_HEAT. */
 int pfem_get_elem(pfem_ctx* ctx, int what, const uint8_t* noheat, double* out);
 int pfem_get_junction_cond(pfem_ctx* ctx, double* junc_cond /* [ncol][2] */);
+
+/* ---- field exchange between two contexts on the same device ------------------------
+ * The ThermoElectric meta loop (solvers/meta/shockley/thermoelectric.py:207-211) connects
+ *     electrical.inTemperature <- thermal.outTemperature      and      thermal.inHeat <- electrical.outHeat.
+ * In the reference both go through a per-point virtual LazyData::at on the host; here the data never leave HBM.
+ * The two meshes may differ (thermoelectric.py:132-138): values are interpolated linearly exactly like
+ * RectilinearMesh3D::interpolateLinear (rectilinear3d.hpp:802-845, constant outside the source mesh).
+ * In slab mode both contexts must hold the same planes of the same partition (the exchange is then local). */
+/* EMPTY-material / "noheat" elements get zero Joule heat (electr3d.cpp:472); kept until the next pfem_set_mesh. */
+int pfem_set_noheat(pfem_ctx* ctx, const uint8_t* noheat /* E, may be NULL to clear */);
+/* T_elem of `electrical` <- temperatures of `thermal` at the element midpoints of `electrical`
+ * (getTemperatures, therm3d.cpp:385-393 -> loadConductivity, electr3d.cpp:203-205). */
+int pfem_transfer_temperature(pfem_ctx* electrical, pfem_ctx* thermal);
+/* load vector of `thermal` <- Joule heat density of `electrical` (saveHeatDensity, electr3d.cpp:444-478; getHeatDensity
+ * :538-548) at the element midpoints of `thermal` (setMatrix, therm3d.cpp:179,223). */
+int pfem_transfer_heat(pfem_ctx* thermal, pfem_ctx* electrical);
 
 /* ---- building blocks exposed for parity tests and the benchmark ---------------------- */
 /* conds from the current field (thermal, therm3d.cpp:204-213) */

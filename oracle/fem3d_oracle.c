@@ -665,3 +665,47 @@ int orc_pcg_jacobi_sparse14(size_t rank, const int icords[14], const double* dat
     free(r); free(z); free(p); free(q);
     return rc ? rc : it;
 }
+
+/* ------------------------------------------------------------------ provider interpolation */
+/* RectilinearMesh3D::interpolateLinear (plask/mesh/rectilinear3d.hpp:802-845) for a geometry without
+ * symmetry/periodicity: per axis prepareInterpolationForAxis (plask/mesh/axis1d.cpp:99-156) — index_hi =
+ * upper_bound(axis, p); outside the axis both indices coincide (constant extrapolation) and the fake
+ * coordinate is axis end -/+ 1 — then interpolation::trilinear (plask/utils/interpolation.hpp:31-71).
+ * src: data on a rectilinear mesh with axes sa0..2 (sizes sn) and linear index i0*ss[0]+i1*ss[1]+i2*ss[2];
+ * destination points: the tensor product of da0 x da1 x da2 (sizes dn), written at j0*ds[0]+j1*ds[1]+j2*ds[2]. */
+static void prep_axis(const double* ax, size_t n, double p, size_t* ilo, size_t* ihi, double* lo, double* hi) {
+    size_t up = 0, cnt = n;            /* std::upper_bound */
+    while (cnt > 0) {
+        size_t step = cnt / 2, it = up + step;
+        if (!(p < ax[it])) { up = it + 1; cnt -= step + 1; } else cnt = step;
+    }
+    *ihi = up;
+    if (up == 0) { *ilo = 0; *lo = ax[0] - 1.; } else { *ilo = up - 1; *lo = ax[up - 1]; }
+    if (up == n) { *ihi = n - 1; *hi = ax[n - 1] + 1.; } else *hi = ax[up];
+}
+
+void orc_interp_linear(const size_t sn[3], const double* sa0, const double* sa1, const double* sa2, const size_t ss[3],
+                       const double* src, const size_t dn[3], const double* da0, const double* da1, const double* da2,
+                       const size_t ds[3], double* dst) {
+    for (size_t j0 = 0; j0 < dn[0]; ++j0) {
+        size_t l0, h0; double back, front;
+        prep_axis(sa0, sn[0], da0[j0], &l0, &h0, &back, &front);
+        for (size_t j1 = 0; j1 < dn[1]; ++j1) {
+            size_t l1, h1; double left, right;
+            prep_axis(sa1, sn[1], da1[j1], &l1, &h1, &left, &right);
+            for (size_t j2 = 0; j2 < dn[2]; ++j2) {
+                size_t l2, h2; double bottom, top;
+                prep_axis(sa2, sn[2], da2[j2], &l2, &h2, &bottom, &top);
+                const double px = da0[j0], py = da1[j1], pz = da2[j2];
+#define D(a, b, c) src[(a) * ss[0] + (b) * ss[1] + (c) * ss[2]]
+                const double dxh = front - px, dxl = px - back;
+                const double lo = ((D(l0, l1, l2) * dxh + D(h0, l1, l2) * dxl) * (right - py) +
+                                   (D(l0, h1, l2) * dxh + D(h0, h1, l2) * dxl) * (py - left)) / (right - left) / (front - back);
+                const double hi = ((D(l0, l1, h2) * dxh + D(h0, l1, h2) * dxl) * (right - py) +
+                                   (D(l0, h1, h2) * dxh + D(h0, h1, h2) * dxl) * (py - left)) / (right - left) / (front - back);
+#undef D
+                dst[j0 * ds[0] + j1 * ds[1] + j2 * ds[2]] = lo + (pz - bottom) / (top - bottom) * (hi - lo);
+            }
+        }
+    }
+}

@@ -460,3 +460,61 @@ class Shockley3DOracle:
         assert len(vals) == 2
         U = vals[1] - vals[0]
         return 2e12 * self.get_total_energy() / (U * U)
+
+
+# ------------------------------------------------------------------------- ThermoElectric3D
+
+
+def midpoints(a):
+    """MidpointAxis::at (plask/mesh/axis1d.cpp:51-53)."""
+    a = np.asarray(a, dtype=np.float64)
+    return (a[:-1] + a[1:]) * 0.5
+
+
+def interp_linear(src_axes, src_strides, src, dst_axes, dst_strides, dst_size):
+    """RectilinearMesh3D::interpolateLinear onto the tensor-product points dst_axes (rectilinear3d.hpp:802-845)."""
+    sa = [np.ascontiguousarray(a, dtype=np.float64) for a in src_axes]
+    da = [np.ascontiguousarray(a, dtype=np.float64) for a in dst_axes]
+    out = np.zeros(dst_size)
+    sn = (c_sz * 3)(*[len(a) for a in sa])
+    dn = (c_sz * 3)(*[len(a) for a in da])
+    ss = (c_sz * 3)(*[int(s) for s in src_strides])
+    ds = (c_sz * 3)(*[int(s) for s in dst_strides])
+    lib().orc_interp_linear(sn, _p(sa[0]), _p(sa[1]), _p(sa[2]), ss, _p(np.ascontiguousarray(src, dtype=np.float64)),
+                            dn, _p(da[0]), _p(da[1]), _p(da[2]), ds, _p(out))
+    return out
+
+
+class ThermoElectric3DOracle:
+    """meta.shockley.ThermoElectric3D (solvers/meta/shockley/thermoelectric.py:187-211) over the two oracles:
+    electrical.inTemperature = thermal.outTemperature (linear interpolation at the electrical element midpoints,
+    therm3d.cpp:385-393, electr3d.cpp:203-205); thermal.inHeat = electrical.outHeat (linear interpolation of the
+    element-mesh data at the thermal element midpoints, electr3d.cpp:538-548, therm3d.cpp:179)."""
+
+    def __init__(self, thermal, electrical, tfreq=6):
+        self.thermal, self.electrical, self.tfreq = thermal, electrical, tfreq
+        self.history = []
+
+    def exchange_temperature(self):
+        t, e = self.thermal, self.electrical
+        e.Te = interp_linear(t.mesh.axes, t.mesh.ns, t.temperatures, [midpoints(a) for a in e.mesh.axes], e.mesh.es, e.mesh.E)
+
+    def exchange_heat(self):
+        t, e = self.thermal, self.electrical
+        e.heat = None
+        heat = e.heat_density()
+        t.heat = interp_linear([midpoints(a) for a in e.mesh.axes], e.mesh.es, heat, [midpoints(a) for a in t.mesh.axes],
+                               t.mesh.es, t.mesh.E)
+
+    def compute(self, max_meta_loops=100):
+        t, e = self.thermal, self.electrical
+        verr, terr = 2. * e.maxerr, 2. * t.maxerr
+        n = 0
+        while (terr > t.maxerr or verr > e.maxerr) and n < max_meta_loops:
+            self.exchange_temperature()
+            verr = e.compute(self.tfreq)
+            self.exchange_heat()
+            terr = t.compute(1)
+            n += 1
+            self.history.append(dict(verr=verr, terr=terr, maxT=t.maxT, current=e.get_total_current() if e.nact else 0.))
+        return n

@@ -80,6 +80,9 @@ SYMBOLS = {
     "pfem_get_field": (C.c_int, [_vp, c_dp]),
     "pfem_get_elem": (C.c_int, [_vp, C.c_int, _u8p, c_dp]),
     "pfem_get_junction_cond": (C.c_int, [_vp, c_dp]),
+    "pfem_set_noheat": (C.c_int, [_vp, _u8p]),
+    "pfem_transfer_temperature": (C.c_int, [_vp, _vp]),
+    "pfem_transfer_heat": (C.c_int, [_vp, _vp]),
     "pfem_update_conductivity_thermal": (C.c_int, [_vp]),
     "pfem_update_conductivity_shockley": (C.c_int, [_vp]),
     "pfem_set_conductivity": (C.c_int, [_vp, c_dp]),

@@ -365,7 +365,7 @@ def slab_local(nK, rank, nranks):
 
 
 def slab_problem(p, rank, nranks):
-    """Cut the local problem of `rank` out of a global thermal Problem — what the solver plugin would do on each
+    """Cut the local problem of `rank` out of a global Problem (thermal or Shockley) — what the solver plugin would do on each
     process before calling the C ABI in slab mode.  Returns (local Problem, own_lo, own_hi, (lo, hi))."""
     major = ORDERS[p.order][0]
     n = p.n
@@ -387,6 +387,11 @@ def slab_problem(p, rank, nranks):
 
     q.elem_mat = cut_elem(p.elem_mat, np.uint32)
     q.heat = cut_elem(p.heat, np.float64)
+    q.elem_junc = cut_elem(p.elem_junc, np.uint32)
+    q.elem_role = cut_elem(p.elem_role, np.uint8)
+    q.noheat = cut_elem(p.noheat, np.uint8)
+    for name in ("beta", "js", "pcond", "ncond", "start_cond", "Te"):
+        setattr(q, name, getattr(p, name))
     # Dirichlet nodes inside the local planes (halo planes included), in application order
     ns = p.strides
     order3 = sorted(range(3), key=lambda a: -ns[a])            # major, medium, minor

@@ -553,13 +553,39 @@ k_currents(const Grid g, const double* __restrict__ phi, const double* __restric
     }
 }
 
-// maxcur = current at the arg-max element (compact index -> slot)
+// maxcur = current at the arg-max element (compact index -> slot).  One warp.
+// Slab mode: the loop error and max |j|^2 become maxima over the ranks; among ranks that attain the maximum the
+// lowest one wins (slabs are ordered along the major axis, so this is still "first element in reference order")
+// and its current vector is broadcast.  Element layers shared with a neighbour are evaluated by both ranks from
+// identical data, which is harmless for maxima.
 __global__ void k_fetch_maxcur(const Grid g, const double* __restrict__ c0, const double* __restrict__ c1,
                                const double* __restrict__ c2, Scalars* sc) {
+    __shared__ double sh[8];
     const long long e = sc->argidx;
-    if (e < 0 || e >= g.E) { sc->maxcur[0] = sc->maxcur[1] = sc->maxcur[2] = 0.; return; }
-    const idx_t slot = compact_to_slot(g, e);
-    sc->maxcur[0] = c0[slot]; sc->maxcur[1] = c1[slot]; sc->maxcur[2] = c2[slot];
+    double cur[3] = {0., 0., 0.};
+    const bool have = !(e < 0 || e >= g.E);
+    if (have) {
+        const idx_t slot = compact_to_slot(g, e);
+        cur[0] = c0[slot]; cur[1] = c1[slot]; cur[2] = c2[slot];
+    }
+    Comm* cm = sc->comm;
+    if (cm) {
+        const double mine = sc->red[1];
+        double v[2] = {sc->red[0], mine};
+        rank_allreduce<2, true>(v, cm, sh);
+        if (threadIdx.x == 0) { sh[4] = v[0]; sh[5] = v[1]; }
+        __syncthreads();
+        const double g0 = sh[4], g1 = sh[5];
+        double w[1] = {(have && mine == g1) ? -(double)cm->rank : -1e9};
+        rank_allreduce<1, true>(w, cm, sh);
+        if (threadIdx.x == 0) sh[6] = w[0];
+        __syncthreads();
+        const bool winner = (sh[6] == -(double)cm->rank);
+        double b[3] = {winner ? cur[0] : 0., winner ? cur[1] : 0., winner ? cur[2] : 0.};
+        rank_allreduce<3, false>(b, cm, sh);
+        if (threadIdx.x == 0) { cur[0] = b[0]; cur[1] = b[1]; cur[2] = b[2]; sc->red[0] = g0; sc->red[1] = g1; }
+    }
+    if (threadIdx.x == 0) { sc->maxcur[0] = cur[0]; sc->maxcur[1] = cur[1]; sc->maxcur[2] = cur[2]; }
 }
 
 // Joule heat (electr3d.cpp:444-478) and heat flux (therm3d.cpp:342-384); o0..o2 padded outputs.
@@ -585,6 +611,43 @@ __global__ void k_gradient_fields(const Grid g, const double* __restrict__ u, co
         o1[n] = -0.25e6 * a * s1 / d1;
         o2[n] = -0.25e6 * b * s2 / d2;
     }
+}
+
+// ----------------------------------------------------- provider interpolation ----------
+// RectilinearMesh3D::interpolateLinear (plask/mesh/rectilinear3d.hpp:802-845) of a source lattice array onto the
+// element midpoints of the destination mesh.  The per-axis bracketing (prepareInterpolationForAxis,
+// plask/mesh/axis1d.cpp:99-156) is tabulated by the host per destination element index of each PHYSICAL axis:
+// lo/hi source indices, their (possibly faked) coordinates and the point coordinate.  Arithmetic in the order of
+// interpolation::trilinear (plask/utils/interpolation.hpp:31-71), no FMA contraction: bit-equal to the oracle.
+struct InterpAxis {
+    const int *ilo, *ihi;
+    const double *lo, *hi, *pt;
+};
+__global__ void k_interp_to_elems(const Grid gd, const idx_t ss0, const idx_t ss1, const idx_t ss2,
+                                  const double* __restrict__ src, const InterpAxis a0, const InterpAxis a1,
+                                  const InterpAxis a2, double* __restrict__ dst) {
+    const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
+    const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
+    const int k = blockIdx.z;
+    int pi[3];
+    if (!elem_slot(gd, i, j, k, pi)) return;
+    const idx_t l0 = a0.ilo[pi[0]] * ss0, h0 = a0.ihi[pi[0]] * ss0;
+    const idx_t l1 = a1.ilo[pi[1]] * ss1, h1 = a1.ihi[pi[1]] * ss1;
+    const idx_t l2 = a2.ilo[pi[2]] * ss2, h2 = a2.ihi[pi[2]] * ss2;
+    const double back = a0.lo[pi[0]], front = a0.hi[pi[0]], px = a0.pt[pi[0]];
+    const double left = a1.lo[pi[1]], right = a1.hi[pi[1]], py = a1.pt[pi[1]];
+    const double bottom = a2.lo[pi[2]], top = a2.hi[pi[2]], pz = a2.pt[pi[2]];
+    const double dxh = __dsub_rn(front, px), dxl = __dsub_rn(px, back);
+    const double dyh = __dsub_rn(right, py), dyl = __dsub_rn(py, left);
+    const double wy = __dsub_rn(right, left), wx = __dsub_rn(front, back);
+    auto plane = [&](idx_t z) {
+        const double b = __dadd_rn(__dmul_rn(src[l0 + l1 + z], dxh), __dmul_rn(src[h0 + l1 + z], dxl));
+        const double t = __dadd_rn(__dmul_rn(src[l0 + h1 + z], dxh), __dmul_rn(src[h0 + h1 + z], dxl));
+        return __ddiv_rn(__ddiv_rn(__dadd_rn(__dmul_rn(b, dyh), __dmul_rn(t, dyl)), wy), wx);
+    };
+    const double lo = plane(l2), hi = plane(h2);
+    const double w = __ddiv_rn(__dsub_rn(pz, bottom), __dsub_rn(top, bottom));
+    dst[i + gd.sJ * j + gd.sK * k] = __dadd_rn(lo, __dmul_rn(w, __dsub_rn(hi, lo)));
 }
 
 }  // namespace pfem

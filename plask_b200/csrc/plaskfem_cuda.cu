@@ -73,6 +73,8 @@ struct pfem_ctx {
     long long launches = 0;
     double last_relres_pre = 0.;
     int sm_count = 148;
+    std::vector<double> hax[3];   // host copy of the physical axes (interpolation tables of the field exchange)
+    bool noheat_set = false;
     TiledPlan plan;
     TmaPlan tma;
     FusedPlan fused;
@@ -154,6 +156,7 @@ static void free_all(pfem_ctx* ctx) {
     ctx->partials = nullptr; ctx->partial_idx = nullptr; ctx->n_partials = 0;
     if (ctx->stage) { cudaFree(ctx->stage); ctx->stage = nullptr; ctx->stage_bytes = 0; }
     ctx->have_mesh = ctx->have_materials = ctx->have_junctions = ctx->conds_valid = false;
+    ctx->noheat_set = false;
 }
 
 template <typename T>
@@ -309,6 +312,8 @@ extern "C" int pfem_set_mesh(pfem_ctx* ctx, const size_t n[3], const double* ax0
     free_all(ctx);
     Grid& g = ctx->g;
     memset(&g, 0, sizeof(g));
+    for (int a = 0; a < 3; ++a) ctx->hax[a].assign(ax[a], ax[a] + n[a]);
+    ctx->noheat_set = false;
     g.nI = (int)n[minor]; g.nJ = (int)n[medium]; g.nK = (int)n[major];
     g.sJ = ((idx_t)g.nI + 15) / 16 * 16;   // 128-byte rows
     g.sK = g.sJ * g.nJ;
@@ -998,8 +1003,10 @@ extern "C" int pfem_solve_shockley(pfem_ctx* ctx, const pfem_opts* o, pfem_stats
     NEED_MESH();
     TRY(check_opts(ctx, o));
     if (!ctx->have_materials) FAIL(PFEM_ERR_STATE, "pfem_set_materials has not been called");
-    if (ctx->nranks > 1) FAIL(PFEM_ERR_BAD_INPUT, "slab mode (multi-GPU) is implemented for the thermal and the linear solve only");
     const Grid& g = ctx->g;
+    // slab mode: a junction must not be cut by the partition, i.e. the slab (major) axis has to be lateral
+    if (ctx->nranks > 1 && ctx->nact && g.vdim == 2)
+        FAIL(PFEM_ERR_BAD_INPUT, "slab mode with junctions needs a lateral major axis (iteration order 0xx or 1xx)");
     TRY(ensure_elem_arrays(ctx, true));
     long long l0 = ctx->launches;
     Timer t(ctx->stream);
@@ -1010,6 +1017,7 @@ extern "C" int pfem_solve_shockley(pfem_ctx* ctx, const pfem_opts* o, pfem_stats
     long long total_iters = 0;
     double err = 0., toterr = 0., mcur = 0., relres = 0.;
     const int cap = o->loops > 0 ? o->loops : 100000;
+    TRY(halo_sync(ctx, SA_X));                                  // slab mode: the potential of the halo planes
     do {
         if (ctx->loopno != 0 && ctx->nact) {                    // :246-274
             k_junction_update<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->junc, ctx->act, ctx->x, ctx->beta_col,
@@ -1018,10 +1026,11 @@ extern "C" int pfem_solve_shockley(pfem_ctx* ctx, const pfem_opts* o, pfem_stats
         }
         TRY(pcg_solve(ctx, o, &iters, &relres, &conv));        // assembly + applyBC + solve, :281-344,385
         total_iters += iters;
+        TRY(halo_sync(ctx, SA_X));                             // slab mode: the solve updates owned planes only
         k_currents<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->x, ctx->cl, ctx->cv, ctx->junc, noactive,
                                                                     ctx->cur0, ctx->cur1, ctx->cur2, ctx->d_sc,
                                                                     ctx->partials, ctx->partial_idx);
-        k_fetch_maxcur<<<1, 1, 0, ctx->stream>>>(g, ctx->cur0, ctx->cur1, ctx->cur2, ctx->d_sc);
+        k_fetch_maxcur<<<1, 32, 0, ctx->stream>>>(g, ctx->cur0, ctx->cur1, ctx->cur2, ctx->d_sc);
         KCHECK(); LAUNCHED(2);
         TRY(read_scalars(ctx));
         mcur = sqrt(ctx->h_sc->red[1]);
@@ -1071,12 +1080,8 @@ extern "C" int pfem_get_elem(pfem_ctx* ctx, int what, const uint8_t* noheat, dou
         case PFEM_ELEM_HEAT: {
             if (!ctx->conds_valid) FAIL(PFEM_ERR_STATE, "conductivities have not been computed");
             TRY(ensure_elem_arrays(ctx, false));
-            const uint8_t* nh = nullptr;
-            if (noheat) {
-                if (!ctx->noheat) TRY(dev_alloc(ctx, &ctx->noheat, (size_t)g.NP, (size_t)g.G));
-                TRY(upload_elem<uint8_t, 1>(ctx, noheat, ctx->noheat, nullptr, nullptr));
-                nh = ctx->noheat;
-            }
+            if (noheat) TRY(pfem_set_noheat(ctx, noheat));
+            const uint8_t* nh = ctx->noheat_set ? ctx->noheat : nullptr;
             k_gradient_fields<true><<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->x, ctx->cl, ctx->cv, nh, ctx->aux0,
                                                                                      ctx->aux1, ctx->aux2);
             KCHECK(); LAUNCHED(1);
@@ -1100,6 +1105,121 @@ extern "C" int pfem_get_junction_cond(pfem_ctx* ctx, double* junc_cond) {
     NEED_MESH();
     if (!ctx->nact || !junc_cond) FAIL(PFEM_ERR_BAD_INPUT, "no junctions / null output");
     CU(cudaMemcpyAsync(junc_cond, ctx->junc_cond, 2 * ctx->ncol * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+
+// ------------------------------------------------------------------ field exchange -------
+
+extern "C" int pfem_set_noheat(pfem_ctx* ctx, const uint8_t* noheat) {
+    NEED_MESH();
+    if (!noheat) { ctx->noheat_set = false; return PFEM_OK; }
+    if (!ctx->noheat) TRY(dev_alloc(ctx, &ctx->noheat, (size_t)ctx->g.NP, (size_t)ctx->g.G));
+    TRY(upload_elem<uint8_t, 1>(ctx, noheat, ctx->noheat, nullptr, nullptr));
+    ctx->noheat_set = true;
+    return PFEM_OK;
+}
+
+// Bracketing tables of prepareInterpolationForAxis (plask/mesh/axis1d.cpp:99-156, no symmetry / periodicity) for the
+// midpoints of `dst_ax` in the source axis `src` (node coordinates, or their midpoints when src_mid).
+struct AxisTab { std::vector<int> ilo, ihi; std::vector<double> lo, hi, pt; };
+static AxisTab make_axis_tab(const std::vector<double>& src_nodes, bool src_mid, const std::vector<double>& dst_ax) {
+    std::vector<double> mid;
+    if (src_mid) { mid.resize(src_nodes.size() - 1); for (size_t i = 0; i + 1 < src_nodes.size(); ++i) mid[i] = (src_nodes[i] + src_nodes[i + 1]) * 0.5; }
+    const std::vector<double>& src = src_mid ? mid : src_nodes;
+    const size_t n = src.size(), m = dst_ax.size() - 1;
+    AxisTab t;
+    t.ilo.resize(m); t.ihi.resize(m); t.lo.resize(m); t.hi.resize(m); t.pt.resize(m);
+    for (size_t j = 0; j < m; ++j) {
+        const double p = (dst_ax[j] + dst_ax[j + 1]) * 0.5;   // MidpointAxis::at, axis1d.cpp:51-53
+        size_t up = std::upper_bound(src.begin(), src.end(), p) - src.begin();
+        size_t ilo, ihi = up; double lo, hi;
+        if (up == 0) { ilo = 0; lo = src[0] - 1.; } else { ilo = up - 1; lo = src[up - 1]; }
+        if (up == n) { ihi = n - 1; hi = src[n - 1] + 1.; } else hi = src[up];
+        t.ilo[j] = (int)ilo; t.ihi[j] = (int)ihi; t.lo[j] = lo; t.hi[j] = hi; t.pt[j] = p;
+    }
+    return t;
+}
+
+// dst_arr (element lattice of dst) <- linear interpolation of src_arr (node or element lattice of src)
+static int interp_to_elems(pfem_ctx* dst, pfem_ctx* src, const double* src_arr, bool src_is_elem, double* dst_arr) {
+    pfem_ctx* ctx = dst;
+    if (src->device != dst->device) FAIL(PFEM_ERR_BAD_INPUT, "field exchange needs both contexts on the same device");
+    if (src->nranks != dst->nranks || src->rank != dst->rank) FAIL(PFEM_ERR_BAD_INPUT, "field exchange needs the same slab partition on both sides");
+    AxisTab tab[3];
+    size_t ni = 0, nd = 0;
+    for (int a = 0; a < 3; ++a) {
+        if (src_is_elem && src->hax[a].size() < 2) FAIL(PFEM_ERR_STATE, "source mesh not set");
+        tab[a] = make_axis_tab(src->hax[a], src_is_elem, dst->hax[a]);
+        ni += 2 * tab[a].ilo.size(); nd += 3 * tab[a].lo.size();
+    }
+    // one staging buffer: doubles first (8-byte aligned), then ints
+    const size_t bytes = nd * sizeof(double) + ni * sizeof(int);
+    std::vector<unsigned char> hb(bytes);
+    double* hd = reinterpret_cast<double*>(hb.data());
+    int* hi = reinterpret_cast<int*>(hb.data() + nd * sizeof(double));
+    void* dbuf = nullptr;
+    CU(cudaMalloc(&dbuf, bytes));
+    double* dd = reinterpret_cast<double*>(dbuf);
+    int* di = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(dbuf) + nd * sizeof(double));
+    InterpAxis ia[3];
+    size_t od = 0, oi = 0;
+    for (int a = 0; a < 3; ++a) {
+        const size_t m = tab[a].lo.size();
+        memcpy(hd + od, tab[a].lo.data(), m * 8); ia[a].lo = dd + od; od += m;
+        memcpy(hd + od, tab[a].hi.data(), m * 8); ia[a].hi = dd + od; od += m;
+        memcpy(hd + od, tab[a].pt.data(), m * 8); ia[a].pt = dd + od; od += m;
+        memcpy(hi + oi, tab[a].ilo.data(), m * 4); ia[a].ilo = di + oi; oi += m;
+        memcpy(hi + oi, tab[a].ihi.data(), m * 4); ia[a].ihi = di + oi; oi += m;
+    }
+    cudaError_t e = cudaStreamSynchronize(src->stream);            // the source field is final
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dbuf, hb.data(), bytes, cudaMemcpyHostToDevice, dst->stream);
+    if (e == cudaSuccess) {
+        const Grid& gs = src->g;
+        k_interp_to_elems<<<node_grid(dst->g), node_block(), 0, dst->stream>>>(dst->g, gs.ps[0], gs.ps[1], gs.ps[2], src_arr,
+                                                                                ia[0], ia[1], ia[2], dst_arr);
+        e = cudaGetLastError();
+        dst->launches += 1;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(dst->stream);
+    cudaFree(dbuf);
+    CU(e);
+    return PFEM_OK;
+}
+
+extern "C" int pfem_transfer_temperature(pfem_ctx* electrical, pfem_ctx* thermal) {
+    pfem_ctx* ctx = electrical;
+    NEED_MESH();
+    if (!thermal || !thermal->have_mesh) FAIL(PFEM_ERR_STATE, "thermal context has no mesh");
+    const Grid& g = ctx->g;
+    if (!ctx->Te) TRY(dev_alloc(ctx, &ctx->Te, (size_t)g.NP, (size_t)g.G));
+    TRY(interp_to_elems(electrical, thermal, thermal->x, false, ctx->Te));
+    ctx->conds_valid = false;
+    return PFEM_OK;
+}
+
+extern "C" int pfem_transfer_heat(pfem_ctx* thermal, pfem_ctx* electrical) {
+    pfem_ctx* ctx = electrical;
+    if (!thermal || !thermal->have_mesh) return PFEM_ERR_STATE;
+    NEED_MESH();
+    if (!ctx->conds_valid) FAIL(PFEM_ERR_STATE, "electrical conductivities have not been computed");
+    {   // Joule heat of the electrical solution on its own element lattice (aux0)
+        const Grid& g = ctx->g;
+        TRY(ensure_elem_arrays(ctx, false));
+        k_gradient_fields<true><<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->x, ctx->cl, ctx->cv,
+                                                                                 ctx->noheat_set ? ctx->noheat : nullptr,
+                                                                                 ctx->aux0, ctx->aux1, ctx->aux2);
+        KCHECK(); LAUNCHED(1);
+    }
+    const double* heat = ctx->aux0;
+    ctx = thermal;
+    CU(cudaSetDevice(ctx->device));
+    const Grid& g = ctx->g;
+    TRY(ensure_elem_arrays(ctx, false));
+    CU(cudaMemsetAsync(ctx->aux0 - g.G, 0, (size_t)(g.NP + 2 * g.G) * sizeof(double), ctx->stream));
+    TRY(interp_to_elems(thermal, electrical, heat, true, ctx->aux0));
+    k_load_vector<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->aux0, ctx->f);
+    KCHECK(); LAUNCHED(1);
     CU(cudaStreamSynchronize(ctx->stream));
     return PFEM_OK;
 }

@@ -105,6 +105,23 @@ class DeviceFem:
                                              er.ctypes.data_as(L._u8p) if er is not None else None, float(pcond),
                                              float(ncond), self.ncol, _dp(jc), _dp(bc), _dp(jsn), int(bool(stable))))
 
+    # ---- field exchange with another context on the same device (ThermoElectric meta loop)
+    def set_noheat(self, noheat):
+        nh = None if noheat is None else np.ascontiguousarray(noheat, dtype=np.uint8)
+        self._ck(self.lib.pfem_set_noheat(self.ctx, nh.ctypes.data_as(L._u8p) if nh is not None else None))
+
+    def take_temperature_from(self, thermal):
+        """self (electrical): T_elem <- thermal's temperatures at my element midpoints"""
+        self._ck(self.lib.pfem_transfer_temperature(self.ctx, thermal.ctx))
+
+    def take_heat_from(self, electrical):
+        """self (thermal): load vector <- electrical's Joule heat at my element midpoints"""
+        rc = self.lib.pfem_transfer_heat(self.ctx, electrical.ctx)
+        if rc < 0:   # the failing step recorded its message in the context it was working on
+            detail = self.lib.pfem_last_error(electrical.ctx)
+            L.check(electrical.ctx if detail else self.ctx, rc)
+        return rc
+
     # ---- slab mode (one DeviceFem per GPU / process; see include/plaskfem_cuda.h)
     def slab_configure(self, rank, nranks, own_lo, own_hi):
         self._ck(self.lib.pfem_slab_configure(self.ctx, int(rank), int(nranks), int(own_lo), int(own_hi)))

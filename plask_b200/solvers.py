@@ -70,6 +70,14 @@ class _FemSolver:
         self._fem = None
         self.initialized = False
 
+    def _setup_slab(self, f):
+        """slab mode: tell the context which planes it owns and map the neighbours' memory (collective)"""
+        if self.slab is not None:
+            sl = self.slab
+            f.slab_configure(sl["rank"], sl["nranks"], sl["own_lo"], sl["own_hi"])
+            if sl["nranks"] > 1:
+                f.slab_connect(sl["allgather"](f.slab_export()))
+
     def _opts(self, loops, outer_tol):
         if self.algorithm != "cuda":
             raise L.BadInput(f"{self.id}: algorithm '{self.algorithm}' is not provided by plask_b200 "
@@ -108,11 +116,7 @@ class Static3D(_FemSolver):
             raise L.BadInput(f"{self.id}: no geometry/mesh (problem) specified")
         f = self._fem = DeviceFem(self.device)
         f.set_mesh(p.axes, p.strides)
-        if self.slab is not None:
-            sl = self.slab
-            f.slab_configure(sl["rank"], sl["nranks"], sl["own_lo"], sl["own_hi"])
-            if sl["nranks"] > 1:
-                f.slab_connect(sl["allgather"](f.slab_export()))
+        self._setup_slab(f)
         f.set_materials(p.elem_mat, p.T0, p.dT, p.tab_lat, p.tab_vert)
         f.set_field(float(self.inittemp))               # temperatures.reset(size, inittemp), :79
         f.set_dirichlet(p.bc_nodes, p.bc_values)
@@ -125,9 +129,13 @@ class Static3D(_FemSolver):
             self.initialize()
         f, p = self._fem, self._problem
         heat = p.heat if self.inHeat is None else self.inHeat
-        if heat is not None and np.isscalar(heat):
-            heat = np.full(p.E, float(heat))
-        f.set_source(heat)
+        if isinstance(heat, Shockley3D):
+            # inHeat connected to electrical.outHeat: device-to-device, interpolated like getHeatDensity (electr3d.cpp:538-548)
+            f.take_heat_from(heat._fem)
+        else:
+            if heat is not None and np.isscalar(heat):
+                heat = np.full(p.E, float(heat))
+            f.set_source(heat)
         rc, st = f.solve_thermal(**self._opts(loops, self.maxerr))
         self._after(rc, st)
         self.maxT, self.loopno = st["maxval"], st["loopno"]
@@ -176,10 +184,12 @@ class Shockley3D(_FemSolver):
             self.js = p.js
         f = self._fem = DeviceFem(self.device)
         f.set_mesh(p.axes, p.strides)
+        self._setup_slab(f)
         f.set_materials(p.elem_mat, p.T0, p.dT, p.tab_lat, p.tab_vert)
         f.set_field(0.)                                  # potential.reset(size, 0.), electr3d.cpp:190
         f.set_dirichlet(p.bc_nodes, p.bc_values)
         f.set_source(None)
+        f.set_noheat(p.noheat)
         self._acts, self._ncol = setup_active(p)         # setupActiveRegions, :89-183
         if self._junc_cond is None or len(self._junc_cond) != max(self._ncol, 1):
             self._junc_cond = np.tile(np.asarray(self.start_cond, dtype=np.float64), (max(self._ncol, 1), 1))
@@ -189,6 +199,10 @@ class Shockley3D(_FemSolver):
     def invalidate(self):
         super().invalidate()
         self._junc_cond = None      # junction_conductivity.reset(1, default), :200
+
+    def _midplane_temperature(self):
+        """element temperatures on the host (only when beta/js are callables of T)"""
+        raise L.BadInput(f"{self.id}: beta(T)/js(T) callables with a connected inTemperature are not supported yet")
 
     def _per_junction(self, v, k):
         return v[k] if isinstance(v, (list, tuple)) else v
@@ -219,7 +233,16 @@ class Shockley3D(_FemSolver):
             self.initialize()
         f, p = self._fem, self._problem
         Te = self.inTemperature
-        f.set_elem_temperature(Te if np.isscalar(Te) else np.asarray(Te, dtype=np.float64))
+        if isinstance(Te, Static3D):
+            # inTemperature connected to thermal.outTemperature: device-to-device, interpolated like getTemperatures
+            # (therm3d.cpp:385-393); beta(T)/js(T) callables need the mid-plane values on the host
+            if not Te.initialized:
+                Te.initialize()
+            f.take_temperature_from(Te._fem)
+            need_T = any(callable(self._per_junction(v, k)) for k in range(len(self._acts)) for v in (self.beta, self.js))
+            Te = self._midplane_temperature() if need_T else 300.
+        else:
+            f.set_elem_temperature(Te if np.isscalar(Te) else np.asarray(Te, dtype=np.float64))
         bcol, jcol = self._junction_params(Te)
         f.set_junctions(self._acts, p.elem_junc if p.elem_junc is not None else np.zeros(p.E, np.uint32),
                         p.elem_role, self.pcond, self.ncond, self._junc_cond, bcol, jcol,
@@ -289,3 +312,51 @@ class Shockley3D(_FemSolver):
         d = self._elem_sizes()
         vol = d[0][:, None, None] * d[1][None, :, None] * d[2][None, None, :]
         return float((1e-15 * vol * heat[p.elem_index_grid()]).sum())
+
+
+class ThermoElectric3D:
+    """meta.shockley.ThermoElectric3D (solvers/meta/shockley/thermoelectric.py:160-215) over the two CUDA solvers.
+
+    `thermal.inHeat <- electrical.outHeat` and `electrical.inTemperature <- thermal.outTemperature` are connected
+    on the device (pfem_transfer_heat / pfem_transfer_temperature); the loop is the reference's:
+
+        while terr > thermal.maxerr or verr > electrical.maxerr:
+            verr = electrical.compute(tfreq)
+            terr = thermal.compute(1)
+    """
+
+    def __init__(self, name=""):
+        self.id = name
+        self.thermal = Static3D(name + "-thermal")
+        self.electrical = Shockley3D(name + "-electrical")
+        self.tfreq = 6                                   # thermoelectric.py:57
+        self.thermal.inHeat = self.electrical
+        self.electrical.inTemperature = self.thermal
+        self.history = []
+
+    def initialize(self):
+        if not self.thermal.initialized:
+            self.thermal.initialize()
+        if not self.electrical.initialized:
+            self.electrical.initialize()
+
+    def invalidate(self):
+        self.thermal.invalidate()
+        self.electrical.invalidate()
+
+    def compute(self, invalidate=True, max_meta_loops=100):
+        if invalidate:
+            self.invalidate()
+        self.initialize()
+        t, e = self.thermal, self.electrical
+        verr, terr = 2. * e.maxerr, 2. * t.maxerr
+        n = 0
+        while (terr > t.maxerr or verr > e.maxerr) and n < max_meta_loops:
+            verr = e.compute(self.tfreq)
+            terr = t.compute(1)
+            n += 1
+            self.history.append(dict(verr=verr, terr=terr, maxT=t.maxT))
+        return n
+
+    def get_total_current(self, nact=0):
+        return self.electrical.get_total_current(nact)

@@ -55,6 +55,18 @@ def main():
     d = cf.config_B(n, rows0=(lo, hi))
     assert np.array_equal(d.elem_mat, q.elem_mat) and np.array_equal(d.heat, q.heat)
     assert np.array_equal(np.sort(d.bc_nodes), np.sort(q.bc_nodes))
+    # Shockley problem: junction / role arrays are cut the same way and the local junction description is consistent
+    pc = cf.config_C((8 * world + 5, 22, 52), order="012")
+    qc, c_lo, c_hi, (clo, chi) = cf.slab_problem(pc, rank, world)
+    egc = np.broadcast_to(pc.elem_index_grid(), tuple(k - 1 for k in pc.n))
+    legc = np.broadcast_to(qc.elem_index_grid(), tuple(k - 1 for k in qc.n))
+    assert np.array_equal(qc.elem_junc[legc], pc.elem_junc[egc][clo:chi - 1])
+    assert np.array_equal(qc.noheat[legc], pc.noheat[egc][clo:chi - 1])
+    acts_g, _ = cf.setup_active(pc)
+    acts_l, ncol_l = cf.setup_active(qc)
+    if ncol_l:
+        assert acts_l[0]["bottom"] == acts_g[0]["bottom"] and acts_l[0]["top"] == acts_g[0]["top"]
+        assert acts_l[0]["back"] + clo >= acts_g[0]["back"] and acts_l[0]["front"] + clo <= acts_g[0]["front"]
     blobs = allgather_bytes(bytes([rank]) * 64)
     assert [b[0] for b in blobs] == list(range(world))
     if host_only:
@@ -107,6 +119,47 @@ def main():
         assert stats[0]["outer_loops"] == one.stats["outer_loops"] == len(o.history)
         assert abs(stats[0]["lin_iters"] - one.stats["lin_iters"]) <= 0.02 * one.stats["lin_iters"] + 2
         assert d1 <= 1e-6 and d2 <= 1e-3
+        one.invalidate()
+    dist.barrier()
+
+    # ---- Shockley3D in slab mode: fixed number of loops, against the single-GPU solve and the oracle's Cholesky
+    from plask_b200.solvers import Shockley3D
+    LOOPS = 6
+
+    def shockley(name, prob, slab=None, dev=local):
+        e = Shockley3D(name)
+        e.device = dev
+        e.problem = prob
+        e.slab = slab
+        e.beta, e.js, e.maxerr = prob.beta, prob.js, prob.maxerr
+        e.iterative.maxerr = 1e-12
+        e.iterative.maxit = 50000
+        e.compute(LOOPS)
+        return e
+
+    e = shockley(f"eslab{rank}", qc, dict(rank=rank, nranks=world, own_lo=c_lo, own_hi=c_hi, allgather=allgather_bytes))
+    V_loc = e.outVoltage()
+    heat_loc = e.outHeat()
+    partsV = allgather_bytes((cf.slab_field_owned(qc, V_loc, c_lo, c_hi), e.stats, e.maxcur))
+    assert all(x[1]["err"] == partsV[0][1]["err"] and x[1]["maxval"] == partsV[0][1]["maxval"] for x in partsV)
+    assert all(tuple(x[2]) == tuple(partsV[0][2]) for x in partsV)
+    e.invalidate()
+    if rank == 0:
+        from helpers import oracle_shockley
+        V = np.concatenate([x[0] for x in partsV], axis=0).ravel()
+        one = shockley("esingle", pc, None, 0)
+        V1 = one.outVoltage()
+        oe = oracle_shockley(pc, algorithm="cholesky")
+        oe.compute(LOOPS)
+        d1 = float(np.abs(V - V1).max())
+        d2 = float(np.abs(V - oe.potential).max())
+        st = partsV[0][1]
+        print(f"slab x{world} Shockley: {LOOPS} loops, err {st['err']:.6g}% (single {one.stats['err']:.6g}%, oracle {oe.history[-1]['err']:.6g}%), "
+              f"max|V_slab - V_single| = {d1:.3e} V, max|V_slab - V_cholesky| = {d2:.3e} V")
+        assert d1 <= 1e-9 and d2 <= 1e-6
+        assert abs(st["err"] - one.stats["err"]) <= 1e-6 * max(1., abs(one.stats["err"]))
+        assert abs(st["maxval"] - one.stats["maxval"]) <= 1e-9 * abs(one.stats["maxval"])
+        assert np.allclose(partsV[0][2], one.maxcur, rtol=1e-7, atol=1e-12)
         one.invalidate()
     dist.barrier()
     dist.destroy_process_group()

@@ -1,0 +1,104 @@
+"""ThermoElectric3D meta loop (solvers/meta/shockley/thermoelectric.py:207-211) with the device-resident field
+exchange against the two coupled oracles.  Tolerances: 1e-3 K, 1e-6 V (north star); the
+interpolated element temperatures are checked bit-exactly through the conductivities they select."""
+import numpy as np
+import pytest
+
+from helpers import oracle_shockley, oracle_thermal
+from oracle import oracle as orc
+from plask_b200 import _lib as L
+from plask_b200 import configs as cf
+from plask_b200.fem import DeviceFem
+from plask_b200.solvers import ThermoElectric3D
+
+pytestmark = pytest.mark.gpu
+
+
+def make_pair(nt, ne, order_t="optimal", order_e="optimal"):
+    pt = cf.config_B(nt, order=order_t)
+    pt.heat = None
+    pe = cf.config_C(ne, order=order_e)
+    return pt, pe
+
+
+def run_both(pt, pe, meta_loops, tfreq):
+    te = ThermoElectric3D("te")
+    te.thermal.problem, te.electrical.problem = pt, pe
+    te.tfreq = tfreq
+    for s in (te.thermal, te.electrical):
+        s.iterative.maxerr, s.iterative.maxit = 1e-12, 100000
+    te.electrical.beta, te.electrical.js, te.electrical.maxerr = pe.beta, pe.js, pe.maxerr
+    te.thermal.maxerr = pt.maxerr
+    n = te.compute(max_meta_loops=meta_loops)
+    ot = oracle_thermal(pt, algorithm="cholesky")
+    oe = oracle_shockley(pe, algorithm="cholesky")
+    o = orc.ThermoElectric3DOracle(ot, oe, tfreq=tfreq)
+    no = o.compute(max_meta_loops=meta_loops)
+    return te, o, n, no
+
+
+@pytest.mark.parametrize("order", ["optimal", "012", "120"])
+def test_same_mesh_meta_loop_vs_oracles(order):
+    pt, pe = make_pair((20, 22, 52), (20, 22, 52), order, order)
+    te, o, n, no = run_both(pt, pe, 3, 4)
+    assert n == no == 3
+    T, V = te.thermal.outTemperature(), te.electrical.outVoltage()
+    assert np.abs(T - o.thermal.temperatures).max() <= 1e-3, np.abs(T - o.thermal.temperatures).max()
+    assert np.abs(V - o.electrical.potential).max() <= 1e-6
+    assert te.thermal.maxT == pytest.approx(o.thermal.maxT, abs=1e-3)
+    assert te.thermal.maxT > 300.5                      # the Joule heat really arrived in the thermal solver
+    assert te.get_total_current() == pytest.approx(o.electrical.get_total_current(), rel=1e-6)
+    for h, g in zip(te.history, o.history):
+        assert h["terr"] == pytest.approx(g["terr"], abs=1e-3)
+        assert h["verr"] == pytest.approx(g["verr"], rel=1e-3, abs=1e-6)
+    te.invalidate()
+
+
+def test_different_meshes_meta_loop_vs_oracles():
+    """thermal and electrical solvers on different meshes (thermoelectric.py:132-138): both exchanges interpolate"""
+    pt, pe = make_pair((16, 18, 44), (20, 22, 52))
+    te, o, n, no = run_both(pt, pe, 2, 3)
+    assert n == no == 2
+    T, V = te.thermal.outTemperature(), te.electrical.outVoltage()
+    assert np.abs(T - o.thermal.temperatures).max() <= 1e-3
+    assert np.abs(V - o.electrical.potential).max() <= 1e-6
+    te.invalidate()
+
+
+@pytest.mark.parametrize("nt,ne", [((9, 8, 11), (9, 8, 11)), ((9, 8, 11), (7, 12, 10)), ((6, 5, 7), (13, 12, 15))])
+def test_temperature_exchange_bit_exact(nt, ne):
+    """T_elem = interpolateLinear(T) at the element midpoints selects exactly the oracle's conductivities"""
+    rng = np.random.default_rng(20261017)
+    pt, pe = make_pair(nt, ne, "102", "021")
+    T = 300. + 60. * rng.random(pt.N)
+    ft, fe = DeviceFem(0), DeviceFem(0)
+    ft.set_mesh(pt.axes, pt.strides)
+    ft.set_field(T)
+    fe.set_mesh(pe.axes, pe.strides)
+    fe.set_materials(pe.elem_mat, pe.T0, pe.dT, pe.tab_lat, pe.tab_vert)
+    fe.take_temperature_from(ft)
+    fe.update_conductivity_shockley()
+    cond = fe.get_elem(L.ELEM_COND)
+    mt, me = orc.Mesh(*pt.axes, pt.order), orc.Mesh(*pe.axes, pe.order)
+    Te = orc.interp_linear(mt.axes, mt.ns, T, [orc.midpoints(a) for a in me.axes], me.es, me.E)
+    oe = oracle_shockley(pe, algorithm="cholesky")
+    oe.elem_junc[:] = 0
+    oe.Te = Te
+    oe.load_conductivity()
+    assert np.array_equal(cond, oe.conds)
+    if nt == ne:   # same mesh: the midpoint value is the mean of the 8 corners up to rounding
+        ng = np.broadcast_to(pt.node_index_grid(), pt.n)
+        T3 = T[ng]
+        mean8 = sum(T3[a:pt.n[0] - 1 + a, b:pt.n[1] - 1 + b, c:pt.n[2] - 1 + c] for a in (0, 1) for b in (0, 1) for c in (0, 1)) / 8
+        assert np.abs(Te[np.broadcast_to(pe.elem_index_grid(), mean8.shape)] - mean8).max() <= 1e-11
+    ft.close(); fe.close()
+
+
+def test_heat_without_electrical_solution_is_an_error():
+    pt, pe = make_pair((8, 8, 12), (8, 8, 12))
+    te = ThermoElectric3D("te")
+    te.thermal.problem, te.electrical.problem = pt, pe
+    te.initialize()
+    with pytest.raises(L.BadInput):
+        te.thermal.compute(1)      # NoValue("heat density") in the reference (electr3d.cpp:539)
+    te.invalidate()

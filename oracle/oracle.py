@@ -313,6 +313,11 @@ class Static3DOracle:
         return toterr
 
     def heat_fluxes(self):
+        """saveHeatFluxes, therm3d.cpp:342-384: thermk is re-evaluated at the CURRENT temperatures (:362-370)."""
+        t = self.tables
+        lib().orc_thermal_conds(self.mesh.ref, _p(self.temperatures), _p(self.elem_mat, C.c_uint32),
+                                C.c_uint32(t.nT), C.c_double(t.T0), C.c_double(t.dT), _p(t.lat), _p(t.vert),
+                                _p(self.conds))
         flux = np.zeros((self.mesh.E, 3))
         lib().orc_heat_flux(self.mesh.ref, _p(self.temperatures), _p(self.conds), _p(flux))
         return flux

@@ -74,10 +74,6 @@ def test_random_problem_linear_solve_and_flux():
     T = s.outTemperature()
     assert np.abs(T - o.temperatures).max() <= 1e-6
     # heat flux provider (therm3d.cpp:342-384): conds re-evaluated at the final temperatures
-    lib, C = orc.lib(), orc.C
-    t = o.tables
-    lib.orc_thermal_conds(o.mesh.ref, orc._p(o.temperatures), orc._p(o.elem_mat, C.c_uint32), C.c_uint32(t.nT),
-                          C.c_double(t.T0), C.c_double(t.dT), orc._p(t.lat), orc._p(t.vert), orc._p(o.conds))
     flux_ref = o.heat_fluxes()
     flux = s.outHeatFlux()
     assert np.abs(flux - flux_ref).max() <= 1e-6 * np.abs(flux_ref).max()

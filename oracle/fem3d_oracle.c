@@ -331,6 +331,95 @@ void orc_apply_bc_dpb(size_t rank, size_t kd, size_t ld, double* AB, double* B, 
     }
 }
 
+/* ---------------- a7: boundary conditions of the 2nd / 3rd kind, radiation ---- */
+
+/* setBoundaries (therm3d.cpp:140-168) and its three uses in setMatrix (:242-268), element by
+ * element.  The per-node optional values (`boundary_conditions.getValue(idx[i])`,
+ * plask/mesh/boundary_conditions.hpp:182-186: FIRST matching condition wins) are given as
+ * flag + value arrays of length N.  A side of an element carries the condition when all 4 of its
+ * nodes have a value (:153).
+ *
+ * quirk != 0 — VERBATIM: the reference accumulates into the LOCAL slots `F[i]`, `K[i][j]` with
+ *   i,j in 0..3 (:157-162), i.e. always into the element's z-low nodes idx[0..3] whatever the
+ *   side, decides "edge" from the slot numbers (:159-160), and the radiation lambda reads
+ *   `temperatures[i]` with the local node number i = wall[i] in 0..7 (:265).  For the side
+ *   {0,1,2,3} (z-low face of the element) slots and wall nodes coincide.
+ * quirk == 0 — CORRECTED: F[wall[i]], K[wall[i]][wall[j]], edge from wall[i]^wall[j],
+ *   temperatures[idx[wall[i]]].  The CUDA library takes a flattened face-term list built by the
+ *   host in either mode.
+ *
+ * Output: B additions are applied to B directly; matrix additions A(rows[k], cols[k]) += vals[k]
+ * (symmetric storage, one triplet per local (i,j), j <= i) are appended up to `cap`.  Returns the
+ * number of triplets produced (call again with a larger cap if it exceeds it). */
+size_t orc_boundary_terms(const orc_mesh* m, const double* T, const uint8_t* has_flux, const double* flux,
+                          const uint8_t* has_conv, const double* conv_coeff, const double* conv_amb,
+                          const uint8_t* has_rad, const double* rad_emis, const double* rad_amb, int quirk,
+                          size_t cap, size_t* rows, size_t* cols, double* vals, double* B) {
+    static const int walls[6][4] = {{0, 1, 2, 3}, {4, 5, 6, 7}, {0, 2, 4, 6}, {1, 3, 5, 7}, {0, 1, 4, 5}, {2, 3, 6, 7}};
+    const double SB = 5.670373e-8; /* plask/phys/constants.hpp:41 */
+    size_t E = orc_mesh_elements(m), nt = 0;
+    for (size_t e = 0; e < E; ++e) {
+        size_t ix[3], idx[8];
+        elem_indices(m, e, ix);
+        elem_nodes(m, ix, idx);
+        double dx = m->ax[0][ix[0] + 1] - m->ax[0][ix[0]];
+        double dy = m->ax[1][ix[1] + 1] - m->ax[1][ix[1]];
+        double dz = m->ax[2][ix[2] + 1] - m->ax[2][ix[2]];
+        const double areas[3] = {dx * dy, dy * dz, dz * dx};
+        double F[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        double K[8][8];
+        memset(K, 0, sizeof K);
+        for (int kind = 0; kind < 3; ++kind) { /* heat flux, convection, radiation — the order of :242-268 */
+            const uint8_t* has = kind == 0 ? has_flux : kind == 1 ? has_conv : has_rad;
+            if (!has) continue;
+            for (int side = 0; side < 6; ++side) {
+                const int* wall = walls[side];
+                if (!(has[idx[wall[0]]] && has[idx[wall[1]]] && has[idx[wall[2]]] && has[idx[wall[3]]])) continue;
+                double area = areas[side / 2];
+                for (int i = 0; i < 4; ++i) {
+                    size_t ni = idx[wall[i]];
+                    int si = quirk ? i : wall[i]; /* slot that receives the term */
+                    double fv;
+                    if (kind == 0) fv = -0.25e-12 * area * flux[ni];
+                    else if (kind == 1) fv = 0.25e-12 * area * conv_coeff[ni] * conv_amb[ni];
+                    else {
+                        double a = rad_amb[ni]; a = a * a;
+                        double t = quirk ? T[wall[i]] : T[ni]; t = t * t;
+                        fv = -0.25e-12 * area * rad_emis[ni] * SB * (t * t - a * a);
+                    }
+                    F[si] += fv;
+                    if (kind != 1) continue;
+                    for (int j = 0; j <= i; ++j) {
+                        int sj = quirk ? j : wall[j];
+                        int ij = quirk ? (i ^ j) : (wall[i] ^ wall[j]);
+                        int edge = (ij == 1 || ij == 2 || ij == 4);
+                        double v = 0.125e-12 * area * (conv_coeff[ni] + conv_coeff[idx[wall[j]]]);
+                        v = v / (wall[j] == wall[i] ? 9. : edge ? 18. : 36.);
+                        if (si >= sj) K[si][sj] += v; else K[sj][si] += v;
+                    }
+                }
+            }
+        }
+        for (int i = 0; i < 8; ++i) {
+            for (int j = 0; j <= i; ++j)
+                if (K[i][j] != 0.) {
+                    if (nt < cap) { rows[nt] = idx[i]; cols[nt] = idx[j]; vals[nt] = K[i][j]; }
+                    ++nt;
+                }
+            B[idx[i]] += F[i];
+        }
+    }
+    return nt;
+}
+
+void orc_add_coo_sparse14(size_t rank, const int icords[14], double* data, size_t nt, const size_t* rows,
+                          const size_t* cols, const double* vals) {
+    for (size_t k = 0; k < nt; ++k) *sparse14_at(data, rank, icords, rows[k], cols[k]) += vals[k];
+}
+void orc_add_coo_dpb(size_t ld, double* AB, size_t nt, const size_t* rows, const size_t* cols, const double* vals) {
+    for (size_t k = 0; k < nt; ++k) *dpb_at(AB, ld, rows[k], cols[k]) += vals[k];
+}
+
 /* ------------------------------------ a11: thermal outer-loop reductions --- */
 
 /* therm3d.cpp:318-325: err = max|T - T_prev|, maxT = max T (maxT starts at 0). */

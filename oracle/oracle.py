@@ -168,6 +168,10 @@ class Sparse14:
                                          _p(self.data), _p(B))
         assert rc == 0
 
+    def add_coo(self, rows, cols, vals):
+        lib().orc_add_coo_sparse14(c_sz(self.mesh.N), _p(self.mesh.icords, C.c_int), _p(self.data), c_sz(len(vals)),
+                                   _p(rows, c_sz), _p(cols, c_sz), _p(vals))
+
     def apply_bc(self, B, nodes, values):
         lib().orc_apply_bc_sparse14(c_sz(self.mesh.N), _p(self.mesh.icords, C.c_int), _p(self.data), _p(B),
                                     c_sz(len(nodes)), _p(nodes, c_sz), _p(values))
@@ -224,6 +228,9 @@ class Dpb:
         lib().orc_assemble_dpb(self.mesh.ref, _p(cond), _p(heat) if heat is not None else None, c_sz(self.ld),
                                _p(self.data), _p(B))
 
+    def add_coo(self, rows, cols, vals):
+        lib().orc_add_coo_dpb(c_sz(self.ld), _p(self.data), c_sz(len(vals)), _p(rows, c_sz), _p(cols, c_sz), _p(vals))
+
     def apply_bc(self, B, nodes, values):
         lib().orc_apply_bc_dpb(c_sz(self.mesh.N), c_sz(self.kd), c_sz(self.ld), _p(self.data), _p(B),
                                c_sz(len(nodes)), _p(nodes, c_sz), _p(values))
@@ -245,12 +252,57 @@ class Dpb:
 # ------------------------------------------------------------------------- Static3D
 
 
+class BoundaryTerms:
+    """heatflux_boundary / convection_boundary / radiation_boundary of ThermalFem3DSolver (therm3d.hpp:79-82) as the
+    per-node optional values `BoundaryConditions::getValue` yields (first matching condition wins,
+    plask/mesh/boundary_conditions.hpp:182-186).  Each list holds (nodes, value...) tuples in definition order:
+    heatflux (nodes, q [W/m2]); convection (nodes, coeff [W/m2/K], ambient [K]); radiation (nodes, emissivity, ambient)."""
+
+    def __init__(self, N, heatflux=(), convection=(), radiation=()):
+        def dense(conds, nval):
+            if not conds:
+                return None, [np.zeros(1)] * nval
+            has = np.zeros(N, dtype=np.uint8)
+            vals = [np.zeros(N) for _ in range(nval)]
+            for cond in conds:
+                nodes = np.asarray(cond[0], dtype=np.int64)
+                new = nodes[has[nodes] == 0]
+                for k in range(nval):
+                    vals[k][new] = cond[1 + k]
+                has[new] = 1
+            return has, vals
+        self.has_flux, (self.flux,) = dense(list(heatflux), 1)
+        self.has_conv, (self.coeff, self.camb) = dense(list(convection), 2)
+        self.has_rad, (self.emis, self.ramb) = dense(list(radiation), 2)
+
+    def terms(self, mesh, T, B, quirk):
+        """setBoundaries for every element (therm3d.cpp:140-168,242-268): adds the load terms to B, returns COO triplets."""
+        def pu(a):
+            return _p(a, C.c_uint8) if a is not None else None
+        cap = 1 << 16
+        while True:
+            rows, cols, vals = np.zeros(cap, dtype=np.uintp), np.zeros(cap, dtype=np.uintp), np.zeros(cap)
+            B0 = B.copy()
+            lib().orc_boundary_terms.restype = c_sz
+            nt = lib().orc_boundary_terms(mesh.ref, _p(np.ascontiguousarray(T)), pu(self.has_flux), _p(self.flux),
+                                          pu(self.has_conv), _p(self.coeff), _p(self.camb), pu(self.has_rad),
+                                          _p(self.emis), _p(self.ramb), C.c_int(1 if quirk else 0), c_sz(cap),
+                                          _p(rows, c_sz), _p(cols, c_sz), _p(vals), _p(B0))
+            if nt <= cap:
+                B[:] = B0
+                return rows[:nt].copy(), cols[:nt].copy(), vals[:nt].copy()
+            cap = int(nt)
+
+
 class Static3DOracle:
     """ThermalFem3DSolver restated (solvers/thermal/static/therm3d.cpp)."""
 
     def __init__(self, mesh, elem_mat, tables, dirichlet_nodes, dirichlet_values, heat=None, inittemp=300.,
-                 maxerr=0.05, algorithm="cholesky", precond="ic", itmaxerr=1e-6, maxit=1000, nfact=10):
+                 maxerr=0.05, algorithm="cholesky", precond="ic", itmaxerr=1e-6, maxit=1000, nfact=10,
+                 boundaries=None, quirk=True):
         self.mesh = mesh
+        self.boundaries = boundaries   # BoundaryTerms or None (heat flux / convection / radiation, therm3d.cpp:242-268)
+        self.quirk = quirk             # True: verbatim local-slot accumulation of setBoundaries (therm3d.cpp:157-162)
         self.elem_mat = np.ascontiguousarray(elem_mat, dtype=np.uint32)
         self.tables = tables
         self.bc_nodes = np.ascontiguousarray(dirichlet_nodes, dtype=np.uintp)
@@ -278,6 +330,9 @@ class Static3DOracle:
                                 C.c_uint32(t.nT), C.c_double(t.T0), C.c_double(t.dT), _p(t.lat), _p(t.vert),
                                 _p(self.conds))
         A.assemble(self.conds, self.heat if self.heat is not None else np.zeros(self.mesh.E), B)
+        if self.boundaries is not None:
+            rows, cols, vals = self.boundaries.terms(self.mesh, self.temperatures, B, self.quirk)
+            A.add_coo(rows, cols, vals)
         A.apply_bc(B, self.bc_nodes, self.bc_values)
 
     def compute(self, loops=0):

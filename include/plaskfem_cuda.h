@@ -88,6 +88,29 @@ int pfem_set_dirichlet(pfem_ctx* ctx, size_t nd, const size_t* node, const doubl
  * NULL = zero load vector (electrical, electr3d.cpp:278). */
 int pfem_set_source(pfem_ctx* ctx, const double* heat_per_elem);
 
+/* Boundary conditions of the 2nd kind (heat flux), 3rd kind (convection) and radiation of ThermalFem3DSolver
+ * (heatflux_boundary, convection_boundary, radiation_boundary: therm3d.hpp:79-82; setBoundaries therm3d.cpp:140-168,
+ * applied in setMatrix :242-268).  Each kind is given as the per-node optional value that
+ * BoundaryConditionsWithMesh::getValue(node) yields (first matching condition wins,
+ * plask/mesh/boundary_conditions.hpp:182-186): has_*[N] flags (NULL = no condition of that kind) and value arrays
+ * of length N in the node order of the mesh.  A side of an element carries a condition when all four of its nodes
+ * have a value (:153).  Heat flux and radiation change the load vector only (radiation is re-evaluated from the
+ * temperatures every nonlinear loop, :262-267), convection also adds a face mass matrix, applied matrix-free.
+ * verbatim != 0 reproduces setBoundaries to the letter: it accumulates into the LOCAL slots F[i], K[i][j], i,j in 0..3
+ * (:157-162), i.e. always into the element's four z-low nodes whatever the side, and radiation reads
+ * temperatures[0..7] (:265), and it keeps the convection matrix as written (:255: 0.125e-12, a QUARTER of the
+ * consistent face mass matrix, so that the solution relaxes towards 4*ambient).  verbatim == 0 is the corrected
+ * form: terms go to the nodes of the wall, radiation reads the wall node, consistent face mass matrix.
+ * b == NULL (or no flags) removes all boundary terms. */
+typedef struct {
+    const uint8_t* has_flux;  const double* flux;                                     /* W/m^2            */
+    const uint8_t* has_conv;  const double* conv_coeff;     const double* conv_ambient; /* W/(m^2 K), K    */
+    const uint8_t* has_rad;   const double* rad_emissivity; const double* rad_ambient;  /* -, K            */
+    int verbatim;
+    int reserved[3];
+} pfem_boundary;
+int pfem_set_boundary(pfem_ctx* ctx, const pfem_boundary* b);
+
 /* Unknown field (temperatures [K] / potential [V]): initial guess and warm start
  * (therm3d.cpp:79, electr3d.cpp:190; iterative_matrix.hpp:205-209). */
 int pfem_set_field(pfem_ctx* ctx, const double* x0);

@@ -20,9 +20,11 @@
 #ifndef PLASKFEM_CUDA_HPP
 #define PLASKFEM_CUDA_HPP
 
+#include <array>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <functional>
 #include <limits>
 #include <map>
@@ -150,6 +152,29 @@ struct Dirichlet {
     void add(const NodeRange& place, double v) { for (size_t r : place) { node.push_back(r); value.push_back(v); } }
 };
 
+// ---- row a7: boundary conditions of the 2nd / 3rd kind and radiation ----------------------------------
+//
+// heatflux_boundary / convection_boundary / radiation_boundary (therm3d.hpp:79-82) in the form setBoundaries reads
+// them (therm3d.cpp:149): boundary_conditions.getValue(node), i.e. the value of the FIRST condition whose place
+// contains the node (plask/mesh/boundary_conditions.hpp:182-186).  NV = number of scalars of the condition:
+// 1 heat flux, 2 Convection {coeff, ambient} / Radiation {emissivity, ambient} (therm3d.hpp:28-57).
+template <int NV>
+struct NodeConditions {
+    std::vector<uint8_t> has;
+    std::vector<double> v[NV];
+    bool empty() const { return has.empty(); }
+    template <typename NodeRange>
+    void add(size_t mesh_size, const NodeRange& place, const std::array<double, NV>& value) {
+        if (has.empty()) { has.assign(mesh_size, 0); for (auto& a : v) a.assign(mesh_size, 0.); }
+        for (size_t r : place) {
+            if (r >= mesh_size) throw BadInput("boundary condition names a node outside the mesh");
+            if (has[r]) continue;   // an earlier condition already covers the node
+            has[r] = 1;
+            for (int k = 0; k < NV; ++k) v[k][r] = value[k];
+        }
+    }
+};
+
 // ---- junctions (electr3d.hpp:28-78, electr3d.cpp:89-183) ---------------------------------------------
 
 // junction_number(i0, i1, i2) -> 0 (not active) or k+1.  Throws like the reference when a junction does not
@@ -263,6 +288,18 @@ class Context {
         check(pfem_set_materials(ctx_, ids.data(), t.nmat, t.T0, t.dT, t.nT, t.lat.data(), t.vert.data()));
     }
     void set_dirichlet(const Dirichlet& bc) { check(pfem_set_dirichlet(ctx_, bc.node.size(), bc.node.data(), bc.value.data())); }
+    // verbatim = true reproduces setBoundaries to the letter (local slots, quarter mass matrix; plaskfem_cuda.h)
+    void set_boundary(const NodeConditions<1>& heatflux, const NodeConditions<2>& convection, const NodeConditions<2>& radiation,
+                      bool verbatim = true) {
+        if (heatflux.empty() && convection.empty() && radiation.empty()) { check(pfem_set_boundary(ctx_, nullptr)); return; }
+        pfem_boundary b;
+        memset(&b, 0, sizeof b);
+        if (!heatflux.empty()) { b.has_flux = heatflux.has.data(); b.flux = heatflux.v[0].data(); }
+        if (!convection.empty()) { b.has_conv = convection.has.data(); b.conv_coeff = convection.v[0].data(); b.conv_ambient = convection.v[1].data(); }
+        if (!radiation.empty()) { b.has_rad = radiation.has.data(); b.rad_emissivity = radiation.v[0].data(); b.rad_ambient = radiation.v[1].data(); }
+        b.verbatim = verbatim ? 1 : 0;
+        check(pfem_set_boundary(ctx_, &b));
+    }
     void set_source(const double* heat_per_elem) { check(pfem_set_source(ctx_, heat_per_elem)); }
     void set_field(const double* x0) { check(pfem_set_field(ctx_, x0)); }
     void fill_field(double v) { check(pfem_fill_field(ctx_, v)); }

@@ -345,7 +345,7 @@ void orc_apply_bc_dpb(size_t rank, size_t kd, size_t ld, double* AB, double* B, 
  *   `temperatures[i]` with the local node number i = wall[i] in 0..7 (:265).  For the side
  *   {0,1,2,3} (z-low face of the element) slots and wall nodes coincide.
  * quirk == 0 — CORRECTED: F[wall[i]], K[wall[i]][wall[j]], edge from wall[i]^wall[j],
- *   temperatures[idx[wall[i]]].  The CUDA library takes a flattened face-term list built by the
+ *   temperatures[idx[wall[i]]], and the convection matrix scaled to the consistent face mass matrix (see below).  The CUDA library takes a flattened face-term list built by the
  *   host in either mode.
  *
  * Output: B additions are applied to B directly; matrix additions A(rows[k], cols[k]) += vals[k]
@@ -393,7 +393,10 @@ size_t orc_boundary_terms(const orc_mesh* m, const double* T, const uint8_t* has
                         int sj = quirk ? j : wall[j];
                         int ij = quirk ? (i ^ j) : (wall[i] ^ wall[j]);
                         int edge = (ij == 1 || ij == 2 || ij == 4);
-                        double v = 0.125e-12 * area * (conv_coeff[ni] + conv_coeff[idx[wall[j]]]);
+                        /* :255 has 0.125e-12: with the /9,/18,/36 weights that is a QUARTER of the consistent face
+                         * mass matrix (rows sum to A c/16 while the load is A c Ta/4), so the verbatim form relaxes
+                         * towards 4 Ta; the corrected form uses the consistent matrix (rows sum to A c/4). */
+                        double v = (quirk ? 0.125e-12 : 0.5e-12) * area * (conv_coeff[ni] + conv_coeff[idx[wall[j]]]);
                         v = v / (wall[j] == wall[i] ? 9. : edge ? 18. : 36.);
                         if (si >= sj) K[si][sj] += v; else K[sj][si] += v;
                     }

@@ -30,6 +30,13 @@ class Junction(C.Structure):
                 ("ld", c_sz), ("offset", C.c_ssize_t), ("height", C.c_double)]
 
 
+class Boundary(C.Structure):
+    _fields_ = [("has_flux", C.POINTER(C.c_uint8)), ("flux", c_dp),
+                ("has_conv", C.POINTER(C.c_uint8)), ("conv_coeff", c_dp), ("conv_ambient", c_dp),
+                ("has_rad", C.POINTER(C.c_uint8)), ("rad_emissivity", c_dp), ("rad_ambient", c_dp),
+                ("verbatim", C.c_int), ("reserved", C.c_int * 3)]
+
+
 class Opts(C.Structure):
     _fields_ = [("maxit", C.c_int), ("lin_tol", C.c_double), ("precond", C.c_int), ("outer_tol", C.c_double),
                 ("loops", C.c_int), ("batch", C.c_int), ("variant", C.c_int), ("reserved", C.c_int * 5)]
@@ -65,6 +72,7 @@ SYMBOLS = {
     "pfem_set_materials": (C.c_int, [_vp, _u32p, C.c_uint32, C.c_double, C.c_double, C.c_uint32, c_dp, c_dp]),
     "pfem_set_dirichlet": (C.c_int, [_vp, c_sz, _szp, c_dp]),
     "pfem_set_source": (C.c_int, [_vp, c_dp]),
+    "pfem_set_boundary": (C.c_int, [_vp, C.POINTER(Boundary)]),
     "pfem_set_field": (C.c_int, [_vp, c_dp]),
     "pfem_fill_field": (C.c_int, [_vp, C.c_double]),
     "pfem_set_elem_temperature": (C.c_int, [_vp, c_dp, C.c_double]),

@@ -408,6 +408,22 @@ def slab_problem(p, rank, nranks):
     return q, own_lo, own_hi, (lo, hi)
 
 
+def slab_local_nodes(p, q, lo, hi, nodes):
+    """Global node numbers of `p` -> (node numbers in the local problem `q` holding planes [lo, hi) of the major axis,
+    mask of the entries that lie inside) — for Dirichlet lists and the boundary conditions of the 2nd / 3rd kind."""
+    major = ORDERS[p.order][0]
+    ns = p.strides
+    order3 = sorted(range(3), key=lambda a: -ns[a])            # major, medium, minor
+    rem = np.asarray(nodes, dtype=np.int64)
+    c = [None] * 3
+    for a in order3:
+        c[a], rem = np.divmod(rem, ns[a])
+    keep = (c[major] >= lo) & (c[major] < hi)
+    c[major] = c[major] - lo
+    qs = q.strides
+    return (c[0][keep] * qs[0] + c[1][keep] * qs[1] + c[2][keep] * qs[2]).astype(np.int64), keep
+
+
 def slab_field_owned(q, field, own_lo, own_hi):
     """Owned part of a local node field as an array shaped (owned planes, medium, minor)."""
     major, medium, minor = ORDERS[q.order]

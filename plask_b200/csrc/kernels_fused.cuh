@@ -403,6 +403,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
             const double pq = red[0], rho = red[1], qz = red[2], qdq = red[3], rr = red[4], zz = red[5], xx = red[6];
             const double rho_old = sc->rho;
             sc->rho_prev = rho_old; sc->rho = rho; sc->pq = pq; sc->rr = rr; sc->zz = zz; sc->xx = xx;
+            const int surf = sc->surf;   // boundary-face matrix terms: k_surf_iter adds S p' to q' and takes over from here
             const int launch = sc->launch + 1;
             sc->launch = launch;
             const int it = sc->bench ? launch : launch - 1;   // launch m has applied m-1 updates to x
@@ -413,9 +414,10 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
                 else if (!(rr == rr) || !(pq == pq)) { sc->done = 1; sc->status = -2; stop = true; }
                 else if (rr <= sc->tol2 * sc->bb && rho <= sc->tol2 * sc->bz && zz <= sc->tol2 * xx) { sc->done = 1; sc->status = 1; stop = true; }
                 else if (it >= sc->maxit) { sc->done = 1; sc->status = 2; stop = true; }
-                else if (!(pq > 0.)) { sc->done = 1; sc->status = -1; stop = true; }
+                else if (!surf && !(pq > 0.)) { sc->done = 1; sc->status = -1; stop = true; }
             }
-            if (!stop) {
+            if (surf) { sc->qz = qz; sc->qdq = qdq; }
+            else if (!stop) {
                 const double al = (pq > 0.) ? rho / pq : 0.;
                 const double rho_next = fma(al * al, qdq, fma(-2. * al, qz, rho));
                 sc->alpha = al;

@@ -80,9 +80,27 @@ struct Scalars {
     int bench;        // 1: ignore breakdown / convergence
     int neg_diag;     // a free row has a negative diagonal (NSPCG ier = -4)
     int launch;       // fused kernel: launches since the start of the solve (launch m has applied m-1 updates)
-    int pad_;
+    int surf;         // 1: boundary-face matrix terms exist (convection); k_surf_iter completes q and finalises alpha/beta
     unsigned int ticket[8];
     Comm* comm;       // null unless the context is one slab of a multi-GPU solve
+    double qz, qdq;   // q.z and q.D^-1 q of the stiffness part, handed from k_fpcg to k_surf_iter when surf != 0
+};
+
+// Boundary-face terms (conditions of the 2nd / 3rd kind and radiation, therm3d.cpp:140-168,242-268) flattened by the
+// host into rows = mesh nodes that receive a load term or carry matrix entries.  All indices are lattice indices.
+struct Surf {
+    int nrows;                 // 0: no boundary terms
+    int nnz;                   // matrix entries (both triangles), 0 unless convection is present
+    const idx_t* node;         // [nrows] ascending
+    const double* lconst;      // [nrows] temperature-independent load: heat flux + convection coeff*ambient
+    const int* radptr;         // [nrows+1] radiation terms of the row
+    const idx_t* rad_src;      // node whose temperature the term reads
+    const double* rad_coef;    // 0.25e-12 * area * emissivity * sigma_SB
+    const double* rad_amb4;    // ambient^4
+    double* radv;              // [nrows] radiation load evaluated at the start of the current loop
+    const int* kptr;           // [nrows+1] CSR of the matrix terms
+    const idx_t* kcol;
+    const double* kval;
 };
 
 // ------------------------------------------------------------------ reductions ----------

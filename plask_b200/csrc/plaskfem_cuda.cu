@@ -17,6 +17,7 @@
 #include "kernels_tiled.cuh"
 #include "kernels_tma.cuh"
 #include "kernels_fused.cuh"
+#include "kernels_surface.cuh"
 
 using namespace pfem;
 
@@ -69,7 +70,12 @@ struct pfem_ctx {
     size_t stage_bytes = 0;
     // cached CUDA graph of `graph_batch` PCG iterations
     cudaGraphExec_t graph = nullptr;
-    int graph_batch = 0, graph_variant = -1, graph_precond = -1;
+    int graph_batch = 0, graph_variant = -1, graph_precond = -1, graph_surf = -1;
+    // boundary-face terms (2nd / 3rd kind, radiation): flattened rows on the device, effective load vector
+    Surf surf = {};
+    double* fS = nullptr;
+    int surf_iter = 0;          // 1: k_surf_iter follows k_fpcg (convection terms exist on some rank)
+    bool surf_iter_known = false;
     long long launches = 0;
     double last_relres_pre = 0.;
     int sm_count = 148;
@@ -154,6 +160,7 @@ static void free_all(pfem_ctx* ctx) {
     ctx->act = nullptr; ctx->nact = 0; ctx->ncol = 0;
     ctx->junc_cond = ctx->beta_col = ctx->js_col = nullptr;
     ctx->partials = nullptr; ctx->partial_idx = nullptr; ctx->n_partials = 0;
+    memset(&ctx->surf, 0, sizeof ctx->surf); ctx->fS = nullptr; ctx->surf_iter = 0; ctx->surf_iter_known = false;
     if (ctx->stage) { cudaFree(ctx->stage); ctx->stage = nullptr; ctx->stage_bytes = 0; }
     ctx->have_mesh = ctx->have_materials = ctx->have_junctions = ctx->conds_valid = false;
     ctx->noheat_set = false;
@@ -528,6 +535,202 @@ extern "C" int pfem_set_source(pfem_ctx* ctx, const double* heat) {
     return PFEM_OK;
 }
 
+// ------------------------------------------------ boundary conditions of the 2nd / 3rd kind, radiation (a7) ------
+// setBoundaries (therm3d.cpp:140-168) and its three uses in setMatrix (:242-268), flattened once on the host into the
+// row list `Surf` (kernels_surface.cuh).  The per-node optional values are what
+// BoundaryConditionsWithMesh::getValue yields (first matching condition wins, boundary_conditions.hpp:182-186).
+
+template <typename T>
+static int surf_upload(pfem_ctx* ctx, const T** dst, const std::vector<T>& v) {
+    T* d = nullptr;
+    TRY(dev_alloc(ctx, &d, v.size() ? v.size() : 1, 0));
+    if (!v.empty()) CU(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *dst = d;
+    return PFEM_OK;
+}
+
+static void surf_release(pfem_ctx* ctx) {
+    Surf& s = ctx->surf;
+    dev_release(ctx, const_cast<idx_t**>(&s.node));
+    dev_release(ctx, const_cast<double**>(&s.lconst));
+    dev_release(ctx, const_cast<int**>(&s.radptr));
+    dev_release(ctx, const_cast<idx_t**>(&s.rad_src));
+    dev_release(ctx, const_cast<double**>(&s.rad_coef));
+    dev_release(ctx, const_cast<double**>(&s.rad_amb4));
+    dev_release(ctx, &s.radv);
+    dev_release(ctx, const_cast<int**>(&s.kptr));
+    dev_release(ctx, const_cast<idx_t**>(&s.kcol));
+    dev_release(ctx, const_cast<double**>(&s.kval));
+    memset(&s, 0, sizeof s);
+    ctx->surf_iter = 0; ctx->surf_iter_known = false;
+    if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
+}
+
+extern "C" int pfem_set_boundary(pfem_ctx* ctx, const pfem_boundary* b) {
+    NEED_MESH();
+    const Grid& g = ctx->g;
+    CU(cudaStreamSynchronize(ctx->stream));
+    surf_release(ctx);
+    if (!b || (!b->has_flux && !b->has_conv && !b->has_rad)) return PFEM_OK;
+    if ((b->has_flux && !b->flux) || (b->has_conv && (!b->conv_coeff || !b->conv_ambient)) ||
+        (b->has_rad && (!b->rad_emissivity || !b->rad_ambient)))
+        FAIL(PFEM_ERR_BAD_INPUT, "boundary condition flags without values");
+    if (b->verbatim && b->has_rad && ctx->nranks > 1)
+        FAIL(PFEM_ERR_BAD_INPUT, "slab mode: verbatim radiation reads temperatures[0..7] of the whole mesh (therm3d.cpp:265); use the corrected form");
+    // dense (ABI) and lattice strides of the physical axes; element extents along them
+    idx_t dps[3], cnt[3] = {g.nI, g.nJ, g.nK};
+    for (int a = 0; a < 3; ++a) dps[a] = g.dim_of_phys[a] == 0 ? 1 : g.dim_of_phys[a] == 1 ? (idx_t)g.nI : (idx_t)g.nI * g.nJ;
+    const size_t N = (size_t)g.N;
+    std::vector<uint8_t> mask(N, 0);
+    for (size_t n = 0; n < N; ++n)
+        mask[n] = (uint8_t)((b->has_flux && b->has_flux[n] ? 1 : 0) | (b->has_conv && b->has_conv[n] ? 2 : 0) | (b->has_rad && b->has_rad[n] ? 4 : 0));
+    auto lattice = [&](idx_t r) { const idx_t i = r % g.nI, t = r / g.nI; return i + g.sJ * (t % g.nJ) + g.sK * (t / g.nJ); };
+    struct LoadT { idx_t node; double v; };
+    struct RadT { idx_t node, src; double coef, amb4; };
+    struct KT { idx_t row, col; double v; };
+    std::vector<LoadT> loads;
+    std::vector<RadT> rads;
+    std::vector<KT> kts;
+    static const int walls[6][4] = {{0, 1, 2, 3}, {4, 5, 6, 7}, {0, 2, 4, 6}, {1, 3, 5, 7}, {0, 1, 4, 5}, {2, 3, 6, 7}};
+    const double SB = 5.670373e-8;   // plask/phys/constants.hpp:41
+    const int quirk = b->verbatim ? 1 : 0;
+    for (idx_t ek = 0; ek < cnt[2] - 1; ++ek)
+        for (idx_t ej = 0; ej < cnt[1] - 1; ++ej)
+            for (idx_t ei = 0; ei < cnt[0] - 1; ++ei) {
+                const idx_t n0 = ei + g.nI * (ej + (idx_t)g.nJ * ek);   // dense index of the lowest corner
+                idx_t idx[8];
+                uint8_t any = 0, mk[8];
+                for (int l = 0; l < 8; ++l) {
+                    idx[l] = n0 + ((l & 1) ? dps[0] : 0) + ((l & 2) ? dps[1] : 0) + ((l & 4) ? dps[2] : 0);
+                    mk[l] = mask[idx[l]];
+                    any |= mk[l];
+                }
+                if (!any) continue;
+                const idx_t ix[3] = {ei, ej, ek};
+                double d[3];
+                for (int a = 0; a < 3; ++a) { const idx_t t = ix[g.dim_of_phys[a]]; d[a] = ctx->hax[a][t + 1] - ctx->hax[a][t]; }
+                const double areas[3] = {d[0] * d[1], d[1] * d[2], d[2] * d[0]};
+                double F[8] = {0, 0, 0, 0, 0, 0, 0, 0}, K[8][8];
+                bool anyK = false, anyF = false;
+                memset(K, 0, sizeof K);
+                for (int kind = 0; kind < 3; ++kind) {      // heat flux, convection, radiation: the order of :242-268
+                    const uint8_t bit = (uint8_t)(1 << kind);
+                    for (int side = 0; side < 6; ++side) {
+                        const int* w = walls[side];
+                        if (!(mk[w[0]] & mk[w[1]] & mk[w[2]] & mk[w[3]] & bit)) continue;   // all four nodes carry it, :153
+                        const double area = areas[side / 2];
+                        for (int i = 0; i < 4; ++i) {
+                            const idx_t ni = idx[w[i]];
+                            const int si = quirk ? i : w[i];   // slot that receives the term (:157)
+                            if (kind == 0) { F[si] += -0.25e-12 * area * b->flux[ni]; anyF = true; }
+                            else if (kind == 1) { F[si] += 0.25e-12 * area * b->conv_coeff[ni] * b->conv_ambient[ni]; anyF = true; }
+                            else {
+                                double a = b->rad_ambient[ni]; a = a * a;
+                                // :265 reads temperatures[i] with the LOCAL node number; corrected: the wall node itself
+                                const idx_t src = quirk ? (idx_t)w[i] : ni;
+                                if ((size_t)src >= N) FAIL(PFEM_ERR_BAD_INPUT, "mesh has fewer than 8 nodes");
+                                rads.push_back({lattice(idx[si]), lattice(src), 0.25e-12 * area * b->rad_emissivity[ni] * SB, a * a});
+                            }
+                            if (kind != 1) continue;
+                            for (int j = 0; j <= i; ++j) {
+                                const int sj = quirk ? j : w[j];
+                                const int ij = quirk ? (i ^ j) : (w[i] ^ w[j]);
+                                const bool edge = (ij == 1 || ij == 2 || ij == 4);
+                                // :255 has 0.125e-12, a quarter of the consistent face mass matrix (rows sum to A c/16 against a
+                                // load of A c Ta/4); kept verbatim, the corrected form uses the consistent matrix
+                                double v = (quirk ? 0.125e-12 : 0.5e-12) * area * (b->conv_coeff[ni] + b->conv_coeff[idx[w[j]]]);
+                                v = v / (w[j] == w[i] ? 9. : edge ? 18. : 36.);
+                                if (si >= sj) K[si][sj] += v; else K[sj][si] += v;
+                                anyK = true;
+                            }
+                        }
+                    }
+                }
+                if (anyF)
+                    for (int l = 0; l < 8; ++l)
+                        if (F[l] != 0.) loads.push_back({lattice(idx[l]), F[l]});
+                if (anyK)
+                    for (int i = 0; i < 8; ++i)
+                        for (int j = 0; j <= i; ++j)
+                            if (K[i][j] != 0.) {
+                                const idx_t r = lattice(idx[i]), c = lattice(idx[j]);
+                                kts.push_back({r, c, K[i][j]});
+                                if (r != c) kts.push_back({c, r, K[i][j]});
+                            }
+            }
+    if (loads.empty() && rads.empty() && kts.empty()) return PFEM_OK;
+    std::stable_sort(loads.begin(), loads.end(), [](const LoadT& a, const LoadT& c) { return a.node < c.node; });
+    std::stable_sort(rads.begin(), rads.end(), [](const RadT& a, const RadT& c) { return a.node < c.node; });
+    std::stable_sort(kts.begin(), kts.end(), [](const KT& a, const KT& c) { return a.row != c.row ? a.row < c.row : a.col < c.col; });
+    std::vector<idx_t> rows;
+    rows.reserve(loads.size() + rads.size() + kts.size());
+    for (auto& t : loads) rows.push_back(t.node);
+    for (auto& t : rads) rows.push_back(t.node);
+    for (auto& t : kts) rows.push_back(t.row);
+    std::sort(rows.begin(), rows.end());
+    rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+    const size_t nr = rows.size();
+    if (nr > 0x7fffffffull || kts.size() > 0x7fffffffull || rads.size() > 0x7fffffffull) FAIL(PFEM_ERR_BAD_INPUT, "too many boundary terms");
+    std::vector<double> lconst(nr, 0.), rcoef, ramb, kval;
+    std::vector<int> radptr(nr + 1, 0), kptr(nr + 1, 0);
+    std::vector<idx_t> rsrc, kcol;
+    size_t il = 0, ir = 0, ik = 0;
+    for (size_t r = 0; r < nr; ++r) {
+        const idx_t n = rows[r];
+        for (; il < loads.size() && loads[il].node == n; ++il) lconst[r] += loads[il].v;
+        radptr[r] = (int)rsrc.size();
+        for (; ir < rads.size() && rads[ir].node == n; ++ir) { rsrc.push_back(rads[ir].src); rcoef.push_back(rads[ir].coef); ramb.push_back(rads[ir].amb4); }
+        kptr[r] = (int)kcol.size();
+        for (; ik < kts.size() && kts[ik].row == n; ++ik) {
+            if ((int)kcol.size() > kptr[r] && kcol.back() == kts[ik].col) kval.back() += kts[ik].v;
+            else { kcol.push_back(kts[ik].col); kval.push_back(kts[ik].v); }
+        }
+    }
+    radptr[nr] = (int)rsrc.size();
+    kptr[nr] = (int)kcol.size();
+    Surf& s = ctx->surf;
+    TRY(surf_upload(ctx, &s.node, rows));
+    TRY(surf_upload(ctx, &s.lconst, lconst));
+    TRY(surf_upload(ctx, &s.radptr, radptr));
+    TRY(surf_upload(ctx, &s.rad_src, rsrc));
+    TRY(surf_upload(ctx, &s.rad_coef, rcoef));
+    TRY(surf_upload(ctx, &s.rad_amb4, ramb));
+    TRY(surf_upload(ctx, &s.kptr, kptr));
+    TRY(surf_upload(ctx, &s.kcol, kcol));
+    TRY(surf_upload(ctx, &s.kval, kval));
+    TRY(dev_alloc(ctx, &s.radv, nr, 0));
+    if (!ctx->fS) TRY(dev_alloc(ctx, &ctx->fS, (size_t)g.NP, (size_t)g.G));
+    s.nrows = (int)nr;
+    s.nnz = (int)kcol.size();
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+
+static inline int surf_blocks(const pfem_ctx* ctx) {
+    int b = (ctx->surf.nrows + 255) / 256;
+    const int cap = ctx->sm_count * 4;
+    return b < 1 ? 1 : (b > cap ? cap : b);
+}
+
+// radiation loads from the temperatures the loop starts with (call BEFORE the Dirichlet values are scattered into x)
+static int surf_eval_rad(pfem_ctx* ctx) {
+    if (!ctx->surf.nrows) return PFEM_OK;
+    k_surf_rad<<<surf_blocks(ctx), 256, 0, ctx->stream>>>(ctx->surf, ctx->x);
+    KCHECK(); LAUNCHED(1);
+    return PFEM_OK;
+}
+
+// effective load vector for  M (f - A in):  f + boundary loads - S in  (ctx->f itself without boundary terms)
+static int surf_rhs(pfem_ctx* ctx, const double* in, const double** feff) {
+    *feff = ctx->f;
+    if (!ctx->surf.nrows) return PFEM_OK;
+    CU(cudaMemcpyAsync(ctx->fS, ctx->f, (size_t)ctx->g.NP * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    k_surf_rhs<<<surf_blocks(ctx), 256, 0, ctx->stream>>>(ctx->surf, ctx->f, in, ctx->fS);
+    KCHECK(); LAUNCHED(1);
+    *feff = ctx->fS;
+    return PFEM_OK;
+}
+
 extern "C" int pfem_set_field(pfem_ctx* ctx, const double* x0) {
     NEED_MESH();
     if (!x0) FAIL(PFEM_ERR_BAD_INPUT, "null field");
@@ -690,6 +893,7 @@ extern "C" int pfem_slab_connect(pfem_ctx* ctx, const void* blobs) {
     }
     CU(cudaMemcpy(ctx->d_comm, &hc, sizeof hc, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(&ctx->d_sc->comm, &ctx->d_comm, sizeof(Comm*), cudaMemcpyHostToDevice));
+    ctx->surf_iter_known = false;
     return PFEM_OK;
 }
 
@@ -774,8 +978,8 @@ extern "C" int pfem_set_conductivity(pfem_ctx* ctx, const double* cond) {
 
 // ------------------------------------------------------------------------ PCG -----------
 
-__global__ void k_set_params(Scalars* sc, double tol2, int maxit, int bench) {
-    sc->tol2 = tol2; sc->maxit = maxit; sc->bench = bench; sc->neg_diag = 0;
+__global__ void k_set_params(Scalars* sc, double tol2, int maxit, int bench, int surf) {
+    sc->tol2 = tol2; sc->maxit = maxit; sc->bench = bench; sc->neg_diag = 0; sc->surf = surf;
 }
 __global__ void k_force_running(Scalars* sc) { sc->done = 0; sc->status = 0; }
 
@@ -783,14 +987,18 @@ static int launch_diag(pfem_ctx* ctx) {
     const Grid& g = ctx->g;
     k_diag<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->cl, ctx->cv, ctx->fixed, ctx->dinv, ctx->d_sc);
     KCHECK(); LAUNCHED(1);
+    if (ctx->surf.nnz) {   // convection adds a face mass matrix (therm3d.cpp:253-257)
+        k_surf_diag<<<surf_blocks(ctx), 256, 0, ctx->stream>>>(ctx->surf, ctx->dinv);
+        KCHECK(); LAUNCHED(1);
+    }
     return PFEM_OK;
 }
 
 // out = M (f - A in) [MODE 1/2] or M A in [MODE 3]
 template <int MODE>
-static int launch_apply_simple(pfem_ctx* ctx, const double* in, double* out) {
+static int launch_apply_simple(pfem_ctx* ctx, const double* in, double* out, const double* f = nullptr) {
     const Grid& g = ctx->g;
-    k_apply_simple<MODE><<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->cl, ctx->cv, in, ctx->dinv, ctx->f, out,
+    k_apply_simple<MODE><<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->cl, ctx->cv, in, ctx->dinv, f ? f : ctx->f, out,
                                                                           ctx->d_sc, ctx->partials);
     KCHECK(); LAUNCHED(1);
     return PFEM_OK;
@@ -813,8 +1021,14 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
         double* const pp[2] = {ctx->p, ctx->p2};
         launch_fused_dispatch<true>(ctx->fused, g, parity, rr[1 - parity], qq[1 - parity], pp[1 - parity], ctx->x, ctx->d_sc,
                                     ctx->partials, peer_out(ctx, 1 - parity), ctx->stream);
-        if (ev) { cudaEventRecord(ev[1], ctx->stream); cudaEventRecord(ev[2], ctx->stream); }
-        return 1;
+        if (ev) cudaEventRecord(ev[1], ctx->stream);
+        if (ctx->surf_iter) {   // q' += S p' on the boundary rows, then the alpha / beta step
+            k_surf_iter<<<surf_blocks(ctx), 256, 0, ctx->stream>>>(ctx->surf, g, pp[1 - parity], qq[1 - parity], rr[1 - parity], ctx->dinv,
+                                                                    ctx->d_sc, ctx->partials, peer_out(ctx, 1 - parity));
+            launched = 1;
+        }
+        if (ev) cudaEventRecord(ev[2], ctx->stream);
+        return 1 + launched;
     }
     if (variant == 1) {
         k_pupdate<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->r, ctx->dinv, ctx->p, ctx->d_sc);
@@ -838,10 +1052,11 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
     return launched;
 }
 
-static int kernels_per_iteration(int variant) { return variant == 1 ? 3 : (variant == 3 ? 1 : 2); }  // variants 0 (TMA) and 2 (LDG tiled) fuse the p-update
+static int kernels_per_iteration(const pfem_ctx* ctx, int variant) { return variant == 1 ? 3 : (variant == 3 ? 1 + ctx->surf_iter : 2); }  // variants 0 (TMA) and 2 (LDG tiled) fuse the p-update
 
 static int build_graph(pfem_ctx* ctx, int batch, int variant, int precond) {
-    if (ctx->graph && ctx->graph_batch == batch && ctx->graph_variant == variant && ctx->graph_precond == precond)
+    if (ctx->graph && ctx->graph_batch == batch && ctx->graph_variant == variant && ctx->graph_precond == precond &&
+        ctx->graph_surf == ctx->surf_iter)
         return PFEM_OK;
     if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
     cudaGraph_t graph = nullptr;
@@ -852,7 +1067,7 @@ static int build_graph(pfem_ctx* ctx, int batch, int variant, int precond) {
     e = cudaGraphInstantiate(&ctx->graph, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { ctx->graph = nullptr; FAIL(PFEM_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
-    ctx->graph_batch = batch; ctx->graph_variant = variant; ctx->graph_precond = precond;
+    ctx->graph_batch = batch; ctx->graph_variant = variant; ctx->graph_precond = precond; ctx->graph_surf = ctx->surf_iter;
     return PFEM_OK;
 }
 
@@ -867,17 +1082,28 @@ static int pcg_prepare(pfem_ctx* ctx, const pfem_opts* o, int bench) {
     const Grid& g = ctx->g;
     if (!ctx->conds_valid) FAIL(PFEM_ERR_STATE, "conductivities have not been computed");
     double tol2 = bench ? -1. : o->lin_tol * o->lin_tol;
-    k_set_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, tol2, o->maxit, bench);
+    if (!ctx->surf_iter_known) {             // convection terms on ANY rank: every rank runs k_surf_iter (it is collective)
+        int any = ctx->surf.nnz > 0;
+        if (ctx->nranks > 1) TRY(rank_barrier(ctx, any, &any));
+        ctx->surf_iter = any ? 1 : 0;
+        ctx->surf_iter_known = true;
+    }
+    if (ctx->surf_iter && o->variant != 3) FAIL(PFEM_ERR_BAD_INPUT, "convection boundary terms run with the fused PCG kernel only (variant 3)");
+    k_set_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, tol2, o->maxit, bench, ctx->surf_iter);
     LAUNCHED(1);
     TRY(launch_diag(ctx));
     TRY(halo_sync(ctx, SA_DINV));            // slab mode: the diagonal of a halo plane needs the neighbour's elements
+    TRY(surf_eval_rad(ctx));                 // radiation load from the temperatures of the previous loop (therm3d.cpp:262-267)
     TRY(scatter_bc(ctx, ctx->x, nullptr));   // x_D = v_D (B[r] = val, iterative_matrix.hpp:463-464)
     // ||b_free||^2 with b_free = M (f - A x_D): q <- x_D, p <- b_free (scratch)
     k_dirichlet_only<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->x, ctx->fixed, ctx->q);
     LAUNCHED(1);
-    TRY(launch_apply_simple<2>(ctx, ctx->q, ctx->p));
+    const double* feff = nullptr;
+    TRY(surf_rhs(ctx, ctx->q, &feff));
+    TRY(launch_apply_simple<2>(ctx, ctx->q, ctx->p, feff));
     // r0 = M (f - A x)
-    TRY(launch_apply_simple<1>(ctx, ctx->x, ctx->r));
+    TRY(surf_rhs(ctx, ctx->x, &feff));
+    TRY(launch_apply_simple<1>(ctx, ctx->x, ctx->r, feff));
     TRY(halo_sync(ctx, SA_R));
     CU(cudaMemsetAsync(ctx->p, 0, (size_t)g.NP * sizeof(double), ctx->stream));
     CU(cudaMemsetAsync(ctx->q, 0, (size_t)g.NP * sizeof(double), ctx->stream));   // fused kernel: r' = r - 0*q on the first launch
@@ -902,7 +1128,7 @@ static int pcg_solve(pfem_ctx* ctx, const pfem_opts* o, int* iters, double* relr
     if (neg_diag) FAIL(PFEM_ERR_NOT_SPD, "nonpositive diagonal element in stiffness matrix");
     while (!ctx->h_sc->done) {
         CU(cudaGraphLaunch(ctx->graph, ctx->stream));
-        LAUNCHED((long long)batch * kernels_per_iteration(o->variant));
+        LAUNCHED((long long)batch * kernels_per_iteration(ctx, o->variant));
         TRY(read_scalars(ctx));
     }
     const Scalars& s = *ctx->h_sc;
@@ -1254,6 +1480,10 @@ extern "C" int pfem_apply(pfem_ctx* ctx, const double* p, double* q, int variant
         CU(launch_tma_dispatch<false>(ctx->tma, g, ctx->tma.m_p[0], ctx->dinv, nullptr, ctx->q, nullptr, nullptr, ctx->stream));
         LAUNCHED(1);
     } else FAIL(PFEM_ERR_BAD_INPUT, "unknown kernel variant %d", variant);
+    if (ctx->surf.nnz) {
+        k_surf_add<<<surf_blocks(ctx), 256, 0, ctx->stream>>>(ctx->surf, ctx->dinv, ctx->p, ctx->q);
+        LAUNCHED(1);
+    }
     k_select_fixed<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->fixed, ctx->r, ctx->q, ctx->q);
     KCHECK(); LAUNCHED(1);
     CU(download_nodes(ctx, q, ctx->q));
@@ -1270,7 +1500,10 @@ extern "C" int pfem_get_rhs(pfem_ctx* ctx, double* b) {
     // q <- v_D on Dirichlet nodes, 0 elsewhere; p <- M (f - A q); b = fixed ? v_D : p
     CU(cudaMemsetAsync(ctx->q, 0, (size_t)g.NP * sizeof(double), ctx->stream));
     TRY(scatter_bc(ctx, ctx->q, nullptr));
-    TRY(launch_apply_simple<1>(ctx, ctx->q, ctx->p));
+    const double* feff = nullptr;
+    TRY(surf_eval_rad(ctx));
+    TRY(surf_rhs(ctx, ctx->q, &feff));
+    TRY(launch_apply_simple<1>(ctx, ctx->q, ctx->p, feff));
     k_select_fixed<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->fixed, ctx->q, ctx->p, ctx->p);
     KCHECK(); LAUNCHED(1);
     CU(download_nodes(ctx, b, ctx->p));
@@ -1327,7 +1560,7 @@ extern "C" int pfem_bench_pcg(pfem_ctx* ctx, const pfem_opts* o, int iters, int 
         int done = 0;
         while (done + batch <= iters) {
             CU(cudaGraphLaunch(ctx->graph, ctx->stream));
-            LAUNCHED((long long)batch * kernels_per_iteration(o->variant));
+            LAUNCHED((long long)batch * kernels_per_iteration(ctx, o->variant));
             done += batch;
         }
         for (; done < iters; ++done) LAUNCHED(launch_iteration(ctx, o->variant, done & 1, nullptr));
@@ -1335,7 +1568,7 @@ extern "C" int pfem_bench_pcg(pfem_ctx* ctx, const pfem_opts* o, int iters, int 
         t_total = t.stop();
     }
     TRY(read_scalars(ctx));
-    k_set_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, o->lin_tol * o->lin_tol, o->maxit, 0);
+    k_set_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, o->lin_tol * o->lin_tol, o->maxit, 0, ctx->surf_iter);
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->h_sc->iter != iters) FAIL(PFEM_ERR_CUDA, "benchmark ran %d iterations instead of %d", ctx->h_sc->iter, iters);
     if (ms) *ms = t_total;

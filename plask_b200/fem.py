@@ -74,6 +74,37 @@ class DeviceFem:
             assert h.size == self.E
             self._ck(self.lib.pfem_set_source(self.ctx, _dp(h)))
 
+    def set_boundary(self, heatflux=(), convection=(), radiation=(), verbatim=True):
+        """heatflux_boundary / convection_boundary / radiation_boundary (therm3d.hpp:79-82) as lists of conditions in
+        definition order: (nodes, q) / (nodes, coeff, ambient) / (nodes, emissivity, ambient).  Densified like
+        BoundaryConditionsWithMesh::getValue: the FIRST condition naming a node wins."""
+        def dense(conds, nval):
+            if not conds:
+                return None, [None] * nval
+            has = np.zeros(self.N, dtype=np.uint8)
+            vals = [np.zeros(self.N) for _ in range(nval)]
+            for cond in conds:
+                nodes = np.asarray(cond[0], dtype=np.int64)
+                new = nodes[has[nodes] == 0]
+                for k in range(nval):
+                    vals[k][new] = cond[1 + k]
+                has[new] = 1
+            return has, vals
+        hf, (qf,) = dense(list(heatflux), 1)
+        hc, (cc, ca) = dense(list(convection), 2)
+        hr, (re, ra) = dense(list(radiation), 2)
+        if hf is None and hc is None and hr is None:
+            self._ck(self.lib.pfem_set_boundary(self.ctx, None))
+            return
+        b = L.Boundary()
+        u8 = lambda a: a.ctypes.data_as(L._u8p) if a is not None else None
+        dp = lambda a: _dp(a) if a is not None else None
+        b.has_flux, b.flux = u8(hf), dp(qf)
+        b.has_conv, b.conv_coeff, b.conv_ambient = u8(hc), dp(cc), dp(ca)
+        b.has_rad, b.rad_emissivity, b.rad_ambient = u8(hr), dp(re), dp(ra)
+        b.verbatim = int(bool(verbatim))
+        self._ck(self.lib.pfem_set_boundary(self.ctx, C.byref(b)))
+
     def set_field(self, x):
         if np.isscalar(x):
             self._ck(self.lib.pfem_fill_field(self.ctx, float(x)))

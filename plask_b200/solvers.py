@@ -107,6 +107,12 @@ class Static3D(_FemSolver):
         self.inittemp = 300.     # therm3d.cpp:23
         self.maxerr = 0.05       # therm3d.cpp:24
         self.inHeat = None       # None -> problem.heat; scalar or [E] array (W/m3)
+        # boundary conditions of the 2nd / 3rd kind and radiation (therm3d.hpp:79-82), lists in definition order:
+        # (nodes, q [W/m2]) / (nodes, coeff [W/m2/K], ambient [K]) / (nodes, emissivity, ambient [K])
+        self.heatflux_boundary = []
+        self.convection_boundary = []
+        self.radiation_boundary = []
+        self.boundary_verbatim = True   # reproduce setBoundaries' local-slot accumulation (therm3d.cpp:157-162)
         self.maxT = 0.
         self.loopno = 0
 
@@ -120,6 +126,7 @@ class Static3D(_FemSolver):
         f.set_materials(p.elem_mat, p.T0, p.dT, p.tab_lat, p.tab_vert)
         f.set_field(float(self.inittemp))               # temperatures.reset(size, inittemp), :79
         f.set_dirichlet(p.bc_nodes, p.bc_values)
+        f.set_boundary(self.heatflux_boundary, self.convection_boundary, self.radiation_boundary, self.boundary_verbatim)
         self.loopno = 0
         self.initialized = True
 

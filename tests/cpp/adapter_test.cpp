@@ -75,6 +75,18 @@ static int host_tests() {
     bc.add(bottom, 300.);
     REQUIRE(bc.node.size() == 20 && bc.value[19] == 300.);
 
+    // conditions of the 2nd / 3rd kind: getValue semantics, the FIRST condition naming a node wins
+    NodeConditions<2> conv;
+    REQUIRE(conv.empty());
+    conv.add(m.size(), bottom, {1e4, 300.});
+    std::vector<size_t> edge = {m.node(0, 0, 0), m.node(0, 0, 1)};
+    conv.add(m.size(), edge, {5e4, 350.});
+    REQUIRE(!conv.empty() && conv.has[m.node(0, 0, 0)] == 1 && conv.v[0][m.node(0, 0, 0)] == 1e4 && conv.v[1][m.node(0, 0, 1)] == 350.);
+    REQUIRE(conv.has[m.node(1, 1, 1)] == 0);
+    bool outside = false;
+    try { std::vector<size_t> far = {m.size()}; conv.add(m.size(), far, {1., 1.}); } catch (const BadInput&) { outside = true; }
+    REQUIRE(outside);
+
     Tables t = sample_tables(2, [](uint32_t id, double T) { return std::make_pair(10. * (id + 1) * 300. / T, 5. * (id + 1)); }, 250., 0.5, 701);
     REQUIRE(t.lat.size() == 1402 && std::fabs(t.lat[701 + 100] - 20. * 300. / 300.) < 1e-12);
 
@@ -120,6 +132,44 @@ static int gpu_tests() {
             maxd = std::fmax(maxd, std::fabs(T[m.node(i0, i1, i2)] - ex));
         }
         printf("order %d: loops %d, PCG iterations %lld, max|T - T_exact| = %.3e K (max T %.3f)\n", ord, r.loops, r.lin_iters, maxd, r.maxval);
+        REQUIRE(maxd < 1e-6);
+    }
+    // ---- convection on the top plane, corrected form: T linear, k (T(H) - T0)/H = h (Ta - T(H))
+    {
+        Mesh m = make_mesh(6, 5, 17, ORDER_012);
+        const double k = 40., h = 2e5, Ta = 350., T0 = 300.;
+        Context c(0, "convection");
+        c.set_mesh(m);
+        std::vector<uint32_t> ids(m.elements(), 0);
+        c.set_materials(ids, sample_tables(1, [&](uint32_t, double) { return std::make_pair(k, k); }, 250., 1., 400));
+        c.fill_field(T0);
+        Dirichlet bc;
+        std::vector<size_t> bottom, top;
+        for (size_t i0 = 0; i0 < m.n(0); ++i0) for (size_t i1 = 0; i1 < m.n(1); ++i1) {
+            bottom.push_back(m.node(i0, i1, 0));
+            top.push_back(m.node(i0, i1, m.n(2) - 1));
+        }
+        bc.add(bottom, T0);
+        c.set_dirichlet(bc);
+        c.set_source(nullptr);
+        NodeConditions<1> none1;
+        NodeConditions<2> conv, none2;
+        conv.add(m.size(), top, {h, Ta});
+        c.set_boundary(none1, conv, none2, false);
+        IterParams ip;
+        ip.maxerr = 1e-12; ip.maxit = 20000;
+        c.solve(true, ip, 0.05, 1);
+        REQUIRE(ip.converged);
+        std::vector<double> T(m.size());
+        c.get_field(T.data());
+        const double H = (m.axis[2].back() - m.axis[2].front()) * 1e-6;
+        const double TH = (k * T0 / H + h * Ta) / (k / H + h);
+        double maxd = 0.;
+        for (size_t i0 = 0; i0 < m.n(0); ++i0) for (size_t i1 = 0; i1 < m.n(1); ++i1) for (size_t i2 = 0; i2 < m.n(2); ++i2) {
+            const double z = (m.axis[2][i2] - m.axis[2][0]) * 1e-6;
+            maxd = std::fmax(maxd, std::fabs(T[m.node(i0, i1, i2)] - (T0 + (TH - T0) * z / H)));
+        }
+        printf("convection: max|T - T_exact| = %.3e K (T(H) = %.4f)\n", maxd, TH);
         REQUIRE(maxd < 1e-6);
     }
     // ---- noconv policy

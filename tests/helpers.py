@@ -88,3 +88,30 @@ def shockley3d_reference_problem(order="optimal"):
     p.bc_values = np.concatenate([np.zeros(top.size), np.ones(bot.size)])
     p.beta, p.js, p.maxerr = 10., 1., 1e-3
     return p
+
+
+def face_nodes(p, axis, side):
+    """node numbers of the mesh plane `side` (0 or -1) of physical axis `axis` (RectangularMesh<3>::getLeft/Right/...
+    Boundary, plask/mesh/rectangular3d.hpp)"""
+    ng = np.broadcast_to(p.node_index_grid(), p.n)
+    return np.ascontiguousarray(np.take(ng, side, axis=axis).ravel(), dtype=np.int64)
+
+
+def slab_problem_1d(n=(4, 4, 17), H=10., k=40., T0=300., order="012", dirichlet="bottom"):
+    """uniform material of constant conductivity k on a box of height H um (non-uniform vertical spacing), no heat
+    source, T0 on the bottom (or top) plane: every solution driven by conditions on horizontal planes is 1-D."""
+    rng = np.random.default_rng(3)
+    axes = [np.linspace(0., 3., n[0]), np.linspace(0., 2., n[1])]
+    h = 1. + 0.6 * (rng.random(n[2] - 1) - 0.5)
+    z = np.concatenate([[0.], np.cumsum(h)])
+    axes.append(z * (H / z[-1]))
+    tab = np.full((1, 2), float(k))
+    p = cf.Problem("slab1d", "thermal", axes, order, None, 200., 1000., tab, tab.copy(), None, None)
+    p.elem_mat = np.zeros(p.E, dtype=np.uint32)
+    nodes = face_nodes(p, 2, 0 if dirichlet == "bottom" else -1)
+    p.bc_nodes = nodes.astype(np.uintp)
+    p.bc_values = np.full(nodes.size, float(T0))
+    p.heat = np.zeros(p.E)
+    p.inittemp = float(T0)
+    p.maxerr = 1e-9
+    return p

@@ -67,6 +67,9 @@ def main():
     if ncol_l:
         assert acts_l[0]["bottom"] == acts_g[0]["bottom"] and acts_l[0]["top"] == acts_g[0]["top"]
         assert acts_l[0]["back"] + clo >= acts_g[0]["back"] and acts_l[0]["front"] + clo <= acts_g[0]["front"]
+    # node lists of boundary conditions are localised like the Dirichlet list
+    ln, keep = cf.slab_local_nodes(p, q, lo, hi, p.bc_nodes)
+    assert np.array_equal(ln.astype(np.uintp), q.bc_nodes) and keep.sum() == q.bc_nodes.size
     blobs = allgather_bytes(bytes([rank]) * 64)
     assert [b[0] for b in blobs] == list(range(world))
     if host_only:
@@ -118,6 +121,55 @@ def main():
               f"{one.stats['lin_iters']}), max|T_slab - T_single| = {d1:.3e} K, max|T_slab - T_cholesky| = {d2:.3e} K")
         assert stats[0]["outer_loops"] == one.stats["outer_loops"] == len(o.history)
         assert abs(stats[0]["lin_iters"] - one.stats["lin_iters"]) <= 0.02 * one.stats["lin_iters"] + 2
+        assert d1 <= 1e-6 and d2 <= 1e-3
+        one.invalidate()
+    dist.barrier()
+
+    # ---- boundary conditions of the 2nd / 3rd kind and radiation in slab mode (corrected form; conditions on the two
+    # end planes of the slab axis live on one rank only, the others cross every slab)
+    from helpers import face_nodes
+    gconds = dict(convection=[(face_nodes(p, 2, -1), 4.0e4, 310.), (face_nodes(p, 0, 0), 9.0e4, 295.)],
+                  heatflux=[(face_nodes(p, 0, -1), -3.0e5)], radiation=[(face_nodes(p, 1, -1), 0.85, 285.)])
+
+    def localise(conds):
+        out = {}
+        for kind, lst in conds.items():
+            out[kind] = []
+            for c in lst:
+                ln, keep = cf.slab_local_nodes(p, q, lo, hi, c[0])
+                out[kind].append((ln,) + tuple(c[1:]))
+        return out
+
+    def with_conditions(sv, conds):
+        sv.heatflux_boundary, sv.convection_boundary, sv.radiation_boundary = conds["heatflux"], conds["convection"], conds["radiation"]
+        sv.boundary_verbatim = False
+        sv.iterative.maxerr = 1e-11
+        sv.iterative.maxit = 50000
+
+    sb = Static3D(f"slabbc{rank}")
+    sb.device = local
+    sb.problem = q
+    sb.slab = dict(rank=rank, nranks=world, own_lo=own_lo, own_hi=own_hi, allgather=allgather_bytes)
+    with_conditions(sb, localise(gconds))
+    sb.compute(0)
+    partsB = allgather_bytes((cf.slab_field_owned(q, sb.outTemperature(), own_lo, own_hi), sb.stats))
+    sb.invalidate()
+    if rank == 0:
+        from oracle import oracle as orc
+        from helpers import oracle_thermal
+        T = np.concatenate([x[0] for x in partsB], axis=0).ravel()
+        o = oracle_thermal(p, algorithm="cholesky", boundaries=orc.BoundaryTerms(p.N, **gconds), quirk=False)
+        o.compute(0)
+        one = Static3D("singlebc")
+        one.device = 0
+        one.problem = p
+        with_conditions(one, gconds)
+        one.compute(0)
+        d1 = float(np.abs(T - one.outTemperature()).max())
+        d2 = float(np.abs(T - o.temperatures).max())
+        print(f"slab x{world} with boundary terms: loops {partsB[0][1]['outer_loops']}, PCG iterations {partsB[0][1]['lin_iters']} "
+              f"(single GPU {one.stats['lin_iters']}), max|Tb_slab - Tb_single| = {d1:.3e} K, max|Tb_slab - Tb_cholesky| = {d2:.3e} K")
+        assert partsB[0][1]["outer_loops"] == one.stats["outer_loops"] == len(o.history)
         assert d1 <= 1e-6 and d2 <= 1e-3
         one.invalidate()
     dist.barrier()

@@ -159,13 +159,18 @@ def electrical_tables(T0=250., dT=0.25, nT=1601):
 
 # --------------------------------------------------------------------------- config A
 
-def config_A(n=64, order="optimal", heat=1e15):
+def config_A(n=64, order="optimal", heat=1e15, rows0=None):
     """Static3D on an n^3 GaAs/AlGaAs stack with uniform heat source (BASELINE configs[0]):
     lateral axes uniform over n um, vertical axis = DBR layer interfaces, one element per
-    layer; T = 300 K on the bottom plane."""
+    layer; T = 300 K on the bottom plane.  rows0 = (lo, hi): one slab (node rows lo..hi-1 of axis 0) of the mesh."""
     n = (n, n, n) if np.isscalar(n) else tuple(n)
+    if rows0 is not None and order == "optimal":
+        order = optimal_order(n)
     ax0 = np.linspace(0., float(n[0]), n[0])
     ax1 = np.linspace(0., float(n[1]), n[1])
+    if rows0 is not None:
+        ax0 = ax0[rows0[0]:rows0[1]]
+        n = (len(ax0), n[1], n[2])
     hz = np.where(np.arange(n[2] - 1) % 2 == 0, D_GAAS, D_ALGAAS)
     ax2 = np.concatenate([[0.], np.cumsum(hz)])
     if order == "optimal":
@@ -273,9 +278,13 @@ def config_B(n=256, order="optimal", rows0=None):
     return p
 
 
-def config_C(n=(192, 192, 400), order="optimal", voltage=1.4):
-    """Shockley3D with oxide aperture and a nonlinear junction layer (BASELINE configs[2])."""
-    n, axes, order, mat, tagv, reg = _vcsel(n, order, "shockley")
+def config_C(n=(192, 192, 400), order="optimal", voltage=1.4, rows0=None):
+    """Shockley3D with oxide aperture and a nonlinear junction layer (BASELINE configs[2]).
+    rows0 = (lo, hi): direct construction of one slab (node rows lo..hi-1 of axis 0), like config_B."""
+    nglob = (n, n, n) if np.isscalar(n) else tuple(n)
+    if rows0 is not None and order == "optimal":
+        order = optimal_order(nglob)
+    n, axes, order, mat, tagv, reg = _vcsel(n, order, "shockley", rows0=rows0)
     T0, dT, lat, vert = electrical_tables()
     p = Problem("C", "shockley", axes, order, None, T0, dT, lat, vert, None, None)
     p.elem_mat = p.to_elem_order(mat, np.uint32)
@@ -293,8 +302,15 @@ def config_C(n=(192, 192, 400), order="optimal", voltage=1.4):
     Rn = np.sqrt(x[:, None] ** 2 + y[None, :] ** 2)
     # nodes whose four surrounding top-layer elements are all Au
     ring_e = reg["ring"]
-    ring_n = np.zeros((n[0], n[1]), dtype=bool)
+    if rows0 is not None:   # the ring of the whole mesh (2-D, cheap), cut to the local rows afterwards
+        gx, gy = graded_axis(nglob[0], 0.25, 4.), axes[1]
+        gxm, gym = 0.5 * (gx[1:] + gx[:-1]), 0.5 * (gy[1:] + gy[:-1])
+        Rg = np.sqrt(gxm[:, None] ** 2 + gym[None, :] ** 2)
+        ring_e = (Rg > 1.5 * 4.) & (Rg < 0.8 * 15.)
+    ring_n = np.zeros((ring_e.shape[0] + 1, n[1]), dtype=bool)
     ring_n[1:-1, 1:-1] = ring_e[:-1, :-1] & ring_e[1:, :-1] & ring_e[:-1, 1:] & ring_e[1:, 1:]
+    if rows0 is not None:
+        ring_n = ring_n[rows0[0]:rows0[1]]
     top = ng[:, :, -1][ring_n]
     bottom = ng[:, :, 0].ravel()
     p.bc_nodes = np.concatenate([top, bottom]).astype(np.uintp)

@@ -62,6 +62,10 @@ def main():
     legc = np.broadcast_to(qc.elem_index_grid(), tuple(k - 1 for k in qc.n))
     assert np.array_equal(qc.elem_junc[legc], pc.elem_junc[egc][clo:chi - 1])
     assert np.array_equal(qc.noheat[legc], pc.noheat[egc][clo:chi - 1])
+    dc = cf.config_C(pc.n, order="012", rows0=(clo, chi))      # direct construction (tools/run_configs.py at scale)
+    assert np.array_equal(dc.elem_mat, qc.elem_mat) and np.array_equal(dc.elem_junc, qc.elem_junc)
+    ia, ib = np.argsort(dc.bc_nodes), np.argsort(qc.bc_nodes)
+    assert np.array_equal(dc.bc_nodes[ia], qc.bc_nodes[ib]) and np.array_equal(dc.bc_values[ia], qc.bc_values[ib])
     acts_g, _ = cf.setup_active(pc)
     acts_l, ncol_l = cf.setup_active(qc)
     if ncol_l:

@@ -107,3 +107,32 @@ def test_no_junction_noactive_path():
     assert s.stats["maxval"] == pytest.approx(o.history[-1]["mcur"], rel=1e-6)
     assert np.allclose(s.maxcur, o.maxcur, rtol=1e-5, atol=1e-12)
     s.invalidate()
+
+
+def test_full_size_properties_C():
+    """BASELINE configs[2] at full size (192x192x400, 14.7 M nodes): the oracle cannot factorise this, so check
+    size-independent properties after a fixed number of loops: the linear residual target is met, the potential has the
+    oracle's extrema, and the current is continuous — the same total current crosses every horizontal
+    plane that spans the whole structure (div j = 0 for the conductivities of the last loop)."""
+    p = cf.config_C()
+    assert p.n == (192, 192, 400)
+    e = Shockley3D("C")
+    e.problem = p
+    e.iterative.maxerr = 1e-10
+    e.iterative.maxit = 200000
+    e.compute(8)
+    assert e.iterative.converged and e.iterative.err <= 1e-8
+    V = e.outVoltage()
+    # no discrete maximum principle here: Q1 bricks with aspect ratios ~ 800 next to the insulating air / oxide give
+    # positive off-diagonal entries, and the oracle's Cholesky solution of this structure undershoots to -1.69 V at
+    # every size tried (20x22x52, 40x40x100) in the same place (air beside the mesa) — so only sanity bounds
+    assert np.isfinite(V).all() and V.min() >= -2.5 and V.max() <= 1.4 + 0.1
+    assert V.min() == pytest.approx(-1.69, abs=0.05)        # ... and the same undershoot as the oracle's small cases
+    a = e._acts[0]
+    I_junction = e.integrate_current((a["bottom"] + a["top"]) // 2)
+    planes = [2, a["bottom"] // 2, a["bottom"] - 2]          # substrate and n-DBR, below the mesa (full cross-section conducts)
+    for k in planes:
+        assert e.integrate_current(k) == pytest.approx(I_junction, rel=1e-5), k
+    assert abs(I_junction) > 1e-3
+    assert e.stats["maxval"] > 0.
+    e.invalidate()

@@ -76,7 +76,15 @@ int pfem_set_mesh(pfem_ctx* ctx, const size_t n[3], const double* ax0, const dou
 /* Material id per element + per-id conductivity tables c_lat/c_vert[nmat][nT] sampled by the
  * host on the grid T0 + i*dT from material->thermk(T, thickness) (thermal, therm3d.cpp:213;
  * ids distinguish (material, layer thickness) pairs, therm3d.cpp:81-114) or material->cond(T)
- * (electrical, electr3d.cpp:221).  Interpolation is linear, clamped at both ends. */
+ * (electrical, electr3d.cpp:221).  Interpolation is linear, clamped at both ends.
+ *
+ * Masked meshes (empty-elements="exclude", FemSolverWithMaskedMesh::setupMaskedMesh, fem_solver.hpp:182-189 — the
+ * default of the reference's Cholesky path): pass PFEM_MAT_EXCLUDED for the elements that are not in the masked mesh
+ * (material kind EMPTY).  They get no stiffness, no load, no current, heat or flux; mesh nodes that touch no kept element
+ * drop out of the system (they are not nodes of RectangularMaskedMesh3D) and read back as 0 from pfem_get_field.  All
+ * arrays of the ABI stay in FULL-mesh numbering; the plugin maps to its masked numbering (plaskfem::MaskedNumbering in
+ * plaskfem_cuda.hpp).  Call pfem_set_materials before pfem_set_source when elements are excluded. */
+#define PFEM_MAT_EXCLUDED 0xFFFFFFFFu
 int pfem_set_materials(pfem_ctx* ctx, const uint32_t* elem_mat, uint32_t nmat, double T0, double dT, uint32_t nT,
                        const double* c_lat, const double* c_vert);
 

@@ -152,6 +152,49 @@ struct Dirichlet {
     void add(const NodeRange& place, double v) { for (size_t r : place) { node.push_back(r); value.push_back(v); } }
 };
 
+// ---- masked meshes: empty-elements = "exclude" (fem_solver.hpp:182-189) --------------------------------
+//
+// RectangularMaskedMesh3D keeps the elements whose material is not EMPTY and the nodes of those elements, both numbered in
+// the order of the full mesh.  The C ABI stays in full-mesh numbering (excluded elements are marked PFEM_MAT_EXCLUDED in
+// the material ids); this helper gives the plugin the two index maps to move its DataVectors across.
+struct MaskedNumbering {
+    static constexpr size_t NONE = std::numeric_limits<size_t>::max();
+    std::vector<size_t> node_of_full, elem_of_full;   // full index -> masked index or NONE
+    std::vector<size_t> full_of_node, full_of_elem;   // masked index -> full index
+    // included(i0, i1, i2) -> true if the element is kept (material kind != EMPTY)
+    template <typename Included>
+    MaskedNumbering(const Mesh& m, Included included) {
+        const size_t n0 = m.n(0), n1 = m.n(1), n2 = m.n(2);
+        node_of_full.assign(m.size(), NONE);
+        elem_of_full.assign(m.elements(), NONE);
+        std::vector<uint8_t> used(m.size(), 0);
+        for (size_t i0 = 0; i0 + 1 < n0; ++i0) for (size_t i1 = 0; i1 + 1 < n1; ++i1) for (size_t i2 = 0; i2 + 1 < n2; ++i2) {
+            if (!included(i0, i1, i2)) continue;
+            elem_of_full[m.elem(i0, i1, i2)] = 0;
+            for (int l = 0; l < 8; ++l) used[m.node(i0 + (l & 1), i1 + ((l >> 1) & 1), i2 + ((l >> 2) & 1))] = 1;
+        }
+        for (size_t i = 0; i < used.size(); ++i) if (used[i]) { node_of_full[i] = full_of_node.size(); full_of_node.push_back(i); }
+        for (size_t e = 0; e < elem_of_full.size(); ++e) if (elem_of_full[e] != NONE) { elem_of_full[e] = full_of_elem.size(); full_of_elem.push_back(e); }
+    }
+    // material ids for pfem_set_materials: the caller's ids on kept elements, PFEM_MAT_EXCLUDED elsewhere
+    std::vector<uint32_t> mark_excluded(std::vector<uint32_t> ids) const {
+        for (size_t e = 0; e < ids.size(); ++e) if (elem_of_full[e] == NONE) ids[e] = PFEM_MAT_EXCLUDED;
+        return ids;
+    }
+    // masked vector <-> full vector (NC interleaved components per entry)
+    void nodes_to_masked(const double* full, double* masked) const { for (size_t k = 0; k < full_of_node.size(); ++k) masked[k] = full[full_of_node[k]]; }
+    void nodes_to_full(const double* masked, double* full, double fill = 0.) const {
+        for (size_t i = 0; i < node_of_full.size(); ++i) full[i] = node_of_full[i] == NONE ? fill : masked[node_of_full[i]];
+    }
+    void elems_to_masked(const double* full, double* masked, int nc = 1) const {
+        for (size_t k = 0; k < full_of_elem.size(); ++k) for (int c = 0; c < nc; ++c) masked[k * nc + c] = full[full_of_elem[k] * nc + c];
+    }
+    void elems_to_full(const double* masked, double* full, int nc = 1, double fill = 0.) const {
+        for (size_t e = 0; e < elem_of_full.size(); ++e) for (int c = 0; c < nc; ++c)
+            full[e * nc + c] = elem_of_full[e] == NONE ? fill : masked[elem_of_full[e] * nc + c];
+    }
+};
+
 // ---- row a7: boundary conditions of the 2nd / 3rd kind and radiation ----------------------------------
 //
 // heatflux_boundary / convection_boundary / radiation_boundary (therm3d.hpp:79-82) in the form setBoundaries reads

@@ -316,6 +316,67 @@ void orc_assemble_dpb(const orc_mesh* m, const double* cond, const double* heat,
     }
 }
 
+/* ---------------- masked mesh: empty-elements = "exclude" (fem_solver.hpp:182-189) -------
+ * RectangularMaskedMesh3D keeps the elements whose material is not EMPTY and the nodes of those elements,
+ * numbered in the order of the full mesh (compressed sets, plask/mesh/rectangular_masked3d.hpp).  This is the
+ * DEFAULT of the reference's Cholesky path (EMPTY_ELEMENTS_DEFAULT + ALGORITHM_CHOLESKY, fem_solver.hpp:183-187).
+ * included[E] != 0 marks the kept elements; nodemap[N] receives the masked node number or SIZE_MAX.
+ * Returns the number of masked nodes. */
+size_t orc_masked_nodes(const orc_mesh* m, const uint8_t* included, size_t* nodemap) {
+    size_t N = orc_mesh_nodes(m), E = orc_mesh_elements(m), cnt = 0;
+    for (size_t i = 0; i < N; ++i) nodemap[i] = 0;
+    for (size_t e = 0; e < E; ++e) {
+        if (!included[e]) continue;
+        size_t ix[3], idx[8];
+        elem_indices(m, e, ix);
+        elem_nodes(m, ix, idx);
+        for (int l = 0; l < 8; ++l) nodemap[idx[l]] = 1;
+    }
+    for (size_t i = 0; i < N; ++i) nodemap[i] = nodemap[i] ? cnt++ : (size_t)-1;
+    return cnt;
+}
+
+/* FemSolverWithMaskedMesh<Geometry3D,...>::getMatrix, fem_solver.hpp:219-231: band = max over the masked elements
+ * of (UpUpUp - LoLoLo) in masked numbering; DpbMatrix ctor (cholesky_matrix.hpp:64-65) for ld. */
+void orc_dpb_dims_masked(const orc_mesh* m, const uint8_t* included, const size_t* nodemap, size_t* kd, size_t* ld) {
+    size_t E = orc_mesh_elements(m), band = 0;
+    for (size_t e = 0; e < E; ++e) {
+        if (!included[e]) continue;
+        size_t ix[3], idx[8];
+        elem_indices(m, e, ix);
+        elem_nodes(m, ix, idx);
+        size_t span = nodemap[idx[7]] - nodemap[idx[0]];
+        if (span > band) band = span;
+    }
+    *kd = band;
+    *ld = ((band + 1 + (15 / sizeof(double))) & ~(size_t)(15 / sizeof(double))) - 1;
+}
+
+/* The assembly loops (therm3d.cpp:186-276, electr3d.cpp:281-342) over maskedMesh->elements(), indices in masked
+ * numbering.  AB is Nm*(ld+1), B is Nm. */
+void orc_assemble_dpb_masked(const orc_mesh* m, const double* cond, const double* heat, const uint8_t* included,
+                             const size_t* nodemap, size_t Nm, size_t ld, double* AB, double* B) {
+    size_t E = orc_mesh_elements(m);
+    memset(AB, 0, Nm * (ld + 1) * sizeof(double));
+    memset(B, 0, Nm * sizeof(double));
+    for (size_t e = 0; e < E; ++e) {
+        if (!included[e]) continue;
+        size_t ix[3], idx[8];
+        elem_indices(m, e, ix);
+        elem_nodes(m, ix, idx);
+        double dx = m->ax[0][ix[0] + 1] - m->ax[0][ix[0]];
+        double dy = m->ax[1][ix[1] + 1] - m->ax[1][ix[1]];
+        double dz = m->ax[2][ix[2] + 1] - m->ax[2][ix[2]];
+        double kv[8];
+        elem_stiffness(cond[2 * e], cond[2 * e + 1], dx, dy, dz, kv);
+        double f = heat ? 0.125e-18 * dx * dy * dz * heat[e] : 0.;
+        for (int i = 0; i < 8; ++i) {
+            for (int j = 0; j <= i; ++j) *dpb_at(AB, ld, nodemap[idx[i]], nodemap[idx[j]]) += kv[i ^ j];
+            B[nodemap[idx[i]]] += f;
+        }
+    }
+}
+
 /* BandMatrix::setBC, matrix.hpp:132-145. */
 void orc_apply_bc_dpb(size_t rank, size_t kd, size_t ld, double* AB, double* B, size_t nd, const size_t* node,
                       const double* value) {

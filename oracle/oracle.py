@@ -249,6 +249,60 @@ class Dpb:
         return dict(ier=0, converged=True, iters=0, err=0.)
 
 
+class DpbMasked:
+    """DpbMatrix on a RectangularMaskedMesh3D — empty-elements="exclude", the default of the reference's Cholesky path
+    (fem_solver.hpp:182-189,219-231): rank = number of masked nodes, band from the masked element spans.  Vectors
+    given to / returned from this class are FULL-mesh arrays; entries of nodes outside the masked mesh are left alone
+    (the reference has no such entries)."""
+
+    def __init__(self, mesh, included):
+        self.mesh = mesh
+        self.included = np.ascontiguousarray(included, dtype=np.uint8)
+        assert self.included.size == mesh.E
+        self.nodemap = np.zeros(mesh.N, dtype=np.uintp)
+        lib().orc_masked_nodes.restype = c_sz
+        self.Nm = lib().orc_masked_nodes(mesh.ref, _p(self.included, C.c_uint8), _p(self.nodemap, c_sz))
+        self.active = self.nodemap != np.uintp(np.iinfo(np.uintp).max)
+        kd, ld = c_sz(0), c_sz(0)
+        lib().orc_dpb_dims_masked(mesh.ref, _p(self.included, C.c_uint8), _p(self.nodemap, c_sz), C.byref(kd), C.byref(ld))
+        self.kd, self.ld = kd.value, ld.value
+        self.data = np.zeros((self.Nm, self.ld + 1))
+        self.Bm = np.zeros(self.Nm)
+
+    def assemble(self, cond, heat, B):
+        lib().orc_assemble_dpb_masked(self.mesh.ref, _p(cond), _p(heat) if heat is not None else None,
+                                      _p(self.included, C.c_uint8), _p(self.nodemap, c_sz), c_sz(self.Nm), c_sz(self.ld),
+                                      _p(self.data), _p(self.Bm))
+        B[:] = 0.
+        B[self.active] = self.Bm
+
+    def add_coo(self, rows, cols, vals):
+        raise NotImplementedError("boundary terms on a masked mesh")
+
+    def apply_bc(self, B, nodes, values):
+        """boundary conditions live on the masked mesh: places outside it hold no nodes"""
+        mn = self.nodemap[np.asarray(nodes, dtype=np.int64)]
+        keep = mn != np.uintp(np.iinfo(np.uintp).max)
+        mn = np.ascontiguousarray(mn[keep], dtype=np.uintp)
+        mv = np.ascontiguousarray(np.asarray(values, dtype=np.float64)[keep])
+        lib().orc_apply_bc_dpb(c_sz(self.Nm), c_sz(self.kd), c_sz(self.ld), _p(self.data), _p(self.Bm),
+                               c_sz(len(mn)), _p(mn, c_sz), _p(mv))
+        B[self.active] = self.Bm
+
+    def solve(self, B, X, threads=None):
+        from scipy.linalg import lapack
+        ab = self.data.T
+        c, info = lapack.dpbtrf(ab, lower=1, overwrite_ab=1)
+        if info > 0:
+            raise RuntimeError(f"leading minor of order {info} of the stiffness matrix is not positive-definite")
+        assert info == 0
+        x, info = lapack.dpbtrs(c, self.Bm, lower=1)
+        assert info == 0
+        X[self.active] = x
+        return dict(ier=0, converged=True, iters=0, err=0.)
+
+
+# ------------------------------------------------------------------------- Static3D
 # ------------------------------------------------------------------------- Static3D
 
 
@@ -299,8 +353,10 @@ class Static3DOracle:
 
     def __init__(self, mesh, elem_mat, tables, dirichlet_nodes, dirichlet_values, heat=None, inittemp=300.,
                  maxerr=0.05, algorithm="cholesky", precond="ic", itmaxerr=1e-6, maxit=1000, nfact=10,
-                 boundaries=None, quirk=True):
+                 boundaries=None, quirk=True, included=None):
         self.mesh = mesh
+        # empty-elements="exclude": uint8 [E], 0 = element outside the masked mesh (Cholesky only); None = full mesh
+        self.included = None if included is None else np.ascontiguousarray(included, dtype=np.uint8)
         self.boundaries = boundaries   # BoundaryTerms or None (heat flux / convection / radiation, therm3d.cpp:242-268)
         self.quirk = quirk             # True: verbatim local-slot accumulation of setBoundaries (therm3d.cpp:157-162)
         self.elem_mat = np.ascontiguousarray(elem_mat, dtype=np.uint32)
@@ -320,7 +376,12 @@ class Static3DOracle:
 
     def _matrix(self):
         if self._A is None:
-            self._A = Dpb(self.mesh) if self.algorithm == "cholesky" else Sparse14(self.mesh)
+            if self.included is not None:
+                assert self.algorithm == "cholesky", "the masked mesh is restated for the Cholesky path only"
+                self._A = DpbMasked(self.mesh, self.included)
+                self.temperatures[~self._A.active] = 0.   # nodes outside the masked mesh do not exist
+            else:
+                self._A = Dpb(self.mesh) if self.algorithm == "cholesky" else Sparse14(self.mesh)
         return self._A
 
     def set_matrix(self, A, B):
@@ -329,6 +390,8 @@ class Static3DOracle:
         lib().orc_thermal_conds(self.mesh.ref, _p(self.temperatures), _p(self.elem_mat, C.c_uint32),
                                 C.c_uint32(t.nT), C.c_double(t.T0), C.c_double(t.dT), _p(t.lat), _p(t.vert),
                                 _p(self.conds))
+        if self.included is not None:
+            self.conds[self.included == 0] = 0.
         A.assemble(self.conds, self.heat if self.heat is not None else np.zeros(self.mesh.E), B)
         if self.boundaries is not None:
             rows, cols, vals = self.boundaries.terms(self.mesh, self.temperatures, B, self.quirk)
@@ -373,6 +436,8 @@ class Static3DOracle:
         lib().orc_thermal_conds(self.mesh.ref, _p(self.temperatures), _p(self.elem_mat, C.c_uint32),
                                 C.c_uint32(t.nT), C.c_double(t.T0), C.c_double(t.dT), _p(t.lat), _p(t.vert),
                                 _p(self.conds))
+        if self.included is not None:
+            self.conds[self.included == 0] = 0.   # saveHeatFluxes loops over maskedMesh->elements() (:352)
         flux = np.zeros((self.mesh.E, 3))
         lib().orc_heat_flux(self.mesh.ref, _p(self.temperatures), _p(self.conds), _p(flux))
         return flux
@@ -387,9 +452,12 @@ class Shockley3DOracle:
 
     def __init__(self, mesh, elem_mat, tables, dirichlet_nodes, dirichlet_values, elem_junc=None, elem_role=None,
                  beta=None, js=None, pcond=5., ncond=50., start_cond=(0., 5.), maxerr=0.05, convergence="fast",
-                 algorithm="cholesky", precond="ic", itmaxerr=1e-6, maxit=1000, nfact=10, noheat=None, eps=None):
+                 algorithm="cholesky", precond="ic", itmaxerr=1e-6, maxit=1000, nfact=10, noheat=None, eps=None,
+                 included=None):
         self.mesh = mesh
         E = mesh.E
+        # empty-elements="exclude": uint8 [E], 0 = element outside the masked mesh (Cholesky only); None = full mesh
+        self.included = None if included is None else np.ascontiguousarray(included, dtype=np.uint8)
         self.elem_mat = np.ascontiguousarray(elem_mat, dtype=np.uint32)
         self.tables = tables
         self.bc_nodes = np.ascontiguousarray(dirichlet_nodes, dtype=np.uintp)
@@ -425,7 +493,11 @@ class Shockley3DOracle:
 
     def _matrix(self):
         if self._A is None:
-            self._A = Dpb(self.mesh) if self.algorithm == "cholesky" else Sparse14(self.mesh)
+            if self.included is not None:
+                assert self.algorithm == "cholesky", "the masked mesh is restated for the Cholesky path only"
+                self._A = DpbMasked(self.mesh, self.included)
+            else:
+                self._A = Dpb(self.mesh) if self.algorithm == "cholesky" else Sparse14(self.mesh)
         return self._A
 
     def _junction_params(self):
@@ -453,6 +525,8 @@ class Shockley3DOracle:
                                       C.c_double(t.dT), _p(t.lat), _p(t.vert), self.active,
                                       _p(self.junction_conductivity), C.c_double(self.pcond), C.c_double(self.ncond),
                                       _p(self.conds))
+        if self.included is not None:
+            self.conds[self.included == 0] = 0.   # elements outside the masked mesh do not exist: no current, no heat
 
     def compute(self, loops=0):
         """compute, electr3d.cpp:356-442."""
@@ -512,7 +586,10 @@ class Shockley3DOracle:
         return lib().orc_total_heat(self.mesh.ref, _p(self.heat_density()))
 
     def get_total_energy(self):
-        return lib().orc_total_energy(self.mesh.ref, _p(self.potential), _p(self.eps))
+        eps = self.eps
+        if self.included is not None:   # getTotalEnergy loops over maskedMesh->elements() (electr3d.cpp:577-600)
+            eps = np.ascontiguousarray(np.where(self.included != 0, eps, 0.))
+        return lib().orc_total_energy(self.mesh.ref, _p(self.potential), _p(eps))
 
     def get_capacitance(self):
         """getCapacitance, electr3d.cpp:602-610 (exactly two voltage conditions)."""

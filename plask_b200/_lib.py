@@ -105,6 +105,7 @@ PFEM_OK, PFEM_NOT_CONVERGED = 0, 1
 PFEM_ERR_CUDA, PFEM_ERR_NO_DEVICE, PFEM_ERR_BAD_INPUT, PFEM_ERR_STATE = -1, -2, -3, -4
 PFEM_ERR_NOT_SPD, PFEM_ERR_NOMEM, PFEM_ERR_NAN = -5, -6, -7
 ELEM_COND, ELEM_CURRENT, ELEM_HEAT, ELEM_FLUX = 0, 1, 2, 3
+MAT_EXCLUDED = 0xFFFFFFFF
 
 _lib = None
 

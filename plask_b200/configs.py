@@ -59,6 +59,7 @@ class Problem:
     ncond: float = 50.
     start_cond: tuple = (0., 5.)
     Te: float = 300.
+    empty: np.ndarray = None       # uint8 [E]: material kind EMPTY (the elements empty-elements="exclude" drops)
     meta: dict = field(default_factory=dict)
 
     @property
@@ -264,6 +265,7 @@ def config_B(n=256, order="optimal", rows0=None):
     T0, dT, lat, vert = thermal_tables()
     p = Problem("B", "thermal", axes, order, None, T0, dT, lat, vert, None, None)
     p.elem_mat = p.to_elem_order(mat, np.uint32)
+    p.empty = (p.elem_mat == AIR).astype(np.uint8)
     heat = np.zeros(mat.shape)
     mesa_layers = np.isin(tagv, ["bar", "qw", "ox", "pA", "pG"])
     # ~14 mW in the active cylinder (r < r_ap, 55 nm thick) + ~6 mW of Joule heat spread over the mesa:
@@ -294,6 +296,7 @@ def config_C(n=(192, 192, 400), order="optimal", voltage=1.4, rows0=None):
     p.elem_junc = p.to_elem_order(junc, np.uint32)
     p.elem_role = np.zeros(p.E, dtype=np.uint8)
     p.noheat = p.to_elem_order((mat == AIR).astype(np.uint8), np.uint8)
+    p.empty = p.noheat.copy()
     p.maxerr = 0.05
     p.beta, p.js = 11., 1.   # thermoelectric.xpl:91
     ng = np.broadcast_to(p.node_index_grid(), n)
@@ -406,6 +409,7 @@ def slab_problem(p, rank, nranks):
     q.elem_junc = cut_elem(p.elem_junc, np.uint32)
     q.elem_role = cut_elem(p.elem_role, np.uint8)
     q.noheat = cut_elem(p.noheat, np.uint8)
+    q.empty = cut_elem(p.empty, np.uint8)
     for name in ("beta", "js", "pcond", "ncond", "start_cond", "Te"):
         setattr(q, name, getattr(p, name))
     # Dirichlet nodes inside the local planes (halo planes included), in application order

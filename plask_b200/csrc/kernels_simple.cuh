@@ -109,7 +109,8 @@ __global__ void k_diag(const Grid g, const double* __restrict__ cl, const double
 
 // Load vector: B[node] += 0.125e-18*dx*dy*dz*heat[e] over the 8 adjacent elements
 // (therm3d.cpp:223,274).  heat lives on the padded element lattice (0 in padding).
-__global__ void k_load_vector(const Grid g, const double* __restrict__ heat, double* __restrict__ f) {
+// mat != nullptr: elements marked PFEM_MAT_EXCLUDED (outside the masked mesh) carry no load.
+__global__ void k_load_vector(const Grid g, const double* __restrict__ heat, const uint32_t* __restrict__ mat, double* __restrict__ f) {
     const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
     const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
     const int k = blockIdx.z;
@@ -123,9 +124,37 @@ __global__ void k_load_vector(const Grid g, const double* __restrict__ heat, dou
 #pragma unroll
             for (int di = -1; di <= 0; ++di) {
                 const idx_t slot = n + di + g.sJ * dj + g.sK * dk;
+                if (mat && mat[slot] == PFEM_MAT_EXCLUDED) continue;
                 s += 0.125e-18 * g.hI[i + di] * g.hJ[j + dj] * g.hK[k + dk] * heat[slot];
             }
     f[n] = s;
+}
+
+// Masked mesh: a node belongs to the masked mesh iff one of its (up to 8) adjacent elements is kept.  The other nodes
+// do not exist in the reference (RectangularMaskedMesh3D); here they are rows with an empty diagonal (dinv = 0) whose
+// field value is pinned to 0 so that they contribute nothing to any norm, maximum or gradient.
+__global__ void k_mark_inactive(const Grid g, const uint32_t* __restrict__ mat, uint8_t* __restrict__ inactive) {
+    const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
+    const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= g.nI || j >= g.nJ) return;
+    const idx_t n = i + g.sJ * j + g.sK * k;
+    bool any = false;
+#pragma unroll
+    for (int dk = -1; dk <= 0; ++dk)
+#pragma unroll
+        for (int dj = -1; dj <= 0; ++dj)
+#pragma unroll
+            for (int di = -1; di <= 0; ++di) {
+                const int ei = i + di, ej = j + dj, ek = k + dk;
+                if (ei < 0 || ej < 0 || ek < 0 || ei >= g.nI - 1 || ej >= g.nJ - 1 || ek >= g.nK - 1) continue;
+                if (mat[n + di + g.sJ * dj + g.sK * dk] != PFEM_MAT_EXCLUDED) any = true;
+            }
+    inactive[n] = any ? 0 : 1;
+}
+__global__ void k_zero_inactive(idx_t N, const uint8_t* __restrict__ inactive, double* __restrict__ x) {
+    for (idx_t n = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; n < N; n += (idx_t)gridDim.x * blockDim.x)
+        if (inactive[n]) x[n] = 0.;
 }
 
 // ------------------------------------------------------------ vector kernels (PCG) ------
@@ -340,6 +369,7 @@ __global__ void k_cond_thermal(const Grid g, const double* __restrict__ T, const
         temp = __dadd_rn(temp, T[n + ((l & 1) ? g.ps[0] : 0) + ((l & 2) ? g.ps[1] : 0) + ((l & 4) ? g.ps[2] : 0)]);
     temp *= 0.125;
     const uint32_t m = mat[n];
+    if (m == PFEM_MAT_EXCLUDED) { cl[n] = 0.; cv[n] = 0.; return; }   // element outside the masked mesh
     cl[n] = table_at(tab_lat, m, nT, T0, dT, temp);
     cv[n] = table_at(tab_vert, m, nT, T0, dT, temp);
 }
@@ -363,7 +393,9 @@ __global__ void k_cond_shockley(const Grid g, const uint32_t* __restrict__ mat, 
     const idx_t n = i + g.sJ * j + g.sK * k;
     const uint32_t actn = junc ? junc[n] : 0u;
     double c0, c1;
-    if (actn) {
+    if (mat[n] == PFEM_MAT_EXCLUDED) {   // element outside the masked mesh
+        c0 = c1 = 0.;
+    } else if (actn) {
         const JunctionDev a = act[actn - 1];
         const idx_t col = a.offset + a.ld * pi[1] + pi[0];
         c0 = junc_cond[2 * col];

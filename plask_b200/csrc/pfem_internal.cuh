@@ -14,6 +14,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef PFEM_MAT_EXCLUDED
+#define PFEM_MAT_EXCLUDED 0xFFFFFFFFu   /* include/plaskfem_cuda.h: element outside the masked mesh */
+#endif
+
 namespace pfem {
 
 typedef long long idx_t;

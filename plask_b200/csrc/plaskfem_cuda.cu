@@ -47,6 +47,8 @@ struct pfem_ctx {
     double *aux0 = nullptr, *aux1 = nullptr, *aux2 = nullptr;
     uint32_t *mat = nullptr, *junc = nullptr;
     uint8_t *role = nullptr, *noheat = nullptr;
+    uint8_t* inactive = nullptr;   // masked mesh: nodes that touch no kept element (null unless elements are excluded)
+    bool has_excluded = false, source_set = false;
     // small arrays
     double* hbuf = nullptr;
     double *tab_lat = nullptr, *tab_vert = nullptr;
@@ -156,6 +158,7 @@ static void free_all(pfem_ctx* ctx) {
     ctx->fixed = nullptr; ctx->bc_node = nullptr; ctx->bc_val = nullptr; ctx->nbc = 0;
     ctx->cl = ctx->cv = ctx->Te = ctx->cur0 = ctx->cur1 = ctx->cur2 = ctx->aux0 = ctx->aux1 = ctx->aux2 = nullptr;
     ctx->mat = ctx->junc = nullptr; ctx->role = ctx->noheat = nullptr;
+    ctx->inactive = nullptr; ctx->has_excluded = false; ctx->source_set = false;
     ctx->hbuf = ctx->tab_lat = ctx->tab_vert = nullptr;
     ctx->act = nullptr; ctx->nact = 0; ctx->ncol = 0;
     ctx->junc_cond = ctx->beta_col = ctx->js_col = nullptr;
@@ -431,9 +434,20 @@ extern "C" int pfem_set_materials(pfem_ctx* ctx, const uint32_t* elem_mat, uint3
     NEED_MESH();
     if (!elem_mat || !c_lat || !c_vert) FAIL(PFEM_ERR_BAD_INPUT, "null material argument");
     if (nmat == 0 || nT < 2 || !(dT > 0.)) FAIL(PFEM_ERR_BAD_INPUT, "need nmat >= 1, nT >= 2, dT > 0");
-    for (idx_t e = 0; e < ctx->g.E; ++e)
+    bool excluded = false;
+    for (idx_t e = 0; e < ctx->g.E; ++e) {
+        if (elem_mat[e] == PFEM_MAT_EXCLUDED) { excluded = true; continue; }
         if (elem_mat[e] >= nmat) FAIL(PFEM_ERR_BAD_INPUT, "element %lld has material id %u >= nmat %u", (long long)e, elem_mat[e], nmat);
+    }
+    if (excluded && ctx->source_set)
+        FAIL(PFEM_ERR_STATE, "elements are excluded: call pfem_set_materials before pfem_set_source");
     TRY(upload_elem<uint32_t, 1>(ctx, elem_mat, ctx->mat, nullptr, nullptr));
+    ctx->has_excluded = excluded;
+    if (excluded) {   // masked mesh: mark the nodes that touch no kept element
+        if (!ctx->inactive) TRY(dev_alloc(ctx, &ctx->inactive, (size_t)ctx->g.NP, (size_t)ctx->g.G));
+        k_mark_inactive<<<node_grid(ctx->g), node_block(), 0, ctx->stream>>>(ctx->g, ctx->mat, ctx->inactive);
+        KCHECK(); LAUNCHED(1);
+    }
     size_t cnt = (size_t)nmat * nT;
     dev_release(ctx, &ctx->tab_lat);
     dev_release(ctx, &ctx->tab_vert);
@@ -521,6 +535,7 @@ static int ensure_elem_arrays(pfem_ctx* ctx, bool shockley) {
 extern "C" int pfem_set_source(pfem_ctx* ctx, const double* heat) {
     NEED_MESH();
     const Grid& g = ctx->g;
+    ctx->source_set = true;
     if (!heat) {
         CU(cudaMemsetAsync(ctx->f, 0, (size_t)g.NP * sizeof(double), ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
@@ -529,7 +544,7 @@ extern "C" int pfem_set_source(pfem_ctx* ctx, const double* heat) {
     TRY(ensure_elem_arrays(ctx, false));
     CU(cudaMemsetAsync(ctx->aux0 - g.G, 0, (size_t)(g.NP + 2 * g.G) * sizeof(double), ctx->stream));
     TRY(upload_elem<double, 1>(ctx, heat, ctx->aux0, nullptr, nullptr));
-    k_load_vector<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->aux0, ctx->f);
+    k_load_vector<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->aux0, ctx->has_excluded ? ctx->mat : nullptr, ctx->f);
     KCHECK(); LAUNCHED(1);
     CU(cudaStreamSynchronize(ctx->stream));
     return PFEM_OK;
@@ -976,6 +991,14 @@ extern "C" int pfem_set_conductivity(pfem_ctx* ctx, const double* cond) {
     return PFEM_OK;
 }
 
+// masked mesh: the field is pinned to 0 on the nodes that are not part of it
+static int mask_field(pfem_ctx* ctx) {
+    if (!ctx->has_excluded) return PFEM_OK;
+    k_zero_inactive<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(ctx->g.NP, ctx->inactive, ctx->x);
+    KCHECK(); LAUNCHED(1);
+    return PFEM_OK;
+}
+
 // ------------------------------------------------------------------------ PCG -----------
 
 __global__ void k_set_params(Scalars* sc, double tol2, int maxit, int bench, int surf) {
@@ -1081,6 +1104,7 @@ static int read_scalars(pfem_ctx* ctx) {
 static int pcg_prepare(pfem_ctx* ctx, const pfem_opts* o, int bench) {
     const Grid& g = ctx->g;
     if (!ctx->conds_valid) FAIL(PFEM_ERR_STATE, "conductivities have not been computed");
+    TRY(mask_field(ctx));
     double tol2 = bench ? -1. : o->lin_tol * o->lin_tol;
     if (!ctx->surf_iter_known) {             // convection terms on ANY rank: every rank runs k_surf_iter (it is collective)
         int any = ctx->surf.nnz > 0;
@@ -1195,6 +1219,7 @@ extern "C" int pfem_solve_thermal(pfem_ctx* ctx, const pfem_opts* o, pfem_stats*
     int loop = 0, conv = 1, iters = 0;
     long long total_iters = 0;
     double err = 0., toterr = 0., maxT = 0., relres = 0.;
+    TRY(mask_field(ctx));
     const int cap = o->loops > 0 ? o->loops : 100000;
     const idx_t own_off = g.sK * g.kown0, own_cnt = g.sK * (g.kown1 - g.kown0);
     do {
@@ -1236,6 +1261,7 @@ extern "C" int pfem_solve_shockley(pfem_ctx* ctx, const pfem_opts* o, pfem_stats
     TRY(ensure_elem_arrays(ctx, true));
     long long l0 = ctx->launches;
     Timer t(ctx->stream);
+    TRY(mask_field(ctx));
     TRY(pfem_update_conductivity_shockley(ctx));               // loadConductivity, electr3d.cpp:378
     const int noactive = (ctx->nact == 0);
     const double minj = 100e-7;                                 // :381
@@ -1287,6 +1313,7 @@ extern "C" int pfem_solve_shockley(pfem_ctx* ctx, const pfem_opts* o, pfem_stats
 extern "C" int pfem_get_field(pfem_ctx* ctx, double* x) {
     NEED_MESH();
     if (!x) FAIL(PFEM_ERR_BAD_INPUT, "null output");
+    TRY(mask_field(ctx));
     CU(download_nodes(ctx, x, ctx->x));
     CU(cudaStreamSynchronize(ctx->stream));
     return PFEM_OK;
@@ -1444,7 +1471,7 @@ extern "C" int pfem_transfer_heat(pfem_ctx* thermal, pfem_ctx* electrical) {
     TRY(ensure_elem_arrays(ctx, false));
     CU(cudaMemsetAsync(ctx->aux0 - g.G, 0, (size_t)(g.NP + 2 * g.G) * sizeof(double), ctx->stream));
     TRY(interp_to_elems(thermal, electrical, heat, true, ctx->aux0));
-    k_load_vector<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->aux0, ctx->f);
+    k_load_vector<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->aux0, ctx->has_excluded ? ctx->mat : nullptr, ctx->f);
     KCHECK(); LAUNCHED(1);
     CU(cudaStreamSynchronize(ctx->stream));
     return PFEM_OK;

@@ -41,6 +41,10 @@ class _FemSolver:
         self.algorithm = "cuda"
         self.iterative = IterativeParams()
         self.device = 0
+        # FemSolverWithMaskedMesh::empty_elements (fem_solver.hpp:152-189): 'include' keeps the full mesh (what the
+        # reference does for its iterative algorithm by default), 'exclude' drops the elements of EMPTY material
+        # (problem.empty) like the reference's Cholesky default does
+        self.empty_elements = "include"
         self.variant = 3            # 3 production (fused single-kernel iteration); 0/2 two-kernel; 1 simple reference kernels
         self._fem = None
         self._problem = None
@@ -69,6 +73,41 @@ class _FemSolver:
             self._fem.close()
         self._fem = None
         self.initialized = False
+
+    def _elem_materials(self):
+        """material id per element; elements outside the masked mesh are marked PFEM_MAT_EXCLUDED"""
+        p = self._problem
+        if self.empty_elements not in ("include", "exclude", "default"):
+            raise L.BadInput(f"{self.id}: empty_elements must be 'include', 'exclude' or 'default'")
+        if self.empty_elements != "exclude" or p.empty is None or not np.any(p.empty):
+            return p.elem_mat
+        m = np.array(p.elem_mat, dtype=np.uint32, copy=True)
+        m[np.asarray(p.empty) != 0] = L.MAT_EXCLUDED
+        return m
+
+    def _dirichlet(self):
+        """boundary conditions live on the masked mesh: a place holds no nodes outside it"""
+        p = self._problem
+        nodes, vals = np.asarray(p.bc_nodes), np.asarray(p.bc_values)
+        if self.empty_elements == "exclude" and p.empty is not None and np.any(p.empty):
+            keep = self.masked_nodes()[nodes.astype(np.int64)]
+            nodes, vals = nodes[keep], vals[keep]
+        return nodes, vals
+
+    def masked_nodes(self):
+        """bool [N]: nodes of the masked mesh (RectangularMaskedMesh3D keeps the nodes of the kept elements)"""
+        p = self._problem
+        keep = np.ones(p.E, dtype=bool) if (self.empty_elements != "exclude" or p.empty is None) else (np.asarray(p.empty) == 0)
+        n = p.n
+        k3 = keep[np.broadcast_to(p.elem_index_grid(), tuple(k - 1 for k in n))]
+        act = np.zeros(n, dtype=bool)
+        for d0 in (0, 1):
+            for d1 in (0, 1):
+                for d2 in (0, 1):
+                    act[d0:n[0] - 1 + d0, d1:n[1] - 1 + d1, d2:n[2] - 1 + d2] |= k3
+        out = np.zeros(p.N, dtype=bool)
+        out[np.broadcast_to(p.node_index_grid(), n).ravel()] = act.ravel()
+        return out
 
     def _setup_slab(self, f):
         """slab mode: tell the context which planes it owns and map the neighbours' memory (collective)"""
@@ -123,9 +162,9 @@ class Static3D(_FemSolver):
         f = self._fem = DeviceFem(self.device)
         f.set_mesh(p.axes, p.strides)
         self._setup_slab(f)
-        f.set_materials(p.elem_mat, p.T0, p.dT, p.tab_lat, p.tab_vert)
+        f.set_materials(self._elem_materials(), p.T0, p.dT, p.tab_lat, p.tab_vert)
         f.set_field(float(self.inittemp))               # temperatures.reset(size, inittemp), :79
-        f.set_dirichlet(p.bc_nodes, p.bc_values)
+        f.set_dirichlet(*self._dirichlet())
         f.set_boundary(self.heatflux_boundary, self.convection_boundary, self.radiation_boundary, self.boundary_verbatim)
         self.loopno = 0
         self.initialized = True
@@ -192,9 +231,9 @@ class Shockley3D(_FemSolver):
         f = self._fem = DeviceFem(self.device)
         f.set_mesh(p.axes, p.strides)
         self._setup_slab(f)
-        f.set_materials(p.elem_mat, p.T0, p.dT, p.tab_lat, p.tab_vert)
+        f.set_materials(self._elem_materials(), p.T0, p.dT, p.tab_lat, p.tab_vert)
         f.set_field(0.)                                  # potential.reset(size, 0.), electr3d.cpp:190
-        f.set_dirichlet(p.bc_nodes, p.bc_values)
+        f.set_dirichlet(*self._dirichlet())
         f.set_source(None)
         f.set_noheat(p.noheat)
         self._acts, self._ncol = setup_active(p)         # setupActiveRegions, :89-183

@@ -87,6 +87,25 @@ static int host_tests() {
     try { std::vector<size_t> far = {m.size()}; conv.add(m.size(), far, {1., 1.}); } catch (const BadInput&) { outside = true; }
     REQUIRE(outside);
 
+    // masked mesh numbering: keep the elements with i2 >= 2 or i0 < 2 -> nodes (i0 > 2, any i1, i2 < 2) drop out
+    {
+        auto inc = [](size_t i0, size_t, size_t i2) { return i2 >= 2 || i0 < 2; };
+        MaskedNumbering mn(m, inc);
+        size_t ne = 0, nn = 0;
+        for (size_t i0 = 0; i0 + 1 < 5; ++i0) for (size_t i1 = 0; i1 + 1 < 4; ++i1) for (size_t i2 = 0; i2 + 1 < m.n(2); ++i2) ne += inc(i0, i1, i2);
+        for (size_t i0 = 0; i0 < 5; ++i0) for (size_t i1 = 0; i1 < 4; ++i1) for (size_t i2 = 0; i2 < m.n(2); ++i2) nn += !(i0 > 2 && i2 < 2);
+        REQUIRE(mn.full_of_elem.size() == ne && mn.full_of_node.size() == nn);
+        REQUIRE(mn.node_of_full[m.node(4, 1, 0)] == MaskedNumbering::NONE && mn.node_of_full[m.node(2, 1, 0)] != MaskedNumbering::NONE);
+        for (size_t k = 1; k < mn.full_of_node.size(); ++k) REQUIRE(mn.full_of_node[k] > mn.full_of_node[k - 1]);   // full-mesh order
+        std::vector<uint32_t> ids = mn.mark_excluded(std::vector<uint32_t>(m.elements(), 7));
+        REQUIRE(ids[m.elem(3, 0, 0)] == PFEM_MAT_EXCLUDED && ids[m.elem(1, 0, 0)] == 7 && ids[m.elem(3, 0, 2)] == 7);
+        std::vector<double> full(m.size()), masked(nn), back(m.size());
+        for (size_t i = 0; i < full.size(); ++i) full[i] = 1. + (double)i;
+        mn.nodes_to_masked(full.data(), masked.data());
+        mn.nodes_to_full(masked.data(), back.data(), -1.);
+        REQUIRE(back[m.node(4, 1, 0)] == -1. && back[m.node(1, 1, 1)] == full[m.node(1, 1, 1)]);
+    }
+
     Tables t = sample_tables(2, [](uint32_t id, double T) { return std::make_pair(10. * (id + 1) * 300. / T, 5. * (id + 1)); }, 250., 0.5, 701);
     REQUIRE(t.lat.size() == 1402 && std::fabs(t.lat[701 + 100] - 20. * 300. / 300.) < 1e-12);
 

@@ -79,6 +79,7 @@ def shockley3d_reference_problem(order="optimal"):
     p.elem_mat = p.to_elem_order(mat, np.uint32)
     p.elem_junc = p.to_elem_order(is_j.astype(np.uint32), np.uint32)
     p.noheat = (p.elem_mat == 2).astype(np.uint8)
+    p.empty = p.noheat.copy()                       # air: Material::EMPTY, dropped by empty_elements='exclude'
     p.meta["eps"] = np.array([1., 12.9, 1.])[p.elem_mat]
     ng = np.broadcast_to(p.node_index_grid(), n)
     Xn, Yn = np.meshgrid(x, x, indexing="ij")

@@ -100,3 +100,27 @@ def test_shockley3d_conductivity():
     s.load_conductivity()
     expect = np.where(c["elem_junc"][:, None] > 0, np.array([0., 5.]), c["tables"].lat[c["elem_mat"], 0][:, None])
     assert np.array_equal(s.conds, expect)
+
+
+def test_shockley3d_analytic_excluded():
+    """shockley3d.py:71-73 (testComputationsExcluded): empty_elements='exclude' — the masked mesh drops the air
+    elements beside the contacts; same analytic current, capacitance and heat.  (This is also the default mesh of the
+    reference's Cholesky path, fem_solver.hpp:183-187.)"""
+    c = shockley3d_reference_case()
+    included = (c["elem_mat"] != 2).astype(np.uint8)
+    s = orc.Shockley3DOracle(c["mesh"], c["elem_mat"], c["tables"], c["nodes"], c["values"], elem_junc=c["elem_junc"],
+                             beta=10., js=1., maxerr=1e-3, algorithm="cholesky", noheat=c["noheat"], eps=c["eps"],
+                             included=included)
+    s.compute(1000)
+    A = s._matrix()
+    assert A.Nm == 764 and c["mesh"].N == 1100          # 4 x 2 x 42 corner-region nodes of the two contact layers drop out
+    S = 1e6
+    correct_current = 1e-9 * S * 1. * (np.exp(10.) - 1)
+    assert abs(s.get_total_current()) == pytest.approx(correct_current, abs=0.5e-3)
+    assert s.get_capacitance() == pytest.approx(8.854187817e-6 * 12.9 * S / 0.02, abs=0.5e-2)
+    assert s.get_total_heat() == pytest.approx(correct_current * 1., abs=0.5e-3)
+    # against the full mesh (air kept, sigma = 5.5e-15 S/m): same potential on the masked nodes
+    f = orc.Shockley3DOracle(c["mesh"], c["elem_mat"], c["tables"], c["nodes"], c["values"], elem_junc=c["elem_junc"],
+                             beta=10., js=1., maxerr=1e-3, algorithm="cholesky", noheat=c["noheat"], eps=c["eps"])
+    f.compute(len(s.history))
+    assert np.abs(s.potential - f.potential)[A.active].max() < 1e-9

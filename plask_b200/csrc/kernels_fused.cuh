@@ -50,14 +50,16 @@ struct FusedTile {
     static constexpr int CHALF = (CW * CH * 2 + 15) / 16 * 16;   // (sij, ui) then (uj, kk): conflict-free LDS.128
     static constexpr int LAYER = 2 * CHALF;
     static constexpr int NRED = 7;
-    static constexpr size_t smem_bytes(int ns, bool fused, int lk) {
-        return 128 + sizeof(double) * ((size_t)ns * (fused ? 6 : 4) * BOXP + 2 * PLANE + 2 * LAYER + 32 * NRED + 2 * (size_t)(lk + 2)) +
+    static constexpr size_t smem_bytes(int ns, int mode, int lk) {
+        return 128 + sizeof(double) * ((size_t)ns * (mode == 1 ? 6 : mode == 2 ? 5 : 4) * BOXP + 2 * PLANE + 2 * LAYER + 32 * NRED + 2 * (size_t)(lk + 2)) +
                16 * 8 + 16;
     }
 };
 
 
-template <int TJ, int RJ, int NS, int MINB, int VDIM, bool FUSED>
+// MODE 0: plain q = M A p (tests, pfem_apply);  1: the fused Jacobi-PCG iteration;  2: operator step of the line-Jacobi
+// iteration (kernels_line.cuh): boxes z, p, mask instead of r, q, p, D^-1 — p' = mask z + beta p, x' = x + alpha p, q' = M A p'.
+template <int TJ, int RJ, int NS, int MINB, int VDIM, int MODE>
 __global__ void __launch_bounds__(32 * (TJ / RJ), MINB)
 k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_q,
        const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_d,
@@ -68,9 +70,10 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
     constexpr int TI = T::TI, HX = T::HX, PW = T::PW, PH = T::PH, BOX = T::BOX, BOXP = T::BOXP, PWP = T::PWP;
     constexpr int PLANE = T::PLANE, CW = T::CW, CHALF = T::CHALF, LAYER = T::LAYER, NRED = T::NRED;
     constexpr int NT = TI * (TJ / RJ);
-    constexpr int NBN = FUSED ? 4 : 2;   // node boxes per stage: r q p d | p d
+    constexpr bool FUSED = MODE >= 1, LINE = MODE == 2;
+    constexpr int NBN = LINE ? 3 : FUSED ? 4 : 2;   // node boxes per stage: r q p d | z p mask | p d
     constexpr int NB = NBN + 2;          // + c_lat, c_vert
-    constexpr int B_P = FUSED ? 2 : 0, B_D = FUSED ? 3 : 1, B_CL = NBN, B_CV = NBN + 1;
+    constexpr int B_P = LINE ? 1 : FUSED ? 2 : 0, B_D = B_P + 1, B_CL = NBN, B_CV = NBN + 1;
     constexpr int NRING = 2 * PWP + 2 * TJ;     // halo ring of the p' plane
     constexpr int NERING = TI + TJ + 1;         // halo row/column of the coefficient layer
 
@@ -83,7 +86,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
     int* const sh_flag = reinterpret_cast<int*>(bars + 16);
     double* const sHK = reinterpret_cast<double*>(bars + 18);   // [lk+2] hK and [lk+2] 1/hK of the element layers of this chunk
 
-    if (FUSED && sc->done) return;
+    if (FUSED && sc->done == 1) return;   // done == 2 (line-Jacobi PCG): the pending x update is still to be applied
     const double alpha = FUSED ? sc->alpha : 0.;
     const double beta = FUSED ? sc->beta : 0.;
 
@@ -151,10 +154,8 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         uint64_t* bar = &bars[st];
         mbar_expect_tx(bar, (uint32_t)((NBN + (t > 0 ? 2 : 0)) * BOX * sizeof(double)));
         const int P = k0 - 1 + t;
-        if (FUSED) {
-            tma_load_3d(dst, &tm_r, bar, i0 - HX, j0 - 1, P);
-            tma_load_3d(dst + BOXP, &tm_q, bar, i0 - HX, j0 - 1, P);
-        }
+        if (FUSED) tma_load_3d(dst, &tm_r, bar, i0 - HX, j0 - 1, P);
+        if (FUSED && !LINE) tma_load_3d(dst + BOXP, &tm_q, bar, i0 - HX, j0 - 1, P);
         tma_load_3d(dst + B_P * BOXP, &tm_p, bar, i0 - HX, j0 - 1, P);
         tma_load_3d(dst + B_D * BOXP, &tm_d, bar, i0 - HX, j0 - 1, P);
         if (t > 0) {
@@ -235,8 +236,8 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
             const int ro = (jl0 + rr + 1) * PW + tx + HX;
             double pn;
             if (FUSED) {
-                const double r0 = raw[ro], q0 = raw[BOXP + ro], p0 = raw[B_P * BOXP + ro], dd = raw[B_D * BOXP + ro];
-                const double rn = fma(-alpha, q0, r0);
+                const double r0 = raw[ro], q0 = LINE ? 0. : raw[BOXP + ro], p0 = raw[B_P * BOXP + ro], dd = raw[B_D * BOXP + ro];
+                const double rn = LINE ? r0 : fma(-alpha, q0, r0);
                 const double z = dd * rn;
                 pn = fma(beta, p0, z);
                 zdb[rr] = z; zdb[RJ + rr] = dd;
@@ -244,7 +245,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
                     if (vj[rr]) {
                         const idx_t n = nown[rr];
                         const double xv = fma(alpha, p0, xcur[rr]);
-                        r_out[n] = rn;
+                        if (!LINE) r_out[n] = rn;   // line-Jacobi iteration: r' is written by the line kernel
                         p_out[n] = pn;
                         x[n] = xv;
                         if (slab) {
@@ -253,9 +254,11 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
                             if (push_lo && P == g.kown0) { po.r_lo[nip] = rn; po.p_lo[nip] = pn; }
                             if (push_hi && P == g.kown1 - 1) { po.r_hi[nip] = rn; po.p_hi[nip] = pn; }
                         }
-                        red[1] = fma(rn, z, red[1]);
-                        red[4] = fma(rn, rn, red[4]);
-                        red[5] = fma(z, z, red[5]);
+                        if (!LINE) {
+                            red[1] = fma(rn, z, red[1]);
+                            red[4] = fma(rn, rn, red[4]);
+                            red[5] = fma(z, z, red[5]);
+                        }
                         red[6] = fma(xv, xv, red[6]);
                     }
                 }
@@ -277,9 +280,9 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         if (ring_raw >= 0) {
             double pn;
             if (FUSED) {
-                const double r0 = raw[ring_raw], q0 = raw[BOXP + ring_raw], p0 = raw[B_P * BOXP + ring_raw],
+                const double r0 = raw[ring_raw], q0 = LINE ? 0. : raw[BOXP + ring_raw], p0 = raw[B_P * BOXP + ring_raw],
                              dd = raw[B_D * BOXP + ring_raw];
-                pn = fma(beta, p0, dd * fma(-alpha, q0, r0));
+                pn = fma(beta, p0, dd * (LINE ? r0 : fma(-alpha, q0, r0)));
             } else {
                 pn = raw[B_P * BOXP + ring_raw];
             }
@@ -360,7 +363,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
                             if (push_hi && Pa == g.kown1 - 1) po.q_hi[nip] = qv;
                         }
                         red[0] = fma(wa[yc][1], qv, red[0]);
-                        if (FUSED) {
+                        if (FUSED && !LINE) {
                             red[2] = fma(qv, zda[rr], red[2]);
                             red[3] = fma(qv * qv, da, red[3]);
                         }
@@ -399,7 +402,14 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
     if (!FUSED) return;
     if (grid_reduce<NRED, false>(red, partials, &sc->ticket[0], sRed, sh_flag, slab)) {
         if (sc->comm) rank_allreduce<NRED, false>(red, sc->comm, sRed);
-        if (tid == 0) {
+        if (tid == 0 && LINE) {
+            // line-Jacobi PCG: rho, beta and the stopping test belong to the line kernel; here only alpha = rho / p'.q'
+            const double pq = red[0];
+            sc->pq = pq; sc->xx = red[6];
+            if (sc->done == 2) sc->done = 1;
+            else if (!sc->bench && !(pq > 0.)) { sc->done = 1; sc->status = (pq == pq) ? -1 : -2; }
+            else sc->alpha = (pq > 0.) ? sc->rho / pq : 0.;
+        } else if (tid == 0) {
             const double pq = red[0], rho = red[1], qz = red[2], qdq = red[3], rr = red[4], zz = red[5], xx = red[6];
             const double rho_old = sc->rho;
             sc->rho_prev = rho_old; sc->rho = rho; sc->pq = pq; sc->rr = rr; sc->zz = zz; sc->xx = xx;
@@ -486,49 +496,44 @@ static inline FusedPlan make_fused_plan(const Grid& g, int sm_count, double* con
     return f;
 }
 
-template <int TJ, int RJ, int NS, int MINB, int VDIM, bool FUSED>
+template <int TJ, int RJ, int NS, int MINB, int VDIM, int MODE>
 static inline cudaError_t launch_fused_inst(const FusedPlan& f, const Grid& g, int par, double* r_out, double* q_out, double* p_out,
                                             double* x, Scalars* sc, double* partials, const PeerOut& po, cudaStream_t st) {
-    const size_t smem = FusedTile<TJ>::smem_bytes(NS, FUSED, f.lk);
+    const size_t smem = FusedTile<TJ>::smem_bytes(NS, MODE, f.lk);
     static size_t attr_done = 0;
     if (attr_done < smem) {
-        cudaError_t e = cudaFuncSetAttribute(k_fpcg<TJ, RJ, NS, MINB, VDIM, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done = smem;
     }
     dim3 grid(f.tilesI, f.tilesJ, f.chunksK), block(32, TJ / RJ, 1);
-    k_fpcg<TJ, RJ, NS, MINB, VDIM, FUSED><<<grid, block, smem, st>>>(f.m_r[par], f.m_q[par], f.m_p[par], f.m_d, f.m_cl, f.m_cv, g, f.lk,
+    k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE><<<grid, block, smem, st>>>(f.m_r[par], f.m_q[par], f.m_p[par], f.m_d, f.m_cl, f.m_cv, g, f.lk,
                                                                 r_out, q_out, p_out, x, sc, partials, po);
     return cudaGetLastError();
 }
 
-template <int TJ, int RJ, int NS, int MINB, bool FUSED>
+template <int TJ, int RJ, int NS, int MINB, int MODE>
 static inline cudaError_t launch_fused_vdim(const FusedPlan& f, const Grid& g, int par, double* r_out, double* q_out, double* p_out,
                                             double* x, Scalars* sc, double* partials, const PeerOut& po, cudaStream_t st) {
     switch (g.vdim) {
-        case 0: return launch_fused_inst<TJ, RJ, NS, MINB, 0, FUSED>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st);
-        case 1: return launch_fused_inst<TJ, RJ, NS, MINB, 1, FUSED>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st);
-        default: return launch_fused_inst<TJ, RJ, NS, MINB, 2, FUSED>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st);
+        case 0: return launch_fused_inst<TJ, RJ, NS, MINB, 0, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st);
+        case 1: return launch_fused_inst<TJ, RJ, NS, MINB, 1, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st);
+        default: return launch_fused_inst<TJ, RJ, NS, MINB, 2, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st);
     }
 }
 
 // par: which of the double buffers holds the INPUT vectors r, q, p (outputs go to the other one).
-// FUSED = false: plain q_out = M A p with p = p[par] (tests, pfem_apply).
-template <bool FUSED>
+// MODE 0: plain q_out = M A p with p = p[par] (tests, pfem_apply); 2: line-Jacobi operator step (f.m_r = z, f.m_d = mask).
+template <int MODE>
 static inline cudaError_t launch_fused_dispatch(const FusedPlan& f, const Grid& g, int par, double* r_out, double* q_out,
                                                 double* p_out, double* x, Scalars* sc, double* partials, const PeerOut& po,
                                                 cudaStream_t st) {
 #define PFEM_FUSED_CASE(TJ, RJ, NS, MINB) \
-    if (f.tj == TJ && f.rj == RJ && f.ns == NS && f.minb == MINB) return launch_fused_vdim<TJ, RJ, NS, MINB, FUSED>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st);
-    PFEM_FUSED_CASE(8, 1, 3, 2)
-    PFEM_FUSED_CASE(8, 1, 2, 2)
-    PFEM_FUSED_CASE(8, 2, 3, 2)
+    if (f.tj == TJ && f.rj == RJ && f.ns == NS && f.minb == MINB) return launch_fused_vdim<TJ, RJ, NS, MINB, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st);
+    PFEM_FUSED_CASE(8, 2, 2, 3)    // production tile (tools/tune_fused.py); the others are kept for PFEM_FUSED_TILE tuning runs
     PFEM_FUSED_CASE(8, 2, 2, 2)
-    PFEM_FUSED_CASE(8, 2, 2, 3)
-    PFEM_FUSED_CASE(16, 2, 2, 1)
+    PFEM_FUSED_CASE(8, 1, 2, 2)
     PFEM_FUSED_CASE(16, 2, 2, 2)
-    PFEM_FUSED_CASE(16, 1, 2, 1)
-    PFEM_FUSED_CASE(16, 4, 2, 1)
 #undef PFEM_FUSED_CASE
     return cudaErrorInvalidConfiguration;
 }

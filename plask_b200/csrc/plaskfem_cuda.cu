@@ -18,6 +18,7 @@
 #include "kernels_tma.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_surface.cuh"
+#include "kernels_line.cuh"
 
 using namespace pfem;
 
@@ -78,6 +79,11 @@ struct pfem_ctx {
     double* fS = nullptr;
     int surf_iter = 0;          // 1: k_surf_iter follows k_fpcg (convection terms exist on some rank)
     bool surf_iter_known = false;
+    // line-Jacobi preconditioner (pfem_opts::precond = 1): z, free-row mask, L D L^T factors of the vertical line blocks,
+    // a tiny zero buffer whose tensor map stands in for q (every box is out of range -> zero fill, no traffic)
+    double *lz = nullptr, *lmask = nullptr, *ll = nullptr, *ld = nullptr, *zero1 = nullptr;
+    FusedPlan line_plan;
+    int precond = 0;            // preconditioner of the PCG state prepared last
     long long launches = 0;
     double last_relres_pre = 0.;
     int sm_count = 148;
@@ -164,6 +170,7 @@ static void free_all(pfem_ctx* ctx) {
     ctx->junc_cond = ctx->beta_col = ctx->js_col = nullptr;
     ctx->partials = nullptr; ctx->partial_idx = nullptr; ctx->n_partials = 0;
     memset(&ctx->surf, 0, sizeof ctx->surf); ctx->fS = nullptr; ctx->surf_iter = 0; ctx->surf_iter_known = false;
+    ctx->lz = ctx->lmask = ctx->ll = ctx->ld = ctx->zero1 = nullptr; ctx->line_plan.valid = false; ctx->precond = 0;
     if (ctx->stage) { cudaFree(ctx->stage); ctx->stage = nullptr; ctx->stage_bytes = 0; }
     ctx->have_mesh = ctx->have_materials = ctx->have_junctions = ctx->conds_valid = false;
     ctx->noheat_set = false;
@@ -1001,8 +1008,56 @@ static int mask_field(pfem_ctx* ctx) {
 
 // ------------------------------------------------------------------------ PCG -----------
 
-__global__ void k_set_params(Scalars* sc, double tol2, int maxit, int bench, int surf) {
-    sc->tol2 = tol2; sc->maxit = maxit; sc->bench = bench; sc->neg_diag = 0; sc->surf = surf;
+__global__ void k_set_params(Scalars* sc, double tol2, int maxit, int bench, int surf, int line) {
+    sc->tol2 = tol2; sc->maxit = maxit; sc->bench = bench; sc->neg_diag = 0; sc->surf = surf; sc->line = line;
+}
+
+// line-Jacobi preconditioner: arrays and the tensor maps of its operator step (k_fpcg reading z for r, zeros for q,
+// the free-row mask for D^-1)
+static int ensure_line(pfem_ctx* ctx) {
+    if (ctx->line_plan.valid) return PFEM_OK;
+    const Grid& g = ctx->g;
+    const size_t N = (size_t)g.NP, G = (size_t)g.G;
+    if (!ctx->lz) {
+        TRY(dev_alloc(ctx, &ctx->lz, N, G));
+        TRY(dev_alloc(ctx, &ctx->lmask, N, G));
+        TRY(dev_alloc(ctx, &ctx->ll, N, G));
+        TRY(dev_alloc(ctx, &ctx->ld, N, G));
+    }
+    double* const zz[2] = {ctx->lz, ctx->lz};
+    double* const qq[2] = {ctx->q, ctx->q2};
+    double* const pp[2] = {ctx->p, ctx->p2};
+    FusedPlan f = make_fused_plan(g, ctx->sm_count, zz, qq, pp, ctx->lmask, ctx->cl, ctx->cv);
+    if (!f.valid) FAIL(PFEM_ERR_STATE, "line preconditioner: %s", f.why);
+    ctx->line_plan = f;
+    return PFEM_OK;
+}
+
+static inline int line_seg(const Grid& g) {   // nodes per lane of the I-line kernel
+    for (int s = 2; s <= 16; s *= 2) if (32 * s >= g.nI) return s;
+    return 0;
+}
+
+// z = M^-1 (r - alpha q) for the line-Jacobi preconditioner; mode 1: only b.M^-1 b -> sc->bz
+static int launch_line_solve(pfem_ctx* ctx, const double* r_in, const double* q_in, double* r_out, int mode) {
+    const Grid& g = ctx->g;
+    if (g.vdim == 0) {
+        const idx_t rows = (idx_t)g.nJ * (g.kown1 - g.kown0);
+        int blocks = (int)std::min<idx_t>((rows + 7) / 8, (idx_t)ctx->sm_count * 16);
+        if (blocks < 1) blocks = 1;
+#define PFEM_LINE_CASE(S) case S: k_line_I<S><<<blocks, 256, 0, ctx->stream>>>(g, r_in, q_in, ctx->ll, ctx->ld, r_out, ctx->lz, ctx->d_sc, ctx->partials, mode); break;
+        switch (line_seg(g)) {
+            PFEM_LINE_CASE(2) PFEM_LINE_CASE(4) PFEM_LINE_CASE(8) PFEM_LINE_CASE(16)
+            default: FAIL(PFEM_ERR_BAD_INPUT, "line preconditioner along the minor axis handles up to 512 nodes per line");
+        }
+#undef PFEM_LINE_CASE
+    } else {
+        const idx_t lines = (idx_t)g.nI * (g.vdim == 1 ? g.nK : g.nJ);
+        int blocks = (int)std::min<idx_t>((lines + 127) / 128, (idx_t)ctx->sm_count * 16);
+        k_line_strided<<<blocks, 128, 0, ctx->stream>>>(g, r_in, q_in, ctx->ll, ctx->ld, r_out, ctx->lz, ctx->d_sc, ctx->partials, mode);
+    }
+    KCHECK(); LAUNCHED(1);
+    return PFEM_OK;
 }
 __global__ void k_force_running(Scalars* sc) { sc->done = 0; sc->status = 0; }
 
@@ -1037,12 +1092,25 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
     double* pout = parity ? ctx->p : ctx->p2;
     const double* pnew = (variant == 1) ? ctx->p : pout;
     if (ev) cudaEventRecord(ev[0], ctx->stream);
+    if (variant == 3 && ctx->precond == 1) {
+        // line-Jacobi PCG: line solve (r in place, z) then the operator step of k_fpcg with z for r and zeros for q
+        double* const qq[2] = {ctx->q, ctx->q2};
+        double* const pp[2] = {ctx->p, ctx->p2};
+        launch_line_solve(ctx, ctx->r, qq[parity], ctx->r, 0);
+        if (ev) cudaEventRecord(ev[1], ctx->stream);
+        PeerOut none;
+        memset(&none, 0, sizeof none);
+        launch_fused_dispatch<2>(ctx->line_plan, g, parity, nullptr, qq[1 - parity], pp[1 - parity], ctx->x, ctx->d_sc, ctx->partials,
+                                    none, ctx->stream);
+        if (ev) cudaEventRecord(ev[2], ctx->stream);
+        return 2;
+    }
     if (variant == 3) {
         // the whole iteration in one kernel: inputs r,q,p[parity] -> outputs r,q,p[1-parity], x in place
         double* const rr[2] = {ctx->r, ctx->r2};
         double* const qq[2] = {ctx->q, ctx->q2};
         double* const pp[2] = {ctx->p, ctx->p2};
-        launch_fused_dispatch<true>(ctx->fused, g, parity, rr[1 - parity], qq[1 - parity], pp[1 - parity], ctx->x, ctx->d_sc,
+        launch_fused_dispatch<1>(ctx->fused, g, parity, rr[1 - parity], qq[1 - parity], pp[1 - parity], ctx->x, ctx->d_sc,
                                     ctx->partials, peer_out(ctx, 1 - parity), ctx->stream);
         if (ev) cudaEventRecord(ev[1], ctx->stream);
         if (ctx->surf_iter) {   // q' += S p' on the boundary rows, then the alpha / beta step
@@ -1075,7 +1143,7 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
     return launched;
 }
 
-static int kernels_per_iteration(const pfem_ctx* ctx, int variant) { return variant == 1 ? 3 : (variant == 3 ? 1 + ctx->surf_iter : 2); }  // variants 0 (TMA) and 2 (LDG tiled) fuse the p-update
+static int kernels_per_iteration(const pfem_ctx* ctx, int variant) { return variant == 1 ? 3 : (variant == 3 ? (ctx->precond == 1 ? 2 : 1 + ctx->surf_iter) : 2); }  // variants 0 (TMA) and 2 (LDG tiled) fuse the p-update
 
 static int build_graph(pfem_ctx* ctx, int batch, int variant, int precond) {
     if (ctx->graph && ctx->graph_batch == batch && ctx->graph_variant == variant && ctx->graph_precond == precond &&
@@ -1113,7 +1181,12 @@ static int pcg_prepare(pfem_ctx* ctx, const pfem_opts* o, int bench) {
         ctx->surf_iter_known = true;
     }
     if (ctx->surf_iter && o->variant != 3) FAIL(PFEM_ERR_BAD_INPUT, "convection boundary terms run with the fused PCG kernel only (variant 3)");
-    k_set_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, tol2, o->maxit, bench, ctx->surf_iter);
+    if (o->precond == 1) {
+        if (ctx->surf_iter) FAIL(PFEM_ERR_BAD_INPUT, "the line preconditioner does not handle convection boundary terms yet");
+        TRY(ensure_line(ctx));
+    }
+    ctx->precond = o->precond;
+    k_set_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, tol2, o->maxit, bench, ctx->surf_iter, o->precond == 1);
     LAUNCHED(1);
     TRY(launch_diag(ctx));
     TRY(halo_sync(ctx, SA_DINV));            // slab mode: the diagonal of a halo plane needs the neighbour's elements
@@ -1125,6 +1198,12 @@ static int pcg_prepare(pfem_ctx* ctx, const pfem_opts* o, int bench) {
     const double* feff = nullptr;
     TRY(surf_rhs(ctx, ctx->q, &feff));
     TRY(launch_apply_simple<2>(ctx, ctx->q, ctx->p, feff));
+    if (o->precond == 1) {   // factors of the line blocks, then ||b_free|| in the metric of this preconditioner
+        k_line_factor<<<(unsigned)((g.N / (g.vdim == 0 ? g.nI : g.vdim == 1 ? g.nJ : g.nK) + 127) / 128), 128, 0, ctx->stream>>>(
+            g, ctx->cl, ctx->cv, ctx->dinv, ctx->ll, ctx->ld, ctx->lmask, ctx->d_sc);
+        KCHECK(); LAUNCHED(1);
+        TRY(launch_line_solve(ctx, ctx->p, nullptr, nullptr, 1));
+    }
     // r0 = M (f - A x)
     TRY(surf_rhs(ctx, ctx->x, &feff));
     TRY(launch_apply_simple<1>(ctx, ctx->x, ctx->r, feff));
@@ -1170,7 +1249,9 @@ static int check_opts(pfem_ctx* ctx, const pfem_opts* o) {
     if (!o) FAIL(PFEM_ERR_BAD_INPUT, "null options");
     if (o->maxit <= 0) FAIL(PFEM_ERR_BAD_INPUT, "maxit must be positive");
     if (!(o->lin_tol > 0.)) FAIL(PFEM_ERR_BAD_INPUT, "lin_tol must be positive");
-    if (o->precond != 0) FAIL(PFEM_ERR_BAD_INPUT, "preconditioner %d is not implemented", o->precond);
+    if (o->precond != 0 && o->precond != 1) FAIL(PFEM_ERR_BAD_INPUT, "preconditioner %d is not implemented (0 = Jacobi, 1 = line-Jacobi)", o->precond);
+    if (o->precond == 1 && o->variant != 3) FAIL(PFEM_ERR_BAD_INPUT, "the line preconditioner runs with kernel variant 3 only");
+    if (o->precond == 1 && ctx->nranks > 1) FAIL(PFEM_ERR_BAD_INPUT, "the line preconditioner is not available in slab mode yet");
     if (o->variant < 0 || o->variant > 3) FAIL(PFEM_ERR_BAD_INPUT, "unknown kernel variant %d", o->variant);
     if (o->variant == 3 && !ctx->fused.valid) FAIL(PFEM_ERR_STATE, "fused PCG kernel unavailable: %s", ctx->fused.why);
     if (ctx->nranks > 1 && o->variant != 3) FAIL(PFEM_ERR_BAD_INPUT, "slab mode runs the fused PCG kernel only (variant 3)");
@@ -1500,7 +1581,7 @@ extern "C" int pfem_apply(pfem_ctx* ctx, const double* p, double* q, int variant
         if (!ctx->fused.valid) FAIL(PFEM_ERR_STATE, "fused PCG kernel unavailable: %s", ctx->fused.why);
         PeerOut none;
         memset(&none, 0, sizeof none);
-        CU(launch_fused_dispatch<false>(ctx->fused, g, 0, nullptr, ctx->q, nullptr, nullptr, nullptr, nullptr, none, ctx->stream));
+        CU(launch_fused_dispatch<0>(ctx->fused, g, 0, nullptr, ctx->q, nullptr, nullptr, nullptr, nullptr, none, ctx->stream));
         LAUNCHED(1);
     } else if (variant == 0) {
         if (!ctx->tma.valid) FAIL(PFEM_ERR_STATE, "TMA operator kernel unavailable: %s", ctx->tma.why);
@@ -1595,7 +1676,7 @@ extern "C" int pfem_bench_pcg(pfem_ctx* ctx, const pfem_opts* o, int iters, int 
         t_total = t.stop();
     }
     TRY(read_scalars(ctx));
-    k_set_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, o->lin_tol * o->lin_tol, o->maxit, 0, ctx->surf_iter);
+    k_set_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, o->lin_tol * o->lin_tol, o->maxit, 0, ctx->surf_iter, 0);
     CU(cudaStreamSynchronize(ctx->stream));
     if (ctx->h_sc->iter != iters) FAIL(PFEM_ERR_CUDA, "benchmark ran %d iterations instead of %d", ctx->h_sc->iter, iters);
     if (ms) *ms = t_total;

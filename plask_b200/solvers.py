@@ -121,9 +121,10 @@ class _FemSolver:
         if self.algorithm != "cuda":
             raise L.BadInput(f"{self.id}: algorithm '{self.algorithm}' is not provided by plask_b200 "
                              "(cholesky/gauss/iterative live in the reference); use 'cuda'")
-        pre = {"jac": 0}.get(self.iterative.preconditioner)
+        # NSPCG names (iterative_matrix.hpp:27-46): 'jac' point Jacobi, 'ljac' line Jacobi (here: lines along the vertical axis)
+        pre = {"jac": 0, "ljac": 1}.get(self.iterative.preconditioner)
         if pre is None or self.iterative.accelerator != "cg":
-            raise L.BadInput(f"{self.id}: the CUDA algorithm implements accelerator 'cg' with preconditioner 'jac'")
+            raise L.BadInput(f"{self.id}: the CUDA algorithm implements accelerator 'cg' with preconditioner 'jac' or 'ljac'")
         return dict(maxit=int(self.iterative.maxit), lin_tol=float(self.iterative.maxerr), precond=pre,
                     outer_tol=float(outer_tol), loops=int(loops), variant=int(self.variant))
 

@@ -1,0 +1,100 @@
+"""Line-Jacobi preconditioner (pfem_opts::precond = 1, NSPCG's 'ljac'; kernels_line.cuh): same solutions as the
+oracle's Cholesky to the north-star tolerances, for vertical lines along the minor (I), medium (J) and major (K)
+index axis, with fewer PCG iterations than point Jacobi on layered meshes."""
+import numpy as np
+import pytest
+
+from helpers import oracle_shockley, oracle_thermal, random_problem
+from plask_b200 import configs as cf
+from plask_b200.fem import DeviceFem
+from plask_b200.solvers import Shockley3D, Static3D
+
+pytestmark = pytest.mark.gpu
+
+
+def _thermal(p, pre, tol=1e-11):
+    s = Static3D("line")
+    s.problem = p
+    s.iterative.preconditioner = pre
+    s.iterative.maxerr = tol
+    s.iterative.maxit = 100000
+    return s
+
+
+@pytest.mark.parametrize("order", ["012", "021", "102", "120", "201", "210"])
+def test_config_B_small_line_vs_cholesky(order):
+    p = cf.config_B((18, 20, 44), order=order)
+    o = oracle_thermal(p, algorithm="cholesky")
+    o.compute(0)
+    s = _thermal(p, "ljac")
+    s.compute(0)
+    assert s.stats["outer_loops"] == len(o.history)
+    dT = np.abs(s.outTemperature() - o.temperatures).max()
+    assert dT <= 1e-3, dT
+    assert s.iterative.converged and s.iterative.err <= 1e-8
+    j = _thermal(p, "jac")
+    j.compute(0)
+    assert np.abs(s.outTemperature() - j.outTemperature()).max() <= 1e-6
+    assert s.stats["lin_iters"] < 0.5 * j.stats["lin_iters"], (s.stats["lin_iters"], j.stats["lin_iters"])
+    s.invalidate()
+    j.invalidate()
+
+
+@pytest.mark.parametrize("n,order", [((7, 9, 11), "012"), ((34, 5, 19), "210"), ((3, 3, 3), "012"), ((2, 2, 2), "120"),
+                                     ((70, 6, 5), "012"), ((5, 6, 70), "012"), ((5, 6, 130), "012"), ((4, 5, 300), "012")])
+def test_random_problem_line_linear_solve(n, order):
+    """random conductivities and Dirichlet sets, line lengths that straddle the lane segments of the warp-per-row kernel"""
+    p = random_problem(n, order, nd_frac=0.1)
+    rng = np.random.default_rng(3)
+    T = rng.uniform(290., 350., size=p.N)
+    o = oracle_thermal(p, algorithm="cholesky")
+    o.temperatures[:] = T
+    A, B = o._matrix(), np.zeros(p.N)
+    o.set_matrix(A, B)
+    x_ref = T.copy()
+    A.solve(B, x_ref)
+    f = DeviceFem(0)
+    f.set_mesh(p.axes, p.strides)
+    f.set_materials(p.elem_mat, p.T0, p.dT, p.tab_lat, p.tab_vert)
+    f.set_field(T)
+    f.set_dirichlet(p.bc_nodes, p.bc_values)
+    f.set_source(p.heat)
+    f.update_conductivity_thermal()
+    rc, st = f.solve_linear(lin_tol=1e-13, maxit=50000, precond=1)
+    assert rc == 0 and st["converged"]
+    x = f.get_field()
+    assert np.abs(x - x_ref).max() <= 1e-8 * np.abs(x_ref).max(), np.abs(x - x_ref).max()
+    f.close()
+
+
+def test_config_C_small_line_vs_cholesky():
+    p = cf.config_C((20, 22, 52))
+    LOOPS = 8
+    o = oracle_shockley(p, algorithm="cholesky")
+    o.compute(LOOPS)
+    e = Shockley3D("C")
+    e.problem = p
+    e.beta, e.js, e.maxerr = p.beta, p.js, p.maxerr
+    e.iterative.preconditioner = "ljac"
+    e.iterative.maxerr = 1e-13
+    e.iterative.maxit = 200000
+    e.compute(LOOPS)
+    dV = np.abs(e.outVoltage() - o.potential).max()
+    assert dV <= 1e-6, dV
+    e.invalidate()
+
+
+def test_warm_start_converged_and_maxit():
+    p = cf.config_B(20)
+    s = _thermal(p, "ljac", tol=1e-9)
+    s.compute(0)
+    n1 = s.stats["lin_iters"]
+    s.compute(1)                      # one more loop from the converged field: warm start, far fewer iterations
+    assert s.stats["lin_iters"] < n1 // 2
+    s.invalidate()
+    s = _thermal(p, "ljac", tol=1e-14)
+    s.iterative.maxit = 5
+    s.iterative.noconv = "continue"
+    s.compute(1)
+    assert not s.iterative.converged and s.iterative.iters == 5
+    s.invalidate()

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--boundary", action="store_true")
     ap.add_argument("--lin-tol", type=float, default=1e-8)
     ap.add_argument("--meta-loops", type=int, default=100)
+    ap.add_argument("--precond", default="jac", help="jac | ljac (line-Jacobi along the vertical axis)")
+    ap.add_argument("--order", default="optimal")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -51,12 +53,13 @@ def main():
         s.device = local
         s.iterative.maxerr = a.lin_tol
         s.iterative.maxit = 200000
+        s.iterative.preconditioner = a.precond
 
-    out = dict(config=a.config, n_gpus=world)
+    out = dict(config=a.config, n_gpus=world, preconditioner=a.precond)
     t0 = time.perf_counter()
     if a.config == "C":
         n = tuple(a.n) if a.n else (192, 192, 400)
-        p = cf.config_C(n)
+        p = cf.config_C(n, order=a.order)
         e = Shockley3D("C")
         tune(e)
         e.problem = p
@@ -70,7 +73,7 @@ def main():
                    max_j_kAcm2=st["maxval"], total_current_mA=I, dof_iter_per_s=p.N * st["lin_iters"] / (st["t_solve_ms"] * 1e-3))
     elif a.config == "B":
         n = tuple(a.n) if a.n else (256, 256, 256)
-        p = cf.config_B(n)
+        p = cf.config_B(n, order=a.order)
         s = Static3D("B")
         tune(s)
         s.problem = p

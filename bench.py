@@ -347,6 +347,24 @@ def run_ours(args):
         except Exception as ex:  # keep the bench line even if the long solve fails
             tts = {"error": str(ex)}
         s.invalidate()
+        # the same solve with the line-Jacobi preconditioner (two kernels per iteration, single device only)
+        if not slab and "error" not in tts:
+            s2 = Static3D("bench-ljac")
+            s2.device = local
+            s2.problem = p
+            s2.iterative.preconditioner = "ljac"
+            s2.iterative.maxerr = args.lin_tol
+            s2.iterative.maxit = args.tts_maxit
+            t0 = time.perf_counter()
+            try:
+                s2.compute(args.tts_loops)
+                st_ = s2.stats
+                tts["line_jacobi"] = {"seconds": time.perf_counter() - t0, "outer_loops": st_["outer_loops"],
+                                      "pcg_iterations": st_["lin_iters"], "converged": st_["converged"],
+                                      "lin_relres": st_["lin_relres"], "maxT": st_["maxval"], "device_ms": st_["t_solve_ms"]}
+            except Exception as ex:
+                tts["line_jacobi"] = {"error": str(ex)}
+            s2.invalidate()
 
     cpu = None
     if rank == 0 and world == 1 and args.cpu_baseline:

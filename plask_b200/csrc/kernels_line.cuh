@@ -133,20 +133,28 @@ k_line_I(const Grid g, const double* __restrict__ r_in, const double* __restrict
         const int j = (int)(row % g.nJ), k = g.kown0 + (int)(row / g.nJ);
         const idx_t base = g.sJ * j + g.sK * (idx_t)k;
         double rp[SEG], l[SEG + 1], w[SEG];
-        // r' = r - alpha q: coalesced, stored right away, then transposed into segments
+        // all global loads of the row first (coalesced, in flight together); r' = r - alpha q is stored right away
+        double2 vr[SEG / 2], vl[SEG / 2], vd[SEG / 2];
 #pragma unroll
         for (int c = 0; c < SEG / 2; ++c) {
             const int i = 2 * lane + 64 * c;
-            double2 v = make_double2(0., 0.);
+            vr[c] = vl[c] = vd[c] = make_double2(0., 0.);
             if (i < g.sJ) {   // pads inside the pitch hold zeros
-                v = *reinterpret_cast<const double2*>(r_in + base + i);
+                vr[c] = *reinterpret_cast<const double2*>(r_in + base + i);
+                vl[c] = *reinterpret_cast<const double2*>(ll + base + i);
+                vd[c] = *reinterpret_cast<const double2*>(ld + base + i);
                 if (mode == 0) {
                     const double2 qv = *reinterpret_cast<const double2*>(q_in + base + i);
-                    v.x = fma(-alpha, qv.x, v.x); v.y = fma(-alpha, qv.y, v.y);
-                    *reinterpret_cast<double2*>(r_out + base + i) = v;
+                    vr[c].x = fma(-alpha, qv.x, vr[c].x); vr[c].y = fma(-alpha, qv.y, vr[c].y);
+                    *reinterpret_cast<double2*>(r_out + base + i) = vr[c];
                 }
             }
-            tb[i + i / SEG] = v.x; tb[i + 1 + (i + 1) / SEG] = v.y;
+        }
+        // transposition into the segment layout, one array at a time through the padded row buffer
+#pragma unroll
+        for (int c = 0; c < SEG / 2; ++c) {
+            const int i = 2 * lane + 64 * c;
+            tb[i + i / SEG] = vr[c].x; tb[i + 1 + (i + 1) / SEG] = vr[c].y;
         }
         __syncwarp();
 #pragma unroll
@@ -155,8 +163,7 @@ k_line_I(const Grid g, const double* __restrict__ r_in, const double* __restrict
 #pragma unroll
         for (int c = 0; c < SEG / 2; ++c) {
             const int i = 2 * lane + 64 * c;
-            const double2 v = (i < g.sJ) ? *reinterpret_cast<const double2*>(ll + base + i) : make_double2(0., 0.);
-            tb[i + i / SEG] = v.x; tb[i + 1 + (i + 1) / SEG] = v.y;
+            tb[i + i / SEG] = vl[c].x; tb[i + 1 + (i + 1) / SEG] = vl[c].y;
         }
         __syncwarp();
 #pragma unroll
@@ -166,8 +173,7 @@ k_line_I(const Grid g, const double* __restrict__ r_in, const double* __restrict
 #pragma unroll
         for (int c = 0; c < SEG / 2; ++c) {
             const int i = 2 * lane + 64 * c;
-            const double2 v = (i < g.sJ) ? *reinterpret_cast<const double2*>(ld + base + i) : make_double2(0., 0.);
-            tb[i + i / SEG] = v.x; tb[i + 1 + (i + 1) / SEG] = v.y;
+            tb[i + i / SEG] = vd[c].x; tb[i + 1 + (i + 1) / SEG] = vd[c].y;
         }
         __syncwarp();
 #pragma unroll

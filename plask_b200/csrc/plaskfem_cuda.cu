@@ -1043,7 +1043,11 @@ static int launch_line_solve(pfem_ctx* ctx, const double* r_in, const double* q_
     const Grid& g = ctx->g;
     if (g.vdim == 0) {
         const idx_t rows = (idx_t)g.nJ * (g.kown1 - g.kown0);
-        int blocks = (int)std::min<idx_t>((rows + 7) / 8, (idx_t)ctx->sm_count * 16);
+        // balanced: every warp gets the same number of rows (8 warps per block)
+        static const int cap_env = getenv("PFEM_LINE_BLOCKS") ? atoi(getenv("PFEM_LINE_BLOCKS")) : 0;
+        const idx_t cap_warps = (idx_t)(cap_env > 0 ? cap_env : ctx->sm_count * 2) * 8;   // one resident wave (measured best)
+        const idx_t rpw = (rows + cap_warps - 1) / cap_warps;
+        int blocks = (int)(((rows + rpw - 1) / rpw + 7) / 8);
         if (blocks < 1) blocks = 1;
 #define PFEM_LINE_CASE(S) case S: k_line_I<S><<<blocks, 256, 0, ctx->stream>>>(g, r_in, q_in, ctx->ll, ctx->ld, r_out, ctx->lz, ctx->d_sc, ctx->partials, mode); break;
         switch (line_seg(g)) {

@@ -407,6 +407,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
             const double pq = red[0];
             sc->pq = pq; sc->xx = red[6];
             if (sc->done == 2) sc->done = 1;
+            else if (sc->surf) {}   // convection terms: k_surf_iter adds p'.S p' and computes alpha
             else if (!sc->bench && !(pq > 0.)) { sc->done = 1; sc->status = (pq == pq) ? -1 : -2; }
             else sc->alpha = (pq > 0.) ? sc->rho / pq : 0.;
         } else if (tid == 0) {

@@ -99,6 +99,7 @@ k_surf_iter(const Surf s, const Grid g, const double* __restrict__ p, double* __
             const double pq = sc->pq + c[0], qz = sc->qz + c[1], qdq = sc->qdq + c[2], rho = sc->rho;
             sc->pq = pq;
             if (!sc->bench && !(pq > 0.)) { sc->done = 1; sc->status = (pq == pq) ? -1 : -2; }
+            else if (sc->line) sc->alpha = (pq > 0.) ? rho / pq : 0.;   // line-Jacobi PCG: beta belongs to the line kernel
             else {
                 const double al = (pq > 0.) ? rho / pq : 0.;
                 const double rho_next = fma(al * al, qdq, fma(-2. * al, qz, rho));

@@ -1106,8 +1106,11 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
         memset(&none, 0, sizeof none);
         launch_fused_dispatch<2>(ctx->line_plan, g, parity, nullptr, qq[1 - parity], pp[1 - parity], ctx->x, ctx->d_sc, ctx->partials,
                                     none, ctx->stream);
+        if (ctx->surf_iter)   // q' += S p' on the boundary rows, alpha from the completed p'.q'
+            k_surf_iter<<<surf_blocks(ctx), 256, 0, ctx->stream>>>(ctx->surf, g, pp[1 - parity], qq[1 - parity], ctx->r, ctx->dinv, ctx->d_sc,
+                                                                    ctx->partials, none);
         if (ev) cudaEventRecord(ev[2], ctx->stream);
-        return 2;
+        return 2 + ctx->surf_iter;
     }
     if (variant == 3) {
         // the whole iteration in one kernel: inputs r,q,p[parity] -> outputs r,q,p[1-parity], x in place
@@ -1147,7 +1150,7 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
     return launched;
 }
 
-static int kernels_per_iteration(const pfem_ctx* ctx, int variant) { return variant == 1 ? 3 : (variant == 3 ? (ctx->precond == 1 ? 2 : 1 + ctx->surf_iter) : 2); }  // variants 0 (TMA) and 2 (LDG tiled) fuse the p-update
+static int kernels_per_iteration(const pfem_ctx* ctx, int variant) { return variant == 1 ? 3 : (variant == 3 ? (ctx->precond == 1 ? 2 + ctx->surf_iter : 1 + ctx->surf_iter) : 2); }  // variants 0 (TMA) and 2 (LDG tiled) fuse the p-update
 
 static int build_graph(pfem_ctx* ctx, int batch, int variant, int precond) {
     if (ctx->graph && ctx->graph_batch == batch && ctx->graph_variant == variant && ctx->graph_precond == precond &&
@@ -1186,7 +1189,6 @@ static int pcg_prepare(pfem_ctx* ctx, const pfem_opts* o, int bench) {
     }
     if (ctx->surf_iter && o->variant != 3) FAIL(PFEM_ERR_BAD_INPUT, "convection boundary terms run with the fused PCG kernel only (variant 3)");
     if (o->precond == 1) {
-        if (ctx->surf_iter) FAIL(PFEM_ERR_BAD_INPUT, "the line preconditioner does not handle convection boundary terms yet");
         TRY(ensure_line(ctx));
     }
     ctx->precond = o->precond;

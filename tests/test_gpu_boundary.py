@@ -77,15 +77,17 @@ def test_operator_rhs_diag_with_boundary_terms(order, quirk):
     f.close()
 
 
+@pytest.mark.parametrize("precond", ["jac", "ljac"])
 @pytest.mark.parametrize("quirk", [True, False])
 @pytest.mark.parametrize("order", ["012", "210"])
-def test_nonlinear_solve_vs_cholesky(order, quirk):
+def test_nonlinear_solve_vs_cholesky(order, quirk, precond):
     p = cf.config_B((14, 16, 40), order=order)
     conds = _conditions(p)
     o = _oracle(p, conds, quirk)
     o.compute(0)
     s = Static3D("bc")
     s.problem = p
+    s.iterative.preconditioner = precond
     s.heatflux_boundary, s.convection_boundary, s.radiation_boundary = conds["heatflux"], conds["convection"], conds["radiation"]
     s.boundary_verbatim = quirk
     s.iterative.maxerr = 1e-11
@@ -105,11 +107,12 @@ def test_convection_only_no_dirichlet():
     p.bc_nodes = np.zeros(0, dtype=np.uintp)
     p.bc_values = np.zeros(0)
     conds = dict(convection=[(face_nodes(p, 2, 0), 2.0e5, 300.), (face_nodes(p, 0, -1), 5.0e4, 320.)])
-    for quirk in (True, False):
+    for quirk, precond in ((True, "jac"), (False, "jac"), (False, "ljac")):
         o = _oracle(p, conds, quirk)
         o.compute(0)
         s = Static3D("conv")
         s.problem = p
+        s.iterative.preconditioner = precond
         s.convection_boundary = conds["convection"]
         s.boundary_verbatim = quirk
         s.iterative.maxerr = 1e-11

@@ -289,6 +289,9 @@ struct IterParams {
     bool converged = true;
     int iters = 0;
     double err = 0.;
+    // iter_params.preconditioner (:27-46): the two NSPCG choices the CUDA algorithm provides
+    enum Preconditioner { PRECOND_JAC = 0, PRECOND_LJAC = 1 };
+    Preconditioner preconditioner = PRECOND_JAC;
 };
 
 typedef std::function<void(int level /*0 error .. 3 result, 4 detail*/, const std::string&)> LogFn;
@@ -364,7 +367,7 @@ class Context {
     LoopResult solve(bool thermal, IterParams& ip, double maxerr, int loops, const LogFn& log = LogFn()) {
         pfem_opts o;
         pfem_default_opts(&o);
-        o.maxit = ip.maxit; o.lin_tol = ip.maxerr; o.outer_tol = maxerr; o.loops = loops;
+        o.maxit = ip.maxit; o.lin_tol = ip.maxerr; o.outer_tol = maxerr; o.loops = loops; o.precond = (int)ip.preconditioner;
         pfem_stats st;
         int rc = thermal ? pfem_solve_thermal(ctx_, &o, &st) : pfem_solve_shockley(ctx_, &o, &st);
         check(rc);

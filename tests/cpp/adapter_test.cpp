@@ -139,6 +139,7 @@ static int gpu_tests() {
         c.set_source(heat.data());
         IterParams ip;
         ip.maxerr = 1e-12; ip.maxit = 20000;
+        ip.preconditioner = (ord & 1) ? IterParams::PRECOND_LJAC : IterParams::PRECOND_JAC;   // both preconditioners
         Context::LoopResult r = c.solve(true, ip, 0.05, 0);
         REQUIRE(ip.converged && r.loops >= 1);
         std::vector<double> T(N);

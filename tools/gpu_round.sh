@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-for f in tests/test_gpu_operator.py tests/test_gpu_thermal.py tests/test_gpu_shockley.py tests/test_gpu_thermoelectric.py; do
+for f in tests/test_gpu_operator.py tests/test_gpu_thermal.py tests/test_gpu_shockley.py tests/test_gpu_thermoelectric.py tests/test_gpu_boundary.py tests/test_gpu_masked.py tests/test_gpu_line.py tests/test_adapter_cpp.py; do
   b=$(basename $f .py)
   timeout 900 python -m pytest $f -q -m gpu --tb=short -p no:cacheprovider > gpurun_out/$b.log 2>&1
   echo "$b exit $?" | tee -a gpurun_out/summary.txt
@@ -25,4 +25,8 @@ if [ "${WITH_NCU_FULL:-1}" = "1" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_fpcg' -s 30 -c 2 -f -o gpurun_out/prof_fused \
      python bench.py --steps 1 --warmup 1 --iters 10 --no-tts --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
   echo "ncu full exit $?" | tee -a gpurun_out/summary.txt
+  # the line-Jacobi iteration: line solve kernel + operator step (k_fpcg MODE 2)
+  timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'k_line_I|k_fpcg<8, 2, 2, 3, 0, 2>' -s 20 -c 4 -f -o gpurun_out/prof_line \
+     python tools/time_line.py 256 012 > gpurun_out/ncu_line.log 2>&1
+  echo "ncu line exit $?" | tee -a gpurun_out/summary.txt
 fi

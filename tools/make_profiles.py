@@ -113,6 +113,29 @@ dram = float(r[idx["dram__bytes_read.sum"]].replace(",", "")) * scale[units[idx[
 json.dump({"k_fpcg_dram_bytes_per_launch": dram, "source": f"profiles/{tag}_k_fpcg_ncu.md", "workload": "config B 256^3"},
           open(os.path.join(P, "traffic.json"), "w"), indent=1)
 
+# 2b. the line-Jacobi iteration: line solve kernel and operator step (k_fpcg MODE 2), headline metrics per kernel
+rep2 = os.path.join(G, "prof_line.ncu-rep")
+if os.path.exists(rep2):
+    raw = subprocess.run(["ncu", "-i", rep2, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(io.StringIO(raw)))
+    h, units = rr[0], rr[1]
+    idx = {k: i for i, k in enumerate(h)}
+    per = {}
+    for r in rr[2:]:
+        name = r[idx["Kernel Name"]]
+        t = float(r[idx["gpu__time_duration.sum"]].replace(",", ""))
+        if name not in per or t > per[name][0]:
+            per[name] = (t, r)
+    with open(os.path.join(P, f"{tag}_line_ncu.md"), "w") as f:
+        f.write(f"# `ncu --set full --clock-control none -k regex:'k_line_I|k_fpcg' python tools/time_line.py 256 012`, {tag}\n\n"
+                "The two kernels of one line-Jacobi PCG iteration (DESIGN.md §4.4), config B 256^3, lines along I; the longest launch of each "
+                "kernel in the capture (numbers under the profiler are not bench values; tools/time_line.py prints the event timings).\n")
+        for name, (t, r) in per.items():
+            f.write(f"\n## `{name[:150]}`\n\n| metric | value | unit |\n|---|---:|---|\n")
+            for k in keys:
+                if k in idx:
+                    f.write(f"| {k} | {r[idx[k]]} | {units[idx[k]]} |\n")
+
 # 3. the bench line and the test summary of the same session
 for name in ("bench.log", "summary.txt", "smoke.log", "gpu.txt"):
     src = os.path.join(G, name)

@@ -81,8 +81,58 @@ def shockley_cases():
     print(f"shockley_C_20x22x52: loops={len(o.history)} I={o.get_total_current():.6e} mA")
 
 
+def boundary_conditions(p):
+    """conditions of the 2nd / 3rd kind and radiation on all six sides of config B (the same set tests/test_golden.py builds)"""
+    from helpers import face_nodes
+    top, bot = face_nodes(p, 2, -1), face_nodes(p, 2, 0)
+    return dict(convection=[(top, 4.0e4, 310.), (face_nodes(p, 0, 0), 9.0e4, 295.)],
+                heatflux=[(face_nodes(p, 0, -1), -3.0e5), (bot[: bot.size // 2], 1.0e5)],
+                radiation=[(face_nodes(p, 1, -1), 0.85, 285.), (face_nodes(p, 1, 0), 0.3, 330.), (top, 0.5, 300.)])
+
+
+def boundary_cases():
+    """setBoundaries (therm3d.cpp:140-168,242-268), verbatim and corrected: Cholesky and the reference NSPCG on the same matrix"""
+    p = cf.config_B((14, 16, 40))
+    out = {}
+    for tag, quirk in (("verbatim", True), ("corrected", False)):
+        b = orc.BoundaryTerms(p.N, **boundary_conditions(p))
+        o = oracle_thermal(p, algorithm="cholesky", boundaries=b, quirk=quirk)
+        o.compute(0)
+        r = oracle_thermal(p, algorithm="iterative", precond="ic", itmaxerr=1e-12, maxit=5000, boundaries=b, quirk=quirk)
+        r.compute(0)
+        out[f"T_cholesky_{tag}"], out[f"T_nspcg_{tag}"], out[f"loops_{tag}"] = o.temperatures, r.temperatures, len(o.history)
+        print(f"static3d_B_boundary {tag}: loops={len(o.history)} maxT={o.maxT:.6f} |T_chol-T_nspcg|={np.abs(o.temperatures - r.temperatures).max():.2e}")
+    np.savez_compressed(os.path.join(HERE, "static3d_B_boundary_14x16x40.npz"), n=np.array(p.n), order=p.order, **out)
+
+
+def masked_cases():
+    """empty-elements="exclude": Cholesky on the RectangularMaskedMesh3D numbering (the reference's default Cholesky mesh)"""
+    p = shockley3d_reference_problem()
+    inc = (p.empty == 0).astype(np.uint8)
+    o = oracle_shockley(p, algorithm="cholesky", eps=p.meta["eps"], included=inc)
+    o.compute(25)
+    np.savez_compressed(os.path.join(HERE, "shockley3d_py_excluded.npz"), V_cholesky=o.potential, masked_nodes=o._matrix().active,
+                        total_current=o.get_total_current(), total_heat=o.get_total_heat(), capacitance=o.get_capacitance(),
+                        loops=len(o.history), n=np.array(p.n), order=p.order)
+    print(f"shockley3d_py_excluded: loops={len(o.history)} I={o.get_total_current():.6f} mA, masked nodes {int(o._matrix().active.sum())} of {p.N}")
+    p = cf.config_B((14, 16, 40))
+    inc = (p.empty == 0).astype(np.uint8)
+    o = oracle_thermal(p, algorithm="cholesky", included=inc)
+    o.compute(0)
+    np.savez_compressed(os.path.join(HERE, "static3d_B_excluded_14x16x40.npz"), T_cholesky=o.temperatures, masked_nodes=o._matrix().active,
+                        loops=len(o.history), maxT=o.maxT, n=np.array(p.n), order=p.order)
+    print(f"static3d_B_excluded: loops={len(o.history)} maxT={o.maxT:.6f}, masked nodes {int(o._matrix().active.sum())} of {p.N}")
+
+
 if __name__ == "__main__":
     orc.build(ref=True, quiet=True)
-    for name, mk in CASES.items():
-        thermal_case(name, mk())
-    shockley_cases()
+    which = sys.argv[1:] or ["thermal", "shockley", "boundary", "masked"]
+    if "thermal" in which:
+        for name, mk in CASES.items():
+            thermal_case(name, mk())
+    if "shockley" in which:
+        shockley_cases()
+    if "boundary" in which:
+        boundary_cases()
+    if "masked" in which:
+        masked_cases()

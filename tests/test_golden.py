@@ -125,3 +125,90 @@ def test_cuda_shockley_vs_fixtures():
         heat = s.outHeat()
         assert np.abs(heat - g["heat"]).max() <= 1e-5 * np.abs(g["heat"]).max()
         s.invalidate()
+
+
+# ------------------------------------------------------------------------------ boundary terms and masked meshes
+
+def _boundary_conditions(p):
+    from helpers import face_nodes
+    top, bot = face_nodes(p, 2, -1), face_nodes(p, 2, 0)
+    return dict(convection=[(top, 4.0e4, 310.), (face_nodes(p, 0, 0), 9.0e4, 295.)],
+                heatflux=[(face_nodes(p, 0, -1), -3.0e5), (bot[: bot.size // 2], 1.0e5)],
+                radiation=[(face_nodes(p, 1, -1), 0.85, 285.), (face_nodes(p, 1, 0), 0.3, 330.), (top, 0.5, 300.)])
+
+
+@pytest.mark.parametrize("tag,quirk", [("verbatim", True), ("corrected", False)])
+def test_oracle_reproduces_boundary_fixture(tag, quirk):
+    g, p = gold("static3d_B_boundary_14x16x40"), cf.config_B((14, 16, 40))
+    assert np.abs(g[f"T_cholesky_{tag}"] - g[f"T_nspcg_{tag}"]).max() <= 1e-6     # LAPACK and the reference NSPCG agree
+    o = oracle_thermal(p, algorithm="cholesky", boundaries=orc.BoundaryTerms(p.N, **_boundary_conditions(p)), quirk=quirk)
+    o.compute(0)
+    assert len(o.history) == int(g[f"loops_{tag}"])
+    assert np.abs(o.temperatures - g[f"T_cholesky_{tag}"]).max() <= 1e-9
+
+
+def test_oracle_reproduces_masked_fixtures():
+    g, p = gold("shockley3d_py_excluded"), shockley3d_reference_problem()
+    o = oracle_shockley(p, algorithm="cholesky", eps=p.meta["eps"], included=(p.empty == 0).astype(np.uint8))
+    o.compute(25)
+    act = g["masked_nodes"]
+    assert np.array_equal(o._matrix().active, act)
+    assert np.abs(o.potential - g["V_cholesky"])[act].max() <= 1e-10
+    assert o.get_capacitance() == pytest.approx(float(g["capacitance"]), rel=1e-9)
+    g, p = gold("static3d_B_excluded_14x16x40"), cf.config_B((14, 16, 40))
+    o = oracle_thermal(p, algorithm="cholesky", included=(p.empty == 0).astype(np.uint8))
+    o.compute(0)
+    assert len(o.history) == int(g["loops"])
+    assert np.abs(o.temperatures - g["T_cholesky"])[g["masked_nodes"]].max() <= 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precond", ["jac", "ljac"])
+@pytest.mark.parametrize("tag,quirk", [("verbatim", True), ("corrected", False)])
+def test_cuda_boundary_vs_fixture(tag, quirk, precond):
+    from plask_b200.solvers import Static3D
+    g, p = gold("static3d_B_boundary_14x16x40"), cf.config_B((14, 16, 40))
+    c = _boundary_conditions(p)
+    s = Static3D(tag)
+    s.problem = p
+    s.heatflux_boundary, s.convection_boundary, s.radiation_boundary = c["heatflux"], c["convection"], c["radiation"]
+    s.boundary_verbatim = quirk
+    s.iterative.preconditioner = precond
+    s.iterative.maxerr, s.iterative.maxit = 1e-11, 100000
+    s.compute(0)
+    T = s.outTemperature()
+    assert s.stats["outer_loops"] == int(g[f"loops_{tag}"])
+    assert np.abs(T - g[f"T_cholesky_{tag}"]).max() <= 1e-3          # north-star tolerance (K)
+    assert np.abs(T - g[f"T_nspcg_{tag}"]).max() <= 1e-3
+    s.invalidate()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precond", ["jac", "ljac"])
+def test_cuda_masked_vs_fixtures(precond):
+    from plask_b200.solvers import Shockley3D, Static3D
+    g, p = gold("shockley3d_py_excluded"), shockley3d_reference_problem()
+    e = Shockley3D("excluded")
+    e.problem = p
+    e.empty_elements = "exclude"
+    e.beta, e.js, e.maxerr = p.beta, p.js, p.maxerr
+    e.iterative.preconditioner = precond
+    e.iterative.maxerr, e.iterative.maxit = 1e-13, 100000
+    e.compute(25)
+    act = g["masked_nodes"]
+    assert np.array_equal(e.masked_nodes(), act)
+    assert np.abs(e.outVoltage() - g["V_cholesky"])[act].max() <= 1e-6   # north-star tolerance (V)
+    assert e.get_total_current() == pytest.approx(float(g["total_current"]), rel=1e-5)
+    assert e.get_total_heat() == pytest.approx(float(g["total_heat"]), rel=1e-5)
+    e.invalidate()
+    g, p = gold("static3d_B_excluded_14x16x40"), cf.config_B((14, 16, 40))
+    s = Static3D("excluded")
+    s.problem = p
+    s.empty_elements = "exclude"
+    s.iterative.preconditioner = precond
+    s.iterative.maxerr, s.iterative.maxit = 1e-11, 100000
+    s.compute(0)
+    assert s.stats["outer_loops"] == int(g["loops"])
+    assert np.abs(s.outTemperature() - g["T_cholesky"])[g["masked_nodes"]].max() <= 1e-3
+    assert s.maxT == pytest.approx(float(g["maxT"]), abs=1e-6)
+    s.invalidate()

@@ -347,11 +347,13 @@ def run_ours(args):
         except Exception as ex:  # keep the bench line even if the long solve fails
             tts = {"error": str(ex)}
         s.invalidate()
-        # the same solve with the line-Jacobi preconditioner (two kernels per iteration, single device only)
-        if not slab and "error" not in tts:
+        # the same solve with the line-Jacobi preconditioner (two kernels per iteration)
+        if "error" not in tts:
             s2 = Static3D("bench-ljac")
             s2.device = local
             s2.problem = p
+            if slab:
+                s2.slab = dict(rank=rank, nranks=world, own_lo=slab[0], own_hi=slab[1], allgather=allgather_bytes)
             s2.iterative.preconditioner = "ljac"
             s2.iterative.maxerr = args.lin_tol
             s2.iterative.maxit = args.tts_maxit

@@ -173,7 +173,7 @@ typedef struct {
     int maxit;        /* max PCG iterations per linear solve (iter_params.maxit)            */
     double lin_tol;   /* stop when ||r||2 <= lin_tol*||b||2 AND ||r||_D^-1 <= lin_tol*||b||_D^-1 (b = free rows of the rhs) */
     int precond;      /* 0 = Jacobi (NSPCG "jac"); 1 = line-Jacobi (NSPCG "ljac"): tridiagonal line blocks along the
-                       * physical vertical axis, two kernels per iteration, single device only */
+                       * physical vertical axis, two kernels per iteration; in slab mode the vertical axis must not be the major one */
     double outer_tol; /* maxerr of the nonlinear loop: K (thermal) or % (electrical)        */
     int loops;        /* max nonlinear loops in this call, 0 = until converged              */
     int batch;        /* PCG iterations per captured CUDA graph launch (0 = default)        */

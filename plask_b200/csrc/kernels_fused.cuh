@@ -98,7 +98,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
     const int nsteps = k1 - k0 + 1;   // items t = 0 .. nsteps: node planes k0-1 .. k1, element layers k0-1 .. k1-1
     const int jl0 = ty * RJ;
     // slab mode: the first / last owned plane is also stored into the neighbour's halo plane (NVLink peer stores)
-    const bool push_lo = FUSED && po.r_lo != nullptr, push_hi = FUSED && po.r_hi != nullptr;
+    const bool push_lo = FUSED && po.p_lo != nullptr, push_hi = FUSED && po.p_hi != nullptr;
     const bool slab = push_lo || push_hi;
 
     // ---- per-thread constants -----------------------------------------------------------
@@ -251,8 +251,8 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
                         if (slab) {
                             const int P = k0 - 1 + t;
                             const idx_t nip = n - sK * P;   // offset inside the plane
-                            if (push_lo && P == g.kown0) { po.r_lo[nip] = rn; po.p_lo[nip] = pn; }
-                            if (push_hi && P == g.kown1 - 1) { po.r_hi[nip] = rn; po.p_hi[nip] = pn; }
+                            if (push_lo && P == g.kown0) { if (!LINE) po.r_lo[nip] = rn; po.p_lo[nip] = pn; }
+                            if (push_hi && P == g.kown1 - 1) { if (!LINE) po.r_hi[nip] = rn; po.p_hi[nip] = pn; }
                         }
                         if (!LINE) {
                             red[1] = fma(rn, z, red[1]);
@@ -356,7 +356,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
                         const double da = zda[RJ + rr];
                         const double qv = (da == 0.) ? 0. : carry[rr] + lo;
                         q_out[nown[rr] - sK] = qv;
-                        if (slab) {
+                        if (slab && !LINE) {   // the line-Jacobi iteration reads q on owned rows only
                             const int Pa = k0 - 2 + t;
                             const idx_t nip = nown[rr] - sK - sK * Pa;
                             if (push_lo && Pa == g.kown0) po.q_lo[nip] = qv;

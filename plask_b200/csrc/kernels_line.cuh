@@ -114,7 +114,7 @@ template <int SEG>
 __global__ void __launch_bounds__(256)
 k_line_I(const Grid g, const double* __restrict__ r_in, const double* __restrict__ q_in, const double* __restrict__ ll,
          const double* __restrict__ ld, double* __restrict__ r_out, double* __restrict__ z_out, Scalars* sc, double* partials,
-         const int mode) {
+         const int mode, const PeerOut po) {
     constexpr int ROW = 32 * SEG, ROWP = ROW + ROW / SEG;   // one pad per segment: conflict-free segment reads
     __shared__ double sh[32 * 3];
     __shared__ int sh_flag;
@@ -215,11 +215,18 @@ k_line_I(const Grid g, const double* __restrict__ r_in, const double* __restrict
 #pragma unroll
         for (int c = 0; c < SEG / 2; ++c) {
             const int i = 2 * lane + 64 * c;
-            if (i < g.sJ) *reinterpret_cast<double2*>(z_out + base + i) = make_double2(tb[i + i / SEG], tb[i + 1 + (i + 1) / SEG]);
+            if (i < g.sJ) {
+                const double2 zv = make_double2(tb[i + i / SEG], tb[i + 1 + (i + 1) / SEG]);
+                *reinterpret_cast<double2*>(z_out + base + i) = zv;
+                // slab mode: z of the first / last owned plane also goes into the neighbour's halo plane (NVLink peer store)
+                if (po.z_lo && k == g.kown0) *reinterpret_cast<double2*>(po.z_lo + g.sJ * j + i) = zv;
+                if (po.z_hi && k == g.kown1 - 1) *reinterpret_cast<double2*>(po.z_hi + g.sJ * j + i) = zv;
+            }
         }
         __syncwarp();
     }
-    if (grid_reduce<3, false>(acc, partials, &sc->ticket[3], sh, &sh_flag)) {
+    if (grid_reduce<3, false>(acc, partials, &sc->ticket[3], sh, &sh_flag, po.z_lo != nullptr || po.z_hi != nullptr)) {
+        if (sc->comm) rank_allreduce<3, false>(acc, sc->comm, sh);   // also orders the z halo stores before the operator step
         if (threadIdx.x == 0) line_finalize(sc, acc[0], acc[1], acc[2], mode);
     }
 }
@@ -229,20 +236,26 @@ k_line_I(const Grid g, const double* __restrict__ r_in, const double* __restrict
 // loaded, swept and stored.  rho = y.D^-1 y comes out of the forward sweep (r'.M^-1 r' = y^T D^-1 y).
 __global__ void __launch_bounds__(128)
 k_line_strided(const Grid g, const double* r_in, const double* __restrict__ q_in, const double* __restrict__ ll,
-               const double* __restrict__ ld, double* r_out, double* z_out, Scalars* sc, double* partials, const int mode) {
+               const double* __restrict__ ld, double* r_out, double* z_out, Scalars* sc, double* partials, const int mode,
+               const PeerOut po) {
     constexpr int U = 8;
     __shared__ double sh[32 * 3];
     __shared__ int sh_flag;
     if (mode == 0 && sc->done) return;
     const double alpha = mode == 0 ? sc->alpha : 0.;
-    const int vd = g.vdim;   // 1 or 2
+    const int vd = g.vdim;   // 1 (lines along J, one per (i, owned plane k)) or 2 (lines along K, never in slab mode)
     const int nL = vd == 1 ? g.nJ : g.nK;
-    const int nB = vd == 1 ? g.nK : g.nJ;
+    const int b0 = vd == 1 ? g.kown0 : 0;
+    const int nB = vd == 1 ? g.kown1 - g.kown0 : g.nJ;
     const idx_t sL = vd == 1 ? g.sJ : g.sK, sB = vd == 1 ? g.sK : g.sJ;
     const idx_t lines = (idx_t)g.nI * nB;
     double acc[3] = {0., 0., 0.};
     for (idx_t line = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; line < lines; line += (idx_t)gridDim.x * blockDim.x) {
-        const idx_t n0 = (line % g.nI) + sB * (line / g.nI);
+        const int bi = b0 + (int)(line / g.nI);
+        const idx_t n0 = (line % g.nI) + sB * bi;
+        double* const zp = (vd == 1 && po.z_lo && bi == g.kown0) ? po.z_lo - sB * bi
+                         : (vd == 1 && po.z_hi && bi == g.kown1 - 1) ? po.z_hi - sB * bi : nullptr;   // halo copy of this plane
+        double* const zp2 = (vd == 1 && po.z_lo && po.z_hi && bi == g.kown0 && bi == g.kown1 - 1) ? po.z_hi - sB * bi : nullptr;
         double y = 0.;
         for (int m0 = 0; m0 < nL; m0 += U) {
             double rp[U], lv[U], dv[U];
@@ -293,11 +306,16 @@ k_line_strided(const Grid g, const double* r_in, const double* __restrict__ q_in
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int m = m1 - 1 - u;
-                if (m >= 0) z_out[n0 + sL * m] = yv[u];
+                if (m >= 0) {
+                    z_out[n0 + sL * m] = yv[u];
+                    if (zp) zp[n0 + sL * m] = yv[u];
+                    if (zp2) zp2[n0 + sL * m] = yv[u];
+                }
             }
         }
     }
-    if (grid_reduce<3, false>(acc, partials, &sc->ticket[3], sh, &sh_flag)) {
+    if (grid_reduce<3, false>(acc, partials, &sc->ticket[3], sh, &sh_flag, po.z_lo != nullptr || po.z_hi != nullptr)) {
+        if (sc->comm) rank_allreduce<3, false>(acc, sc->comm, sh);   // also orders the z halo stores before the operator step
         if (threadIdx.x == 0) line_finalize(sc, acc[0], acc[1], acc[2], mode);
     }
 }

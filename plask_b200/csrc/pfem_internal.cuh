@@ -58,6 +58,7 @@ struct Comm {
 struct PeerOut {
     double *r_lo, *q_lo, *p_lo;        // upper halo plane of the lower neighbour
     double *r_hi, *q_hi, *p_hi;        // lower halo plane of the upper neighbour
+    double *z_lo, *z_hi;               // the same for z of the line-Jacobi iteration (kernels_line.cuh)
 };
 
 // Scalars of the PCG iteration and of the nonlinear loop; device resident, one instance per

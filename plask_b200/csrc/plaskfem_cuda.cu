@@ -97,15 +97,16 @@ struct pfem_ctx {
     Comm* d_comm = nullptr;
     Inbox* inbox = nullptr;                 // exported
     Inbox* peer_inbox[PFEM_MAX_RANKS] = {};  // imported (null for self)
-    struct Neighbour { bool present = false; double* arr[8] = {}; long long G = 0, sK = 0, nK = 0; } nb_lo, nb_hi;
+    struct Neighbour { bool present = false; double* arr[9] = {}; long long G = 0, sK = 0, nK = 0; } nb_lo, nb_hi;
 };
 
 // arrays a neighbour may write / read: indices into pfem_ctx (order fixed by the blob layout)
-enum { SA_R = 0, SA_R2, SA_Q, SA_Q2, SA_P, SA_P2, SA_DINV, SA_X, SA_COUNT };
+enum { SA_R = 0, SA_R2, SA_Q, SA_Q2, SA_P, SA_P2, SA_DINV, SA_X, SA_LZ, SA_COUNT };
+static_assert(SA_COUNT == 9, "pfem_ctx::Neighbour::arr holds SA_COUNT pointers");
 static double* slab_array(pfem_ctx* ctx, int a) {
     switch (a) {
         case SA_R: return ctx->r; case SA_R2: return ctx->r2; case SA_Q: return ctx->q; case SA_Q2: return ctx->q2;
-        case SA_P: return ctx->p; case SA_P2: return ctx->p2; case SA_DINV: return ctx->dinv; default: return ctx->x;
+        case SA_P: return ctx->p; case SA_P2: return ctx->p2; case SA_DINV: return ctx->dinv; case SA_LZ: return ctx->lz; default: return ctx->x;
     }
 }
 struct SlabBlob {
@@ -200,6 +201,17 @@ static void dev_release(pfem_ctx* ctx, T** p) {
             break;
         }
     *p = nullptr;
+}
+
+// line-Jacobi preconditioner: z, free-row mask and the L D L^T factors (allocated on first use; in slab mode before the export)
+static int alloc_line_arrays(pfem_ctx* ctx) {
+    if (ctx->lz) return PFEM_OK;
+    const size_t N = (size_t)ctx->g.NP, G = (size_t)ctx->g.G;
+    TRY(dev_alloc(ctx, &ctx->lz, N, G));
+    TRY(dev_alloc(ctx, &ctx->lmask, N, G));
+    TRY(dev_alloc(ctx, &ctx->ll, N, G));
+    TRY(dev_alloc(ctx, &ctx->ld, N, G));
+    return PFEM_OK;
 }
 
 static int ensure_stage(pfem_ctx* ctx, size_t bytes) {
@@ -860,6 +872,8 @@ extern "C" int pfem_slab_configure(pfem_ctx* ctx, int rank, int nranks, size_t o
     ctx->rank = rank; ctx->nranks = nranks;
     g.kown0 = (int)own_lo; g.kown1 = (int)own_hi;
     if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
+    ctx->line_plan.valid = false;
+    if (nranks > 1) TRY(alloc_line_arrays(ctx));   // z of the line-Jacobi iteration is exported to the neighbours
     {   // the fused plan chunks the OWNED planes
         double* const rr[2] = {ctx->r, ctx->r2};
         double* const qq[2] = {ctx->q, ctx->q2};
@@ -961,6 +975,8 @@ static PeerOut peer_out(pfem_ctx* ctx, int out_parity) {
         po.q_hi = ctx->nb_hi.arr[out_parity ? SA_Q2 : SA_Q];
         po.p_hi = ctx->nb_hi.arr[out_parity ? SA_P2 : SA_P];
     }
+    if (ctx->nb_lo.present && ctx->nb_lo.arr[SA_LZ]) po.z_lo = ctx->nb_lo.arr[SA_LZ] + (ctx->nb_lo.nK - 1) * ctx->nb_lo.sK;
+    if (ctx->nb_hi.present && ctx->nb_hi.arr[SA_LZ]) po.z_hi = ctx->nb_hi.arr[SA_LZ];
     return po;
 }
 
@@ -1017,13 +1033,7 @@ __global__ void k_set_params(Scalars* sc, double tol2, int maxit, int bench, int
 static int ensure_line(pfem_ctx* ctx) {
     if (ctx->line_plan.valid) return PFEM_OK;
     const Grid& g = ctx->g;
-    const size_t N = (size_t)g.NP, G = (size_t)g.G;
-    if (!ctx->lz) {
-        TRY(dev_alloc(ctx, &ctx->lz, N, G));
-        TRY(dev_alloc(ctx, &ctx->lmask, N, G));
-        TRY(dev_alloc(ctx, &ctx->ll, N, G));
-        TRY(dev_alloc(ctx, &ctx->ld, N, G));
-    }
+    TRY(alloc_line_arrays(ctx));
     double* const zz[2] = {ctx->lz, ctx->lz};
     double* const qq[2] = {ctx->q, ctx->q2};
     double* const pp[2] = {ctx->p, ctx->p2};
@@ -1041,6 +1051,7 @@ static inline int line_seg(const Grid& g) {   // nodes per lane of the I-line ke
 // z = M^-1 (r - alpha q) for the line-Jacobi preconditioner; mode 1: only b.M^-1 b -> sc->bz
 static int launch_line_solve(pfem_ctx* ctx, const double* r_in, const double* q_in, double* r_out, int mode) {
     const Grid& g = ctx->g;
+    const PeerOut po = peer_out(ctx, 0);   // only the z pointers are used
     if (g.vdim == 0) {
         const idx_t rows = (idx_t)g.nJ * (g.kown1 - g.kown0);
         // balanced: every warp gets the same number of rows (8 warps per block)
@@ -1049,16 +1060,17 @@ static int launch_line_solve(pfem_ctx* ctx, const double* r_in, const double* q_
         const idx_t rpw = (rows + cap_warps - 1) / cap_warps;
         int blocks = (int)(((rows + rpw - 1) / rpw + 7) / 8);
         if (blocks < 1) blocks = 1;
-#define PFEM_LINE_CASE(S) case S: k_line_I<S><<<blocks, 256, 0, ctx->stream>>>(g, r_in, q_in, ctx->ll, ctx->ld, r_out, ctx->lz, ctx->d_sc, ctx->partials, mode); break;
+#define PFEM_LINE_CASE(S) case S: k_line_I<S><<<blocks, 256, 0, ctx->stream>>>(g, r_in, q_in, ctx->ll, ctx->ld, r_out, ctx->lz, ctx->d_sc, ctx->partials, mode, po); break;
         switch (line_seg(g)) {
             PFEM_LINE_CASE(2) PFEM_LINE_CASE(4) PFEM_LINE_CASE(8) PFEM_LINE_CASE(16)
             default: FAIL(PFEM_ERR_BAD_INPUT, "line preconditioner along the minor axis handles up to 512 nodes per line");
         }
 #undef PFEM_LINE_CASE
     } else {
-        const idx_t lines = (idx_t)g.nI * (g.vdim == 1 ? g.nK : g.nJ);
+        const idx_t lines = (idx_t)g.nI * (g.vdim == 1 ? g.kown1 - g.kown0 : g.nJ);
         int blocks = (int)std::min<idx_t>((lines + 127) / 128, (idx_t)ctx->sm_count * 16);
-        k_line_strided<<<blocks, 128, 0, ctx->stream>>>(g, r_in, q_in, ctx->ll, ctx->ld, r_out, ctx->lz, ctx->d_sc, ctx->partials, mode);
+        if (blocks < 1) blocks = 1;
+        k_line_strided<<<blocks, 128, 0, ctx->stream>>>(g, r_in, q_in, ctx->ll, ctx->ld, r_out, ctx->lz, ctx->d_sc, ctx->partials, mode, po);
     }
     KCHECK(); LAUNCHED(1);
     return PFEM_OK;
@@ -1102,13 +1114,15 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
         double* const pp[2] = {ctx->p, ctx->p2};
         launch_line_solve(ctx, ctx->r, qq[parity], ctx->r, 0);
         if (ev) cudaEventRecord(ev[1], ctx->stream);
-        PeerOut none;
-        memset(&none, 0, sizeof none);
+        const PeerOut po = peer_out(ctx, 1 - parity);   // slab mode: p' of the boundary planes goes to the neighbours
         launch_fused_dispatch<2>(ctx->line_plan, g, parity, nullptr, qq[1 - parity], pp[1 - parity], ctx->x, ctx->d_sc, ctx->partials,
-                                    none, ctx->stream);
-        if (ctx->surf_iter)   // q' += S p' on the boundary rows, alpha from the completed p'.q'
+                                    po, ctx->stream);
+        if (ctx->surf_iter) {  // q' += S p' on the boundary rows, alpha from the completed p'.q' (q is only read on owned rows: no push)
+            PeerOut none;
+            memset(&none, 0, sizeof none);
             k_surf_iter<<<surf_blocks(ctx), 256, 0, ctx->stream>>>(ctx->surf, g, pp[1 - parity], qq[1 - parity], ctx->r, ctx->dinv, ctx->d_sc,
                                                                     ctx->partials, none);
+        }
         if (ev) cudaEventRecord(ev[2], ctx->stream);
         return 2 + ctx->surf_iter;
     }
@@ -1257,7 +1271,8 @@ static int check_opts(pfem_ctx* ctx, const pfem_opts* o) {
     if (!(o->lin_tol > 0.)) FAIL(PFEM_ERR_BAD_INPUT, "lin_tol must be positive");
     if (o->precond != 0 && o->precond != 1) FAIL(PFEM_ERR_BAD_INPUT, "preconditioner %d is not implemented (0 = Jacobi, 1 = line-Jacobi)", o->precond);
     if (o->precond == 1 && o->variant != 3) FAIL(PFEM_ERR_BAD_INPUT, "the line preconditioner runs with kernel variant 3 only");
-    if (o->precond == 1 && ctx->nranks > 1) FAIL(PFEM_ERR_BAD_INPUT, "the line preconditioner is not available in slab mode yet");
+    if (o->precond == 1 && ctx->nranks > 1 && ctx->g.vdim == 2)
+        FAIL(PFEM_ERR_BAD_INPUT, "slab mode: the line preconditioner needs the vertical axis inside the slabs (a lateral major axis)");
     if (o->variant < 0 || o->variant > 3) FAIL(PFEM_ERR_BAD_INPUT, "unknown kernel variant %d", o->variant);
     if (o->variant == 3 && !ctx->fused.valid) FAIL(PFEM_ERR_STATE, "fused PCG kernel unavailable: %s", ctx->fused.why);
     if (ctx->nranks > 1 && o->variant != 3) FAIL(PFEM_ERR_BAD_INPUT, "slab mode runs the fused PCG kernel only (variant 3)");

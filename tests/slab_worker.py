@@ -129,6 +129,28 @@ def main():
         one.invalidate()
     dist.barrier()
 
+    # ---- line-Jacobi preconditioner in slab mode (order 012: the vertical lines run along the minor axis, inside every slab)
+    sl = Static3D(f"slabline{rank}")
+    sl.device = local
+    sl.problem = q
+    sl.slab = dict(rank=rank, nranks=world, own_lo=own_lo, own_hi=own_hi, allgather=allgather_bytes)
+    sl.iterative.preconditioner = "ljac"
+    sl.iterative.maxerr = 1e-11
+    sl.iterative.maxit = 50000
+    sl.compute(0)
+    partsL = allgather_bytes((cf.slab_field_owned(q, sl.outTemperature(), own_lo, own_hi), sl.stats))
+    assert all(x[1]["lin_iters"] == partsL[0][1]["lin_iters"] for x in partsL)
+    sl.invalidate()
+    if rank == 0:
+        TL = np.concatenate([x[0] for x in partsL], axis=0).ravel()
+        d3 = float(np.abs(TL - T).max())
+        print(f"slab x{world} line-Jacobi: PCG iterations {partsL[0][1]['lin_iters']} (Jacobi {stats[0]['lin_iters']}), "
+              f"max|Tl_slab - T_slab| = {d3:.3e} K")
+        assert partsL[0][1]["outer_loops"] == stats[0]["outer_loops"]
+        assert partsL[0][1]["lin_iters"] < stats[0]["lin_iters"]
+        assert d3 <= 1e-6
+    dist.barrier()
+
     # ---- boundary conditions of the 2nd / 3rd kind and radiation in slab mode (corrected form; conditions on the two
     # end planes of the slab axis live on one rank only, the others cross every slab)
     from helpers import face_nodes

@@ -30,5 +30,6 @@ def test_slab_solve_two_gpus():
     r = _torchrun(2, 29551, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "max|T_slab - T_single|" in r.stdout
+    assert "max|Tl_slab - T_slab|" in r.stdout
     assert "max|Tb_slab - Tb_single|" in r.stdout
     assert "max|V_slab - V_single|" in r.stdout

@@ -64,6 +64,16 @@ void pfem_destroy(pfem_ctx* ctx);
 const char* pfem_strerror(int status);
 const char* pfem_last_error(const pfem_ctx* ctx);  /* detail of the last failing call */
 
+/* ---- internal layout (optional, before pfem_set_mesh) --------------------------------- */
+/* The ABI always speaks the mesh's own iteration order (node index = rectilinear3d.cpp:20-32, element index
+ * likewise).  PFEM_LAYOUT_ABI keeps that order in device memory.  PFEM_LAYOUT_VERTICAL_MINOR stores the fields with the
+ * physical vertical axis fastest, whatever the mesh order: the lines of the line-Jacobi preconditioner are then
+ * contiguous rows (warp-per-row solve instead of the strided one).  Transfers permute on the device; results do not
+ * depend on the layout.  Slab mode needs the ABI's major axis to be lateral with this layout. */
+#define PFEM_LAYOUT_ABI 0
+#define PFEM_LAYOUT_VERTICAL_MINOR 1
+int pfem_set_layout(pfem_ctx* ctx, int layout);
+
 /* ---- problem description (host arrays, copied) --------------------------------------- */
 
 /* Mesh: n[a], coordinates ax_a[0..n[a]-1] in um for the physical axes a = 0,1,2 (axis 2 is

@@ -68,6 +68,7 @@ SYMBOLS = {
     "pfem_destroy": (None, [_vp]),
     "pfem_strerror": (C.c_char_p, [C.c_int]),
     "pfem_last_error": (C.c_char_p, [_vp]),
+    "pfem_set_layout": (C.c_int, [_vp, C.c_int]),
     "pfem_set_mesh": (C.c_int, [_vp, _szp, c_dp, c_dp, c_dp, _szp]),
     "pfem_set_materials": (C.c_int, [_vp, _u32p, C.c_uint32, C.c_double, C.c_double, C.c_uint32, c_dp, c_dp]),
     "pfem_set_dirichlet": (C.c_int, [_vp, c_sz, _szp, c_dp]),
@@ -106,6 +107,7 @@ PFEM_ERR_CUDA, PFEM_ERR_NO_DEVICE, PFEM_ERR_BAD_INPUT, PFEM_ERR_STATE = -1, -2, 
 PFEM_ERR_NOT_SPD, PFEM_ERR_NOMEM, PFEM_ERR_NAN = -5, -6, -7
 ELEM_COND, ELEM_CURRENT, ELEM_HEAT, ELEM_FLUX = 0, 1, 2, 3
 MAT_EXCLUDED = 0xFFFFFFFF
+LAYOUT_ABI, LAYOUT_VERTICAL_MINOR = 0, 1
 
 _lib = None
 

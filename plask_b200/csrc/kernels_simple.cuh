@@ -292,16 +292,34 @@ __global__ void k_diag_from_dinv(idx_t N, const double* __restrict__ dinv, const
 
 // ------------------------------------------------- element lattice <-> compact order ----
 
-// Compact (ABI order: the element mesh keeps the node iteration order, so compact element
-// e = ei + (nI-1)*(ej + (nJ-1)*ek) in index space) <-> padded node-lattice slots.
+// Compact (ABI order: the element mesh keeps the node iteration order of the ABI, e = e_minor + n_minor'*(e_medium +
+// n_medium'*e_major)) <-> padded node-lattice slots.  g.abi_dim says which index-space axis each ABI axis is.
 __device__ __forceinline__ idx_t compact_to_slot(const Grid& g, idx_t e) {
-    const idx_t eI = g.nI - 1, eJ = g.nJ - 1;
-    const idx_t ei = e % eI, t = e / eI;
-    const idx_t ej = t % eJ, ek = t / eJ;
-    return ei + g.sJ * ej + g.sK * ek;
+    const idx_t en[3] = {g.nI - 1, g.nJ - 1, g.nK - 1}, st[3] = {1, g.sJ, g.sK};
+    const idx_t n0 = en[g.abi_dim[0]], n1 = en[g.abi_dim[1]];
+    const idx_t m0 = e % n0, t = e / n0;
+    const idx_t m1 = t % n1, m2 = t / n1;
+    return m0 * st[g.abi_dim[0]] + m1 * st[g.abi_dim[1]] + m2 * st[g.abi_dim[2]];
 }
 __device__ __forceinline__ idx_t slot_to_compact(const Grid& g, int i, int j, int k) {
-    return i + (idx_t)(g.nI - 1) * (j + (idx_t)(g.nJ - 1) * k);
+    const idx_t en[3] = {g.nI - 1, g.nJ - 1, g.nK - 1};
+    const int ii[3] = {i, j, k};
+    return ii[g.abi_dim[0]] + en[g.abi_dim[0]] * (ii[g.abi_dim[1]] + en[g.abi_dim[1]] * (idx_t)ii[g.abi_dim[2]]);
+}
+// dense ABI node array <-> pitched lattice when the internal layout differs from the ABI's iteration order
+__global__ void k_node_expand(const Grid g, const double* __restrict__ dense, double* __restrict__ lat) {
+    const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
+    const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= g.nI || j >= g.nJ) return;
+    lat[i + g.sJ * j + g.sK * k] = dense[i * g.abi_ns[0] + j * g.abi_ns[1] + k * g.abi_ns[2]];
+}
+__global__ void k_node_compact(const Grid g, const double* __restrict__ lat, double* __restrict__ dense) {
+    const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
+    const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= g.nI || j >= g.nJ) return;
+    dense[i * g.abi_ns[0] + j * g.abi_ns[1] + k * g.abi_ns[2]] = lat[i + g.sJ * j + g.sK * k];
 }
 template <typename T, int NC>
 __global__ void k_elem_expand(const Grid g, const T* __restrict__ src, T* __restrict__ dst0, T* __restrict__ dst1,

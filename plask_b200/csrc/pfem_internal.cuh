@@ -33,6 +33,9 @@ struct Grid {
     idx_t ps[3];         // node stride of physical axis a
     int pn[3];           // node count of physical axis a
     idx_t es[3];         // element stride of physical axis a in the ABI (compact) element order
+    int abi_dim[3];      // index-space axis (0 I, 1 J, 2 K) of the ABI's minor, medium, major axis (identity unless the
+                         // context was given another internal layout with pfem_set_layout)
+    idx_t abi_ns[3];     // ABI node stride of index-space axis I, J, K
     idx_t E;             // compact element count
     int kown0, kown1;    // node planes [kown0, kown1) along K owned by this context (slab mode; else 0, nK)
     // spacings per index-space axis and their reciprocals; each array has one guard entry in

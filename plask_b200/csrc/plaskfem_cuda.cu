@@ -84,6 +84,10 @@ struct pfem_ctx {
     double *lz = nullptr, *lmask = nullptr, *ll = nullptr, *ld = nullptr, *zero1 = nullptr;
     FusedPlan line_plan;
     int precond = 0;            // preconditioner of the PCG state prepared last
+    // internal layout (pfem_set_layout): 0 = the ABI's iteration order, 1 = vertical axis as the minor (I) axis
+    int layout = 0;
+    bool permuted = false;      // the lattice order differs from the ABI order: transfers go through permuting kernels
+    size_t abi_n[3] = {0, 0, 0};   // node counts of the ABI's minor, medium, major axis
     long long launches = 0;
     double last_relres_pre = 0.;
     int sm_count = 148;
@@ -229,15 +233,40 @@ static inline dim3 node_grid(const Grid& g) {
 static inline int vec_blocks(const pfem_ctx* ctx) { return ctx->sm_count * 8; }
 
 // host <-> device copies of node arrays: the ABI side is dense (row length nI), the device side pitched
+static int ensure_stage(pfem_ctx* ctx, size_t bytes);
 static cudaError_t upload_nodes(pfem_ctx* ctx, double* dev, const double* host) {
     const Grid& g = ctx->g;
-    return cudaMemcpy2DAsync(dev, (size_t)g.sJ * 8, host, (size_t)g.nI * 8, (size_t)g.nI * 8, (size_t)g.nJ * g.nK,
-                             cudaMemcpyHostToDevice, ctx->stream);
+    if (!ctx->permuted)
+        return cudaMemcpy2DAsync(dev, (size_t)g.sJ * 8, host, (size_t)g.nI * 8, (size_t)g.nI * 8, (size_t)g.nJ * g.nK,
+                                 cudaMemcpyHostToDevice, ctx->stream);
+    if (ensure_stage(ctx, (size_t)g.N * 8) < 0) return cudaErrorMemoryAllocation;
+    cudaError_t e = cudaMemcpyAsync(ctx->stage, host, (size_t)g.N * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) return e;
+    k_node_expand<<<dim3((g.nI + PFEM_NODE_BLOCK_X - 1) / PFEM_NODE_BLOCK_X, (g.nJ + PFEM_NODE_BLOCK_Y - 1) / PFEM_NODE_BLOCK_Y, g.nK),
+                    dim3(PFEM_NODE_BLOCK_X, PFEM_NODE_BLOCK_Y, 1), 0, ctx->stream>>>(g, (const double*)ctx->stage, dev);
+    ++ctx->launches;
+    return cudaGetLastError();
 }
 static cudaError_t download_nodes(pfem_ctx* ctx, double* host, const double* dev) {
     const Grid& g = ctx->g;
-    return cudaMemcpy2DAsync(host, (size_t)g.nI * 8, dev, (size_t)g.sJ * 8, (size_t)g.nI * 8, (size_t)g.nJ * g.nK,
-                             cudaMemcpyDeviceToHost, ctx->stream);
+    if (!ctx->permuted)
+        return cudaMemcpy2DAsync(host, (size_t)g.nI * 8, dev, (size_t)g.sJ * 8, (size_t)g.nI * 8, (size_t)g.nJ * g.nK,
+                                 cudaMemcpyDeviceToHost, ctx->stream);
+    if (ensure_stage(ctx, (size_t)g.N * 8) < 0) return cudaErrorMemoryAllocation;
+    k_node_compact<<<dim3((g.nI + PFEM_NODE_BLOCK_X - 1) / PFEM_NODE_BLOCK_X, (g.nJ + PFEM_NODE_BLOCK_Y - 1) / PFEM_NODE_BLOCK_Y, g.nK),
+                     dim3(PFEM_NODE_BLOCK_X, PFEM_NODE_BLOCK_Y, 1), 0, ctx->stream>>>(g, dev, (double*)ctx->stage);
+    ++ctx->launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(host, ctx->stage, (size_t)g.N * 8, cudaMemcpyDeviceToHost, ctx->stream);
+}
+// ABI node number -> pitched lattice index
+static inline idx_t abi_to_lattice(const pfem_ctx* ctx, idx_t r) {
+    const Grid& g = ctx->g;
+    const idx_t st[3] = {1, g.sJ, g.sK};
+    const idx_t m0 = r % (idx_t)ctx->abi_n[0], t = r / (idx_t)ctx->abi_n[0];
+    const idx_t m1 = t % (idx_t)ctx->abi_n[1], m2 = t / (idx_t)ctx->abi_n[1];
+    return m0 * st[g.abi_dim[0]] + m1 * st[g.abi_dim[1]] + m2 * st[g.abi_dim[2]];
 }
 
 #define LAUNCHED(n) (ctx->launches += (n))
@@ -302,6 +331,14 @@ extern "C" void pfem_destroy(pfem_ctx* ctx) {
     delete ctx;
 }
 
+extern "C" int pfem_set_layout(pfem_ctx* ctx, int layout) {
+    if (!ctx) return PFEM_ERR_BAD_INPUT;
+    if (layout != PFEM_LAYOUT_ABI && layout != PFEM_LAYOUT_VERTICAL_MINOR) FAIL(PFEM_ERR_BAD_INPUT, "unknown layout %d", layout);
+    if (ctx->have_mesh && layout != ctx->layout) FAIL(PFEM_ERR_STATE, "pfem_set_layout must be called before pfem_set_mesh");
+    ctx->layout = layout;
+    return PFEM_OK;
+}
+
 extern "C" void pfem_default_opts(pfem_opts* o) {
     memset(o, 0, sizeof(*o));
     o->maxit = 10000;
@@ -343,23 +380,36 @@ extern "C" int pfem_set_mesh(pfem_ctx* ctx, const size_t n[3], const double* ax0
     memset(&g, 0, sizeof(g));
     for (int a = 0; a < 3; ++a) ctx->hax[a].assign(ax[a], ax[a] + n[a]);
     ctx->noheat_set = false;
-    g.nI = (int)n[minor]; g.nJ = (int)n[medium]; g.nK = (int)n[major];
+    // internal layout: I, J, K = the ABI's minor, medium, major axis, or (pfem_set_layout) the vertical axis as I and the two
+    // lateral axes in their ABI order behind it
+    int im = minor, jm = medium, km = major;
+    if (ctx->layout == 1 && minor != 2) {
+        im = 2;
+        jm = (medium == 2) ? minor : (minor == 2 ? medium : minor);
+        km = 3 - im - jm;
+        if (stride[jm] > stride[km]) { int t = jm; jm = km; km = t; }
+    }
+    ctx->permuted = !(im == minor && jm == medium && km == major);
+    ctx->abi_n[0] = n[minor]; ctx->abi_n[1] = n[medium]; ctx->abi_n[2] = n[major];
+    g.nI = (int)n[im]; g.nJ = (int)n[jm]; g.nK = (int)n[km];
     g.sJ = ((idx_t)g.nI + 15) / 16 * 16;   // 128-byte rows
     g.sK = g.sJ * g.nJ;
     g.N = (idx_t)g.nI * g.nJ * g.nK;
     g.NP = g.sK * g.nK;
     g.G = ((g.sK + g.sJ + 2 + 15) / 16) * 16;
-    g.dim_of_phys[minor] = 0; g.dim_of_phys[medium] = 1; g.dim_of_phys[major] = 2;
+    g.dim_of_phys[im] = 0; g.dim_of_phys[jm] = 1; g.dim_of_phys[km] = 2;
+    g.abi_dim[0] = g.dim_of_phys[minor]; g.abi_dim[1] = g.dim_of_phys[medium]; g.abi_dim[2] = g.dim_of_phys[major];
+    g.abi_ns[0] = (idx_t)stride[im]; g.abi_ns[1] = (idx_t)stride[jm]; g.abi_ns[2] = (idx_t)stride[km];
     g.vdim = g.dim_of_phys[2];
     for (int a = 0; a < 3; ++a) g.pn[a] = (int)n[a];
-    g.ps[minor] = 1; g.ps[medium] = g.sJ; g.ps[major] = g.sK;   // strides in the pitched device layout
-    g.es[minor] = 1; g.es[medium] = g.nI - 1; g.es[major] = (idx_t)(g.nI - 1) * (g.nJ - 1);
+    g.ps[im] = 1; g.ps[jm] = g.sJ; g.ps[km] = g.sK;   // strides in the pitched device layout
+    g.es[minor] = 1; g.es[medium] = (idx_t)n[minor] - 1; g.es[major] = (idx_t)(n[minor] - 1) * (idx_t)(n[medium] - 1);
     g.E = (idx_t)(g.nI - 1) * (g.nJ - 1) * (g.nK - 1);
     g.kown0 = 0; g.kown1 = g.nK;
 
     // spacing arrays with one guard entry (value 1) on both sides
     const int cnt[3] = {g.nI - 1, g.nJ - 1, g.nK - 1};
-    const int phys_of_dim[3] = {minor, medium, major};
+    const int phys_of_dim[3] = {im, jm, km};
     size_t tot = 0;
     for (int d = 0; d < 3; ++d) tot += 2 * (size_t)(cnt[d] + 2);
     std::vector<double> hb(tot, 1.0);
@@ -506,10 +556,7 @@ extern "C" int pfem_set_dirichlet(pfem_ctx* ctx, size_t nd, const size_t* node, 
         for (size_t m = 0; m < nd; ++m) {
             if (node[m] >= (size_t)g.N) FAIL(PFEM_ERR_BAD_INPUT, "Dirichlet node %zu out of range", node[m]);
             if (!(value[m] == value[m]) || isinf(value[m])) FAIL(PFEM_ERR_BAD_INPUT, "non-finite Dirichlet value");
-            // ABI index (dense rows) -> pitched lattice index
-            const idx_t r = (idx_t)node[m];
-            const idx_t i = r % g.nI, t = r / g.nI;
-            order[m] = {i + g.sJ * (t % g.nJ) + g.sK * (t / g.nJ), m};
+            order[m] = {abi_to_lattice(ctx, (idx_t)node[m]), m};   // ABI index (dense rows) -> pitched lattice index
         }
         std::sort(order.begin(), order.end());
         for (size_t m = 0; m < nd; ++m) {
@@ -613,12 +660,12 @@ extern "C" int pfem_set_boundary(pfem_ctx* ctx, const pfem_boundary* b) {
         FAIL(PFEM_ERR_BAD_INPUT, "slab mode: verbatim radiation reads temperatures[0..7] of the whole mesh (therm3d.cpp:265); use the corrected form");
     // dense (ABI) and lattice strides of the physical axes; element extents along them
     idx_t dps[3], cnt[3] = {g.nI, g.nJ, g.nK};
-    for (int a = 0; a < 3; ++a) dps[a] = g.dim_of_phys[a] == 0 ? 1 : g.dim_of_phys[a] == 1 ? (idx_t)g.nI : (idx_t)g.nI * g.nJ;
+    for (int a = 0; a < 3; ++a) dps[a] = g.abi_ns[g.dim_of_phys[a]];
     const size_t N = (size_t)g.N;
     std::vector<uint8_t> mask(N, 0);
     for (size_t n = 0; n < N; ++n)
         mask[n] = (uint8_t)((b->has_flux && b->has_flux[n] ? 1 : 0) | (b->has_conv && b->has_conv[n] ? 2 : 0) | (b->has_rad && b->has_rad[n] ? 4 : 0));
-    auto lattice = [&](idx_t r) { const idx_t i = r % g.nI, t = r / g.nI; return i + g.sJ * (t % g.nJ) + g.sK * (t / g.nJ); };
+    auto lattice = [&](idx_t r) { return abi_to_lattice(ctx, r); };
     struct LoadT { idx_t node; double v; };
     struct RadT { idx_t node, src; double coef, amb4; };
     struct KT { idx_t row, col; double v; };
@@ -631,7 +678,7 @@ extern "C" int pfem_set_boundary(pfem_ctx* ctx, const pfem_boundary* b) {
     for (idx_t ek = 0; ek < cnt[2] - 1; ++ek)
         for (idx_t ej = 0; ej < cnt[1] - 1; ++ej)
             for (idx_t ei = 0; ei < cnt[0] - 1; ++ei) {
-                const idx_t n0 = ei + g.nI * (ej + (idx_t)g.nJ * ek);   // dense index of the lowest corner
+                const idx_t n0 = ei * g.abi_ns[0] + ej * g.abi_ns[1] + ek * g.abi_ns[2];   // dense (ABI) index of the lowest corner
                 idx_t idx[8];
                 uint8_t any = 0, mk[8];
                 for (int l = 0; l < 8; ++l) {
@@ -867,6 +914,7 @@ extern "C" int pfem_slab_configure(pfem_ctx* ctx, int rank, int nranks, size_t o
     if (own_lo != (rank > 0 ? 1u : 0u) || (size_t)g.nK - own_hi != (rank < nranks - 1 ? 1u : 0u))
         FAIL(PFEM_ERR_BAD_INPUT, "the local mesh must hold exactly one halo plane towards each neighbour");
     if (!ctx->fused.valid) FAIL(PFEM_ERR_STATE, "slab mode needs the fused PCG kernel: %s", ctx->fused.why);
+    if (g.abi_dim[2] != 2) FAIL(PFEM_ERR_BAD_INPUT, "slab mode cuts the ABI's major axis, which this internal layout does not keep as the slowest axis (vertical major axis with pfem_set_layout)");
     CU(cudaStreamSynchronize(ctx->stream));
     slab_release(ctx);
     ctx->rank = rank; ctx->nranks = nranks;

@@ -44,6 +44,10 @@ class DeviceFem:
         return L.check(self.ctx, rc)
 
     # ---- problem description
+    def set_layout(self, layout):
+        """internal layout, before set_mesh: L.LAYOUT_ABI (default) or L.LAYOUT_VERTICAL_MINOR"""
+        self._ck(self.lib.pfem_set_layout(self.ctx, int(layout)))
+
     def set_mesh(self, axes, strides):
         ax = [_f64(a) for a in axes]
         n = (L.c_sz * 3)(*[len(a) for a in ax])

@@ -45,6 +45,9 @@ class _FemSolver:
         # reference does for its iterative algorithm by default), 'exclude' drops the elements of EMPTY material
         # (problem.empty) like the reference's Cholesky default does
         self.empty_elements = "include"
+        # device layout: 'abi' keeps the mesh's iteration order, 'vertical-minor' stores the vertical axis fastest (contiguous
+        # lines for the 'ljac' preconditioner), 'auto' = 'vertical-minor' when the preconditioner is 'ljac'
+        self.layout = "auto"
         self.variant = 3            # 3 production (fused single-kernel iteration); 0/2 two-kernel; 1 simple reference kernels
         self._fem = None
         self._problem = None
@@ -109,6 +112,18 @@ class _FemSolver:
         out[np.broadcast_to(p.node_index_grid(), n).ravel()] = act.ravel()
         return out
 
+    def _new_fem(self):
+        f = DeviceFem(self.device)
+        lay = self.layout
+        if lay == "auto":
+            lay = "vertical-minor" if self.iterative.preconditioner == "ljac" else "abi"
+            if self.slab is not None and self.slab["nranks"] > 1 and self._problem.strides[2] == max(self._problem.strides):
+                lay = "abi"     # a vertical major axis cannot be cut into slabs in the vertical-minor layout
+        if lay not in ("abi", "vertical-minor"):
+            raise L.BadInput(f"{self.id}: layout must be 'auto', 'abi' or 'vertical-minor'")
+        f.set_layout(L.LAYOUT_VERTICAL_MINOR if lay == "vertical-minor" else L.LAYOUT_ABI)
+        return f
+
     def _setup_slab(self, f):
         """slab mode: tell the context which planes it owns and map the neighbours' memory (collective)"""
         if self.slab is not None:
@@ -160,7 +175,7 @@ class Static3D(_FemSolver):
         p = self._problem
         if p is None:
             raise L.BadInput(f"{self.id}: no geometry/mesh (problem) specified")
-        f = self._fem = DeviceFem(self.device)
+        f = self._fem = self._new_fem()
         f.set_mesh(p.axes, p.strides)
         self._setup_slab(f)
         f.set_materials(self._elem_materials(), p.T0, p.dT, p.tab_lat, p.tab_vert)
@@ -229,7 +244,7 @@ class Shockley3D(_FemSolver):
             self.beta = p.beta
         if self.js is None:
             self.js = p.js
-        f = self._fem = DeviceFem(self.device)
+        f = self._fem = self._new_fem()
         f.set_mesh(p.axes, p.strides)
         self._setup_slab(f)
         f.set_materials(self._elem_materials(), p.T0, p.dT, p.tab_lat, p.tab_vert)

@@ -151,6 +151,37 @@ def main():
         assert d3 <= 1e-6
     dist.barrier()
 
+    # ---- the same with the vertical axis as the MEDIUM axis of the mesh (order 021): the 'auto' layout stores it fastest
+    # (pfem_set_layout), the slab axis stays the slowest one
+    p21 = cf.config_B(n, order="021")
+    q21, o_lo, o_hi, _ = cf.slab_problem(p21, rank, world)
+    s21 = Static3D(f"slab021_{rank}")
+    s21.device = local
+    s21.problem = q21
+    s21.slab = dict(rank=rank, nranks=world, own_lo=o_lo, own_hi=o_hi, allgather=allgather_bytes)
+    s21.iterative.preconditioner = "ljac"
+    s21.iterative.maxerr = 1e-11
+    s21.iterative.maxit = 50000
+    s21.compute(0)
+    parts21 = allgather_bytes((cf.slab_field_owned(q21, s21.outTemperature(), o_lo, o_hi), s21.stats))
+    s21.invalidate()
+    if rank == 0:
+        T21 = np.concatenate([x[0] for x in parts21], axis=0).ravel()
+        one21 = Static3D("single021")
+        one21.device = 0
+        one21.problem = p21
+        one21.iterative.preconditioner = "ljac"
+        one21.iterative.maxerr = 1e-11
+        one21.iterative.maxit = 50000
+        one21.compute(0)
+        d4 = float(np.abs(T21 - one21.outTemperature()).max())
+        print(f"slab x{world} order 021 line-Jacobi (vertical-minor layout): PCG iterations {parts21[0][1]['lin_iters']} "
+              f"(single GPU {one21.stats['lin_iters']}), max|T021_slab - T021_single| = {d4:.3e} K")
+        assert parts21[0][1]["outer_loops"] == one21.stats["outer_loops"]
+        assert d4 <= 1e-6
+        one21.invalidate()
+    dist.barrier()
+
     # ---- boundary conditions of the 2nd / 3rd kind and radiation in slab mode (corrected form; conditions on the two
     # end planes of the slab axis live on one rank only, the others cross every slab)
     from helpers import face_nodes

@@ -85,10 +85,8 @@ __global__ void k_line_factor(const Grid g, const double* __restrict__ cl, const
     }
 }
 
-struct LineScal {   // what the last block of the line kernel does with the sums
-    int mode;       // 0: PCG iteration, 1: rho -> sc->bz (norm of the lifted rhs in the preconditioner metric)
-};
-
+// What the last block of a line kernel does with the sums.  mode 0: PCG iteration; mode 1: rho -> sc->bz (norm of the lifted
+// rhs in the metric of this preconditioner).
 __device__ __forceinline__ void line_finalize(Scalars* sc, const double rho, const double rr, const double zz, const int mode) {
     if (mode == 1) { sc->bz = rho; return; }
     const double rho_old = sc->rho;

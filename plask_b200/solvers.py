@@ -116,7 +116,8 @@ class _FemSolver:
         f = DeviceFem(self.device)
         lay = self.layout
         if lay == "auto":
-            lay = "vertical-minor" if self.iterative.preconditioner == "ljac" else "abi"
+            # the warp-per-row line kernel holds up to 512 nodes per line; longer vertical axes keep the mesh order (strided kernel)
+            lay = "vertical-minor" if (self.iterative.preconditioner == "ljac" and self._problem.n[2] <= 512) else "abi"
             if self.slab is not None and self.slab["nranks"] > 1 and self._problem.strides[2] == max(self._problem.strides):
                 lay = "abi"     # a vertical major axis cannot be cut into slabs in the vertical-minor layout
         if lay not in ("abi", "vertical-minor"):

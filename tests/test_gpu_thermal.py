@@ -65,6 +65,27 @@ def test_vs_reference_nspcg():
     s.invalidate()
 
 
+@pytest.mark.parametrize("precond", ["jac", "ljac"])
+def test_config_A_full_size_vs_reference_nspcg(precond):
+    """BASELINE configs[0] at its full size (64^3 GaAs/AlGaAs stack, uniform heat): the reference's iterative path
+    (its own NSPCG, cg + ic, tightened maxerr) against the CUDA algorithm, both preconditioners"""
+    if not orc.ref_available():
+        pytest.skip("oracle/_ref not built")
+    p = cf.config_A(64)
+    o = oracle_thermal(p, algorithm="iterative", precond="ic", itmaxerr=1e-12, maxit=5000)
+    o.compute(0)
+    s = Static3D("A64")
+    s.problem = p
+    s.iterative.preconditioner = precond
+    s.iterative.maxerr = 1e-11
+    s.iterative.maxit = 200000
+    s.compute(0)
+    assert s.stats["outer_loops"] == len(o.history)
+    assert np.abs(s.outTemperature() - o.temperatures).max() <= TOL_T
+    assert s.maxT == pytest.approx(o.maxT, abs=TOL_T)
+    s.invalidate()
+
+
 def test_random_problem_linear_solve_and_flux():
     p = random_problem((23, 17, 29), "120", nd_frac=0.02)
     p.maxerr = 1e-6

@@ -377,6 +377,35 @@ class Shockley3D(_FemSolver):
         return float((1e-15 * vol * heat[p.elem_index_grid()]).sum())
 
 
+    def get_total_energy(self, eps=None):
+        """getTotalEnergy (electr3d.cpp:568-600), J: 0.5 eps0 eps |grad V|^2 over the elements of the (masked) mesh, the
+        gradient at the element midpoint.  eps: relative permittivity per element (material->eps(T)); default problem.meta['eps']."""
+        p = self._problem
+        eps = np.asarray(p.meta["eps"] if eps is None else eps, dtype=np.float64)
+        V = self.outVoltage()[np.broadcast_to(p.node_index_grid(), p.n)]
+        lo, up = slice(None, -1), slice(1, None)
+        c = {(a, b, c_): V[a, b, c_] for a in (lo, up) for b in (lo, up) for c_ in (lo, up)}
+        d = self._elem_sizes()
+        d0, d1, d2 = d[0][:, None, None], d[1][None, :, None], d[2][None, None, :]
+        s = lambda f: sum(f(k) * v for k, v in c.items())
+        dvx = -0.25e6 * s(lambda k: 1. if k[0] is up else -1.) / d0
+        dvy = -0.25e6 * s(lambda k: 1. if k[1] is up else -1.) / d1
+        dvz = -0.25e6 * s(lambda k: 1. if k[2] is up else -1.) / d2
+        e3 = eps[p.elem_index_grid()]
+        if self.empty_elements == "exclude" and p.empty is not None:
+            e3 = np.where(np.asarray(p.empty)[p.elem_index_grid()] != 0, 0., e3)   # loop over maskedMesh->elements()
+        epsilon0 = 1. / (4e-7 * np.pi) / 299792458. ** 2
+        return float((0.5e-18 * epsilon0 * d0 * d1 * d2 * e3 * (dvx * dvx + dvy * dvy + dvz * dvz)).sum())
+
+    def get_capacitance(self):
+        """getCapacitance (electr3d.cpp:602-610), pF: exactly two voltage boundary conditions are required."""
+        vals = np.unique(np.asarray(self._problem.bc_values))
+        if len(vals) != 2:
+            raise L.BadInput(f"{self.id}: cannot estimate applied voltage (exactly 2 voltage boundary conditions required)")
+        U = float(vals[1] - vals[0])
+        return 2e12 * self.get_total_energy() / (U * U)
+
+
 class ThermoElectric3D:
     """meta.shockley.ThermoElectric3D (solvers/meta/shockley/thermoelectric.py:160-215) over the two CUDA solvers.
 

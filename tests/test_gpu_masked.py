@@ -30,6 +30,7 @@ def test_shockley3d_reference_case_excluded():
     correct_current = 1e-9 * S * 1. * (np.exp(10.) - 1)
     assert abs(e.get_total_current()) == pytest.approx(correct_current, abs=0.5e-3)       # shockley3d.py:64-65,71-73
     assert e.get_total_heat() == pytest.approx(correct_current * 1., abs=0.5e-3)         # :68-69
+    assert e.get_capacitance() == pytest.approx(8.854187817e-6 * 12.9 * S / 0.02, abs=0.5e-2)   # :66-67, masked elements only
     act = e.masked_nodes()
     assert act.sum() == 764 and p.N == 1100
     V = e.outVoltage()

@@ -55,6 +55,8 @@ def test_reference_case_analytic():
     correct = 1e-9 * 1e6 * 1. * (np.exp(10.) - 1)
     assert abs(s.get_total_current()) == pytest.approx(correct, abs=0.5e-3)
     assert s.get_total_heat() == pytest.approx(correct * 1., abs=0.5e-3)
+    capacitance = 8.854187817e-6 * 12.9 * 1e6 / 0.02                     # shockley3d.py:66-67, pF to 2 decimals
+    assert s.get_capacitance() == pytest.approx(capacitance, abs=0.5e-2)
     s.invalidate()
 
 

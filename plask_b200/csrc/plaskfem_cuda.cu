@@ -1065,7 +1065,10 @@ extern "C" int pfem_set_conductivity(pfem_ctx* ctx, const double* cond) {
 // masked mesh: the field is pinned to 0 on the nodes that are not part of it
 static int mask_field(pfem_ctx* ctx) {
     if (!ctx->has_excluded) return PFEM_OK;
-    k_zero_inactive<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(ctx->g.NP, ctx->inactive, ctx->x);
+    // owned planes only: whether a node of a halo plane belongs to the masked mesh is the neighbour's knowledge (its value
+    // arrives with the halo exchange)
+    const idx_t off = ctx->g.sK * ctx->g.kown0, cnt = ctx->g.sK * (ctx->g.kown1 - ctx->g.kown0);
+    k_zero_inactive<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(cnt, ctx->inactive + off, ctx->x + off);
     KCHECK(); LAUNCHED(1);
     return PFEM_OK;
 }

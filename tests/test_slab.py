@@ -32,5 +32,6 @@ def test_slab_solve_two_gpus():
     assert "max|T_slab - T_single|" in r.stdout
     assert "max|Tl_slab - T_slab|" in r.stdout
     assert "max|T021_slab - T021_single|" in r.stdout
+    assert "max|Tm_slab - Tm_single|" in r.stdout
     assert "max|Tb_slab - Tb_single|" in r.stdout
     assert "max|V_slab - V_single|" in r.stdout

@@ -199,3 +199,31 @@ def _elem_volumes(p):
     out = np.empty(p.E)
     out[p.elem_index_grid().ravel()] = vol.ravel()
     return out
+
+
+@pytest.mark.parametrize("precond", ["jac", "ljac"])
+def test_degenerate_systems(precond):
+    """edge cases of the linear system: every node fixed (no free row at all), and a homogeneous problem whose
+    solution is the boundary value itself (zero right-hand side after lifting)"""
+    rng = np.random.default_rng(9)
+    p = cf.config_A(9)
+    vals = rng.uniform(290., 310., size=p.N)
+    p.bc_nodes = np.arange(p.N, dtype=np.uintp)
+    p.bc_values = vals
+    s = Static3D("allfixed")
+    s.problem = p
+    s.iterative.preconditioner = precond
+    s.compute(1)
+    assert np.array_equal(s.outTemperature(), vals) and s.stats["lin_iters"] == 0 and s.iterative.converged
+    s.invalidate()
+    p = cf.config_A(9)
+    p.heat = np.zeros(p.E)
+    s = Static3D("homogeneous")
+    s.problem = p
+    s.inittemp = 345.
+    s.iterative.preconditioner = precond
+    s.iterative.maxerr = 1e-12
+    err = s.compute(0)
+    T = s.outTemperature()
+    assert np.abs(T - 300.).max() <= 1e-6 and s.stats["outer_loops"] <= 3 and err >= 44.9   # first loop moves 345 K -> 300 K
+    s.invalidate()

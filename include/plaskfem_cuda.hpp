@@ -356,6 +356,32 @@ class Context {
         check(pfem_set_junctions(ctx_, (uint32_t)act.size(), act.data(), elem_junc.data(), elem_role.empty() ? nullptr : elem_role.data(),
                                  pcond, ncond, beta_col.size(), junc_cond.data(), beta_col.data(), js_col.data(), stable ? 1 : 0));
     }
+    // internal layout, before set_mesh: PFEM_LAYOUT_VERTICAL_MINOR keeps the vertical lines contiguous for the 'ljac' preconditioner
+    void set_layout(int layout) { check(pfem_set_layout(ctx_, layout)); }
+    // EMPTY-material / "noheat" elements produce no Joule heat (electr3d.cpp:472)
+    void set_noheat(const std::vector<uint8_t>& noheat) { check(pfem_set_noheat(ctx_, noheat.empty() ? nullptr : noheat.data())); }
+    // Device-resident field exchange of the ThermoElectric meta loop (thermoelectric.py:207-211): call on the RECEIVING solver.
+    //   electrical.take_temperature_from(thermal)  ==  inTemperature(elementMesh) <- thermal.outTemperature   (electr3d.cpp:203-205)
+    //   thermal.take_heat_from(electrical)         ==  inHeat(elementMesh)        <- electrical.outHeat      (therm3d.cpp:179)
+    // Both interpolate linearly like RectilinearMesh3D::interpolateLinear (rectilinear3d.hpp:802-845); the meshes may differ.
+    void take_temperature_from(const Context& thermal) { check(pfem_transfer_temperature(ctx_, thermal.ctx_)); }
+    void take_heat_from(const Context& electrical) {
+        int rc = pfem_transfer_heat(ctx_, electrical.ctx_);
+        if (rc < 0) { const char* d = pfem_last_error(electrical.ctx_); if (d && *d) throw ComputationError(id_ + ": " + d); }
+        check(rc);
+    }
+    // Slab mode (one Context per GPU / process): the local mesh holds the owned planes of the major axis plus one halo plane
+    // per neighbour; exchange the blobs of all ranks with any host transport, then connect.  Solves are collective afterwards.
+    void slab_configure(int rank, int nranks, size_t own_lo, size_t own_hi) { check(pfem_slab_configure(ctx_, rank, nranks, own_lo, own_hi)); }
+    std::vector<unsigned char> slab_export() {
+        std::vector<unsigned char> blob(pfem_slab_blob_size());
+        check(pfem_slab_export(ctx_, blob.data()));
+        return blob;
+    }
+    void slab_connect(const std::vector<unsigned char>& all_blobs) {
+        if (all_blobs.size() % pfem_slab_blob_size() != 0) throw BadInput(id_ + ": slab blobs have the wrong size");
+        check(pfem_slab_connect(ctx_, all_blobs.data()));
+    }
     void get_field(double* x) { check(pfem_get_field(ctx_, x)); }
     void get_elem(int what, double* out, const uint8_t* noheat = nullptr) { check(pfem_get_elem(ctx_, what, noheat, out)); }
     void get_junction_cond(double* jc) { check(pfem_get_junction_cond(ctx_, jc)); }

@@ -192,6 +192,62 @@ static int gpu_tests() {
         printf("convection: max|T - T_exact| = %.3e K (T(H) = %.4f)\n", maxd, TH);
         REQUIRE(maxd < 1e-6);
     }
+    // ---- device-resident field exchange (ThermoElectric meta loop): heat taken from the electrical context on the device
+    //      equals heat downloaded and passed back through set_source
+    {
+        Mesh m = make_mesh(8, 7, 15, ORDER_012);
+        const size_t E = m.elements();
+        std::vector<size_t> bottom, top;
+        for (size_t i0 = 0; i0 < m.n(0); ++i0) for (size_t i1 = 0; i1 < m.n(1); ++i1) {
+            bottom.push_back(m.node(i0, i1, 0));
+            top.push_back(m.node(i0, i1, m.n(2) - 1));
+        }
+        std::vector<uint32_t> ids(E, 0);
+        Context el(0, "electrical");
+        el.set_layout(PFEM_LAYOUT_VERTICAL_MINOR);
+        el.set_mesh(m);
+        el.set_materials(ids, sample_tables(1, [](uint32_t, double T) { return std::make_pair(1e4 * 300. / T, 2e4 * 300. / T); }, 250., 1., 400));
+        el.fill_field(0.);
+        Dirichlet bv;
+        bv.add(bottom, 0.);
+        bv.add(top, 0.3);
+        el.set_dirichlet(bv);
+        el.set_source(nullptr);
+        el.set_elem_temperature(nullptr, 300.);
+        el.set_noheat(std::vector<uint8_t>());
+        IterParams ip;
+        ip.maxerr = 1e-12; ip.maxit = 20000;
+        el.solve(false, ip, 0.05, 1);
+        REQUIRE(ip.converged);
+        std::vector<double> heat(E);
+        el.get_elem(PFEM_ELEM_HEAT, heat.data());
+        double hmax = 0.;
+        for (double h : heat) hmax = std::fmax(hmax, h);
+        REQUIRE(hmax > 0.);
+        std::vector<double> T[2];
+        for (int via_device = 0; via_device < 2; ++via_device) {
+            Context th(0, "thermal");
+            th.set_mesh(m);
+            th.set_materials(ids, sample_tables(1, [](uint32_t, double) { return std::make_pair(44., 44.); }, 250., 1., 400));
+            th.fill_field(300.);
+            Dirichlet bt;
+            bt.add(bottom, 300.);
+            th.set_dirichlet(bt);
+            if (via_device) th.take_heat_from(el); else th.set_source(heat.data());
+            IterParams it;
+            it.maxerr = 1e-12; it.maxit = 20000;
+            it.preconditioner = IterParams::PRECOND_LJAC;
+            th.solve(true, it, 0.05, 1);
+            REQUIRE(it.converged);
+            T[via_device].resize(m.size());
+            th.get_field(T[via_device].data());
+            if (via_device) el.take_temperature_from(th);     // and back: temperatures at the electrical element midpoints
+        }
+        double maxd = 0., maxT = 0.;
+        for (size_t i = 0; i < m.size(); ++i) { maxd = std::fmax(maxd, std::fabs(T[0][i] - T[1][i])); maxT = std::fmax(maxT, T[1][i]); }
+        printf("field exchange: max|T_device - T_host| = %.3e K, max T = %.4f K\n", maxd, maxT);
+        REQUIRE(maxd < 1e-9 && maxT > 300.);
+    }
     // ---- noconv policy
     {
         Mesh m = make_mesh(9, 7, 21, ORDER_012);

@@ -400,7 +400,10 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         else step(N(), N(), Y(), Y(), nsteps, w1, w0, zd1, zd0);
     }
     if (!FUSED) return;
-    if (grid_reduce<NRED, false>(red, partials, &sc->ticket[0], sRed, sh_flag, slab)) {
+    // system-scope fence only in the CTAs that stored into a neighbour's halo planes (first / last chunk); the others publish
+    // their partials with a device-scope fence, the last CTA's own system fence before the flag covers them by cumulativity
+    const bool cta_pushes = (push_lo && k0 == g.kown0) || (push_hi && k1 == g.kown1);
+    if (grid_reduce<NRED, false>(red, partials, &sc->ticket[0], sRed, sh_flag, cta_pushes)) {
         if (sc->comm) rank_allreduce<NRED, false>(red, sc->comm, sRed);
         if (tid == 0 && LINE) {
             // line-Jacobi PCG: rho, beta and the stopping test belong to the line kernel; here only alpha = rho / p'.q'

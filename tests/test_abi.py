@@ -48,15 +48,17 @@ def test_struct_layouts_match_header(lib, tmp_path):
 #include <stddef.h>
 #include "plaskfem_cuda.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(pfem_junction), sizeof(pfem_opts), sizeof(pfem_stats),
-         offsetof(pfem_opts, outer_tol), offsetof(pfem_stats, maxcur), offsetof(pfem_stats, kernel_launches));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(pfem_junction), sizeof(pfem_opts), sizeof(pfem_stats),
+         offsetof(pfem_opts, outer_tol), offsetof(pfem_stats, maxcur), offsetof(pfem_stats, kernel_launches),
+         sizeof(pfem_boundary), offsetof(pfem_boundary, rad_ambient), offsetof(pfem_boundary, verbatim));
   return 0; }
 """)
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     want = [ctypes.sizeof(_lib.Junction), ctypes.sizeof(_lib.Opts), ctypes.sizeof(_lib.Stats),
-            _lib.Opts.outer_tol.offset, _lib.Stats.maxcur.offset, _lib.Stats.kernel_launches.offset]
+            _lib.Opts.outer_tol.offset, _lib.Stats.maxcur.offset, _lib.Stats.kernel_launches.offset,
+            ctypes.sizeof(_lib.Boundary), _lib.Boundary.rad_ambient.offset, _lib.Boundary.verbatim.offset]
     assert got == want
 
 

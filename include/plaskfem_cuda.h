@@ -221,6 +221,13 @@ int pfem_solve_shockley(pfem_ctx* ctx, const pfem_opts* opts, pfem_stats* stats)
 /* ---- results ------------------------------------------------------------------------- */
 int pfem_get_field(pfem_ctx* ctx, double* x);  /* temperatures / potential, N doubles */
 
+/* Provider on a foreign mesh (getTemperatures / getVoltage with INTERPOLATION_LINEAR, therm3d.cpp:387-395,
+ * electr3d.cpp:518-524): the field interpolated linearly, exactly like RectilinearMesh3D::interpolateLinear
+ * (rectilinear3d.hpp:802-845; constant outside the mesh), at the tensor-product points of the target axes; out[] is dense
+ * with the target mesh's own index strides (any of its 6 iteration orders).  Not available in slab mode. */
+int pfem_interpolate_field(pfem_ctx* ctx, const size_t n[3], const double* ax0, const double* ax1, const double* ax2,
+                           const size_t stride[3], double* out);
+
 typedef enum {
     PFEM_ELEM_COND = 0,     /* conds, E x (c00,c11)  [W/m/K or S/m]                          */
     PFEM_ELEM_CURRENT = 1,  /* current, E x 3 [kA/cm2]            (electr3d.cpp:399-411)     */

@@ -383,6 +383,12 @@ class Context {
         check(pfem_slab_connect(ctx_, all_blobs.data()));
     }
     void get_field(double* x) { check(pfem_get_field(ctx_, x)); }
+    // provider on a foreign rectilinear mesh (getTemperatures / getVoltage with INTERPOLATION_LINEAR): out in `dst`'s own order
+    void interpolate_field(const Mesh& dst, double* out) {
+        size_t n[3] = {dst.n(0), dst.n(1), dst.n(2)}, s[3];
+        dst.strides(s);
+        check(pfem_interpolate_field(ctx_, n, dst.axis[0].data(), dst.axis[1].data(), dst.axis[2].data(), s, out));
+    }
     void get_elem(int what, double* out, const uint8_t* noheat = nullptr) { check(pfem_get_elem(ctx_, what, noheat, out)); }
     void get_junction_cond(double* jc) { check(pfem_get_junction_cond(ctx_, jc)); }
 

@@ -87,6 +87,7 @@ SYMBOLS = {
     "pfem_solve_thermal": (C.c_int, [_vp, C.POINTER(Opts), C.POINTER(Stats)]),
     "pfem_solve_shockley": (C.c_int, [_vp, C.POINTER(Opts), C.POINTER(Stats)]),
     "pfem_get_field": (C.c_int, [_vp, c_dp]),
+    "pfem_interpolate_field": (C.c_int, [_vp, _szp, c_dp, c_dp, c_dp, _szp, c_dp]),
     "pfem_get_elem": (C.c_int, [_vp, C.c_int, _u8p, c_dp]),
     "pfem_get_junction_cond": (C.c_int, [_vp, c_dp]),
     "pfem_set_noheat": (C.c_int, [_vp, _u8p]),

@@ -700,4 +700,32 @@ __global__ void k_interp_to_elems(const Grid gd, const idx_t ss0, const idx_t ss
     dst[i + gd.sJ * j + gd.sK * k] = __dadd_rn(lo, __dmul_rn(w, __dsub_rn(hi, lo)));
 }
 
+// The same interpolation onto the tensor-product points of a target mesh given by its axes (providers on a foreign mesh:
+// getTemperatures / getVoltage with INTERPOLATION_LINEAR, therm3d.cpp:387-395); out is dense with the target's own strides.
+__global__ void k_interp_to_points(const int n0, const int n1, const int n2, const idx_t os0, const idx_t os1, const idx_t os2,
+                                   const idx_t ss0, const idx_t ss1, const idx_t ss2, const double* __restrict__ src,
+                                   const InterpAxis a0, const InterpAxis a1, const InterpAxis a2, double* __restrict__ out) {
+    const idx_t total = (idx_t)n0 * n1 * n2;
+    for (idx_t m = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; m < total; m += (idx_t)gridDim.x * blockDim.x) {
+        const int i2 = (int)(m % n2), i1 = (int)((m / n2) % n1), i0 = (int)(m / ((idx_t)n2 * n1));
+        const idx_t l0 = a0.ilo[i0] * ss0, h0 = a0.ihi[i0] * ss0;
+        const idx_t l1 = a1.ilo[i1] * ss1, h1 = a1.ihi[i1] * ss1;
+        const idx_t l2 = a2.ilo[i2] * ss2, h2 = a2.ihi[i2] * ss2;
+        const double back = a0.lo[i0], front = a0.hi[i0], px = a0.pt[i0];
+        const double left = a1.lo[i1], right = a1.hi[i1], py = a1.pt[i1];
+        const double bottom = a2.lo[i2], top = a2.hi[i2], pz = a2.pt[i2];
+        const double dxh = __dsub_rn(front, px), dxl = __dsub_rn(px, back);
+        const double dyh = __dsub_rn(right, py), dyl = __dsub_rn(py, left);
+        const double wy = __dsub_rn(right, left), wx = __dsub_rn(front, back);
+        auto plane = [&](idx_t z) {
+            const double b = __dadd_rn(__dmul_rn(src[l0 + l1 + z], dxh), __dmul_rn(src[h0 + l1 + z], dxl));
+            const double t = __dadd_rn(__dmul_rn(src[l0 + h1 + z], dxh), __dmul_rn(src[h0 + h1 + z], dxl));
+            return __ddiv_rn(__ddiv_rn(__dadd_rn(__dmul_rn(b, dyh), __dmul_rn(t, dyl)), wy), wx);
+        };
+        const double lo = plane(l2), hi = plane(h2);
+        const double w = __ddiv_rn(__dsub_rn(pz, bottom), __dsub_rn(top, bottom));
+        out[i0 * os0 + i1 * os1 + i2 * os2] = __dadd_rn(lo, __dmul_rn(w, __dsub_rn(hi, lo)));
+    }
+}
+
 }  // namespace pfem

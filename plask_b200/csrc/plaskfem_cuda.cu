@@ -1529,15 +1529,16 @@ extern "C" int pfem_set_noheat(pfem_ctx* ctx, const uint8_t* noheat) {
 // Bracketing tables of prepareInterpolationForAxis (plask/mesh/axis1d.cpp:99-156, no symmetry / periodicity) for the
 // midpoints of `dst_ax` in the source axis `src` (node coordinates, or their midpoints when src_mid).
 struct AxisTab { std::vector<int> ilo, ihi; std::vector<double> lo, hi, pt; };
-static AxisTab make_axis_tab(const std::vector<double>& src_nodes, bool src_mid, const std::vector<double>& dst_ax) {
+// dst_mid: the targets are the midpoints of dst_ax (element mesh of a context), else the points of dst_ax themselves
+static AxisTab make_axis_tab(const std::vector<double>& src_nodes, bool src_mid, const std::vector<double>& dst_ax, bool dst_mid = true) {
     std::vector<double> mid;
     if (src_mid) { mid.resize(src_nodes.size() - 1); for (size_t i = 0; i + 1 < src_nodes.size(); ++i) mid[i] = (src_nodes[i] + src_nodes[i + 1]) * 0.5; }
     const std::vector<double>& src = src_mid ? mid : src_nodes;
-    const size_t n = src.size(), m = dst_ax.size() - 1;
+    const size_t n = src.size(), m = dst_mid ? dst_ax.size() - 1 : dst_ax.size();
     AxisTab t;
     t.ilo.resize(m); t.ihi.resize(m); t.lo.resize(m); t.hi.resize(m); t.pt.resize(m);
     for (size_t j = 0; j < m; ++j) {
-        const double p = (dst_ax[j] + dst_ax[j + 1]) * 0.5;   // MidpointAxis::at, axis1d.cpp:51-53
+        const double p = dst_mid ? (dst_ax[j] + dst_ax[j + 1]) * 0.5 : dst_ax[j];   // MidpointAxis::at, axis1d.cpp:51-53
         size_t up = std::upper_bound(src.begin(), src.end(), p) - src.begin();
         size_t ilo, ihi = up; double lo, hi;
         if (up == 0) { ilo = 0; lo = src[0] - 1.; } else { ilo = up - 1; lo = src[up - 1]; }
@@ -1588,6 +1589,63 @@ static int interp_to_elems(pfem_ctx* dst, pfem_ctx* src, const double* src_arr, 
         dst->launches += 1;
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(dst->stream);
+    cudaFree(dbuf);
+    CU(e);
+    return PFEM_OK;
+}
+
+// Provider on a foreign rectilinear mesh: the unknown field interpolated linearly at the tensor-product points of the target axes.
+extern "C" int pfem_interpolate_field(pfem_ctx* ctx, const size_t n[3], const double* ax0, const double* ax1, const double* ax2,
+                                      const size_t stride[3], double* out) {
+    NEED_MESH();
+    if (!n || !ax0 || !ax1 || !ax2 || !stride || !out) FAIL(PFEM_ERR_BAD_INPUT, "null argument");
+    if (ctx->nranks > 1) FAIL(PFEM_ERR_BAD_INPUT, "interpolation onto a foreign mesh is not available in slab mode (download the field instead)");
+    const double* ax[3] = {ax0, ax1, ax2};
+    size_t total = 1, ni = 0, nd = 0;
+    AxisTab tab[3];
+    for (int a = 0; a < 3; ++a) {
+        if (n[a] < 1) FAIL(PFEM_ERR_BAD_INPUT, "target axis %d is empty", a);
+        total *= n[a];
+        tab[a] = make_axis_tab(ctx->hax[a], false, std::vector<double>(ax[a], ax[a] + n[a]), false);
+        ni += 2 * n[a]; nd += 3 * n[a];
+    }
+    if (total > 0x7fffffffull * 4) FAIL(PFEM_ERR_BAD_INPUT, "target mesh too large");
+    {   // the output strides must be an iteration order of the target mesh (dense array of `total` values)
+        int o[3] = {0, 1, 2};
+        std::sort(o, o + 3, [&](int p, int q) { return stride[p] < stride[q]; });
+        if (stride[o[0]] != 1 || stride[o[1]] != n[o[0]] || stride[o[2]] != n[o[0]] * n[o[1]])
+            FAIL(PFEM_ERR_BAD_INPUT, "output strides are not an iteration order of the target mesh");
+    }
+    TRY(mask_field(ctx));
+    const size_t tbytes = nd * sizeof(double) + ni * sizeof(int), off_out = ((tbytes + 15) / 16) * 16;
+    std::vector<unsigned char> hb(tbytes);
+    double* hd = reinterpret_cast<double*>(hb.data());
+    int* hi = reinterpret_cast<int*>(hb.data() + nd * sizeof(double));
+    void* dbuf = nullptr;
+    CU(cudaMalloc(&dbuf, off_out + total * sizeof(double)));
+    double* dd = reinterpret_cast<double*>(dbuf);
+    int* di = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(dbuf) + nd * sizeof(double));
+    double* dout = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(dbuf) + off_out);
+    InterpAxis ia[3];
+    size_t od = 0, oi = 0;
+    for (int a = 0; a < 3; ++a) {
+        const size_t m = n[a];
+        memcpy(hd + od, tab[a].lo.data(), m * 8); ia[a].lo = dd + od; od += m;
+        memcpy(hd + od, tab[a].hi.data(), m * 8); ia[a].hi = dd + od; od += m;
+        memcpy(hd + od, tab[a].pt.data(), m * 8); ia[a].pt = dd + od; od += m;
+        memcpy(hi + oi, tab[a].ilo.data(), m * 4); ia[a].ilo = di + oi; oi += m;
+        memcpy(hi + oi, tab[a].ihi.data(), m * 4); ia[a].ihi = di + oi; oi += m;
+    }
+    cudaError_t e = cudaMemcpyAsync(dbuf, hb.data(), tbytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        const Grid& g = ctx->g;
+        k_interp_to_points<<<vec_blocks(ctx), 256, 0, ctx->stream>>>((int)n[0], (int)n[1], (int)n[2], (idx_t)stride[0], (idx_t)stride[1],
+                                                                      (idx_t)stride[2], g.ps[0], g.ps[1], g.ps[2], ctx->x, ia[0], ia[1], ia[2], dout);
+        e = cudaGetLastError();
+        ctx->launches += 1;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(dbuf);
     CU(e);
     return PFEM_OK;

@@ -211,6 +211,15 @@ class DeviceFem:
         self._ck(self.lib.pfem_get_field(self.ctx, _dp(x)))
         return x
 
+    def interpolate_field(self, axes, strides):
+        """the field at the tensor-product points of a foreign rectilinear mesh (linear interpolation on the device)"""
+        ax = [_f64(a) for a in axes]
+        n = (L.c_sz * 3)(*[len(a) for a in ax])
+        s = (L.c_sz * 3)(*[int(v) for v in strides])
+        out = np.empty(len(ax[0]) * len(ax[1]) * len(ax[2]))
+        self._ck(self.lib.pfem_interpolate_field(self.ctx, n, _dp(ax[0]), _dp(ax[1]), _dp(ax[2]), s, _dp(out)))
+        return out
+
     def get_elem(self, what, noheat=None):
         nc = {L.ELEM_COND: 2, L.ELEM_CURRENT: 3, L.ELEM_HEAT: 1, L.ELEM_FLUX: 3}[what]
         out = np.empty((self.E, nc))

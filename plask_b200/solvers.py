@@ -207,10 +207,17 @@ class Static3D(_FemSolver):
         return st["toterr"]
 
     # providers, on the solver's own mesh (interpolation onto other meshes is a "next" row)
-    def outTemperature(self):
+    def outTemperature(self, mesh=None):
+        """temperatures on the solver's own mesh, or (mesh = (axes, order)) interpolated linearly onto a foreign rectilinear
+        mesh like getTemperatures(dst_mesh, INTERPOLATION_LINEAR) (therm3d.cpp:387-395)"""
         if not self.initialized:
-            return np.full(self._problem.N, float(self.inittemp))
-        return self._fem.get_field()
+            n = self._problem.N if mesh is None else int(np.prod([len(a) for a in mesh[0]]))
+            return np.full(n, float(self.inittemp))
+        if mesh is None:
+            return self._fem.get_field()
+        from .configs import strides_for
+        axes, order = mesh
+        return self._fem.interpolate_field(axes, strides_for(tuple(len(a) for a in axes), order)[0])
 
     def outHeatFlux(self):
         return self._fem.get_elem(L.ELEM_FLUX)
@@ -320,8 +327,13 @@ class Shockley3D(_FemSolver):
         return st["toterr"]
 
     # providers on the solver's own meshes
-    def outVoltage(self):
-        return self._fem.get_field()
+    def outVoltage(self, mesh=None):
+        """potential on the solver's own mesh, or interpolated linearly onto a foreign rectilinear mesh (axes, order)"""
+        if mesh is None:
+            return self._fem.get_field()
+        from .configs import strides_for
+        axes, order = mesh
+        return self._fem.interpolate_field(axes, strides_for(tuple(len(a) for a in axes), order)[0])
 
     def outCurrentDensity(self):
         return self._fem.get_elem(L.ELEM_CURRENT)

@@ -102,3 +102,32 @@ def test_heat_without_electrical_solution_is_an_error():
     with pytest.raises(L.BadInput):
         te.thermal.compute(1)      # NoValue("heat density") in the reference (electr3d.cpp:539)
     te.invalidate()
+
+
+@pytest.mark.parametrize("order_src,order_dst,layout", [("012", "201", "abi"), ("210", "012", "vertical-minor"), ("120", "120", "abi")])
+def test_provider_on_foreign_mesh(order_src, order_dst, layout):
+    """outTemperature(mesh) with linear interpolation (getTemperatures, therm3d.cpp:387-395 ->
+    RectilinearMesh3D::interpolateLinear, rectilinear3d.hpp:802-845): bit-equal to the oracle's restatement, including
+    points outside the source mesh (constant continuation) and points that coincide with source nodes"""
+    from oracle import oracle as orc
+    from plask_b200.solvers import Static3D
+    p = cf.config_B((14, 16, 40), order=order_src)
+    s = Static3D("prov")
+    s.problem = p
+    s.layout = layout
+    s.iterative.maxerr = 1e-10
+    s.compute(1)
+    T = s.outTemperature()
+    rng = np.random.default_rng(4)
+    axes = []
+    for a, m in zip(p.axes, (9, 11, 23)):
+        lo, hi = a[0] - 0.1 * (a[-1] - a[0]), a[-1] + 0.1 * (a[-1] - a[0])
+        pts = np.sort(np.concatenate([rng.uniform(lo, hi, size=m - 3), a[[0, len(a) // 2, -1]]]))
+        axes.append(pts)
+    n = tuple(len(a) for a in axes)
+    dst_strides = cf.strides_for(n, order_dst)[0]
+    ref = orc.interp_linear(p.axes, p.strides, T, axes, dst_strides, int(np.prod(n)))
+    got = s.outTemperature((axes, order_dst))
+    assert np.array_equal(got, ref)
+    assert got.min() >= T.min() - 1e-9 and got.max() <= T.max() + 1e-9      # interpolation::trilinear rounds at 1e-13
+    s.invalidate()

@@ -241,19 +241,22 @@ k_line_strided(const Grid g, const double* r_in, const double* __restrict__ q_in
     __shared__ int sh_flag;
     if (mode == 0 && sc->done) return;
     const double alpha = mode == 0 ? sc->alpha : 0.;
-    const int vd = g.vdim;   // 1 (lines along J, one per (i, owned plane k)) or 2 (lines along K, never in slab mode)
-    const int nL = vd == 1 ? g.nJ : g.nK;
-    const int b0 = vd == 1 ? g.kown0 : 0;
-    const int nB = vd == 1 ? g.kown1 - g.kown0 : g.nJ;
-    const idx_t sL = vd == 1 ? g.sJ : g.sK, sB = vd == 1 ? g.sK : g.sJ;
-    const idx_t lines = (idx_t)g.nI * nB;
+    // vd = 1: lines along J, one per (i, owned plane k);  vd = 2: lines along K, one per (i, j), never in slab mode;
+    // vd = 0: lines along I, one per (j, owned plane k) — the uncoalesced fallback for lines longer than k_line_I holds
+    const int vd = g.vdim;
+    const int nL = vd == 0 ? g.nI : vd == 1 ? g.nJ : g.nK;
+    const int nA = vd == 0 ? g.nJ : g.nI;
+    const int b0 = vd == 2 ? 0 : g.kown0;
+    const int nB = vd == 2 ? g.nJ : g.kown1 - g.kown0;
+    const idx_t sL = vd == 0 ? 1 : vd == 1 ? g.sJ : g.sK, sA = vd == 0 ? g.sJ : 1, sB = vd == 2 ? g.sJ : g.sK;
+    const idx_t lines = (idx_t)nA * nB;
     double acc[3] = {0., 0., 0.};
     for (idx_t line = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; line < lines; line += (idx_t)gridDim.x * blockDim.x) {
-        const int bi = b0 + (int)(line / g.nI);
-        const idx_t n0 = (line % g.nI) + sB * bi;
-        double* const zp = (vd == 1 && po.z_lo && bi == g.kown0) ? po.z_lo - sB * bi
-                         : (vd == 1 && po.z_hi && bi == g.kown1 - 1) ? po.z_hi - sB * bi : nullptr;   // halo copy of this plane
-        double* const zp2 = (vd == 1 && po.z_lo && po.z_hi && bi == g.kown0 && bi == g.kown1 - 1) ? po.z_hi - sB * bi : nullptr;
+        const int bi = b0 + (int)(line / nA);
+        const idx_t n0 = sA * (line % nA) + sB * bi;
+        double* const zp = (vd != 2 && po.z_lo && bi == g.kown0) ? po.z_lo - sB * bi
+                         : (vd != 2 && po.z_hi && bi == g.kown1 - 1) ? po.z_hi - sB * bi : nullptr;   // halo copy of this plane
+        double* const zp2 = (vd != 2 && po.z_lo && po.z_hi && bi == g.kown0 && bi == g.kown1 - 1) ? po.z_hi - sB * bi : nullptr;
         double y = 0.;
         for (int m0 = 0; m0 < nL; m0 += U) {
             double rp[U], lv[U], dv[U];

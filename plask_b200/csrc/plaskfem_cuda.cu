@@ -1103,7 +1103,7 @@ static inline int line_seg(const Grid& g) {   // nodes per lane of the I-line ke
 static int launch_line_solve(pfem_ctx* ctx, const double* r_in, const double* q_in, double* r_out, int mode) {
     const Grid& g = ctx->g;
     const PeerOut po = peer_out(ctx, 0);   // only the z pointers are used
-    if (g.vdim == 0) {
+    if (g.vdim == 0 && line_seg(g) > 0) {
         const idx_t rows = (idx_t)g.nJ * (g.kown1 - g.kown0);
         // balanced: every warp gets the same number of rows (8 warps per block)
         static const int cap_env = getenv("PFEM_LINE_BLOCKS") ? atoi(getenv("PFEM_LINE_BLOCKS")) : 0;
@@ -1114,11 +1114,12 @@ static int launch_line_solve(pfem_ctx* ctx, const double* r_in, const double* q_
 #define PFEM_LINE_CASE(S) case S: k_line_I<S><<<blocks, 256, 0, ctx->stream>>>(g, r_in, q_in, ctx->ll, ctx->ld, r_out, ctx->lz, ctx->d_sc, ctx->partials, mode, po); break;
         switch (line_seg(g)) {
             PFEM_LINE_CASE(2) PFEM_LINE_CASE(4) PFEM_LINE_CASE(8) PFEM_LINE_CASE(16)
-            default: FAIL(PFEM_ERR_BAD_INPUT, "line preconditioner along the minor axis handles up to 512 nodes per line");
+            default: FAIL(PFEM_ERR_STATE, "no warp-per-row line kernel for %d nodes per line", g.nI);
         }
 #undef PFEM_LINE_CASE
     } else {
-        const idx_t lines = (idx_t)g.nI * (g.vdim == 1 ? g.kown1 - g.kown0 : g.nJ);
+        // lines along J or K, or along I when they are longer than the warp-per-row kernel holds (> 512 nodes)
+        const idx_t lines = g.vdim == 0 ? (idx_t)g.nJ * (g.kown1 - g.kown0) : (idx_t)g.nI * (g.vdim == 1 ? g.kown1 - g.kown0 : g.nJ);
         int blocks = (int)std::min<idx_t>((lines + 127) / 128, (idx_t)ctx->sm_count * 16);
         if (blocks < 1) blocks = 1;
         k_line_strided<<<blocks, 128, 0, ctx->stream>>>(g, r_in, q_in, ctx->ll, ctx->ld, r_out, ctx->lz, ctx->d_sc, ctx->partials, mode, po);

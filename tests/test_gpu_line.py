@@ -41,7 +41,8 @@ def test_config_B_small_line_vs_cholesky(order):
 
 
 @pytest.mark.parametrize("n,order", [((7, 9, 11), "012"), ((34, 5, 19), "210"), ((3, 3, 3), "012"), ((2, 2, 2), "120"),
-                                     ((70, 6, 5), "012"), ((5, 6, 70), "012"), ((5, 6, 130), "012"), ((4, 5, 300), "012")])
+                                     ((70, 6, 5), "012"), ((5, 6, 70), "012"), ((5, 6, 130), "012"), ((4, 5, 300), "012"),
+                                     ((3, 4, 515), "012"), ((3, 4, 700), "012")])   # > 512 nodes per line: the thread-per-line fallback
 def test_random_problem_line_linear_solve(n, order):
     """random conductivities and Dirichlet sets, line lengths that straddle the lane segments of the warp-per-row kernel"""
     p = random_problem(n, order, nd_frac=0.1)

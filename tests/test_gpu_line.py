@@ -99,3 +99,23 @@ def test_warm_start_converged_and_maxit():
     s.compute(1)
     assert not s.iterative.converged and s.iterative.iters == 5
     s.invalidate()
+
+
+def test_iteration_counts_like_the_reference_nspcg():
+    """the two preconditioners are NSPCG's jac2 / ljac2 (extlib/nspcg/nspcg.f:1577,1592): on the same nonlinear solve (order 012:
+    NSPCG's lines along the minor axis are the vertical lines) the PCG iteration counts are those of the reference's own
+    cg+jac and cg+ljac up to the different stopping tests (NSPCG: pseudo-residual test #2; here: three residual norms)"""
+    from oracle import oracle as orc
+    if not orc.ref_available():
+        pytest.skip("oracle/_ref not built")
+    p = cf.config_B((18, 20, 44), order="012")
+    for pre in ("jac", "ljac"):
+        o = oracle_thermal(p, algorithm="iterative", precond=pre, itmaxerr=1e-10, maxit=20000)
+        o.compute(0)
+        ref_iters = sum(h["iters"] for h in o.history)
+        s = _thermal(p, pre, tol=1e-10)
+        s.compute(0)
+        assert s.stats["outer_loops"] == len(o.history)
+        assert 0.6 * ref_iters <= s.stats["lin_iters"] <= 1.6 * ref_iters, (pre, s.stats["lin_iters"], ref_iters)
+        assert np.abs(s.outTemperature() - o.temperatures).max() <= 1e-3
+        s.invalidate()

@@ -116,6 +116,10 @@ def test_iteration_counts_like_the_reference_nspcg():
         s = _thermal(p, pre, tol=1e-10)
         s.compute(0)
         assert s.stats["outer_loops"] == len(o.history)
-        assert 0.6 * ref_iters <= s.stats["lin_iters"] <= 1.6 * ref_iters, (pre, s.stats["lin_iters"], ref_iters)
+        if pre == "jac":      # same preconditioner: same counts up to the stopping test (observed 4863 against 5664)
+            assert 0.6 * ref_iters <= s.stats["lin_iters"] <= 1.4 * ref_iters, (s.stats["lin_iters"], ref_iters)
+        else:                 # the reference hands NSPCG kblsz = n_minor - 1 (iterative_matrix.hpp:388): its blocks drift against
+            #                   the mesh lines and its ljac needs 3x more iterations than true mesh lines (observed 748 against 2183)
+            assert s.stats["lin_iters"] <= ref_iters, (s.stats["lin_iters"], ref_iters)
         assert np.abs(s.outTemperature() - o.temperatures).max() <= 1e-3
         s.invalidate()

@@ -124,3 +124,38 @@ def test_shockley3d_analytic_excluded():
                              beta=10., js=1., maxerr=1e-3, algorithm="cholesky", noheat=c["noheat"], eps=c["eps"])
     f.compute(len(s.history))
     assert np.abs(s.potential - f.potential)[A.active].max() < 1e-9
+
+
+def test_brick_stiffness_is_the_exact_galerkin_integral():
+    """The closed-form 8x8 brick matrix of setMatrix (therm3d.cpp:226-237, electr3d.cpp:326-337) restated in
+    oracle/fem3d_oracle.c equals the Galerkin integral of grad N_i . k grad N_j over the brick with trilinear shape functions
+    (2x2x2 Gauss quadrature is exact for it), and the load vector is the exact integral of a constant source — an
+    independent, first-principles pin of the assembly for Static3D, which has no reference test."""
+    dx, dy, dz = 0.7, 1.9, 0.013                 # um; strongly anisotropic like a thin epitaxial layer
+    k_lat, k_vert = 44.0, 3.5                    # W/(m K)
+    mesh = orc.Mesh(np.array([0., dx]), np.array([0., dy]), np.array([0., dz]), "012")
+    A = orc.Sparse14(mesh)
+    B = np.zeros(8)
+    heat = np.array([2.5e15])
+    A.assemble(np.array([[k_lat, k_vert]]), heat, B)
+    K = np.column_stack([A.mult(np.eye(8)[:, j].copy()) for j in range(8)])
+    # reference node numbering of the element: bit 0 = axis 0 upper, bit 1 = axis 1, bit 2 = axis 2 (therm3d.cpp:190-197)
+    ng = mesh.nodes_grid()
+    idx = [ng[l & 1, (l >> 1) & 1, (l >> 2) & 1] for l in range(8)]
+    g = 1. / np.sqrt(3.)
+    Kq = np.zeros((8, 8))
+    for gx in (-g, g):
+        for gy in (-g, g):
+            for gz in (-g, g):
+                grads = np.zeros((8, 3))
+                for l in range(8):
+                    sx, sy, sz = (1 if l & 1 else -1), (1 if l & 2 else -1), (1 if l & 4 else -1)
+                    grads[l] = [sx * (1 + sy * gy) * (1 + sz * gz) / 8. * 2. / dx,
+                                sy * (1 + sx * gx) * (1 + sz * gz) / 8. * 2. / dy,
+                                sz * (1 + sx * gx) * (1 + sy * gy) / 8. * 2. / dz]
+                kk = np.array([k_lat, k_lat, k_vert]) * 1e-6            # W/(um K): coordinates are in um (:215)
+                Kq += (grads * kk) @ grads.T * (dx * dy * dz / 8.)
+    Kref = K[np.ix_(idx, idx)]
+    assert np.abs(Kref - Kq).max() <= 1e-13 * np.abs(Kq).max()
+    assert np.allclose(B[idx], 0.125e-18 * dx * dy * dz * heat[0], rtol=1e-15)   # int N_i f dV = f V / 8, um^3 -> m^3
+    assert abs(Kref.sum()) <= 1e-12 * np.abs(Kq).max() and np.allclose(Kref, Kref.T)

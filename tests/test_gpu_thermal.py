@@ -227,3 +227,39 @@ def test_degenerate_systems(precond):
     T = s.outTemperature()
     assert np.abs(T - 300.).max() <= 1e-6 and s.stats["outer_loops"] <= 3 and err >= 44.9   # first loop moves 345 K -> 300 K
     s.invalidate()
+
+
+@pytest.mark.parametrize("precond", ["jac", "ljac"])
+def test_nonlinear_loop_converges_to_the_kirchhoff_solution(precond):
+    """the CUDA path against the exact solution of (k(T) T')' = -q with k = k0 (300/T)^a (Kirchhoff transform), second-order
+    convergence in h — the same first-principles check tests/test_oracle_pin.py applies to the oracle"""
+    from helpers import face_nodes
+    k0, a, Tb, q, H = 45., 1.28, 300., 8.0e13, 6.0
+    Tt = 250. + 0.05 * np.arange(6001)
+    lat = (k0 * (300. / Tt) ** a)[None, :]
+    c = k0 * 300. ** a
+
+    def exact(z_um):
+        z = z_um * 1e-6
+        theta = q * (2. * H * 1e-6 * z - z * z) / 2.
+        return (Tb ** (1. - a) + (1. - a) * theta / c) ** (1. / (1. - a))
+
+    errs = []
+    for nz in (9, 17, 33):
+        axes = [np.linspace(0., 1., 3), np.linspace(0., 1., 3), np.linspace(0., H, nz)]
+        p = cf.Problem("kirchhoff", "thermal", axes, "012", None, 250., 0.05, lat, lat.copy(), None, None)
+        p.elem_mat = np.zeros(p.E, dtype=np.uint32)
+        bot = face_nodes(p, 2, 0)
+        p.bc_nodes, p.bc_values = bot.astype(np.uintp), np.full(bot.size, Tb)
+        p.heat = np.full(p.E, q)
+        s = Static3D("kirchhoff")
+        s.problem = p
+        s.inittemp, s.maxerr = Tb, 1e-9
+        s.iterative.preconditioner = precond
+        s.iterative.maxerr = 1e-13
+        s.compute(200)
+        T = s.outTemperature()[np.broadcast_to(p.node_index_grid(), p.n)][1, 1, :]
+        errs.append(np.abs(T - exact(axes[2])).max())
+        s.invalidate()
+    assert errs[0] / errs[1] == pytest.approx(4., rel=0.25) and errs[1] / errs[2] == pytest.approx(4., rel=0.25), errs
+    assert errs[2] < 0.02

@@ -159,3 +159,38 @@ def test_brick_stiffness_is_the_exact_galerkin_integral():
     assert np.abs(Kref - Kq).max() <= 1e-13 * np.abs(Kq).max()
     assert np.allclose(B[idx], 0.125e-18 * dx * dy * dz * heat[0], rtol=1e-15)   # int N_i f dV = f V / 8, um^3 -> m^3
     assert abs(Kref.sum()) <= 1e-12 * np.abs(Kq).max() and np.allclose(Kref, Kref.T)
+
+
+def test_nonlinear_loop_converges_to_the_kirchhoff_solution():
+    """Static3D's loop (k evaluated at the 8-node average temperature of the previous loop, therm3d.cpp:204-213,311-334) against
+    the exact solution of  (k(T) T')' = -q,  T(0) = Tb,  T'(H) = 0  with  k = k0 (300/T)^a  (Kirchhoff transform):
+    theta(T) = int_Tb^T k dT = q (2 H z - z^2) / 2.  The discretisation error must fall like h^2."""
+    from helpers import face_nodes
+    from plask_b200 import configs as cf
+    k0, a, Tb, q, H = 45., 1.28, 300., 8.0e13, 6.0                  # GaAs thermk (materials/GaAs.cpp), W/m3, um
+    Tt = 250. + 0.05 * np.arange(6001)
+    lat = (k0 * (300. / Tt) ** a)[None, :]
+    c = k0 * 300. ** a
+
+    def exact(z_um):
+        z = z_um * 1e-6
+        theta = q * (2. * H * 1e-6 * z - z * z) / 2.
+        return (Tb ** (1. - a) + (1. - a) * theta / c) ** (1. / (1. - a))
+
+    errs = []
+    for nz in (9, 17, 33):
+        axes = [np.linspace(0., 1., 3), np.linspace(0., 1., 3), np.linspace(0., H, nz)]
+        p = cf.Problem("kirchhoff", "thermal", axes, "012", None, 250., 0.05, lat, lat.copy(), None, None)
+        p.elem_mat = np.zeros(p.E, dtype=np.uint32)
+        bot = face_nodes(p, 2, 0)
+        p.bc_nodes, p.bc_values = bot.astype(np.uintp), np.full(bot.size, Tb)
+        p.heat = np.full(p.E, q)
+        m = orc.Mesh(*axes, "012")
+        o = orc.Static3DOracle(m, p.elem_mat, orc.Tables(250., 0.05, lat, lat), p.bc_nodes, p.bc_values, heat=p.heat,
+                               inittemp=Tb, maxerr=1e-9, algorithm="cholesky")
+        o.compute(200)
+        T = o.temperatures[np.broadcast_to(p.node_index_grid(), p.n)][1, 1, :]
+        errs.append(np.abs(T - exact(axes[2])).max())
+        assert T.max() > Tb + q * (H * 1e-6) ** 2 / (2. * k0) + 1.     # k(T) matters: well above the constant-k solution (332 K)
+    assert errs[0] / errs[1] == pytest.approx(4., rel=0.25) and errs[1] / errs[2] == pytest.approx(4., rel=0.25), errs
+    assert errs[2] < 0.02

@@ -57,7 +57,7 @@ for n in (32, 48):
     res = {}
     res['jac'] = pcg(A, b, jac)
     res['line'] = pcg(A, b, line)
-    for c in (2, 4):
+    for c in (2, 4, 8):
         a0 = np.arange(n0) // c; a1 = np.arange(n1) // c
         m0, m1 = a0.max() + 1, a1.max() + 1
         agg = (a0[:, None, None] * m1 + a1[None, :, None]) * n2 + np.arange(n2)[None, None, :]
@@ -65,8 +65,5 @@ for n in (32, 48):
         Ac = (P.T @ A @ P).tocsc()
         Aclu = spla.splu(Ac)
         add = lambda r: Tlu.solve(r) + P @ Aclu.solve(P.T @ r)                  # additive two-level
-        def mult(r):                                                            # symmetric multiplicative: line, coarse, line
-            z = Tlu.solve(r); z += P @ Aclu.solve(P.T @ (r - A @ z)); z += Tlu.solve(r - A @ z); return z
         res[f'line+coarse{c}x{c} additive'] = pcg(A, b, add)
-        res[f'line+coarse{c}x{c} symmetric multiplicative'] = pcg(A, b, mult)
     print(n, N, res, flush=True)

@@ -183,7 +183,11 @@ typedef struct {
     int maxit;        /* max PCG iterations per linear solve (iter_params.maxit)            */
     double lin_tol;   /* stop when ||r||2 <= lin_tol*||b||2 AND ||r||_D^-1 <= lin_tol*||b||_D^-1 (b = free rows of the rhs) */
     int precond;      /* 0 = Jacobi (NSPCG "jac"); 1 = line-Jacobi (NSPCG "ljac"): tridiagonal line blocks along the
-                       * physical vertical axis, two kernels per iteration; in slab mode the vertical axis must not be the major one */
+                       * physical vertical axis, two kernels per iteration; in slab mode the vertical axis must not be the major one;
+                       * 2 = additive multilevel line preconditioner (kernels_ml.cuh): line blocks + the line blocks of the Galerkin
+                       * operators on 4^l x 4^l lateral aggregates up to one column — the counterpart of the strength of the
+                       * reference's default "ic" (iterative_matrix.hpp:73); needs PFEM_LAYOUT_VERTICAL_MINOR (or a mesh order whose
+                       * minor axis is vertical) and at most 512 nodes per vertical line */
     double outer_tol; /* maxerr of the nonlinear loop: K (thermal) or % (electrical)        */
     int loops;        /* max nonlinear loops in this call, 0 = until converged              */
     int batch;        /* PCG iterations per captured CUDA graph launch (0 = default)        */
@@ -265,6 +269,10 @@ int pfem_set_conductivity(pfem_ctx* ctx, const double* cond);
 /* q = A p with A the Dirichlet-eliminated stiffness matrix of the current conds
  * (== SparseBandMatrix::mult after applyBC, iterative_matrix.hpp:420-433,462-485) */
 int pfem_apply(pfem_ctx* ctx, const double* p, double* q, int variant);
+/* z = M^-1 r with the preconditioner opts->precond (0 Jacobi, 1 line-Jacobi, 2 multilevel) built from the current conds and
+ * Dirichlet set; r is masked to the free rows first.  Lets the parity tests compare the preconditioner itself (not only the
+ * converged solution, which no SPD preconditioner can change) with its construction from the assembled matrix. */
+int pfem_apply_precond(pfem_ctx* ctx, const pfem_opts* opts, const double* r, double* z);
 /* load vector after applyBC (B of therm3d.cpp:278 / electr3d.cpp:344) */
 int pfem_get_rhs(pfem_ctx* ctx, double* b);
 /* diagonal of the eliminated matrix (1 on Dirichlet rows) */

@@ -97,6 +97,7 @@ SYMBOLS = {
     "pfem_update_conductivity_shockley": (C.c_int, [_vp]),
     "pfem_set_conductivity": (C.c_int, [_vp, c_dp]),
     "pfem_apply": (C.c_int, [_vp, c_dp, c_dp, C.c_int]),
+    "pfem_apply_precond": (C.c_int, [_vp, C.POINTER(Opts), c_dp, c_dp]),
     "pfem_get_rhs": (C.c_int, [_vp, c_dp]),
     "pfem_get_diag": (C.c_int, [_vp, c_dp]),
     "pfem_solve_linear": (C.c_int, [_vp, C.POINTER(Opts), C.POINTER(Stats)]),

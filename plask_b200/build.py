@@ -6,7 +6,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "plaskfem_cuda.cu")
 OUT = os.path.join(_HERE, "libplaskfem_cuda.so")
 DEPS = [SRC] + [os.path.join(_HERE, "csrc", f) for f in ("pfem_internal.cuh", "kernels_simple.cuh", "kernels_tiled.cuh", "kernels_tma.cuh", "kernels_fused.cuh",
-                                                          "kernels_surface.cuh", "kernels_line.cuh")]
+                                                          "kernels_surface.cuh", "kernels_line.cuh", "kernels_ml.cuh")]
 DEPS.append(os.path.join(os.path.dirname(_HERE), "include", "plaskfem_cuda.h"))
 
 

@@ -35,6 +35,7 @@
 #include <type_traits>
 
 #include "kernels_tma.cuh"
+#include "kernels_ml.cuh"
 
 namespace pfem {
 
@@ -65,7 +66,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
        const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_d,
        const __grid_constant__ CUtensorMap tm_cl, const __grid_constant__ CUtensorMap tm_cv, const Grid g, const int lk,
        double* __restrict__ r_out, double* __restrict__ q_out, double* __restrict__ p_out, double* __restrict__ x,
-       Scalars* sc, double* partials, const PeerOut po) {
+       Scalars* sc, double* partials, const PeerOut po, const CoarseAdd ca) {
     typedef FusedTile<TJ> T;
     constexpr int TI = T::TI, HX = T::HX, PW = T::PW, PH = T::PH, BOX = T::BOX, BOXP = T::BOXP, PWP = T::PWP;
     constexpr int PLANE = T::PLANE, CW = T::CW, CHALF = T::CHALF, LAYER = T::LAYER, NRED = T::NRED;
@@ -131,6 +132,19 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         else { const int h = tid - 2 * PWP; jj = 1 + (h >> 1); ii = (h & 1) ? PWP - 1 : 0; }
         ring_raw = jj * PW + ii + (HX - 1);
         ring_pl = jj * PWP + ii;
+    }
+    // multilevel preconditioner (MODE 2 only, vertical axis = I): z = z_0 + z_1(parent aggregate).  Row offsets of the own nodes
+    // and of the ring node inside a level-1 plane; the plane offset is added per step.
+    const bool mlz = LINE && ca.z1 != nullptr;
+    idx_t zc_own[RJ], zc_ring = 0;
+    if (mlz) {
+        const int ic = min(i, g.nI - 1);
+#pragma unroll
+        for (int rr = 0; rr < RJ; ++rr) zc_own[rr] = (idx_t)(min(j0 + jl0 + rr, g.nJ - 1) >> PFEM_ML_SHIFT) * g.sJ + ic;
+        if (ring_raw >= 0) {
+            const int jj = ring_pl / PWP, ii = ring_pl % PWP;
+            zc_ring = (idx_t)(min(max(j0 - 1 + jj, 0), g.nJ - 1) >> PFEM_ML_SHIFT) * g.sJ + min(max(i0 - 1 + ii, 0), g.nI - 1);
+        }
     }
     // halo row / column of the element layer handled by this thread (entry e = NT-1-tid)
     int er_raw = -1, er_c = 0;
@@ -228,6 +242,13 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
                 if (vj[rr]) xn[rr] = x[nown[rr] + sK];
         }
         const double hk = sHK[t], rk = sHK[lk + 2 + t];   // element layer L = P - 1 of this step (t >= 1)
+        double zc[RJ], zcr = 0.;
+        if (mlz) {   // coarse correction of this plane, in flight while the stage lands
+            const idx_t pc = (idx_t)(min(max(k0 - 1 + t, 0), g.nK - 1) >> PFEM_ML_SHIFT) * ca.nJ1 * g.sJ;
+#pragma unroll
+            for (int rr = 0; rr < RJ; ++rr) zc[rr] = __ldg(ca.z1 + pc + zc_own[rr]);
+            if (ring_raw >= 0) zcr = __ldg(ca.z1 + pc + zc_ring);
+        }
         mbar_wait(&bars[st], (uint32_t)((t / NS) & 1));
 
         // ---------------- phase 1: p' plane and coefficient layer -------------------------
@@ -237,7 +258,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
             double pn;
             if (FUSED) {
                 const double r0 = raw[ro], q0 = LINE ? 0. : raw[BOXP + ro], p0 = raw[B_P * BOXP + ro], dd = raw[B_D * BOXP + ro];
-                const double rn = LINE ? r0 : fma(-alpha, q0, r0);
+                const double rn = LINE ? (mlz ? r0 + zc[rr] : r0) : fma(-alpha, q0, r0);
                 const double z = dd * rn;
                 pn = fma(beta, p0, z);
                 zdb[rr] = z; zdb[RJ + rr] = dd;
@@ -259,6 +280,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
                             red[4] = fma(rn, rn, red[4]);
                             red[5] = fma(z, z, red[5]);
                         }
+                        if (LINE) red[5] = fma(z, z, red[5]);
                         red[6] = fma(xv, xv, red[6]);
                     }
                 }
@@ -282,7 +304,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
             if (FUSED) {
                 const double r0 = raw[ring_raw], q0 = LINE ? 0. : raw[BOXP + ring_raw], p0 = raw[B_P * BOXP + ring_raw],
                              dd = raw[B_D * BOXP + ring_raw];
-                pn = fma(beta, p0, dd * (LINE ? r0 : fma(-alpha, q0, r0)));
+                pn = fma(beta, p0, dd * (LINE ? (mlz ? r0 + zcr : r0) : fma(-alpha, q0, r0)));
             } else {
                 pn = raw[B_P * BOXP + ring_raw];
             }
@@ -409,6 +431,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
             // line-Jacobi PCG: rho, beta and the stopping test belong to the line kernel; here only alpha = rho / p'.q'
             const double pq = red[0];
             sc->pq = pq; sc->xx = red[6];
+            if (sc->line == 2) sc->zz = red[5];   // multilevel: the complete z exists only here (stopping test of the next iteration)
             if (sc->done == 2) sc->done = 1;
             else if (sc->surf) {}   // convection terms: k_surf_iter adds p'.S p' and computes alpha
             else if (!sc->bench && !(pq > 0.)) { sc->done = 1; sc->status = (pq == pq) ? -1 : -2; }
@@ -502,27 +525,29 @@ static inline FusedPlan make_fused_plan(const Grid& g, int sm_count, double* con
 
 template <int TJ, int RJ, int NS, int MINB, int VDIM, int MODE>
 static inline cudaError_t launch_fused_inst(const FusedPlan& f, const Grid& g, int par, double* r_out, double* q_out, double* p_out,
-                                            double* x, Scalars* sc, double* partials, const PeerOut& po, cudaStream_t st) {
+                                            double* x, Scalars* sc, double* partials, const PeerOut& po, cudaStream_t st, const CoarseAdd& ca) {
     const size_t smem = FusedTile<TJ>::smem_bytes(NS, MODE, f.lk);
-    static size_t attr_done = 0;
-    if (attr_done < smem) {
+    static size_t attr_done[64] = {};   // the opt-in is per function AND per device (contexts may live on different GPUs)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr_done[dev & 63] < smem) {
         cudaError_t e = cudaFuncSetAttribute(k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done = smem;
+        attr_done[dev & 63] = smem;
     }
     dim3 grid(f.tilesI, f.tilesJ, f.chunksK), block(32, TJ / RJ, 1);
     k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE><<<grid, block, smem, st>>>(f.m_r[par], f.m_q[par], f.m_p[par], f.m_d, f.m_cl, f.m_cv, g, f.lk,
-                                                                r_out, q_out, p_out, x, sc, partials, po);
+                                                                r_out, q_out, p_out, x, sc, partials, po, ca);
     return cudaGetLastError();
 }
 
 template <int TJ, int RJ, int NS, int MINB, int MODE>
 static inline cudaError_t launch_fused_vdim(const FusedPlan& f, const Grid& g, int par, double* r_out, double* q_out, double* p_out,
-                                            double* x, Scalars* sc, double* partials, const PeerOut& po, cudaStream_t st) {
+                                            double* x, Scalars* sc, double* partials, const PeerOut& po, cudaStream_t st, const CoarseAdd& ca) {
     switch (g.vdim) {
-        case 0: return launch_fused_inst<TJ, RJ, NS, MINB, 0, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st);
-        case 1: return launch_fused_inst<TJ, RJ, NS, MINB, 1, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st);
-        default: return launch_fused_inst<TJ, RJ, NS, MINB, 2, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st);
+        case 0: return launch_fused_inst<TJ, RJ, NS, MINB, 0, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st, ca);
+        case 1: return launch_fused_inst<TJ, RJ, NS, MINB, 1, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st, ca);
+        default: return launch_fused_inst<TJ, RJ, NS, MINB, 2, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st, ca);
     }
 }
 
@@ -531,9 +556,9 @@ static inline cudaError_t launch_fused_vdim(const FusedPlan& f, const Grid& g, i
 template <int MODE>
 static inline cudaError_t launch_fused_dispatch(const FusedPlan& f, const Grid& g, int par, double* r_out, double* q_out,
                                                 double* p_out, double* x, Scalars* sc, double* partials, const PeerOut& po,
-                                                cudaStream_t st) {
+                                                cudaStream_t st, const CoarseAdd ca = CoarseAdd{nullptr, 0}) {
 #define PFEM_FUSED_CASE(TJ, RJ, NS, MINB) \
-    if (f.tj == TJ && f.rj == RJ && f.ns == NS && f.minb == MINB) return launch_fused_vdim<TJ, RJ, NS, MINB, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st);
+    if (f.tj == TJ && f.rj == RJ && f.ns == NS && f.minb == MINB) return launch_fused_vdim<TJ, RJ, NS, MINB, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st, ca);
     PFEM_FUSED_CASE(8, 2, 2, 3)    // production tile (tools/tune_fused.py); the others are kept for PFEM_FUSED_TILE tuning runs
     PFEM_FUSED_CASE(8, 2, 2, 2)
     PFEM_FUSED_CASE(8, 1, 2, 2)

@@ -223,10 +223,12 @@ static inline cudaError_t launch_tiled_inst(const TiledPlan& p, const Grid& g, c
                                             const double* r, const double* dinv, const double* pin, double* pout,
                                             double* q, Scalars* sc, double* partials, cudaStream_t st) {
     const size_t smem = TileSmem<TI, TJ>::bytes;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {};   // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 63]) {
         cudaFuncSetAttribute(k_apply_tiled<TI, TJ, RJ, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
+        attr_done[dev & 63] = true;
     }
     dim3 grid(p.tilesI, p.tilesJ, p.chunksK), block(TI, TJ / RJ, 1);
     k_apply_tiled<TI, TJ, RJ, FUSED><<<grid, block, smem, st>>>(g, p.lk, cl, cv, r, dinv, pin, pout, q, sc, partials);

@@ -321,11 +321,13 @@ template <int TI, int TJ, int RJ, int NS, bool FUSED>
 static inline cudaError_t launch_tma_inst(const TmaPlan& p, const Grid& g, const CUtensorMap& mp, const double* dinv,
                                           double* pout, double* q, Scalars* sc, double* partials, cudaStream_t st) {
     const size_t smem = TmaTile<TI, TJ>::smem_bytes(NS, FUSED);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {};   // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(k_apply_tma<TI, TJ, RJ, NS, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_done[dev & 63] = true;
     }
     dim3 grid(p.tilesI, p.tilesJ, p.chunksK), block(TI, TJ / RJ, 1);
     k_apply_tma<TI, TJ, RJ, NS, FUSED><<<grid, block, smem, st>>>(mp, p.m_r, p.m_d, p.m_cl, p.m_cv, g, p.lk, dinv, pout, q, sc, partials);

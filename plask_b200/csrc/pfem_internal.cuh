@@ -92,8 +92,9 @@ struct Scalars {
     unsigned int ticket[8];
     Comm* comm;       // null unless the context is one slab of a multi-GPU solve
     double qz, qdq;   // q.z and q.D^-1 q of the stiffness part, handed from k_fpcg to k_surf_iter when surf != 0
-    int line;         // 1: line-Jacobi PCG (kernels_line.cuh): k_fpcg only forms p', q', x' and alpha
+    int line;         // 1: line-Jacobi PCG (kernels_line.cuh): k_fpcg only forms p', q', x' and alpha; 2: multilevel (kernels_ml.cuh)
     int pad2_;
+    double ml_rho, ml_rr;   // multilevel preconditioner: r'.z summed over the levels so far, |r'|^2 of the fine level
 };
 
 // Boundary-face terms (conditions of the 2nd / 3rd kind and radiation, therm3d.cpp:140-168,242-268) flattened by the

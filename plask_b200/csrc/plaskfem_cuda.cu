@@ -19,6 +19,7 @@
 #include "kernels_fused.cuh"
 #include "kernels_surface.cuh"
 #include "kernels_line.cuh"
+#include "kernels_ml.cuh"
 
 using namespace pfem;
 
@@ -84,6 +85,10 @@ struct pfem_ctx {
     double *lz = nullptr, *lmask = nullptr, *ll = nullptr, *ld = nullptr, *zero1 = nullptr;
     FusedPlan line_plan;
     int precond = 0;            // preconditioner of the PCG state prepared last
+    // multilevel line preconditioner (pfem_opts::precond = 2, kernels_ml.cuh): level arrays, set-up partial sums
+    MLDev ml = {};
+    double* mlS = nullptr;
+    idx_t ml_slen = 0;
     // internal layout (pfem_set_layout): 0 = the ABI's iteration order, 1 = vertical axis as the minor (I) axis
     int layout = 0;
     bool permuted = false;      // the lattice order differs from the ABI order: transfers go through permuting kernels
@@ -176,6 +181,7 @@ static void free_all(pfem_ctx* ctx) {
     ctx->partials = nullptr; ctx->partial_idx = nullptr; ctx->n_partials = 0;
     memset(&ctx->surf, 0, sizeof ctx->surf); ctx->fS = nullptr; ctx->surf_iter = 0; ctx->surf_iter_known = false;
     ctx->lz = ctx->lmask = ctx->ll = ctx->ld = ctx->zero1 = nullptr; ctx->line_plan.valid = false; ctx->precond = 0;
+    memset(&ctx->ml, 0, sizeof ctx->ml); ctx->mlS = nullptr; ctx->ml_slen = 0;
     if (ctx->stage) { cudaFree(ctx->stage); ctx->stage = nullptr; ctx->stage_bytes = 0; }
     ctx->have_mesh = ctx->have_materials = ctx->have_junctions = ctx->conds_valid = false;
     ctx->noheat_set = false;
@@ -1124,10 +1130,96 @@ static int launch_line_solve(pfem_ctx* ctx, const double* r_in, const double* q_
         if (blocks < 1) blocks = 1;
         k_line_strided<<<blocks, 128, 0, ctx->stream>>>(g, r_in, q_in, ctx->ll, ctx->ld, r_out, ctx->lz, ctx->d_sc, ctx->partials, mode, po);
     }
-    KCHECK(); LAUNCHED(1);
+    KCHECK();   // counted by the caller (launch_iteration returns the kernels of an iteration)
     return PFEM_OK;
 }
 __global__ void k_force_running(Scalars* sc) { sc->done = 0; sc->status = 0; }
+
+// ---- multilevel line preconditioner (kernels_ml.cuh) ----------------------------------------------------------
+static int ensure_ml(pfem_ctx* ctx) {
+    if (ctx->ml.nlev) return PFEM_OK;
+    const Grid& g = ctx->g;
+    if (g.vdim != 0) FAIL(PFEM_ERR_STATE, "the multilevel preconditioner needs the vertical axis as the fastest one: call pfem_set_layout(PFEM_LAYOUT_VERTICAL_MINOR) before pfem_set_mesh");
+    if (line_seg(g) == 0) FAIL(PFEM_ERR_BAD_INPUT, "the multilevel preconditioner holds at most 512 nodes per vertical line (%d given)", g.nI);
+    MLDev ml;
+    memset(&ml, 0, sizeof ml);
+    ml.dom[0] = LineDom{g.nI, g.nJ, g.nK, g.sJ, g.sK};
+    int L = 0;
+    for (int nJ = g.nJ, nK = g.nK; nJ > 1 || nK > 1;) {
+        if (L == PFEM_ML_MAXL) FAIL(PFEM_ERR_BAD_INPUT, "mesh too wide for %d aggregation levels", PFEM_ML_MAXL);
+        nJ = (nJ + PFEM_ML_C - 1) / PFEM_ML_C; nK = (nK + PFEM_ML_C - 1) / PFEM_ML_C;
+        ++L;
+        ml.dom[L] = LineDom{g.nI, nJ, nK, g.sJ, g.sJ * nJ};
+    }
+    const idx_t slen = (idx_t)ml.dom[1].nJ * ml.dom[1].nK * g.sJ;
+    TRY(dev_alloc(ctx, &ctx->mlS, (size_t)(2 * L * slen), 0));
+    for (int l = 1; l <= L; ++l) {
+        const size_t len = (size_t)ml.dom[l].nJ * ml.dom[l].nK * g.sJ;
+        TRY(dev_alloc(ctx, &ml.r[l], len, 0));
+        TRY(dev_alloc(ctx, &ml.z[l], len, 0));
+        if (l == 1) { ml.ld[1] = ctx->mlS; ml.ll[1] = ctx->mlS + slen; }   // level 1: the partial sums are the blocks themselves
+        else { TRY(dev_alloc(ctx, &ml.ld[l], len, 0)); TRY(dev_alloc(ctx, &ml.ll[l], len, 0)); }
+    }
+    ml.nlev = L;
+    ctx->ml = ml;
+    ctx->ml_slen = slen;
+    return PFEM_OK;
+}
+
+// tridiagonal blocks of the Galerkin operators of all levels and their L D L^T factors (after launch_diag: dinv is current)
+static int ml_setup(pfem_ctx* ctx) {
+    const Grid& g = ctx->g;
+    const MLDev& ml = ctx->ml;
+    const int L = ml.nlev;
+    k_ml_rowsums<<<dim3((unsigned)((g.sJ + 31) / 32), ml.dom[1].nJ, ml.dom[1].nK), dim3(32, PFEM_ML_C, PFEM_ML_C), 0, ctx->stream>>>(
+        g, ctx->cl, ctx->cv, ctx->dinv, L, ml.dom[1].nJ, ctx->mlS, ctx->ml_slen);
+    KCHECK(); LAUNCHED(1);
+    for (int l = 2, f = PFEM_ML_C; l <= L; ++l, f *= PFEM_ML_C) {
+        k_ml_gather<<<dim3((unsigned)((g.sJ + 127) / 128), ml.dom[l].nJ, ml.dom[l].nK), 128, 0, ctx->stream>>>(
+            ml.dom[1], ml.dom[l], f, ctx->mlS + (size_t)(2 * (l - 1)) * ctx->ml_slen, ctx->mlS + (size_t)(2 * (l - 1) + 1) * ctx->ml_slen, ml.ld[l], ml.ll[l]);
+        KCHECK(); LAUNCHED(1);
+    }
+    for (int l = 1; l <= L; ++l) {
+        const idx_t lines = (idx_t)ml.dom[l].nJ * ml.dom[l].nK;
+        k_ml_factor<<<(unsigned)((lines + 63) / 64), 64, 0, ctx->stream>>>(ml.dom[l], ml.ll[l], ml.ld[l], ctx->d_sc);
+        KCHECK(); LAUNCHED(1);
+    }
+    return PFEM_OK;
+}
+
+template <int SEG>
+static void launch_ml_chain_seg(pfem_ctx* ctx, const double* r_in, const double* q_in, double* r_out, int mode) {
+    const MLDev& ml = ctx->ml;
+    const int L = ml.nlev;
+    const int cap = ctx->sm_count * 2;   // one resident wave of 256-thread blocks, like k_line_I
+    auto blocks = [&](const LineDom& d) {
+        const int na = ((d.nJ + PFEM_ML_C - 1) / PFEM_ML_C) * ((d.nK + PFEM_ML_C - 1) / PFEM_ML_C);
+        if (na <= cap) return na;
+        const int per = (na + cap - 1) / cap;   // every block the same number of aggregates (+-1)
+        return (na + per - 1) / per;
+    };
+    k_line_ml<SEG, true><<<blocks(ml.dom[0]), 256, 0, ctx->stream>>>(ml.dom[0], r_in, q_in, ctx->ll, ctx->ld, r_out, ctx->lz, ml.r[1], ml.dom[1].nJ,
+                                                                        ctx->d_sc, ctx->partials, mode, 0);
+    for (int l = 1; l <= L; ++l)
+        k_line_ml<SEG, false><<<blocks(ml.dom[l]), 256, 0, ctx->stream>>>(ml.dom[l], ml.r[l], nullptr, ml.ll[l], ml.ld[l], nullptr, ml.z[l],
+                                                                             l < L ? ml.r[l + 1] : nullptr, l < L ? ml.dom[l + 1].nJ : 0, ctx->d_sc,
+                                                                             ctx->partials, mode, l == L);
+    if (L >= 2 && mode != 1)
+        k_ml_down<<<dim3((unsigned)((ml.dom[1].sJ + 127) / 128), ml.dom[1].nJ, ml.dom[1].nK), 128, 0, ctx->stream>>>(ml, ctx->d_sc, mode);
+}
+
+// z_0 .. z_L and the CG scalars of the multilevel preconditioner; mode 1: only b.M^-1 b -> sc->bz
+static int launch_ml_chain(pfem_ctx* ctx, const double* r_in, const double* q_in, double* r_out, int mode) {
+    switch (line_seg(ctx->g)) {
+        case 2: launch_ml_chain_seg<2>(ctx, r_in, q_in, r_out, mode); break;
+        case 4: launch_ml_chain_seg<4>(ctx, r_in, q_in, r_out, mode); break;
+        case 8: launch_ml_chain_seg<8>(ctx, r_in, q_in, r_out, mode); break;
+        case 16: launch_ml_chain_seg<16>(ctx, r_in, q_in, r_out, mode); break;
+        default: FAIL(PFEM_ERR_STATE, "no warp-per-row line kernel for %d nodes per line", ctx->g.nI);
+    }
+    KCHECK();
+    return PFEM_OK;
+}
 
 static int launch_diag(pfem_ctx* ctx) {
     const Grid& g = ctx->g;
@@ -1150,6 +1242,8 @@ static int launch_apply_simple(pfem_ctx* ctx, const double* in, double* out, con
     return PFEM_OK;
 }
 
+static int kernels_per_iteration(const pfem_ctx* ctx, int variant);
+
 // one PCG iteration's kernels on ctx->stream; returns the number of kernels launched.
 // The tiled operator kernel reads p_old from one buffer and writes p_new to the other
 // (halo nodes of p_old are read by neighbouring CTAs), so `parity` = iteration & 1 picks them.
@@ -1160,15 +1254,18 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
     double* pout = parity ? ctx->p : ctx->p2;
     const double* pnew = (variant == 1) ? ctx->p : pout;
     if (ev) cudaEventRecord(ev[0], ctx->stream);
-    if (variant == 3 && ctx->precond == 1) {
-        // line-Jacobi PCG: line solve (r in place, z) then the operator step of k_fpcg with z for r and zeros for q
+    if (variant == 3 && ctx->precond >= 1) {
+        // line-Jacobi PCG: line solve (r in place, z) then the operator step of k_fpcg with z for r and zeros for q;
+        // multilevel: the level chain instead of the single line solve, k_fpcg adds the coarse correction while it forms p'
         double* const qq[2] = {ctx->q, ctx->q2};
         double* const pp[2] = {ctx->p, ctx->p2};
-        launch_line_solve(ctx, ctx->r, qq[parity], ctx->r, 0);
+        const bool mlp = ctx->precond == 2;
+        if (mlp) launch_ml_chain(ctx, ctx->r, qq[parity], ctx->r, 0);
+        else launch_line_solve(ctx, ctx->r, qq[parity], ctx->r, 0);
         if (ev) cudaEventRecord(ev[1], ctx->stream);
         const PeerOut po = peer_out(ctx, 1 - parity);   // slab mode: p' of the boundary planes goes to the neighbours
         launch_fused_dispatch<2>(ctx->line_plan, g, parity, nullptr, qq[1 - parity], pp[1 - parity], ctx->x, ctx->d_sc, ctx->partials,
-                                    po, ctx->stream);
+                                    po, ctx->stream, mlp ? CoarseAdd{ctx->ml.z[1], ctx->ml.dom[1].nJ} : CoarseAdd{nullptr, 0});
         if (ctx->surf_iter) {  // q' += S p' on the boundary rows, alpha from the completed p'.q' (q is only read on owned rows: no push)
             PeerOut none;
             memset(&none, 0, sizeof none);
@@ -1176,7 +1273,7 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
                                                                     ctx->partials, none);
         }
         if (ev) cudaEventRecord(ev[2], ctx->stream);
-        return 2 + ctx->surf_iter;
+        return kernels_per_iteration(ctx, 3);
     }
     if (variant == 3) {
         // the whole iteration in one kernel: inputs r,q,p[parity] -> outputs r,q,p[1-parity], x in place
@@ -1216,7 +1313,10 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
     return launched;
 }
 
-static int kernels_per_iteration(const pfem_ctx* ctx, int variant) { return variant == 1 ? 3 : (variant == 3 ? (ctx->precond == 1 ? 2 + ctx->surf_iter : 1 + ctx->surf_iter) : 2); }  // variants 0 (TMA) and 2 (LDG tiled) fuse the p-update
+static int kernels_per_iteration(const pfem_ctx* ctx, int variant) {
+    if (variant == 3 && ctx->precond == 2) return 2 + ctx->ml.nlev + (ctx->ml.nlev >= 2 ? 1 : 0) + ctx->surf_iter;
+    return variant == 1 ? 3 : (variant == 3 ? (ctx->precond == 1 ? 2 + ctx->surf_iter : 1 + ctx->surf_iter) : 2);
+}  // variants 0 (TMA) and 2 (LDG tiled) fuse the p-update
 
 static int build_graph(pfem_ctx* ctx, int batch, int variant, int precond) {
     if (ctx->graph && ctx->graph_batch == batch && ctx->graph_variant == variant && ctx->graph_precond == precond &&
@@ -1254,11 +1354,10 @@ static int pcg_prepare(pfem_ctx* ctx, const pfem_opts* o, int bench) {
         ctx->surf_iter_known = true;
     }
     if (ctx->surf_iter && o->variant != 3) FAIL(PFEM_ERR_BAD_INPUT, "convection boundary terms run with the fused PCG kernel only (variant 3)");
-    if (o->precond == 1) {
-        TRY(ensure_line(ctx));
-    }
+    if (o->precond >= 1) TRY(ensure_line(ctx));
+    if (o->precond == 2) TRY(ensure_ml(ctx));
     ctx->precond = o->precond;
-    k_set_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, tol2, o->maxit, bench, ctx->surf_iter, o->precond == 1);
+    k_set_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, tol2, o->maxit, bench, ctx->surf_iter, o->precond);
     LAUNCHED(1);
     TRY(launch_diag(ctx));
     TRY(halo_sync(ctx, SA_DINV));            // slab mode: the diagonal of a halo plane needs the neighbour's elements
@@ -1270,11 +1369,12 @@ static int pcg_prepare(pfem_ctx* ctx, const pfem_opts* o, int bench) {
     const double* feff = nullptr;
     TRY(surf_rhs(ctx, ctx->q, &feff));
     TRY(launch_apply_simple<2>(ctx, ctx->q, ctx->p, feff));
-    if (o->precond == 1) {   // factors of the line blocks, then ||b_free|| in the metric of this preconditioner
+    if (o->precond >= 1) {   // factors of the line blocks, then ||b_free|| in the metric of this preconditioner
         k_line_factor<<<(unsigned)((g.N / (g.vdim == 0 ? g.nI : g.vdim == 1 ? g.nJ : g.nK) + 127) / 128), 128, 0, ctx->stream>>>(
             g, ctx->cl, ctx->cv, ctx->dinv, ctx->ll, ctx->ld, ctx->lmask, ctx->d_sc);
         KCHECK(); LAUNCHED(1);
-        TRY(launch_line_solve(ctx, ctx->p, nullptr, nullptr, 1));
+        if (o->precond == 2) { TRY(ml_setup(ctx)); TRY(launch_ml_chain(ctx, ctx->p, nullptr, nullptr, 1)); LAUNCHED(1 + ctx->ml.nlev); }
+        else { TRY(launch_line_solve(ctx, ctx->p, nullptr, nullptr, 1)); LAUNCHED(1); }
     }
     // r0 = M (f - A x)
     TRY(surf_rhs(ctx, ctx->x, &feff));
@@ -1321,9 +1421,10 @@ static int check_opts(pfem_ctx* ctx, const pfem_opts* o) {
     if (!o) FAIL(PFEM_ERR_BAD_INPUT, "null options");
     if (o->maxit <= 0) FAIL(PFEM_ERR_BAD_INPUT, "maxit must be positive");
     if (!(o->lin_tol > 0.)) FAIL(PFEM_ERR_BAD_INPUT, "lin_tol must be positive");
-    if (o->precond != 0 && o->precond != 1) FAIL(PFEM_ERR_BAD_INPUT, "preconditioner %d is not implemented (0 = Jacobi, 1 = line-Jacobi)", o->precond);
-    if (o->precond == 1 && o->variant != 3) FAIL(PFEM_ERR_BAD_INPUT, "the line preconditioner runs with kernel variant 3 only");
-    if (o->precond == 1 && ctx->nranks > 1 && ctx->g.vdim == 2)
+    if (o->precond < 0 || o->precond > 2) FAIL(PFEM_ERR_BAD_INPUT, "preconditioner %d is not implemented (0 = Jacobi, 1 = line-Jacobi, 2 = multilevel line)", o->precond);
+    if (o->precond == 2 && ctx->nranks > 1) FAIL(PFEM_ERR_BAD_INPUT, "the multilevel preconditioner is not available in slab mode");
+    if (o->precond >= 1 && o->variant != 3) FAIL(PFEM_ERR_BAD_INPUT, "the line preconditioner runs with kernel variant 3 only");
+    if (o->precond >= 1 && ctx->nranks > 1 && ctx->g.vdim == 2)
         FAIL(PFEM_ERR_BAD_INPUT, "slab mode: the line preconditioner needs the vertical axis inside the slabs (a lateral major axis)");
     if (o->variant < 0 || o->variant > 3) FAIL(PFEM_ERR_BAD_INPUT, "unknown kernel variant %d", o->variant);
     if (o->variant == 3 && !ctx->fused.valid) FAIL(PFEM_ERR_STATE, "fused PCG kernel unavailable: %s", ctx->fused.why);
@@ -1726,6 +1827,44 @@ extern "C" int pfem_apply(pfem_ctx* ctx, const double* p, double* q, int variant
     k_select_fixed<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->fixed, ctx->r, ctx->q, ctx->q);
     KCHECK(); LAUNCHED(1);
     CU(download_nodes(ctx, q, ctx->q));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+
+// z = M^-1 r for the preconditioner opts->precond built from the current conds / Dirichlet set (free rows; 0 on fixed rows)
+extern "C" int pfem_apply_precond(pfem_ctx* ctx, const pfem_opts* o, const double* r, double* z) {
+    NEED_MESH();
+    TRY(check_opts(ctx, o));
+    if (!r || !z) FAIL(PFEM_ERR_BAD_INPUT, "null vector");
+    if (!ctx->conds_valid) FAIL(PFEM_ERR_STATE, "conductivities have not been computed");
+    if (ctx->nranks > 1) FAIL(PFEM_ERR_BAD_INPUT, "not available in slab mode");
+    const Grid& g = ctx->g;
+    TRY(launch_diag(ctx));
+    CU(upload_nodes(ctx, ctx->q, r));
+    CU(cudaMemsetAsync(ctx->r, 0, (size_t)g.NP * sizeof(double), ctx->stream));
+    k_select_fixed<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->fixed, ctx->r, ctx->q, ctx->p);   // p = free rows of r
+    LAUNCHED(1);
+    if (o->precond == 0) {
+        k_pupdate_plain<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->p, ctx->dinv, ctx->q);
+        KCHECK(); LAUNCHED(1);
+    } else {
+        TRY(ensure_line(ctx));
+        k_line_factor<<<(unsigned)((g.N / (g.vdim == 0 ? g.nI : g.vdim == 1 ? g.nJ : g.nK) + 127) / 128), 128, 0, ctx->stream>>>(
+            g, ctx->cl, ctx->cv, ctx->dinv, ctx->ll, ctx->ld, ctx->lmask, ctx->d_sc);
+        KCHECK(); LAUNCHED(1);
+        if (o->precond == 2) {
+            TRY(ensure_ml(ctx));
+            TRY(ml_setup(ctx));
+            TRY(launch_ml_chain(ctx, ctx->p, nullptr, nullptr, 2));
+            k_ml_prolong_add<<<dim3((unsigned)((g.nI + 127) / 128), g.nJ, g.nK), 128, 0, ctx->stream>>>(g, ctx->lz, ctx->ml.z[1], ctx->ml.dom[1].nJ, ctx->q);
+            KCHECK(); LAUNCHED(3 + ctx->ml.nlev);
+        } else {
+            TRY(launch_line_solve(ctx, ctx->p, nullptr, nullptr, 1));
+            CU(cudaMemcpyAsync(ctx->q, ctx->lz, (size_t)g.NP * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            LAUNCHED(1);
+        }
+    }
+    CU(download_nodes(ctx, z, ctx->q));
     CU(cudaStreamSynchronize(ctx->stream));
     return PFEM_OK;
 }

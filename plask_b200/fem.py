@@ -250,6 +250,14 @@ class DeviceFem:
         self._ck(self.lib.pfem_apply(self.ctx, _dp(p), _dp(q), int(variant)))
         return q
 
+    def apply_precond(self, r, **kw):
+        """z = M^-1 r of the preconditioner `precond` built from the current conductivities (parity tests)"""
+        r = _f64(r)
+        z = np.empty(self.N)
+        o = self.opts(**kw)
+        self._ck(self.lib.pfem_apply_precond(self.ctx, C.byref(o), _dp(r), _dp(z)))
+        return z
+
     def get_rhs(self):
         b = np.empty(self.N)
         self._ck(self.lib.pfem_get_rhs(self.ctx, _dp(b)))

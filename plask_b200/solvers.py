@@ -117,7 +117,7 @@ class _FemSolver:
         lay = self.layout
         if lay == "auto":
             # the warp-per-row line kernel holds up to 512 nodes per line; longer vertical axes keep the mesh order (strided kernel)
-            lay = "vertical-minor" if (self.iterative.preconditioner == "ljac" and self._problem.n[2] <= 512) else "abi"
+            lay = "vertical-minor" if (self.iterative.preconditioner in ("ljac", "mlj") and self._problem.n[2] <= 512) else "abi"
             if self.slab is not None and self.slab["nranks"] > 1 and self._problem.strides[2] == max(self._problem.strides):
                 lay = "abi"     # a vertical major axis cannot be cut into slabs in the vertical-minor layout
         if lay not in ("abi", "vertical-minor"):
@@ -137,10 +137,11 @@ class _FemSolver:
         if self.algorithm != "cuda":
             raise L.BadInput(f"{self.id}: algorithm '{self.algorithm}' is not provided by plask_b200 "
                              "(cholesky/gauss/iterative live in the reference); use 'cuda'")
-        # NSPCG names (iterative_matrix.hpp:27-46): 'jac' point Jacobi, 'ljac' line Jacobi (here: lines along the vertical axis)
-        pre = {"jac": 0, "ljac": 1}.get(self.iterative.preconditioner)
+        # NSPCG names (iterative_matrix.hpp:27-46): 'jac' point Jacobi, 'ljac' line Jacobi (here: lines along the vertical axis);
+        # 'mlj' (new): additive multilevel line preconditioner, the GPU counterpart of the reference's default 'ic' strength
+        pre = {"jac": 0, "ljac": 1, "mlj": 2}.get(self.iterative.preconditioner)
         if pre is None or self.iterative.accelerator != "cg":
-            raise L.BadInput(f"{self.id}: the CUDA algorithm implements accelerator 'cg' with preconditioner 'jac' or 'ljac'")
+            raise L.BadInput(f"{self.id}: the CUDA algorithm implements accelerator 'cg' with preconditioner 'jac', 'ljac' or 'mlj'")
         return dict(maxit=int(self.iterative.maxit), lin_tol=float(self.iterative.maxerr), precond=pre,
                     outer_tol=float(outer_tol), loops=int(loops), variant=int(self.variant))
 

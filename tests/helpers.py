@@ -116,3 +116,70 @@ def slab_problem_1d(n=(4, 4, 17), H=10., k=40., T0=300., order="012", dirichlet=
     p.inittemp = float(T0)
     p.maxerr = 1e-9
     return p
+
+
+def assembled_csr(A14, mesh):
+    """the oracle's SparseBandMatrix (14 diagonals of the upper triangle, iterative_matrix.hpp:372-390) as a scipy CSR matrix"""
+    import scipy.sparse as sp
+    N = mesh.N
+    data = A14.data.reshape(14, N)
+    ic = mesh.icords
+    rows, cols, vals = [np.arange(N)], [np.arange(N)], [data[0].copy()]
+    for i in range(14):
+        d = int(ic[i])
+        if d == 0:
+            continue
+        c = np.arange(N - d)
+        v = data[i][:N - d]
+        nz = v != 0
+        rows += [c[nz] + d, c[nz]]
+        cols += [c[nz], c[nz] + d]
+        vals += [v[nz], v[nz]]
+    return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(N, N))
+
+
+def multilevel_reference(p, A, fixed, c=4):
+    """M^-1 = sum_l P_l T_l^-1 P_l^T of kernels_ml.cuh built from the ASSEMBLED matrix with scipy: level 0 = vertical line
+    blocks, level l = piecewise-constant aggregates of c^l x c^l lateral columns of free nodes, up to one column.
+    Returns a function r -> z (full-mesh vectors in the problem's node numbering)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    n0, n1, n2 = p.n
+    N = p.N
+    ng = np.broadcast_to(p.node_index_grid(), p.n)
+    free = np.ones(N)
+    free[np.asarray(fixed, dtype=np.int64)] = 0.
+    D = A.diagonal()
+    free[D <= 0] = 0.
+
+    def line_solver(P):
+        """tridiagonal blocks of P^T A P along the vertical index; columns of P are numbered (aggregate, i2)"""
+        Al = (P.T @ A @ P).tocsr()
+        m = Al.shape[0]
+        d = np.array(Al.diagonal())
+        off = np.array(Al.diagonal(1)) if m > 1 else np.zeros(0)
+        off = off * ((np.arange(m - 1) + 1) % n2 != 0)
+        dead = d <= 0
+        d = np.where(dead, 1., d)
+        off[dead[:-1] | dead[1:]] = 0.
+        lu = spla.splu(sp.diags([d, off, off], [0, 1, -1], format="csc"))
+        return lambda r: lu.solve(np.where(dead, 0., r))
+
+    levels = []
+    f = 1
+    while True:
+        a0, a1 = np.arange(n0) // f, np.arange(n1) // f
+        m0, m1 = a0.max() + 1, a1.max() + 1
+        agg = (a0[:, None, None] * m1 + a1[None, :, None]) * n2 + np.arange(n2)[None, None, :]
+        P = sp.csr_matrix((free[ng.ravel()], (ng.ravel(), np.broadcast_to(agg, p.n).ravel())), shape=(N, m0 * m1 * n2))
+        levels.append((P, line_solver(P)))
+        if m0 * m1 == 1:
+            break
+        f *= c
+    def apply(r):
+        z = np.zeros(N)
+        for P, s in levels:
+            z += P @ s(P.T @ r)
+        return z
+    apply.nlevels = len(levels)
+    return apply

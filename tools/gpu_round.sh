@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-for f in tests/test_gpu_operator.py tests/test_gpu_thermal.py tests/test_gpu_shockley.py tests/test_gpu_thermoelectric.py tests/test_gpu_boundary.py tests/test_gpu_masked.py tests/test_gpu_line.py tests/test_gpu_layout.py tests/test_golden.py tests/test_adapter_cpp.py; do
+for f in tests/test_gpu_multilevel.py tests/test_gpu_operator.py tests/test_gpu_thermal.py tests/test_gpu_shockley.py tests/test_gpu_thermoelectric.py tests/test_gpu_boundary.py tests/test_gpu_masked.py tests/test_gpu_line.py tests/test_gpu_layout.py tests/test_golden.py tests/test_adapter_cpp.py; do
   b=$(basename $f .py)
   timeout 900 python -m pytest $f -q -m gpu --tb=short -p no:cacheprovider > gpurun_out/$b.log 2>&1
   echo "$b exit $?" | tee -a gpurun_out/summary.txt

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libplaskfem_cuda.so")
+LIB_PATH = os.environ.get("PFEM_LIB") or os.path.join(_HERE, "libplaskfem_cuda.so")   # PFEM_LIB: A/B runs of two builds
 
 c_sz = C.c_size_t
 c_dp = C.POINTER(C.c_double)
@@ -123,6 +123,8 @@ def load():
                            "the CUDA algorithm has no CPU fallback")
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
+            if os.environ.get("PFEM_LIB") and not hasattr(lib, name):
+                continue    # A/B run against an older build
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args

@@ -52,13 +52,14 @@ struct FusedTile {
     static constexpr int LAYER = 2 * CHALF;
     static constexpr int NRED = 7;
     static constexpr size_t smem_bytes(int ns, int mode, int lk) {
-        return 128 + sizeof(double) * ((size_t)ns * (mode == 1 ? 6 : mode == 2 ? 5 : 4) * BOXP + 2 * PLANE + 2 * LAYER + 32 * NRED + 2 * (size_t)(lk + 2)) +
+        return 128 + sizeof(double) * ((size_t)ns * (mode == 1 ? 6 : mode >= 2 ? 5 : 4) * BOXP + 2 * PLANE + 2 * LAYER + 32 * NRED + 2 * (size_t)(lk + 2)) +
                16 * 8 + 16;
     }
 };
 
 
-// MODE 0: plain q = M A p (tests, pfem_apply);  1: the fused Jacobi-PCG iteration;  2: operator step of the line-Jacobi
+// MODE 0: plain q = M A p (tests, pfem_apply);  1: the fused Jacobi-PCG iteration;  3: MODE 2 with z = z_0 + z_1(parent aggregate)
+// (multilevel preconditioner, kernels_ml.cuh; vertical axis = I only);  2: operator step of the line-Jacobi
 // iteration (kernels_line.cuh): boxes z, p, mask instead of r, q, p, D^-1 — p' = mask z + beta p, x' = x + alpha p, q' = M A p'.
 template <int TJ, int RJ, int NS, int MINB, int VDIM, int MODE>
 __global__ void __launch_bounds__(32 * (TJ / RJ), MINB)
@@ -71,7 +72,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
     constexpr int TI = T::TI, HX = T::HX, PW = T::PW, PH = T::PH, BOX = T::BOX, BOXP = T::BOXP, PWP = T::PWP;
     constexpr int PLANE = T::PLANE, CW = T::CW, CHALF = T::CHALF, LAYER = T::LAYER, NRED = T::NRED;
     constexpr int NT = TI * (TJ / RJ);
-    constexpr bool FUSED = MODE >= 1, LINE = MODE == 2;
+    constexpr bool FUSED = MODE >= 1, LINE = MODE >= 2, MLZ = MODE == 3;
     constexpr int NBN = LINE ? 3 : FUSED ? 4 : 2;   // node boxes per stage: r q p d | z p mask | p d
     constexpr int NB = NBN + 2;          // + c_lat, c_vert
     constexpr int B_P = LINE ? 1 : FUSED ? 2 : 0, B_D = B_P + 1, B_CL = NBN, B_CV = NBN + 1;
@@ -133,19 +134,32 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         ring_raw = jj * PW + ii + (HX - 1);
         ring_pl = jj * PWP + ii;
     }
-    // multilevel preconditioner (MODE 2 only, vertical axis = I): z = z_0 + z_1(parent aggregate).  Row offsets of the own nodes
-    // and of the ring node inside a level-1 plane; the plane offset is added per step.
-    const bool mlz = LINE && ca.z1 != nullptr;
-    idx_t zc_own[RJ], zc_ring = 0;
-    if (mlz) {
-        const int ic = min(i, g.nI - 1);
+    // multilevel preconditioner (MODE 3, vertical axis = I): z = z_0 + z_1(parent) + z_2(parent).  The coarse values of a node
+    // change only every 4th / 16th plane of the march: they are kept in registers and re-fetched one step AHEAD of the plane
+    // that needs them, so the L2 latency of the gather never sits on the critical path of a step.
+    int zj_own[RJ], zj_ring = 0, zi_own = 0, zi_ring = 0;
+    double zc[RJ], zcr = 0., zt_own = 0., zt_ring = 0.;
+    if (MLZ) {
+        zi_own = min(i, g.nI - 1);
+        zt_own = __ldg(ca.zt + zi_own);
 #pragma unroll
-        for (int rr = 0; rr < RJ; ++rr) zc_own[rr] = (idx_t)(min(j0 + jl0 + rr, g.nJ - 1) >> PFEM_ML_SHIFT) * g.sJ + ic;
+        for (int rr = 0; rr < RJ; ++rr) { zj_own[rr] = min(j0 + jl0 + rr, g.nJ - 1); zc[rr] = 0.; }
         if (ring_raw >= 0) {
             const int jj = ring_pl / PWP, ii = ring_pl % PWP;
-            zc_ring = (idx_t)(min(max(j0 - 1 + jj, 0), g.nJ - 1) >> PFEM_ML_SHIFT) * g.sJ + min(max(i0 - 1 + ii, 0), g.nI - 1);
+            zj_ring = min(max(j0 - 1 + jj, 0), g.nJ - 1);
+            zi_ring = min(max(i0 - 1 + ii, 0), g.nI - 1);
+            zt_ring = __ldg(ca.zt + zi_ring);
         }
     }
+    auto load_zc = [&](const int P) {   // coarse correction of node plane P
+        const int Pc = min(max(P, 0), g.nK - 1);
+        const double* const a1 = ca.z1 + (idx_t)(Pc >> ca.sh1) * ca.nJ1 * g.sJ;
+        const double* const a2 = ca.z2 + (idx_t)(Pc >> ca.sh2) * ca.nJ2 * g.sJ;
+#pragma unroll
+        for (int rr = 0; rr < RJ; ++rr)
+            zc[rr] = (__ldg(a1 + (idx_t)(zj_own[rr] >> ca.sh1) * g.sJ + zi_own) + __ldg(a2 + (idx_t)(zj_own[rr] >> ca.sh2) * g.sJ + zi_own)) + zt_own;
+        if (ring_raw >= 0) zcr = (__ldg(a1 + (idx_t)(zj_ring >> ca.sh1) * g.sJ + zi_ring) + __ldg(a2 + (idx_t)(zj_ring >> ca.sh2) * g.sJ + zi_ring)) + zt_ring;
+    };
     // halo row / column of the element layer handled by this thread (entry e = NT-1-tid)
     int er_raw = -1, er_c = 0;
     double wIr = 0., wJr = 0., wKr = 0.;
@@ -242,13 +256,6 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
                 if (vj[rr]) xn[rr] = x[nown[rr] + sK];
         }
         const double hk = sHK[t], rk = sHK[lk + 2 + t];   // element layer L = P - 1 of this step (t >= 1)
-        double zc[RJ], zcr = 0.;
-        if (mlz) {   // coarse correction of this plane, in flight while the stage lands
-            const idx_t pc = (idx_t)(min(max(k0 - 1 + t, 0), g.nK - 1) >> PFEM_ML_SHIFT) * ca.nJ1 * g.sJ;
-#pragma unroll
-            for (int rr = 0; rr < RJ; ++rr) zc[rr] = __ldg(ca.z1 + pc + zc_own[rr]);
-            if (ring_raw >= 0) zcr = __ldg(ca.z1 + pc + zc_ring);
-        }
         mbar_wait(&bars[st], (uint32_t)((t / NS) & 1));
 
         // ---------------- phase 1: p' plane and coefficient layer -------------------------
@@ -258,7 +265,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
             double pn;
             if (FUSED) {
                 const double r0 = raw[ro], q0 = LINE ? 0. : raw[BOXP + ro], p0 = raw[B_P * BOXP + ro], dd = raw[B_D * BOXP + ro];
-                const double rn = LINE ? (mlz ? r0 + zc[rr] : r0) : fma(-alpha, q0, r0);
+                const double rn = MLZ ? r0 + zc[rr] : LINE ? r0 : fma(-alpha, q0, r0);
                 const double z = dd * rn;
                 pn = fma(beta, p0, z);
                 zdb[rr] = z; zdb[RJ + rr] = dd;
@@ -280,7 +287,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
                             red[4] = fma(rn, rn, red[4]);
                             red[5] = fma(z, z, red[5]);
                         }
-                        if (LINE) red[5] = fma(z, z, red[5]);
+                        if (MLZ) red[5] = fma(z, z, red[5]);
                         red[6] = fma(xv, xv, red[6]);
                     }
                 }
@@ -304,7 +311,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
             if (FUSED) {
                 const double r0 = raw[ring_raw], q0 = LINE ? 0. : raw[BOXP + ring_raw], p0 = raw[B_P * BOXP + ring_raw],
                              dd = raw[B_D * BOXP + ring_raw];
-                pn = fma(beta, p0, dd * (LINE ? (mlz ? r0 + zcr : r0) : fma(-alpha, q0, r0)));
+                pn = fma(beta, p0, dd * (MLZ ? r0 + zcr : LINE ? r0 : fma(-alpha, q0, r0)));
             } else {
                 pn = raw[B_P * BOXP + ring_raw];
             }
@@ -320,6 +327,10 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         }
         __syncthreads();
         if (tid == 0 && t + NS <= nsteps) issue(t + NS);
+        if (MLZ) {   // the next plane lies in another level-1 aggregate: fetch its coarse correction now, use it next step
+            const int Pn = min(max(k0 + t, 0), g.nK - 1), Pc = min(max(k0 - 1 + t, 0), g.nK - 1);
+            if ((Pn >> ca.sh1) != (Pc >> ca.sh1)) load_zc(Pn);
+        }
 
         // ---------------- phase 2: gather layer L between planes a (registers) and b --------
 #pragma unroll
@@ -398,6 +409,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         for (int rr = 0; rr < RJ; ++rr) nown[rr] += sK;
     };
 
+    if (MLZ) load_zc(k0 - 1);
     {
         typedef std::true_type Y;
         typedef std::false_type N;
@@ -431,7 +443,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
             // line-Jacobi PCG: rho, beta and the stopping test belong to the line kernel; here only alpha = rho / p'.q'
             const double pq = red[0];
             sc->pq = pq; sc->xx = red[6];
-            if (sc->line == 2) sc->zz = red[5];   // multilevel: the complete z exists only here (stopping test of the next iteration)
+            if (MLZ) sc->zz = red[5];   // multilevel: the complete z exists only here (stopping test of the next iteration)
             if (sc->done == 2) sc->done = 1;
             else if (sc->surf) {}   // convection terms: k_surf_iter adds p'.S p' and computes alpha
             else if (!sc->bench && !(pq > 0.)) { sc->done = 1; sc->status = (pq == pq) ? -1 : -2; }
@@ -544,10 +556,15 @@ static inline cudaError_t launch_fused_inst(const FusedPlan& f, const Grid& g, i
 template <int TJ, int RJ, int NS, int MINB, int MODE>
 static inline cudaError_t launch_fused_vdim(const FusedPlan& f, const Grid& g, int par, double* r_out, double* q_out, double* p_out,
                                             double* x, Scalars* sc, double* partials, const PeerOut& po, cudaStream_t st, const CoarseAdd& ca) {
-    switch (g.vdim) {
-        case 0: return launch_fused_inst<TJ, RJ, NS, MINB, 0, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st, ca);
-        case 1: return launch_fused_inst<TJ, RJ, NS, MINB, 1, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st, ca);
-        default: return launch_fused_inst<TJ, RJ, NS, MINB, 2, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st, ca);
+    if constexpr (MODE == 3) {   // multilevel preconditioner: vertical axis = I only
+        if (g.vdim != 0) return cudaErrorInvalidConfiguration;
+        return launch_fused_inst<TJ, RJ, NS, MINB, 0, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st, ca);
+    } else {
+        switch (g.vdim) {
+            case 0: return launch_fused_inst<TJ, RJ, NS, MINB, 0, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st, ca);
+            case 1: return launch_fused_inst<TJ, RJ, NS, MINB, 1, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st, ca);
+            default: return launch_fused_inst<TJ, RJ, NS, MINB, 2, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st, ca);
+        }
     }
 }
 
@@ -556,7 +573,7 @@ static inline cudaError_t launch_fused_vdim(const FusedPlan& f, const Grid& g, i
 template <int MODE>
 static inline cudaError_t launch_fused_dispatch(const FusedPlan& f, const Grid& g, int par, double* r_out, double* q_out,
                                                 double* p_out, double* x, Scalars* sc, double* partials, const PeerOut& po,
-                                                cudaStream_t st, const CoarseAdd ca = CoarseAdd{nullptr, 0}) {
+                                                cudaStream_t st, const CoarseAdd ca = CoarseAdd{nullptr, 0, 0, nullptr, 0, 0, nullptr}) {
 #define PFEM_FUSED_CASE(TJ, RJ, NS, MINB) \
     if (f.tj == TJ && f.rj == RJ && f.ns == NS && f.minb == MINB) return launch_fused_vdim<TJ, RJ, NS, MINB, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st, ca);
     PFEM_FUSED_CASE(8, 2, 2, 3)    // production tile (tools/tune_fused.py); the others are kept for PFEM_FUSED_TILE tuning runs

@@ -27,7 +27,7 @@
 
 namespace pfem {
 
-#define PFEM_ML_MAXL 6          // 4^6 = 4096 nodes per lateral axis
+#define PFEM_ML_MAXL 3          // levels: 4x4 aggregates, 16x16 aggregates, one column
 #define PFEM_ML_C 4             // aggregation factor per level and lateral axis
 #define PFEM_ML_SHIFT 2
 
@@ -38,18 +38,15 @@ struct LineDom {
 };
 
 struct MLDev {
-    int nlev;                               // coarse levels 1..nlev (0: preconditioner not set up)
+    int nlev;                               // coarse levels 1..nlev, the LAST one is the top level = one column (0: not set up)
+    int nagg;                               // aggregated levels with more than one column: nlev - 1 (at most 2: 4x4 and 16x16)
     LineDom dom[PFEM_ML_MAXL + 1];          // [0] = fine mesh
-    double* r[PFEM_ML_MAXL + 1];            // restricted residual of level l >= 1
-    double* z[PFEM_ML_MAXL + 1];            // z_l, l >= 1 (z[1] also receives the prolonged sum of the higher levels)
+    double* r[PFEM_ML_MAXL + 1];            // restricted residual of the aggregated level l >= 1
+    double* z[PFEM_ML_MAXL + 1];            // z_l, l >= 1 (the last aggregated level also receives z_top)
     double* ll[PFEM_ML_MAXL + 1];           // L D L^T factors of T_l, l >= 1 (before k_ml_factor: off-diagonals / diagonals)
     double* ld[PFEM_ML_MAXL + 1];
-};
-
-// What k_fpcg<MODE 2> adds to z_0 on the fly: z_1 of the parent aggregate (null: plain line-Jacobi)
-struct CoarseAdd {
-    const double* z1;
-    int nJ1;
+    double* part;                           // block totals for the top-level residual
+    double* zero;                           // a zero row
 };
 
 // ---- set-up: tridiagonal blocks of the Galerkin operators -------------------------------------------------------
@@ -166,12 +163,12 @@ __global__ void k_ml_factor(const LineDom d, double* __restrict__ ll, double* __
 
 // ---- iteration ---------------------------------------------------------------------------------------------------
 
-// Finalise rho / beta / stopping test once all levels have added their r_l.z_l.  mode 1: rho -> sc->bz.
+// Finalise rho / beta / stopping test once all levels have added their r_l.z_l.  mode 1: rho -> sc->bz; mode 2: nothing (test hook).
 // ||z||^2 of the stopping test comes from the operator kernel of the PREVIOUS iteration (it is the only kernel that forms
 // the complete z); a test that lags by one iteration can only delay the stop by one iteration.
 __device__ __forceinline__ void ml_finalize(Scalars* sc, const double rho, const double rr, const int mode) {
     if (mode == 1) { sc->bz = rho; return; }
-    if (mode == 2) return;   // pfem_apply_precond: z only
+    if (mode == 2) return;
     const double rho_old = sc->rho;
     const int first = (sc->launch == 0);
     sc->rho_prev = rho_old; sc->rho = rho; sc->rr = rr;
@@ -187,17 +184,102 @@ __device__ __forceinline__ void ml_finalize(Scalars* sc, const double rho, const
     }
 }
 
+// One tridiagonal solve T z = r by a warp, operands in the coalesced layout (lane holds the double2 at 2*lane + 64*c):
+// transposition into the segment layout through the padded row `tb`, forward and backward sweep as warp scans over
+// affine maps (same scheme as k_line_I).  Returns z in the coalesced layout and this lane's part of r.z (and of r.r).
+template <int SEG>
+__device__ __forceinline__ void warp_line_solve(double* tb, const int lane, const double2 (&vr)[SEG / 2], const double2 (&vl)[SEG / 2],
+                                                const double2 (&vd)[SEG / 2], double2 (&vz)[SEG / 2], double& rz, double& rr) {
+    const int so = lane * SEG + lane;
+    double rp[SEG], l[SEG + 1], wv[SEG];
+#pragma unroll
+    for (int c = 0; c < SEG / 2; ++c) {
+        const int i = 2 * lane + 64 * c;
+        tb[i + i / SEG] = vr[c].x; tb[i + 1 + (i + 1) / SEG] = vr[c].y;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < SEG; ++e) rp[e] = tb[so + e];
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < SEG / 2; ++c) {
+        const int i = 2 * lane + 64 * c;
+        tb[i + i / SEG] = vl[c].x; tb[i + 1 + (i + 1) / SEG] = vl[c].y;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < SEG; ++e) l[e] = tb[so + e];
+    l[SEG] = (lane < 31) ? tb[so + SEG + 1] : 0.;
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < SEG / 2; ++c) {
+        const int i = 2 * lane + 64 * c;
+        tb[i + i / SEG] = vd[c].x; tb[i + 1 + (i + 1) / SEG] = vd[c].y;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < SEG; ++e) wv[e] = tb[so + e];
+    __syncwarp();
+    // forward sweep y_e = r_e - l_e y_{e-1}: affine map of the segment, inclusive warp scan, replay
+    double A = 1., B = 0.;
+#pragma unroll
+    for (int e = 0; e < SEG; ++e) { B = fma(-l[e], B, rp[e]); A = -l[e] * A; }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double Ap = __shfl_up_sync(0xffffffffu, A, o), Bp = __shfl_up_sync(0xffffffffu, B, o);
+        if (lane >= o) { B = fma(A, Bp, B); A *= Ap; }
+    }
+    double y = __shfl_up_sync(0xffffffffu, B, 1);
+    if (lane == 0) y = 0.;
+#pragma unroll
+    for (int e = 0; e < SEG; ++e) { y = fma(-l[e], y, rp[e]); wv[e] *= y; }
+    // backward sweep z_e = w_e - l_{e+1} z_{e+1}
+    A = 1.; B = 0.;
+#pragma unroll
+    for (int e = SEG - 1; e >= 0; --e) { B = fma(-l[e + 1], B, wv[e]); A = -l[e + 1] * A; }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double An = __shfl_down_sync(0xffffffffu, A, o), Bn = __shfl_down_sync(0xffffffffu, B, o);
+        if (lane + o < 32) { B = fma(A, Bn, B); A *= An; }
+    }
+    double z = __shfl_down_sync(0xffffffffu, B, 1);
+    if (lane == 31) z = 0.;
+#pragma unroll
+    for (int e = SEG - 1; e >= 0; --e) {
+        z = fma(-l[e + 1], z, wv[e]);
+        tb[so + e] = z;
+        rz = fma(rp[e], z, rz);
+        rr = fma(rp[e], rp[e], rr);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < SEG / 2; ++c) {
+        const int i = 2 * lane + 64 * c;
+        vz[c] = make_double2(tb[i + i / SEG], tb[i + 1 + (i + 1) / SEG]);
+    }
+    __syncwarp();
+}
+
+// The top level (ONE column = the 1-D vertical problem of the whole device) rides on the last aggregated level's kernel:
+// every block also totals the residual rows it handles, the block that finishes last adds the totals in block order, solves
+// the top line and finalises (z_top depends on i only: the operator kernel loads it once per thread).
+struct MLTop {
+    double* part;        // [gridDim.x][sJ] block totals; null: this launch is not the last aggregated level
+    const double* ll;    // factors of the top line
+    const double* ld;
+    double* z;           // [sJ] z_top
+};
+
 // One level of the preconditioner.  One block (8 warps) per 4x4 aggregate of rows: warp w solves rows
-// (j = 4J + (w & 3), k = 4K + 2 (w >> 2) + {0,1}) with the warp-scan line solve of k_line_I and accumulates their residuals;
-// the block then adds the 8 partial rows in a fixed order into the residual row of the parent aggregate.
+// (j = 4J + (w & 3), k = 4K + 2 (w >> 2) + {0,1}) and accumulates their residuals; the block then adds the 8 partial rows
+// in a fixed order into the residual row of the parent aggregate (rc_out, null on the last aggregated level).
 // FINE: level 0 — r' = r - alpha q is formed and stored, the sums start the accumulators; otherwise r_in is the level's residual.
-// last: this launch is the top level — finalise.
 template <int SEG, bool FINE>
 __global__ void __launch_bounds__(256)
 k_line_ml(const LineDom d, const double* __restrict__ r_in, const double* __restrict__ q_in, const double* __restrict__ ll,
           const double* __restrict__ ld, double* __restrict__ r_out, double* __restrict__ z_out, double* __restrict__ rc_out,
-          const int nJc, Scalars* sc, double* partials, const int mode, const int last) {
-    constexpr int ROW = 32 * SEG, ROWP = ROW + ROW / SEG;
+          const int nJc, Scalars* sc, double* partials, const int mode, const MLTop top) {
+    constexpr int ROW = 32 * SEG, ROWP = ROW + ROW / SEG, NE = (ROW + 255) / 256;
     __shared__ double sh[32 * 2];
     __shared__ int sh_flag;
     __shared__ double tbuf[8][ROWP];   // per-warp transposition row; afterwards the warp's partial residual row
@@ -206,8 +288,10 @@ k_line_ml(const LineDom d, const double* __restrict__ r_in, const double* __rest
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double* const tb = tbuf[w];
     const int naJ = (d.nJ + PFEM_ML_C - 1) / PFEM_ML_C, naK = (d.nK + PFEM_ML_C - 1) / PFEM_ML_C;
-    const int so = lane * SEG + lane;
     double acc[2] = {0., 0.};
+    double tot[NE];                    // block total of the residual rows (elements threadIdx.x + 256 e)
+#pragma unroll
+    for (int e = 0; e < NE; ++e) tot[e] = 0.;
     for (int agg = blockIdx.x; agg < naJ * naK; agg += gridDim.x) {
         const int J = agg % naJ, K = agg / naJ;
         double2 rs[SEG / 2];
@@ -218,8 +302,7 @@ k_line_ml(const LineDom d, const double* __restrict__ r_in, const double* __rest
             const int j = J * PFEM_ML_C + (w & 3), k = K * PFEM_ML_C + 2 * (w >> 2) + t;
             if (j >= d.nJ || k >= d.nK) continue;     // warp-uniform
             const idx_t base = d.sJ * j + d.sK * (idx_t)k;
-            double rp[SEG], l[SEG + 1], wv[SEG];
-            double2 vr[SEG / 2], vl[SEG / 2], vd[SEG / 2];
+            double2 vr[SEG / 2], vl[SEG / 2], vd[SEG / 2], vz[SEG / 2];
 #pragma unroll
             for (int c = 0; c < SEG / 2; ++c) {
                 const int i = 2 * lane + 64 * c;
@@ -236,124 +319,104 @@ k_line_ml(const LineDom d, const double* __restrict__ r_in, const double* __rest
                     rs[c].x += vr[c].x; rs[c].y += vr[c].y;
                 }
             }
+            double rr = 0.;
+            warp_line_solve<SEG>(tb, lane, vr, vl, vd, vz, acc[0], rr);
+            if (FINE) acc[1] += rr;
 #pragma unroll
             for (int c = 0; c < SEG / 2; ++c) {
                 const int i = 2 * lane + 64 * c;
-                tb[i + i / SEG] = vr[c].x; tb[i + 1 + (i + 1) / SEG] = vr[c].y;
+                if (i < d.sJ) *reinterpret_cast<double2*>(z_out + base + i) = vz[c];
             }
-            __syncwarp();
-#pragma unroll
-            for (int e = 0; e < SEG; ++e) rp[e] = tb[so + e];
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < SEG / 2; ++c) {
-                const int i = 2 * lane + 64 * c;
-                tb[i + i / SEG] = vl[c].x; tb[i + 1 + (i + 1) / SEG] = vl[c].y;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int e = 0; e < SEG; ++e) l[e] = tb[so + e];
-            l[SEG] = (lane < 31) ? tb[so + SEG + 1] : 0.;
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < SEG / 2; ++c) {
-                const int i = 2 * lane + 64 * c;
-                tb[i + i / SEG] = vd[c].x; tb[i + 1 + (i + 1) / SEG] = vd[c].y;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int e = 0; e < SEG; ++e) wv[e] = tb[so + e];
-            __syncwarp();
-            // forward sweep y_e = r_e - l_e y_{e-1}: affine map of the segment, inclusive warp scan, replay
-            double A = 1., B = 0.;
-#pragma unroll
-            for (int e = 0; e < SEG; ++e) { B = fma(-l[e], B, rp[e]); A = -l[e] * A; }
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double Ap = __shfl_up_sync(0xffffffffu, A, o), Bp = __shfl_up_sync(0xffffffffu, B, o);
-                if (lane >= o) { B = fma(A, Bp, B); A *= Ap; }
-            }
-            double y = __shfl_up_sync(0xffffffffu, B, 1);
-            if (lane == 0) y = 0.;
-#pragma unroll
-            for (int e = 0; e < SEG; ++e) { y = fma(-l[e], y, rp[e]); wv[e] *= y; }
-            // backward sweep z_e = w_e - l_{e+1} z_{e+1}
-            A = 1.; B = 0.;
-#pragma unroll
-            for (int e = SEG - 1; e >= 0; --e) { B = fma(-l[e + 1], B, wv[e]); A = -l[e + 1] * A; }
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double An = __shfl_down_sync(0xffffffffu, A, o), Bn = __shfl_down_sync(0xffffffffu, B, o);
-                if (lane + o < 32) { B = fma(A, Bn, B); A *= An; }
-            }
-            double z = __shfl_down_sync(0xffffffffu, B, 1);
-            if (lane == 31) z = 0.;
-#pragma unroll
-            for (int e = SEG - 1; e >= 0; --e) {
-                z = fma(-l[e + 1], z, wv[e]);
-                tb[so + e] = z;
-                acc[0] = fma(rp[e], z, acc[0]);
-                if (FINE) acc[1] = fma(rp[e], rp[e], acc[1]);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < SEG / 2; ++c) {
-                const int i = 2 * lane + 64 * c;
-                if (i < d.sJ) *reinterpret_cast<double2*>(z_out + base + i) = make_double2(tb[i + i / SEG], tb[i + 1 + (i + 1) / SEG]);
-            }
-            __syncwarp();
         }
-        if (rc_out) {
+        if (rc_out || top.part) {
 #pragma unroll
             for (int c = 0; c < SEG / 2; ++c) { tb[2 * lane + 64 * c] = rs[c].x; tb[2 * lane + 64 * c + 1] = rs[c].y; }
             __syncthreads();
             const idx_t cb = ((idx_t)K * nJc + J) * d.sJ;
-            for (int i = threadIdx.x; i < d.sJ; i += 256) {
-                double s = tbuf[0][i];
 #pragma unroll
-                for (int u = 1; u < 8; ++u) s += tbuf[u][i];
-                rc_out[cb + i] = s;
+            for (int e = 0; e < NE; ++e) {
+                const int i = threadIdx.x + 256 * e;
+                if (i < d.sJ) {
+                    double s = tbuf[0][i];
+#pragma unroll
+                    for (int u = 1; u < 8; ++u) s += tbuf[u][i];
+                    if (rc_out) rc_out[cb + i] = s;
+                    tot[e] += s;
+                }
             }
             __syncthreads();
         }
     }
+    if (top.part) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const int i = threadIdx.x + 256 * e;
+            if (i < d.sJ) top.part[(idx_t)blockIdx.x * d.sJ + i] = tot[e];
+        }
+    }
     if (grid_reduce<2, false>(acc, partials, &sc->ticket[3], sh, &sh_flag)) {
+        double rho_top = 0.;
+        if (top.part) {
+            // residual of the top level = sum of all rows of this level, block totals added in block order
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const int i = threadIdx.x + 256 * e;
+                if (i < ROW) {
+                    double s = 0.;
+                    if (i < d.sJ)
+                        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(top.part + (idx_t)b * d.sJ + i);
+                    tbuf[1][i] = s;
+                }
+            }
+            __syncthreads();
+            if (w == 0) {
+                double2 vr[SEG / 2], vl[SEG / 2], vd[SEG / 2], vz[SEG / 2];
+#pragma unroll
+                for (int c = 0; c < SEG / 2; ++c) {
+                    const int i = 2 * lane + 64 * c;
+                    vr[c] = make_double2(tbuf[1][i], tbuf[1][i + 1]);
+                    vl[c] = vd[c] = make_double2(0., 0.);
+                    if (i < d.sJ) { vl[c] = *reinterpret_cast<const double2*>(top.ll + i); vd[c] = *reinterpret_cast<const double2*>(top.ld + i); }
+                }
+                double rr = 0.;
+                warp_line_solve<SEG>(tbuf[0], lane, vr, vl, vd, vz, rho_top, rr);
+                rho_top = warp_sum(rho_top);
+#pragma unroll
+                for (int c = 0; c < SEG / 2; ++c) {
+                    const int i = 2 * lane + 64 * c;
+                    if (i < d.sJ) *reinterpret_cast<double2*>(top.z + i) = vz[c];
+                }
+            }
+        }
         if (threadIdx.x == 0) {
-            const double rho = FINE ? acc[0] : sc->ml_rho + acc[0];
+            const double rho = (FINE ? acc[0] : sc->ml_rho + acc[0]) + rho_top;
             const double rr = FINE ? acc[1] : sc->ml_rr;
             sc->ml_rho = rho; sc->ml_rr = rr;
-            if (last) ml_finalize(sc, rho, rr, mode);
+            if (top.part) ml_finalize(sc, rho, rr, mode);
         }
     }
 }
 
-// z_1 += sum over the levels l >= 2 of z_l at the parent aggregate: afterwards z_1 alone is the whole coarse correction
-__global__ void k_ml_down(const MLDev ml, Scalars* sc, const int mode) {
-    if (mode == 0 && sc->done == 1) return;
-    const LineDom d1 = ml.dom[1];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int J = blockIdx.y, K = blockIdx.z;
-    if (i >= d1.sJ) return;
-    double s = 0.;
-    for (int l = 2; l <= ml.nlev; ++l) {
-        const int sh = PFEM_ML_SHIFT * (l - 1);
-        s += ml.z[l][((idx_t)(K >> sh) * ml.dom[l].nJ + (J >> sh)) * d1.sJ + i];
-    }
-    ml.z[1][((idx_t)K * d1.nJ + J) * d1.sJ + i] += s;
-}
+// What k_fpcg<MODE 3> adds to z_0 on the fly: z of the parent aggregates on the (up to) two aggregated levels,
+// z_a[((k >> sh_a) * nJ_a + (j >> sh_a)) * sJ + i], plus z_top[i].  Unused slots point to a zero row with shift 31.
+struct CoarseAdd {
+    const double* z1;
+    int nJ1, sh1;
+    const double* z2;
+    int nJ2, sh2;
+    const double* zt;    // z_top [sJ]
+};
 
-}  // namespace pfem
-
-namespace pfem {
 __global__ void k_pupdate_plain(idx_t N, const double* __restrict__ r, const double* __restrict__ dinv, double* __restrict__ z) {
     for (idx_t n = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; n < N; n += (idx_t)gridDim.x * blockDim.x) z[n] = dinv[n] * r[n];
 }
-// test hook (pfem_apply_precond): the complete z = z_0 + z_1(parent) on the fine lattice
-__global__ void k_ml_prolong_add(const Grid g, const double* __restrict__ z0, const double* __restrict__ z1, const int nJ1, double* __restrict__ out) {
+// test hook (pfem_apply_precond): the complete z = z_0 + coarse correction on the fine lattice
+__global__ void k_ml_prolong_add(const Grid g, const double* __restrict__ z0, const CoarseAdd ca, double* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y, k = blockIdx.z;
     if (i >= g.nI) return;
     const idx_t n = i + g.sJ * j + g.sK * (idx_t)k;
-    out[n] = z0[n] + (z1 ? z1[((idx_t)(k >> PFEM_ML_SHIFT) * nJ1 + (j >> PFEM_ML_SHIFT)) * g.sJ + i] : 0.);
+    out[n] = z0[n] + ca.z1[((idx_t)(k >> ca.sh1) * ca.nJ1 + (j >> ca.sh1)) * g.sJ + i] + ca.z2[((idx_t)(k >> ca.sh2) * ca.nJ2 + (j >> ca.sh2)) * g.sJ + i] + ca.zt[i];
 }
+
 }  // namespace pfem

@@ -1136,6 +1136,14 @@ static int launch_line_solve(pfem_ctx* ctx, const double* r_in, const double* q_
 __global__ void k_force_running(Scalars* sc) { sc->done = 0; sc->status = 0; }
 
 // ---- multilevel line preconditioner (kernels_ml.cuh) ----------------------------------------------------------
+static int ml_blocks(const pfem_ctx* ctx, const LineDom& d) {
+    const int cap = ctx->sm_count * 2;   // one resident wave of 256-thread blocks, like k_line_I
+    const int na = ((d.nJ + PFEM_ML_C - 1) / PFEM_ML_C) * ((d.nK + PFEM_ML_C - 1) / PFEM_ML_C);
+    if (na <= cap) return na;
+    const int per = (na + cap - 1) / cap;   // every block the same number of aggregates (+-1)
+    return (na + per - 1) / per;
+}
+
 static int ensure_ml(pfem_ctx* ctx) {
     if (ctx->ml.nlev) return PFEM_OK;
     const Grid& g = ctx->g;
@@ -1144,23 +1152,30 @@ static int ensure_ml(pfem_ctx* ctx) {
     MLDev ml;
     memset(&ml, 0, sizeof ml);
     ml.dom[0] = LineDom{g.nI, g.nJ, g.nK, g.sJ, g.sK};
+    // aggregated levels (4x4, 16x16 lateral columns) as long as they hold more than one column, then the top level = one column
     int L = 0;
-    for (int nJ = g.nJ, nK = g.nK; nJ > 1 || nK > 1;) {
-        if (L == PFEM_ML_MAXL) FAIL(PFEM_ERR_BAD_INPUT, "mesh too wide for %d aggregation levels", PFEM_ML_MAXL);
+    for (int nJ = g.nJ, nK = g.nK; L < PFEM_ML_MAXL - 1;) {
         nJ = (nJ + PFEM_ML_C - 1) / PFEM_ML_C; nK = (nK + PFEM_ML_C - 1) / PFEM_ML_C;
+        if (nJ == 1 && nK == 1) break;
         ++L;
         ml.dom[L] = LineDom{g.nI, nJ, nK, g.sJ, g.sJ * nJ};
     }
-    const idx_t slen = (idx_t)ml.dom[1].nJ * ml.dom[1].nK * g.sJ;
-    TRY(dev_alloc(ctx, &ctx->mlS, (size_t)(2 * L * slen), 0));
-    for (int l = 1; l <= L; ++l) {
+    ml.nagg = L;
+    ml.nlev = L + 1;
+    ml.dom[ml.nlev] = LineDom{g.nI, 1, 1, g.sJ, g.sJ};
+    // set-up partial sums live on the level-1 aggregates whether or not level 1 is a level of its own
+    const int nJ1 = (g.nJ + PFEM_ML_C - 1) / PFEM_ML_C, nK1 = (g.nK + PFEM_ML_C - 1) / PFEM_ML_C;
+    const idx_t slen = (idx_t)nJ1 * nK1 * g.sJ;
+    TRY(dev_alloc(ctx, &ctx->mlS, (size_t)(2 * ml.nlev * slen), 0));
+    for (int l = 1; l <= ml.nlev; ++l) {
         const size_t len = (size_t)ml.dom[l].nJ * ml.dom[l].nK * g.sJ;
-        TRY(dev_alloc(ctx, &ml.r[l], len, 0));
+        if (l <= ml.nagg) TRY(dev_alloc(ctx, &ml.r[l], len, 0));
         TRY(dev_alloc(ctx, &ml.z[l], len, 0));
         if (l == 1) { ml.ld[1] = ctx->mlS; ml.ll[1] = ctx->mlS + slen; }   // level 1: the partial sums are the blocks themselves
         else { TRY(dev_alloc(ctx, &ml.ld[l], len, 0)); TRY(dev_alloc(ctx, &ml.ll[l], len, 0)); }
     }
-    ml.nlev = L;
+    TRY(dev_alloc(ctx, &ml.part, (size_t)(ctx->sm_count * 2 + 1) * g.sJ, 0));
+    TRY(dev_alloc(ctx, &ml.zero, (size_t)g.sJ, 0));
     ctx->ml = ml;
     ctx->ml_slen = slen;
     return PFEM_OK;
@@ -1171,12 +1186,15 @@ static int ml_setup(pfem_ctx* ctx) {
     const Grid& g = ctx->g;
     const MLDev& ml = ctx->ml;
     const int L = ml.nlev;
-    k_ml_rowsums<<<dim3((unsigned)((g.sJ + 31) / 32), ml.dom[1].nJ, ml.dom[1].nK), dim3(32, PFEM_ML_C, PFEM_ML_C), 0, ctx->stream>>>(
-        g, ctx->cl, ctx->cv, ctx->dinv, L, ml.dom[1].nJ, ctx->mlS, ctx->ml_slen);
+    const int nJ1 = (g.nJ + PFEM_ML_C - 1) / PFEM_ML_C, nK1 = (g.nK + PFEM_ML_C - 1) / PFEM_ML_C;
+    const LineDom d1{g.nI, nJ1, nK1, g.sJ, g.sJ * nJ1};
+    k_ml_rowsums<<<dim3((unsigned)((g.sJ + 31) / 32), nJ1, nK1), dim3(32, PFEM_ML_C, PFEM_ML_C), 0, ctx->stream>>>(
+        g, ctx->cl, ctx->cv, ctx->dinv, L, nJ1, ctx->mlS, ctx->ml_slen);
     KCHECK(); LAUNCHED(1);
-    for (int l = 2, f = PFEM_ML_C; l <= L; ++l, f *= PFEM_ML_C) {
+    for (int l = 2; l <= L; ++l) {
+        const int f = (l == L) ? (1 << 30) : PFEM_ML_C;   // the top level gathers everything
         k_ml_gather<<<dim3((unsigned)((g.sJ + 127) / 128), ml.dom[l].nJ, ml.dom[l].nK), 128, 0, ctx->stream>>>(
-            ml.dom[1], ml.dom[l], f, ctx->mlS + (size_t)(2 * (l - 1)) * ctx->ml_slen, ctx->mlS + (size_t)(2 * (l - 1) + 1) * ctx->ml_slen, ml.ld[l], ml.ll[l]);
+            d1, ml.dom[l], f, ctx->mlS + (size_t)(2 * (l - 1)) * ctx->ml_slen, ctx->mlS + (size_t)(2 * (l - 1) + 1) * ctx->ml_slen, ml.ld[l], ml.ll[l]);
         KCHECK(); LAUNCHED(1);
     }
     for (int l = 1; l <= L; ++l) {
@@ -1187,28 +1205,38 @@ static int ml_setup(pfem_ctx* ctx) {
     return PFEM_OK;
 }
 
+// the two gathers of k_fpcg<MODE 3>
+static CoarseAdd ml_coarse_add(const pfem_ctx* ctx) {
+    const MLDev& ml = ctx->ml;
+    CoarseAdd ca;
+    const double* zt = ml.z[ml.nlev];
+    if (ml.nagg == 0) ca = CoarseAdd{ml.zero, 1, 31, ml.zero, 1, 31, zt};                                   // top level only
+    else if (ml.nagg == 1) ca = CoarseAdd{ml.z[1], ml.dom[1].nJ, PFEM_ML_SHIFT, ml.zero, 1, 31, zt};
+    else ca = CoarseAdd{ml.z[1], ml.dom[1].nJ, PFEM_ML_SHIFT, ml.z[2], ml.dom[2].nJ, 2 * PFEM_ML_SHIFT, zt};
+    return ca;
+}
+
 template <int SEG>
 static void launch_ml_chain_seg(pfem_ctx* ctx, const double* r_in, const double* q_in, double* r_out, int mode) {
     const MLDev& ml = ctx->ml;
-    const int L = ml.nlev;
-    const int cap = ctx->sm_count * 2;   // one resident wave of 256-thread blocks, like k_line_I
-    auto blocks = [&](const LineDom& d) {
-        const int na = ((d.nJ + PFEM_ML_C - 1) / PFEM_ML_C) * ((d.nK + PFEM_ML_C - 1) / PFEM_ML_C);
-        if (na <= cap) return na;
-        const int per = (na + cap - 1) / cap;   // every block the same number of aggregates (+-1)
-        return (na + per - 1) / per;
+    const int La = ml.nagg, T = ml.nlev;
+    auto top_of = [&](int l) {   // the kernel of the last aggregated level also does the top level
+        MLTop t;
+        memset(&t, 0, sizeof t);
+        if (l != La) return t;
+        t.part = ml.part; t.ll = ml.ll[T]; t.ld = ml.ld[T]; t.z = ml.z[T];
+        return t;
     };
-    k_line_ml<SEG, true><<<blocks(ml.dom[0]), 256, 0, ctx->stream>>>(ml.dom[0], r_in, q_in, ctx->ll, ctx->ld, r_out, ctx->lz, ml.r[1], ml.dom[1].nJ,
-                                                                        ctx->d_sc, ctx->partials, mode, 0);
-    for (int l = 1; l <= L; ++l)
-        k_line_ml<SEG, false><<<blocks(ml.dom[l]), 256, 0, ctx->stream>>>(ml.dom[l], ml.r[l], nullptr, ml.ll[l], ml.ld[l], nullptr, ml.z[l],
-                                                                             l < L ? ml.r[l + 1] : nullptr, l < L ? ml.dom[l + 1].nJ : 0, ctx->d_sc,
-                                                                             ctx->partials, mode, l == L);
-    if (L >= 2 && mode != 1)
-        k_ml_down<<<dim3((unsigned)((ml.dom[1].sJ + 127) / 128), ml.dom[1].nJ, ml.dom[1].nK), 128, 0, ctx->stream>>>(ml, ctx->d_sc, mode);
+    k_line_ml<SEG, true><<<ml_blocks(ctx, ml.dom[0]), 256, 0, ctx->stream>>>(ml.dom[0], r_in, q_in, ctx->ll, ctx->ld, r_out, ctx->lz,
+                                                                           La >= 1 ? ml.r[1] : nullptr, La >= 1 ? ml.dom[1].nJ : 0, ctx->d_sc,
+                                                                           ctx->partials, mode, top_of(0));
+    for (int l = 1; l <= La; ++l)
+        k_line_ml<SEG, false><<<ml_blocks(ctx, ml.dom[l]), 256, 0, ctx->stream>>>(ml.dom[l], ml.r[l], nullptr, ml.ll[l], ml.ld[l], nullptr, ml.z[l],
+                                                                                l < La ? ml.r[l + 1] : nullptr, l < La ? ml.dom[l + 1].nJ : 0,
+                                                                                ctx->d_sc, ctx->partials, mode, top_of(l));
 }
 
-// z_0 .. z_L and the CG scalars of the multilevel preconditioner; mode 1: only b.M^-1 b -> sc->bz
+// z_0 .. z_top and the CG scalars of the multilevel preconditioner; mode 1: only b.M^-1 b -> sc->bz; mode 2: z only
 static int launch_ml_chain(pfem_ctx* ctx, const double* r_in, const double* q_in, double* r_out, int mode) {
     switch (line_seg(ctx->g)) {
         case 2: launch_ml_chain_seg<2>(ctx, r_in, q_in, r_out, mode); break;
@@ -1264,8 +1292,10 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
         else launch_line_solve(ctx, ctx->r, qq[parity], ctx->r, 0);
         if (ev) cudaEventRecord(ev[1], ctx->stream);
         const PeerOut po = peer_out(ctx, 1 - parity);   // slab mode: p' of the boundary planes goes to the neighbours
-        launch_fused_dispatch<2>(ctx->line_plan, g, parity, nullptr, qq[1 - parity], pp[1 - parity], ctx->x, ctx->d_sc, ctx->partials,
-                                    po, ctx->stream, mlp ? CoarseAdd{ctx->ml.z[1], ctx->ml.dom[1].nJ} : CoarseAdd{nullptr, 0});
+        if (mlp) launch_fused_dispatch<3>(ctx->line_plan, g, parity, nullptr, qq[1 - parity], pp[1 - parity], ctx->x, ctx->d_sc, ctx->partials,
+                                          po, ctx->stream, ml_coarse_add(ctx));
+        else launch_fused_dispatch<2>(ctx->line_plan, g, parity, nullptr, qq[1 - parity], pp[1 - parity], ctx->x, ctx->d_sc, ctx->partials,
+                                      po, ctx->stream);
         if (ctx->surf_iter) {  // q' += S p' on the boundary rows, alpha from the completed p'.q' (q is only read on owned rows: no push)
             PeerOut none;
             memset(&none, 0, sizeof none);
@@ -1314,7 +1344,7 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
 }
 
 static int kernels_per_iteration(const pfem_ctx* ctx, int variant) {
-    if (variant == 3 && ctx->precond == 2) return 2 + ctx->ml.nlev + (ctx->ml.nlev >= 2 ? 1 : 0) + ctx->surf_iter;
+    if (variant == 3 && ctx->precond == 2) return 2 + ctx->ml.nagg + ctx->surf_iter;   // level kernels (the top level rides on the last one) + k_fpcg
     return variant == 1 ? 3 : (variant == 3 ? (ctx->precond == 1 ? 2 + ctx->surf_iter : 1 + ctx->surf_iter) : 2);
 }  // variants 0 (TMA) and 2 (LDG tiled) fuse the p-update
 
@@ -1373,7 +1403,7 @@ static int pcg_prepare(pfem_ctx* ctx, const pfem_opts* o, int bench) {
         k_line_factor<<<(unsigned)((g.N / (g.vdim == 0 ? g.nI : g.vdim == 1 ? g.nJ : g.nK) + 127) / 128), 128, 0, ctx->stream>>>(
             g, ctx->cl, ctx->cv, ctx->dinv, ctx->ll, ctx->ld, ctx->lmask, ctx->d_sc);
         KCHECK(); LAUNCHED(1);
-        if (o->precond == 2) { TRY(ml_setup(ctx)); TRY(launch_ml_chain(ctx, ctx->p, nullptr, nullptr, 1)); LAUNCHED(1 + ctx->ml.nlev); }
+        if (o->precond == 2) { TRY(ml_setup(ctx)); TRY(launch_ml_chain(ctx, ctx->p, nullptr, nullptr, 1)); LAUNCHED(1 + ctx->ml.nagg); }
         else { TRY(launch_line_solve(ctx, ctx->p, nullptr, nullptr, 1)); LAUNCHED(1); }
     }
     // r0 = M (f - A x)
@@ -1856,8 +1886,8 @@ extern "C" int pfem_apply_precond(pfem_ctx* ctx, const pfem_opts* o, const doubl
             TRY(ensure_ml(ctx));
             TRY(ml_setup(ctx));
             TRY(launch_ml_chain(ctx, ctx->p, nullptr, nullptr, 2));
-            k_ml_prolong_add<<<dim3((unsigned)((g.nI + 127) / 128), g.nJ, g.nK), 128, 0, ctx->stream>>>(g, ctx->lz, ctx->ml.z[1], ctx->ml.dom[1].nJ, ctx->q);
-            KCHECK(); LAUNCHED(3 + ctx->ml.nlev);
+            k_ml_prolong_add<<<dim3((unsigned)((g.nI + 127) / 128), g.nJ, g.nK), 128, 0, ctx->stream>>>(g, ctx->lz, ml_coarse_add(ctx), ctx->q);
+            KCHECK(); LAUNCHED(2 + ctx->ml.nagg);
         } else {
             TRY(launch_line_solve(ctx, ctx->p, nullptr, nullptr, 1));
             CU(cudaMemcpyAsync(ctx->q, ctx->lz, (size_t)g.NP * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));

@@ -20,7 +20,8 @@ for order in orders:
     f.set_dirichlet(p.bc_nodes, p.bc_values)
     f.set_source(p.heat)
     f.update_conductivity_thermal()
-    for pre in (0, 1, 2) if order == "012" else (0, 1):
+    pres = [int(a) for a in os.environ["PRE"].split(",")] if os.environ.get("PRE") else ((0, 1, 2) if order == "012" else (0, 1))
+    for pre in pres:
         f.bench_pcg(20, precond=pre)
         a = f.bench_pcg(200, precond=pre)
         b = f.bench_pcg(100, split_timing=True, precond=pre)

@@ -113,34 +113,54 @@ def pinned_copy(a):
 
 # ----------------------------------------------------------------------------------- CPU arm
 
-def cpu_pcg_sample(n_sample, iters, want_ref=True):
-    """The reference's CPU iterative path on a bounded sample: assemble config B at n_sample^3 the
-    way setMatrix does (therm3d.cpp:170-279) and run NSPCG cg+ic (PLaSK default,
-    iterative_matrix.hpp:50,73) for `iters` iterations; falls back to the oracle's Jacobi-PCG port."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from helpers import oracle_thermal
-    from oracle import oracle as orc
-    p = workload(n_sample)
-    use_ref = want_ref and orc.ref_available()
-    o = oracle_thermal(p, algorithm="iterative" if use_ref else "pcg")
-    A = orc.Sparse14(o.mesh)
-    B = np.zeros(o.mesh.N)
-    t0 = time.perf_counter()
-    o.set_matrix(A, B)
-    t_asm = time.perf_counter() - t0
-    X = o.temperatures.copy()
-    t0 = time.perf_counter()
-    if use_ref:
-        info = A.solve_nspcg(B, X, precond="ic", accel="cg", maxit=iters, maxerr=1e-30)
-    else:
-        info = A.solve_pcg(B, X, maxit=iters, tol=1e-30)
-    t_solve = time.perf_counter() - t0
-    done = max(int(info["iters"]), 1)
-    return dict(N=o.mesh.N, iters=done, t_solve=t_solve, t_assembly=t_asm, kind="reference" if use_ref else "port",
-                value=o.mesh.N * done / t_solve,
-                sample=f"config B at {n_sample}^3 ({o.mesh.N} DOF), assembly {t_asm:.2f} s + "
-                       f"{'NSPCG cg+ic (oracle/_ref)' if use_ref else 'oracle Jacobi-PCG port'} x {done} iterations "
-                       f"in {t_solve:.2f} s, 1 thread (NSPCG is serial by construction)")
+class CpuArm:
+    """The reference's CPU iterative path on the bench workload itself (config B at n^3, 256^3 by default): the matrix is
+    assembled once the way setMatrix does (therm3d.cpp:170-279) — inputs resident, like the GPU arm — and every step runs
+    a BOUNDED number of NSPCG iterations (cg + ic, PLaSK's default, iterative_matrix.hpp:50,73; or cg + jac, the same
+    iteration the GPU metric counts) from the same initial field.  Falls back to the oracle's Jacobi-PCG port when
+    oracle/_ref (the reference's own NSPCG) is absent.  One thread: NSPCG and the assembly are serial by construction."""
+
+    def __init__(self, n, want_ref=True, problem=None):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from helpers import oracle_thermal
+        from oracle import oracle as orc
+        self.p = problem if problem is not None else workload(n)
+        self.n = n
+        self.use_ref = want_ref and orc.ref_available()
+        self.o = oracle_thermal(self.p, algorithm="iterative" if self.use_ref else "pcg")
+        self.A = {}
+        self.orc = orc
+        t0 = time.perf_counter()
+        self.A0 = orc.Sparse14(self.o.mesh)
+        self.B = np.zeros(self.o.mesh.N)
+        self.o.set_matrix(self.A0, self.B)
+        self.t_assembly = time.perf_counter() - t0
+        self.N = self.o.mesh.N
+
+    def step(self, iters, precond="ic"):
+        X = self.o.temperatures.copy()
+        if precond not in self.A:           # one matrix object (and NSPCG workspace / factorisation state) per preconditioner
+            A = self.orc.Sparse14(self.o.mesh)
+            A.data[:] = self.A0.data
+            self.A[precond] = A
+        A = self.A[precond]
+        t0 = time.perf_counter()
+        if self.use_ref:
+            info = A.solve_nspcg(self.B, X, precond=precond, accel="cg", maxit=iters, maxerr=1e-30)
+        else:
+            info = A.solve_pcg(self.B, X, maxit=iters, tol=1e-30)
+        dt = time.perf_counter() - t0
+        done = max(int(info["iters"]), 1)
+        return dict(N=self.N, iters=done, t_solve=dt, value=self.N * done / dt)
+
+    def describe(self, r, precond="ic"):
+        kind = f"NSPCG cg+{precond} (oracle/_ref)" if self.use_ref else "oracle Jacobi-PCG port"
+        return (f"config B at {self.n}^3 ({self.N} DOF) — the bench workload itself, matrix assembled once ({self.t_assembly:.1f} s, "
+                f"not timed), {kind} x {r['iters']} iterations per step in {r['t_solve']:.2f} s, 1 thread (NSPCG is serial by construction)")
+
+    @property
+    def kind(self):
+        return "reference" if self.use_ref else "port"
 
 
 def cpu_tts_sample(n_sample):
@@ -178,24 +198,54 @@ def gpu_tts_sample(n_sample, device, precond):
     return out
 
 
+def recorded_full_size_cpu():
+    """Full-size CPU reference runs recorded in the build container by tests/golden/make_golden_full.py (profiles/r02_cpu_full_*.jsonl):
+    too long to repeat inside a bench run (43 min for config B at 256^3)."""
+    out = {}
+    for tag, fn in (("config_B_256_defaults", "r02_cpu_full_B_256_default.jsonl"), ("config_B_256_tight", "r02_cpu_full_B_256.jsonl"),
+                    ("config_C_4_loops_tight", "r02_cpu_full_C_192x192x400.jsonl")):
+        path = os.path.join(ROOT, "profiles", fn)
+        if not os.path.exists(path):
+            continue
+        try:
+            recs = [json.loads(l) for l in open(path) if l.strip()]
+            done = [r for r in recs if r.get("done")]
+            if done:
+                d = done[-1]
+                out[tag] = {k: d[k] for k in ("loops", "total_iters", "total_s", "assembly_s", "solve_s", "N", "cores", "cpu") if k in d}
+                out[tag]["source"] = "profiles/" + fn
+        except Exception:
+            pass
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
+    arm = CpuArm(args.n)
+    vals, jac = [], None
     for s in range(args.warmup + args.steps):
-        r = cpu_pcg_sample(args.cpu_n, args.cpu_iters)
+        r = arm.step(args.cpu_iters, "ic")
         if s >= args.warmup:
             vals.append(r)
+    if arm.use_ref:   # like-for-like iterations: the Jacobi-preconditioned CG the GPU metric counts (one bounded step)
+        jac = arm.step(args.cpu_iters, "jac")
+        jac = arm.step(args.cpu_iters, "jac")
     t = sum(v["t_solve"] for v in vals)
     value = sum(v["N"] * v["iters"] for v in vals) / t
+    cb = {"value": value, "unit": "DOF*iter/s", "cores": 1, "kind": arm.kind, "sample": arm.describe(vals[-1]), "assembly_s": arm.t_assembly}
+    if jac:
+        cb["jacobi_iterations"] = {"value": jac["value"], "unit": "DOF*iter/s", "sample": arm.describe(jac, "jac")}
+    cb["recorded_full_size_runs"] = recorded_full_size_cpu()
     line = {
         "impl": "reference", "metric": "pcg_dof_iter_per_s", "value": value, "unit": "DOF*iter/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(vals), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"Static3D config B (VCSEL-like, k(T)), bounded CPU sample at {args.cpu_n}^3 of the 256^3 case",
-                   "iters_per_step": vals[-1]["iters"]},
-        "cpu_baseline": {"value": value, "unit": "DOF*iter/s", "cores": 1, "kind": vals[-1]["kind"], "sample": vals[-1]["sample"]},
+        "config": {"workload": f"Static3D config B: {args.n}^3 VCSEL-like layered block, nonlinear k(T) tables, {arm.N} DOF, "
+                               f"CG + IC(0) (the reference's default), bounded to {vals[-1]['iters']} iterations per step",
+                   "iters_per_step": vals[-1]["iters"], "same_config_as_gpu_arm": True},
+        "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "DOF*iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -382,32 +432,44 @@ def run_ours(args):
         except Exception as ex:  # keep the bench line even if the long solve fails
             tts = {"error": str(ex)}
         s.invalidate()
-        # the same solve with the line-Jacobi preconditioner (two kernels per iteration)
-        if "error" not in tts:
-            s2 = Static3D("bench-ljac")
+        # the same solve with the line-Jacobi preconditioner (two kernels per iteration) and — one GPU — with the multilevel
+        # line preconditioner (the counterpart of the strength of the reference's default IC(0))
+        for key, pre in (("line_jacobi", "ljac"), ("multilevel", "mlj")):
+            if "error" in tts or (pre == "mlj" and slab):
+                continue
+            s2 = Static3D("bench-" + pre)
             s2.device = local
             s2.problem = p
             if slab:
                 s2.slab = dict(rank=rank, nranks=world, own_lo=slab[0], own_hi=slab[1], allgather=allgather_bytes)
-            s2.iterative.preconditioner = "ljac"
+            s2.iterative.preconditioner = pre
             s2.iterative.maxerr = args.lin_tol
             s2.iterative.maxit = args.tts_maxit
             t0 = time.perf_counter()
             try:
                 s2.compute(args.tts_loops)
                 st_ = s2.stats
-                tts["line_jacobi"] = {"seconds": time.perf_counter() - t0, "outer_loops": st_["outer_loops"],
-                                      "pcg_iterations": st_["lin_iters"], "converged": st_["converged"],
-                                      "lin_relres": st_["lin_relres"], "maxT": st_["maxval"], "device_ms": st_["t_solve_ms"]}
+                tts[key] = {"seconds": time.perf_counter() - t0, "outer_loops": st_["outer_loops"],
+                            "pcg_iterations": st_["lin_iters"], "converged": st_["converged"],
+                            "lin_relres": st_["lin_relres"], "maxT": st_["maxval"], "device_ms": st_["t_solve_ms"]}
             except Exception as ex:
-                tts["line_jacobi"] = {"error": str(ex)}
+                tts[key] = {"error": str(ex)}
             s2.invalidate()
+        rec = recorded_full_size_cpu().get("config_B_256_defaults")
+        if rec and n == 256 and world == 1 and "error" not in tts:
+            best = min(v["seconds"] for v in (tts, tts.get("line_jacobi", {}), tts.get("multilevel", {})) if "seconds" in v)
+            tts["cpu_reference_recorded"] = dict(rec, note="the reference's CPU path (assembly + NSPCG cg+ic with PLaSK's default tolerances, "
+                                                 "1 thread) on this very mesh, recorded once in the build container; the CUDA path solves every "
+                                                 "loop to a 100x tighter tolerance", speedup_best_gpu=rec["total_s"] / best)
 
     cpu = None
     if rank == 0 and world == 1 and args.cpu_baseline:
-        c = cpu_pcg_sample(args.cpu_n, args.cpu_iters)
-        cpu = {"value": c["value"], "unit": "DOF*iter/s", "cores": 1, "kind": c["kind"], "sample": c["sample"],
-               "assembly_s": c["t_assembly"]}
+        arm = CpuArm(args.n, problem=p)
+        arm.step(args.cpu_iters, "ic")          # first call: IC factorisation + workspace
+        c = arm.step(args.cpu_iters, "ic")
+        cpu = {"value": c["value"], "unit": "DOF*iter/s", "cores": 1, "kind": arm.kind, "sample": arm.describe(c),
+               "assembly_s": arm.t_assembly, "recorded_full_size_runs": recorded_full_size_cpu()}
+        del arm
         if args.cpu_tts_n > 0:
             # apples to apples: the SAME nonlinear solve (config B at a bounded size) to convergence on both sides, each
             # with its own defaults — DOF*iter/s alone compares iterations of different preconditioners
@@ -415,10 +477,12 @@ def run_ours(args):
             if ct is not None:
                 gj = gpu_tts_sample(args.cpu_tts_n, local, "jac")
                 gl = gpu_tts_sample(args.cpu_tts_n, local, "ljac")
+                gm = gpu_tts_sample(args.cpu_tts_n, local, "mlj")
                 cpu["time_to_solution_sample"] = {
                     "workload": f"config B at {args.cpu_tts_n}^3 ({ct['dof']} DOF), full nonlinear Static3D solve",
-                    "cpu_reference": ct, "gpu_jacobi": gj, "gpu_line_jacobi": gl,
-                    "speedup_vs_cpu": {"jacobi": ct["seconds"] / gj["seconds"], "line_jacobi": ct["seconds"] / gl["seconds"]},
+                    "cpu_reference": ct, "gpu_jacobi": gj, "gpu_line_jacobi": gl, "gpu_multilevel": gm,
+                    "speedup_vs_cpu": {"jacobi": ct["seconds"] / gj["seconds"], "line_jacobi": ct["seconds"] / gl["seconds"],
+                                       "multilevel": ct["seconds"] / gm["seconds"]},
                     "maxT_difference_K": abs(ct["maxT"] - gl["maxT"]),
                     "note": "the reference runs with its default tolerances (NSPCG stop test #2 at 1e-6, loops until the update is "
                             "below 0.05 K) and so stops a loop earlier than the CUDA path solving every loop to 1e-8; the parity "
@@ -455,8 +519,7 @@ def main():
     ap.add_argument("--n", type=int, default=256, help="nodes per axis of config B")
     ap.add_argument("--iters", type=int, default=500, help="PCG iterations per step")
     ap.add_argument("--variant", type=int, default=3, help="3 fused single-kernel iteration (production), 0/2 two-kernel, 1 simple")
-    ap.add_argument("--cpu-n", type=int, default=96)
-    ap.add_argument("--cpu-iters", type=int, default=40)
+    ap.add_argument("--cpu-iters", type=int, default=6, help="NSPCG iterations per CPU step (the CPU arm runs the bench mesh itself)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-tts-n", type=int, default=96, help="size of the full CPU-vs-GPU time-to-solution sample (0 = skip)")
     ap.add_argument("--no-tts", dest="tts", action="store_false")

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_json_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--cpu-n", "20", "--cpu-iters", "5"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                        "--n", "20", "--cpu-iters", "5"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -19,7 +19,8 @@ def test_reference_arm_json_line():
     assert d["higher_is_better"] is True and d["dtype"] == "f64" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"] and "model" not in d["config"]
+    assert "workload" in d["config"] and "model" not in d["config"] and d["config"]["same_config_as_gpu_arm"] is True
+    assert d["cpu_baseline"]["jacobi_iterations"]["value"] > 0
 
 
 def test_gpu_arm_refuses_without_device():

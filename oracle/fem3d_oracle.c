@@ -415,12 +415,15 @@ void orc_apply_bc_dpb(size_t rank, size_t kd, size_t ld, double* AB, double* B, 
 size_t orc_boundary_terms(const orc_mesh* m, const double* T, const uint8_t* has_flux, const double* flux,
                           const uint8_t* has_conv, const double* conv_coeff, const double* conv_amb,
                           const uint8_t* has_rad, const double* rad_emis, const double* rad_amb, int quirk,
-                          size_t cap, size_t* rows, size_t* cols, double* vals, double* B) {
+                          size_t cap, size_t* rows, size_t* cols, double* vals, double* B, const uint8_t* included) {
     static const int walls[6][4] = {{0, 1, 2, 3}, {4, 5, 6, 7}, {0, 2, 4, 6}, {1, 3, 5, 7}, {0, 1, 4, 5}, {2, 3, 6, 7}};
     const double SB = 5.670373e-8; /* plask/phys/constants.hpp:41 */
     size_t E = orc_mesh_elements(m), nt = 0;
     for (size_t e = 0; e < E; ++e) {
         size_t ix[3], idx[8];
+        /* the loop is `for (auto elem : this->maskedMesh->elements())`, therm3d.cpp:186: elements outside the masked mesh
+         * (empty-elements="exclude") add nothing */
+        if (included && !included[e]) continue;
         elem_indices(m, e, ix);
         elem_nodes(m, ix, idx);
         double dx = m->ax[0][ix[0] + 1] - m->ax[0][ix[0]];

@@ -277,10 +277,16 @@ class DpbMasked:
         B[self.active] = self.Bm
 
     def add_coo(self, rows, cols, vals):
-        raise NotImplementedError("boundary terms on a masked mesh")
+        """convection terms of the kept elements (their nodes all belong to the masked mesh)"""
+        none = np.uintp(np.iinfo(np.uintp).max)
+        mr = np.ascontiguousarray(self.nodemap[np.asarray(rows, dtype=np.int64)], dtype=np.uintp)
+        mc = np.ascontiguousarray(self.nodemap[np.asarray(cols, dtype=np.int64)], dtype=np.uintp)
+        assert not (mr == none).any() and not (mc == none).any()
+        lib().orc_add_coo_dpb(c_sz(self.ld), _p(self.data), c_sz(len(vals)), _p(mr, c_sz), _p(mc, c_sz), _p(np.ascontiguousarray(vals)))
 
     def apply_bc(self, B, nodes, values):
         """boundary conditions live on the masked mesh: places outside it hold no nodes"""
+        self.Bm[:] = B[self.active]      # load terms added to B since assemble() (heat flux, convection, radiation)
         mn = self.nodemap[np.asarray(nodes, dtype=np.int64)]
         keep = mn != np.uintp(np.iinfo(np.uintp).max)
         mn = np.ascontiguousarray(mn[keep], dtype=np.uintp)
@@ -329,7 +335,7 @@ class BoundaryTerms:
         self.has_conv, (self.coeff, self.camb) = dense(list(convection), 2)
         self.has_rad, (self.emis, self.ramb) = dense(list(radiation), 2)
 
-    def terms(self, mesh, T, B, quirk):
+    def terms(self, mesh, T, B, quirk, included=None):
         """setBoundaries for every element (therm3d.cpp:140-168,242-268): adds the load terms to B, returns COO triplets."""
         def pu(a):
             return _p(a, C.c_uint8) if a is not None else None
@@ -341,7 +347,7 @@ class BoundaryTerms:
             nt = lib().orc_boundary_terms(mesh.ref, _p(np.ascontiguousarray(T)), pu(self.has_flux), _p(self.flux),
                                           pu(self.has_conv), _p(self.coeff), _p(self.camb), pu(self.has_rad),
                                           _p(self.emis), _p(self.ramb), C.c_int(1 if quirk else 0), c_sz(cap),
-                                          _p(rows, c_sz), _p(cols, c_sz), _p(vals), _p(B0))
+                                          _p(rows, c_sz), _p(cols, c_sz), _p(vals), _p(B0), pu(included))
             if nt <= cap:
                 B[:] = B0
                 return rows[:nt].copy(), cols[:nt].copy(), vals[:nt].copy()
@@ -394,7 +400,7 @@ class Static3DOracle:
             self.conds[self.included == 0] = 0.
         A.assemble(self.conds, self.heat if self.heat is not None else np.zeros(self.mesh.E), B)
         if self.boundaries is not None:
-            rows, cols, vals = self.boundaries.terms(self.mesh, self.temperatures, B, self.quirk)
+            rows, cols, vals = self.boundaries.terms(self.mesh, self.temperatures, B, self.quirk, self.included)
             A.add_coo(rows, cols, vals)
         A.apply_bc(B, self.bc_nodes, self.bc_values)
 
@@ -634,14 +640,33 @@ class ThermoElectric3DOracle:
 
     def exchange_temperature(self):
         t, e = self.thermal, self.electrical
-        e.Te = interp_linear(t.mesh.axes, t.mesh.ns, t.temperatures, [midpoints(a) for a in e.mesh.axes], e.mesh.es, e.mesh.E)
+        mids = [midpoints(a) for a in e.mesh.axes]
+        e.Te = interp_linear(t.mesh.axes, t.mesh.ns, t.temperatures, mids, e.mesh.es, e.mesh.E)
+        if t.included is not None:
+            # thermal solver on a masked mesh: interpolate(maskedMesh, ...) is NaN outside the kept elements and
+            # SafeData<double>(..., 300.) substitutes 300 K (getTemperatures, therm3d.cpp:391-392)
+            idx, inside = [], []
+            for a in range(3):
+                ax = t.mesh.axes[a]
+                up = np.searchsorted(ax, mids[a], side="right")
+                inside.append((up > 0) & (up < len(ax)))
+                idx.append(np.clip(up - 1, 0, len(ax) - 2))
+            te = idx[0][:, None, None] * t.mesh.es[0] + idx[1][None, :, None] * t.mesh.es[1] + idx[2][None, None, :] * t.mesh.es[2]
+            ok = inside[0][:, None, None] & inside[1][None, :, None] & inside[2][None, None, :] & (t.included[te] != 0)
+            ee = e.mesh.elems_grid()
+            e.Te[ee[~ok]] = 300.
 
     def exchange_heat(self):
         t, e = self.thermal, self.electrical
         e.heat = None
         heat = e.heat_density()
-        t.heat = interp_linear([midpoints(a) for a in e.mesh.axes], e.mesh.es, heat, [midpoints(a) for a in t.mesh.axes],
-                               t.mesh.es, t.mesh.E)
+        mids = [midpoints(a) for a in t.mesh.axes]
+        t.heat = interp_linear([midpoints(a) for a in e.mesh.axes], e.mesh.es, heat, mids, t.mesh.es, t.mesh.E)
+        # getHeatDensity returns 0 outside the bounding box of the electrical geometry (electr3d.cpp:545-548; bounds included);
+        # the box is taken as the extent of the electrical mesh
+        ins = [(m >= e.mesh.axes[a][0]) & (m <= e.mesh.axes[a][-1]) for a, m in enumerate(mids)]
+        ok = ins[0][:, None, None] & ins[1][None, :, None] & ins[2][None, None, :]
+        t.heat[t.mesh.elems_grid()[~ok]] = 0.
 
     def compute(self, max_meta_loops=100):
         t, e = self.thermal, self.electrical

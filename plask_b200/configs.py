@@ -366,6 +366,39 @@ def setup_active(p):
     return acts, tot
 
 
+# ------------------------------------------------------------------- layer thickness (a2)
+
+def layer_thickness(p, key):
+    """ThermalFem3DSolver::onInitialize (therm3d.cpp:81-114): thickness[e] = height of the maximal run of vertically
+    adjacent elements of the same material that contains e.  `key`: material identity per element, [E] in element order
+    (the plugin compares shared_ptr<Material> with operator==, material.hpp:836-872).  Returns [E] in element order."""
+    n = p.n
+    ne = tuple(k - 1 for k in n)
+    eg = np.broadcast_to(p.elem_index_grid(), ne)
+    k3 = np.asarray(key)[eg]                                    # (n0-1, n1-1, n2-1)
+    hz = np.diff(np.asarray(p.axes[2], dtype=np.float64))
+    brk = np.ones(ne, dtype=bool)                               # True where a new run starts
+    brk[:, :, 1:] = k3[:, :, 1:] != k3[:, :, :-1]
+    run = np.cumsum(brk, axis=2) - 1                            # run number of every element inside its column
+    nrun = int(run.max()) + 1
+    th = np.zeros(ne[:2] + (nrun,))
+    i0, i1 = np.meshgrid(np.arange(ne[0]), np.arange(ne[1]), indexing="ij")
+    for r in range(ne[2]):                                      # sum the element heights per (column, run)
+        np.add.at(th, (i0, i1, run[:, :, r]), hz[r])
+    t3 = np.take_along_axis(th, run, axis=2)
+    return p.to_elem_order(t3, np.float64)
+
+
+def thickness_material_ids(key, thickness):
+    """One table id per distinct (material, layer thickness) pair, so that thermk(T, thickness) can be tabulated per id
+    (pfem_set_materials).  Returns (ids [E] uint32, list of (material key, thickness) per id) — the Python twin of
+    plaskfem::material_ids (include/plaskfem_cuda.hpp)."""
+    key = np.asarray(key)
+    pairs = np.stack([key.astype(np.float64), np.asarray(thickness, dtype=np.float64)], axis=1)
+    uniq, inv = np.unique(pairs, axis=0, return_inverse=True)
+    return inv.astype(np.uint32).ravel(), [(int(a), float(b)) for a, b in uniq]
+
+
 # ------------------------------------------------------------------------- slab partition
 
 def slab_range(nK, rank, nranks):

@@ -673,14 +673,41 @@ struct InterpAxis {
     const int *ilo, *ihi;
     const double *lo, *hi, *pt;
 };
+// What the providers do with points the plain interpolation does not cover:
+//   bbox     getHeatDensity returns 0 outside the bounding box of the source geometry (electr3d.cpp:545-548); the box is
+//            taken as the extent of the source node axes (bb[2a], bb[2a+1]), bounds included like Box3D::contains
+//   src_mat  source on a masked mesh: interpolate(maskedMesh, ...) yields NaN outside the kept elements and SafeData
+//            substitutes `fill` (getTemperatures, therm3d.cpp:391-392: 300 K); src_mat = material ids on the source lattice
+struct InterpOutside {
+    int bbox;
+    double bb[6];
+    const uint32_t* src_mat;
+    double fill;
+};
 __global__ void k_interp_to_elems(const Grid gd, const idx_t ss0, const idx_t ss1, const idx_t ss2,
                                   const double* __restrict__ src, const InterpAxis a0, const InterpAxis a1,
-                                  const InterpAxis a2, double* __restrict__ dst) {
+                                  const InterpAxis a2, double* __restrict__ dst, const InterpOutside out) {
     const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
     const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
     const int k = blockIdx.z;
     int pi[3];
     if (!elem_slot(gd, i, j, k, pi)) return;
+    if (out.bbox) {
+        const double q0 = a0.pt[pi[0]], q1 = a1.pt[pi[1]], q2 = a2.pt[pi[2]];
+        if (!(q0 >= out.bb[0] && q0 <= out.bb[1] && q1 >= out.bb[2] && q1 <= out.bb[3] && q2 >= out.bb[4] && q2 <= out.bb[5])) {
+            dst[i + gd.sJ * j + gd.sK * k] = 0.;
+            return;
+        }
+    }
+    if (out.src_mat) {
+        // the source element that holds the point: lo index on every axis, none when the point is outside the source axes
+        const int e0 = a0.ilo[pi[0]], e1 = a1.ilo[pi[1]], e2 = a2.ilo[pi[2]];
+        const bool inside = e0 != a0.ihi[pi[0]] && e1 != a1.ihi[pi[1]] && e2 != a2.ihi[pi[2]];
+        if (!inside || out.src_mat[e0 * ss0 + e1 * ss1 + e2 * ss2] == PFEM_MAT_EXCLUDED) {
+            dst[i + gd.sJ * j + gd.sK * k] = out.fill;
+            return;
+        }
+    }
     const idx_t l0 = a0.ilo[pi[0]] * ss0, h0 = a0.ihi[pi[0]] * ss0;
     const idx_t l1 = a1.ilo[pi[1]] * ss1, h1 = a1.ihi[pi[1]] * ss1;
     const idx_t l2 = a2.ilo[pi[2]] * ss2, h2 = a2.ihi[pi[2]] * ss2;

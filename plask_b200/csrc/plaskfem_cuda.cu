@@ -43,6 +43,7 @@ struct pfem_ctx {
     uint8_t* fixed = nullptr;
     idx_t* bc_node = nullptr;   // de-duplicated Dirichlet nodes (device lattice indices) and values
     double* bc_val = nullptr;
+    double* bc_val_first = nullptr;   // value of the FIRST condition naming each node; null unless some node is named with different values
     size_t nbc = 0;
     // element arrays on the node lattice
     double *cl = nullptr, *cv = nullptr, *Te = nullptr, *cur0 = nullptr, *cur1 = nullptr, *cur2 = nullptr;
@@ -50,6 +51,7 @@ struct pfem_ctx {
     uint32_t *mat = nullptr, *junc = nullptr;
     uint8_t *role = nullptr, *noheat = nullptr;
     uint8_t* inactive = nullptr;   // masked mesh: nodes that touch no kept element (null unless elements are excluded)
+    std::vector<uint8_t> h_excluded;   // host copy: element (ABI order) is outside the masked mesh (empty unless elements are excluded)
     bool has_excluded = false, source_set = false;
     // small arrays
     double* hbuf = nullptr;
@@ -171,10 +173,10 @@ static void free_all(pfem_ctx* ctx) {
     ctx->allocs.clear();
     // every pointer below came from dev_alloc: a later pfem_set_mesh must not see stale addresses
     ctx->x = ctx->xprev = ctx->r = ctx->r2 = ctx->p = ctx->p2 = ctx->q = ctx->q2 = ctx->dinv = ctx->f = nullptr;
-    ctx->fixed = nullptr; ctx->bc_node = nullptr; ctx->bc_val = nullptr; ctx->nbc = 0;
+    ctx->fixed = nullptr; ctx->bc_node = nullptr; ctx->bc_val = nullptr; ctx->bc_val_first = nullptr; ctx->nbc = 0;
     ctx->cl = ctx->cv = ctx->Te = ctx->cur0 = ctx->cur1 = ctx->cur2 = ctx->aux0 = ctx->aux1 = ctx->aux2 = nullptr;
     ctx->mat = ctx->junc = nullptr; ctx->role = ctx->noheat = nullptr;
-    ctx->inactive = nullptr; ctx->has_excluded = false; ctx->source_set = false;
+    ctx->inactive = nullptr; ctx->has_excluded = false; ctx->source_set = false; ctx->h_excluded.clear();
     ctx->hbuf = ctx->tab_lat = ctx->tab_vert = nullptr;
     ctx->act = nullptr; ctx->nact = 0; ctx->ncol = 0;
     ctx->junc_cond = ctx->beta_col = ctx->js_col = nullptr;
@@ -471,6 +473,7 @@ extern "C" int pfem_set_mesh(pfem_ctx* ctx, const size_t n[3], const double* ax0
     ctx->nbc = 0;
     ctx->bc_node = nullptr;
     ctx->bc_val = nullptr;
+    ctx->bc_val_first = nullptr;
     ctx->have_mesh = true;
     CU(cudaStreamSynchronize(ctx->stream));
     return PFEM_OK;
@@ -516,6 +519,13 @@ extern "C" int pfem_set_materials(pfem_ctx* ctx, const uint32_t* elem_mat, uint3
     }
     if (excluded && ctx->source_set)
         FAIL(PFEM_ERR_STATE, "elements are excluded: call pfem_set_materials before pfem_set_source");
+    if (excluded != ctx->has_excluded && ctx->surf.nrows)
+        FAIL(PFEM_ERR_STATE, "the masked mesh changed: call pfem_set_materials before pfem_set_boundary (boundary terms exist on kept elements only)");
+    ctx->h_excluded.clear();
+    if (excluded) {
+        ctx->h_excluded.resize((size_t)ctx->g.E);
+        for (idx_t e = 0; e < ctx->g.E; ++e) ctx->h_excluded[(size_t)e] = elem_mat[e] == PFEM_MAT_EXCLUDED;
+    }
     TRY(upload_elem<uint32_t, 1>(ctx, elem_mat, ctx->mat, nullptr, nullptr));
     ctx->has_excluded = excluded;
     if (excluded) {   // masked mesh: mark the nodes that touch no kept element
@@ -538,11 +548,11 @@ extern "C" int pfem_set_materials(pfem_ctx* ctx, const uint32_t* elem_mat, uint3
 }
 
 // x[node] = value and/or fixed[node] = 1 for the stored Dirichlet list
-static int scatter_bc(pfem_ctx* ctx, double* x, uint8_t* fixed) {
+static int scatter_bc(pfem_ctx* ctx, double* x, uint8_t* fixed, bool first = false) {
     if (!ctx->nbc) return PFEM_OK;
     int blocks = (int)((ctx->nbc + 255) / 256);
     if (blocks > 4096) blocks = 4096;
-    k_scatter_dirichlet<<<blocks, 256, 0, ctx->stream>>>(ctx->nbc, ctx->bc_node, ctx->bc_val, x, fixed);
+    k_scatter_dirichlet<<<blocks, 256, 0, ctx->stream>>>(ctx->nbc, ctx->bc_node, (first && ctx->bc_val_first) ? ctx->bc_val_first : ctx->bc_val, x, fixed);
     KCHECK(); LAUNCHED(1);
     return PFEM_OK;
 }
@@ -551,11 +561,13 @@ extern "C" int pfem_set_dirichlet(pfem_ctx* ctx, size_t nd, const size_t* node, 
     NEED_MESH();
     const Grid& g = ctx->g;
     if (nd && (!node || !value)) FAIL(PFEM_ERR_BAD_INPUT, "null Dirichlet argument");
-    // De-duplicate keeping the LAST value per node: B[r] = val of the last condition that names
-    // r (iterative_matrix.hpp:462-464).
+    // De-duplicate.  setBC (iterative_matrix.hpp:462-485) handles the conditions one by one: the FIRST one that names node r
+    // lifts its value into the neighbours' right-hand sides and clears the couplings, every later one only overwrites B[r].
+    // So the free rows see the first value, the node itself ends with the last one; both are kept.
     std::vector<idx_t> nn;
-    std::vector<double> vv;
-    nn.reserve(nd); vv.reserve(nd);
+    std::vector<double> vv, vfirst;
+    bool conflict = false;
+    nn.reserve(nd); vv.reserve(nd); vfirst.reserve(nd);
     {
         std::vector<long long> last;  // node -> position, lazily via sort-free map for big meshes
         std::vector<std::pair<idx_t, size_t>> order(nd);
@@ -565,10 +577,14 @@ extern "C" int pfem_set_dirichlet(pfem_ctx* ctx, size_t nd, const size_t* node, 
             order[m] = {abi_to_lattice(ctx, (idx_t)node[m]), m};   // ABI index (dense rows) -> pitched lattice index
         }
         std::sort(order.begin(), order.end());
+        size_t run0 = 0;
         for (size_t m = 0; m < nd; ++m) {
+            if (m > 0 && order[m].first != order[m - 1].first) run0 = m;
             if (m + 1 < nd && order[m + 1].first == order[m].first) continue;  // keep the last occurrence
             nn.push_back(order[m].first);
             vv.push_back(value[order[m].second]);
+            vfirst.push_back(value[order[run0].second]);
+            if (vfirst.back() != vv.back()) conflict = true;
         }
     }
     // The values are NOT written into the field here: like the reference (applyBC works on the
@@ -578,6 +594,11 @@ extern "C" int pfem_set_dirichlet(pfem_ctx* ctx, size_t nd, const size_t* node, 
     ctx->nbc = nn.size();
     dev_release(ctx, &ctx->bc_node);
     dev_release(ctx, &ctx->bc_val);
+    dev_release(ctx, &ctx->bc_val_first);
+    if (conflict) {
+        TRY(dev_alloc(ctx, &ctx->bc_val_first, nn.size(), 0));
+        CU(cudaMemcpyAsync(ctx->bc_val_first, vfirst.data(), vfirst.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
     if (!nn.empty()) {
         TRY(dev_alloc(ctx, &ctx->bc_node, nn.size(), 0));
         TRY(dev_alloc(ctx, &ctx->bc_val, nn.size(), 0));
@@ -694,6 +715,13 @@ extern "C" int pfem_set_boundary(pfem_ctx* ctx, const pfem_boundary* b) {
                 }
                 if (!any) continue;
                 const idx_t ix[3] = {ei, ej, ek};
+                if (!ctx->h_excluded.empty()) {
+                    // setBoundaries runs inside `for (elem : maskedMesh->elements())` (therm3d.cpp:186-268): an element outside
+                    // the masked mesh adds nothing, even if all four nodes of one of its sides carry a condition
+                    idx_t e = 0;
+                    for (int a = 0; a < 3; ++a) e += g.es[a] * ix[g.dim_of_phys[a]];
+                    if (ctx->h_excluded[(size_t)e]) continue;
+                }
                 double d[3];
                 for (int a = 0; a < 3; ++a) { const idx_t t = ix[g.dim_of_phys[a]]; d[a] = ctx->hax[a][t + 1] - ctx->hax[a][t]; }
                 const double areas[3] = {d[0] * d[1], d[1] * d[2], d[2] * d[0]};
@@ -881,6 +909,22 @@ extern "C" int pfem_set_junctions(pfem_ctx* ctx, uint32_t njunc, const pfem_junc
         }
     }
     if (need > ncol) FAIL(PFEM_ERR_BAD_INPUT, "junction table too short: need %zu entries, got %zu", need, ncol);
+    if (njunc) {
+        // every element of junction k addresses table entry offset + ld * i1 + i0 (electr3d.cpp:213-215,250): it must exist,
+        // also for elements outside [back,front) x [left,right) (setupActiveRegions does not widen the region for the
+        // column that creates it, electr3d.cpp:120-135)
+        int ord[3] = {0, 1, 2};
+        std::sort(ord, ord + 3, [&](int a, int b) { return g.es[a] > g.es[b]; });   // major, medium, minor element axis
+        for (idx_t e = 0; e < g.E; ++e) {
+            if (!elem_junc[e]) continue;
+            idx_t c[3], rem = e;
+            for (int q = 0; q < 3; ++q) { c[ord[q]] = rem / g.es[ord[q]]; rem %= g.es[ord[q]]; }
+            const pfem_junction& a = junc[elem_junc[e] - 1];
+            const long long col = (long long)a.offset + (long long)a.ld * c[1] + c[0];
+            if (col < 0 || col >= (long long)ncol)
+                FAIL(PFEM_ERR_BAD_INPUT, "element %lld of junction %u addresses junction-table entry %lld outside [0, %zu)", (long long)e, elem_junc[e] - 1, col, ncol);
+        }
+    }
     ctx->nact = (int)njunc;
     ctx->ncol = ncol;
     dev_release(ctx, &ctx->act);
@@ -1392,7 +1436,7 @@ static int pcg_prepare(pfem_ctx* ctx, const pfem_opts* o, int bench) {
     TRY(launch_diag(ctx));
     TRY(halo_sync(ctx, SA_DINV));            // slab mode: the diagonal of a halo plane needs the neighbour's elements
     TRY(surf_eval_rad(ctx));                 // radiation load from the temperatures of the previous loop (therm3d.cpp:262-267)
-    TRY(scatter_bc(ctx, ctx->x, nullptr));   // x_D = v_D (B[r] = val, iterative_matrix.hpp:463-464)
+    TRY(scatter_bc(ctx, ctx->x, nullptr, true));   // x_D = v_D as the free rows see it (first condition per node, iterative_matrix.hpp:466-484)
     // ||b_free||^2 with b_free = M (f - A x_D): q <- x_D, p <- b_free (scratch)
     k_dirichlet_only<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->x, ctx->fixed, ctx->q);
     LAUNCHED(1);
@@ -1410,6 +1454,7 @@ static int pcg_prepare(pfem_ctx* ctx, const pfem_opts* o, int bench) {
     TRY(surf_rhs(ctx, ctx->x, &feff));
     TRY(launch_apply_simple<1>(ctx, ctx->x, ctx->r, feff));
     TRY(halo_sync(ctx, SA_R));
+    if (ctx->bc_val_first) TRY(scatter_bc(ctx, ctx->x, nullptr));   // B[r] = val of the LAST condition (:463-464); fixed rows stay put in CG
     CU(cudaMemsetAsync(ctx->p, 0, (size_t)g.NP * sizeof(double), ctx->stream));
     CU(cudaMemsetAsync(ctx->q, 0, (size_t)g.NP * sizeof(double), ctx->stream));   // fused kernel: r' = r - 0*q on the first launch
     {   // initial scalars over the OWNED planes (all planes unless this is a slab)
@@ -1681,7 +1726,7 @@ static AxisTab make_axis_tab(const std::vector<double>& src_nodes, bool src_mid,
 }
 
 // dst_arr (element lattice of dst) <- linear interpolation of src_arr (node or element lattice of src)
-static int interp_to_elems(pfem_ctx* dst, pfem_ctx* src, const double* src_arr, bool src_is_elem, double* dst_arr) {
+static int interp_to_elems(pfem_ctx* dst, pfem_ctx* src, const double* src_arr, bool src_is_elem, double* dst_arr, const InterpOutside& outside) {
     pfem_ctx* ctx = dst;
     if (src->device != dst->device) FAIL(PFEM_ERR_BAD_INPUT, "field exchange needs both contexts on the same device");
     if (src->nranks != dst->nranks || src->rank != dst->rank) FAIL(PFEM_ERR_BAD_INPUT, "field exchange needs the same slab partition on both sides");
@@ -1716,7 +1761,7 @@ static int interp_to_elems(pfem_ctx* dst, pfem_ctx* src, const double* src_arr, 
     if (e == cudaSuccess) {
         const Grid& gs = src->g;
         k_interp_to_elems<<<node_grid(dst->g), node_block(), 0, dst->stream>>>(dst->g, gs.ps[0], gs.ps[1], gs.ps[2], src_arr,
-                                                                                ia[0], ia[1], ia[2], dst_arr);
+                                                                                ia[0], ia[1], ia[2], dst_arr, outside);
         e = cudaGetLastError();
         dst->launches += 1;
     }
@@ -1789,7 +1834,13 @@ extern "C" int pfem_transfer_temperature(pfem_ctx* electrical, pfem_ctx* thermal
     if (!thermal || !thermal->have_mesh) FAIL(PFEM_ERR_STATE, "thermal context has no mesh");
     const Grid& g = ctx->g;
     if (!ctx->Te) TRY(dev_alloc(ctx, &ctx->Te, (size_t)g.NP, (size_t)g.G));
-    TRY(interp_to_elems(electrical, thermal, thermal->x, false, ctx->Te));
+    InterpOutside out;
+    memset(&out, 0, sizeof out);
+    if (thermal->has_excluded) {   // masked thermal mesh: NaN outside the kept elements -> SafeData's 300 K (therm3d.cpp:391-392)
+        out.src_mat = thermal->mat;
+        out.fill = 300.;
+    }
+    TRY(interp_to_elems(electrical, thermal, thermal->x, false, ctx->Te, out));
     ctx->conds_valid = false;
     return PFEM_OK;
 }
@@ -1813,7 +1864,11 @@ extern "C" int pfem_transfer_heat(pfem_ctx* thermal, pfem_ctx* electrical) {
     const Grid& g = ctx->g;
     TRY(ensure_elem_arrays(ctx, false));
     CU(cudaMemsetAsync(ctx->aux0 - g.G, 0, (size_t)(g.NP + 2 * g.G) * sizeof(double), ctx->stream));
-    TRY(interp_to_elems(thermal, electrical, heat, true, ctx->aux0));
+    InterpOutside out;
+    memset(&out, 0, sizeof out);
+    out.bbox = 1;                  // no heat outside the electrical solver's domain (electr3d.cpp:545-548)
+    for (int a = 0; a < 3; ++a) { out.bb[2 * a] = electrical->hax[a].front(); out.bb[2 * a + 1] = electrical->hax[a].back(); }
+    TRY(interp_to_elems(thermal, electrical, heat, true, ctx->aux0, out));
     k_load_vector<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->aux0, ctx->has_excluded ? ctx->mat : nullptr, ctx->f);
     KCHECK(); LAUNCHED(1);
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1907,11 +1962,12 @@ extern "C" int pfem_get_rhs(pfem_ctx* ctx, double* b) {
     TRY(launch_diag(ctx));
     // q <- v_D on Dirichlet nodes, 0 elsewhere; p <- M (f - A q); b = fixed ? v_D : p
     CU(cudaMemsetAsync(ctx->q, 0, (size_t)g.NP * sizeof(double), ctx->stream));
-    TRY(scatter_bc(ctx, ctx->q, nullptr));
+    TRY(scatter_bc(ctx, ctx->q, nullptr, true));   // the value the free rows see (first condition per node)
     const double* feff = nullptr;
     TRY(surf_eval_rad(ctx));
     TRY(surf_rhs(ctx, ctx->q, &feff));
     TRY(launch_apply_simple<1>(ctx, ctx->q, ctx->p, feff));
+    if (ctx->bc_val_first) TRY(scatter_bc(ctx, ctx->q, nullptr));   // B[r] = the last value
     k_select_fixed<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->fixed, ctx->q, ctx->p, ctx->p);
     KCHECK(); LAUNCHED(1);
     CU(download_nodes(ctx, b, ctx->p));

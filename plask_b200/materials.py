@@ -42,6 +42,11 @@ def thermk_Cu(T):        # materials/metals/Cu.cpp:67-70
     return _iso(400.8 * (300. / T) ** 0.073)
 
 
+def thermk_GaN(T, t):    # materials/semiconductors35/nitrides/GaN.cpp:38-44 — depends on the LAYER THICKNESS t [um]
+    fun_t = np.tanh(0.001529 * t ** 0.984) ** 0.12
+    return _iso(230. * (np.asarray(T, dtype=np.float64) / 300.) ** -1.43 * fun_t)
+
+
 def thermk_air(T):       # plask/material/air.cpp (thermk fit, ~0.025 W/mK at 300 K)
     return _iso(0.0258 * (np.asarray(T, dtype=np.float64) / 300.) ** 0.8)
 

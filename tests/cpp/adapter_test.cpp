@@ -281,7 +281,37 @@ static int gpu_tests() {
     return 0;
 }
 
+// adapter_test thickness <order> <in> <out>: layer_thickness + material_ids on a stack given by the test
+// (in: n[3] uint64, the three axes, elem_mat[E] uint32; out: thickness[E] double, ids[E] uint32), compared with the oracle's
+// orc_thickness by tests/test_thickness_tables.py
+static int thickness_tool(const char* order, const char* fin, const char* fout) {
+    static const char* names[6] = {"012", "021", "102", "120", "201", "210"};
+    static const IterationOrder orders[6] = {ORDER_012, ORDER_021, ORDER_102, ORDER_120, ORDER_201, ORDER_210};
+    Mesh m;
+    int oi = -1;
+    for (int k = 0; k < 6; ++k) if (!strcmp(order, names[k])) oi = k;
+    REQUIRE(oi >= 0);
+    m.order = orders[oi];
+    FILE* f = fopen(fin, "rb");
+    REQUIRE(f != nullptr);
+    uint64_t n[3];
+    REQUIRE(fread(n, 8, 3, f) == 3);
+    for (int a = 0; a < 3; ++a) { m.axis[a].resize(n[a]); REQUIRE(fread(m.axis[a].data(), 8, n[a], f) == n[a]); }
+    std::vector<uint32_t> mat(m.elements());
+    REQUIRE(fread(mat.data(), 4, mat.size(), f) == mat.size());
+    fclose(f);
+    std::vector<double> th = layer_thickness(m, [&](size_t i0, size_t i1, size_t r) { return mat[m.elem(i0, i1, r)]; });
+    std::vector<uint32_t> ids = material_ids(mat, th);
+    f = fopen(fout, "wb");
+    REQUIRE(f != nullptr);
+    fwrite(th.data(), 8, th.size(), f);
+    fwrite(ids.data(), 4, ids.size(), f);
+    fclose(f);
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 4 && !strcmp(argv[1], "thickness")) return thickness_tool(argv[2], argv[3], argv[4]);
     int rc = host_tests();
     if (rc) return rc;
     if (argc > 1 && !strcmp(argv[1], "gpu")) rc = gpu_tests();

@@ -107,3 +107,49 @@ def test_config_B_small_excluded_vs_masked_cholesky(order):
     keep = np.asarray(p.empty) == 0
     assert np.abs(flux - ref)[keep].max() <= 1e-6 * np.abs(ref).max()
     s.invalidate()
+
+
+@pytest.mark.parametrize("quirk", [False, True])
+def test_excluded_elements_add_no_boundary_terms(quirk):
+    """convection / radiation / heat flux on a surface INSIDE the mesh where kept elements meet excluded (air) ones: the
+    reference calls setBoundaries only for elements of the masked mesh (therm3d.cpp:186-268), so the air side adds nothing"""
+    from helpers import face_nodes, oracle_thermal
+    from oracle import oracle as orc
+    from plask_b200.solvers import Static3D
+    p = cf.config_B((14, 16, 40))
+    inc = (p.empty == 0).astype(np.uint8)
+    # every node that belongs to both a kept and an excluded element: the surface of the structure inside the mesh
+    n = p.n
+    eg = np.broadcast_to(p.elem_index_grid(), tuple(k - 1 for k in n))
+    kept3 = inc[eg].astype(bool)
+    touch_kept, touch_excl = np.zeros(n, dtype=bool), np.zeros(n, dtype=bool)
+    for a in (0, 1):
+        for b in (0, 1):
+            for c in (0, 1):
+                sl = (slice(a, n[0] - 1 + a), slice(b, n[1] - 1 + b), slice(c, n[2] - 1 + c))
+                touch_kept[sl] |= kept3
+                touch_excl[sl] |= ~kept3
+    surf = np.broadcast_to(p.node_index_grid(), n)[touch_kept & touch_excl].astype(np.int64)
+    assert surf.size > 50
+    conds = dict(convection=[(surf, 6.0e4, 305.)], radiation=[(surf, 0.7, 295.)])
+    o = oracle_thermal(p, algorithm="cholesky", included=inc, boundaries=orc.BoundaryTerms(p.N, **conds), quirk=quirk)
+    o.compute(0)
+    s = Static3D("masked-boundary")
+    s.problem = p
+    s.empty_elements = "exclude"
+    s.convection_boundary, s.radiation_boundary, s.boundary_verbatim = conds["convection"], conds["radiation"], quirk
+    s.iterative.maxerr = 1e-11
+    s.iterative.maxit = 100000
+    s.compute(0)
+    act = s.masked_nodes()
+    assert s.stats["outer_loops"] == len(o.history)
+    assert np.abs(s.outTemperature() - o.temperatures)[act].max() <= 1e-3
+    s.invalidate()
+    if not quirk:
+        # and it matters: with the terms of the excluded elements counted as well (every inner face twice) the field differs
+        class AllElements(orc.BoundaryTerms):
+            def terms(self, mesh, T, B, quirk, included=None):
+                return super().terms(mesh, T, B, quirk, None)
+        o2 = oracle_thermal(p, algorithm="cholesky", included=inc, boundaries=AllElements(p.N, **conds), quirk=False)
+        o2.compute(0)
+        assert np.abs(o2.temperatures - o.temperatures)[act].max() > 0.05

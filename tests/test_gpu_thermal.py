@@ -4,7 +4,7 @@ Tolerance of the north star: max |dT| <= 1e-3 K, relative residual <= 1e-8."""
 import numpy as np
 import pytest
 
-from helpers import oracle_thermal, random_problem
+from helpers import face_nodes as face_nodes_, oracle_thermal, random_problem
 from oracle import oracle as orc
 from plask_b200 import configs as cf
 from plask_b200.solvers import Static3D
@@ -263,3 +263,37 @@ def test_nonlinear_loop_converges_to_the_kirchhoff_solution(precond):
         s.invalidate()
     assert errs[0] / errs[1] == pytest.approx(4., rel=0.25) and errs[1] / errs[2] == pytest.approx(4., rel=0.25), errs
     assert errs[2] < 0.02
+
+
+@pytest.mark.parametrize("order", ["012", "201"])
+def test_overlapping_dirichlet_conditions_first_lifts_last_stays(order):
+    """two conditions naming the same nodes with different values (an edge shared by two contacts): setBC handles them one by
+    one (iterative_matrix.hpp:462-485) — the free neighbours see the FIRST value, the node itself keeps the LAST"""
+    p = cf.config_B((10, 11, 24), order=order)
+    top = face_nodes_(p, 2, -1)
+    side = face_nodes_(p, 0, 0)
+    shared = np.intersect1d(top, side)
+    assert shared.size >= 8
+    p.bc_nodes = np.concatenate([p.bc_nodes, top, side]).astype(np.uintp)      # bottom 300 K, top 310 K, side 290 K
+    p.bc_values = np.concatenate([p.bc_values, np.full(top.size, 310.), np.full(side.size, 290.)])
+    o = oracle_thermal(p, algorithm="cholesky")
+    o.compute(0)
+    assert np.all(o.temperatures[shared] == 290.)
+    s = Static3D("dup")
+    s.problem = p
+    s.iterative.maxerr = 1e-12
+    s.iterative.maxit = 100000
+    s.compute(0)
+    T = s.outTemperature()
+    assert np.all(T[shared] == 290.)
+    assert np.abs(T - o.temperatures).max() <= 1e-3
+    # the other order of the two conditions is a different problem for the neighbours of the shared edge
+    q = cf.config_B((10, 11, 24), order=order)
+    q.bc_nodes = np.concatenate([q.bc_nodes, side, top]).astype(np.uintp)
+    q.bc_values = np.concatenate([q.bc_values, np.full(side.size, 290.), np.full(top.size, 310.)])
+    o2 = oracle_thermal(q, algorithm="cholesky")
+    o2.compute(0)
+    free = np.ones(p.N, dtype=bool)
+    free[p.bc_nodes.astype(np.int64)] = False
+    assert np.abs(o2.temperatures - o.temperatures)[free].max() > 0.1
+    s.invalidate()

@@ -131,3 +131,54 @@ def test_provider_on_foreign_mesh(order_src, order_dst, layout):
     assert np.array_equal(got, ref)
     assert got.min() >= T.min() - 1e-9 and got.max() <= T.max() + 1e-9      # interpolation::trilinear rounds at 1e-13
     s.invalidate()
+
+
+def test_no_heat_outside_the_electrical_domain():
+    """thermal mesh larger than the electrical one (heat sink / substrate margins in ThermoElectric3D): getHeatDensity is 0
+    outside the bounding box of the electrical geometry (electr3d.cpp:545-548), not the constant continuation of its rim"""
+    pt, pe = make_pair((26, 28, 52), (20, 22, 52))
+    assert pt.axes[0][-1] > pe.axes[0][-1] + 1. and pt.axes[1][0] < pe.axes[1][0] - 1.
+    te, o, n, no = run_both(pt, pe, 2, 3)
+    assert n == no == 2
+    mt = o.thermal.mesh
+    mids = [orc.midpoints(a) for a in mt.axes]
+    outside = ~((mids[0] >= pe.axes[0][0]) & (mids[0] <= pe.axes[0][-1]))[:, None, None] | \
+              ~((mids[1] >= pe.axes[1][0]) & (mids[1] <= pe.axes[1][-1]))[None, :, None] | np.zeros((1, 1, len(mids[2])), dtype=bool)
+    assert outside.sum() > 1000 and np.all(o.thermal.heat[mt.elems_grid()[outside]] == 0.)
+    assert o.thermal.heat.max() > 0.
+    T, V = te.thermal.outTemperature(), te.electrical.outVoltage()
+    assert np.abs(T - o.thermal.temperatures).max() <= 1e-3
+    assert np.abs(V - o.electrical.potential).max() <= 1e-6
+    te.invalidate()
+
+
+def test_temperature_from_a_masked_thermal_mesh_is_300K_outside():
+    """thermal solver with empty-elements='exclude': SafeData substitutes 300 K where the masked mesh has no element
+    (getTemperatures, therm3d.cpp:391-392), so the electrical conductivities there are those of 300 K"""
+    rng = np.random.default_rng(5)
+    pt, pe = make_pair((12, 13, 40), (9, 11, 44), "012", "102")
+    T = 320. + 40. * rng.random(pt.N)
+    mat = np.array(pt.elem_mat, dtype=np.uint32, copy=True)
+    mat[np.asarray(pt.empty) != 0] = L.MAT_EXCLUDED
+    assert (mat == L.MAT_EXCLUDED).sum() > 100
+    ft, fe = DeviceFem(0), DeviceFem(0)
+    ft.set_mesh(pt.axes, pt.strides)
+    ft.set_materials(mat, pt.T0, pt.dT, pt.tab_lat, pt.tab_vert)
+    ft.set_field(T)
+    fe.set_mesh(pe.axes, pe.strides)
+    fe.set_materials(pe.elem_mat, pe.T0, pe.dT, pe.tab_lat, pe.tab_vert)
+    fe.take_temperature_from(ft)
+    fe.update_conductivity_shockley()
+    cond = fe.get_elem(L.ELEM_COND)
+    ot = oracle_thermal(pt, algorithm="cholesky", included=(np.asarray(pt.empty) == 0).astype(np.uint8))
+    # pfem_get_field / the exchange see 0 on the nodes outside the masked mesh (they do not exist in the reference)
+    ot._matrix()
+    ot.temperatures[:] = np.where(ot._A.active, T, 0.)
+    oe = oracle_shockley(pe, algorithm="cholesky")
+    oe.elem_junc[:] = 0
+    o = orc.ThermoElectric3DOracle(ot, oe)
+    o.exchange_temperature()
+    assert (oe.Te == 300.).sum() > 50
+    oe.load_conductivity()
+    assert np.array_equal(cond, oe.conds)
+    ft.close(); fe.close()

@@ -32,6 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BYTES_PER_DOF_FUSED = 88.0   # k_fpcg, one launch = one iteration: reads r q p D^-1 x c_lat c_vert, writes r p q x
+BYTES_PER_DOF_FUSED_ISO = 80.0   # isotropic conductivities (c_lat == c_vert, all materials of config B): c_vert is not streamed
 BYTES_PER_DOF_ITER = 112.0   # two-kernel iteration (variants 0/2): 14 FP64 words, SURVEY.md §8(d)
 BYTES_PER_DOF_APPLY = 56.0   # two-kernel operator kernel: reads r, D^-1, p_old, c_lat, c_vert; writes p_new, q
 FALLBACK_HBM_GBS = 6650.0    # /opt/skills/guides/B200_PROFILING.md
@@ -254,6 +255,52 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------- GPU arm
 
+def slab_parity(world, rank, local, allgather_bytes, gloo_barrier):
+    """N > 1: the slab-partitioned collective solve against the SAME global mesh solved on one GPU (rank 0), at a size
+    that fits one device: a full nonlinear Static3D solve of config B on a (16 N + 3) x 40 x 44 mesh with both
+    preconditioners.  Returns (on rank 0) max |T_slab - T_single| over all nodes."""
+    from plask_b200 import configs
+    from plask_b200.solvers import Static3D
+    gn = (16 * world + 3, 40, 44)
+    lo, hi, own_lo, own_hi = configs.slab_local(gn[0], rank, world)
+    q = configs.config_B(gn, order="012", rows0=(lo, hi))
+    fields, stats = {}, {}
+    for pre in ("jac", "ljac"):
+        s = Static3D("parity-slab-" + pre)
+        s.device = local
+        s.problem = q
+        s.slab = dict(rank=rank, nranks=world, own_lo=own_lo, own_hi=own_hi, allgather=allgather_bytes)
+        s.iterative.preconditioner = pre
+        s.iterative.maxerr = 1e-11
+        s.iterative.maxit = 200000
+        s.compute(0)
+        owned = np.ascontiguousarray(configs.slab_field_owned(q, s.outTemperature(), own_lo, own_hi))
+        parts = allgather_bytes(owned.tobytes())
+        stats[pre] = dict(outer_loops=s.stats["outer_loops"], pcg_iterations=int(s.stats["lin_iters"]), lin_relres=s.stats["lin_relres"])
+        s.invalidate()
+        if rank == 0:
+            fields[pre] = np.concatenate([np.frombuffer(b, dtype=np.float64) for b in parts]).reshape(gn)
+    gloo_barrier()           # no collective kernel is in flight any more: rank 0 may use its GPU alone
+    out = None
+    if rank == 0:
+        p = configs.config_B(gn, order="012")
+        one = Static3D("parity-single")
+        one.device = local
+        one.problem = p
+        one.iterative.maxerr = 1e-11
+        one.iterative.maxit = 200000
+        one.compute(0)
+        T1 = one.outTemperature().reshape(gn)     # order 012: axis 0 slowest
+        out = {"workload": f"config B {gn[0]}x{gn[1]}x{gn[2]} ({gn[0] * gn[1] * gn[2]} nodes), full nonlinear solve: {world} slabs (collective) "
+                           "against the same global mesh on one GPU",
+               "max_abs_dT_K": {pre: float(np.abs(fields[pre] - T1).max()) for pre in fields},
+               "tolerance_K": 1e-3, "outer_loops_single": one.stats["outer_loops"], "slab": stats, "maxT_single": float(T1.max())}
+        out["ok"] = all(v <= 1e-3 for v in out["max_abs_dT_K"].values()) and all(st["outer_loops"] == one.stats["outer_loops"] for st in stats.values())
+        one.invalidate()
+    gloo_barrier()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -343,20 +390,24 @@ def run_ours(args):
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
-            traffic = json.load(open(traffic_file)).get("k_fpcg_dram_bytes_per_launch" if args.variant == 3 else "apply_dram_bytes_per_launch")
+            traffic = json.load(open(traffic_file)).get("k_fpcg_dram_bytes_per_launch" if args.variant == 3 else "apply_dram_bytes_per_launch") if n == 256 else None
         except Exception:
             pass
     if args.variant == 3:
         # one kernel per iteration: its average launch duration IS the timed region / launches (CUDA events on
         # the library's stream around the graph launches)
         launch_ms = sum(ms) / max(launches, 1)
-        achieved = BYTES_PER_DOF_FUSED * N / (launch_ms * 1e-3) / 1e9
+        iso = bool(f.info(L.INFO_COND_ISO))
+        bpd = BYTES_PER_DOF_FUSED_ISO if iso else BYTES_PER_DOF_FUSED
+        achieved = bpd * N / (launch_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_fpcg (whole PCG iteration: update + new direction + matrix-free 27-point operator + 7 dots)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": how,
-                    "traffic": traffic, "algorithmic_bytes_per_launch": BYTES_PER_DOF_FUSED * N, "bytes_per_dof": BYTES_PER_DOF_FUSED,
-                    "avg_launch_ms": launch_ms,
-                    "note": "two-kernel formulation of SURVEY 8(d) is 112 B/DOF: the same time would read %.0f GB/s on that basis"
-                            % (BYTES_PER_DOF_ITER * N / (launch_ms * 1e-3) / 1e9)}
+                    "traffic": traffic, "algorithmic_bytes_per_launch": bpd * N, "bytes_per_dof": bpd,
+                    "avg_launch_ms": launch_ms, "isotropic_conductivity_variant": iso,
+                    "on_other_byte_counts": {"88 B/DOF (round-1 kernel: c_lat and c_vert streamed)": {"achieved": BYTES_PER_DOF_FUSED * N / (launch_ms * 1e-3) / 1e9,
+                                                                                         "frac": BYTES_PER_DOF_FUSED * N / (launch_ms * 1e-3) / 1e9 / peak},
+                                             "112 B/DOF (two-kernel formulation of SURVEY 8d)": {"achieved": BYTES_PER_DOF_ITER * N / (launch_ms * 1e-3) / 1e9,
+                                                                                                "frac": BYTES_PER_DOF_ITER * N / (launch_ms * 1e-3) / 1e9 / peak}}}
     else:
         # per-kernel split (events between kernels, no graph) for the roofline of the operator kernel
         split = f.bench_pcg(min(iters, 20), split_timing=True, **opts)
@@ -409,6 +460,15 @@ def run_ours(args):
 
     f.close()
     barrier()
+
+    # ---- multi-GPU parity: the collective slab solve against the same mesh on one GPU
+    parity = None
+    if slab and args.parity:
+        try:
+            parity = slab_parity(world, rank, local, allgather_bytes, lambda: dist.barrier(group=gloo))
+        except Exception as ex:
+            parity = {"error": str(ex), "ok": False}
+        barrier()
 
     # ---- time to solution of the full nonlinear Static3D solve (reported, not the metric)
     tts = None
@@ -495,7 +555,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"Static3D config B: {n}^3 VCSEL-like layered block, nonlinear k(T) tables, "
                                    f"{N} DOF per GPU, Jacobi-PCG", "iters_per_step": iters,
-                       "l2": "inputs >> L2: every iteration streams 11 vectors of %.0f MB each, nothing survives in the 126 MB L2" % (N * 8 / 1e6),
+                       "l2": "inputs >> L2: every iteration streams 10-11 vectors of %.0f MB each, nothing survives in the 126 MB L2" % (N * 8 / 1e6),
                        "order": p.order, "kernel_variant": args.variant,
                        "multi_gpu": ("single device" if world == 1 else "independent replicas" if not slab else
                                      f"z-slab partition of a {n * world}x{n}x{n} mesh along the major axis, one halo plane per "
@@ -503,7 +563,7 @@ def run_ours(args):
                                      "iteration through peer inboxes (no separate collective kernel)"),
                        "dof_total": N_total},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "time_to_solution": tts, "wall_s_timed_region": t_wall,
+            "time_to_solution": tts, "wall_s_timed_region": t_wall, "parity": parity,
         }
         print(json.dumps(line))
     if world > 1:
@@ -523,6 +583,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-tts-n", type=int, default=96, help="size of the full CPU-vs-GPU time-to-solution sample (0 = skip)")
     ap.add_argument("--no-tts", dest="tts", action="store_false")
+    ap.add_argument("--no-parity", dest="parity", action="store_false", help="N>1: skip the slab-vs-single-GPU parity solve")
     ap.add_argument("--tts-loops", type=int, default=0)
     ap.add_argument("--tts-maxit", type=int, default=200000)
     ap.add_argument("--lin-tol", type=float, default=1e-8)

@@ -279,6 +279,14 @@ int pfem_get_rhs(pfem_ctx* ctx, double* b);
 int pfem_get_diag(pfem_ctx* ctx, double* d);
 /* one linear solve from the current field with the current conds */
 int pfem_solve_linear(pfem_ctx* ctx, const pfem_opts* opts, pfem_stats* stats);
+/* facts about the prepared state, for the benchmark's byte accounting and the tests */
+typedef enum {
+    PFEM_INFO_COND_ISO = 0,     /* 1: c_lat == c_vert in every element, the iteration kernels do not stream c_vert (80 instead of 88 B/DOF) */
+    PFEM_INFO_ML_LEVELS = 1,    /* coarse levels of the multilevel preconditioner (0: not set up) */
+    PFEM_INFO_FUSED_CTAS = 2,   /* grid size of the fused iteration kernel */
+    PFEM_INFO_DEVICE_BYTES = 3  /* device memory held by the context */
+} pfem_info;
+int pfem_get_info(pfem_ctx* ctx, int what, double* value);
 /* exactly `iters` PCG iterations (no convergence exit) from the current state, device
  * resident, timed with CUDA events on the launching stream; *ms = elapsed, *apply_ms /
  * *update_ms = summed duration of the operator kernel / the vector-update kernel when

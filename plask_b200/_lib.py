@@ -101,6 +101,7 @@ SYMBOLS = {
     "pfem_get_rhs": (C.c_int, [_vp, c_dp]),
     "pfem_get_diag": (C.c_int, [_vp, c_dp]),
     "pfem_solve_linear": (C.c_int, [_vp, C.POINTER(Opts), C.POINTER(Stats)]),
+    "pfem_get_info": (C.c_int, [_vp, C.c_int, c_dp]),
     "pfem_bench_pcg": (C.c_int, [_vp, C.POINTER(Opts), C.c_int, C.c_int, c_dp, c_dp, c_dp, C.POINTER(C.c_longlong)]),
 }
 
@@ -110,6 +111,7 @@ PFEM_ERR_NOT_SPD, PFEM_ERR_NOMEM, PFEM_ERR_NAN = -5, -6, -7
 ELEM_COND, ELEM_CURRENT, ELEM_HEAT, ELEM_FLUX = 0, 1, 2, 3
 MAT_EXCLUDED = 0xFFFFFFFF
 LAYOUT_ABI, LAYOUT_VERTICAL_MINOR = 0, 1
+INFO_COND_ISO, INFO_ML_LEVELS, INFO_FUSED_CTAS, INFO_DEVICE_BYTES = 0, 1, 2, 3
 
 _lib = None
 

@@ -51,8 +51,8 @@ struct FusedTile {
     static constexpr int CHALF = (CW * CH * 2 + 15) / 16 * 16;   // (sij, ui) then (uj, kk): conflict-free LDS.128
     static constexpr int LAYER = 2 * CHALF;
     static constexpr int NRED = 7;
-    static constexpr size_t smem_bytes(int ns, int mode, int lk) {
-        return 128 + sizeof(double) * ((size_t)ns * (mode == 1 ? 6 : mode >= 2 ? 5 : 4) * BOXP + 2 * PLANE + 2 * LAYER + 32 * NRED + 2 * (size_t)(lk + 2)) +
+    static constexpr size_t smem_bytes(int ns, int mode, int lk, bool iso = false) {
+        return 128 + sizeof(double) * ((size_t)ns * ((mode == 1 ? 6 : mode >= 2 ? 5 : 4) - (iso ? 1 : 0)) * BOXP + 2 * PLANE + 2 * LAYER + 32 * NRED + 2 * (size_t)(lk + 2)) +
                16 * 8 + 16;
     }
 };
@@ -61,7 +61,9 @@ struct FusedTile {
 // MODE 0: plain q = M A p (tests, pfem_apply);  1: the fused Jacobi-PCG iteration;  3: MODE 2 with z = z_0 + z_1(parent aggregate)
 // (multilevel preconditioner, kernels_ml.cuh; vertical axis = I only);  2: operator step of the line-Jacobi
 // iteration (kernels_line.cuh): boxes z, p, mask instead of r, q, p, D^-1 — p' = mask z + beta p, x' = x + alpha p, q' = M A p'.
-template <int TJ, int RJ, int NS, int MINB, int VDIM, int MODE>
+// ISO: c_lat == c_vert in every element (bulk materials: thermk returns the same lateral and vertical value, e.g. GaAs.cpp:225-228):
+// the c_vert layer is not loaded at all — 10 instead of 11 words per DOF.
+template <int TJ, int RJ, int NS, int MINB, int VDIM, int MODE, bool ISO = false>
 __global__ void __launch_bounds__(32 * (TJ / RJ), MINB)
 k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_q,
        const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_d,
@@ -74,7 +76,8 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
     constexpr int NT = TI * (TJ / RJ);
     constexpr bool FUSED = MODE >= 1, LINE = MODE >= 2, MLZ = MODE == 3;
     constexpr int NBN = LINE ? 3 : FUSED ? 4 : 2;   // node boxes per stage: r q p d | z p mask | p d
-    constexpr int NB = NBN + 2;          // + c_lat, c_vert
+    constexpr int NCB = ISO ? 1 : 2;      // coefficient boxes: c_lat (, c_vert)
+    constexpr int NB = NBN + NCB;
     constexpr int B_P = LINE ? 1 : FUSED ? 2 : 0, B_D = B_P + 1, B_CL = NBN, B_CV = NBN + 1;
     constexpr int NRING = 2 * PWP + 2 * TJ;     // halo ring of the p' plane
     constexpr int NERING = TI + TJ + 1;         // halo row/column of the coefficient layer
@@ -180,7 +183,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         const int st = t % NS;
         double* dst = sRaw + (size_t)st * NB * BOXP;
         uint64_t* bar = &bars[st];
-        mbar_expect_tx(bar, (uint32_t)((NBN + (t > 0 ? 2 : 0)) * BOX * sizeof(double)));
+        mbar_expect_tx(bar, (uint32_t)((NBN + (t > 0 ? NCB : 0)) * BOX * sizeof(double)));
         const int P = k0 - 1 + t;
         if (FUSED) tma_load_3d(dst, &tm_r, bar, i0 - HX, j0 - 1, P);
         if (FUSED && !LINE) tma_load_3d(dst + BOXP, &tm_q, bar, i0 - HX, j0 - 1, P);
@@ -188,7 +191,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         tma_load_3d(dst + B_D * BOXP, &tm_d, bar, i0 - HX, j0 - 1, P);
         if (t > 0) {
             tma_load_3d(dst + B_CL * BOXP, &tm_cl, bar, i0 - HX, j0 - 1, P - 1);
-            tma_load_3d(dst + B_CV * BOXP, &tm_cv, bar, i0 - HX, j0 - 1, P - 1);
+            if (!ISO) tma_load_3d(dst + B_CV * BOXP, &tm_cv, bar, i0 - HX, j0 - 1, P - 1);
         }
     };
 
@@ -297,7 +300,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
             }
             sPb[(jl0 + rr + 1) * PWP + tx + 1] = pn;
             if (GATHER) {
-                const double a = raw[B_CL * BOXP + ro], b = raw[B_CV * BOXP + ro];
+                const double a = raw[B_CL * BOXP + ro], b = ISO ? a : raw[B_CV * BOXP + ro];
                 const double kI = ((VDIM == 0 ? b : a) * wI[rr]) * hk;
                 const double kJ = ((VDIM == 1 ? b : a) * wJ[rr]) * hk;
                 const double kK = ((VDIM == 2 ? b : a) * wK[rr]) * rk;
@@ -318,7 +321,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
             sPb[ring_pl] = pn;
         }
         if (GATHER && er_raw >= 0) {
-            const double a = raw[B_CL * BOXP + er_raw], b = raw[B_CV * BOXP + er_raw];
+            const double a = raw[B_CL * BOXP + er_raw], b = ISO ? a : raw[B_CV * BOXP + er_raw];
             const double kI = ((VDIM == 0 ? b : a) * wIr) * hk;
             const double kJ = ((VDIM == 1 ? b : a) * wJr) * hk;
             const double kK = ((VDIM == 2 ? b : a) * wKr) * rk;
@@ -480,6 +483,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
 
 struct FusedPlan {
     bool valid;
+    bool iso;            // launch the ISO instantiation (set per launch by the host: c_lat == c_vert everywhere)
     int tj, rj, ns, minb;
     int lk, tilesI, tilesJ, chunksK;
     CUtensorMap m_r[2], m_q[2], m_p[2], m_d, m_cl, m_cv;
@@ -535,22 +539,32 @@ static inline FusedPlan make_fused_plan(const Grid& g, int sm_count, double* con
     return f;
 }
 
-template <int TJ, int RJ, int NS, int MINB, int VDIM, int MODE>
-static inline cudaError_t launch_fused_inst(const FusedPlan& f, const Grid& g, int par, double* r_out, double* q_out, double* p_out,
+template <int TJ, int RJ, int NS, int MINB, int VDIM, int MODE, bool ISO>
+static inline cudaError_t launch_fused_inst2(const FusedPlan& f, const Grid& g, int par, double* r_out, double* q_out, double* p_out,
                                             double* x, Scalars* sc, double* partials, const PeerOut& po, cudaStream_t st, const CoarseAdd& ca) {
-    const size_t smem = FusedTile<TJ>::smem_bytes(NS, MODE, f.lk);
+    const size_t smem = FusedTile<TJ>::smem_bytes(NS, MODE, f.lk, ISO);
     static size_t attr_done[64] = {};   // the opt-in is per function AND per device (contexts may live on different GPUs)
     int dev = 0;
     cudaGetDevice(&dev);
     if (attr_done[dev & 63] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE, ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done[dev & 63] = smem;
     }
     dim3 grid(f.tilesI, f.tilesJ, f.chunksK), block(32, TJ / RJ, 1);
-    k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE><<<grid, block, smem, st>>>(f.m_r[par], f.m_q[par], f.m_p[par], f.m_d, f.m_cl, f.m_cv, g, f.lk,
+    k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE, ISO><<<grid, block, smem, st>>>(f.m_r[par], f.m_q[par], f.m_p[par], f.m_d, f.m_cl, f.m_cv, g, f.lk,
                                                                 r_out, q_out, p_out, x, sc, partials, po, ca);
     return cudaGetLastError();
+}
+
+// the ISO instantiation exists for the production tiles and the iteration modes only
+template <int TJ, int RJ, int NS, int MINB, int VDIM, int MODE>
+static inline cudaError_t launch_fused_inst(const FusedPlan& f, const Grid& g, int par, double* r_out, double* q_out, double* p_out,
+                                            double* x, Scalars* sc, double* partials, const PeerOut& po, cudaStream_t st, const CoarseAdd& ca) {
+    if constexpr (MODE >= 1 && TJ == 8 && RJ == 2 && MINB == 3) {
+        if (f.iso) return launch_fused_inst2<TJ, RJ, NS, MINB, VDIM, MODE, true>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st, ca);
+    }
+    return launch_fused_inst2<TJ, RJ, NS, MINB, VDIM, MODE, false>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st, ca);
 }
 
 template <int TJ, int RJ, int NS, int MINB, int MODE>
@@ -577,8 +591,7 @@ static inline cudaError_t launch_fused_dispatch(const FusedPlan& f, const Grid& 
 #define PFEM_FUSED_CASE(TJ, RJ, NS, MINB) \
     if (f.tj == TJ && f.rj == RJ && f.ns == NS && f.minb == MINB) return launch_fused_vdim<TJ, RJ, NS, MINB, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st, ca);
     PFEM_FUSED_CASE(8, 2, 2, 3)    // production tile (tools/tune_fused.py); the others are kept for PFEM_FUSED_TILE tuning runs
-    PFEM_FUSED_CASE(8, 2, 2, 2)
-    PFEM_FUSED_CASE(8, 1, 2, 2)
+    PFEM_FUSED_CASE(8, 2, 3, 3)
     PFEM_FUSED_CASE(16, 2, 2, 2)
 #undef PFEM_FUSED_CASE
     return cudaErrorInvalidConfiguration;

@@ -35,6 +35,8 @@ struct pfem_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     bool have_mesh = false, have_materials = false, have_junctions = false, conds_valid = false;
+    bool tables_iso = false;   // tab_lat == tab_vert entry by entry
+    bool cond_iso = false;     // c_lat == c_vert in every element right now: the iteration kernels skip the c_vert stream
     Grid g;
     std::vector<DevArr> allocs;
     // node arrays (pointers already offset by the guard band)
@@ -76,7 +78,7 @@ struct pfem_ctx {
     size_t stage_bytes = 0;
     // cached CUDA graph of `graph_batch` PCG iterations
     cudaGraphExec_t graph = nullptr;
-    int graph_batch = 0, graph_variant = -1, graph_precond = -1, graph_surf = -1;
+    int graph_batch = 0, graph_variant = -1, graph_precond = -1, graph_surf = -1, graph_iso = -1;
     // boundary-face terms (2nd / 3rd kind, radiation): flattened rows on the device, effective load vector
     Surf surf = {};
     double* fS = nullptr;
@@ -542,6 +544,7 @@ extern "C" int pfem_set_materials(pfem_ctx* ctx, const uint32_t* elem_mat, uint3
     CU(cudaMemcpyAsync(ctx->tab_vert, c_vert, cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->nmat = nmat; ctx->nT = nT; ctx->T0 = T0; ctx->dT = dT;
+    ctx->tables_iso = memcmp(c_lat, c_vert, cnt * sizeof(double)) == 0;
     ctx->have_materials = true;
     ctx->conds_valid = false;
     return PFEM_OK;
@@ -1088,6 +1091,7 @@ extern "C" int pfem_update_conductivity_thermal(pfem_ctx* ctx) {
                                                                     ctx->tab_lat, ctx->tab_vert, ctx->cl, ctx->cv);
     KCHECK(); LAUNCHED(1);
     ctx->conds_valid = true;
+    ctx->cond_iso = ctx->tables_iso;
     return PFEM_OK;
 }
 
@@ -1101,6 +1105,7 @@ extern "C" int pfem_update_conductivity_shockley(pfem_ctx* ctx) {
         ctx->tab_vert, ctx->act, ctx->junc_cond, ctx->pcond, ctx->ncond, ctx->cl, ctx->cv);
     KCHECK(); LAUNCHED(1);
     ctx->conds_valid = true;
+    ctx->cond_iso = ctx->tables_iso && ctx->nact == 0;   // a junction element is (0, sigma): anisotropic by construction
     return PFEM_OK;
 }
 
@@ -1109,6 +1114,8 @@ extern "C" int pfem_set_conductivity(pfem_ctx* ctx, const double* cond) {
     if (!cond) FAIL(PFEM_ERR_BAD_INPUT, "null conductivity");
     TRY(upload_elem<double, 2>(ctx, cond, ctx->cl, ctx->cv, nullptr));
     ctx->conds_valid = true;
+    ctx->cond_iso = true;
+    for (idx_t e = 0; e < ctx->g.E && ctx->cond_iso; ++e) ctx->cond_iso = cond[2 * e] == cond[2 * e + 1];
     return PFEM_OK;
 }
 
@@ -1394,7 +1401,7 @@ static int kernels_per_iteration(const pfem_ctx* ctx, int variant) {
 
 static int build_graph(pfem_ctx* ctx, int batch, int variant, int precond) {
     if (ctx->graph && ctx->graph_batch == batch && ctx->graph_variant == variant && ctx->graph_precond == precond &&
-        ctx->graph_surf == ctx->surf_iter)
+        ctx->graph_surf == ctx->surf_iter && ctx->graph_iso == (int)ctx->fused.iso)
         return PFEM_OK;
     if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
     cudaGraph_t graph = nullptr;
@@ -1405,7 +1412,7 @@ static int build_graph(pfem_ctx* ctx, int batch, int variant, int precond) {
     e = cudaGraphInstantiate(&ctx->graph, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { ctx->graph = nullptr; FAIL(PFEM_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
-    ctx->graph_batch = batch; ctx->graph_variant = variant; ctx->graph_precond = precond; ctx->graph_surf = ctx->surf_iter;
+    ctx->graph_batch = batch; ctx->graph_variant = variant; ctx->graph_precond = precond; ctx->graph_surf = ctx->surf_iter; ctx->graph_iso = (int)ctx->fused.iso;
     return PFEM_OK;
 }
 
@@ -1431,6 +1438,11 @@ static int pcg_prepare(pfem_ctx* ctx, const pfem_opts* o, int bench) {
     if (o->precond >= 1) TRY(ensure_line(ctx));
     if (o->precond == 2) TRY(ensure_ml(ctx));
     ctx->precond = o->precond;
+    {   // isotropic conductivities: the iteration kernels do not stream c_vert (PFEM_NO_ISO=1 keeps the general kernel, for A/B runs)
+        static const bool no_iso = getenv("PFEM_NO_ISO") != nullptr;
+        ctx->fused.iso = ctx->cond_iso && !no_iso;
+        ctx->line_plan.iso = ctx->fused.iso;
+    }
     k_set_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, tol2, o->maxit, bench, ctx->surf_iter, o->precond);
     LAUNCHED(1);
     TRY(launch_diag(ctx));
@@ -1985,6 +1997,19 @@ extern "C" int pfem_get_diag(pfem_ctx* ctx, double* d) {
     KCHECK(); LAUNCHED(1);
     CU(download_nodes(ctx, d, ctx->q));
     CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+
+extern "C" int pfem_get_info(pfem_ctx* ctx, int what, double* value) {
+    NEED_MESH();
+    if (!value) FAIL(PFEM_ERR_BAD_INPUT, "null output");
+    switch (what) {
+        case PFEM_INFO_COND_ISO: *value = (ctx->conds_valid && ctx->cond_iso && !getenv("PFEM_NO_ISO")) ? 1. : 0.; break;
+        case PFEM_INFO_ML_LEVELS: *value = ctx->ml.nlev; break;
+        case PFEM_INFO_FUSED_CTAS: *value = ctx->fused.valid ? (double)ctx->fused.tilesI * ctx->fused.tilesJ * ctx->fused.chunksK : 0.; break;
+        case PFEM_INFO_DEVICE_BYTES: { double b = 0.; for (auto& a : ctx->allocs) b += (double)a.bytes; *value = b + (double)ctx->stage_bytes; break; }
+        default: FAIL(PFEM_ERR_BAD_INPUT, "unknown info %d", what);
+    }
     return PFEM_OK;
 }
 

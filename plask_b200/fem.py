@@ -250,6 +250,11 @@ class DeviceFem:
         self._ck(self.lib.pfem_apply(self.ctx, _dp(p), _dp(q), int(variant)))
         return q
 
+    def info(self, what):
+        v = C.c_double(0)
+        self._ck(self.lib.pfem_get_info(self.ctx, int(what), C.byref(v)))
+        return v.value
+
     def apply_precond(self, r, **kw):
         """z = M^-1 r of the preconditioner `precond` built from the current conductivities (parity tests)"""
         r = _f64(r)

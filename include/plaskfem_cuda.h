@@ -242,6 +242,11 @@ typedef enum {
  * get zero heat (electr3d.cpp:472); only read for PFEM_ELEM_HEAT. */
 int pfem_get_elem(pfem_ctx* ctx, int what, const uint8_t* noheat, double* out);
 int pfem_get_junction_cond(pfem_ctx* ctx, double* junc_cond /* [ncol][2] */);
+/* Element temperatures T_elem (as set by pfem_set_elem_temperature or pfem_transfer_temperature) at `n` selected elements
+ * (indices in the element order of the mesh).  The host needs them at the mid-plane element of every junction column to
+ * evaluate beta(T), js(T) (electr3d.cpp:261-262, electr_python.cpp:103-110) when the temperature field came from another
+ * context and never touched the host. */
+int pfem_get_elem_temperature(pfem_ctx* ctx, size_t n, const size_t* elem, double* T_out);
 
 /* ---- field exchange between two contexts on the same device ------------------------
  * The ThermoElectric meta loop (solvers/meta/shockley/thermoelectric.py:207-211) connects

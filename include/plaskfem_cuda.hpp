@@ -150,6 +150,7 @@ struct Dirichlet {
     std::vector<double> value;
     template <typename NodeRange>
     void add(const NodeRange& place, double v) { for (size_t r : place) { node.push_back(r); value.push_back(v); } }
+    void add_node(size_t r, double v) { node.push_back(r); value.push_back(v); }
 };
 
 // ---- masked meshes: empty-elements = "exclude" (fem_solver.hpp:182-189) --------------------------------
@@ -176,6 +177,13 @@ struct MaskedNumbering {
         for (size_t i = 0; i < used.size(); ++i) if (used[i]) { node_of_full[i] = full_of_node.size(); full_of_node.push_back(i); }
         for (size_t e = 0; e < elem_of_full.size(); ++e) if (elem_of_full[e] != NONE) { elem_of_full[e] = full_of_elem.size(); full_of_elem.push_back(e); }
     }
+    // the same from a flag per element of the full mesh (element order of the mesh); an EMPTY vector means a full mesh
+    MaskedNumbering(const Mesh& m, const std::vector<uint8_t>& included_per_elem)
+        : MaskedNumbering(m, [&](size_t i0, size_t i1, size_t i2) { return included_per_elem.empty() || included_per_elem[m.elem(i0, i1, i2)] != 0; }) {
+        if (!included_per_elem.empty() && included_per_elem.size() != m.elements()) throw BadInput("MaskedNumbering: one flag per element expected");
+    }
+    size_t node_to_full(size_t masked_node) const { return full_of_node[masked_node]; }
+    size_t elem_to_full(size_t masked_elem) const { return full_of_elem[masked_elem]; }
     // material ids for pfem_set_materials: the caller's ids on kept elements, PFEM_MAT_EXCLUDED elsewhere
     std::vector<uint32_t> mark_excluded(std::vector<uint32_t> ids) const {
         for (size_t e = 0; e < ids.size(); ++e) if (elem_of_full[e] == NONE) ids[e] = PFEM_MAT_EXCLUDED;
@@ -215,6 +223,10 @@ struct NodeConditions {
             has[r] = 1;
             for (int k = 0; k < NV; ++k) v[k][r] = value[k];
         }
+    }
+    void add_node(size_t mesh_size, size_t r, const std::array<double, NV>& value) {
+        const size_t one[1] = {r};
+        add(mesh_size, one, value);
     }
 };
 
@@ -289,8 +301,9 @@ struct IterParams {
     bool converged = true;
     int iters = 0;
     double err = 0.;
-    // iter_params.preconditioner (:27-46): the two NSPCG choices the CUDA algorithm provides
-    enum Preconditioner { PRECOND_JAC = 0, PRECOND_LJAC = 1 };
+    // iter_params.preconditioner (:27-46): NSPCG's 'jac' and 'ljac', and the multilevel line preconditioner 'mlj' that stands in
+    // for the reference's default 'ic' (a sequential factorisation; mlj reaches its strength with parallel line solves)
+    enum Preconditioner { PRECOND_JAC = 0, PRECOND_LJAC = 1, PRECOND_MLJ = 2 };
     Preconditioner preconditioner = PRECOND_JAC;
 };
 

@@ -90,6 +90,7 @@ SYMBOLS = {
     "pfem_interpolate_field": (C.c_int, [_vp, _szp, c_dp, c_dp, c_dp, _szp, c_dp]),
     "pfem_get_elem": (C.c_int, [_vp, C.c_int, _u8p, c_dp]),
     "pfem_get_junction_cond": (C.c_int, [_vp, c_dp]),
+    "pfem_get_elem_temperature": (C.c_int, [_vp, c_sz, _szp, c_dp]),
     "pfem_set_noheat": (C.c_int, [_vp, _u8p]),
     "pfem_transfer_temperature": (C.c_int, [_vp, _vp]),
     "pfem_transfer_heat": (C.c_int, [_vp, _vp]),

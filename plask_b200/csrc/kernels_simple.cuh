@@ -755,4 +755,9 @@ __global__ void k_interp_to_points(const int n0, const int n1, const int n2, con
     }
 }
 
+// out[m] = a[slot[m]]
+__global__ void k_gather(const size_t n, const idx_t* __restrict__ slot, const double* __restrict__ a, double* __restrict__ out) {
+    for (size_t m = blockIdx.x * (size_t)blockDim.x + threadIdx.x; m < n; m += (size_t)gridDim.x * blockDim.x) out[m] = a[slot[m]];
+}
+
 }  // namespace pfem

@@ -1704,6 +1704,33 @@ extern "C" int pfem_get_junction_cond(pfem_ctx* ctx, double* junc_cond) {
     return PFEM_OK;
 }
 
+extern "C" int pfem_get_elem_temperature(pfem_ctx* ctx, size_t n, const size_t* elem, double* T_out) {
+    NEED_MESH();
+    if (n && (!elem || !T_out)) FAIL(PFEM_ERR_BAD_INPUT, "null argument");
+    if (!ctx->Te) FAIL(PFEM_ERR_STATE, "no element temperatures: pfem_set_elem_temperature / pfem_transfer_temperature has not been called");
+    if (!n) return PFEM_OK;
+    const Grid& g = ctx->g;
+    int ord[3] = {0, 1, 2};
+    std::sort(ord, ord + 3, [&](int a, int b) { return g.es[a] > g.es[b]; });   // major, medium, minor element axis
+    std::vector<idx_t> slot(n);
+    for (size_t m = 0; m < n; ++m) {
+        if (elem[m] >= (size_t)g.E) FAIL(PFEM_ERR_BAD_INPUT, "element %zu out of range", elem[m]);
+        idx_t rem = (idx_t)elem[m], s = 0;
+        for (int q = 0; q < 3; ++q) { s += g.ps[ord[q]] * (rem / g.es[ord[q]]); rem %= g.es[ord[q]]; }
+        slot[m] = s;    // an element lives at the lattice index of its lowest corner node
+    }
+    const size_t bytes = n * (sizeof(idx_t) + sizeof(double));
+    TRY(ensure_stage(ctx, bytes));
+    idx_t* d_slot = reinterpret_cast<idx_t*>(ctx->stage);
+    double* d_out = reinterpret_cast<double*>(d_slot + n);
+    CU(cudaMemcpyAsync(d_slot, slot.data(), n * sizeof(idx_t), cudaMemcpyHostToDevice, ctx->stream));
+    k_gather<<<(unsigned)std::min<size_t>((n + 255) / 256, 1024), 256, 0, ctx->stream>>>(n, d_slot, ctx->Te, d_out);
+    KCHECK(); LAUNCHED(1);
+    CU(cudaMemcpyAsync(T_out, d_out, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+
 // ------------------------------------------------------------------ field exchange -------
 
 extern "C" int pfem_set_noheat(pfem_ctx* ctx, const uint8_t* noheat) {

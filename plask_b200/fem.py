@@ -227,6 +227,13 @@ class DeviceFem:
         self._ck(self.lib.pfem_get_elem(self.ctx, what, nh.ctypes.data_as(L._u8p) if nh is not None else None, _dp(out)))
         return out[:, 0] if nc == 1 else out
 
+    def get_elem_temperature(self, elems):
+        """T_elem at the given elements (element order of the mesh)"""
+        e = np.ascontiguousarray(elems, dtype=np.uintp)
+        out = np.empty(e.size)
+        self._ck(self.lib.pfem_get_elem_temperature(self.ctx, e.size, e.ctypes.data_as(L._szp), _dp(out)))
+        return out
+
     def get_junction_cond(self):
         out = np.empty((self.ncol, 2))
         self._ck(self.lib.pfem_get_junction_cond(self.ctx, _dp(out)))

@@ -271,9 +271,16 @@ class Shockley3D(_FemSolver):
         super().invalidate()
         self._junc_cond = None      # junction_conductivity.reset(1, default), :200
 
-    def _midplane_temperature(self):
-        """element temperatures on the host (only when beta/js are callables of T)"""
-        raise L.BadInput(f"{self.id}: beta(T)/js(T) callables with a connected inTemperature are not supported yet")
+    def _midplane_elements(self):
+        """element index (element order of the mesh) of the mid-plane element of every junction-table entry, -1 = unused entry"""
+        es = self._problem.estrides
+        out = np.full(max(self._ncol, 1), -1, dtype=np.int64)
+        for a in self._acts:
+            v = (a["top"] + a["bottom"]) // 2
+            t = np.arange(a["left"], a["right"])[:, None]
+            l = np.arange(a["back"], a["front"])[None, :]
+            out[(a["offset"] + a["ld"] * t + l).ravel()] = (l * es[0] + t * es[1] + v * es[2]).ravel()
+        return out
 
     def _per_junction(self, v, k):
         return v[k] if isinstance(v, (list, tuple)) else v
@@ -293,7 +300,10 @@ class Shockley3D(_FemSolver):
             l = np.arange(a["back"], a["front"])[None, :]
             col = (a["offset"] + a["ld"] * t + l).ravel()
             e = (l * es[0] + t * es[1] + v * es[2]).ravel()
-            T = np.full(e.size, float(Te)) if np.isscalar(Te) else np.asarray(Te)[e]
+            if isinstance(Te, dict):        # temperatures fetched from the device: one value per junction-table entry
+                T = Te["per_column"][col]
+            else:
+                T = np.full(e.size, float(Te)) if np.isscalar(Te) else np.asarray(Te)[e]
             bcol[col] = np.vectorize(b)(T) if callable(b) else b
             jcol[col] = np.vectorize(j)(T) if callable(j) else j
         return bcol, jcol
@@ -311,7 +321,15 @@ class Shockley3D(_FemSolver):
                 Te.initialize()
             f.take_temperature_from(Te._fem)
             need_T = any(callable(self._per_junction(v, k)) for k in range(len(self._acts)) for v in (self.beta, self.js))
-            Te = self._midplane_temperature() if need_T else 300.
+            if need_T:
+                # only the mid-plane element of every junction column is read back (electr3d.cpp:261-262: temperature[tidx])
+                elems = self._midplane_elements()
+                Tcol = np.full(elems.size, 300.)
+                used = elems >= 0
+                Tcol[used] = f.get_elem_temperature(elems[used])
+                Te = {"per_column": Tcol}
+            else:
+                Te = 300.
         else:
             f.set_elem_temperature(Te if np.isscalar(Te) else np.asarray(Te, dtype=np.float64))
         bcol, jcol = self._junction_params(Te)

@@ -182,3 +182,51 @@ def test_temperature_from_a_masked_thermal_mesh_is_300K_outside():
     oe.load_conductivity()
     assert np.array_equal(cond, oe.conds)
     ft.close(); fe.close()
+
+
+def test_temperature_dependent_junction_in_the_meta_loop():
+    """beta(T), js(T) as callables with electrical.inTemperature connected to the thermal solver on the device
+    (electr_python.cpp:103-110 evaluates them at temperature[tidx], the mid-plane element of the junction column,
+    electr3d.cpp:261-262): only those elements are read back from the device"""
+    pt, pe = make_pair((16, 18, 44), (20, 22, 52))
+    beta = lambda T: 11. * (300. / T) ** 0.7        # noqa: E731
+    js = lambda T: 1. * np.exp((T - 300.) / 40.)    # noqa: E731
+    te = ThermoElectric3D("te-betaT")
+    te.thermal.problem, te.electrical.problem = pt, pe
+    te.tfreq = 3
+    for s in (te.thermal, te.electrical):
+        s.iterative.maxerr, s.iterative.maxit = 1e-12, 100000
+    te.electrical.beta, te.electrical.js, te.electrical.maxerr = beta, js, pe.maxerr
+    te.thermal.maxerr = pt.maxerr
+    n = te.compute(max_meta_loops=3)
+    ot = oracle_thermal(pt, algorithm="cholesky")
+    oe = oracle_shockley(pe, algorithm="cholesky", beta=beta, js=js)
+    o = orc.ThermoElectric3DOracle(ot, oe, tfreq=3)
+    no = o.compute(max_meta_loops=3)
+    assert n == no == 3
+    assert o.thermal.maxT > 300.5                      # the junction temperature really moved, so beta(T) != beta(300)
+    assert np.abs(te.thermal.outTemperature() - o.thermal.temperatures).max() <= 1e-3
+    assert np.abs(te.electrical.outVoltage() - o.electrical.potential).max() <= 1e-6
+    assert te.get_total_current() == pytest.approx(o.electrical.get_total_current(), rel=1e-6)
+    # against constant parameters the current differs visibly
+    oc = oracle_shockley(pe, algorithm="cholesky", beta=11., js=1.)
+    oc.compute(3)
+    assert abs(oc.get_total_current() - o.electrical.get_total_current()) > 1e-3 * abs(oc.get_total_current())
+    te.invalidate()
+
+
+def test_get_elem_temperature_gathers_the_exchanged_field():
+    rng = np.random.default_rng(8)
+    pt, pe = make_pair((9, 8, 12), (7, 12, 14), "102", "201")
+    T = 300. + 60. * rng.random(pt.N)
+    ft, fe = DeviceFem(0), DeviceFem(0)
+    ft.set_mesh(pt.axes, pt.strides)
+    ft.set_field(T)
+    fe.set_layout(L.LAYOUT_VERTICAL_MINOR)
+    fe.set_mesh(pe.axes, pe.strides)
+    fe.take_temperature_from(ft)
+    mt, me = orc.Mesh(*pt.axes, pt.order), orc.Mesh(*pe.axes, pe.order)
+    Te = orc.interp_linear(mt.axes, mt.ns, T, [orc.midpoints(a) for a in me.axes], me.es, me.E)
+    pick = rng.choice(pe.E, size=200, replace=False)
+    assert np.array_equal(fe.get_elem_temperature(pick), Te[pick])
+    ft.close(); fe.close()

@@ -1,0 +1,629 @@
+"""Generate patches/plask-algorithm-cuda.diff: the binding of libplaskfem_cuda.so into the PLaSK tree as a unified diff
+(`patch -p1` from the PLaSK root).  The edits are expressed against the text of /root/reference, so the script fails loudly
+when the reference moves; tests/test_patch_applies.py applies the committed diff to a scratch copy of the touched files.
+
+    python tools/make_patch.py            # needs /root/reference (build container only)
+
+What the patch does (INTEGRATION.md explains every hunk):
+  * a new FemMatrixAlgorithm value ALGORITHM_CUDA ('cuda' in XPL / Python / the GUI schema)
+  * ThermalFem3DSolver / ElectricalFem3DSolver: a plaskfem::Context member, built in onInitialize(), and a compute()
+    branch that hands the whole nonlinear loop to the library (include/plaskfem_cuda.hpp)
+  * BetaSolver / the Python Shockley class expose beta(T), js(T) per junction through one virtual, so that the host can
+    evaluate them at the mid-plane temperature of every junction column (electr3d.cpp:261-262)
+  * the two solver CMakeLists link plaskfem_cuda
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "patches", "plask-algorithm-cuda.diff")
+
+EDITS = {}
+
+
+def edit(path, old, new, count=1):
+    EDITS.setdefault(path, []).append((old, new, count))
+
+
+# ---------------------------------------------------------------- plask/common/fem/fem_solver.hpp
+F = "plask/common/fem/fem_solver.hpp"
+edit(F, """    ALGORITHM_GAUSS,     ///< Gauss elimination of asymmetric matrix (slower but safer as it uses pivoting)
+    ALGORITHM_ITERATIVE  ///< Conjugate gradient iterative solver
+};""", """    ALGORITHM_GAUSS,     ///< Gauss elimination of asymmetric matrix (slower but safer as it uses pivoting)
+    ALGORITHM_ITERATIVE, ///< Conjugate gradient iterative solver
+    ALGORITHM_CUDA       ///< Matrix-free conjugate gradients on a CUDA device (libplaskfem_cuda, no FemMatrix object)
+};""")
+edit(F, """                            .value("iterative", ALGORITHM_ITERATIVE)
+                            .get(algorithm);""", """                            .value("iterative", ALGORITHM_ITERATIVE)
+                            .value("cuda", ALGORITHM_CUDA)
+                            .get(algorithm);""")
+edit(F, """        case ALGORITHM_ITERATIVE: return new SparseBandMatrix(this, this->mesh->size(), this->mesh->minorAxis()->size());
+    }
+    return nullptr;""", """        case ALGORITHM_ITERATIVE: return new SparseBandMatrix(this, this->mesh->size(), this->mesh->minorAxis()->size());
+        case ALGORITHM_CUDA: throw NotImplemented(this->getId(), "matrix object for algorithm 'cuda' (the solve is matrix-free)");
+    }
+    return nullptr;""")
+edit(F, """            return new SparseBandMatrix(this, this->mesh->size(), mesh->mediumAxis()->size() * mesh->minorAxis()->size(),
+                                        mesh->minorAxis()->size());
+    }
+    return nullptr;""", """            return new SparseBandMatrix(this, this->mesh->size(), mesh->mediumAxis()->size() * mesh->minorAxis()->size(),
+                                        mesh->minorAxis()->size());
+        case ALGORITHM_CUDA: throw NotImplemented(this->getId(), "matrix object for algorithm 'cuda' (the solve is matrix-free)");
+    }
+    return nullptr;""")
+edit(F, """        if (empty_elements == EMPTY_ELEMENTS_INCLUDED ||
+            (this->algorithm == ALGORITHM_ITERATIVE && empty_elements == EMPTY_ELEMENTS_DEFAULT)) {""",
+     """        if (empty_elements == EMPTY_ELEMENTS_INCLUDED ||
+            ((this->algorithm == ALGORITHM_ITERATIVE || this->algorithm == ALGORITHM_CUDA) &&
+             empty_elements == EMPTY_ELEMENTS_DEFAULT)) {""")
+edit(F, """                return new SparseFreeMatrix(this, this->maskedMesh->size(), this->maskedMesh->elements().size() * 10);
+    }
+    return nullptr;""", """                return new SparseFreeMatrix(this, this->maskedMesh->size(), this->maskedMesh->elements().size() * 10);
+        case ALGORITHM_CUDA: throw NotImplemented(this->getId(), "matrix object for algorithm 'cuda' (the solve is matrix-free)");
+    }
+    return nullptr;""")
+edit(F, """                return new SparseFreeMatrix(this, this->maskedMesh->size(), this->maskedMesh->elements().size() * 36);
+    }
+    return nullptr;""", """                return new SparseFreeMatrix(this, this->maskedMesh->size(), this->maskedMesh->elements().size() * 36);
+        case ALGORITHM_CUDA: throw NotImplemented(this->getId(), "matrix object for algorithm 'cuda' (the solve is matrix-free)");
+    }
+    return nullptr;""")
+
+# ---------------------------------------------------------------- python enum, XPL schema
+edit("python/plask/common/fem/fem.cpp", """        .value("ITERATIVE", ALGORITHM_ITERATIVE);""", """        .value("ITERATIVE", ALGORITHM_ITERATIVE)
+        .value("CUDA", ALGORITHM_CUDA);""")
+edit("plask/common/fem.yml", """      - gauss
+      - iterative
+    help: >
+      Algorithm used for solving set of linear positive-definite equations.""", """      - gauss
+      - iterative
+      - cuda
+    help: >
+      Algorithm used for solving set of linear positive-definite equations. ``cuda`` runs the whole nonlinear loop
+      of the 3D thermal and electrical solvers matrix-free on a CUDA device (conjugate gradients with the ``jac``,
+      ``ljac`` or ``mlj`` preconditioner); it has no CPU fallback.""")
+
+# ---------------------------------------------------------------- thermal.static Static3D
+F = "solvers/thermal/static/therm3d.hpp"
+edit(F, """#include <plask/plask.hpp>
+#include <plask/common/fem.hpp>
+
+#include "common.hpp"
+
+namespace plask { namespace thermal { namespace tstatic {
+
+/**
+ * Solver performing calculations in 2D Cartesian or Cylindrical space using finite element method
+ */
+struct PLASK_SOLVER_API ThermalFem3DSolver:""", """#include <plask/plask.hpp>
+#include <plask/common/fem.hpp>
+
+#include "common.hpp"
+
+namespace plaskfem { class Context; }   // plaskfem_cuda.hpp: host adapter of libplaskfem_cuda.so (algorithm 'cuda')
+
+namespace plask { namespace thermal { namespace tstatic {
+
+/**
+ * Solver performing calculations in 2D Cartesian or Cylindrical space using finite element method
+ */
+struct PLASK_SOLVER_API ThermalFem3DSolver:""")
+edit(F, """    DataVector<Vec<3,double>> fluxes;           ///< Computed (only when needed) heat fluxes on our own mesh
+""", """    DataVector<Vec<3,double>> fluxes;           ///< Computed (only when needed) heat fluxes on our own mesh
+
+    std::shared_ptr<plaskfem::Context> cuda;     ///< Device context, exists only for algorithm 'cuda'
+
+    /// Create the device context: mesh, (material, layer thickness) ids and their thermk(T) tables
+    void setupCuda();
+
+    /// The nonlinear loop of compute() on the device
+    double computeCuda(int loops,
+                       const BoundaryConditionsWithMesh<RectangularMesh<3>::Boundary,double>& btemperature,
+                       const BoundaryConditionsWithMesh<RectangularMesh<3>::Boundary,double>& bheatflux,
+                       const BoundaryConditionsWithMesh<RectangularMesh<3>::Boundary,Convection>& bconvection,
+                       const BoundaryConditionsWithMesh<RectangularMesh<3>::Boundary,Radiation>& bradiation);
+""")
+
+F = "solvers/thermal/static/therm3d.cpp"
+edit(F, """#include "therm3d.hpp"
+""", """#include "therm3d.hpp"
+
+#include <plaskfem_cuda.hpp>
+""")
+edit(F, """            if (idx != RectangularMaskedMesh3D::Element::UNKNOWN_ELEMENT_INDEX)
+                thickness[idx] = h;
+        }
+    }
+}
+
+
+void ThermalFem3DSolver::onInvalidate() {
+    temperatures.reset();
+    fluxes.reset();
+    thickness.reset();
+}
+""", """            if (idx != RectangularMaskedMesh3D::Element::UNKNOWN_ELEMENT_INDEX)
+                thickness[idx] = h;
+        }
+    }
+
+    if (algorithm == ALGORITHM_CUDA) setupCuda();
+}
+
+
+/// Flat description of a RectangularMesh<3> for the device library (SURVEY Appendix B)
+static plaskfem::Mesh cudaMesh(const RectangularMesh<3>& mesh) {
+    plaskfem::Mesh fm;
+    for (int a = 0; a < 3; ++a) {
+        fm.axis[a].reserve(mesh.axis[a]->size());
+        for (size_t i = 0; i != mesh.axis[a]->size(); ++i) fm.axis[a].push_back(mesh.axis[a]->at(i));
+    }
+    fm.order = plaskfem::IterationOrder(int(mesh.getIterationOrder()));  // same enumerators, rectilinear3d.hpp:349
+    return fm;
+}
+
+
+void ThermalFem3DSolver::setupCuda() {
+    try {
+        cuda.reset(new plaskfem::Context(0, this->getId()));
+        // the line preconditioners want the vertical axis contiguous whatever the iteration order of the mesh
+        if (iter_params.preconditioner != IterativeMatrixParams::PRECOND_JAC && this->mesh->axis[2]->size() <= 512)
+            cuda->set_layout(PFEM_LAYOUT_VERTICAL_MINOR);
+        plaskfem::Mesh fm = cudaMesh(*this->mesh);
+        cuda->set_mesh(fm);
+
+        // one table id per (material, layer thickness) pair: thermk(T, thickness) is sampled on the host, the device
+        // interpolates (no virtual calls from kernels); elements outside the masked mesh are marked excluded
+        const size_t nfull = this->mesh->getElementsCount();
+        std::vector<shared_ptr<Material>> materials(nfull);
+        std::vector<const Material*> key(nfull, nullptr);
+        std::vector<double> thick(nfull, 0.);
+        std::vector<uint8_t> included(nfull, 0);
+        for (auto elem: this->maskedMesh->elements()) {
+            size_t e = this->mesh->element(elem.getIndex0(), elem.getIndex1(), elem.getIndex2()).getIndex();
+            materials[e] = this->geometry->getMaterial(elem.getMidpoint());
+            key[e] = materials[e].get();
+            thick[e] = thickness[elem.getIndex()];
+            included[e] = 1;
+        }
+        std::vector<size_t> reps;
+        std::vector<uint32_t> ids = plaskfem::material_ids(key, thick, &reps);
+        plaskfem::Tables tables = plaskfem::sample_tables(reps.size(), [&](uint32_t id, double T) {
+            if (!materials[reps[id]]) return std::make_pair(0., 0.);
+            auto k = materials[reps[id]]->thermk(T, thick[reps[id]]);
+            return std::make_pair(k.c00, k.c11);
+        });
+        if (!this->maskedMesh->full()) ids = plaskfem::MaskedNumbering(fm, included).mark_excluded(ids);
+        cuda->set_materials(ids, tables);
+        cuda->fill_field(inittemp);
+    } catch (const plaskfem::NoDevice& err) {
+        throw ComputationError(this->getId(), "algorithm 'cuda' has no CPU fallback: {}", err.what());
+    } catch (const plaskfem::BadInput& err) {
+        throw BadInput(this->getId(), "{}", err.what());
+    }
+}
+
+
+void ThermalFem3DSolver::onInvalidate() {
+    temperatures.reset();
+    fluxes.reset();
+    thickness.reset();
+    cuda.reset();
+}
+""")
+edit(F, """    this->writelog(LOG_INFO, "Running thermal calculations");
+
+    int loop = 0;
+    size_t size = maskedMesh->size();
+
+    std::unique_ptr<FemMatrix> pA(getMatrix());""", """    this->writelog(LOG_INFO, "Running thermal calculations");
+
+    if (algorithm == ALGORITHM_CUDA) return computeCuda(loops, btemperature, bheatflux, bconvection, bradiation);
+
+    int loop = 0;
+    size_t size = maskedMesh->size();
+
+    std::unique_ptr<FemMatrix> pA(getMatrix());""")
+edit(F, """void ThermalFem3DSolver::saveHeatFluxes()
+{""", """double ThermalFem3DSolver::computeCuda(int loops,
+                   const BoundaryConditionsWithMesh<RectangularMesh<3>::Boundary,double>& btemperature,
+                   const BoundaryConditionsWithMesh<RectangularMesh<3>::Boundary,double>& bheatflux,
+                   const BoundaryConditionsWithMesh<RectangularMesh<3>::Boundary,Convection>& bconvection,
+                   const BoundaryConditionsWithMesh<RectangularMesh<3>::Boundary,Radiation>& bradiation)
+{
+    if (!cuda) setupCuda();
+    try {
+        plaskfem::Mesh fm = cudaMesh(*this->mesh);
+        const bool masked = !this->maskedMesh->full();
+        std::vector<uint8_t> included;
+        if (masked) {
+            included.assign(this->mesh->getElementsCount(), 0);
+            for (auto elem: this->maskedMesh->elements())
+                included[this->mesh->element(elem.getIndex0(), elem.getIndex1(), elem.getIndex2()).getIndex()] = 1;
+        }
+        plaskfem::MaskedNumbering numbering(fm, included);   // identity maps on a full mesh
+        const size_t nfull = this->mesh->size();
+        auto full_node = [&](size_t masked_node) { return masked ? numbering.node_to_full(masked_node) : masked_node; };
+
+        // boundary conditions of the 2nd / 3rd kind and radiation (setMatrix :242-268): per-node getValue() arrays,
+        // the element loop of setBoundaries (:140-168) runs inside the library
+        plaskfem::NodeConditions<1> hf;
+        plaskfem::NodeConditions<2> cv, rd;
+        for (auto cond: bheatflux) for (auto r: cond.place) hf.add_node(nfull, full_node(r), {cond.value});
+        for (auto cond: bconvection) for (auto r: cond.place) cv.add_node(nfull, full_node(r), {cond.value.coeff, cond.value.ambient});
+        for (auto cond: bradiation) for (auto r: cond.place) rd.add_node(nfull, full_node(r), {cond.value.emissivity, cond.value.ambient});
+        cuda->set_boundary(hf, cv, rd, /*verbatim=*/true);
+
+        plaskfem::Dirichlet bc;                                   // application order of matrix.hpp:111-118
+        for (auto cond: btemperature) for (auto r: cond.place) bc.add_node(full_node(r), cond.value);
+        cuda->set_dirichlet(bc);
+
+        auto heats = inHeat(this->maskedMesh->getElementMesh());  // :179
+        std::vector<double> heat(this->mesh->getElementsCount(), 0.);
+        for (auto elem: this->maskedMesh->elements())
+            heat[this->mesh->element(elem.getIndex0(), elem.getIndex1(), elem.getIndex2()).getIndex()] = heats[elem.getIndex()];
+        cuda->set_source(heat.data());
+
+        temperatures = temperatures.claim();
+        std::vector<double> field(nfull, 0.);
+        for (size_t i = 0; i != temperatures.size(); ++i) field[full_node(i)] = temperatures[i];
+        cuda->set_field(field.data());                            // warm start, like iterative_matrix.hpp:205-209
+
+        plaskfem::IterParams ip{iter_params.maxit, iter_params.maxerr,
+                                plaskfem::IterParams::NoConvergenceBehavior(int(iter_params.no_convergence_behavior))};
+        // jac / ljac as named; every other choice (ic is the default) -> the multilevel line preconditioner
+        ip.preconditioner = iter_params.preconditioner == IterativeMatrixParams::PRECOND_JAC ? plaskfem::IterParams::PRECOND_JAC :
+                            iter_params.preconditioner == IterativeMatrixParams::PRECOND_LJAC ? plaskfem::IterParams::PRECOND_LJAC :
+                                                                                                plaskfem::IterParams::PRECOND_MLJ;
+        auto result = cuda->solve(true, ip, maxerr, loops,
+                                  [this](int level, const std::string& msg) { this->writelog(LogLevel(level), msg); });
+        iter_params.converged = ip.converged; iter_params.iters = ip.iters; iter_params.err = ip.err;
+
+        cuda->get_field(field.data());
+        for (size_t i = 0; i != temperatures.size(); ++i) temperatures[i] = field[full_node(i)];
+        loopno = result.loopno; maxT = result.maxval; toterr = result.toterr;
+    } catch (const plaskfem::BadInput& err) {
+        throw BadInput(this->getId(), "{}", err.what());
+    } catch (const std::runtime_error& err) {
+        throw ComputationError(this->getId(), "{}", err.what());
+    }
+
+    outTemperature.fireChanged();
+    outHeatFlux.fireChanged();
+
+    return toterr;
+}
+
+void ThermalFem3DSolver::saveHeatFluxes()
+{""")
+
+# ---------------------------------------------------------------- electrical.shockley Shockley3D
+F = "solvers/electrical/shockley/electr3d.hpp"
+edit(F, """#include "common.hpp"
+
+namespace plask { namespace electrical { namespace shockley {
+
+/**
+ * Solver performing calculations in 2D Cartesian or Cylindrical space using finite element method
+ */
+struct PLASK_SOLVER_API ElectricalFem3DSolver :""", """#include "common.hpp"
+
+namespace plaskfem { class Context; }   // plaskfem_cuda.hpp: host adapter of libplaskfem_cuda.so (algorithm 'cuda')
+
+namespace plask { namespace electrical { namespace shockley {
+
+/**
+ * Solver performing calculations in 2D Cartesian or Cylindrical space using finite element method
+ */
+struct PLASK_SOLVER_API ElectricalFem3DSolver :""")
+edit(F, """    virtual Tensor2<double> activeCond(size_t n, double U, double jy, double T) = 0;
+""", """    virtual Tensor2<double> activeCond(size_t n, double U, double jy, double T) = 0;
+
+    /** Parameters of the Shockley law of junction \\p n at temperature \\p T, for solvers whose activeCond is
+     *  10 |jy| beta h / ln(1e7 |jy| / js + 1) (BetaSolver and its Python subclass).  Algorithm 'cuda' evaluates that law
+     *  on the device and therefore needs the parameters instead of the callback.
+     *  \\return false if this solver has another junction model
+     */
+    virtual bool shockleyParameters(size_t PLASK_UNUSED(n), double PLASK_UNUSED(T), double& PLASK_UNUSED(beta),
+                                    double& PLASK_UNUSED(js)) const { return false; }
+
+    std::shared_ptr<plaskfem::Context> cuda;    ///< Device context, exists only for algorithm 'cuda'
+
+    /// Create the device context: mesh and the cond(T) tables of the materials
+    void setupCuda();
+
+    /// The nonlinear loop of compute() on the device
+    double computeCuda(unsigned loops, const BoundaryConditionsWithMesh<RectangularMesh<3>::Boundary, double>& bvoltage);
+""")
+
+F = "solvers/electrical/shockley/beta.hpp"
+edit(F, """        return Tensor2<double>(0., 10. * jy * this->active[n].height * getBeta(n) / log(1e7 * jy / getJs(n) + 1.));
+    }
+""", """        return Tensor2<double>(0., 10. * jy * this->active[n].height * getBeta(n) / log(1e7 * jy / getJs(n) + 1.));
+    }
+
+    bool shockleyParameters(size_t n, double PLASK_UNUSED(T), double& beta, double& js) const override {
+        beta = getBeta(n);
+        js = getJs(n);
+        return true;
+    }
+""")
+
+F = "solvers/electrical/shockley/python/electr_python.cpp"
+edit(F, """        jy = abs(jy);
+        return Tensor2<double>(0., 10. * jy * beta * this->active[n].height / log(1e7 * jy / js + 1.));
+    }
+};
+""", """        jy = abs(jy);
+        return Tensor2<double>(0., 10. * jy * beta * this->active[n].height / log(1e7 * jy / js + 1.));
+    }
+
+    bool shockleyParameters(size_t n, double T, double& beta, double& js) const override {
+        OmpLockGuard lock(python_omp_lock);
+        beta = (n < beta_function.size() && !beta_function[n].is_none()) ? py::extract<double>(beta_function[n](T))
+                                                                         : BetaSolver<GeometryT>::getBeta(n);
+        js = (n < js_function.size() && !js_function[n].is_none()) ? py::extract<double>(js_function[n](T))
+                                                                   : BetaSolver<GeometryT>::getJs(n);
+        return true;
+    }
+};
+""")
+
+F = "solvers/electrical/shockley/electr3d.cpp"
+edit(F, """#include "electr3d.hpp"
+""", """#include "electr3d.hpp"
+
+#include <plaskfem_cuda.hpp>
+""")
+edit(F, """    potential.reset(maskedMesh->size(), 0.);
+    current.reset(maskedMesh->getElementsCount(), vec(0., 0., 0.));
+    conds.reset(maskedMesh->getElementsCount());
+}
+
+void ElectricalFem3DSolver::onInvalidate() {
+    conds.reset();
+    potential.reset();
+    current.reset();
+    heat.reset();
+    junction_conductivity.reset(1, default_junction_conductivity);
+}
+""", """    potential.reset(maskedMesh->size(), 0.);
+    current.reset(maskedMesh->getElementsCount(), vec(0., 0., 0.));
+    conds.reset(maskedMesh->getElementsCount());
+    if (algorithm == ALGORITHM_CUDA) setupCuda();
+}
+
+void ElectricalFem3DSolver::onInvalidate() {
+    conds.reset();
+    potential.reset();
+    current.reset();
+    heat.reset();
+    junction_conductivity.reset(1, default_junction_conductivity);
+    cuda.reset();
+}
+
+/// Flat description of a RectangularMesh<3> for the device library (SURVEY Appendix B)
+static plaskfem::Mesh cudaMesh(const RectangularMesh<3>& mesh) {
+    plaskfem::Mesh fm;
+    for (int a = 0; a < 3; ++a) {
+        fm.axis[a].reserve(mesh.axis[a]->size());
+        for (size_t i = 0; i != mesh.axis[a]->size(); ++i) fm.axis[a].push_back(mesh.axis[a]->at(i));
+    }
+    fm.order = plaskfem::IterationOrder(int(mesh.getIterationOrder()));  // same enumerators, rectilinear3d.hpp:349
+    return fm;
+}
+
+void ElectricalFem3DSolver::setupCuda() {
+    try {
+        cuda.reset(new plaskfem::Context(0, this->getId()));
+        if (iter_params.preconditioner != IterativeMatrixParams::PRECOND_JAC && this->mesh->axis[2]->size() <= 512)
+            cuda->set_layout(PFEM_LAYOUT_VERTICAL_MINOR);
+        plaskfem::Mesh fm = cudaMesh(*this->mesh);
+        cuda->set_mesh(fm);
+        // cond(T) of every distinct material, sampled on the host (loadConductivity :221)
+        const size_t nfull = this->mesh->getElementsCount();
+        std::vector<shared_ptr<Material>> materials(nfull);
+        std::vector<const Material*> key(nfull, nullptr);
+        std::vector<uint8_t> included(nfull, 0);
+        for (auto elem : this->maskedMesh->elements()) {
+            size_t e = this->mesh->element(elem.getIndex0(), elem.getIndex1(), elem.getIndex2()).getIndex();
+            materials[e] = this->geometry->getMaterial(elem.getMidpoint());
+            key[e] = materials[e].get();
+            included[e] = 1;
+        }
+        std::vector<size_t> reps;
+        std::vector<uint32_t> ids = plaskfem::material_ids(key, std::vector<double>(), &reps);
+        plaskfem::Tables tables = plaskfem::sample_tables(reps.size(), [&](uint32_t id, double T) {
+            if (!materials[reps[id]]) return std::make_pair(0., 0.);
+            auto s = materials[reps[id]]->cond(T);
+            return std::make_pair(s.c00, s.c11);
+        });
+        if (!this->maskedMesh->full()) ids = plaskfem::MaskedNumbering(fm, included).mark_excluded(ids);
+        cuda->set_materials(ids, tables);
+        cuda->fill_field(0.);
+    } catch (const plaskfem::NoDevice& err) {
+        throw ComputationError(this->getId(), "algorithm 'cuda' has no CPU fallback: {}", err.what());
+    } catch (const plaskfem::BadInput& err) {
+        throw BadInput(this->getId(), "{}", err.what());
+    }
+}
+""")
+edit(F, """    this->writelog(LOG_INFO, "Running electrical calculations");
+
+    unsigned loop = 0;
+    double err = 0.;
+    toterr = 0.;
+
+    std::unique_ptr<FemMatrix> pA(this->getMatrix());""", """    this->writelog(LOG_INFO, "Running electrical calculations");
+
+    if (algorithm == ALGORITHM_CUDA) return computeCuda(loops, bvoltage);
+
+    unsigned loop = 0;
+    double err = 0.;
+    toterr = 0.;
+
+    std::unique_ptr<FemMatrix> pA(this->getMatrix());""")
+edit(F, """void ElectricalFem3DSolver::saveHeatDensity() {""", """double ElectricalFem3DSolver::computeCuda(unsigned loops,
+                                          const BoundaryConditionsWithMesh<RectangularMesh<3>::Boundary, double>& bvoltage) {
+    if (!cuda) setupCuda();
+    try {
+        plaskfem::Mesh fm = cudaMesh(*this->mesh);
+        const bool masked = !this->maskedMesh->full();
+        const size_t nfull = this->mesh->size(), efull = this->mesh->getElementsCount();
+        std::vector<uint8_t> included;
+        if (masked) {
+            included.assign(efull, 0);
+            for (auto elem : this->maskedMesh->elements())
+                included[this->mesh->element(elem.getIndex0(), elem.getIndex1(), elem.getIndex2()).getIndex()] = 1;
+        }
+        plaskfem::MaskedNumbering numbering(fm, included);
+        auto full_node = [&](size_t i) { return masked ? numbering.node_to_full(i) : i; };
+        auto full_elem = [&](const RectangularMaskedMesh<3>::Element& el) {
+            return this->mesh->element(el.getIndex0(), el.getIndex1(), el.getIndex2()).getIndex();
+        };
+
+        // what loadConductivity (:203-225) and saveHeatDensity (:472) read from the geometry, flattened
+        std::vector<uint32_t> elem_junc(efull, 0);
+        std::vector<uint8_t> elem_role(efull, 0), noheat(efull, 0);
+        std::vector<double> Te(efull, 300.);
+        auto temperature = inTemperature(this->maskedMesh->getElementMesh());
+        for (auto el : this->maskedMesh->elements()) {
+            size_t e = full_elem(el);
+            auto mid = el.getMidpoint();
+            auto roles = this->geometry->getRolesAt(mid);
+            elem_junc[e] = uint32_t(isActive(mid));
+            elem_role[e] = roles.find("p-contact") != roles.end() ? 1 : roles.find("n-contact") != roles.end() ? 2 : 0;
+            noheat[e] = this->geometry->getMaterial(mid)->kind() == Material::EMPTY || roles.find("noheat") != roles.end();
+            Te[e] = temperature[el.getIndex()];
+        }
+        cuda->set_elem_temperature(Te.data());
+        cuda->set_noheat(noheat);
+
+        // junctions: Active maps 1:1 onto pfem_junction; beta(T), js(T) per junction-table entry at the temperature of the
+        // mid-plane element of the column (setMatrix :261-262)
+        std::vector<pfem_junction> junctions(active.size());
+        const size_t ncol = junction_conductivity.size();
+        std::vector<double> beta_col(ncol, 1.), js_col(ncol, 1.);
+        for (size_t n = 0; n != active.size(); ++n) {
+            const Active& act = active[n];
+            junctions[n] = pfem_junction{act.bottom, act.top, act.left, act.right, act.back, act.front, act.ld, act.offset, act.height};
+            const size_t mid = (act.bottom + act.top) / 2;
+            for (size_t t = act.left; t != act.right; ++t)
+                for (size_t l = act.back; l != act.front; ++l) {
+                    const size_t tidx = this->maskedMesh->element(l, t, mid).getIndex();
+                    const double T = tidx != RectangularMaskedMesh3D::Element::UNKNOWN_ELEMENT_INDEX ? temperature[tidx] : 300.;
+                    const size_t col = act.offset + act.ld * t + l;
+                    if (!shockleyParameters(n, T, beta_col[col], js_col[col]))
+                        throw BadInput(this->getId(), "algorithm 'cuda' needs a Shockley junction (beta, js); this solver has a custom junction model");
+                }
+        }
+        std::vector<double> jcond(2 * ncol);
+        for (size_t i = 0; i != ncol; ++i) { jcond[2 * i] = junction_conductivity[i].c00; jcond[2 * i + 1] = junction_conductivity[i].c11; }
+        cuda->set_junctions(junctions, elem_junc, elem_role, pcond, ncond, jcond, beta_col, js_col, convergence == CONVERGENCE_STABLE);
+
+        plaskfem::Dirichlet bc;                                   // application order of matrix.hpp:111-118
+        for (auto cond : bvoltage) for (auto r : cond.place) bc.add_node(full_node(r), cond.value);
+        cuda->set_dirichlet(bc);
+        cuda->set_source(nullptr);                                // zero load vector (:278)
+
+        potential = potential.claim();
+        std::vector<double> field(nfull, 0.);
+        for (size_t i = 0; i != potential.size(); ++i) field[full_node(i)] = potential[i];
+        cuda->set_field(field.data());
+
+        plaskfem::IterParams ip{iter_params.maxit, iter_params.maxerr,
+                                plaskfem::IterParams::NoConvergenceBehavior(int(iter_params.no_convergence_behavior))};
+        ip.preconditioner = iter_params.preconditioner == IterativeMatrixParams::PRECOND_JAC ? plaskfem::IterParams::PRECOND_JAC :
+                            iter_params.preconditioner == IterativeMatrixParams::PRECOND_LJAC ? plaskfem::IterParams::PRECOND_LJAC :
+                                                                                                plaskfem::IterParams::PRECOND_MLJ;
+        auto result = cuda->solve(false, ip, maxerr, int(loops),
+                                  [this](int level, const std::string& msg) { this->writelog(LogLevel(level), msg); });
+        iter_params.converged = ip.converged; iter_params.iters = ip.iters; iter_params.err = ip.err;
+
+        cuda->get_field(field.data());
+        for (size_t i = 0; i != potential.size(); ++i) potential[i] = field[full_node(i)];
+        std::vector<double> cur(3 * efull), cnd(2 * efull);
+        cuda->get_elem(PFEM_ELEM_CURRENT, cur.data());
+        cuda->get_elem(PFEM_ELEM_COND, cnd.data());
+        for (auto el : this->maskedMesh->elements()) {
+            size_t e = full_elem(el), i = el.getIndex();
+            current[i] = vec(cur[3 * e], cur[3 * e + 1], cur[3 * e + 2]);
+            conds[i] = Tensor2<double>(cnd[2 * e], cnd[2 * e + 1]);
+        }
+        cuda->get_junction_cond(jcond.data());                    // saveConductivity (:227-237) happened on the device
+        for (size_t i = 0; i != ncol; ++i) junction_conductivity[i] = Tensor2<double>(jcond[2 * i], jcond[2 * i + 1]);
+        heat.reset();
+        maxcur = vec(result.maxcur[0], result.maxcur[1], result.maxcur[2]);
+        loopno = result.loopno;
+        toterr = result.toterr;
+    } catch (const plaskfem::BadInput& err) {
+        throw BadInput(this->getId(), "{}", err.what());
+    } catch (const std::runtime_error& err) {
+        throw ComputationError(this->getId(), "{}", err.what());
+    }
+
+    outVoltage.fireChanged();
+    outCurrentDensity.fireChanged();
+    outHeat.fireChanged();
+
+    return toterr;
+}
+
+void ElectricalFem3DSolver::saveHeatDensity() {""")
+
+# ---------------------------------------------------------------- build
+for F, target in (("solvers/thermal/static/CMakeLists.txt", "thermal"), ("solvers/electrical/shockley/CMakeLists.txt", "electrical")):
+    edit(F, """# Build everything the default way.
+# Call this macro unless you really know what you are doing!
+make_default()""", """# Algorithm 'cuda': the header-only host adapter plaskfem_cuda.hpp and libplaskfem_cuda.so (a plain C ABI; the solver does not
+# need nvcc).  Point PLASKFEM_CUDA_ROOT at the directory that holds include/ and libplaskfem_cuda.so.
+set(PLASKFEM_CUDA_ROOT "" CACHE PATH "Root of the plaskfem_cuda library (include/plaskfem_cuda.h, libplaskfem_cuda.so)")
+find_path(PLASKFEM_CUDA_INCLUDE_DIR plaskfem_cuda.hpp HINTS ${PLASKFEM_CUDA_ROOT}/include)
+find_library(PLASKFEM_CUDA_LIBRARY plaskfem_cuda HINTS ${PLASKFEM_CUDA_ROOT} ${PLASKFEM_CUDA_ROOT}/lib ${PLASKFEM_CUDA_ROOT}/plask_b200)
+if(NOT PLASKFEM_CUDA_INCLUDE_DIR OR NOT PLASKFEM_CUDA_LIBRARY)
+    message(FATAL_ERROR "plaskfem_cuda not found: set PLASKFEM_CUDA_ROOT")
+endif()
+include_directories(${PLASKFEM_CUDA_INCLUDE_DIR})
+set(SOLVER_LINK_LIBRARIES ${SOLVER_LINK_LIBRARIES} ${PLASKFEM_CUDA_LIBRARY})
+
+# Build everything the default way.
+# Call this macro unless you really know what you are doing!
+make_default()""")
+
+
+def main():
+    if not os.path.isdir(REF):
+        raise SystemExit("needs /root/reference")
+    tmp = tempfile.mkdtemp(prefix="plaskpatch_")
+    a, b = os.path.join(tmp, "a"), os.path.join(tmp, "b")
+    for path, edits in EDITS.items():
+        for side in (a, b):
+            os.makedirs(os.path.dirname(os.path.join(side, path)), exist_ok=True)
+            shutil.copyfile(os.path.join(REF, path), os.path.join(side, path))
+        text = open(os.path.join(b, path)).read()
+        for old, new, count in edits:
+            if text.count(old) != count:
+                raise SystemExit(f"{path}: expected {count} occurrence(s), found {text.count(old)} of:\n{old[:200]}")
+            text = text.replace(old, new)
+        open(os.path.join(b, path), "w").write(text)
+    r = subprocess.run(["diff", "-ruN", "a", "b"], cwd=tmp, capture_output=True, text=True)
+    if r.returncode not in (0, 1):
+        raise SystemExit(r.stderr)
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    # drop the time stamps of the ---/+++ lines: the diff must not change from run to run
+    lines = []
+    for line in r.stdout.splitlines(keepends=True):
+        if line.startswith(("--- a/", "+++ b/")):
+            line = line.split("\t")[0] + "\n"
+        lines.append(line)
+    open(OUT, "w").write("".join(lines))
+    shutil.rmtree(tmp)
+    print(f"{OUT}: {len(lines)} lines, {len(EDITS)} files")
+
+
+if __name__ == "__main__":
+    main()

@@ -32,12 +32,24 @@
 #pragma once
 #include <cuda.h>
 
+#include <algorithm>
+#include <functional>
 #include <type_traits>
+#include <vector>
 
 #include "kernels_tma.cuh"
 #include "kernels_ml.cuh"
 
 namespace pfem {
+
+// Chunks of the march along K: chunk c of every tile covers the owned planes [off[c], off[c+1]) (relative to kown0).
+// The lengths DECREASE with c (make_fused_plan): the hardware hands CTAs to free SM slots in blockIdx order, so long chunks go
+// first and short ones fill the tail of the launch.
+#define PFEM_MAX_CHUNKS 32
+struct ChunkTab {
+    int n, lkmax;
+    int off[PFEM_MAX_CHUNKS + 1];
+};
 
 template <int TJ>
 struct FusedTile {
@@ -67,7 +79,7 @@ template <int TJ, int RJ, int NS, int MINB, int VDIM, int MODE, bool ISO = false
 __global__ void __launch_bounds__(32 * (TJ / RJ), MINB)
 k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_q,
        const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_d,
-       const __grid_constant__ CUtensorMap tm_cl, const __grid_constant__ CUtensorMap tm_cv, const Grid g, const int lk,
+       const __grid_constant__ CUtensorMap tm_cl, const __grid_constant__ CUtensorMap tm_cv, const Grid g, const ChunkTab ck,
        double* __restrict__ r_out, double* __restrict__ q_out, double* __restrict__ p_out, double* __restrict__ x,
        Scalars* sc, double* partials, const PeerOut po, const CoarseAdd ca) {
     typedef FusedTile<TJ> T;
@@ -91,15 +103,18 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
     int* const sh_flag = reinterpret_cast<int*>(bars + 16);
     double* const sHK = reinterpret_cast<double*>(bars + 18);   // [lk+2] hK and [lk+2] 1/hK of the element layers of this chunk
 
-    if (FUSED && sc->done == 1) return;   // done == 2 (line-Jacobi PCG): the pending x update is still to be applied
-    const double alpha = FUSED ? sc->alpha : 0.;
-    const double beta = FUSED ? sc->beta : 0.;
+    // Programmatic dependent launch: the next launch of the stream may become resident as soon as every CTA of this grid has
+    // passed this point and SM slots free up; everything up to pdl_wait() below touches only data that is constant during a
+    // linear solve (mesh spacings, D^-1 / mask, conductivities), so that prologue runs under the tail of the previous launch
+    // (its last CTAs, the grid reduction and — in slab mode — the cross-rank scalar exchange).
+    if (FUSED) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int tid = tx + TI * ty;
     const int i0 = blockIdx.x * TI, j0 = blockIdx.y * TJ;
-    const int k0 = g.kown0 + blockIdx.z * lk;   // owned planes only (slab mode: halo planes belong to the neighbours)
-    const int k1 = min(k0 + lk, g.kown1);
+    const int lk = ck.lkmax;
+    const int k0 = g.kown0 + ck.off[blockIdx.z];   // owned planes only (slab mode: halo planes belong to the neighbours)
+    const int k1 = g.kown0 + ck.off[blockIdx.z + 1];
     const int nsteps = k1 - k0 + 1;   // items t = 0 .. nsteps: node planes k0-1 .. k1, element layers k0-1 .. k1-1
     const int jl0 = ty * RJ;
     // slab mode: the first / last owned plane is also stored into the neighbour's halo plane (NVLink peer stores)
@@ -144,14 +159,12 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
     double zc[RJ], zcr = 0., zt_own = 0., zt_ring = 0.;
     if (MLZ) {
         zi_own = min(i, g.nI - 1);
-        zt_own = __ldg(ca.zt + zi_own);
 #pragma unroll
         for (int rr = 0; rr < RJ; ++rr) { zj_own[rr] = min(j0 + jl0 + rr, g.nJ - 1); zc[rr] = 0.; }
         if (ring_raw >= 0) {
             const int jj = ring_pl / PWP, ii = ring_pl % PWP;
             zj_ring = min(max(j0 - 1 + jj, 0), g.nJ - 1);
             zi_ring = min(max(i0 - 1 + ii, 0), g.nI - 1);
-            zt_ring = __ldg(ca.zt + zi_ring);
         }
     }
     auto load_zc = [&](const int P) {   // coarse correction of node plane P
@@ -179,21 +192,30 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         wKr = s36 * hi * hj;
     }
 
-    auto issue = [&](int t) {
+    // part 1: boxes that are constant during a linear solve (D^-1 or mask, conductivities) + the expected byte count of the
+    // whole stage; part 2: the iteration vectors.  issue() = both.
+    auto issue_const = [&](int t) {
         const int st = t % NS;
         double* dst = sRaw + (size_t)st * NB * BOXP;
         uint64_t* bar = &bars[st];
         mbar_expect_tx(bar, (uint32_t)((NBN + (t > 0 ? NCB : 0)) * BOX * sizeof(double)));
         const int P = k0 - 1 + t;
-        if (FUSED) tma_load_3d(dst, &tm_r, bar, i0 - HX, j0 - 1, P);
-        if (FUSED && !LINE) tma_load_3d(dst + BOXP, &tm_q, bar, i0 - HX, j0 - 1, P);
-        tma_load_3d(dst + B_P * BOXP, &tm_p, bar, i0 - HX, j0 - 1, P);
         tma_load_3d(dst + B_D * BOXP, &tm_d, bar, i0 - HX, j0 - 1, P);
         if (t > 0) {
             tma_load_3d(dst + B_CL * BOXP, &tm_cl, bar, i0 - HX, j0 - 1, P - 1);
             if (!ISO) tma_load_3d(dst + B_CV * BOXP, &tm_cv, bar, i0 - HX, j0 - 1, P - 1);
         }
     };
+    auto issue_vec = [&](int t) {
+        const int st = t % NS;
+        double* dst = sRaw + (size_t)st * NB * BOXP;
+        uint64_t* bar = &bars[st];
+        const int P = k0 - 1 + t;
+        if (FUSED) tma_load_3d(dst, &tm_r, bar, i0 - HX, j0 - 1, P);
+        if (FUSED && !LINE) tma_load_3d(dst + BOXP, &tm_q, bar, i0 - HX, j0 - 1, P);
+        tma_load_3d(dst + B_P * BOXP, &tm_p, bar, i0 - HX, j0 - 1, P);
+    };
+    auto issue = [&](int t) { issue_const(t); issue_vec(t); };
 
     // spacings of the element layers k0-2 .. k1-1 (entry t = layer of step t), staged once: a global load per
     // step would sit on the critical path of every warp
@@ -209,7 +231,18 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
     }
     __syncthreads();
     if (tid == 0)
-        for (int t = 0; t < NS && t <= nsteps; ++t) issue(t);
+        for (int t = 0; t < NS && t <= nsteps; ++t) issue_const(t);
+    if (FUSED) asm volatile("griddepcontrol.wait;" ::: "memory");   // the previous launch has completed and its writes are visible
+    if (tid == 0)
+        for (int t = 0; t < NS && t <= nsteps; ++t) issue_vec(t);
+    const int done_in = FUSED ? sc->done : 0;
+    if (done_in == 1) {   // a finished solve (done == 2, line-Jacobi PCG: the pending x update is still to be applied):
+        if (tid == 0)     // let the boxes in flight land before the shared memory is given back
+            for (int t = 0; t < NS && t <= nsteps; ++t) mbar_wait(&bars[t], 0u);
+        return;
+    }
+    const double alpha = FUSED ? sc->alpha : 0.;
+    const double beta = FUSED ? sc->beta : 0.;
 
     // ---- state carried along the march ----------------------------------------------------
     // The p' windows and (z, D^-1) of the own nodes ping-pong between two register sets so that
@@ -353,6 +386,11 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
                     e_sij[ey][si] = ea.x; e_ui[ey][si] = ea.y; e_uj[ey][si] = eb.x; e_kk[ey][si] = eb.y;
                 }
             }
+            double dw[RJ + 2][3];   // b - a
+#pragma unroll
+            for (int y = 0; y < RJ + 2; ++y)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) dw[y][c] = wb[y][c] - wa[y][c];
             double Bs[RJ + 1], Qs[RJ + 1], Ss[RJ + 1];   // sums over the two elements of a row
 #pragma unroll
             for (int ey = 0; ey <= RJ; ++ey) {
@@ -377,14 +415,11 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
                 double lb2 = fma(-e_sij[rr + 1][1], wb[y2][2], fma(-e_sij[rr + 1][0], wb[y2][0], Bs[rr + 1] * wb[y2][1]));
                 la += la0 + la2;
                 lb += lb0 + lb2;
-                // vertical stiffness M9 (b - a) evaluated as M9 b - M9 a (same rounding class as an assembled SpMV)
-                double ca = fma(P1, wa[yc][2], fma(P0, wa[yc][0], T4 * wa[yc][1]));
-                double ca0 = fma(e_kk[rr][1], wa[y0][2], fma(e_kk[rr][0], wa[y0][0], Q0 * wa[y0][1]));
-                double ca2 = fma(e_kk[rr + 1][1], wa[y2][2], fma(e_kk[rr + 1][0], wa[y2][0], Q1 * wa[y2][1]));
-                double cb = fma(P1, wb[yc][2], fma(P0, wb[yc][0], T4 * wb[yc][1]));
-                double cb0 = fma(e_kk[rr][1], wb[y0][2], fma(e_kk[rr][0], wb[y0][0], Q0 * wb[y0][1]));
-                double cb2 = fma(e_kk[rr + 1][1], wb[y2][2], fma(e_kk[rr + 1][0], wb[y2][0], Q1 * wb[y2][1]));
-                const double cc = (cb + (cb0 + cb2)) - (ca + (ca0 + ca2));
+                // vertical stiffness M9 (b - a) on the difference window
+                double cc = fma(P1, dw[yc][2], fma(P0, dw[yc][0], T4 * dw[yc][1]));
+                const double cc0 = fma(e_kk[rr][1], dw[y0][2], fma(e_kk[rr][0], dw[y0][0], Q0 * dw[y0][1]));
+                const double cc2 = fma(e_kk[rr + 1][1], dw[y2][2], fma(e_kk[rr + 1][0], dw[y2][0], Q1 * dw[y2][1]));
+                cc += cc0 + cc2;
                 const double lo = fma(2., la, lb) - cc;
                 const double hi = fma(2., lb, la) + cc;
                 if (FINAL) {
@@ -412,7 +447,11 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         for (int rr = 0; rr < RJ; ++rr) nown[rr] += sK;
     };
 
-    if (MLZ) load_zc(k0 - 1);
+    if (MLZ) {   // written by the level kernels of this iteration: after pdl wait
+        zt_own = __ldg(ca.zt + zi_own);
+        if (ring_raw >= 0) zt_ring = __ldg(ca.zt + zi_ring);
+        load_zc(k0 - 1);
+    }
     {
         typedef std::true_type Y;
         typedef std::false_type N;
@@ -481,11 +520,122 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
 
 // ---------------------------------------------------------------------- host side -------
 
+static inline bool ck_ok(const int* v, int n, int lmax) {
+    if (n < 1 || n > PFEM_MAX_CHUNKS) return false;
+    for (int c = 0; c < n; ++c) if (v[c] < 1 || v[c] > lmax) return false;
+    return true;
+}
+
+// Model of one launch: `tiles` CTAs per chunk index, handed out in blockIdx order (chunk-major) to `resident` SM slots, a CTA
+// with l owned planes taking l + 2 (halo planes) + 1.5 (start-up) plane steps.  Returns the makespan in plane steps.
+static inline double chunk_makespan(const int* len, int n, int tiles, int resident, std::vector<double>& heap) {
+    heap.assign((size_t)resident, 0.);
+    for (int c = 0; c < n; ++c) {
+        const double cost = len[c] + 3.5;
+        for (int t = 0; t < tiles; ++t) {
+            std::pop_heap(heap.begin(), heap.end(), std::greater<double>());
+            heap.back() += cost;
+            std::push_heap(heap.begin(), heap.end(), std::greater<double>());
+        }
+    }
+    return *std::max_element(heap.begin(), heap.end());
+}
+
+// Chunk lengths along K.  Uniform chunks leave the last wave of CTAs partly empty (256^3 on 148 x 3 slots: 1280 CTAs = 2.9
+// waves, 8 % of the SM time idle in ncu); lengths that decrease with the chunk index let the short chunks fill that tail.
+// Geometric start sequences, then a deterministic hill climb on the modelled makespan.  fixed_lk > 0: uniform chunks of that length.
+static inline void plan_chunks(int nown, int tiles, int resident, int fixed_lk, ChunkTab& ck) {
+    const int LMAX = 510;   // <= 8 KB of staged layer spacings per CTA
+    int best[PFEM_MAX_CHUNKS], nbest = 0;
+    auto finish = [&]() {
+        ck.n = nbest; ck.lkmax = 0; ck.off[0] = 0;
+        for (int c = 0; c < nbest; ++c) { ck.off[c + 1] = ck.off[c] + best[c]; if (best[c] > ck.lkmax) ck.lkmax = best[c]; }
+    };
+    const char* env = getenv("PFEM_FUSED_CHUNKS");   // "l0,l1,..." for tuning runs (must sum to the owned planes)
+    if (env && !fixed_lk) {
+        int sum = 0; nbest = 0;
+        for (const char* s = env; *s && nbest < PFEM_MAX_CHUNKS;) {
+            char* e; long v = strtol(s, &e, 10);
+            if (e == s || v <= 0) break;
+            best[nbest++] = (int)v; sum += (int)v; s = (*e == ',') ? e + 1 : e;
+        }
+        if (sum == nown && ck_ok(best, nbest, LMAX)) { finish(); return; }
+    }
+    if (fixed_lk > 0 || getenv("PFEM_FUSED_UNIFORM")) {
+        int l = fixed_lk;
+        if (l <= 0) {   // round-1 rule: whole waves against the two re-staged halo planes
+            double be = -1.;
+            for (int c = 1; c <= nown; ++c) {
+                const int lc = (nown + c - 1) / c;
+                if (lc < 8 && c > 1) break;
+                const long long ctas = (long long)tiles * ((nown + lc - 1) / lc), waves = (ctas + resident - 1) / resident;
+                const double eff = (double)ctas / (double)(waves * resident) * (double)lc / (double)(lc + 2);
+                if (eff > be + 1e-9) { be = eff; l = lc; }
+            }
+        }
+        if (l > LMAX) l = LMAX;
+        if ((nown + l - 1) / l > PFEM_MAX_CHUNKS) l = (nown + PFEM_MAX_CHUNKS - 1) / PFEM_MAX_CHUNKS;
+        nbest = 0;
+        for (int k = 0; k < nown; k += l) best[nbest++] = (nown - k < l) ? nown - k : l;
+        finish();
+        return;
+    }
+    std::vector<double> heap;
+    double bestT = 1e300;
+    int cur[PFEM_MAX_CHUNKS];
+    const int lmin = nown >= 32 ? 4 : 1;
+    auto normalise = [&](int* v, int n) {   // decreasing order
+        std::sort(v, v + n, std::greater<int>());
+    };
+    auto consider = [&](int* v, int n) {
+        if (!ck_ok(v, n, LMAX)) return false;
+        const double T = chunk_makespan(v, n, tiles, resident, heap);
+        if (T < bestT - 1e-9) { bestT = T; nbest = n; memcpy(best, v, sizeof(int) * n); return true; }
+        return false;
+    };
+    const int nmaxc = std::min(PFEM_MAX_CHUNKS, std::max(1, nown / lmin));
+    const int nminc = (nown + LMAX - 1) / LMAX;
+    static const double ratios[] = {1.0, 0.85, 0.7, 0.55, 0.4, 0.3};
+    for (int n = nminc; n <= nmaxc; ++n)
+        for (double rho : ratios) {
+            if (rho < 1. && n > 12) break;
+            double w[PFEM_MAX_CHUNKS], sw = 0., x = 1.;
+            for (int c = 0; c < n; ++c) { w[c] = x; sw += x; x *= rho; }
+            int sum = 0;
+            for (int c = 0; c < n; ++c) { cur[c] = std::max(lmin, (int)(nown * w[c] / sw)); sum += cur[c]; }
+            if (sum > nown) { cur[0] -= sum - nown; if (cur[0] < lmin) continue; }
+            for (int c = 0; sum < nown; c = (c + 1) % n) { ++cur[c]; ++sum; }
+            normalise(cur, n);
+            consider(cur, n);
+        }
+    if (nbest == 0) { best[0] = nown; nbest = 1; if (!ck_ok(best, 1, LMAX)) { plan_chunks(nown, tiles, resident, std::min(LMAX, nown), ck); return; } }
+    // hill climb: move d planes from chunk a to chunk b
+    unsigned lcg = 12345u;
+    const int budget = tiles * (long long)nbest > 20000 ? 60 : 400;
+    for (int it = 0; it < budget && nbest > 1; ++it) {
+        lcg = lcg * 1664525u + 1013904223u;
+        const int a = (int)((lcg >> 8) % (unsigned)nbest);
+        lcg = lcg * 1664525u + 1013904223u;
+        int b = (int)((lcg >> 8) % (unsigned)nbest);
+        if (a == b) b = (b + 1) % nbest;
+        lcg = lcg * 1664525u + 1013904223u;
+        const int d = 1 << ((lcg >> 8) % 4u);
+        memcpy(cur, best, sizeof(int) * nbest);
+        if (cur[a] - d < lmin) continue;
+        cur[a] -= d; cur[b] += d;
+        normalise(cur, nbest);
+        consider(cur, nbest);
+    }
+    finish();
+}
+
 struct FusedPlan {
     bool valid;
     bool iso;            // launch the ISO instantiation (set per launch by the host: c_lat == c_vert everywhere)
+    bool pdl;            // launch the iteration kernels with programmatic stream serialization (PFEM_NO_PDL=1 turns it off)
     int tj, rj, ns, minb;
     int lk, tilesI, tilesJ, chunksK;
+    ChunkTab ck;
     CUtensorMap m_r[2], m_q[2], m_p[2], m_d, m_cl, m_cv;
     char why[160];
 };
@@ -505,25 +655,14 @@ static inline FusedPlan make_fused_plan(const Grid& g, int sm_count, double* con
     }
     f.tilesI = (g.nI + 31) / 32;
     f.tilesJ = (g.nJ + f.tj - 1) / f.tj;
-    if (lk <= 0) {
-        // Planes per CTA: every chunk re-stages 2 halo planes (efficiency lk/(lk+2)) and the grid should fill
-        // whole waves of sm_count*minb resident CTAs (148 SMs on B200).  Score both and take the best.
-        const long long tiles = (long long)f.tilesI * f.tilesJ;
-        const long long resident = (long long)sm_count * f.minb;
-        double best = -1.;
-        const int nown = g.kown1 - g.kown0;
-        for (int c = 1; c <= nown; ++c) {
-            const int l = (nown + c - 1) / c;
-            if (l < 8 && c > 1) break;
-            const long long ctas = tiles * ((nown + l - 1) / l);
-            const long long waves = (ctas + resident - 1) / resident;
-            const double eff = (double)ctas / (double)(waves * resident) * (double)l / (double)(l + 2);
-            if (eff > best + 1e-9) { best = eff; lk = l; }
-        }
+    plan_chunks(g.kown1 - g.kown0, f.tilesI * f.tilesJ, sm_count * f.minb, lk, f.ck);
+    f.lk = f.ck.lkmax;
+    f.chunksK = f.ck.n;
+    if (getenv("PFEM_DEBUG_PLAN")) {
+        fprintf(stderr, "[pfem] fused plan: %d x %d tiles, %d chunks:", f.tilesI, f.tilesJ, f.ck.n);
+        for (int c = 0; c < f.ck.n; ++c) fprintf(stderr, " %d", f.ck.off[c + 1] - f.ck.off[c]);
+        fprintf(stderr, "\n");
     }
-    if (lk > 510) lk = 510;   // <= 8 KB of staged layer spacings per CTA
-    f.lk = lk;
-    f.chunksK = (g.kown1 - g.kown0 + lk - 1) / lk;
     if ((g.sJ * 8) % 16 != 0 || (g.sK * 8) % 16 != 0) { snprintf(f.why, sizeof f.why, "row pitch is not a multiple of 16 bytes"); return f; }
     const int bw = 32 + 4, bh = f.tj + 2;
     bool ok = true;
@@ -535,6 +674,7 @@ static inline FusedPlan make_fused_plan(const Grid& g, int sm_count, double* con
          make_lattice_map(&f.m_cl, cl, g.nI - 1, g.nJ - 1, g.nK - 1, g.sJ, g.sK, bw, bh) &&
          make_lattice_map(&f.m_cv, cv, g.nI - 1, g.nJ - 1, g.nK - 1, g.sJ, g.sK, bw, bh);
     if (!ok) { snprintf(f.why, sizeof f.why, "cuTensorMapEncodeTiled failed or is unavailable"); return f; }
+    f.pdl = getenv("PFEM_NO_PDL") == nullptr;
     f.valid = true;
     return f;
 }
@@ -552,7 +692,18 @@ static inline cudaError_t launch_fused_inst2(const FusedPlan& f, const Grid& g, 
         attr_done[dev & 63] = smem;
     }
     dim3 grid(f.tilesI, f.tilesJ, f.chunksK), block(32, TJ / RJ, 1);
-    k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE, ISO><<<grid, block, smem, st>>>(f.m_r[par], f.m_q[par], f.m_p[par], f.m_d, f.m_cl, f.m_cv, g, f.lk,
+    if (MODE >= 1 && f.pdl) {   // programmatic dependent launch (see the kernel prologue); also valid inside stream capture
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE, ISO>, f.m_r[par], f.m_q[par], f.m_p[par], f.m_d, f.m_cl, f.m_cv, g,
+                                  f.ck, r_out, q_out, p_out, x, sc, partials, po, ca);
+    }
+    k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE, ISO><<<grid, block, smem, st>>>(f.m_r[par], f.m_q[par], f.m_p[par], f.m_d, f.m_cl, f.m_cv, g, f.ck,
                                                                 r_out, q_out, p_out, x, sc, partials, po, ca);
     return cudaGetLastError();
 }

@@ -222,6 +222,29 @@ int pfem_solve_thermal(pfem_ctx* ctx, const pfem_opts* opts, pfem_stats* stats);
  * including loadConductivity before and saveConductivity after it. */
 int pfem_solve_shockley(pfem_ctx* ctx, const pfem_opts* opts, pfem_stats* stats);
 
+/* ---- Dynamic3D: thermal.dynamic.Dynamic3D --------------------------------------------------------------
+ * Volumetric heat capacity per material id on the temperature grid of pfem_set_materials:
+ * cp_dens[nmat][nT] = material->cp(T) * material->dens(T)  [J/(m^3 K)]  (femT3d.cpp:176). */
+int pfem_set_capacity(pfem_ctx* ctx, uint32_t nmat, uint32_t nT, const double* cp_dens);
+typedef struct {
+    double time;         /* ns to advance in this call (argument of compute, femT3d.cpp:258)                              */
+    double timestep;     /* ns, <loop timestep=...> (:57)                                                                 */
+    double methodparam;  /* theta of the time scheme: 0.5 Crank-Nicolson (default), 1 backward Euler (:63,203-204)        */
+    int lumping;         /* != 0: lumped capacity matrix (default, :207-212); 0: consistent (:216-231, kernel variant 1)  */
+    int rebuildfreq;     /* steps between re-evaluations of k(T), cp(T) dens(T); 0 = only at the start of the call (:274) */
+    double* maxT_log;    /* host array (may be NULL): max T after step i, i < maxT_log_len (the LOG_RESULT of :287-291)    */
+    size_t maxT_log_len;
+    int reserved[4];
+} pfem_dynamic;
+/* The time loop of DynamicThermalFem3DSolver::compute (femT3d.cpp:258-305) on the device, one PCG solve per step (warm start
+ * from T^n like A.solverhs(T, temperatures), :283), with the CORRECTED update (the reference overwrites the
+ * solution with the right-hand side, :287, and leaves the Dirichlet rows in B, :203-204,236):
+ *   (theta K + C/dt) T^{n+1} = (C/dt - (1 - theta) K) T^n + F  on the free rows,  T^{n+1} = value on the Dirichlet rows.
+ * The field (pfem_set_field / pfem_fill_field = inittemp, :82) is advanced in place; stats: outer_loops = steps done,
+ * lin_iters = PCG iterations of all steps, maxval = max T.  opts->precond 0 or 1, opts->variant 3 (lumped) or 1.
+ * The caller keeps the elapsed time (elapstime, :293,297). */
+int pfem_solve_dynamic(pfem_ctx* ctx, const pfem_opts* opts, const pfem_dynamic* dyn, pfem_stats* stats);
+
 /* ---- results ------------------------------------------------------------------------- */
 int pfem_get_field(pfem_ctx* ctx, double* x);  /* temperatures / potential, N doubles */
 

@@ -440,6 +440,59 @@ class Context {
         }
         return r;
     }
+
+    // ---- Dynamic3D (thermal.dynamic.Dynamic3D, femT3d.cpp) ----------------------------------------------
+    // cp(T)*dens(T) per material id on the temperature grid of the Tables given to set_materials (femT3d.cpp:176)
+    void set_capacity(const Tables& t, const std::vector<double>& cp_dens) {
+        if (cp_dens.size() != (size_t)t.nmat * t.nT) throw BadInput(id_ + ": capacity table must be [nmat][nT]");
+        check(pfem_set_capacity(ctx_, t.nmat, t.nT, cp_dens.data()));
+    }
+    struct TimeResult { int steps; double maxT; long long lin_iters; double ms; };
+    // The time loop of DynamicThermalFem3DSolver::compute(time) (femT3d.cpp:258-305, corrected update — plaskfem_cuda.h).
+    // `elapstime` is advanced like :293,297 (steps * timestep - timestep: the loop makes time/timestep + 1 solves while the clock
+    // shows `time`); every `logfreq` steps the LOG_RESULT line of :287-291 goes to `log`.
+    TimeResult solve_dynamic(IterParams& ip, double time, double timestep, double methodparam, bool lumping, int rebuildfreq,
+                             int logfreq, double& elapstime, const LogFn& log = LogFn()) {
+        pfem_opts o;
+        pfem_default_opts(&o);
+        o.maxit = ip.maxit; o.lin_tol = ip.maxerr; o.precond = (int)ip.preconditioner;
+        if (!lumping) o.variant = 1;     // the consistent capacity matrix runs the node-per-thread operator kernel
+        pfem_dynamic d;
+        memset(&d, 0, sizeof d);
+        d.time = time; d.timestep = timestep; d.methodparam = methodparam; d.lumping = lumping ? 1 : 0; d.rebuildfreq = rebuildfreq;
+        std::vector<double> maxlog;
+        if (log && logfreq > 0) {
+            maxlog.resize((size_t)((time + timestep / 2.) / timestep) + 2);
+            d.maxT_log = maxlog.data(); d.maxT_log_len = maxlog.size();
+        }
+        pfem_stats st;
+        int rc = pfem_solve_dynamic(ctx_, &o, &d, &st);
+        check(rc);
+        ip.converged = st.converged != 0; ip.iters = st.last_iters; ip.err = st.lin_relres;
+        if (rc == PFEM_NOT_CONVERGED) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "Failed to converge in %d iterations (error %g)", ip.maxit, ip.err);
+            switch (ip.no_convergence_behavior) {
+                case IterParams::NO_CONVERGENCE_ERROR: throw ComputationError(id_ + ": " + buf);
+                case IterParams::NO_CONVERGENCE_WARNING: if (log) log(1, buf); break;
+                case IterParams::NO_CONVERGENCE_CONTINUE: if (log) log(4, buf); break;
+            }
+        }
+        if (log && logfreq > 0) {
+            int l = logfreq;
+            for (int i = 0; i < st.outer_loops && (size_t)i < maxlog.size(); ++i) {
+                if (l == 0) {
+                    char buf[120];
+                    snprintf(buf, sizeof buf, "Time %.2f ns: max(T) = %.3f K", elapstime + i * timestep, maxlog[(size_t)i]);
+                    log(3, buf);
+                    l = logfreq;
+                }
+                --l;
+            }
+        }
+        elapstime += st.outer_loops * timestep - (st.outer_loops ? timestep : 0.);
+        return TimeResult{st.outer_loops, st.maxval, st.lin_iters, st.t_solve_ms};
+    }
 };
 
 }  // namespace plaskfem

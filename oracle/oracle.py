@@ -452,6 +452,140 @@ class Static3DOracle:
 # ------------------------------------------------------------------------- Shockley3D
 
 
+def table_lookup(tab, mat, T0, dT, T):
+    """numpy twin of table_at (fem3d_oracle.c:115-125): linear interpolation, clamped at both ends"""
+    tab = np.asarray(tab)
+    nT = tab.shape[1]
+    t = np.clip((np.asarray(T, dtype=np.float64) - T0) / dT, 0., float(nT - 1))
+    i = np.minimum(t.astype(np.int64), nT - 2)
+    f = t - i
+    a, b = tab[mat, i], tab[mat, i + 1]
+    return a + f * (b - a)
+
+
+class Dynamic3DOracle:
+    """DynamicThermalFem3DSolver restated (solvers/thermal/dynamic/femT3d.cpp) as a CORRECTED specification — test infrastructure.
+
+    setMatrix (:127-255) is followed to the letter: A = methodparam*K + C, B = -(1-methodparam)*K + C with the brick stiffness K
+    (:186-199, the same as therm3d.cpp:226-237), the element capacity c = cp*dens*0.125e-9*dx*dy*dz/timestep (:176), lumped
+    (:207-212) or consistent (:216-231), F = 0.125e-18*dx*dy*dz*heat (:179,204), conductivities and capacities at the mean of the
+    8 node temperatures (:163).  The time loop (:271-295) is corrected in two places, because as written it cannot be a parity
+    target: (i) `std::swap(temperatures, X)` (:287) replaces the solution by the right-hand side for the iterative algorithm
+    (the 2-D twin femT2d.cpp:424-428 has no such line); (ii) only A and F are eliminated on the Dirichlet rows (:236) while
+    B.mult keeps them (:279), so a fixed node would receive value + (B T)_r.  Here
+        A T^{n+1} = B T^n + F on the free rows,   T^{n+1} = value on the Dirichlet rows
+    with the sparse system solved directly (SuperLU).  Pinned by the analytic 1-D cooling test (tests/test_oracle_dynamic.py)."""
+
+    def __init__(self, mesh, elem_mat, tables, cprho, dirichlet_nodes, dirichlet_values, heat=None, inittemp=300.,
+                 timestep=0.1, methodparam=0.5, lumping=True, rebuildfreq=0):
+        import scipy.sparse as sp  # noqa: F401  (fail early if scipy is missing)
+        self.mesh, self.tables = mesh, tables
+        self.elem_mat = np.ascontiguousarray(elem_mat, dtype=np.uint32)
+        self.cprho = np.ascontiguousarray(cprho, dtype=np.float64)
+        self.bc_nodes = np.ascontiguousarray(dirichlet_nodes, dtype=np.int64)
+        self.bc_values = np.ascontiguousarray(dirichlet_values, dtype=np.float64)
+        self.heat = np.zeros(mesh.E) if heat is None else np.ascontiguousarray(heat, dtype=np.float64)
+        self.inittemp, self.timestep, self.methodparam = float(inittemp), float(timestep), float(methodparam)
+        self.lumping, self.rebuildfreq = bool(lumping), int(rebuildfreq)
+        self.temperatures = np.full(mesh.N, float(inittemp))    # :82
+        self.elapstime = 0.          # the reference's clock: advanced by steps*timestep - timestep per call (:293,297)
+        self.physical_time = 0.      # time the field really advanced: one timestep per solve
+        self.conds = np.zeros((mesh.E, 2))
+        self.maxT_log = []
+        m = mesh
+        eg = m.elems_grid().ravel()
+        i0, i1, i2 = np.meshgrid(*[np.arange(k - 1) for k in m.n], indexing="ij")
+        base = (i0 * m.ns[0] + i1 * m.ns[1] + i2 * m.ns[2]).ravel()
+        # idx[l]: bit 0 -> axis 0, bit 1 -> axis 1, bit 2 -> axis 2 (:143-151)
+        self._idx = np.empty((m.E, 8), dtype=np.int64)
+        for l in range(8):
+            self._idx[eg, l] = base + (l & 1) * m.ns[0] + ((l >> 1) & 1) * m.ns[1] + ((l >> 2) & 1) * m.ns[2]
+        d = [np.diff(a) for a in m.axes]
+        self._dx = np.empty(m.E); self._dy = np.empty(m.E); self._dz = np.empty(m.E)
+        self._dx[eg] = np.broadcast_to(d[0][:, None, None], i0.shape).ravel()
+        self._dy[eg] = np.broadcast_to(d[1][None, :, None], i0.shape).ravel()
+        self._dz[eg] = np.broadcast_to(d[2][None, None, :], i0.shape).ravel()
+
+    def set_matrix(self):
+        """setMatrix, femT3d.cpp:127-255 -> (A, B, F) as scipy CSR / vector, before the Dirichlet elimination"""
+        import scipy.sparse as sp
+        m, t = self.mesh, self.tables
+        lib().orc_thermal_conds(m.ref, _p(self.temperatures), _p(self.elem_mat, C.c_uint32), C.c_uint32(t.nT),
+                                C.c_double(t.T0), C.c_double(t.dT), _p(t.lat), _p(t.vert), _p(self.conds))
+        dx, dy, dz = self._dx, self._dy, self._dz
+        ky = self.conds[:, 0] * 1e-6
+        kz = self.conds[:, 1] * 1e-6
+        kx = ky / dx * dy * dz                 # :170-172
+        ky = ky * dx / dy * dz
+        kz = kz * dx * dy / dz
+        kv = np.empty((m.E, 8))                # K[i][j] by i ^ j (:186-199)
+        kv[:, 0] = (kx + ky + kz) / 9.
+        kv[:, 1] = (-2. * kx + ky + kz) / 18.
+        kv[:, 2] = (kx - 2. * ky + kz) / 18.
+        kv[:, 4] = (kx + ky - 2. * kz) / 18.
+        kv[:, 6] = (kx - 2. * ky - 2. * kz) / 36.
+        kv[:, 5] = (-2. * kx + ky - 2. * kz) / 36.
+        kv[:, 3] = (-2. * kx - 2. * ky + kz) / 36.
+        kv[:, 7] = -(kx + ky + kz) / 36.
+        temp = self.temperatures[self._idx].sum(axis=1) * 0.125       # :163
+        c = table_lookup(self.cprho, self.elem_mat, t.T0, t.dT, temp) * 0.125e-9 * dx * dy * dz / self.timestep   # :176
+        f = 0.125e-18 * dx * dy * dz * self.heat                       # :179
+        rows, cols, ka, cm = [], [], [], []
+        pop = np.array([bin(x).count("1") for x in range(8)])
+        for i in range(8):
+            for j in range(8):
+                rows.append(self._idx[:, i]); cols.append(self._idx[:, j]); ka.append(kv[:, i ^ j])
+                if self.lumping:
+                    cm.append(c if i == j else np.zeros_like(c))                  # :207-212
+                else:
+                    cm.append(c * (8 >> pop[i ^ j]) / 27.)                        # :216-231
+        rows, cols = np.concatenate(rows), np.concatenate(cols)
+        K = sp.coo_matrix((np.concatenate(ka), (rows, cols)), shape=(m.N, m.N)).tocsr()
+        Cm = sp.coo_matrix((np.concatenate(cm), (rows, cols)), shape=(m.N, m.N)).tocsr()
+        F = np.zeros(m.N)
+        np.add.at(F, self._idx.ravel(), np.repeat(f, 8))
+        th = self.methodparam
+        return (th * K + Cm).tocsr(), (-(1. - th) * K + Cm).tocsr(), F     # :203-204
+
+    def _factor(self):
+        import scipy.sparse as sp
+        import scipy.sparse.linalg as spl
+        A, B, F = self.set_matrix()
+        fixed = np.zeros(self.mesh.N, dtype=bool)
+        fixed[self.bc_nodes] = True
+        xD = np.zeros(self.mesh.N)
+        xD[self.bc_nodes] = self.bc_values            # last value wins for duplicated nodes
+        free = ~fixed
+        Aff = A[free][:, free].tocsc()
+        lift = A[free][:, fixed] @ xD[fixed]           # applyBC: F[c] -= A(c,r) * value (:236)
+        return dict(solve=spl.factorized(Aff), B=B, F=F, free=free, fixed=fixed, xD=xD, lift=lift)
+
+    def compute(self, time):
+        """compute(time), femT3d.cpp:258-305 with the corrected update"""
+        sysm = self._factor()
+        r = self.rebuildfreq
+        tend = time + self.timestep / 2.
+        t = 0.
+        while t < tend:
+            if self.rebuildfreq and r == 0:
+                sysm = self._factor()
+                r = self.rebuildfreq
+            rhs = sysm["B"] @ self.temperatures + sysm["F"]
+            free = sysm["free"]
+            Tn = np.empty_like(self.temperatures)
+            Tn[free] = sysm["solve"](rhs[free] - sysm["lift"])
+            Tn[sysm["fixed"]] = sysm["xD"][sysm["fixed"]]
+            self.temperatures = Tn
+            self.maxT_log.append(float(Tn.max()))
+            r -= 1
+            self.elapstime += self.timestep
+            self.physical_time += self.timestep
+            t += self.timestep
+        self.elapstime -= self.timestep            # :297 — the loop runs time/timestep + 1 solves, the clock shows `time`
+        self.maxT = float(self.temperatures.max())
+        return 0.
+
+
 class Shockley3DOracle:
     """ElectricalFem3DSolver + BetaSolver<Geometry3D> restated
     (solvers/electrical/shockley/electr3d.cpp, beta.hpp)."""

@@ -56,6 +56,11 @@ class Stats(C.Structure):
                     lin_relres_precond=self.lin_relres_precond)
 
 
+class Dynamic(C.Structure):
+    _fields_ = [("time", C.c_double), ("timestep", C.c_double), ("methodparam", C.c_double), ("lumping", C.c_int),
+                ("rebuildfreq", C.c_int), ("maxT_log", c_dp), ("maxT_log_len", c_sz), ("reserved", C.c_int * 4)]
+
+
 # every symbol include/plaskfem_cuda.h declares: name -> (restype, argtypes)
 _vp = C.c_void_p
 _u32p = C.POINTER(C.c_uint32)
@@ -86,6 +91,8 @@ SYMBOLS = {
     "pfem_default_opts": (None, [C.POINTER(Opts)]),
     "pfem_solve_thermal": (C.c_int, [_vp, C.POINTER(Opts), C.POINTER(Stats)]),
     "pfem_solve_shockley": (C.c_int, [_vp, C.POINTER(Opts), C.POINTER(Stats)]),
+    "pfem_set_capacity": (C.c_int, [_vp, C.c_uint32, C.c_uint32, c_dp]),
+    "pfem_solve_dynamic": (C.c_int, [_vp, C.POINTER(Opts), C.POINTER(Dynamic), C.POINTER(Stats)]),
     "pfem_get_field": (C.c_int, [_vp, c_dp]),
     "pfem_interpolate_field": (C.c_int, [_vp, _szp, c_dp, c_dp, c_dp, _szp, c_dp]),
     "pfem_get_elem": (C.c_int, [_vp, C.c_int, _u8p, c_dp]),

@@ -60,6 +60,7 @@ class Problem:
     start_cond: tuple = (0., 5.)
     Te: float = 300.
     empty: np.ndarray = None       # uint8 [E]: material kind EMPTY (the elements empty-elements="exclude" drops)
+    tab_cprho: np.ndarray = None   # [nmat][nT] cp(T)*dens(T), J/(m^3 K) (Dynamic3D); None -> capacity_tables() of the thermal ids
     meta: dict = field(default_factory=dict)
 
     @property
@@ -146,6 +147,14 @@ def thermal_tables(T0=250., dT=0.25, nT=1601):
               M.thermk_GaAs, lambda T: M.thermk_AlGaAs(T, 0.73), M.thermk_GaAs, lambda T: M.thermk_AlGaAs(T, 0.73),
               M.thermk_GaAs]
     return M.sample_tables(models, T0, dT, nT)
+
+
+def capacity_tables(T0=250., dT=0.25, nT=1601):
+    """cp(T)*dens(T) per material id of thermal_tables (Dynamic3D, femT3d.cpp:176)"""
+    gaas, algaas = M.cpdens_GaAs, lambda T: M.cpdens_AlGaAs(T, 0.73)
+    models = [gaas, algaas, gaas, M.cpdens_const(880., 3950.), M.cpdens_const(129., 19300.), M.cpdens_const(385., 8960.),
+              M.cpdens_const(1005., 1.2), gaas, algaas, gaas, algaas, gaas]
+    return M.sample_table1(models, T0, dT, nT)
 
 
 def electrical_tables(T0=250., dT=0.25, nT=1601):

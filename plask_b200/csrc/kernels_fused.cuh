@@ -75,13 +75,15 @@ struct FusedTile {
 // iteration (kernels_line.cuh): boxes z, p, mask instead of r, q, p, D^-1 — p' = mask z + beta p, x' = x + alpha p, q' = M A p'.
 // ISO: c_lat == c_vert in every element (bulk materials: thermk returns the same lateral and vertical value, e.g. GaAs.cpp:225-228):
 // the c_vert layer is not loaded at all — 10 instead of 11 words per DOF.
-template <int TJ, int RJ, int NS, int MINB, int VDIM, int MODE, bool ISO = false>
+// MASS: the operator is A + diag(mass) — the time step of Dynamic3D with a lumped capacity matrix (femT3d.cpp:203-212;
+// the conductivities arrive scaled by methodparam); mass is read for the own nodes only, one step ahead of its use.
+template <int TJ, int RJ, int NS, int MINB, int VDIM, int MODE, bool ISO = false, bool MASS = false>
 __global__ void __launch_bounds__(32 * (TJ / RJ), MINB)
 k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_q,
        const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_d,
        const __grid_constant__ CUtensorMap tm_cl, const __grid_constant__ CUtensorMap tm_cv, const Grid g, const ChunkTab ck,
        double* __restrict__ r_out, double* __restrict__ q_out, double* __restrict__ p_out, double* __restrict__ x,
-       Scalars* sc, double* partials, const PeerOut po, const CoarseAdd ca) {
+       Scalars* sc, double* partials, const PeerOut po, const CoarseAdd ca, const double* __restrict__ mass) {
     typedef FusedTile<TJ> T;
     constexpr int TI = T::TI, HX = T::HX, PW = T::PW, PH = T::PH, BOX = T::BOX, BOXP = T::BOXP, PWP = T::PWP;
     constexpr int PLANE = T::PLANE, CW = T::CW, CHALF = T::CHALF, LAYER = T::LAYER, NRED = T::NRED;
@@ -270,6 +272,9 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
     double xn[RJ];
 #pragma unroll
     for (int rr = 0; rr < RJ; ++rr) xn[rr] = 0.;
+    double mprev[RJ];   // MASS: capacity diagonal of the own nodes of the plane below (loaded when that plane was the current one)
+#pragma unroll
+    for (int rr = 0; rr < RJ; ++rr) mprev[rr] = 0.;
 
     // OWN: plane P = k0-1+t is owned (store r', p', x');  NEXT_OWN: plane P+1 is owned (prefetch x)
     // GATHER: t >= 1 (element layer P-1 exists);  FINAL: plane P-1 is owned (store q', dots)
@@ -290,6 +295,11 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
 #pragma unroll
             for (int rr = 0; rr < RJ; ++rr)
                 if (vj[rr]) xn[rr] = x[nown[rr] + sK];
+        }
+        double mcur[RJ];   // MASS: capacity diagonal of plane P (used by the next step)
+        if (MASS) {
+#pragma unroll
+            for (int rr = 0; rr < RJ; ++rr) mcur[rr] = (OWN && vj[rr]) ? mass[nown[rr]] : 0.;
         }
         const double hk = sHK[t], rk = sHK[lk + 2 + t];   // element layer L = P - 1 of this step (t >= 1)
         mbar_wait(&bars[st], (uint32_t)((t / NS) & 1));
@@ -425,7 +435,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
                 if (FINAL) {
                     if (vj[rr]) {       // finalise the plane below
                         const double da = zda[RJ + rr];
-                        const double qv = (da == 0.) ? 0. : carry[rr] + lo;
+                        const double qv = (da == 0.) ? 0. : MASS ? fma(mprev[rr], wa[yc][1], carry[rr] + lo) : carry[rr] + lo;
                         q_out[nown[rr] - sK] = qv;
                         if (slab && !LINE) {   // the line-Jacobi iteration reads q on owned rows only
                             const int Pa = k0 - 2 + t;
@@ -445,6 +455,10 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         }
 #pragma unroll
         for (int rr = 0; rr < RJ; ++rr) nown[rr] += sK;
+        if (MASS) {
+#pragma unroll
+            for (int rr = 0; rr < RJ; ++rr) mprev[rr] = mcur[rr];
+        }
     };
 
     if (MLZ) {   // written by the level kernels of this iteration: after pdl wait
@@ -632,6 +646,7 @@ static inline void plan_chunks(int nown, int tiles, int resident, int fixed_lk, 
 struct FusedPlan {
     bool valid;
     bool iso;            // launch the ISO instantiation (set per launch by the host: c_lat == c_vert everywhere)
+    const double* mass;  // non-null: launch the MASS instantiation (Dynamic3D time step, lumped capacity diagonal)
     bool pdl;            // launch the iteration kernels with programmatic stream serialization (PFEM_NO_PDL=1 turns it off)
     int tj, rj, ns, minb;
     int lk, tilesI, tilesJ, chunksK;
@@ -679,7 +694,7 @@ static inline FusedPlan make_fused_plan(const Grid& g, int sm_count, double* con
     return f;
 }
 
-template <int TJ, int RJ, int NS, int MINB, int VDIM, int MODE, bool ISO>
+template <int TJ, int RJ, int NS, int MINB, int VDIM, int MODE, bool ISO, bool MASS = false>
 static inline cudaError_t launch_fused_inst2(const FusedPlan& f, const Grid& g, int par, double* r_out, double* q_out, double* p_out,
                                             double* x, Scalars* sc, double* partials, const PeerOut& po, cudaStream_t st, const CoarseAdd& ca) {
     const size_t smem = FusedTile<TJ>::smem_bytes(NS, MODE, f.lk, ISO);
@@ -687,7 +702,7 @@ static inline cudaError_t launch_fused_inst2(const FusedPlan& f, const Grid& g, 
     int dev = 0;
     cudaGetDevice(&dev);
     if (attr_done[dev & 63] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE, ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE, ISO, MASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done[dev & 63] = smem;
     }
@@ -700,11 +715,11 @@ static inline cudaError_t launch_fused_inst2(const FusedPlan& f, const Grid& g, 
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE, ISO>, f.m_r[par], f.m_q[par], f.m_p[par], f.m_d, f.m_cl, f.m_cv, g,
-                                  f.ck, r_out, q_out, p_out, x, sc, partials, po, ca);
+        return cudaLaunchKernelEx(&cfg, k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE, ISO, MASS>, f.m_r[par], f.m_q[par], f.m_p[par], f.m_d, f.m_cl, f.m_cv, g,
+                                  f.ck, r_out, q_out, p_out, x, sc, partials, po, ca, f.mass);
     }
-    k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE, ISO><<<grid, block, smem, st>>>(f.m_r[par], f.m_q[par], f.m_p[par], f.m_d, f.m_cl, f.m_cv, g, f.ck,
-                                                                r_out, q_out, p_out, x, sc, partials, po, ca);
+    k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE, ISO, MASS><<<grid, block, smem, st>>>(f.m_r[par], f.m_q[par], f.m_p[par], f.m_d, f.m_cl, f.m_cv, g, f.ck,
+                                                                      r_out, q_out, p_out, x, sc, partials, po, ca, f.mass);
     return cudaGetLastError();
 }
 
@@ -712,6 +727,10 @@ static inline cudaError_t launch_fused_inst2(const FusedPlan& f, const Grid& g, 
 template <int TJ, int RJ, int NS, int MINB, int VDIM, int MODE>
 static inline cudaError_t launch_fused_inst(const FusedPlan& f, const Grid& g, int par, double* r_out, double* q_out, double* p_out,
                                             double* x, Scalars* sc, double* partials, const PeerOut& po, cudaStream_t st, const CoarseAdd& ca) {
+    if constexpr ((MODE == 1 || MODE == 2) && TJ == 8 && RJ == 2 && NS == 2 && MINB == 3) {   // Dynamic3D: general-conductivity kernel + capacity diagonal
+        if (f.mass) return launch_fused_inst2<TJ, RJ, NS, MINB, VDIM, MODE, false, true>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st, ca);
+    }
+    if (f.mass) return cudaErrorInvalidConfiguration;
     if constexpr (MODE >= 1 && TJ == 8 && RJ == 2 && MINB == 3) {
         if (f.iso) return launch_fused_inst2<TJ, RJ, NS, MINB, VDIM, MODE, true>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st, ca);
     }

@@ -17,11 +17,15 @@ namespace pfem {
 // MODE 2: out = M (f - A in),  partials out.out -> bb, out.D^-1 out -> bz   (norms of the lifted rhs)
 // MODE 3: out = M (A in), no reduction, ignores sc->done        (tests: plain operator)
 // M masks Dirichlet rows (dinv == 0).  `in` must be 0 on Dirichlet nodes for MODE 0/3.
+// Dynamic3D (solvers/thermal/dynamic/femT3d.cpp:176,205-231): the operator of a time step is theta*K + C/dt.  The caller
+// passes theta-scaled conductivities; `mass` (node array, may be null) is the lumped capacity diagonal, `cmass` (element
+// lattice, may be null) the element capacity c of the consistent matrix C_e = c * (8,4,2,1)/27 by the number of differing axes.
 template <int MODE>
 __global__ void __launch_bounds__(PFEM_NODE_BLOCK_X* PFEM_NODE_BLOCK_Y)
 k_apply_simple(const Grid g, const double* __restrict__ cl, const double* __restrict__ cv,
                const double* __restrict__ in, const double* __restrict__ dinv, const double* __restrict__ f,
-               double* __restrict__ out, Scalars* sc, double* partials) {
+               double* __restrict__ out, Scalars* sc, double* partials, const double* __restrict__ mass = nullptr,
+               const double* __restrict__ cmass = nullptr) {
     __shared__ double sh[64];
     __shared__ int sh_flag;
     if (MODE == 0 && sc->done) return;
@@ -49,6 +53,11 @@ k_apply_simple(const Grid g, const double* __restrict__ cl, const double* __rest
                     double kI, kJ, kK, kv[8];
                     elem_conductances(g, cl[slot], cv[slot], i + di, j + dj, k + dk, kI, kJ, kK);
                     elem_matrix8(kI, kJ, kK, kv);
+                    if (cmass) {
+                        const double c = cmass[slot] * (1. / 27.);
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) kv[x] += c * (double)(8 >> __popc(x));
+                    }
                     // this node is local corner (-di,-dj,-dk) of the element
 #pragma unroll
                     for (int l = 0; l < 8; ++l) {
@@ -57,6 +66,7 @@ k_apply_simple(const Grid g, const double* __restrict__ cl, const double* __rest
                         acc += kv[x] * P[dk + bk + 1][dj + bj + 1][di + bi + 1];
                     }
                 }
+        if (mass) acc = fma(mass[n], P[1][1][1], acc);
         const double dn = dinv[n];
         const bool fixed = (dn == 0.);
         double o;
@@ -85,7 +95,8 @@ k_apply_simple(const Grid g, const double* __restrict__ cl, const double* __rest
 // Diagonal of the eliminated matrix: sum over the 8 adjacent elements of (kI+kJ+kK)/9
 // (therm3d.cpp:227); dinv = 0 marks Dirichlet rows (and rows with an empty diagonal).
 __global__ void k_diag(const Grid g, const double* __restrict__ cl, const double* __restrict__ cv,
-                       const uint8_t* __restrict__ fixed, double* __restrict__ dinv, Scalars* sc) {
+                       const uint8_t* __restrict__ fixed, double* __restrict__ dinv, Scalars* sc,
+                       const double* __restrict__ mass = nullptr, const double* __restrict__ cmass = nullptr) {
     const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
     const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
     const int k = blockIdx.z;
@@ -102,7 +113,9 @@ __global__ void k_diag(const Grid g, const double* __restrict__ cl, const double
                 double kI, kJ, kK;
                 elem_conductances(g, cl[slot], cv[slot], i + di, j + dj, k + dk, kI, kJ, kK);
                 d += (kI + kJ + kK) * (1. / 9.);
+                if (cmass) d += cmass[slot] * (8. / 27.);
             }
+    if (mass) d += mass[n];
     if (!fixed[n] && d < 0.) sc->neg_diag = 1;
     dinv[n] = (fixed[n] || !(d > 0.)) ? 0. : 1. / d;
 }
@@ -390,6 +403,62 @@ __global__ void k_cond_thermal(const Grid g, const double* __restrict__ T, const
     if (m == PFEM_MAT_EXCLUDED) { cl[n] = 0.; cv[n] = 0.; return; }   // element outside the masked mesh
     cl[n] = table_at(tab_lat, m, nT, T0, dT, temp);
     cv[n] = table_at(tab_vert, m, nT, T0, dT, temp);
+}
+
+// ------------------------------------------------------- Dynamic3D (femT3d.cpp) -----------
+
+// Element capacity c = cp(T_e)*dens(T_e) * 0.125e-9 * dx*dy*dz / timestep (femT3d.cpp:176) with T_e the mean of the 8 node
+// temperatures (:163) and cp*dens from the per-material table; elements outside the masked mesh carry none.
+// lumped != 0: the value each of the 8 nodes receives on its diagonal (:207-212); else the c of the consistent matrix
+// (:216-231), whose entries are c*(8,4,2,1)/27.
+__global__ void k_elem_capacity(const Grid g, const double* __restrict__ T, const uint32_t* __restrict__ mat, uint32_t nT,
+                                double T0, double dT, const double* __restrict__ tab_cprho, double inv_timestep,
+                                double* __restrict__ ce) {
+    const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
+    const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= g.nI || j >= g.nJ) return;
+    const idx_t n = i + g.sJ * j + g.sK * k;
+    int pi[3];
+    if (!elem_slot(g, i, j, k, pi)) { ce[n] = 0.; return; }
+    const uint32_t m = mat[n];
+    if (m == PFEM_MAT_EXCLUDED) { ce[n] = 0.; return; }
+    double temp = 0.;
+#pragma unroll
+    for (int l = 0; l < 8; ++l)
+        temp = __dadd_rn(temp, T[n + ((l & 1) ? g.ps[0] : 0) + ((l & 2) ? g.ps[1] : 0) + ((l & 4) ? g.ps[2] : 0)]);
+    temp *= 0.125;
+    ce[n] = table_at(tab_cprho, m, nT, T0, dT, temp) * 0.125e-9 * g.hI[i] * g.hJ[j] * g.hK[k] * inv_timestep;
+}
+
+// lumped capacity diagonal: mass[node] = sum of c over the 8 adjacent elements (femT3d.cpp:207-212)
+__global__ void k_mass_lumped(const Grid g, const double* __restrict__ ce, double* __restrict__ mass) {
+    const int i = blockIdx.x * PFEM_NODE_BLOCK_X + threadIdx.x;
+    const int j = blockIdx.y * PFEM_NODE_BLOCK_Y + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= g.nI || j >= g.nJ) return;
+    const idx_t n = i + g.sJ * j + g.sK * k;
+    double s = 0.;
+#pragma unroll
+    for (int dk = -1; dk <= 0; ++dk)
+#pragma unroll
+        for (int dj = -1; dj <= 0; ++dj)
+#pragma unroll
+            for (int di = -1; di <= 0; ++di) s += ce[n + di + g.sJ * dj + g.sK * dk];
+    mass[n] = s;
+}
+
+// out = a + b: the right-hand side of a time step, B T + F = M (F - K T) + M (A T) with B = A - K (femT3d.cpp:203-204,279-280)
+__global__ void k_axpby(idx_t N, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+    for (idx_t n = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; n < N; n += (idx_t)gridDim.x * blockDim.x) out[n] = a[n] + b[n];
+}
+
+__global__ void k_scale2(idx_t N, double s, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ ao,
+                         double* __restrict__ bo) {
+    for (idx_t n = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; n < N; n += (idx_t)gridDim.x * blockDim.x) {
+        ao[n] = s * a[n];
+        bo[n] = s * b[n];
+    }
 }
 
 struct JunctionDev {

@@ -105,6 +105,13 @@ struct pfem_ctx {
     TiledPlan plan;
     TmaPlan tma;
     FusedPlan fused;
+    // Dynamic3D (pfem_solve_dynamic): heat-capacity table, operator extension of the current time step (null outside a call),
+    // scratch arrays allocated on first use
+    double* tab_cprho = nullptr;
+    uint32_t cap_nmat = 0, cap_nT = 0;
+    const double *op_mass = nullptr, *op_cmass = nullptr;
+    double *dyn_mass = nullptr, *dyn_ce = nullptr, *dyn_cl = nullptr, *dyn_cv = nullptr, *dyn_f = nullptr;
+    int graph_mass = -1;
     // slab mode (multi-GPU): this context owns node planes [kown0, kown1) of its local mesh, the rest are halo planes
     int rank = 0, nranks = 1;
     Comm* d_comm = nullptr;
@@ -189,6 +196,8 @@ static void free_all(pfem_ctx* ctx) {
     if (ctx->stage) { cudaFree(ctx->stage); ctx->stage = nullptr; ctx->stage_bytes = 0; }
     ctx->have_mesh = ctx->have_materials = ctx->have_junctions = ctx->conds_valid = false;
     ctx->noheat_set = false;
+    ctx->tab_cprho = nullptr; ctx->cap_nmat = ctx->cap_nT = 0; ctx->op_mass = ctx->op_cmass = nullptr;
+    ctx->dyn_mass = ctx->dyn_ce = ctx->dyn_cl = ctx->dyn_cv = ctx->dyn_f = nullptr; ctx->graph_mass = -1;
 }
 
 template <typename T>
@@ -1302,7 +1311,7 @@ static int launch_ml_chain(pfem_ctx* ctx, const double* r_in, const double* q_in
 
 static int launch_diag(pfem_ctx* ctx) {
     const Grid& g = ctx->g;
-    k_diag<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->cl, ctx->cv, ctx->fixed, ctx->dinv, ctx->d_sc);
+    k_diag<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->cl, ctx->cv, ctx->fixed, ctx->dinv, ctx->d_sc, ctx->op_mass, ctx->op_cmass);
     KCHECK(); LAUNCHED(1);
     if (ctx->surf.nnz) {   // convection adds a face mass matrix (therm3d.cpp:253-257)
         k_surf_diag<<<surf_blocks(ctx), 256, 0, ctx->stream>>>(ctx->surf, ctx->dinv);
@@ -1316,7 +1325,7 @@ template <int MODE>
 static int launch_apply_simple(pfem_ctx* ctx, const double* in, double* out, const double* f = nullptr) {
     const Grid& g = ctx->g;
     k_apply_simple<MODE><<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->cl, ctx->cv, in, ctx->dinv, f ? f : ctx->f, out,
-                                                                          ctx->d_sc, ctx->partials);
+                                                                          ctx->d_sc, ctx->partials, ctx->op_mass, ctx->op_cmass);
     KCHECK(); LAUNCHED(1);
     return PFEM_OK;
 }
@@ -1375,7 +1384,7 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
     if (variant == 1) {
         k_pupdate<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->r, ctx->dinv, ctx->p, ctx->d_sc);
         k_apply_simple<0><<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->cl, ctx->cv, ctx->p, ctx->dinv, ctx->f,
-                                                                         ctx->q, ctx->d_sc, ctx->partials);
+                                                                         ctx->q, ctx->d_sc, ctx->partials, ctx->op_mass, ctx->op_cmass);
         launched += 2;
     } else if (variant == 2) {
         launch_apply_tiled(ctx->plan, g, ctx->cl, ctx->cv, ctx->r, ctx->dinv, pin, pout, ctx->q, ctx->d_sc,
@@ -1401,7 +1410,7 @@ static int kernels_per_iteration(const pfem_ctx* ctx, int variant) {
 
 static int build_graph(pfem_ctx* ctx, int batch, int variant, int precond) {
     if (ctx->graph && ctx->graph_batch == batch && ctx->graph_variant == variant && ctx->graph_precond == precond &&
-        ctx->graph_surf == ctx->surf_iter && ctx->graph_iso == (int)ctx->fused.iso)
+        ctx->graph_surf == ctx->surf_iter && ctx->graph_iso == (int)ctx->fused.iso && ctx->graph_mass == (ctx->op_mass || ctx->op_cmass ? 1 : 0))
         return PFEM_OK;
     if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
     cudaGraph_t graph = nullptr;
@@ -1413,6 +1422,7 @@ static int build_graph(pfem_ctx* ctx, int batch, int variant, int precond) {
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { ctx->graph = nullptr; FAIL(PFEM_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
     ctx->graph_batch = batch; ctx->graph_variant = variant; ctx->graph_precond = precond; ctx->graph_surf = ctx->surf_iter; ctx->graph_iso = (int)ctx->fused.iso;
+    ctx->graph_mass = (ctx->op_mass || ctx->op_cmass) ? 1 : 0;
     return PFEM_OK;
 }
 
@@ -1442,6 +1452,8 @@ static int pcg_prepare(pfem_ctx* ctx, const pfem_opts* o, int bench) {
         static const bool no_iso = getenv("PFEM_NO_ISO") != nullptr;
         ctx->fused.iso = ctx->cond_iso && !no_iso;
         ctx->line_plan.iso = ctx->fused.iso;
+        ctx->fused.mass = ctx->op_mass;           // Dynamic3D time step: operator + lumped capacity diagonal
+        ctx->line_plan.mass = ctx->op_mass;
     }
     k_set_params<<<1, 1, 0, ctx->stream>>>(ctx->d_sc, tol2, o->maxit, bench, ctx->surf_iter, o->precond);
     LAUNCHED(1);
@@ -1514,6 +1526,10 @@ static int check_opts(pfem_ctx* ctx, const pfem_opts* o) {
     if (o->precond >= 1 && ctx->nranks > 1 && ctx->g.vdim == 2)
         FAIL(PFEM_ERR_BAD_INPUT, "slab mode: the line preconditioner needs the vertical axis inside the slabs (a lateral major axis)");
     if (o->variant < 0 || o->variant > 3) FAIL(PFEM_ERR_BAD_INPUT, "unknown kernel variant %d", o->variant);
+    if ((ctx->op_mass || ctx->op_cmass) && o->precond == 2) FAIL(PFEM_ERR_BAD_INPUT, "Dynamic3D: the multilevel preconditioner is not available (use jac or ljac)");
+    if (ctx->op_mass && o->variant != 3 && o->variant != 1) FAIL(PFEM_ERR_BAD_INPUT, "Dynamic3D runs kernel variant 3 (fused) or 1 (simple)");
+    if (ctx->op_cmass && (o->variant != 1 || o->precond != 0))
+        FAIL(PFEM_ERR_BAD_INPUT, "Dynamic3D with a consistent capacity matrix (lumping = no) runs kernel variant 1 with the Jacobi preconditioner only");
     if (o->variant == 3 && !ctx->fused.valid) FAIL(PFEM_ERR_STATE, "fused PCG kernel unavailable: %s", ctx->fused.why);
     if (ctx->nranks > 1 && o->variant != 3) FAIL(PFEM_ERR_BAD_INPUT, "slab mode runs the fused PCG kernel only (variant 3)");
     if (o->variant == 0 && !ctx->tma.valid) FAIL(PFEM_ERR_STATE, "TMA operator kernel unavailable: %s", ctx->tma.why);
@@ -1590,6 +1606,135 @@ extern "C" int pfem_solve_thermal(pfem_ctx* ctx, const pfem_opts* o, pfem_stats*
         st->kernel_launches = ctx->launches - l0;
     }
     return conv ? PFEM_OK : PFEM_NOT_CONVERGED;
+}
+
+// ------------------------------------------------------------------ Dynamic3D ------------
+
+extern "C" int pfem_set_capacity(pfem_ctx* ctx, uint32_t nmat, uint32_t nT, const double* cp_dens) {
+    NEED_MESH();
+    if (!ctx->have_materials) FAIL(PFEM_ERR_STATE, "pfem_set_materials has not been called");
+    if (!cp_dens) FAIL(PFEM_ERR_BAD_INPUT, "null capacity table");
+    if (nmat != ctx->nmat || nT != ctx->nT) FAIL(PFEM_ERR_BAD_INPUT, "the capacity table must have the shape [nmat][nT] of pfem_set_materials (%u x %u)", ctx->nmat, ctx->nT);
+    const size_t cnt = (size_t)nmat * nT;
+    for (size_t a = 0; a < cnt; ++a)
+        if (!(cp_dens[a] > 0.)) FAIL(PFEM_ERR_BAD_INPUT, "heat capacity table entry %zu is not positive", a);
+    dev_release(ctx, &ctx->tab_cprho);
+    TRY(dev_alloc(ctx, &ctx->tab_cprho, cnt, 0));
+    CU(cudaMemcpyAsync(ctx->tab_cprho, cp_dens, cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->cap_nmat = nmat; ctx->cap_nT = nT;
+    return PFEM_OK;
+}
+
+// setMatrix of DynamicThermalFem3DSolver (femT3d.cpp:127-255) in matrix-free form: conductivities and capacities at the current
+// temperatures; ctx->cl/cv become methodparam * k (the stiffness part of A), the unscaled values go to dyn_cl/dyn_cv (the K of
+// B = A - K); the capacity becomes a node diagonal (lumped) or stays an element array (consistent).
+static int dynamic_set_matrix(pfem_ctx* ctx, const pfem_dynamic* d) {
+    const Grid& g = ctx->g;
+    TRY(pfem_update_conductivity_thermal(ctx));
+    CU(cudaMemcpyAsync(ctx->dyn_cl, ctx->cl, (size_t)g.NP * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->dyn_cv, ctx->cv, (size_t)g.NP * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    k_scale2<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, d->methodparam, ctx->dyn_cl, ctx->dyn_cv, ctx->cl, ctx->cv);
+    KCHECK(); LAUNCHED(1);
+    k_elem_capacity<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->x, ctx->mat, ctx->nT, ctx->T0, ctx->dT, ctx->tab_cprho,
+                                                                     1. / d->timestep, ctx->dyn_ce);
+    KCHECK(); LAUNCHED(1);
+    if (d->lumping) {
+        k_mass_lumped<<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->dyn_ce, ctx->dyn_mass);
+        KCHECK(); LAUNCHED(1);
+        ctx->op_mass = ctx->dyn_mass; ctx->op_cmass = nullptr;
+    } else {
+        ctx->op_mass = nullptr; ctx->op_cmass = ctx->dyn_ce;
+    }
+    return PFEM_OK;
+}
+
+static int dynamic_steps(pfem_ctx* ctx, const pfem_opts* o, const pfem_dynamic* d, pfem_stats* st, double* f_static) {
+    const Grid& g = ctx->g;
+    int steps = 0, conv = 1, iters = 0, all_conv = 1;
+    long long total_iters = 0;
+    double relres = 0., maxT = 0.;
+    TRY(mask_field(ctx));
+    TRY(dynamic_set_matrix(ctx, d));
+    long long r = d->rebuildfreq;
+    const double tend = d->time + d->timestep / 2.;
+    for (double t = 0.; t < tend; t += d->timestep) {               // femT3d.cpp:271-272
+        if (d->rebuildfreq && r == 0) { TRY(dynamic_set_matrix(ctx, d)); r = d->rebuildfreq; }   // :274-278
+        // right-hand side B T + F with B = A - K:  M (F - K T) + M (A T), then the Dirichlet rows take their values in the solve
+        TRY(launch_diag(ctx));                                      // the row mask (dinv == 0) of the kernels below
+        k_apply_simple<1><<<node_grid(g), node_block(), 0, ctx->stream>>>(g, ctx->dyn_cl, ctx->dyn_cv, ctx->x, ctx->dinv, f_static, ctx->p,
+                                                                          ctx->d_sc, ctx->partials, nullptr, nullptr);
+        KCHECK(); LAUNCHED(1);
+        TRY(launch_apply_simple<3>(ctx, ctx->x, ctx->q));
+        k_axpby<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->p, ctx->q, ctx->dyn_f);
+        KCHECK(); LAUNCHED(1);
+        ctx->f = ctx->dyn_f;
+        const int rc = pcg_solve(ctx, o, &iters, &relres, &conv);   // A.solverhs(T, temperatures): warm start from T^n (:283)
+        ctx->f = f_static;
+        if (rc != PFEM_OK) return rc;
+        total_iters += iters;
+        all_conv = all_conv && conv;
+        ++steps; --r;
+        if (d->maxT_log && (size_t)(steps - 1) < d->maxT_log_len) {
+            k_thermal_error<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->x, ctx->x, ctx->d_sc, ctx->partials);
+            KCHECK(); LAUNCHED(1);
+            TRY(read_scalars(ctx));
+            d->maxT_log[steps - 1] = ctx->h_sc->red[1];
+        }
+    }
+    k_thermal_error<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->x, ctx->x, ctx->d_sc, ctx->partials);
+    KCHECK(); LAUNCHED(1);
+    TRY(read_scalars(ctx));
+    maxT = ctx->h_sc->red[1];
+    if (st) {
+        st->outer_loops = steps; st->loopno = ctx->loopno; st->lin_iters = total_iters; st->last_iters = iters;
+        st->converged = all_conv; st->lin_relres = relres; st->maxval = maxT;
+        st->lin_relres_precond = ctx->last_relres_pre;
+    }
+    return all_conv ? PFEM_OK : PFEM_NOT_CONVERGED;
+}
+
+// The time loop of DynamicThermalFem3DSolver::compute (femT3d.cpp:258-305), corrected specification:
+//   (methodparam K + C/dt) T^{n+1} = (C/dt - (1 - methodparam) K) T^n + F   on the free rows,   T^{n+1} = value on Dirichlet rows.
+extern "C" int pfem_solve_dynamic(pfem_ctx* ctx, const pfem_opts* o, const pfem_dynamic* d, pfem_stats* st) {
+    NEED_MESH();
+    if (!d) FAIL(PFEM_ERR_BAD_INPUT, "null dynamic parameters");
+    if (!ctx->have_materials) FAIL(PFEM_ERR_STATE, "pfem_set_materials has not been called");
+    if (!ctx->tab_cprho) FAIL(PFEM_ERR_STATE, "pfem_set_capacity has not been called");
+    if (!(d->timestep > 0.) || !(d->time >= 0.)) FAIL(PFEM_ERR_BAD_INPUT, "need timestep > 0 and time >= 0");
+    if (!(d->methodparam >= 0. && d->methodparam <= 1.)) FAIL(PFEM_ERR_BAD_INPUT, "methodparam must lie in [0, 1]");
+    if (d->rebuildfreq < 0) FAIL(PFEM_ERR_BAD_INPUT, "negative rebuildfreq");
+    if (ctx->nranks > 1) FAIL(PFEM_ERR_BAD_INPUT, "Dynamic3D is not available in slab mode");
+    if (ctx->surf.nrows) FAIL(PFEM_ERR_BAD_INPUT, "Dynamic3D has boundary conditions of the first kind only (femT3d.hpp)");
+    const Grid& g = ctx->g;
+    if (!ctx->dyn_f) {
+        TRY(dev_alloc(ctx, &ctx->dyn_mass, (size_t)g.NP, (size_t)g.G));
+        TRY(dev_alloc(ctx, &ctx->dyn_ce, (size_t)g.NP, (size_t)g.G));
+        TRY(dev_alloc(ctx, &ctx->dyn_cl, (size_t)g.NP, (size_t)g.G));
+        TRY(dev_alloc(ctx, &ctx->dyn_cv, (size_t)g.NP, (size_t)g.G));
+        TRY(dev_alloc(ctx, &ctx->dyn_f, (size_t)g.NP, (size_t)g.G));
+    }
+    // the operator extension must be known to check_opts
+    if (d->lumping) { ctx->op_mass = ctx->dyn_mass; ctx->op_cmass = nullptr; } else { ctx->op_mass = nullptr; ctx->op_cmass = ctx->dyn_ce; }
+    int rc = check_opts(ctx, o);
+    long long l0 = ctx->launches;
+    if (st) memset(st, 0, sizeof(*st));
+    double* const f_static = ctx->f;
+    if (rc == PFEM_OK) {
+        Timer t(ctx->stream);
+        rc = dynamic_steps(ctx, o, d, st, f_static);
+        if (st) { st->t_solve_ms = t.stop(); st->kernel_launches = ctx->launches - l0; }
+    }
+    // back to the static state: true conductivities in cl/cv (providers read them), no operator extension
+    ctx->f = f_static;
+    ctx->op_mass = nullptr; ctx->op_cmass = nullptr;
+    ctx->fused.mass = nullptr; ctx->line_plan.mass = nullptr;
+    if (ctx->conds_valid && ctx->dyn_cl) {
+        cudaMemcpyAsync(ctx->cl, ctx->dyn_cl, (size_t)g.NP * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaMemcpyAsync(ctx->cv, ctx->dyn_cv, (size_t)g.NP * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    return rc;
 }
 
 extern "C" int pfem_solve_shockley(pfem_ctx* ctx, const pfem_opts* o, pfem_stats* st) {

@@ -64,6 +64,12 @@ class DeviceFem:
         self._ck(self.lib.pfem_set_materials(self.ctx, m.ctypes.data_as(L._u32p), a.shape[0], float(T0), float(dT),
                                              a.shape[1], _dp(a), _dp(b)))
 
+    def set_capacity(self, cp_dens):
+        """cp(T)*dens(T) [J/(m^3 K)] per material id on the temperature grid of set_materials (Dynamic3D)."""
+        a = _f64(cp_dens)
+        assert a.ndim == 2
+        self._ck(self.lib.pfem_set_capacity(self.ctx, a.shape[0], a.shape[1], _dp(a)))
+
     def set_dirichlet(self, nodes, values):
         n = np.ascontiguousarray(nodes, dtype=np.uintp)
         v = _f64(values)
@@ -192,6 +198,20 @@ class DeviceFem:
         o, st = self.opts(**kw), L.Stats()
         rc = self._ck(self.lib.pfem_solve_shockley(self.ctx, C.byref(o), C.byref(st)))
         return rc, st.as_dict()
+
+    def solve_dynamic(self, time, timestep, methodparam=0.5, lumping=True, rebuildfreq=0, log=False, **kw):
+        """DynamicThermalFem3DSolver::compute(time) (femT3d.cpp:258-305, corrected update); returns (rc, stats[, maxT per step])."""
+        o, st, d = self.opts(**kw), L.Stats(), L.Dynamic()
+        d.time, d.timestep, d.methodparam, d.lumping, d.rebuildfreq = float(time), float(timestep), float(methodparam), int(bool(lumping)), int(rebuildfreq)
+        buf = None
+        if log:
+            buf = np.zeros(int((time + timestep / 2.) / timestep) + 2)
+            d.maxT_log, d.maxT_log_len = _dp(buf), buf.size
+        rc = self._ck(self.lib.pfem_solve_dynamic(self.ctx, C.byref(o), C.byref(d), C.byref(st)))
+        out = st.as_dict()
+        if log:
+            out["maxT_log"] = buf[:out["outer_loops"]].copy()
+        return rc, out
 
     def solve_linear(self, **kw):
         o, st = self.opts(**kw), L.Stats()

@@ -78,6 +78,27 @@ def cond_air(T):         # plask/material/air.cpp:43-46
     return _iso(np.full_like(np.asarray(T, dtype=np.float64), 0.55e-14))
 
 
+# ---- volumetric heat capacity cp(T) * dens(T)  [J/(m^3 K)]  (Dynamic3D, femT3d.cpp:176) -------------
+def cpdens_GaAs(T):      # .../GaAs.cpp:243 (dens 5317.49 kg/m^3), :249 (cp 327 J/(kg K))
+    return np.full_like(np.asarray(T, dtype=np.float64), 0.327e3 * 5.31749e3)
+
+
+def cpdens_AlGaAs(T, Al):  # .../AlGaAs.cpp:262-264, 271-273: linear in the composition; AlAs.cpp:234 (3730.16), :240 (424)
+    Ga = 1. - Al
+    return np.full_like(np.asarray(T, dtype=np.float64), (Al * 0.424e3 + Ga * 0.327e3) * (Al * 3.73016e3 + Ga * 5.31749e3))
+
+
+def cpdens_const(cp, dens):
+    """materials without cp / dens in the reference's database (metals, oxides, air): handbook constants, synthetic"""
+    return lambda T: np.full_like(np.asarray(T, dtype=np.float64), cp * dens)
+
+
+def sample_table1(models, T0=250., dT=0.25, nT=1601):
+    """Sample a list of callables T -> value on the uniform grid T0 + i*dT (one table, e.g. cp*dens)."""
+    T = T0 + dT * np.arange(nT)
+    return np.stack([np.asarray(f(T), dtype=np.float64) * np.ones(nT) for f in models])
+
+
 def sample_tables(models, T0=250., dT=0.25, nT=1601):
     """Sample a list of callables T -> (lat, vert) on the uniform grid T0 + i*dT."""
     T = T0 + dT * np.arange(nT)

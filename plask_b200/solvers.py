@@ -228,6 +228,95 @@ class Static3D(_FemSolver):
         return self._fem.get_elem(L.ELEM_COND)
 
 
+class Dynamic3D(_FemSolver):
+    """thermal.dynamic.Dynamic3D with algorithm='cuda' (solvers/thermal/dynamic/femT3d.{hpp,cpp}, python/dynamic_python.cpp:70-86):
+    `compute(time)`, `inittemp`, `timestep`, `methodparam`, `lumping`, `rebuildfreq`, `logfreq`, `time` / `elapsed_time`,
+    `inHeat`, `outTemperature`, `outHeatFlux`, `outThermalConductivity`.  The update is the corrected theta scheme
+    (include/plaskfem_cuda.h, pfem_solve_dynamic)."""
+
+    def __init__(self, name=""):
+        super().__init__(name)
+        self.inittemp = 300.        # femT3d.cpp:27
+        self.methodparam = 0.5      # :28
+        self.timestep = 0.1         # ns, :29
+        self.lumping = True         # :31
+        self.rebuildfreq = 0        # :32
+        self.logfreq = 500          # :33
+        self.inHeat = None
+        self.maxT = 0.
+        self._elapstime = 0.
+        self.physical_time = 0.
+
+    @property
+    def time(self):
+        return self._elapstime
+
+    elapsed_time = time
+
+    def initialize(self):
+        p = self._problem
+        if p is None:
+            raise L.BadInput(f"{self.id}: no geometry/mesh (problem) specified")
+        f = self._fem = self._new_fem()
+        f.set_mesh(p.axes, p.strides)
+        f.set_materials(self._elem_materials(), p.T0, p.dT, p.tab_lat, p.tab_vert)
+        tab = p.tab_cprho
+        if tab is None:
+            from .configs import capacity_tables
+            tab = capacity_tables(p.T0, p.dT, p.tab_lat.shape[1])[:p.tab_lat.shape[0]]
+        f.set_capacity(tab)
+        f.set_field(float(self.inittemp))                # temperatures.reset(size, inittemp), :82
+        f.set_dirichlet(*self._dirichlet())
+        self._elapstime = 0.                              # :76
+        self.physical_time = 0.
+        self.initialized = True
+
+    def compute(self, time):
+        """DynamicThermalFem3DSolver::compute(time) (femT3d.cpp:258-305): advances the temperatures by `time` ns."""
+        if not self.initialized:
+            self.initialize()
+        f, p = self._fem, self._problem
+        heat = p.heat if self.inHeat is None else self.inHeat
+        if heat is not None and np.isscalar(heat):
+            heat = np.full(p.E, float(heat))
+        f.set_source(heat)
+        if not self.lumping and self.variant == 3:
+            raise L.BadInput(f"{self.id}: the consistent capacity matrix (lumping = no) runs with variant = 1")
+        o = self._opts(0, 0.)
+        rc, st = f.solve_dynamic(time, self.timestep, self.methodparam, self.lumping, self.rebuildfreq, log=bool(self.logfreq), **o)
+        self._after(rc, st)
+        self.maxT = st["maxval"]
+        steps = st["outer_loops"]
+        if self.logfreq:                                  # "Time {:.2f} ns: max(T) = {:.3f} K" every logfreq steps (:287-291)
+            l = self.logfreq
+            for i in range(steps):
+                if l == 0:
+                    self.log.append(("result", f"Time {self._elapstime + i * self.timestep:.2f} ns: max(T) = {st['maxT_log'][i]:.3f} K"))
+                    l = self.logfreq
+                l -= 1
+        self._elapstime += steps * self.timestep - (self.timestep if steps else 0.)   # `elapstime -= timestep` after the loop (:297)
+        self.physical_time += steps * self.timestep   # one timestep per solve: the loop runs time/timestep + 1 of them (:271-272)
+        return 0.
+
+    def outTemperature(self, mesh=None):
+        if not self.initialized:
+            n = self._problem.N if mesh is None else int(np.prod([len(a) for a in mesh[0]]))
+            return np.full(n, float(self.inittemp))
+        if mesh is None:
+            return self._fem.get_field()
+        from .configs import strides_for
+        axes, order = mesh
+        return self._fem.interpolate_field(axes, strides_for(tuple(len(a) for a in axes), order)[0])
+
+    def outHeatFlux(self):
+        self._fem.update_conductivity_thermal()           # saveHeatFluxes re-evaluates thermk at the current temperatures (:331-340)
+        return self._fem.get_elem(L.ELEM_FLUX)
+
+    def outThermalConductivity(self):
+        self._fem.update_conductivity_thermal()
+        return self._fem.get_elem(L.ELEM_COND)
+
+
 class Shockley3D(_FemSolver):
     """electrical.shockley.Shockley3D with algorithm='cuda'."""
 

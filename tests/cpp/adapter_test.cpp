@@ -277,6 +277,46 @@ static int gpu_tests() {
         try { c.set_source(nullptr); IterParams z; z.maxit = 0; c.solve(true, z, 0.05, 1); } catch (const BadInput&) { bad = true; }
         REQUIRE(bad);
     }
+    // ---- Dynamic3D: 1-D cooling, bottom at 300 K, top insulated, T(z,0) = 300 + a sin(pi z / 2L):
+    //      T(z,t) = 300 + a sin(pi z / 2L) exp(-alpha (pi/2L)^2 t), Crank-Nicolson, lumped capacity
+    {
+        Mesh m;
+        const size_t nz = 41;
+        const double L = 2.0, k = 45., cprho = 0.327e3 * 5.31749e3, a = 50.;
+        for (size_t i = 0; i < 3; ++i) m.axis[0].push_back(0.5 * i);
+        for (size_t i = 0; i < 4; ++i) m.axis[1].push_back(0.5 * i);
+        for (size_t i = 0; i < nz; ++i) m.axis[2].push_back(L * i / (nz - 1));
+        m.order = ORDER_012;
+        Context c(0, "dynamic");
+        c.set_mesh(m);
+        std::vector<uint32_t> ids(m.elements(), 0);
+        Tables t = sample_tables(1, [&](uint32_t, double) { return std::make_pair(k, k); }, 250., 1., 400);
+        c.set_materials(ids, t);
+        c.set_capacity(t, std::vector<double>(t.nT, cprho));
+        std::vector<double> T(m.size());
+        for (size_t i0 = 0; i0 < m.n(0); ++i0) for (size_t i1 = 0; i1 < m.n(1); ++i1) for (size_t i2 = 0; i2 < nz; ++i2)
+            T[m.node(i0, i1, i2)] = 300. + a * std::sin(M_PI * m.axis[2][i2] / (2. * L));
+        c.set_field(T.data());
+        Dirichlet bc;
+        std::vector<size_t> bottom;
+        for (size_t i0 = 0; i0 < m.n(0); ++i0) for (size_t i1 = 0; i1 < m.n(1); ++i1) bottom.push_back(m.node(i0, i1, 0));
+        bc.add(bottom, 300.);
+        c.set_dirichlet(bc);
+        c.set_source(nullptr);
+        IterParams ip;
+        ip.maxerr = 1e-12; ip.maxit = 5000; ip.preconditioner = IterParams::PRECOND_LJAC;
+        double elapsed = 0.;
+        int lines = 0;
+        Context::TimeResult r = c.solve_dynamic(ip, 200., 4., 0.5, true, 0, 10, elapsed, [&](int lvl, const std::string& s) { if (lvl == 3 && s.rfind("Time", 0) == 0) ++lines; });
+        REQUIRE(r.steps == 51 && std::fabs(elapsed - 200.) < 1e-9 && lines == 4 && ip.converged);
+        c.get_field(T.data());
+        const double alpha = k / cprho * 1e3, rate = alpha * (M_PI / (2. * L)) * (M_PI / (2. * L));
+        double maxd = 0.;
+        for (size_t i2 = 0; i2 < nz; ++i2)
+            maxd = std::fmax(maxd, std::fabs(T[m.node(1, 1, i2)] - (300. + a * std::sin(M_PI * m.axis[2][i2] / (2. * L)) * std::exp(-rate * (elapsed + 4.)))));   // 51 solves of 4 ns
+        printf("Dynamic3D cooling: %d steps, %lld PCG iterations, max|T - T_exact| = %.3e K\n", r.steps, r.lin_iters, maxd);
+        REQUIRE(maxd < 4e-3);
+    }
     printf("adapter gpu tests ok\n");
     return 0;
 }

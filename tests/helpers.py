@@ -183,3 +183,46 @@ def multilevel_reference(p, A, fixed, c=4):
         return z
     apply.nlevels = len(levels)
     return apply
+
+
+def oracle_dynamic(p, cprho=None, **kw):
+    """Dynamic3DOracle (corrected femT3d.cpp) for a thermal Problem; cprho defaults to the problem's / the config tables"""
+    m = oracle_mesh(p)
+    tb = orc.Tables(p.T0, p.dT, p.tab_lat, p.tab_vert)
+    if cprho is None:
+        cprho = p.tab_cprho if p.tab_cprho is not None else cf.capacity_tables(p.T0, p.dT, p.tab_lat.shape[1])[:p.tab_lat.shape[0]]
+    kw.setdefault("inittemp", p.inittemp)
+    return orc.Dynamic3DOracle(m, p.elem_mat, tb, cprho, p.bc_nodes, p.bc_values, heat=p.heat, **kw)
+
+
+def cooling_problem(nz=41, L=2.0, k=45., cprho=0.327e3 * 5.31749e3, order="012", nxy=(3, 4)):
+    """1-D cooling of a slab of thickness L um: bottom plane at 300 K, top insulated, constant k and cp*dens (GaAs.cpp:225,243,249
+    at 300 K).  With T(z,0) = 300 + a sin(pi z / 2L) the exact solution is 300 + a sin(pi z / 2L) exp(-alpha (pi/2L)^2 t),
+    alpha = k/(cp dens) (in um^2/ns: * 1e3)."""
+    axes = [np.linspace(0., 1., nxy[0]), np.linspace(0., 1.5, nxy[1]), np.linspace(0., L, nz)]
+    tab = np.full((1, 2), float(k))
+    p = cf.Problem("cooling", "thermal", axes, order, None, 200., 1000., tab, tab.copy(), None, None)
+    p.elem_mat = np.zeros(p.E, dtype=np.uint32)
+    nodes = face_nodes(p, 2, 0)
+    p.bc_nodes = nodes.astype(np.uintp)
+    p.bc_values = np.full(nodes.size, 300.)
+    p.heat = np.zeros(p.E)
+    p.inittemp = 300.
+    p.tab_cprho = np.full((1, 2), float(cprho))
+    p.meta["alpha"] = k / cprho * 1e3
+    p.meta["L"] = L
+    return p
+
+
+def cooling_initial(p, a=50.):
+    z = np.asarray(p.axes[2])
+    ng = np.broadcast_to(p.node_index_grid(), p.n)
+    T = np.empty(p.N)
+    T[ng] = 300. + a * np.sin(np.pi * z / (2. * p.meta["L"]))[None, None, :]
+    return T
+
+
+def cooling_exact(p, t, a=50.):
+    z = np.asarray(p.axes[2])
+    L, al = p.meta["L"], p.meta["alpha"]
+    return 300. + a * np.sin(np.pi * z / (2. * L)) * np.exp(-al * (np.pi / (2. * L)) ** 2 * t)

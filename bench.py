@@ -103,6 +103,26 @@ def workload(n):
     return configs.config_B(n)
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this process to the CPUs NVML reports as closest to GPU `local` BEFORE any pinned buffer is first touched, so that the
+    host side of the per-step H2D / D2H copies of the e2e arm lives on the GPU's own NUMA node (8 ranks otherwise share the
+    memory controllers of one socket).  Returns the number of CPUs in the mask, or None when NVML cannot tell."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w in range(words) for b in range(64) if (int(mask[w]) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def pinned_copy(a):
     """numpy array backed by CUDA-pinned host memory (torch is only the allocator)."""
     import torch
@@ -313,6 +333,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the CUDA algorithm has no CPU fallback")
     torch.cuda.set_device(local)
+    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -327,7 +348,7 @@ def run_ours(args):
         # z-slab partition along the major axis, weak scaling — every GPU owns n planes of a
         # (n*world) x n x n config-B mesh (+ one halo plane towards each neighbour), built directly per rank.
         from plask_b200 import configs
-        gn = (n * world, n, n)
+        gn = (n, n, n) if args.strong else (n * world, n, n)   # --strong: the n^3 mesh itself cut into `world` slabs
         lo, hi, own_lo, own_hi = configs.slab_local(gn[0], rank, world)
         p = configs.config_B(gn, order="012", rows0=(lo, hi))
         slab = (own_lo, own_hi)
@@ -456,7 +477,8 @@ def run_ours(args):
     e2e = {"value": N_total * e2e_iters / t_e2e, "unit": "DOF*iter/s",
            "h2d_bytes_per_step": int(heat_h.nbytes + x0_h.nbytes + p.bc_nodes.nbytes + p.bc_values.nbytes),
            "d2h_bytes_per_step": int(out_h.nbytes), "ms_per_step": 1e3 * t_e2e / args.steps,
-           "api": "pfem_set_source + pfem_set_field + pfem_set_dirichlet + pfem_solve_linear + pfem_get_field (host buffers)"}
+           "api": "pfem_set_source + pfem_set_field + pfem_set_dirichlet + pfem_solve_linear + pfem_get_field (host buffers)",
+           "host_cpus_bound_to_gpu_numa_node": numa_cpus}
 
     f.close()
     barrier()
@@ -551,14 +573,15 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": "pcg_dof_iter_per_s", "value": value, "unit": "DOF*iter/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
+            "scaling": "strong" if (args.strong and slab) else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"Static3D config B: {n}^3 VCSEL-like layered block, nonlinear k(T) tables, "
                                    f"{N} DOF per GPU, Jacobi-PCG", "iters_per_step": iters,
                        "l2": "inputs >> L2: every iteration streams 10-11 vectors of %.0f MB each, nothing survives in the 126 MB L2" % (N * 8 / 1e6),
                        "order": p.order, "kernel_variant": args.variant,
                        "multi_gpu": ("single device" if world == 1 else "independent replicas" if not slab else
-                                     f"z-slab partition of a {n * world}x{n}x{n} mesh along the major axis, one halo plane per "
+                                     f"z-slab partition of a {n if args.strong else n * world}x{n}x{n} mesh along the major axis, one halo plane per "
                                      "neighbour written by k_fpcg through NVLink peer stores, 7 CG scalars exchanged once per "
                                      "iteration through peer inboxes (no separate collective kernel)"),
                        "dof_total": N_total},
@@ -587,6 +610,7 @@ def main():
     ap.add_argument("--tts-loops", type=int, default=0)
     ap.add_argument("--tts-maxit", type=int, default=200000)
     ap.add_argument("--lin-tol", type=float, default=1e-8)
+    ap.add_argument("--strong", action="store_true", help="N>1: strong scaling — the n^3 mesh itself is cut into N slabs (default: weak, n planes per GPU)")
     ap.add_argument("--replicas", action="store_true", help="N>1: independent replicas instead of the slab-partitioned collective solve")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -251,7 +251,9 @@ int pfem_get_field(pfem_ctx* ctx, double* x);  /* temperatures / potential, N do
 /* Provider on a foreign mesh (getTemperatures / getVoltage with INTERPOLATION_LINEAR, therm3d.cpp:387-395,
  * electr3d.cpp:518-524): the field interpolated linearly, exactly like RectilinearMesh3D::interpolateLinear
  * (rectilinear3d.hpp:802-845; constant outside the mesh), at the tensor-product points of the target axes; out[] is dense
- * with the target mesh's own index strides (any of its 6 iteration orders).  Not available in slab mode. */
+ * with the target mesh's own index strides (any of its 6 iteration orders).  Slab mode: the call is COLLECTIVE (halo planes are
+ * refreshed first) and every rank interpolates on its LOCAL mesh: a target point is valid on the rank whose local extent along
+ * the slab axis (owned planes + halo planes) contains it; elsewhere the rank returns the constant continuation of its own slab. */
 int pfem_interpolate_field(pfem_ctx* ctx, const size_t n[3], const double* ax0, const double* ax1, const double* ax2,
                            const size_t stride[3], double* out);
 

@@ -425,15 +425,36 @@ def slab_local(nK, rank, nranks):
     return lo, hi, K0 - lo, K1 - lo
 
 
-def slab_problem(p, rank, nranks):
-    """Cut the local problem of `rank` out of a global Problem (thermal or Shockley) — what the solver plugin would do on each
-    process before calling the C ABI in slab mode.  Returns (local Problem, own_lo, own_hi, (lo, hi))."""
+def slab_axis(p, need_vertical_inside=None):
+    """Physical axis the slabs cut ("host chooses which physical axis that is").  The major axis of the mesh's own
+    iteration order when that is lateral; for a vertical major axis (the order setOptimalIterationOrder gives a tall mesh,
+    rectilinear3d.cpp:74-85) with a junction (a12 couples the planes act.bottom / act.top, electr3d.cpp:246-274) or whenever
+    `need_vertical_inside` (line preconditioners solve along the vertical lines) the larger lateral axis — the local meshes
+    are then handed to the library in an order with that axis major, which is only a host-side renumbering."""
     major = ORDERS[p.order][0]
+    if need_vertical_inside is None:
+        need_vertical_inside = p.kind == "shockley"
+    if major != 2 or not need_vertical_inside:
+        return major
+    return 0 if p.n[0] >= p.n[1] else 1
+
+
+def slab_order(order, axis):
+    """iteration order of the local meshes: `axis` becomes the major axis, the other two keep their relative order"""
+    rest = [a for a in ORDERS[order] if a != axis]
+    return f"{axis}{rest[0]}{rest[1]}"
+
+
+def slab_problem(p, rank, nranks, axis=None):
+    """Cut the local problem of `rank` out of a global Problem (thermal or Shockley) — what the solver plugin would do on each
+    process before calling the C ABI in slab mode.  `axis`: the physical axis to cut (default: the major axis of the mesh's
+    order; see slab_axis).  Returns (local Problem, own_lo, own_hi, (lo, hi))."""
+    major = ORDERS[p.order][0] if axis is None else int(axis)
     n = p.n
     lo, hi, own_lo, own_hi = slab_local(n[major], rank, nranks)
     axes = [a.copy() for a in p.axes]
     axes[major] = axes[major][lo:hi]
-    q = Problem(p.name + f"[{rank}/{nranks}]", p.kind, axes, p.order, None, p.T0, p.dT, p.tab_lat, p.tab_vert, None, None,
+    q = Problem(p.name + f"[{rank}/{nranks}]", p.kind, axes, slab_order(p.order, major), None, p.T0, p.dT, p.tab_lat, p.tab_vert, None, None,
                 inittemp=p.inittemp, maxerr=p.maxerr)
     esl = [slice(None)] * 3
     esl[major] = slice(lo, hi - 1)
@@ -452,30 +473,23 @@ def slab_problem(p, rank, nranks):
     q.elem_role = cut_elem(p.elem_role, np.uint8)
     q.noheat = cut_elem(p.noheat, np.uint8)
     q.empty = cut_elem(p.empty, np.uint8)
+    q.tab_cprho = p.tab_cprho
     for name in ("beta", "js", "pcond", "ncond", "start_cond", "Te"):
         setattr(q, name, getattr(p, name))
     # Dirichlet nodes inside the local planes (halo planes included), in application order
-    ns = p.strides
-    order3 = sorted(range(3), key=lambda a: -ns[a])            # major, medium, minor
-    idx = np.asarray(p.bc_nodes, dtype=np.int64)
-    c = [None] * 3
-    rem = idx
-    for a in order3:
-        c[a], rem = np.divmod(rem, ns[a])
-    keep = (c[major] >= lo) & (c[major] < hi)
-    c[major] = c[major] - lo
-    qs = q.strides
-    q.bc_nodes = (c[0][keep] * qs[0] + c[1][keep] * qs[1] + c[2][keep] * qs[2]).astype(np.uintp)
+    q.bc_nodes, keep = slab_local_nodes(p, q, lo, hi, p.bc_nodes, axis=major)
+    q.bc_nodes = q.bc_nodes.astype(np.uintp)
     q.bc_values = np.asarray(p.bc_values)[keep].copy()
     return q, own_lo, own_hi, (lo, hi)
 
 
-def slab_local_nodes(p, q, lo, hi, nodes):
-    """Global node numbers of `p` -> (node numbers in the local problem `q` holding planes [lo, hi) of the major axis,
-    mask of the entries that lie inside) — for Dirichlet lists and the boundary conditions of the 2nd / 3rd kind."""
-    major = ORDERS[p.order][0]
+def slab_local_nodes(p, q, lo, hi, nodes, axis=None):
+    """Global node numbers of `p` -> (node numbers in the local problem `q` holding planes [lo, hi) of the cut axis (default:
+    the major axis of p), mask of the entries that lie inside) — for Dirichlet lists and the boundary conditions of the
+    2nd / 3rd kind."""
+    major = ORDERS[p.order][0] if axis is None else int(axis)
     ns = p.strides
-    order3 = sorted(range(3), key=lambda a: -ns[a])            # major, medium, minor
+    order3 = sorted(range(3), key=lambda a: -ns[a])            # major, medium, minor of the GLOBAL numbering
     rem = np.asarray(nodes, dtype=np.int64)
     c = [None] * 3
     for a in order3:
@@ -491,3 +505,14 @@ def slab_field_owned(q, field, own_lo, own_hi):
     major, medium, minor = ORDERS[q.order]
     n = q.n
     return np.asarray(field).reshape(n[major], n[medium], n[minor])[own_lo:own_hi]
+
+
+def slab_assemble(p, q_order, parts):
+    """Global node field of `p` (in p's own numbering) from the owned parts of all ranks (slab_field_owned arrays, in rank
+    order) of local problems numbered in `q_order`."""
+    major, medium, minor = ORDERS[q_order]
+    g = np.concatenate([np.asarray(a) for a in parts], axis=0)          # (n_major, n_medium, n_minor) of the local order
+    g3 = np.transpose(g, np.argsort([major, medium, minor]))            # -> (n0, n1, n2)
+    out = np.empty(p.N)
+    out[np.broadcast_to(p.node_index_grid(), p.n).ravel()] = g3.ravel()
+    return out

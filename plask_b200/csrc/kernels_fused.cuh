@@ -40,6 +40,10 @@
 #include "kernels_tma.cuh"
 #include "kernels_ml.cuh"
 
+#ifndef PFEM_X
+#define PFEM_X 5   // experiment mask of k_fpcg: 1 = phase-1 loads hoisted (-1.7 %), 2 = x fetched two planes ahead (+1.5 %: off), 4 = vertical stiffness per element (-0.5 %)
+#endif
+
 namespace pfem {
 
 // Chunks of the march along K: chunk c of every tile covers the owned planes [off[c], off[c+1]) (relative to kown0).
@@ -269,9 +273,9 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
     const idx_t sK = g.sK;
 
     // x of the own nodes, fetched one step ahead
-    double xn[RJ];
+    double xn[RJ], xn2[RJ];   // PFEM_X & 2: two planes ahead (an HBM round trip under load is longer than one step)
 #pragma unroll
-    for (int rr = 0; rr < RJ; ++rr) xn[rr] = 0.;
+    for (int rr = 0; rr < RJ; ++rr) xn[rr] = xn2[rr] = 0.;
     double mprev[RJ];   // MASS: capacity diagonal of the own nodes of the plane below (loaded when that plane was the current one)
 #pragma unroll
     for (int rr = 0; rr < RJ; ++rr) mprev[rr] = 0.;
@@ -291,7 +295,22 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
 #pragma unroll
             for (int rr = 0; rr < RJ; ++rr) xcur[rr] = xn[rr];
         }
-        if (FUSED && NEXT_OWN) {
+        if (PFEM_X & 2) {
+            if (FUSED) {
+#pragma unroll
+                for (int rr = 0; rr < RJ; ++rr) xn[rr] = xn2[rr];
+                if (t + 2 <= nsteps - 1) {
+#pragma unroll
+                    for (int rr = 0; rr < RJ; ++rr)
+                        if (vj[rr]) xn2[rr] = x[nown[rr] + 2 * sK];
+                }
+                if (t == 0 && NEXT_OWN) {   // start-up: the first owned plane has not been fetched by an earlier step
+#pragma unroll
+                    for (int rr = 0; rr < RJ; ++rr)
+                        if (vj[rr]) xn[rr] = x[nown[rr] + sK];
+                }
+            }
+        } else if (FUSED && NEXT_OWN) {
 #pragma unroll
             for (int rr = 0; rr < RJ; ++rr)
                 if (vj[rr]) xn[rr] = x[nown[rr] + sK];
@@ -304,6 +323,87 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         const double hk = sHK[t], rk = sHK[lk + 2 + t];   // element layer L = P - 1 of this step (t >= 1)
         mbar_wait(&bars[st], (uint32_t)((t / NS) & 1));
 
+#if PFEM_X & 1
+        // ---------------- phase 1: p' plane and coefficient layer -------------------------
+        // all shared-memory loads of the phase are issued before the first store: the compiler cannot prove that the raw boxes
+        // and the p' / coefficient planes do not alias and would otherwise serialise load -> use -> store per node
+        double l_r[RJ], l_q[RJ], l_p[RJ], l_d[RJ], l_a[RJ], l_b[RJ];
+        double g_r = 0., g_q = 0., g_p = 0., g_d = 0., h_a = 0., h_b = 0.;
+#pragma unroll
+        for (int rr = 0; rr < RJ; ++rr) {
+            const int ro = (jl0 + rr + 1) * PW + tx + HX;
+            l_r[rr] = FUSED ? raw[ro] : 0.;
+            l_q[rr] = (FUSED && !LINE) ? raw[BOXP + ro] : 0.;
+            l_p[rr] = raw[B_P * BOXP + ro];
+            l_d[rr] = raw[B_D * BOXP + ro];
+            if (GATHER) { l_a[rr] = raw[B_CL * BOXP + ro]; l_b[rr] = ISO ? l_a[rr] : raw[B_CV * BOXP + ro]; }
+        }
+        if (ring_raw >= 0) {
+            g_p = raw[B_P * BOXP + ring_raw];
+            if (FUSED) { g_r = raw[ring_raw]; g_q = LINE ? 0. : raw[BOXP + ring_raw]; g_d = raw[B_D * BOXP + ring_raw]; }
+        }
+        if (GATHER && er_raw >= 0) { h_a = raw[B_CL * BOXP + er_raw]; h_b = ISO ? h_a : raw[B_CV * BOXP + er_raw]; }
+#pragma unroll
+        for (int rr = 0; rr < RJ; ++rr) {
+            double pn;
+            if (FUSED) {
+                const double r0 = l_r[rr], q0 = l_q[rr], p0 = l_p[rr], dd = l_d[rr];
+                const double rn = MLZ ? r0 + zc[rr] : LINE ? r0 : fma(-alpha, q0, r0);
+                const double z = dd * rn;
+                pn = fma(beta, p0, z);
+                zdb[rr] = z; zdb[RJ + rr] = dd;
+                if (OWN) {
+                    if (vj[rr]) {
+                        const idx_t n = nown[rr];
+                        const double xv = fma(alpha, p0, xcur[rr]);
+                        if (!LINE) r_out[n] = rn;   // line-Jacobi iteration: r' is written by the line kernel
+                        p_out[n] = pn;
+                        x[n] = xv;
+                        if (slab) {
+                            const int P = k0 - 1 + t;
+                            const idx_t nip = n - sK * P;   // offset inside the plane
+                            if (push_lo && P == g.kown0) { if (!LINE) po.r_lo[nip] = rn; po.p_lo[nip] = pn; }
+                            if (push_hi && P == g.kown1 - 1) { if (!LINE) po.r_hi[nip] = rn; po.p_hi[nip] = pn; }
+                        }
+                        if (!LINE) {
+                            red[1] = fma(rn, z, red[1]);
+                            red[4] = fma(rn, rn, red[4]);
+                            red[5] = fma(z, z, red[5]);
+                        }
+                        if (MLZ) red[5] = fma(z, z, red[5]);
+                        red[6] = fma(xv, xv, red[6]);
+                    }
+                }
+            } else {
+                pn = l_p[rr];
+                zdb[rr] = 0.; zdb[RJ + rr] = l_d[rr];
+            }
+            sPb[(jl0 + rr + 1) * PWP + tx + 1] = pn;
+            if (GATHER) {
+                const double a = l_a[rr], b = l_b[rr];
+                const double kI = ((VDIM == 0 ? b : a) * wI[rr]) * hk;
+                const double kJ = ((VDIM == 1 ? b : a) * wJ[rr]) * hk;
+                const double kK = ((VDIM == 2 ? b : a) * wK[rr]) * rk;
+                const int co = (jl0 + rr + 1) * CW + tx + 1;
+                reinterpret_cast<double2*>(sCb)[co] = make_double2(kI + kJ, fma(-2., kI, kJ));
+                reinterpret_cast<double2*>(sCb + CHALF)[co] = make_double2(fma(-2., kJ, kI), kK);
+            }
+        }
+        if (ring_raw >= 0) {
+            double pn;
+            if (FUSED) pn = fma(beta, g_p, g_d * (MLZ ? g_r + zcr : LINE ? g_r : fma(-alpha, g_q, g_r)));
+            else pn = g_p;
+            sPb[ring_pl] = pn;
+        }
+        if (GATHER && er_raw >= 0) {
+            const double a = h_a, b = h_b;
+            const double kI = ((VDIM == 0 ? b : a) * wIr) * hk;
+            const double kJ = ((VDIM == 1 ? b : a) * wJr) * hk;
+            const double kK = ((VDIM == 2 ? b : a) * wKr) * rk;
+            reinterpret_cast<double2*>(sCb)[er_c] = make_double2(kI + kJ, fma(-2., kI, kJ));
+            reinterpret_cast<double2*>(sCb + CHALF)[er_c] = make_double2(fma(-2., kJ, kI), kK);
+        }
+#else
         // ---------------- phase 1: p' plane and coefficient layer -------------------------
 #pragma unroll
         for (int rr = 0; rr < RJ; ++rr) {
@@ -371,6 +471,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
             reinterpret_cast<double2*>(sCb)[er_c] = make_double2(kI + kJ, fma(-2., kI, kJ));
             reinterpret_cast<double2*>(sCb + CHALF)[er_c] = make_double2(fma(-2., kJ, kI), kK);
         }
+#endif
         __syncthreads();
         if (tid == 0 && t + NS <= nsteps) issue(t + NS);
         if (MLZ) {   // the next plane lies in another level-1 aggregate: fetch its coarse correction now, use it next step
@@ -401,21 +502,26 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
             for (int y = 0; y < RJ + 2; ++y)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) dw[y][c] = wb[y][c] - wa[y][c];
-            double Bs[RJ + 1], Qs[RJ + 1], Ss[RJ + 1];   // sums over the two elements of a row
+            double Bs[RJ + 1], Ss[RJ + 1];   // sums over the two elements of a row
 #pragma unroll
             for (int ey = 0; ey <= RJ; ++ey) {
                 Bs[ey] = e_uj[ey][0] + e_uj[ey][1];
-                Qs[ey] = e_kk[ey][0] + e_kk[ey][1];
                 Ss[ey] = e_sij[ey][0] + e_sij[ey][1];
             }
+#if PFEM_X & 4
+            double mw[RJ + 2][2];
+#pragma unroll
+            for (int y = 0; y < RJ + 2; ++y) { mw[y][0] = fma(2., dw[y][1], dw[y][0]); mw[y][1] = fma(2., dw[y][1], dw[y][2]); }
+#else
+            double Qs[RJ + 1];
+#pragma unroll
+            for (int ey = 0; ey <= RJ; ++ey) Qs[ey] = e_kk[ey][0] + e_kk[ey][1];
+#endif
 #pragma unroll
             for (int rr = 0; rr < RJ; ++rr) {
                 const int y0 = rr, yc = rr + 1, y2 = rr + 2;   // window rows; element rows rr (below) and rr+1 (above)
                 const double S2 = 2. * (Ss[rr] + Ss[rr + 1]);
-                const double T4 = 4. * (Qs[rr] + Qs[rr + 1]);
                 const double A0 = e_ui[rr][0] + e_ui[rr + 1][0], A1 = e_ui[rr][1] + e_ui[rr + 1][1];
-                const double P0 = 2. * (e_kk[rr][0] + e_kk[rr + 1][0]), P1 = 2. * (e_kk[rr][1] + e_kk[rr + 1][1]);
-                const double Q0 = 2. * Qs[rr], Q1 = 2. * Qs[rr + 1];
                 // in-plane stiffness of planes a and b: three independent chains each
                 double la = fma(A1, wa[yc][2], fma(A0, wa[yc][0], S2 * wa[yc][1]));
                 double la0 = fma(-e_sij[rr][1], wa[y0][2], fma(-e_sij[rr][0], wa[y0][0], Bs[rr] * wa[y0][1]));
@@ -426,10 +532,20 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
                 la += la0 + la2;
                 lb += lb0 + lb2;
                 // vertical stiffness M9 (b - a) on the difference window
+#if PFEM_X & 4
+                // element by element: kK_e (4 d11 + 2 d_iedge + 2 d_jedge + d_corner) = kK_e (2 m[yc][s] + m[yo][s]) with the row
+                // combinations m[y][s] = 2 d[y][1] + d[y][2s] shared by the nodes of the thread
+                const double cc = fma(e_kk[rr][0], fma(2., mw[yc][0], mw[y0][0]), e_kk[rr][1] * fma(2., mw[yc][1], mw[y0][1])) +
+                                  fma(e_kk[rr + 1][0], fma(2., mw[yc][0], mw[y2][0]), e_kk[rr + 1][1] * fma(2., mw[yc][1], mw[y2][1]));
+#else
+                const double T4 = 4. * (Qs[rr] + Qs[rr + 1]);
+                const double P0 = 2. * (e_kk[rr][0] + e_kk[rr + 1][0]), P1 = 2. * (e_kk[rr][1] + e_kk[rr + 1][1]);
+                const double Q0 = 2. * Qs[rr], Q1 = 2. * Qs[rr + 1];
                 double cc = fma(P1, dw[yc][2], fma(P0, dw[yc][0], T4 * dw[yc][1]));
                 const double cc0 = fma(e_kk[rr][1], dw[y0][2], fma(e_kk[rr][0], dw[y0][0], Q0 * dw[y0][1]));
                 const double cc2 = fma(e_kk[rr + 1][1], dw[y2][2], fma(e_kk[rr + 1][0], dw[y2][0], Q1 * dw[y2][1]));
                 cc += cc0 + cc2;
+#endif
                 const double lo = fma(2., la, lb) - cc;
                 const double hi = fma(2., lb, la) + cc;
                 if (FINAL) {

@@ -1960,7 +1960,9 @@ extern "C" int pfem_interpolate_field(pfem_ctx* ctx, const size_t n[3], const do
                                       const size_t stride[3], double* out) {
     NEED_MESH();
     if (!n || !ax0 || !ax1 || !ax2 || !stride || !out) FAIL(PFEM_ERR_BAD_INPUT, "null argument");
-    if (ctx->nranks > 1) FAIL(PFEM_ERR_BAD_INPUT, "interpolation onto a foreign mesh is not available in slab mode (download the field instead)");
+    // slab mode: COLLECTIVE (the halo planes are refreshed first); every rank interpolates on its local mesh (owned + halo planes),
+    // so a target point is valid on the rank whose local extent along the slab axis contains it and continued as a constant elsewhere
+    if (ctx->nranks > 1) TRY(halo_sync(ctx, SA_X));
     const double* ax[3] = {ax0, ax1, ax2};
     size_t total = 1, ni = 0, nd = 0;
     AxisTab tab[3];

@@ -74,6 +74,21 @@ def main():
     # node lists of boundary conditions are localised like the Dirichlet list
     ln, keep = cf.slab_local_nodes(p, q, lo, hi, p.bc_nodes)
     assert np.array_equal(ln.astype(np.uintp), q.bc_nodes) and keep.sum() == q.bc_nodes.size
+    # a mesh in the generator's optimal order with the vertical axis major (rectilinear3d.cpp:74-85): the host cuts a LATERAL axis
+    # instead (cf.slab_axis) and numbers the local meshes with that axis major — junctions and vertical lines stay inside the slabs
+    pv = cf.config_C((6 * world + 5, 14, 52), order="201")
+    assert cf.ORDERS[pv.order][0] == 2 and cf.slab_axis(pv) == 0
+    qv, v_lo, v_hi, (vlo, vhi) = cf.slab_problem(pv, rank, world, axis=cf.slab_axis(pv))
+    assert qv.order == "021" and qv.n == (vhi - vlo, 14, 52)
+    egv = np.broadcast_to(pv.elem_index_grid(), tuple(k - 1 for k in pv.n))
+    legv = np.broadcast_to(qv.elem_index_grid(), tuple(k - 1 for k in qv.n))
+    assert np.array_equal(qv.elem_junc[legv], pv.elem_junc[egv][vlo:vhi - 1])
+    assert np.array_equal(qv.elem_mat[legv], pv.elem_mat[egv][vlo:vhi - 1])
+    gfv = np.zeros(pv.N); gfv[pv.bc_nodes] = pv.bc_values + 7.
+    lfv = np.zeros(qv.N); lfv[qv.bc_nodes] = qv.bc_values + 7.
+    assert np.array_equal(lfv[np.broadcast_to(qv.node_index_grid(), qv.n)], gfv[np.broadcast_to(pv.node_index_grid(), pv.n)][vlo:vhi])
+    own = allgather_bytes(cf.slab_field_owned(qv, lfv, v_lo, v_hi))
+    assert np.array_equal(cf.slab_assemble(pv, qv.order, own), gfv)
     blobs = allgather_bytes(bytes([rank]) * 64)
     assert [b[0] for b in blobs] == list(range(world))
     if host_only:
@@ -106,6 +121,14 @@ def main():
     stats = [x[1] for x in parts]
     assert all(st["lin_iters"] == stats[0]["lin_iters"] and st["outer_loops"] == stats[0]["outer_loops"] for st in stats)
     assert all(x[2] == parts[0][2] for x in parts)
+    # provider on a foreign mesh in slab mode (collective): every rank interpolates on its local mesh, the host keeps the points
+    # whose coordinate along the slab axis lies in the rank's owned interval
+    tgt_axes = [np.concatenate([[a[0] - 0.3], 0.5 * (a[:-1] + a[1:]) + 0.01, [a[-1] + 0.2]]) for a in p.axes]
+    Ti_loc = s.outTemperature((tgt_axes, "102")).reshape(len(tgt_axes[1]), len(tgt_axes[0]), len(tgt_axes[2]))   # order 102: axis 1 slowest
+    x_lo = -np.inf if rank == 0 else q.axes[0][own_lo]
+    x_hi = np.inf if rank == world - 1 else q.axes[0][own_hi]
+    mine = (tgt_axes[0] >= x_lo) & (tgt_axes[0] < x_hi)
+    partsI = allgather_bytes((Ti_loc[:, mine, :], mine))
     s.invalidate()
     if rank == 0:
         from helpers import oracle_thermal
@@ -119,6 +142,16 @@ def main():
         T1 = one.outTemperature()
         o = oracle_thermal(p, algorithm="cholesky")
         o.compute(0)
+        Ti = np.empty((len(tgt_axes[1]), len(tgt_axes[0]), len(tgt_axes[2])))
+        cover = np.zeros(len(tgt_axes[0]), dtype=int)
+        for vals, m in partsI:
+            Ti[:, m, :] = vals
+            cover += m
+        assert np.all(cover == 1)
+        Ti1 = one.outTemperature((tgt_axes, "102")).reshape(Ti.shape)
+        di = float(np.abs(Ti - Ti1).max())
+        print(f"slab x{world}: outTemperature on a foreign mesh, max|Ti_slab - Ti_single| = {di:.3e} K")
+        assert di <= 1e-6
         d1 = float(np.abs(T - T1).max())
         d2 = float(np.abs(T - o.temperatures).max())
         print(f"slab x{world}: loops {stats[0]['outer_loops']}, PCG iterations {stats[0]['lin_iters']} (single GPU "
@@ -298,6 +331,36 @@ def main():
         assert abs(st["maxval"] - one.stats["maxval"]) <= 1e-9 * abs(one.stats["maxval"])
         assert np.allclose(partsV[0][2], one.maxcur, rtol=1e-7, atol=1e-12)
         one.invalidate()
+    dist.barrier()
+
+    # ---- Shockley3D on a mesh whose own order has the VERTICAL axis major (order 201), line-Jacobi: lateral cut chosen by the host
+    ev = Shockley3D(f"evslab{rank}")
+    ev.device = local
+    ev.problem = qv
+    ev.slab = dict(rank=rank, nranks=world, own_lo=v_lo, own_hi=v_hi, allgather=allgather_bytes)
+    ev.beta, ev.js, ev.maxerr = qv.beta, qv.js, qv.maxerr
+    ev.iterative.preconditioner = "ljac"
+    ev.iterative.maxerr = 1e-12
+    ev.iterative.maxit = 50000
+    ev.compute(LOOPS)
+    partsW = allgather_bytes((cf.slab_field_owned(qv, ev.outVoltage(), v_lo, v_hi), ev.stats))
+    ev.invalidate()
+    if rank == 0:
+        Vg = cf.slab_assemble(pv, qv.order, [x[0] for x in partsW])      # back in the numbering of the global mesh (order 201)
+        onev = Shockley3D("evsingle")
+        onev.device = 0
+        onev.problem = pv
+        onev.beta, onev.js, onev.maxerr = pv.beta, pv.js, pv.maxerr
+        onev.iterative.preconditioner = "ljac"
+        onev.iterative.maxerr = 1e-12
+        onev.iterative.maxit = 50000
+        onev.compute(LOOPS)
+        d6 = float(np.abs(Vg - onev.outVoltage()).max())
+        print(f"slab x{world} Shockley, mesh order 201 (vertical major) cut along axis 0, line-Jacobi: PCG iterations {partsW[0][1]['lin_iters']} "
+              f"(single GPU {onev.stats['lin_iters']}), max|V201_slab - V201_single| = {d6:.3e} V")
+        assert d6 <= 1e-9
+        assert abs(partsW[0][1]["err"] - onev.stats["err"]) <= 1e-6 * max(1., abs(onev.stats["err"]))
+        onev.invalidate()
     dist.barrier()
     dist.destroy_process_group()
 

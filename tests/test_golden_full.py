@@ -97,3 +97,26 @@ def test_config_C_full_vs_reference_nspcg():
     s = e.stats
     assert abs(s["err"] - float(g["loop_err"][-1])) <= 1e-3 * float(g["loop_err"][-1])      # loop error of the last loop [%]
     e.invalidate()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precond", ["jac", "ljac", "mlj"])
+def test_config_A_64_vs_cholesky(precond):
+    """BASELINE configs[0] at its full size against the reference's DIRECT algorithm (DpbMatrix: LAPACK dpbtrf + dpbtrs on 8.7 GB
+    of band storage, cholesky_matrix.hpp:90-111; tests/golden/make_golden_A64.py, timings in profiles/r02_cpu_A_64.jsonl)"""
+    g = _fixture("full_A_64_cholesky.npz")
+    p = cf.config_A(64)
+    assert tuple(int(v) for v in g["n"]) == p.n
+    s = Static3D("A")
+    s.problem = p
+    s.iterative.preconditioner = precond
+    s.iterative.maxerr = 1e-11
+    s.iterative.maxit = 200000
+    s.compute(0)
+    T = s.outTemperature()
+    assert s.stats["outer_loops"] == int(g["loops"])
+    d = np.abs(T[g["nodes"]] - g["values"])
+    assert d.max() <= 1e-3, d.max()
+    assert d.max() <= 1e-5          # in fact: the Cholesky and the PCG solutions agree far below the north-star tolerance
+    assert abs(s.maxT - float(g["maxT"])) <= 1e-5
+    s.invalidate()

@@ -30,8 +30,10 @@ def test_slab_solve_two_gpus():
     r = _torchrun(2, 29551, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "max|T_slab - T_single|" in r.stdout
+    assert "max|Ti_slab - Ti_single|" in r.stdout          # pfem_interpolate_field in slab mode
     assert "max|Tl_slab - T_slab|" in r.stdout
     assert "max|T021_slab - T021_single|" in r.stdout
     assert "max|Tm_slab - Tm_single|" in r.stdout
     assert "max|Tb_slab - Tb_single|" in r.stdout
     assert "max|V_slab - V_single|" in r.stdout
+    assert "max|V201_slab - V201_single|" in r.stdout      # vertical-major mesh: the host cuts a lateral axis

@@ -83,6 +83,13 @@ int pfem_set_layout(pfem_ctx* ctx, int layout);
 int pfem_set_mesh(pfem_ctx* ctx, const size_t n[3], const double* ax0, const double* ax1, const double* ax2,
                   const size_t stride[3]);
 
+/* Element weights along one physical axis (after pfem_set_mesh): every element integral of the stiffness operator, the load
+ * vector and the heat capacity is multiplied by w[i], i = index of the element along `axis` (n[axis] - 1 values, > 0; NULL
+ * removes the weights); gradients (currents, fluxes, Joule heat) keep the geometric spacing.  This is what the cylindrical
+ * 2-D solvers need — K_e and f_e carry the midpoint radius r of the element (therm2d.cpp:338-420, electr2d.cpp:219-230) — when
+ * a 2-D mesh is handed over as a brick mesh of one element layer.  Not combinable with pfem_set_boundary. */
+int pfem_set_axis_weight(pfem_ctx* ctx, int axis, const double* w);
+
 /* Material id per element + per-id conductivity tables c_lat/c_vert[nmat][nT] sampled by the
  * host on the grid T0 + i*dT from material->thermk(T, thickness) (thermal, therm3d.cpp:213;
  * ids distinguish (material, layer thickness) pairs, therm3d.cpp:81-114) or material->cond(T)

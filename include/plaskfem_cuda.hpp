@@ -343,6 +343,8 @@ class Context {
         m.strides(s);
         check(pfem_set_mesh(ctx_, n, m.axis[0].data(), m.axis[1].data(), m.axis[2].data(), s));
     }
+    // cylindrical 2-D solvers on a one-layer brick mesh: element weights = midpoint radii along the radial axis
+    void set_axis_weight(int axis, const std::vector<double>& w) { check(pfem_set_axis_weight(ctx_, axis, w.empty() ? nullptr : w.data())); }
     void set_materials(const std::vector<uint32_t>& ids, const Tables& t) {
         check(pfem_set_materials(ctx_, ids.data(), t.nmat, t.T0, t.dT, t.nT, t.lat.data(), t.vert.data()));
     }

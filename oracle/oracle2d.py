@@ -1,0 +1,308 @@
+"""CPU restatement of PLaSK's TWO-DIMENSIONAL FEM solvers — TEST INFRASTRUCTURE, never imported by plask_b200/ (SURVEY.md 8f-4).
+
+    Static2D / StaticCyl     thermal.static      solvers/thermal/static/therm2d.cpp
+    Shockley2D / ShockleyCyl electrical.shockley solvers/electrical/shockley/electr2d.cpp + beta.hpp
+
+It is written independently of the 3-D code paths (oracle.py, fem3d_oracle.c, the CUDA library): 4-node rectangles assembled
+entry by entry into a scipy sparse matrix and solved directly (SuperLU) — the stand-in for the reference's Cholesky — so that
+the brick-mesh embedding the product uses for these solvers (plask_b200/solvers2d.py: one element layer, z-invariant data,
+element weights r for the cylindrical case) is checked against genuinely two-dimensional arithmetic.
+
+Pins: solvers/electrical/shockley/tests/shockley2d.py:40-118 (analytic current, capacitance and heat of Shockley2D and
+ShockleyCyl, T-dependent beta) in tests/test_oracle2d_pin.py; Static2D / StaticCyl have no numeric fixture in the reference
+(solvers/thermal/static/tests/therm.py checks providers only) and are pinned by analytic solutions — "parity unpinned" by
+reference fixtures for the thermal pair.
+
+Mesh convention: axes = [x (tran or r), y (vert)], node (i0, i1) -> i0 * n1 + i1, element (i0, i1) -> i0 * (n1 - 1) + i1."""
+import numpy as np
+
+EPS0 = 8.854187817e-12   # F/m  (plask/phys.hpp)
+
+
+def table_lookup(tab, mat, T0, dT, T):
+    """linear interpolation in the per-material tables, clamped at both ends (the host samples material->thermk / ->cond)"""
+    tab = np.asarray(tab)
+    nT = tab.shape[1]
+    t = np.clip((np.asarray(T, dtype=np.float64) - T0) / dT, 0., float(nT - 1))
+    i = np.minimum(t.astype(np.int64), nT - 2)
+    f = t - i
+    a, b = tab[mat, i], tab[mat, i + 1]
+    return a + f * (b - a)
+
+
+class Mesh2D:
+    def __init__(self, x, y):
+        self.x, self.y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+        self.n = (len(self.x), len(self.y))
+        self.N = self.n[0] * self.n[1]
+        self.E = (self.n[0] - 1) * (self.n[1] - 1)
+        n0, n1 = self.n
+        i0, i1 = np.meshgrid(np.arange(n0 - 1), np.arange(n1 - 1), indexing="ij")
+        i0, i1 = i0.ravel(), i1.ravel()
+        self.ei0, self.ei1 = i0, i1
+        # lower-left, lower-right, upper-right, upper-left (the i1, i2, i3, i4 of therm2d.cpp:186-191)
+        self.ll = i0 * n1 + i1
+        self.lr = (i0 + 1) * n1 + i1
+        self.ur = (i0 + 1) * n1 + i1 + 1
+        self.ul = i0 * n1 + i1 + 1
+        self.w = (self.x[1:] - self.x[:-1])[i0]
+        self.h = (self.y[1:] - self.y[:-1])[i1]
+        self.rmid = (0.5 * (self.x[1:] + self.x[:-1]))[i0]       # midpoint.rad_r()
+
+
+def assemble(mesh, kx, ky, f, cyl):
+    """setMatrix: therm2d.cpp:186-279 (Cartesian) / :338-420 (cylindrical: K_e and f_e times the midpoint radius); electr2d.cpp:281-316
+    + setLocalMatrix (:190-230).  kx, ky: element conductivities already scaled by h/w and w/h.  Returns (A csr, B)."""
+    import scipy.sparse as sp
+    m = mesh
+    r = m.rmid if cyl else 1.
+    k_diag = r * (kx + ky) / 3.
+    k_hor = r * (-2. * kx + ky) / 6.      # k21 = k43: lower-left <-> lower-right, upper-left <-> upper-right
+    k_dia = r * -(kx + ky) / 6.           # k31 = k42
+    k_ver = r * (kx - 2. * ky) / 6.       # k41 = k32: lower-left <-> upper-left, lower-right <-> upper-right
+    nd = [m.ll, m.lr, m.ur, m.ul]
+    kind = [[0, 1, 2, 3], [1, 0, 3, 2], [2, 3, 0, 1], [3, 2, 1, 0]]   # 0 diag, 1 horizontal edge, 2 diagonal, 3 vertical edge
+    vals = [k_diag, k_hor, k_dia, k_ver]
+    rows, cols, data = [], [], []
+    for a in range(4):
+        for b in range(4):
+            rows.append(nd[a]); cols.append(nd[b]); data.append(vals[kind[a][b]])
+    A = sp.coo_matrix((np.concatenate(data), (np.concatenate(rows), np.concatenate(cols))), shape=(m.N, m.N)).tocsr()
+    B = np.zeros(m.N)
+    if f is not None:
+        fe = (r * f) if cyl else f
+        for a in range(4):
+            np.add.at(B, nd[a], fe)
+    return A, B
+
+
+def solve_dirichlet(A, B, nodes, values):
+    """applyBC (matrix.hpp:111-118) + direct solve: rows of fixed nodes become identity, the columns move to the right-hand side"""
+    import scipy.sparse.linalg as spl
+    N = A.shape[0]
+    fixed = np.zeros(N, dtype=bool)
+    fixed[nodes] = True
+    xD = np.zeros(N)
+    xD[nodes] = values
+    free = ~fixed
+    X = xD.copy()
+    if free.any():
+        Aff = A[free][:, free].tocsc()
+        rhs = B[free] - A[free][:, fixed] @ xD[fixed]
+        X[free] = spl.spsolve(Aff, rhs)
+    return X
+
+
+class Static2DOracle:
+    """ThermalFem2DSolver<Cartesian / Cylindrical> (therm2d.cpp): nonlinear loop of compute (:438-492) with boundary conditions of
+    the first kind and the volumetric heat source."""
+
+    def __init__(self, x, y, elem_mat, T0, dT, tab_lat, tab_vert, bc_nodes, bc_values, heat=None, inittemp=300., maxerr=0.05, cyl=False):
+        self.mesh = Mesh2D(x, y)
+        self.elem_mat = np.asarray(elem_mat, dtype=np.int64)
+        self.T0, self.dT, self.tab_lat, self.tab_vert = T0, dT, np.asarray(tab_lat), np.asarray(tab_vert)
+        self.bc_nodes, self.bc_values = np.asarray(bc_nodes, dtype=np.int64), np.asarray(bc_values, dtype=np.float64)
+        self.heat = np.zeros(self.mesh.E) if heat is None else np.asarray(heat, dtype=np.float64)
+        self.maxerr, self.cyl = maxerr, cyl
+        self.temperatures = np.full(self.mesh.N, float(inittemp))
+        self.history = []
+        self.maxT = float(inittemp)
+        self.conds = None
+
+    def _conds(self):
+        m, T = self.mesh, self.temperatures
+        temp = 0.25 * (T[m.ll] + T[m.lr] + T[m.ul] + T[m.ur])                                    # :200
+        return (table_lookup(self.tab_lat, self.elem_mat, self.T0, self.dT, temp),
+                table_lookup(self.tab_vert, self.elem_mat, self.T0, self.dT, temp))
+
+    def compute(self, loops=0):
+        m = self.mesh
+        loop, toterr = 0, 0.
+        while True:
+            kl, kv = self._conds()
+            self.conds = np.stack([kl, kv], axis=1)
+            kx = kl * m.h / m.w                                                                    # :206-207
+            ky = kv * m.w / m.h
+            f = 0.25e-12 * m.w * m.h * self.heat                                                   # :210
+            A, B = assemble(m, kx, ky, f, self.cyl)
+            Tn = solve_dirichlet(A, B, self.bc_nodes, self.bc_values)
+            err = float(np.abs(Tn - self.temperatures).max())
+            self.temperatures = Tn
+            self.maxT = float(Tn.max())
+            toterr = max(toterr, err)
+            loop += 1
+            self.history.append(dict(loop=loop, err=err, maxT=self.maxT))
+            if not (err > self.maxerr and (loops == 0 or loop < loops)):
+                break
+        return toterr
+
+    def heat_fluxes(self):
+        """saveHeatFluxes (therm2d.cpp:494-527): -k grad T at the element midpoints, W/m^2 (1e6: um -> m)"""
+        m, T = self.mesh, self.temperatures
+        kl, kv = self._conds()
+        gx = 0.5e6 * (-T[m.ll] + T[m.lr] - T[m.ul] + T[m.ur]) / m.w
+        gy = 0.5e6 * (-T[m.ll] - T[m.lr] + T[m.ul] + T[m.ur]) / m.h
+        return np.stack([-kl * gx, -kv * gy], axis=1)
+
+
+class Shockley2DOracle:
+    """ElectricalFem2DSolver<Cartesian / Cylindrical> + BetaSolver (electr2d.cpp, beta.hpp:43-46).  Junctions: `acts` = list of
+    dicts(left, right, bottom, top) in element / node-row indices like setupActiveRegions (:61-168); elem_junc[e] = k + 1 for the
+    elements of junction k; elem_role: 1 p-contact, 2 n-contact."""
+
+    def __init__(self, x, y, elem_mat, T0, dT, tab_lat, tab_vert, bc_nodes, bc_values, elem_junc, acts, elem_role=None,
+                 beta=11., js=1., pcond=5., ncond=50., start_cond=(0., 5.), maxerr=0.05, Te=300., cyl=False, length=1000.,
+                 stable=False, noheat=None, eps=None):
+        self.mesh = Mesh2D(x, y)
+        m = self.mesh
+        self.elem_mat = np.asarray(elem_mat, dtype=np.int64)
+        self.T0, self.dT, self.tab_lat, self.tab_vert = T0, dT, np.asarray(tab_lat), np.asarray(tab_vert)
+        self.bc_nodes, self.bc_values = np.asarray(bc_nodes, dtype=np.int64), np.asarray(bc_values, dtype=np.float64)
+        self.elem_junc = np.asarray(elem_junc, dtype=np.int64)
+        self.elem_role = np.zeros(m.E, dtype=np.int64) if elem_role is None else np.asarray(elem_role, dtype=np.int64)
+        self.acts = [dict(a) for a in acts]
+        off = 0
+        for a in self.acts:
+            a["offset"] = off
+            a["height"] = m.y[a["top"]] - m.y[a["bottom"]]                                         # :156
+            off += a["right"] - a["left"]                                                          # :157
+        self.junction_conductivity = np.tile(np.asarray(start_cond, dtype=np.float64), (max(off, 1), 1))
+        self.beta = beta if callable(beta) else (lambda T, b=float(beta): b)
+        self.js = js if callable(js) else (lambda T, j=float(js): j)
+        self.pcond, self.ncond, self.maxerr, self.cyl, self.length, self.stable = pcond, ncond, maxerr, cyl, length, stable
+        self.Te = np.full(m.E, float(Te)) if np.isscalar(Te) else np.asarray(Te, dtype=np.float64)
+        self.noheat = np.zeros(m.E, dtype=bool) if noheat is None else np.asarray(noheat).astype(bool)
+        self.eps = np.ones(m.E) if eps is None else np.asarray(eps, dtype=np.float64)
+        self.potentials = np.zeros(m.N)
+        self.currents = np.zeros((m.E, 2))
+        self.conds = np.zeros((m.E, 2))
+        self.loopno = 0
+        self.history = []
+        self.maxcur = np.zeros(2)
+
+    def _elem(self, i0, i1):
+        return i0 * (self.mesh.n[1] - 1) + i1
+
+    def load_conductivities(self):
+        """loadConductivities, electr2d.cpp:330-352"""
+        m = self.mesh
+        c = table_lookup(self.tab_lat, self.elem_mat, self.T0, self.dT, self.Te)
+        d = table_lookup(self.tab_vert, self.elem_mat, self.T0, self.dT, self.Te)
+        self.conds = np.stack([c, d], axis=1)
+        self.conds[self.elem_role == 1] = self.pcond
+        self.conds[self.elem_role == 2] = self.ncond
+        for e in np.nonzero(self.elem_junc)[0]:
+            a = self.acts[self.elem_junc[e] - 1]
+            self.conds[e] = self.junction_conductivity[a["offset"] + m.ei0[e]]                     # :341 (absolute index0)
+            if np.isnan(self.conds[e, 1]) or abs(self.conds[e, 1]) < 1e-16:
+                self.conds[e, 1] = 1e-16
+
+    def save_conductivities(self):
+        """saveConductivities, electr2d.cpp:354-360"""
+        for a in self.acts:
+            r = (a["top"] + a["bottom"]) // 2
+            for i in range(a["left"], a["right"]):
+                self.junction_conductivity[a["offset"] + i] = self.conds[self._elem(i, r)]
+
+    def _update_junctions(self):
+        """setMatrix :238-262"""
+        m, V = self.mesh, self.potentials
+        n1 = m.n[1]
+        for e in np.nonzero(self.elem_junc)[0]:
+            k = self.elem_junc[e] - 1
+            a = self.acts[k]
+            left, right = m.ei0[e], m.ei0[e] + 1
+            U = 0.5 * (V[left * n1 + a["top"]] - V[left * n1 + a["bottom"]] + V[right * n1 + a["top"]] - V[right * n1 + a["bottom"]])
+            jy = 0.1 * self.conds[e, 1] * U / a["height"]
+            ti = self._elem(m.ei0[e], (a["top"] + a["bottom"]) // 2)
+            T = self.Te[ti]
+            jy = abs(jy)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                cond = np.array([0., 10. * jy * a["height"] * self.beta(T) / np.log(1e7 * jy / self.js(T) + 1.)])   # beta.hpp:43-46
+            if self.stable:
+                cond = 0.5 * (self.conds[e] + cond)
+            self.conds[e] = cond
+            if np.isnan(self.conds[e, 1]) or abs(self.conds[e, 1]) < 1e-16:
+                self.conds[e, 1] = 1e-16
+
+    def compute(self, loops=0):
+        """compute, electr2d.cpp:362-440"""
+        m = self.mesh
+        self.load_conductivities()
+        noactive = len(self.acts) == 0
+        minj = 100e-7
+        loop, toterr = 0, 0.
+        while True:
+            if self.loopno != 0:
+                self._update_junctions()
+            kx = self.conds[:, 0] * m.h / m.w
+            ky = self.conds[:, 1] * m.w / m.h
+            A, B = assemble(m, kx, ky, None, self.cyl)
+            self.potentials = V = solve_dirichlet(A, B, self.bc_nodes, self.bc_values)
+            dvx = -0.05 * (-V[m.ll] + V[m.lr] - V[m.ul] + V[m.ur]) / m.w
+            dvy = -0.05 * (-V[m.ll] - V[m.lr] + V[m.ul] + V[m.ur]) / m.h
+            cur = np.stack([self.conds[:, 0] * dvx, self.conds[:, 1] * dvy], axis=1)
+            a2 = (cur ** 2).sum(axis=1)
+            sel = a2 if noactive else np.where(self.elem_junc > 0, a2, -1.)
+            mcur = 0.
+            if sel.size and sel.max() > 0.:
+                k = int(np.argmax(sel))
+                mcur, self.maxcur = float(sel[k]), cur[k].copy()
+            err = float(((self.currents - cur) ** 2).sum(axis=1).max())
+            self.currents = cur
+            mcur = np.sqrt(mcur)
+            err = 100. * np.sqrt(err) / max(mcur, minj)
+            if (loop != 0 or mcur >= minj) and err > toterr:
+                toterr = err
+            self.loopno += 1
+            loop += 1
+            self.history.append(dict(loop=loop, err=err, mcur=mcur))
+            if not (err > self.maxerr and (loops == 0 or loop < loops)):
+                break
+        self.save_conductivities()
+        return toterr
+
+    # ---- integrals (electr2d.cpp:466-505, 574-649)
+    def integrate_current(self, vindex, onlyactive=False):
+        m = self.mesh
+        res = 0.
+        for i in range(m.n[0] - 1):
+            e = self._elem(i, vindex)
+            if not onlyactive or self.elem_junc[e]:
+                if self.cyl:
+                    res += self.currents[e, 1] * (m.x[i + 1] ** 2 - m.x[i] ** 2)
+                else:
+                    res += self.currents[e, 1] * (m.x[i + 1] - m.x[i])
+        return res * np.pi * 0.01 if self.cyl else res * self.length * 0.01
+
+    def get_total_current(self, nact=0):
+        a = self.acts[nact]
+        return self.integrate_current((a["bottom"] + a["top"]) // 2, True)
+
+    def heat_densities(self):
+        m, V = self.mesh, self.potentials
+        dvx = 0.5e6 * (-V[m.ll] + V[m.lr] - V[m.ul] + V[m.ur]) / m.w
+        dvy = 0.5e6 * (-V[m.ll] - V[m.lr] + V[m.ul] + V[m.ur]) / m.h
+        return np.where(self.noheat, 0., self.conds[:, 0] * dvx * dvx + self.conds[:, 1] * dvy * dvy)
+
+    def get_total_heat(self):
+        m = self.mesh
+        H = self.heat_densities()
+        if self.cyl:
+            return 2e-15 * np.pi * float((m.w * m.h * m.rmid * H).sum())
+        return self.length * 1e-15 * float((m.w * m.h * H).sum())
+
+    def get_total_energy(self):
+        m, V = self.mesh, self.potentials
+        dvx = 0.5e6 * (-V[m.ll] + V[m.lr] - V[m.ul] + V[m.ur]) / m.w
+        dvy = 0.5e6 * (-V[m.ll] - V[m.lr] + V[m.ul] + V[m.ur]) / m.h
+        w = self.eps * (dvx * dvx + dvy * dvy)
+        if self.cyl:
+            return 2. * np.pi * 0.5e-18 * EPS0 * float((m.w * m.h * m.rmid * w).sum())
+        return self.length * 0.5e-18 * EPS0 * float((m.w * m.h * w).sum())
+
+    def get_capacitance(self):
+        vals = np.unique(self.bc_values)
+        assert len(vals) == 2
+        U = float(vals[1] - vals[0])
+        return 2e12 * self.get_total_energy() / (U * U)

@@ -92,6 +92,7 @@ SYMBOLS = {
     "pfem_solve_thermal": (C.c_int, [_vp, C.POINTER(Opts), C.POINTER(Stats)]),
     "pfem_solve_shockley": (C.c_int, [_vp, C.POINTER(Opts), C.POINTER(Stats)]),
     "pfem_set_capacity": (C.c_int, [_vp, C.c_uint32, C.c_uint32, c_dp]),
+    "pfem_set_axis_weight": (C.c_int, [_vp, C.c_int, c_dp]),
     "pfem_solve_dynamic": (C.c_int, [_vp, C.POINTER(Opts), C.POINTER(Dynamic), C.POINTER(Stats)]),
     "pfem_get_field": (C.c_int, [_vp, c_dp]),
     "pfem_interpolate_field": (C.c_int, [_vp, _szp, c_dp, c_dp, c_dp, _szp, c_dp]),

@@ -579,7 +579,7 @@ __device__ __forceinline__ void brick_edge_sums(const Grid& g, const double* __r
     s2 = -lll + llu - lul + luu - ull + ulu - uul + uuu;
 }
 __device__ __forceinline__ void brick_sizes(const Grid& g, const int (&pi)[3], double& d0, double& d1, double& d2) {
-    const double* h[3] = {g.hI, g.hJ, g.hK};
+    const double* h[3] = {g.uI, g.uJ, g.uK};
     d0 = h[g.dim_of_phys[0]][pi[0]];
     d1 = h[g.dim_of_phys[1]][pi[1]];
     d2 = h[g.dim_of_phys[2]][pi[2]];

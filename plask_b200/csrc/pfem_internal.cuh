@@ -41,6 +41,9 @@ struct Grid {
     // spacings per index-space axis and their reciprocals; each array has one guard entry in
     // front and one behind (value 1), so h[-1] and h[n-1] are readable.
     const double *hI, *hJ, *hK, *rI, *rJ, *rK;
+    // geometric spacings for gradients (currents, fluxes, heat): equal to h unless pfem_set_axis_weight made h = w * spacing and
+    // r = w / spacing on one axis (cylindrical 2-D solvers: every element integral carries the factor r of its midpoint)
+    const double *uI, *uJ, *uK;
 };
 
 // ---- slab mode (one context per GPU, peers mapped with CUDA IPC over NVLink) ----------------

@@ -57,6 +57,9 @@ struct pfem_ctx {
     bool has_excluded = false, source_set = false;
     // small arrays
     double* hbuf = nullptr;
+    std::vector<double> h_host;          // host copy of hbuf: per index-space axis h, r (weighted) and u (geometric spacing)
+    size_t h_off[3] = {0, 0, 0}, r_off[3] = {0, 0, 0}, u_off[3] = {0, 0, 0};
+    bool weighted = false;               // pfem_set_axis_weight is in force (2-D cylindrical embedding)
     double *tab_lat = nullptr, *tab_vert = nullptr;
     uint32_t nmat = 0, nT = 0;
     double T0 = 0, dT = 1;
@@ -426,14 +429,15 @@ extern "C" int pfem_set_mesh(pfem_ctx* ctx, const size_t n[3], const double* ax0
     g.E = (idx_t)(g.nI - 1) * (g.nJ - 1) * (g.nK - 1);
     g.kown0 = 0; g.kown1 = g.nK;
 
-    // spacing arrays with one guard entry (value 1) on both sides
+    // spacing arrays with one guard entry (value 1) on both sides: h, r = 1/h and the geometric spacing u per index-space axis
     const int cnt[3] = {g.nI - 1, g.nJ - 1, g.nK - 1};
     const int phys_of_dim[3] = {im, jm, km};
     size_t tot = 0;
-    for (int d = 0; d < 3; ++d) tot += 2 * (size_t)(cnt[d] + 2);
-    std::vector<double> hb(tot, 1.0);
+    for (int d = 0; d < 3; ++d) tot += 3 * (size_t)(cnt[d] + 2);
+    std::vector<double>& hb = ctx->h_host;
+    hb.assign(tot, 1.0);
     size_t off = 0;
-    size_t hoff[3], roff[3];
+    size_t* hoff = ctx->h_off; size_t* roff = ctx->r_off; size_t* uoff = ctx->u_off;
     for (int d = 0; d < 3; ++d) {
         hoff[d] = off + 1;
         for (int i = 0; i < cnt[d]; ++i) hb[hoff[d] + i] = ax[phys_of_dim[d]][i + 1] - ax[phys_of_dim[d]][i];
@@ -441,13 +445,17 @@ extern "C" int pfem_set_mesh(pfem_ctx* ctx, const size_t n[3], const double* ax0
         roff[d] = off + 1;
         for (int i = 0; i < cnt[d]; ++i) hb[roff[d] + i] = 1.0 / hb[hoff[d] + i];
         off += cnt[d] + 2;
+        uoff[d] = off + 1;
+        for (int i = 0; i < cnt[d]; ++i) hb[uoff[d] + i] = hb[hoff[d] + i];
+        off += cnt[d] + 2;
     }
+    ctx->weighted = false;
     TRY(dev_alloc(ctx, &ctx->hbuf, tot, 0));
     CU(cudaMemcpyAsync(ctx->hbuf, hb.data(), tot * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    g.hI = ctx->hbuf + hoff[0]; g.rI = ctx->hbuf + roff[0];
-    g.hJ = ctx->hbuf + hoff[1]; g.rJ = ctx->hbuf + roff[1];
-    g.hK = ctx->hbuf + hoff[2]; g.rK = ctx->hbuf + roff[2];
+    g.hI = ctx->hbuf + hoff[0]; g.rI = ctx->hbuf + roff[0]; g.uI = ctx->hbuf + uoff[0];
+    g.hJ = ctx->hbuf + hoff[1]; g.rJ = ctx->hbuf + roff[1]; g.uJ = ctx->hbuf + uoff[1];
+    g.hK = ctx->hbuf + hoff[2]; g.rK = ctx->hbuf + roff[2]; g.uK = ctx->hbuf + uoff[2];
 
     const size_t N = (size_t)g.NP, G = (size_t)g.G;
     TRY(dev_alloc(ctx, &ctx->x, N, G));
@@ -514,6 +522,37 @@ static int download_elem(pfem_ctx* ctx, const T* s0, const T* s1, const T* s2, T
     k_elem_compact<T, NC><<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g, s0, s1, s2, (T*)ctx->stage);
     KCHECK(); LAUNCHED(1);
     CU(cudaMemcpyAsync(host, ctx->stage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PFEM_OK;
+}
+
+// Weight of the elements along one physical axis: every element integral of the operator, the load vector and the heat capacity is
+// multiplied by w[index of the element along `axis`] — h := w * spacing, r := w / spacing in the spacing tables, while gradients
+// keep the geometric spacing.  This is how the cylindrical 2-D solvers (therm2d.cpp:338-420: K_e and f_e times the midpoint
+// radius r) run on the brick kernels: axis = the radial axis, w = element midpoint radii.  w == NULL removes the weights.
+extern "C" int pfem_set_axis_weight(pfem_ctx* ctx, int axis, const double* w) {
+    NEED_MESH();
+    if (axis < 0 || axis > 2) FAIL(PFEM_ERR_BAD_INPUT, "axis must be 0, 1 or 2");
+    if (ctx->surf.nrows) FAIL(PFEM_ERR_BAD_INPUT, "element weights and boundary conditions of the 2nd / 3rd kind cannot be combined");
+    const Grid& g = ctx->g;
+    const int d = g.dim_of_phys[axis];
+    const int cnt = g.pn[axis] - 1;
+    std::vector<double>& hb = ctx->h_host;
+    for (int i = 0; i < cnt; ++i) {
+        const double wi = w ? w[i] : 1.;
+        if (!(wi > 0.) || !(wi < 1e300)) FAIL(PFEM_ERR_BAD_INPUT, "weight %d of axis %d is not a positive finite number", i, axis);
+        const double u = hb[ctx->u_off[d] + i];
+        hb[ctx->h_off[d] + i] = wi * u;
+        hb[ctx->r_off[d] + i] = wi / u;
+    }
+    bool any = false;
+    for (int dd = 0; dd < 3 && !any; ++dd) {
+        const int c = (dd == 0 ? g.nI : dd == 1 ? g.nJ : g.nK) - 1;
+        for (int i = 0; i < c && !any; ++i) any = hb[ctx->h_off[dd] + i] != hb[ctx->u_off[dd] + i];
+    }
+    ctx->weighted = any;
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpyAsync(ctx->hbuf, hb.data(), hb.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return PFEM_OK;
 }
@@ -695,6 +734,7 @@ extern "C" int pfem_set_boundary(pfem_ctx* ctx, const pfem_boundary* b) {
     if ((b->has_flux && !b->flux) || (b->has_conv && (!b->conv_coeff || !b->conv_ambient)) ||
         (b->has_rad && (!b->rad_emissivity || !b->rad_ambient)))
         FAIL(PFEM_ERR_BAD_INPUT, "boundary condition flags without values");
+    if (ctx->weighted) FAIL(PFEM_ERR_BAD_INPUT, "element weights (pfem_set_axis_weight) and boundary conditions of the 2nd / 3rd kind cannot be combined");
     if (b->verbatim && b->has_rad && ctx->nranks > 1)
         FAIL(PFEM_ERR_BAD_INPUT, "slab mode: verbatim radiation reads temperatures[0..7] of the whole mesh (therm3d.cpp:265); use the corrected form");
     // dense (ABI) and lattice strides of the physical axes; element extents along them

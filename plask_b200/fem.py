@@ -64,6 +64,15 @@ class DeviceFem:
         self._ck(self.lib.pfem_set_materials(self.ctx, m.ctypes.data_as(L._u32p), a.shape[0], float(T0), float(dT),
                                              a.shape[1], _dp(a), _dp(b)))
 
+    def set_axis_weight(self, axis, w):
+        """element weights along a physical axis (cylindrical 2-D embedding: midpoint radii); None removes them"""
+        if w is None:
+            self._ck(self.lib.pfem_set_axis_weight(self.ctx, int(axis), None))
+            return
+        a = _f64(w)
+        assert a.ndim == 1 and a.size == self.n[axis] - 1
+        self._ck(self.lib.pfem_set_axis_weight(self.ctx, int(axis), _dp(a)))
+
     def set_capacity(self, cp_dens):
         """cp(T)*dens(T) [J/(m^3 K)] per material id on the temperature grid of set_materials (Dynamic3D)."""
         a = _f64(cp_dens)

@@ -226,3 +226,96 @@ def cooling_exact(p, t, a=50.):
     z = np.asarray(p.axes[2])
     L, al = p.meta["L"], p.meta["alpha"]
     return 300. + a * np.sin(np.pi * z / (2. * L)) * np.exp(-al * (np.pi / (2. * L)) ** 2 * t)
+
+
+# ------------------------------------------------------------------------------------------ 2-D solvers
+
+def _divide(edges, k):
+    out = [edges[0]]
+    for a, b in zip(edges[:-1], edges[1:]):
+        out += [a + (b - a) * (i + 1) / k for i in range(k)]
+    return np.array(out)
+
+
+GAAS_COND = 1e2 * 1.60217733e-19 * 8000. * 1e16      # undoped GaAs at 300 K (like shockley3d_reference_problem)
+
+
+def shockley2d_reference_problem(cyl=False, nx=2, ny=1):
+    """solvers/electrical/shockley/tests/shockley2d.py as a Problem2D: Shockley2D_Test.setUp (:36-55) or, cyl=True, ShockleyCyl_Test.setUp
+    (:78-103).  Meshes = DivideGenerator with prediv (2, 1) on the object boundaries (nx, ny refine them for convergence checks)."""
+    from plask_b200.solvers2d import Problem2D
+    if not cyl:
+        x = _divide([0., 1000.], nx)
+        y = _divide([0., 300., 300.02, 600.02], ny)
+    else:
+        x = _divide([0., 400., 600., 1000.], nx)
+        y = _divide([0., 300., 300.02, 600.02, 700.02], ny)
+    sig = np.array([[1e9, 1e9], [GAAS_COND, GAAS_COND], [0.55e-14, 0.55e-14]])
+    xm, ym = 0.5 * (x[1:] + x[:-1]), 0.5 * (y[1:] + y[:-1])
+    X, Y = np.meshgrid(xm, ym, indexing="ij")
+    mat = np.zeros(X.shape, dtype=np.uint32)
+    is_j = (Y > 300.) & (Y < 300.02)
+    mat[is_j] = 1
+    if cyl:
+        mat[(Y > 600.02) & (X > 400.) & (X < 600.)] = 2          # the gap of the shelf: air
+    n0, n1 = len(x), len(y)
+    ng = np.arange(n0 * n1).reshape(n0, n1)
+    if cyl:
+        top = ng[(x <= 400. + 1e-9) | (x >= 600. - 1e-9), -1]    # mesh.TopOf(cont): both instances of the contact
+    else:
+        top = ng[:, -1]
+    bot = ng[:, 0]
+    p = Problem2D("shockley2d.py", "shockley", x, y, mat.ravel(), 300., 100., sig, sig.copy(),
+                  np.concatenate([top, bot]).astype(np.uintp), np.concatenate([np.zeros(top.size), np.ones(bot.size)]), cyl=cyl)
+    p.elem_junc = is_j.astype(np.uint32).ravel()
+    p.noheat = (mat == 2).astype(np.uint8).ravel()
+    p.meta["eps"] = np.array([1., 12.9, 1.])[mat.ravel()]
+    p.beta, p.js, p.maxerr = 10., 1., 1e-5
+    return p
+
+
+def active_regions_2d(p2):
+    """setupActiveRegions of electr2d.cpp:61-168 for rectangular junctions: one dict(left, right, bottom, top) per junction number"""
+    ej = np.asarray(p2.elem_junc).reshape(p2.n[0] - 1, p2.n[1] - 1)
+    acts = []
+    for k in range(int(ej.max())):
+        cols, rows = np.nonzero(ej == k + 1)
+        acts.append(dict(left=int(cols.min()), right=int(cols.max()) + 1, bottom=int(rows.min()), top=int(rows.max()) + 1))
+    return acts
+
+
+def oracle_shockley2d(p2, **kw):
+    from oracle import oracle2d
+    kw.setdefault("beta", p2.beta)
+    kw.setdefault("js", p2.js)
+    kw.setdefault("maxerr", p2.maxerr)
+    return oracle2d.Shockley2DOracle(p2.x, p2.y, p2.elem_mat, p2.T0, p2.dT, p2.tab_lat, p2.tab_vert, p2.bc_nodes, p2.bc_values,
+                                     p2.elem_junc, active_regions_2d(p2), elem_role=p2.elem_role, pcond=p2.pcond, ncond=p2.ncond,
+                                     start_cond=p2.start_cond, cyl=p2.cyl, length=p2.length, noheat=p2.noheat,
+                                     eps=p2.meta.get("eps"), **kw)
+
+
+def oracle_static2d(p2, **kw):
+    from oracle import oracle2d
+    return oracle2d.Static2DOracle(p2.x, p2.y, p2.elem_mat, p2.T0, p2.dT, p2.tab_lat, p2.tab_vert, p2.bc_nodes, p2.bc_values,
+                                   heat=p2.heat, inittemp=p2.inittemp, maxerr=p2.maxerr, cyl=p2.cyl, **kw)
+
+
+def thermal2d_problem(n=(33, 41), cyl=False, seed=3):
+    """layered GaAs / AlGaAs / Cu block with k(T) tables (the thermal ids of configs.thermal_tables), a hot disc / stripe near the
+    axis, 300 K on the bottom edge; graded mesh in both directions"""
+    from plask_b200.solvers2d import Problem2D
+    x = cf.graded_axis(n[0], 0.3, 3.0)
+    x = x - x[0]
+    y = np.concatenate([[0.], np.cumsum(np.resize([0.07, 0.0795, 0.12, 0.5, 0.03], n[1] - 1))])
+    T0, dT, lat, vert = cf.thermal_tables()
+    xm, ym = 0.5 * (x[1:] + x[:-1]), 0.5 * (y[1:] + y[:-1])
+    X, Y = np.meshgrid(xm, ym, indexing="ij")
+    J = np.broadcast_to(np.arange(n[1] - 1)[None, :], X.shape)
+    mat = (J % 2).astype(np.uint32)                      # GaAs / AlGaAs pairs
+    mat[J < 4] = 5                                       # Cu heat spreader at the bottom
+    heat = np.where((X < 0.35 * x[-1]) & (J > (n[1] - 1) // 2) & (J < (n[1] - 1) // 2 + 6), 4e16, 1e13)
+    ng = np.arange(n[0] * n[1]).reshape(n)
+    p = Problem2D("thermal2d", "thermal", x, y, mat.ravel(), T0, dT, lat, vert, ng[:, 0].astype(np.uintp), np.full(n[0], 300.),
+                  heat=heat.ravel(), cyl=cyl)
+    return p

@@ -41,7 +41,8 @@
 #include "kernels_ml.cuh"
 
 #ifndef PFEM_X
-#define PFEM_X 5   // experiment mask of k_fpcg: 1 = phase-1 loads hoisted (-1.7 %), 2 = x fetched two planes ahead (+1.5 %: off), 4 = vertical stiffness per element (-0.5 %)
+#define PFEM_X 13   // experiment mask of k_fpcg: 1 = phase-1 loads hoisted (-1.7 %), 2 = x fetched two planes ahead in registers (+1.5 %: off),
+                    // 4 = vertical stiffness per element (-0.5 %), 8 = x of the own tile through the TMA stage instead of a global load (-3 %)
 #endif
 
 namespace pfem {
@@ -68,7 +69,8 @@ struct FusedTile {
     static constexpr int LAYER = 2 * CHALF;
     static constexpr int NRED = 7;
     static constexpr size_t smem_bytes(int ns, int mode, int lk, bool iso = false) {
-        return 128 + sizeof(double) * ((size_t)ns * ((mode == 1 ? 6 : mode >= 2 ? 5 : 4) - (iso ? 1 : 0)) * BOXP + 2 * PLANE + 2 * LAYER + 32 * NRED + 2 * (size_t)(lk + 2)) +
+        return 128 + sizeof(double) * ((size_t)ns * ((mode == 1 ? 6 : mode >= 2 ? 5 : 4) - (iso ? 1 : 0)) * BOXP + (((PFEM_X & 9) == 9) && mode >= 1 ? (size_t)ns * TI * TJ : 0) +
+                                       2 * PLANE + 2 * LAYER + 32 * NRED + 2 * (size_t)(lk + 2)) +
                16 * 8 + 16;
     }
 };
@@ -85,7 +87,8 @@ template <int TJ, int RJ, int NS, int MINB, int VDIM, int MODE, bool ISO = false
 __global__ void __launch_bounds__(32 * (TJ / RJ), MINB)
 k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_q,
        const __grid_constant__ CUtensorMap tm_p, const __grid_constant__ CUtensorMap tm_d,
-       const __grid_constant__ CUtensorMap tm_cl, const __grid_constant__ CUtensorMap tm_cv, const Grid g, const ChunkTab ck,
+       const __grid_constant__ CUtensorMap tm_cl, const __grid_constant__ CUtensorMap tm_cv, const __grid_constant__ CUtensorMap tm_x,
+       const Grid g, const ChunkTab ck,
        double* __restrict__ r_out, double* __restrict__ q_out, double* __restrict__ p_out, double* __restrict__ x,
        Scalars* sc, double* partials, const PeerOut po, const CoarseAdd ca, const double* __restrict__ mass) {
     typedef FusedTile<TJ> T;
@@ -102,7 +105,10 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
 
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     double* const sRaw = reinterpret_cast<double*>(smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u));  // [NS][NB][BOXP]
-    double* const sP = sRaw + (size_t)NS * NB * BOXP;   // [2][PLANE]
+    constexpr bool XTMA = ((PFEM_X & 9) == 9) && FUSED;   // x of the own tile arrives with the stage (box TI x TJ, no halo) instead of a per-thread
+    constexpr int XBOX = TI * TJ;                  // global load one step ahead, whose HBM latency under load exceeds a step (ncu: long_scoreboard)
+    double* const sX = sRaw + (size_t)NS * NB * BOXP;   // [NS][XBOX] (XTMA)
+    double* const sP = sX + (XTMA ? (size_t)NS * XBOX : 0);   // [2][PLANE]
     double* const sC = sP + 2 * PLANE;                  // [2][LAYER]
     double* const sRed = sC + 2 * LAYER;                // [32*NRED]
     uint64_t* const bars = reinterpret_cast<uint64_t*>(sRed + 32 * NRED);  // [NS]
@@ -204,7 +210,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         const int st = t % NS;
         double* dst = sRaw + (size_t)st * NB * BOXP;
         uint64_t* bar = &bars[st];
-        mbar_expect_tx(bar, (uint32_t)((NBN + (t > 0 ? NCB : 0)) * BOX * sizeof(double)));
+        mbar_expect_tx(bar, (uint32_t)(((NBN + (t > 0 ? NCB : 0)) * BOX + (XTMA ? XBOX : 0)) * sizeof(double)));
         const int P = k0 - 1 + t;
         tma_load_3d(dst + B_D * BOXP, &tm_d, bar, i0 - HX, j0 - 1, P);
         if (t > 0) {
@@ -220,6 +226,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         if (FUSED) tma_load_3d(dst, &tm_r, bar, i0 - HX, j0 - 1, P);
         if (FUSED && !LINE) tma_load_3d(dst + BOXP, &tm_q, bar, i0 - HX, j0 - 1, P);
         tma_load_3d(dst + B_P * BOXP, &tm_p, bar, i0 - HX, j0 - 1, P);
+        if (XTMA) tma_load_3d(sX + (size_t)st * XBOX, &tm_x, bar, i0, j0, P);
     };
     auto issue = [&](int t) { issue_const(t); issue_vec(t); };
 
@@ -291,11 +298,12 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         double* sPb = sP + (t & 1) * PLANE;
         double* sCb = sC + (t & 1) * LAYER;
         double xcur[RJ];
-        if (FUSED && OWN) {
+        if (FUSED && OWN && !XTMA) {
 #pragma unroll
             for (int rr = 0; rr < RJ; ++rr) xcur[rr] = xn[rr];
         }
-        if (PFEM_X & 2) {
+        if (XTMA) {
+        } else if (PFEM_X & 2) {
             if (FUSED) {
 #pragma unroll
                 for (int rr = 0; rr < RJ; ++rr) xn[rr] = xn2[rr];
@@ -337,6 +345,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
             l_p[rr] = raw[B_P * BOXP + ro];
             l_d[rr] = raw[B_D * BOXP + ro];
             if (GATHER) { l_a[rr] = raw[B_CL * BOXP + ro]; l_b[rr] = ISO ? l_a[rr] : raw[B_CV * BOXP + ro]; }
+            if (XTMA && OWN) xcur[rr] = sX[(size_t)st * XBOX + (jl0 + rr) * TI + tx];
         }
         if (ring_raw >= 0) {
             g_p = raw[B_P * BOXP + ring_raw];
@@ -767,12 +776,12 @@ struct FusedPlan {
     int tj, rj, ns, minb;
     int lk, tilesI, tilesJ, chunksK;
     ChunkTab ck;
-    CUtensorMap m_r[2], m_q[2], m_p[2], m_d, m_cl, m_cv;
+    CUtensorMap m_r[2], m_q[2], m_p[2], m_d, m_cl, m_cv, m_x;
     char why[160];
 };
 
 static inline FusedPlan make_fused_plan(const Grid& g, int sm_count, double* const r[2], double* const q[2], double* const p[2],
-                                        double* dinv, double* cl, double* cv) {
+                                        double* dinv, double* cl, double* cv, double* x) {
     FusedPlan f;
     memset(&f, 0, sizeof(f));
     f.tj = 8; f.rj = 2; f.ns = 2; f.minb = 3;   // measured best on B200 at 256^3 (tools/tune_fused.py)
@@ -803,7 +812,8 @@ static inline FusedPlan make_fused_plan(const Grid& g, int sm_count, double* con
              make_lattice_map(&f.m_p[b], p[b], g.nI, g.nJ, g.nK, g.sJ, g.sK, bw, bh);
     ok = ok && make_lattice_map(&f.m_d, dinv, g.nI, g.nJ, g.nK, g.sJ, g.sK, bw, bh) &&
          make_lattice_map(&f.m_cl, cl, g.nI - 1, g.nJ - 1, g.nK - 1, g.sJ, g.sK, bw, bh) &&
-         make_lattice_map(&f.m_cv, cv, g.nI - 1, g.nJ - 1, g.nK - 1, g.sJ, g.sK, bw, bh);
+         make_lattice_map(&f.m_cv, cv, g.nI - 1, g.nJ - 1, g.nK - 1, g.sJ, g.sK, bw, bh) &&
+         make_lattice_map(&f.m_x, x, g.nI, g.nJ, g.nK, g.sJ, g.sK, 32, f.tj);
     if (!ok) { snprintf(f.why, sizeof f.why, "cuTensorMapEncodeTiled failed or is unavailable"); return f; }
     f.pdl = getenv("PFEM_NO_PDL") == nullptr;
     f.valid = true;
@@ -831,10 +841,10 @@ static inline cudaError_t launch_fused_inst2(const FusedPlan& f, const Grid& g, 
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE, ISO, MASS>, f.m_r[par], f.m_q[par], f.m_p[par], f.m_d, f.m_cl, f.m_cv, g,
+        return cudaLaunchKernelEx(&cfg, k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE, ISO, MASS>, f.m_r[par], f.m_q[par], f.m_p[par], f.m_d, f.m_cl, f.m_cv, f.m_x, g,
                                   f.ck, r_out, q_out, p_out, x, sc, partials, po, ca, f.mass);
     }
-    k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE, ISO, MASS><<<grid, block, smem, st>>>(f.m_r[par], f.m_q[par], f.m_p[par], f.m_d, f.m_cl, f.m_cv, g, f.ck,
+    k_fpcg<TJ, RJ, NS, MINB, VDIM, MODE, ISO, MASS><<<grid, block, smem, st>>>(f.m_r[par], f.m_q[par], f.m_p[par], f.m_d, f.m_cl, f.m_cv, f.m_x, g, f.ck,
                                                                       r_out, q_out, p_out, x, sc, partials, po, ca, f.mass);
     return cudaGetLastError();
 }

@@ -57,6 +57,8 @@ struct pfem_ctx {
     bool has_excluded = false, source_set = false;
     // small arrays
     double* hbuf = nullptr;
+    void* itab = nullptr;                // interpolation tables of the field exchange / foreign-mesh provider (grow-only, reused)
+    size_t itab_bytes = 0;
     std::vector<double> h_host;          // host copy of hbuf: per index-space axis h, r (weighted) and u (geometric spacing)
     size_t h_off[3] = {0, 0, 0}, r_off[3] = {0, 0, 0}, u_off[3] = {0, 0, 0};
     bool weighted = false;               // pfem_set_axis_weight is in force (2-D cylindrical embedding)
@@ -197,6 +199,7 @@ static void free_all(pfem_ctx* ctx) {
     ctx->lz = ctx->lmask = ctx->ll = ctx->ld = ctx->zero1 = nullptr; ctx->line_plan.valid = false; ctx->precond = 0;
     memset(&ctx->ml, 0, sizeof ctx->ml); ctx->mlS = nullptr; ctx->ml_slen = 0;
     if (ctx->stage) { cudaFree(ctx->stage); ctx->stage = nullptr; ctx->stage_bytes = 0; }
+    if (ctx->itab) { cudaFree(ctx->itab); ctx->itab = nullptr; ctx->itab_bytes = 0; }
     ctx->have_mesh = ctx->have_materials = ctx->have_junctions = ctx->conds_valid = false;
     ctx->noheat_set = false;
     ctx->tab_cprho = nullptr; ctx->cap_nmat = ctx->cap_nT = 0; ctx->op_mass = ctx->op_cmass = nullptr;
@@ -237,6 +240,17 @@ static int alloc_line_arrays(pfem_ctx* ctx) {
     TRY(dev_alloc(ctx, &ctx->lmask, N, G));
     TRY(dev_alloc(ctx, &ctx->ll, N, G));
     TRY(dev_alloc(ctx, &ctx->ld, N, G));
+    return PFEM_OK;
+}
+
+// grow-only device buffer for the interpolation tables: the meta loop exchanges fields every iteration and must not pay a
+// cudaMalloc / cudaFree (a device-wide synchronisation) each time
+static int ensure_itab(pfem_ctx* ctx, size_t bytes) {
+    if (ctx->itab_bytes >= bytes) return PFEM_OK;
+    if (ctx->itab) { CU(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->itab); ctx->itab = nullptr; ctx->itab_bytes = 0; }
+    const size_t cap = (bytes + 4095) / 4096 * 4096;
+    CU(cudaMalloc(&ctx->itab, cap));
+    ctx->itab_bytes = cap;
     return PFEM_OK;
 }
 
@@ -487,7 +501,7 @@ extern "C" int pfem_set_mesh(pfem_ctx* ctx, const size_t n[3], const double* ax0
         double* const rr[2] = {ctx->r, ctx->r2};
         double* const qq[2] = {ctx->q, ctx->q2};
         double* const pp[2] = {ctx->p, ctx->p2};
-        ctx->fused = make_fused_plan(g, ctx->sm_count, rr, qq, pp, ctx->dinv, ctx->cl, ctx->cv);
+        ctx->fused = make_fused_plan(g, ctx->sm_count, rr, qq, pp, ctx->dinv, ctx->cl, ctx->cv, ctx->x);
     }
     ctx->nbc = 0;
     ctx->bc_node = nullptr;
@@ -1028,7 +1042,7 @@ extern "C" int pfem_slab_configure(pfem_ctx* ctx, int rank, int nranks, size_t o
         double* const rr[2] = {ctx->r, ctx->r2};
         double* const qq[2] = {ctx->q, ctx->q2};
         double* const pp[2] = {ctx->p, ctx->p2};
-        ctx->fused = make_fused_plan(g, ctx->sm_count, rr, qq, pp, ctx->dinv, ctx->cl, ctx->cv);
+        ctx->fused = make_fused_plan(g, ctx->sm_count, rr, qq, pp, ctx->dinv, ctx->cl, ctx->cv, ctx->x);
     }
     if (nranks == 1) return PFEM_OK;
     CU(cudaMalloc(&ctx->inbox, sizeof(Inbox)));
@@ -1194,7 +1208,7 @@ static int ensure_line(pfem_ctx* ctx) {
     double* const zz[2] = {ctx->lz, ctx->lz};
     double* const qq[2] = {ctx->q, ctx->q2};
     double* const pp[2] = {ctx->p, ctx->p2};
-    FusedPlan f = make_fused_plan(g, ctx->sm_count, zz, qq, pp, ctx->lmask, ctx->cl, ctx->cv);
+    FusedPlan f = make_fused_plan(g, ctx->sm_count, zz, qq, pp, ctx->lmask, ctx->cl, ctx->cv, ctx->x);
     if (!f.valid) FAIL(PFEM_ERR_STATE, "line preconditioner: %s", f.why);
     ctx->line_plan = f;
     return PFEM_OK;
@@ -1966,8 +1980,8 @@ static int interp_to_elems(pfem_ctx* dst, pfem_ctx* src, const double* src_arr, 
     std::vector<unsigned char> hb(bytes);
     double* hd = reinterpret_cast<double*>(hb.data());
     int* hi = reinterpret_cast<int*>(hb.data() + nd * sizeof(double));
-    void* dbuf = nullptr;
-    CU(cudaMalloc(&dbuf, bytes));
+    TRY(ensure_itab(dst, bytes));
+    void* const dbuf = dst->itab;
     double* dd = reinterpret_cast<double*>(dbuf);
     int* di = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(dbuf) + nd * sizeof(double));
     InterpAxis ia[3];
@@ -1989,8 +2003,7 @@ static int interp_to_elems(pfem_ctx* dst, pfem_ctx* src, const double* src_arr, 
         e = cudaGetLastError();
         dst->launches += 1;
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(dst->stream);
-    cudaFree(dbuf);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(dst->stream);   // hb (host staging of the tables) goes out of scope
     CU(e);
     return PFEM_OK;
 }
@@ -2024,8 +2037,8 @@ extern "C" int pfem_interpolate_field(pfem_ctx* ctx, const size_t n[3], const do
     std::vector<unsigned char> hb(tbytes);
     double* hd = reinterpret_cast<double*>(hb.data());
     int* hi = reinterpret_cast<int*>(hb.data() + nd * sizeof(double));
-    void* dbuf = nullptr;
-    CU(cudaMalloc(&dbuf, off_out + total * sizeof(double)));
+    TRY(ensure_itab(ctx, off_out + total * sizeof(double)));
+    void* const dbuf = ctx->itab;
     double* dd = reinterpret_cast<double*>(dbuf);
     int* di = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(dbuf) + nd * sizeof(double));
     double* dout = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(dbuf) + off_out);
@@ -2049,7 +2062,6 @@ extern "C" int pfem_interpolate_field(pfem_ctx* ctx, const size_t n[3], const do
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(dbuf);
     CU(e);
     return PFEM_OK;
 }

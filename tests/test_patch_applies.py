@@ -22,7 +22,8 @@ def test_patch_touches_the_documented_files():
             "solvers/thermal/static/therm3d.hpp", "solvers/thermal/static/therm3d.cpp",
             "solvers/electrical/shockley/electr3d.hpp", "solvers/electrical/shockley/electr3d.cpp",
             "solvers/electrical/shockley/beta.hpp", "solvers/electrical/shockley/python/electr_python.cpp",
-            "solvers/thermal/static/CMakeLists.txt", "solvers/electrical/shockley/CMakeLists.txt"}
+            "solvers/thermal/static/CMakeLists.txt", "solvers/electrical/shockley/CMakeLists.txt",
+            "solvers/thermal/dynamic/femT3d.hpp", "solvers/thermal/dynamic/femT3d.cpp", "solvers/thermal/dynamic/CMakeLists.txt"}
     assert set(_files()) == want
 
 
@@ -40,6 +41,8 @@ def test_patch_applies_to_the_reference(tmp_path):
     assert "ALGORITHM_CUDA" in text and '.value("cuda", ALGORITHM_CUDA)' in text
     assert "computeCuda" in open(tmp_path / "solvers/thermal/static/therm3d.cpp").read()
     assert "shockleyParameters" in open(tmp_path / "solvers/electrical/shockley/beta.hpp").read()
+    dyn = open(tmp_path / "solvers/thermal/dynamic/femT3d.cpp").read()
+    assert "solve_dynamic" in dyn and "set_capacity" in dyn and "if (algorithm == ALGORITHM_CUDA) return computeCuda(time, btemperature);" in dyn
 
 
 def test_every_adapter_call_of_the_patch_exists():

@@ -10,7 +10,8 @@ What the patch does (INTEGRATION.md explains every hunk):
     branch that hands the whole nonlinear loop to the library (include/plaskfem_cuda.hpp)
   * BetaSolver / the Python Shockley class expose beta(T), js(T) per junction through one virtual, so that the host can
     evaluate them at the mid-plane temperature of every junction column (electr3d.cpp:261-262)
-  * the two solver CMakeLists link plaskfem_cuda
+  * DynamicThermalFem3DSolver: the same for the time loop of compute(time) (pfem_solve_dynamic, corrected update)
+  * the three solver CMakeLists link plaskfem_cuda
 """
 import os
 import shutil
@@ -575,8 +576,199 @@ edit(F, """void ElectricalFem3DSolver::saveHeatDensity() {""", """double Electri
 
 void ElectricalFem3DSolver::saveHeatDensity() {""")
 
+# ---------------------------------------------------------------- thermal.dynamic Dynamic3D
+F = "solvers/thermal/dynamic/femT3d.hpp"
+edit(F, """namespace plask { namespace thermal { namespace dynamic {
+
+/**
+ * Solver performing calculations in 2D Cartesian or Cylindrical space using finite element method
+ */
+struct PLASK_SOLVER_API DynamicThermalFem3DSolver:""", """namespace plaskfem { class Context; }   // plaskfem_cuda.hpp: host adapter of libplaskfem_cuda.so (algorithm 'cuda')
+
+namespace plask { namespace thermal { namespace dynamic {
+
+/**
+ * Solver performing calculations in 2D Cartesian or Cylindrical space using finite element method
+ */
+struct PLASK_SOLVER_API DynamicThermalFem3DSolver:""")
+edit(F, """    DataVector<Vec<3,double>> fluxes;      ///< Computed (only when needed) heat fluxes on our own mesh
+""", """    DataVector<Vec<3,double>> fluxes;      ///< Computed (only when needed) heat fluxes on our own mesh
+
+    std::shared_ptr<plaskfem::Context> cuda;   ///< Device context, exists only for algorithm 'cuda'
+
+    /// Create the device context: mesh, (material, layer thickness) ids, thermk(T) and cp(T)*dens(T) tables
+    void setupCuda();
+
+    /// The time loop of compute() on the device (pfem_solve_dynamic)
+    double computeCuda(double time, const BoundaryConditionsWithMesh<RectangularMesh<3>::Boundary,double>& btemperature);
+""")
+
+F = "solvers/thermal/dynamic/femT3d.cpp"
+edit(F, """#include "femT3d.hpp"
+""", """#include "femT3d.hpp"
+
+#include <plaskfem_cuda.hpp>
+""")
+edit(F, """            if (idx != RectangularMaskedMesh3D::Element::UNKNOWN_ELEMENT_INDEX)
+                thickness[idx] = h;
+        }
+    }
+}
+
+
+void DynamicThermalFem3DSolver::onInvalidate() {
+    temperatures.reset();
+    fluxes.reset();
+    thickness.reset();
+}
+""", """            if (idx != RectangularMaskedMesh3D::Element::UNKNOWN_ELEMENT_INDEX)
+                thickness[idx] = h;
+        }
+    }
+
+    if (algorithm == ALGORITHM_CUDA) setupCuda();
+}
+
+
+void DynamicThermalFem3DSolver::setupCuda() {
+    try {
+        cuda.reset(new plaskfem::Context(0, this->getId()));
+        if (iter_params.preconditioner != IterativeMatrixParams::PRECOND_JAC && this->mesh->axis[2]->size() <= 512)
+            cuda->set_layout(PFEM_LAYOUT_VERTICAL_MINOR);
+        plaskfem::Mesh fm;
+        for (int a = 0; a < 3; ++a) {
+            fm.axis[a].reserve(this->mesh->axis[a]->size());
+            for (size_t i = 0; i != this->mesh->axis[a]->size(); ++i) fm.axis[a].push_back(this->mesh->axis[a]->at(i));
+        }
+        fm.order = plaskfem::IterationOrder(int(this->mesh->getIterationOrder()));
+        cuda->set_mesh(fm);
+
+        // ids per (material, layer thickness) pair as in ThermalFem3DSolver::setupCuda; one more table per id: cp(T) * dens(T) (:176)
+        const size_t nfull = this->mesh->getElementsCount();
+        std::vector<shared_ptr<Material>> materials(nfull);
+        std::vector<const Material*> key(nfull, nullptr);
+        std::vector<double> thick(nfull, 0.);
+        std::vector<uint8_t> included(nfull, 0);
+        for (auto elem: this->maskedMesh->elements()) {
+            size_t e = this->mesh->element(elem.getIndex0(), elem.getIndex1(), elem.getIndex2()).getIndex();
+            materials[e] = this->geometry->getMaterial(elem.getMidpoint());
+            key[e] = materials[e].get();
+            thick[e] = thickness[elem.getIndex()];
+            included[e] = 1;
+        }
+        std::vector<size_t> reps;
+        std::vector<uint32_t> ids = plaskfem::material_ids(key, thick, &reps);
+        plaskfem::Tables tables = plaskfem::sample_tables(reps.size(), [&](uint32_t id, double T) {
+            if (!materials[reps[id]]) return std::make_pair(1., 1.);
+            auto k = materials[reps[id]]->thermk(T, thick[reps[id]]);
+            return std::make_pair(k.c00, k.c11);
+        });
+        std::vector<double> cpdens(size_t(tables.nmat) * tables.nT, 1.);
+        for (uint32_t id = 0; id != tables.nmat; ++id)
+            if (materials[reps[id]])
+                for (uint32_t i = 0; i != tables.nT; ++i) {
+                    double T = tables.T0 + i * tables.dT;
+                    cpdens[size_t(id) * tables.nT + i] = materials[reps[id]]->cp(T) * materials[reps[id]]->dens(T);
+                }
+        if (!this->maskedMesh->full()) ids = plaskfem::MaskedNumbering(fm, included).mark_excluded(ids);
+        cuda->set_materials(ids, tables);
+        cuda->set_capacity(tables, cpdens);
+        cuda->fill_field(inittemp);
+    } catch (const plaskfem::NoDevice& err) {
+        throw ComputationError(this->getId(), "algorithm 'cuda' has no CPU fallback: {}", err.what());
+    } catch (const plaskfem::BadInput& err) {
+        throw BadInput(this->getId(), "{}", err.what());
+    }
+}
+
+
+double DynamicThermalFem3DSolver::computeCuda(double time,
+                   const BoundaryConditionsWithMesh<RectangularMesh<3>::Boundary,double>& btemperature)
+{
+    if (!cuda) setupCuda();
+    try {
+        plaskfem::Mesh fm;
+        for (int a = 0; a < 3; ++a)
+            for (size_t i = 0; i != this->mesh->axis[a]->size(); ++i) fm.axis[a].push_back(this->mesh->axis[a]->at(i));
+        fm.order = plaskfem::IterationOrder(int(this->mesh->getIterationOrder()));
+        const bool masked = !this->maskedMesh->full();
+        std::vector<uint8_t> included;
+        if (masked) {
+            included.assign(this->mesh->getElementsCount(), 0);
+            for (auto elem: this->maskedMesh->elements())
+                included[this->mesh->element(elem.getIndex0(), elem.getIndex1(), elem.getIndex2()).getIndex()] = 1;
+        }
+        plaskfem::MaskedNumbering numbering(fm, included);
+        const size_t nfull = this->mesh->size();
+        auto full_node = [&](size_t masked_node) { return masked ? numbering.node_to_full(masked_node) : masked_node; };
+
+        plaskfem::Dirichlet bc;
+        for (auto cond: btemperature) for (auto r: cond.place) bc.add_node(full_node(r), cond.value);
+        cuda->set_dirichlet(bc);
+
+        auto heats = inHeat(this->maskedMesh->getElementMesh());  // :160
+        std::vector<double> heat(this->mesh->getElementsCount(), 0.);
+        for (auto elem: this->maskedMesh->elements())
+            heat[this->mesh->element(elem.getIndex0(), elem.getIndex1(), elem.getIndex2()).getIndex()] = heats[elem.getIndex()];
+        cuda->set_source(heat.data());
+
+        temperatures = temperatures.claim();
+        std::vector<double> field(nfull, 0.);
+        for (size_t i = 0; i != temperatures.size(); ++i) field[full_node(i)] = temperatures[i];
+        cuda->set_field(field.data());
+
+        plaskfem::IterParams ip{iter_params.maxit, iter_params.maxerr,
+                                plaskfem::IterParams::NoConvergenceBehavior(int(iter_params.no_convergence_behavior))};
+        // jac as named, every other choice -> line-Jacobi (the multilevel preconditioner does not take the capacity diagonal yet)
+        ip.preconditioner = iter_params.preconditioner == IterativeMatrixParams::PRECOND_JAC ? plaskfem::IterParams::PRECOND_JAC :
+                                                                                                plaskfem::IterParams::PRECOND_LJAC;
+        // the corrected theta scheme (plaskfem_cuda.h): no std::swap(temperatures, X) (:287), Dirichlet rows keep their values
+        auto result = cuda->solve_dynamic(ip, time, timestep, methodparam, lumping, int(rebuildfreq), int(logfreq), elapstime,
+                                          [this](int level, const std::string& msg) { this->writelog(LogLevel(level), msg); });
+        iter_params.converged = ip.converged; iter_params.iters = ip.iters; iter_params.err = ip.err;
+
+        cuda->get_field(field.data());
+        for (size_t i = 0; i != temperatures.size(); ++i) temperatures[i] = field[full_node(i)];
+        maxT = result.maxT;
+    } catch (const plaskfem::BadInput& err) {
+        throw BadInput(this->getId(), "{}", err.what());
+    } catch (const std::runtime_error& err) {
+        throw ComputationError(this->getId(), "{}", err.what());
+    }
+
+    outTemperature.fireChanged();
+    outHeatFlux.fireChanged();
+
+    return 0.;
+}
+
+
+void DynamicThermalFem3DSolver::onInvalidate() {
+    temperatures.reset();
+    fluxes.reset();
+    thickness.reset();
+    cuda.reset();
+}
+""")
+edit(F, """    size_t size = this->maskedMesh->size();
+
+    std::unique_ptr<FemMatrix> pA(this->getMatrix());
+    FemMatrix& A = *pA.get();
+    std::unique_ptr<FemMatrix> pB(this->getMatrix());
+    FemMatrix& B = *pB.get();
+""", """    if (algorithm == ALGORITHM_CUDA) return computeCuda(time, btemperature);
+
+    size_t size = this->maskedMesh->size();
+
+    std::unique_ptr<FemMatrix> pA(this->getMatrix());
+    FemMatrix& A = *pA.get();
+    std::unique_ptr<FemMatrix> pB(this->getMatrix());
+    FemMatrix& B = *pB.get();
+""")
+
 # ---------------------------------------------------------------- build
-for F, target in (("solvers/thermal/static/CMakeLists.txt", "thermal"), ("solvers/electrical/shockley/CMakeLists.txt", "electrical")):
+for F, target in (("solvers/thermal/static/CMakeLists.txt", "thermal"), ("solvers/electrical/shockley/CMakeLists.txt", "electrical"),
+                  ("solvers/thermal/dynamic/CMakeLists.txt", "dynamic")):
     edit(F, """# Build everything the default way.
 # Call this macro unless you really know what you are doing!
 make_default()""", """# Algorithm 'cuda': the header-only host adapter plaskfem_cuda.hpp and libplaskfem_cuda.so (a plain C ABI; the solver does not

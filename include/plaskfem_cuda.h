@@ -249,7 +249,8 @@ typedef struct {
  *   (theta K + C/dt) T^{n+1} = (C/dt - (1 - theta) K) T^n + F  on the free rows,  T^{n+1} = value on the Dirichlet rows.
  * The field (pfem_set_field / pfem_fill_field = inittemp, :82) is advanced in place; stats: outer_loops = steps done,
  * lin_iters = PCG iterations of all steps, maxval = max T.  opts->precond 0 or 1, opts->variant 3 (lumped) or 1.
- * The caller keeps the elapsed time (elapstime, :293,297). */
+ * The caller keeps the elapsed time (elapstime, :293,297).  Slab mode: collective, lumped capacity only, every rank passes the
+ * same parameters (maxT_log_len included: the per-step maximum is a cross-rank reduction). */
 int pfem_solve_dynamic(pfem_ctx* ctx, const pfem_opts* opts, const pfem_dynamic* dyn, pfem_stats* stats);
 
 /* ---- results ------------------------------------------------------------------------- */

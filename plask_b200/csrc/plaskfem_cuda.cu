@@ -1708,11 +1708,14 @@ static int dynamic_steps(pfem_ctx* ctx, const pfem_opts* o, const pfem_dynamic* 
     int steps = 0, conv = 1, iters = 0, all_conv = 1;
     long long total_iters = 0;
     double relres = 0., maxT = 0.;
+    const idx_t own_off = g.sK * g.kown0, own_cnt = g.sK * (g.kown1 - g.kown0);   // slab mode: reductions over the owned planes
     TRY(mask_field(ctx));
+    TRY(halo_sync(ctx, SA_X));                                     // slab mode: conductivities / capacities of the boundary elements
     TRY(dynamic_set_matrix(ctx, d));
     long long r = d->rebuildfreq;
     const double tend = d->time + d->timestep / 2.;
     for (double t = 0.; t < tend; t += d->timestep) {               // femT3d.cpp:271-272
+        if (steps > 0) TRY(halo_sync(ctx, SA_X));                   // slab mode: the solve updates owned planes only
         if (d->rebuildfreq && r == 0) { TRY(dynamic_set_matrix(ctx, d)); r = d->rebuildfreq; }   // :274-278
         // right-hand side B T + F with B = A - K:  M (F - K T) + M (A T), then the Dirichlet rows take their values in the solve
         TRY(launch_diag(ctx));                                      // the row mask (dinv == 0) of the kernels below
@@ -1730,16 +1733,17 @@ static int dynamic_steps(pfem_ctx* ctx, const pfem_opts* o, const pfem_dynamic* 
         all_conv = all_conv && conv;
         ++steps; --r;
         if (d->maxT_log && (size_t)(steps - 1) < d->maxT_log_len) {
-            k_thermal_error<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->x, ctx->x, ctx->d_sc, ctx->partials);
+            k_thermal_error<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(own_cnt, ctx->x + own_off, ctx->x + own_off, ctx->d_sc, ctx->partials);
             KCHECK(); LAUNCHED(1);
             TRY(read_scalars(ctx));
             d->maxT_log[steps - 1] = ctx->h_sc->red[1];
         }
     }
-    k_thermal_error<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(g.NP, ctx->x, ctx->x, ctx->d_sc, ctx->partials);
+    k_thermal_error<<<vec_blocks(ctx), 256, 0, ctx->stream>>>(own_cnt, ctx->x + own_off, ctx->x + own_off, ctx->d_sc, ctx->partials);
     KCHECK(); LAUNCHED(1);
     TRY(read_scalars(ctx));
     maxT = ctx->h_sc->red[1];
+    TRY(halo_sync(ctx, SA_X));
     if (st) {
         st->outer_loops = steps; st->loopno = ctx->loopno; st->lin_iters = total_iters; st->last_iters = iters;
         st->converged = all_conv; st->lin_relres = relres; st->maxval = maxT;
@@ -1758,7 +1762,9 @@ extern "C" int pfem_solve_dynamic(pfem_ctx* ctx, const pfem_opts* o, const pfem_
     if (!(d->timestep > 0.) || !(d->time >= 0.)) FAIL(PFEM_ERR_BAD_INPUT, "need timestep > 0 and time >= 0");
     if (!(d->methodparam >= 0. && d->methodparam <= 1.)) FAIL(PFEM_ERR_BAD_INPUT, "methodparam must lie in [0, 1]");
     if (d->rebuildfreq < 0) FAIL(PFEM_ERR_BAD_INPUT, "negative rebuildfreq");
-    if (ctx->nranks > 1) FAIL(PFEM_ERR_BAD_INPUT, "Dynamic3D is not available in slab mode");
+    // slab mode: collective; every rank must pass the same time span, step, rebuild frequency and maxT_log_len (the per-step maximum
+    // is a cross-rank reduction); the consistent capacity matrix runs the node-per-thread kernel, which is single-GPU
+    if (ctx->nranks > 1 && !d->lumping) FAIL(PFEM_ERR_BAD_INPUT, "slab mode: Dynamic3D runs with a lumped capacity matrix only");
     if (ctx->surf.nrows) FAIL(PFEM_ERR_BAD_INPUT, "Dynamic3D has boundary conditions of the first kind only (femT3d.hpp)");
     const Grid& g = ctx->g;
     if (!ctx->dyn_f) {

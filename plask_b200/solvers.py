@@ -259,6 +259,7 @@ class Dynamic3D(_FemSolver):
             raise L.BadInput(f"{self.id}: no geometry/mesh (problem) specified")
         f = self._fem = self._new_fem()
         f.set_mesh(p.axes, p.strides)
+        self._setup_slab(f)
         f.set_materials(self._elem_materials(), p.T0, p.dT, p.tab_lat, p.tab_vert)
         tab = p.tab_cprho
         if tab is None:

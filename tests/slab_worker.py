@@ -362,6 +362,38 @@ def main():
         assert abs(partsW[0][1]["err"] - onev.stats["err"]) <= 1e-6 * max(1., abs(onev.stats["err"]))
         onev.invalidate()
     dist.barrier()
+
+    # ---- Dynamic3D in slab mode: 6 Crank-Nicolson steps with a rebuild of k(T), cp(T) every 2 steps, line-Jacobi
+    from plask_b200.solvers import Dynamic3D
+
+    def dynamic(name, prob, slab=None, dev=local):
+        d = Dynamic3D(name)
+        d.device = dev
+        d.problem = prob
+        d.slab = slab
+        d.timestep, d.rebuildfreq, d.logfreq = 20., 2, 1
+        d.iterative.preconditioner = "ljac"
+        d.iterative.maxerr = 1e-12
+        d.iterative.maxit = 50000
+        d.compute(100.)
+        return d
+
+    ph = cf.config_B(n)
+    ph.heat = ph.heat * 200.
+    qh, h_lo, h_hi, _ = cf.slab_problem(ph, rank, world)
+    dd = dynamic(f"dslab{rank}", qh, dict(rank=rank, nranks=world, own_lo=h_lo, own_hi=h_hi, allgather=allgather_bytes))
+    partsD = allgather_bytes((cf.slab_field_owned(qh, dd.outTemperature(), h_lo, h_hi), dd.stats, dd.maxT))
+    assert all(x[2] == partsD[0][2] and x[1]["outer_loops"] == 6 for x in partsD)
+    dd.invalidate()
+    if rank == 0:
+        Td = np.concatenate([x[0] for x in partsD], axis=0).ravel()
+        oned = dynamic("dsingle", ph, None, 0)
+        d7 = float(np.abs(Td - oned.outTemperature()).max())
+        print(f"slab x{world} Dynamic3D: 6 steps, PCG iterations {partsD[0][1]['lin_iters']} (single GPU {oned.stats['lin_iters']}), max T {partsD[0][2]:.3f} K, "
+              f"max|Td_slab - Td_single| = {d7:.3e} K")
+        assert oned.maxT - 300. > 5. and abs(oned.maxT - partsD[0][2]) <= 1e-6 and d7 <= 1e-6
+        oned.invalidate()
+    dist.barrier()
     dist.destroy_process_group()
 
 

@@ -36,4 +36,5 @@ def test_slab_solve_two_gpus():
     assert "max|Tm_slab - Tm_single|" in r.stdout
     assert "max|Tb_slab - Tb_single|" in r.stdout
     assert "max|V_slab - V_single|" in r.stdout
-    assert "max|V201_slab - V201_single|" in r.stdout      # vertical-major mesh: the host cuts a lateral axis
+    assert "max|V201_slab - V201_single|" in r.stdout
+    assert "max|Td_slab - Td_single|" in r.stdout          # Dynamic3D in slab mode      # vertical-major mesh: the host cuts a lateral axis

@@ -61,7 +61,23 @@ class Dynamic(C.Structure):
                 ("rebuildfreq", C.c_int), ("maxT_log", c_dp), ("maxT_log_len", c_sz), ("reserved", C.c_int * 4)]
 
 
-# every symbol include/plaskfem_cuda.h declares: name -> (restype, argtypes)
+class DiffOpts(C.Structure):
+    _fields_ = [("loops", C.c_int), ("maxerr", C.c_double), ("maxit", C.c_int), ("lin_tol", C.c_double), ("verbatim", C.c_int),
+                ("loop_cap", C.c_int), ("reserved", C.c_int * 6)]
+
+
+class DiffStats(C.Structure):
+    _fields_ = [("loops", C.c_int), ("converged", C.c_int), ("err", C.c_double), ("lin_iters", C.c_longlong),
+                ("last_iters", C.c_int), ("lin_relres", C.c_double), ("t_solve_ms", C.c_double),
+                ("kernel_launches", C.c_longlong), ("err_log", C.c_double * 64), ("lin_relres_precond", C.c_double), ("reserved", C.c_double * 3)]
+
+    def as_dict(self):
+        return dict(loops=self.loops, converged=bool(self.converged), err=self.err, lin_iters=self.lin_iters,
+                    last_iters=self.last_iters, lin_relres=self.lin_relres, lin_relres_precond=self.lin_relres_precond,
+                    t_solve_ms=self.t_solve_ms, kernel_launches=self.kernel_launches, err_log=list(self.err_log[:min(self.loops, 64)]))
+
+
+# every symbol include/plaskfem_cuda.h and include/plaskdiff_cuda.h declare: name -> (restype, argtypes)
 _vp = C.c_void_p
 _u32p = C.POINTER(C.c_uint32)
 _u8p = C.POINTER(C.c_uint8)
@@ -112,6 +128,22 @@ SYMBOLS = {
     "pfem_solve_linear": (C.c_int, [_vp, C.POINTER(Opts), C.POINTER(Stats)]),
     "pfem_get_info": (C.c_int, [_vp, C.c_int, c_dp]),
     "pfem_bench_pcg": (C.c_int, [_vp, C.POINTER(Opts), C.c_int, C.c_int, c_dp, c_dp, c_dp, C.POINTER(C.c_longlong)]),
+    # include/plaskdiff_cuda.h
+    "pdiff_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "pdiff_destroy": (None, [_vp]),
+    "pdiff_last_error": (C.c_char_p, [_vp]),
+    "pdiff_set_mesh": (C.c_int, [_vp, c_sz, c_sz, c_dp, c_dp, C.c_int, _u8p]),
+    "pdiff_set_parameters": (C.c_int, [_vp, c_dp, c_dp, c_dp, c_dp]),
+    "pdiff_set_current": (C.c_int, [_vp, c_dp]),
+    "pdiff_set_modes": (C.c_int, [_vp, c_sz, c_dp, c_dp, c_dp]),
+    "pdiff_set_concentration": (C.c_int, [_vp, c_dp]),
+    "pdiff_get_concentration": (C.c_int, [_vp, c_dp]),
+    "pdiff_default_opts": (None, [C.POINTER(DiffOpts)]),
+    "pdiff_compute": (C.c_int, [_vp, C.POINTER(DiffOpts), C.POINTER(DiffStats)]),
+    "pdiff_interpolate": (C.c_int, [_vp, c_sz, c_dp, c_dp, C.c_int, c_dp]),
+    "pdiff_get_element_matrices": (C.c_int, [_vp, C.c_int, c_dp, c_dp]),
+    "pdiff_apply": (C.c_int, [_vp, C.c_int, c_dp, c_dp]),
+    "pdiff_get_rhs": (C.c_int, [_vp, C.c_int, c_dp]),
 }
 
 PFEM_OK, PFEM_NOT_CONVERGED = 0, 1
@@ -121,6 +153,8 @@ ELEM_COND, ELEM_CURRENT, ELEM_HEAT, ELEM_FLUX = 0, 1, 2, 3
 MAT_EXCLUDED = 0xFFFFFFFF
 LAYOUT_ABI, LAYOUT_VERTICAL_MINOR = 0, 1
 INFO_COND_ISO, INFO_ML_LEVELS, INFO_FUSED_CTAS, INFO_DEVICE_BYTES = 0, 1, 2, 3
+DIFF_ORDER_01, DIFF_ORDER_10 = 0, 1
+DIFF_INTERP_SPLINE, DIFF_INTERP_LINEAR = 0, 1
 
 _lib = None
 
@@ -143,12 +177,12 @@ def load():
     return _lib
 
 
-def check(ctx, rc):
+def check(ctx, rc, last_error="pfem_last_error"):
     """Map a pfem_status to the exceptions the PLaSK solver would throw."""
     if rc >= 0:
         return rc
     lib = load()
-    detail = lib.pfem_last_error(ctx).decode() if ctx else ""
+    detail = getattr(lib, last_error)(ctx).decode() if ctx else ""
     msg = f"{lib.pfem_strerror(rc).decode()}: {detail}" if detail else lib.pfem_strerror(rc).decode()
     if rc == PFEM_ERR_NO_DEVICE:
         raise NoDevice(msg)

@@ -41,8 +41,10 @@
 #include "kernels_ml.cuh"
 
 #ifndef PFEM_X
-#define PFEM_X 13   // experiment mask of k_fpcg: 1 = phase-1 loads hoisted (-1.7 %), 2 = x fetched two planes ahead in registers (+1.5 %: off),
-                    // 4 = vertical stiffness per element (-0.5 %), 8 = x of the own tile through the TMA stage instead of a global load (-3 %)
+#define PFEM_X 45   // experiment mask of k_fpcg: 1 = phase-1 loads hoisted (-1.7 %), 2 = x fetched two planes ahead in registers (+1.5 %: off),
+                    // 4 = vertical stiffness per element (-0.5 %), 8 = x of the own tile through the TMA stage instead of a global load (-3 %),
+                    // 32 = isotropic coefficient layer from per-thread constants (-0.4 ... -1.0 % inside the power-capped bench);
+                    // tried and dropped: a branch-free phase 2 that guards only the stores (+1.1 %)
 #endif
 
 namespace pfem {
@@ -138,7 +140,8 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
     const bool vi = i < g.nI;
     constexpr double s36 = 1e-6 / 36.;
     // element weights: kI = cI wI hk, kJ = cJ wJ hk, kK = cK wK rk   (therm3d.cpp:215-220)
-    double wI[RJ], wJ[RJ], wK[RJ];
+    constexpr bool ISOW = ISO && ((PFEM_X & 33) == 33);   // 6 instead of 9 FP64 operations per element for the coefficient layer
+    double wI[RJ], wJ[RJ], wK[RJ], wU[RJ];
     bool vj[RJ];
     {
         const int ei = min(i, g.nI - 1);
@@ -152,6 +155,12 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
             wI[rr] = s36 * hj * ri;
             wJ[rr] = s36 * hi * g.rJ[ej];
             wK[rr] = s36 * hi * hj;
+            if (ISOW) {   // isotropic conductivity: the three stencil coefficients are (c hk) times constants of the thread
+                const double a = wI[rr], b = wJ[rr];
+                wI[rr] = a + b;              // kI + kJ
+                wJ[rr] = fma(-2., a, b);     // kJ - 2 kI
+                wU[rr] = fma(-2., b, a);     // kI - 2 kJ
+            }
         }
     }
     // halo ring of the node plane handled by this thread (entry h = tid), offsets into raw box / p' plane
@@ -190,7 +199,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
     };
     // halo row / column of the element layer handled by this thread (entry e = NT-1-tid)
     int er_raw = -1, er_c = 0;
-    double wIr = 0., wJr = 0., wKr = 0.;
+    double wIr = 0., wJr = 0., wKr = 0., wUr = 0.;
     if (NT - 1 - tid < NERING) {
         const int e = NT - 1 - tid;
         int ejl, eil;                       // layer coordinates: element (j0-1+ejl, i0-1+eil)
@@ -202,6 +211,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         wIr = s36 * hj * g.rI[ei];
         wJr = s36 * hi * g.rJ[ej];
         wKr = s36 * hi * hj;
+        if (ISOW) { const double a = wIr, b = wJr; wIr = a + b; wJr = fma(-2., a, b); wUr = fma(-2., b, a); }
     }
 
     // part 1: boxes that are constant during a linear solve (D^-1 or mask, conductivities) + the expected byte count of the
@@ -390,12 +400,18 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
             sPb[(jl0 + rr + 1) * PWP + tx + 1] = pn;
             if (GATHER) {
                 const double a = l_a[rr], b = l_b[rr];
-                const double kI = ((VDIM == 0 ? b : a) * wI[rr]) * hk;
-                const double kJ = ((VDIM == 1 ? b : a) * wJ[rr]) * hk;
-                const double kK = ((VDIM == 2 ? b : a) * wK[rr]) * rk;
                 const int co = (jl0 + rr + 1) * CW + tx + 1;
-                reinterpret_cast<double2*>(sCb)[co] = make_double2(kI + kJ, fma(-2., kI, kJ));
-                reinterpret_cast<double2*>(sCb + CHALF)[co] = make_double2(fma(-2., kJ, kI), kK);
+                if (ISOW) {
+                    const double ah = a * hk;
+                    reinterpret_cast<double2*>(sCb)[co] = make_double2(ah * wI[rr], ah * wJ[rr]);
+                    reinterpret_cast<double2*>(sCb + CHALF)[co] = make_double2(ah * wU[rr], (a * rk) * wK[rr]);
+                } else {
+                    const double kI = ((VDIM == 0 ? b : a) * wI[rr]) * hk;
+                    const double kJ = ((VDIM == 1 ? b : a) * wJ[rr]) * hk;
+                    const double kK = ((VDIM == 2 ? b : a) * wK[rr]) * rk;
+                    reinterpret_cast<double2*>(sCb)[co] = make_double2(kI + kJ, fma(-2., kI, kJ));
+                    reinterpret_cast<double2*>(sCb + CHALF)[co] = make_double2(fma(-2., kJ, kI), kK);
+                }
             }
         }
         if (ring_raw >= 0) {
@@ -406,11 +422,17 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         }
         if (GATHER && er_raw >= 0) {
             const double a = h_a, b = h_b;
-            const double kI = ((VDIM == 0 ? b : a) * wIr) * hk;
-            const double kJ = ((VDIM == 1 ? b : a) * wJr) * hk;
-            const double kK = ((VDIM == 2 ? b : a) * wKr) * rk;
-            reinterpret_cast<double2*>(sCb)[er_c] = make_double2(kI + kJ, fma(-2., kI, kJ));
-            reinterpret_cast<double2*>(sCb + CHALF)[er_c] = make_double2(fma(-2., kJ, kI), kK);
+            if (ISOW) {
+                const double ah = a * hk;
+                reinterpret_cast<double2*>(sCb)[er_c] = make_double2(ah * wIr, ah * wJr);
+                reinterpret_cast<double2*>(sCb + CHALF)[er_c] = make_double2(ah * wUr, (a * rk) * wKr);
+            } else {
+                const double kI = ((VDIM == 0 ? b : a) * wIr) * hk;
+                const double kJ = ((VDIM == 1 ? b : a) * wJr) * hk;
+                const double kK = ((VDIM == 2 ? b : a) * wKr) * rk;
+                reinterpret_cast<double2*>(sCb)[er_c] = make_double2(kI + kJ, fma(-2., kI, kJ));
+                reinterpret_cast<double2*>(sCb + CHALF)[er_c] = make_double2(fma(-2., kJ, kI), kK);
+            }
         }
 #else
         // ---------------- phase 1: p' plane and coefficient layer -------------------------

@@ -19,14 +19,17 @@ def lib():
 
 
 def declared_functions():
-    text = open(os.path.join(ROOT, "include", "plaskfem_cuda.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(pfem_[a-z_0-9]+)\s*\(", text)))
+    names = set()
+    for header in ("plaskfem_cuda.h", "plaskdiff_cuda.h"):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(p(?:fem|diff)_[a-z_0-9]+)\s*\(", text))
+    return sorted(names)
 
 
 def test_header_symbols_exported(lib):
     names = declared_functions()
-    assert len(names) >= 25
+    assert len(names) >= 40 and sum(n.startswith("pdiff_") for n in names) >= 15
     for name in names:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
         assert name in _lib.SYMBOLS, f"{name} has no ctypes prototype"
@@ -47,10 +50,13 @@ def test_struct_layouts_match_header(lib, tmp_path):
 #include <stdio.h>
 #include <stddef.h>
 #include "plaskfem_cuda.h"
+#include "plaskdiff_cuda.h"
 int main(void) {
   printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(pfem_junction), sizeof(pfem_opts), sizeof(pfem_stats),
          offsetof(pfem_opts, outer_tol), offsetof(pfem_stats, maxcur), offsetof(pfem_stats, kernel_launches),
          sizeof(pfem_boundary), offsetof(pfem_boundary, rad_ambient), offsetof(pfem_boundary, verbatim));
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(pdiff_opts), sizeof(pdiff_stats), offsetof(pdiff_opts, lin_tol),
+         offsetof(pdiff_opts, verbatim), offsetof(pdiff_stats, lin_relres), offsetof(pdiff_stats, err_log));
   return 0; }
 """)
     exe = tmp_path / "sz"
@@ -58,7 +64,9 @@ int main(void) {
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     want = [ctypes.sizeof(_lib.Junction), ctypes.sizeof(_lib.Opts), ctypes.sizeof(_lib.Stats),
             _lib.Opts.outer_tol.offset, _lib.Stats.maxcur.offset, _lib.Stats.kernel_launches.offset,
-            ctypes.sizeof(_lib.Boundary), _lib.Boundary.rad_ambient.offset, _lib.Boundary.verbatim.offset]
+            ctypes.sizeof(_lib.Boundary), _lib.Boundary.rad_ambient.offset, _lib.Boundary.verbatim.offset,
+            ctypes.sizeof(_lib.DiffOpts), ctypes.sizeof(_lib.DiffStats), _lib.DiffOpts.lin_tol.offset,
+            _lib.DiffOpts.verbatim.offset, _lib.DiffStats.lin_relres.offset, _lib.DiffStats.err_log.offset]
     assert got == want
 
 

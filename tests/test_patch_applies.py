@@ -23,7 +23,9 @@ def test_patch_touches_the_documented_files():
             "solvers/electrical/shockley/electr3d.hpp", "solvers/electrical/shockley/electr3d.cpp",
             "solvers/electrical/shockley/beta.hpp", "solvers/electrical/shockley/python/electr_python.cpp",
             "solvers/thermal/static/CMakeLists.txt", "solvers/electrical/shockley/CMakeLists.txt",
-            "solvers/thermal/dynamic/femT3d.hpp", "solvers/thermal/dynamic/femT3d.cpp", "solvers/thermal/dynamic/CMakeLists.txt"}
+            "solvers/thermal/dynamic/femT3d.hpp", "solvers/thermal/dynamic/femT3d.cpp", "solvers/thermal/dynamic/CMakeLists.txt",
+            "solvers/electrical/diffusion/diffusion3d.hpp", "solvers/electrical/diffusion/diffusion3d.cpp",
+            "solvers/electrical/diffusion/CMakeLists.txt"}
     assert set(_files()) == want
 
 
@@ -43,6 +45,8 @@ def test_patch_applies_to_the_reference(tmp_path):
     assert "shockleyParameters" in open(tmp_path / "solvers/electrical/shockley/beta.hpp").read()
     dyn = open(tmp_path / "solvers/thermal/dynamic/femT3d.cpp").read()
     assert "solve_dynamic" in dyn and "set_capacity" in dyn and "if (algorithm == ALGORITHM_CUDA) return computeCuda(time, btemperature);" in dyn
+    dif = open(tmp_path / "solvers/electrical/diffusion/diffusion3d.cpp").read()
+    assert "computeCuda(loops, act, active, A, B, C, D, J, nmodes, Ps, nrs);" in dif and "#include <plaskdiff_cuda.hpp>" in dif
 
 
 def test_every_adapter_call_of_the_patch_exists():
@@ -56,3 +60,8 @@ def test_every_adapter_call_of_the_patch_exists():
         assert re.search(r"\b%s\b" % name, hdr), f"plaskfem::{name} is not declared in plaskfem_cuda.hpp"
     for name in ("add_node", "node_to_full", "mark_excluded", "PRECOND_MLJ"):
         assert name in added and name in hdr
+    dhdr = open(os.path.join(ROOT, "include", "plaskdiff_cuda.hpp")).read()
+    for name in set(re.findall(r"region->(\w+)\(", added)):
+        assert re.search(r"\b%s\(" % name, dhdr), f"Region::{name} is not declared in plaskdiff_cuda.hpp"
+    for name in set(re.findall(r"plaskdiff::(\w+)", added)):
+        assert re.search(r"\b%s\b" % name, dhdr), f"plaskdiff::{name} is not declared in plaskdiff_cuda.hpp"

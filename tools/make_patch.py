@@ -11,7 +11,8 @@ What the patch does (INTEGRATION.md explains every hunk):
   * BetaSolver / the Python Shockley class expose beta(T), js(T) per junction through one virtual, so that the host can
     evaluate them at the mid-plane temperature of every junction column (electr3d.cpp:261-262)
   * DynamicThermalFem3DSolver: the same for the time loop of compute(time) (pfem_solve_dynamic, corrected update)
-  * the three solver CMakeLists link plaskfem_cuda
+  * Diffusion3DSolver: compute() hands the whole loop of one active region to pdiff_compute (include/plaskdiff_cuda.hpp)
+  * the four solver CMakeLists link plaskfem_cuda
 """
 import os
 import shutil
@@ -766,9 +767,136 @@ edit(F, """    size_t size = this->maskedMesh->size();
     FemMatrix& B = *pB.get();
 """)
 
+# ---------------------------------------------------------------- electrical.diffusion Diffusion3D
+F = "solvers/electrical/diffusion/diffusion3d.hpp"
+edit(F, """#include <plask/common/fem.hpp>
+#include <plask/plask.hpp>
+""", """#include <plask/common/fem.hpp>
+#include <plask/plask.hpp>
+
+namespace plaskdiff { class Region; }
+""")
+edit(F, """    std::map<size_t, ActiveRegion3D> active;  ///< Active regions information
+""", """    std::map<size_t, ActiveRegion3D> active;  ///< Active regions information
+
+    /// Algorithm 'cuda': one device context per active region (holds K, F and U on the device)
+    std::map<size_t, std::unique_ptr<plaskdiff::Region>> cuda;
+
+    /// The while(true) loop of compute() handed to libplaskfem_cuda (pdiff_compute)
+    void computeCuda(unsigned loops, size_t act, ActiveRegion3D& active,
+                     const DataVector<double>& A, const DataVector<double>& B, const DataVector<double>& C, const DataVector<double>& D,
+                     const DataVector<double>& J, size_t nmodes, const std::vector<DataVector<Tensor2<double>>>& Ps,
+                     const std::vector<DataVector<double>>& nrs);
+""")
+
+F = "solvers/electrical/diffusion/diffusion3d.cpp"
+edit(F, """#include "diffusion3d.hpp"
+
+#define DEFAULT_MESH_SPACING 0.01  // µm
+""", """#include "diffusion3d.hpp"
+
+#include <plaskdiff_cuda.hpp>
+
+#define DEFAULT_MESH_SPACING 0.01  // µm
+""")
+edit(F, """void Diffusion3DSolver::onInvalidate() { active.clear(); }
+""", """void Diffusion3DSolver::onInvalidate() {
+    active.clear();
+    cuda.clear();
+}
+
+void Diffusion3DSolver::computeCuda(unsigned loops, size_t act, ActiveRegion3D& active,
+                                    const DataVector<double>& A, const DataVector<double>& B, const DataVector<double>& C,
+                                    const DataVector<double>& D, const DataVector<double>& J, size_t nmodes,
+                                    const std::vector<DataVector<Tensor2<double>>>& Ps, const std::vector<DataVector<double>>& nrs) {
+    const size_t nn = active.mesh2->size(), ne = active.emesh2->size();
+    try {
+        auto& region = cuda[act];
+        if (!region) {
+            const auto& lateral = *active.mesh2->lateralMesh;
+            const auto& full = lateral.fullMesh;
+            std::vector<double> ax0(full.axis[0]->size()), ax1(full.axis[1]->size());
+            for (size_t i = 0; i != ax0.size(); ++i) ax0[i] = full.axis[0]->at(i);
+            for (size_t i = 0; i != ax1.size(); ++i) ax1[i] = full.axis[1]->at(i);
+            const int order = full.getIterationOrder() == RectangularMesh2D::ORDER_01 ? PDIFF_ORDER_01 : PDIFF_ORDER_10;
+            region.reset(new plaskdiff::Region(this->getId(), ax0, ax1, order, [&](size_t i0, size_t i1) {
+                return lateral.getElementIndexFromLowIndexes(i0, i1) != RectangularMaskedMesh2D::NOT_INCLUDED;
+            }));
+            region->set_U(active.U.data());
+        }
+        region->set_parameters(A.data(), B.data(), C.data(), D.data());
+        region->set_current(J.data());
+        std::vector<DataVector<double>> Pm(nmodes), Gm(nmodes), dGm(nmodes);
+        std::vector<const double*> Pp(nmodes), Gp(nmodes), dGp(nmodes);
+        std::fill(active.modesP.begin(), active.modesP.end(), 0.);
+        for (size_t n = 0; n != nmodes; ++n) {
+            double wavelength = real(inWavelength(n));
+            double factor = inv_hc * wavelength;
+            auto gain = inGain(active.emesh2, wavelength, InterpolationMethod::INTERPOLATION_SPLINE);
+            auto dgdn = inGain(Gain::DGDN, active.emesh2, wavelength, InterpolationMethod::INTERPOLATION_SPLINE);
+            Pm[n].reset(2 * nn); Gm[n].reset(2 * ne); dGm[n].reset(2 * ne);
+            for (size_t i = 0; i != nn; ++i) { Pm[n][2 * i] = Ps[n][i].c00; Pm[n][2 * i + 1] = Ps[n][i].c11; }
+            for (size_t ie = 0; ie != ne; ++ie) {
+                ElementParams3D el(active, ie);
+                Tensor2<double> g = nrs[n][ie] * gain[ie], dg = nrs[n][ie] * dgdn[ie];
+                Tensor2<double> p = integrateBilinear(el.X, el.Y, Ps[n].data() + ie);
+                active.modesP[n] += p.c00 * g.c00 + p.c11 * g.c11;
+                Gm[n][2 * ie] = factor * g.c00; Gm[n][2 * ie + 1] = factor * g.c11;
+                dGm[n][2 * ie] = factor * dg.c00; dGm[n][2 * ie + 1] = factor * dg.c11;
+            }
+            active.modesP[n] *= 1e-13 * active.QWheight;
+            Pp[n] = Pm[n].data(); Gp[n] = Gm[n].data(); dGp[n] = dGm[n].data();
+        }
+        region->set_modes(Pp, Gp, dGp);
+        pdiff_stats stats;
+        int rc = region->compute(loops, maxerr, stats, true, int(iter_params.maxit));
+        for (int i = 1; i < stats.loops && i < 64; ++i)
+            this->writelog(LOG_RESULT, "Loop {:d}({:d}) @ active region {}: error = {:g}%", i, loopno + i, act, stats.err_log[i]);
+        loopno += stats.loops;
+        if (rc == PFEM_NOT_CONVERGED) {
+            if (iter_params.no_convergence_behavior == IterativeMatrixParams::NO_CONVERGENCE_ERROR)
+                throw ComputationError(this->getId(), "Iterative solver did not converge in {} iterations", iter_params.maxit);
+            this->writelog(LOG_WARNING, "Iterative solver did not converge in {} iterations", iter_params.maxit);
+        }
+        region->get_U(active.U.data());
+    } catch (const plaskdiff::NoDevice& err) {
+        throw ComputationError(this->getId(), "algorithm 'cuda' has no CPU fallback: {}", err.what());
+    } catch (const plaskdiff::BadInput& err) {
+        throw BadInput(this->getId(), "{}", err.what());
+    } catch (const plaskdiff::ComputationError& err) {
+        throw ComputationError(this->getId(), "{}", err.what());
+    }
+}
+""")
+edit(F, """    unsigned loop = 0;
+
+    std::unique_ptr<FemMatrix> K;
+
+    toterr = 0.;
+""", """    unsigned loop = 0;
+
+    if (this->algorithm == ALGORITHM_CUDA) {
+        // assembly, residual, decision and linear solve of every loop run on the device (include/plaskdiff_cuda.h)
+        toterr = 0.;
+        computeCuda(loops, act, active, A, B, C, D, J, nmodes, Ps, nrs);
+        outCarriersConcentration.fireChanged();
+        return toterr;
+    }
+
+    std::unique_ptr<FemMatrix> K;
+
+    toterr = 0.;
+""")
+edit(F, """        case ALGORITHM_ITERATIVE: K.reset(new SparseFreeMatrix(this, N, 78 * ne)); break;
+    }
+""", """        case ALGORITHM_ITERATIVE: K.reset(new SparseFreeMatrix(this, N, 78 * ne)); break;
+        case ALGORITHM_CUDA: break;  // handled above
+    }
+""")
+
 # ---------------------------------------------------------------- build
 for F, target in (("solvers/thermal/static/CMakeLists.txt", "thermal"), ("solvers/electrical/shockley/CMakeLists.txt", "electrical"),
-                  ("solvers/thermal/dynamic/CMakeLists.txt", "dynamic")):
+                  ("solvers/thermal/dynamic/CMakeLists.txt", "dynamic"), ("solvers/electrical/diffusion/CMakeLists.txt", "diffusion")):
     edit(F, """# Build everything the default way.
 # Call this macro unless you really know what you are doing!
 make_default()""", """# Algorithm 'cuda': the header-only host adapter plaskfem_cuda.hpp and libplaskfem_cuda.so (a plain C ABI; the solver does not

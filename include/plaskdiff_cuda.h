@@ -12,7 +12,7 @@
  * and the spline evaluation of outCarriersConcentration                   diffusion3d.cpp:420-458.
  * The plugin keeps what is geometry: setupActiveRegions (diffusion3d.cpp:89-178), the vertical averaging of inTemperature /
  * inLightE over the quantum wells (diffusion3d.hpp:92-105), the material calls A(T), B(T), C(T), D(T), Nr (diffusion3d.cpp:222-230,
- * 258-262) and the receivers inCurrentDensity / inGain (diffusion3d.cpp:232-238, 295-296).  INTEGRATION.md 11 shows the binding.
+ * 258-262) and the receivers inCurrentDensity / inGain (diffusion3d.cpp:232-238, 295-296).  INTEGRATION.md 10 shows the binding.
  *
  * The unknowns are those of the reference: three per node of the lateral mesh — value, d/dy, d/dx (ElementParams3D,
  * diffusion3d.hpp:108-141) — on the 12-function Hermite element.  The element integrals are evaluated on the device by 7x7
@@ -24,7 +24,7 @@
  * thread-safe per context).  Arrays use the FULL lateral grid numbering of RectangularMesh2D(lon, tran) — node = index_f(i0, i1)
  * of the given iteration order (rectangular2d.cpp:21-33), element likewise on (n0-1) x (n1-1) — NOT the masked numbering of
  * RectangularMaskedMesh2D: elements outside the active region are flagged in `elem_active`, nodes that touch no active element are
- * not unknowns and read back as 0 (plaskfem::MaskedNumbering2D in plaskfem_cuda.hpp maps between the two numberings).
+ * not unknowns and read back as 0 (plaskdiff::MaskedNumbering2D in plaskdiff_cuda.hpp maps between the two numberings).
  */
 #ifndef PLASKDIFF_CUDA_H
 #define PLASKDIFF_CUDA_H
@@ -65,7 +65,7 @@ int pdiff_set_current(pdiff_ctx* ctx, const double* J);
  *   P[m][node][2]  = (c00, c11) of Ps[m] (diffusion3d.cpp:264-271),
  *   G[m][elem][2]  = factor * nrs[m][e] * gain[e]   (c00, c11),  dG likewise from dgdn   (diffusion3d.cpp:289-294).
  * nmodes = 0 switches it off.  The burned power modesP (diffusion3d.cpp:295,303) does not involve the unknowns and stays with the
- * host (plaskfem::burned_power). */
+ * host (plaskdiff::burned_power). */
 int pdiff_set_modes(pdiff_ctx* ctx, size_t nmodes, const double* P, const double* G, const double* dG);
 
 /* The unknowns active.U, 3 per node of the full grid (value, d/dy, d/dx); NULL in set = zeros. */

@@ -42,6 +42,7 @@ struct Problem {
     int nmodes;
     const double *P, *G, *dG;   // [m][NL][2]
     double* Ke;                 // [144][NLp]
+    double* St;                 // [81][NLp] nodal stencil of K (see gather_nodes)
     double* Mi;                 // [6][NLp] inverse of the nodal 3x3 blocks (xx, xy, xz, yy, yz, zz)
     double *F, *U, *r, *z, *q, *p0, *p1;   // [3][NLp]
     double* part;               // [grid][4] block partial sums
@@ -146,34 +147,55 @@ __device__ void assemble_all(const Problem& P, int verbatim, double* Fe /* [12][
 
 __device__ __forceinline__ int elem_off(const Problem& P, int l) { return (l & 1 ? P.s1 : 0) + (l & 2 ? P.s0 : 0); }
 
-// load vector (gather of the element entries: no atomics, bit-reproducible) and the inverse nodal blocks
+// Per node: the load vector, the 9 x (3x3) blocks of the node's rows of K (the nodal stencil St[(27 c + 3 nb + c2)*NLp + n],
+// neighbour nb = 3 (d0 + 1) + (d1 + 1)) and the inverse of the diagonal block — gathered from the <= 4 adjacent elements, no atomics,
+// bit-reproducible.  The iteration applies K from the stencil: 81 + 27 loads per node instead of 144 + 48 through the element
+// matrices, 648 B per node instead of 1 152 B per element.  Nodes that are not unknowns get a unit row.
 __device__ void gather_nodes(const Problem& P, const double* Fe, int gtid, int gsize) {
     for (int n = gtid; n < P.NL; n += gsize) {
         double f[3] = {0., 0., 0.};
         double m[6] = {0., 0., 0., 0., 0., 0.};
-        if (P.nact[n]) {
+        const bool act = P.nact[n];
+        bool ea[4];
 #pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                const int e = n - elem_off(P, l);
-                if (!P.eact[e]) continue;
-                const int r0 = 3 * l;
+        for (int l = 0; l < 4; ++l) ea[l] = act && P.eact[n - elem_off(P, l)];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) f[c] += Fe[(size_t)(r0 + c) * P.NLp + e];
-                m[0] += P.Ke[(size_t)(12 * r0 + r0) * P.NLp + e];
-                m[1] += P.Ke[(size_t)(12 * r0 + r0 + 1) * P.NLp + e];
-                m[2] += P.Ke[(size_t)(12 * r0 + r0 + 2) * P.NLp + e];
-                m[3] += P.Ke[(size_t)(12 * (r0 + 1) + r0 + 1) * P.NLp + e];
-                m[4] += P.Ke[(size_t)(12 * (r0 + 1) + r0 + 2) * P.NLp + e];
-                m[5] += P.Ke[(size_t)(12 * (r0 + 2) + r0 + 2) * P.NLp + e];
+        for (int l = 0; l < 4; ++l)
+            if (ea[l]) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) f[c] += Fe[(size_t)(3 * l + c) * P.NLp + n - elem_off(P, l)];
             }
-            // inverse of the symmetric 3x3 block by cofactors
+#pragma unroll
+        for (int nb = 0; nb < 9; ++nb) {
+            const int d0 = nb / 3 - 1, d1 = nb % 3 - 1;
+            double b[9] = {0., 0., 0., 0., 0., 0., 0., 0., 0.};
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {      // the node is local node l of element n - off(l); the neighbour is its local node l2
+                const int a0 = (l >> 1) + d0, a1 = (l & 1) + d1;
+                if (a0 < 0 || a0 > 1 || a1 < 0 || a1 > 1) continue;
+                const int l2 = 2 * a0 + a1;
+                if (!ea[l]) continue;
+                const double* Kb = P.Ke + (size_t)(12 * 3 * l + 3 * l2) * P.NLp + (n - elem_off(P, l));
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int c2 = 0; c2 < 3; ++c2) b[3 * c + c2] += Kb[(size_t)(12 * c + c2) * P.NLp];
+            }
+            if (nb == 4) {
+                if (!act) b[0] = b[4] = b[8] = 1.;
+                m[0] = b[0]; m[1] = b[1]; m[2] = b[2]; m[3] = b[4]; m[4] = b[5]; m[5] = b[8];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int c2 = 0; c2 < 3; ++c2) P.St[(size_t)(27 * c + 3 * nb + c2) * P.NLp + n] = b[3 * c + c2];
+        }
+        if (act) {   // inverse of the symmetric 3x3 diagonal block by cofactors
             const double c00 = m[3] * m[5] - m[4] * m[4], c01 = m[2] * m[4] - m[1] * m[5], c02 = m[1] * m[4] - m[2] * m[3];
             const double det = m[0] * c00 + m[1] * c01 + m[2] * c02, id = 1. / det;
             const double i0 = c00 * id, i1 = c01 * id, i2 = c02 * id;
             const double i3 = (m[0] * m[5] - m[2] * m[2]) * id, i4 = (m[1] * m[2] - m[0] * m[4]) * id, i5 = (m[0] * m[3] - m[1] * m[1]) * id;
             m[0] = i0; m[1] = i1; m[2] = i2; m[3] = i3; m[4] = i4; m[5] = i5;
-        } else {
-            m[0] = m[3] = m[5] = 1.;
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) P.F[c * P.NLp + n] = f[c];
@@ -182,30 +204,20 @@ __device__ void gather_nodes(const Problem& P, const double* Fe, int gtid, int g
     }
 }
 
-// y = (K v)(node n); `getv(node, c)` supplies v.  Rows of nodes that are not unknowns are unit rows.
+// y = (K v)(node n) from the nodal stencil; `getv(node, c)` supplies v.  Stencil entries towards nodes that do not exist are zero; the
+// index is clamped so that the (unused) load stays inside the vector.
 template <class GetV> __device__ __forceinline__ void apply_node(const Problem& P, int n, GetV getv, double y[3]) {
-    if (!P.nact[n]) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) y[c] = getv(n, c);
-        return;
-    }
     y[0] = y[1] = y[2] = 0.;
+    const double* S = P.St + n;
 #pragma unroll
-    for (int l = 0; l < 4; ++l) {
-        const int e = n - elem_off(P, l);
-        if (!P.eact[e]) continue;
-        const double* Kr = P.Ke + (size_t)(36 * l) * P.NLp + e;   // rows 3l .. 3l+2
+    for (int nb = 0; nb < 9; ++nb) {
+        const int m = min(max(n + (nb / 3 - 1) * P.s0 + (nb % 3 - 1) * P.s1, 0), P.NL - 1);
 #pragma unroll
-        for (int l2 = 0; l2 < 4; ++l2) {
-            const int nb = e + elem_off(P, l2);
-#pragma unroll
-            for (int c2 = 0; c2 < 3; ++c2) {
-                const double v = getv(nb, c2);
-                const int col = 3 * l2 + c2;
-                y[0] = fma(Kr[(size_t)col * P.NLp], v, y[0]);
-                y[1] = fma(Kr[(size_t)(12 + col) * P.NLp], v, y[1]);
-                y[2] = fma(Kr[(size_t)(24 + col) * P.NLp], v, y[2]);
-            }
+        for (int c2 = 0; c2 < 3; ++c2) {
+            const double v = getv(m, c2);
+            y[0] = fma(S[(size_t)(3 * nb + c2) * P.NLp], v, y[0]);
+            y[1] = fma(S[(size_t)(27 + 3 * nb + c2) * P.NLp], v, y[1]);
+            y[2] = fma(S[(size_t)(54 + 3 * nb + c2) * P.NLp], v, y[2]);
         }
     }
 }

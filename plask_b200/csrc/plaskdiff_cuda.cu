@@ -26,7 +26,7 @@ struct pdiff_ctx {
     // device allocations
     double *d_ax0 = nullptr, *d_ax1 = nullptr, *d_h0 = nullptr, *d_h1 = nullptr;
     uint8_t *d_eact_base = nullptr, *d_nact = nullptr;
-    double *d_par = nullptr, *d_J = nullptr, *d_modes = nullptr, *d_Ke = nullptr, *d_Mi = nullptr, *d_vec = nullptr, *d_Fe = nullptr,
+    double *d_par = nullptr, *d_J = nullptr, *d_modes = nullptr, *d_Ke = nullptr, *d_St = nullptr, *d_Mi = nullptr, *d_vec = nullptr, *d_Fe = nullptr,
            *d_part = nullptr, *d_tmp = nullptr;
     Control* d_ctl = nullptr;
     size_t modes_cap = 0, tmp_cap = 0;
@@ -117,11 +117,11 @@ int init_tables(pdiff_ctx* ctx) {
 }
 
 void free_mesh(pdiff_ctx* c) {
-    void* ptrs[] = {c->d_ax0, c->d_ax1, c->d_h0, c->d_h1, c->d_eact_base, c->d_nact, c->d_par, c->d_J, c->d_modes, c->d_Ke, c->d_Mi,
+    void* ptrs[] = {c->d_ax0, c->d_ax1, c->d_h0, c->d_h1, c->d_eact_base, c->d_nact, c->d_par, c->d_J, c->d_modes, c->d_Ke, c->d_St, c->d_Mi,
                     c->d_vec, c->d_Fe, c->d_part, c->d_tmp};
     for (void* p : ptrs)
         if (p) cudaFree(p);
-    c->d_ax0 = c->d_ax1 = c->d_h0 = c->d_h1 = c->d_par = c->d_J = c->d_modes = c->d_Ke = c->d_Mi = c->d_vec = c->d_Fe = c->d_part =
+    c->d_ax0 = c->d_ax1 = c->d_h0 = c->d_h1 = c->d_par = c->d_J = c->d_modes = c->d_Ke = c->d_St = c->d_Mi = c->d_vec = c->d_Fe = c->d_part =
         c->d_tmp = nullptr;
     c->d_eact_base = c->d_nact = nullptr;
     c->modes_cap = c->tmp_cap = 0;
@@ -269,6 +269,7 @@ int pdiff_set_mesh(pdiff_ctx* ctx, size_t n0, size_t n1, const double* ax0, cons
     PD_CUDA(cudaMalloc(&ctx->d_par, 4 * NLp * sizeof(double)));
     PD_CUDA(cudaMalloc(&ctx->d_J, NLp * sizeof(double)));
     PD_CUDA(cudaMalloc(&ctx->d_Ke, 144 * NLp * sizeof(double)));
+    PD_CUDA(cudaMalloc(&ctx->d_St, 81 * NLp * sizeof(double)));
     PD_CUDA(cudaMalloc(&ctx->d_Mi, 6 * NLp * sizeof(double)));
     PD_CUDA(cudaMalloc(&ctx->d_vec, 7 * 3 * NLp * sizeof(double)));
     PD_CUDA(cudaMalloc(&ctx->d_Fe, 12 * NLp * sizeof(double)));
@@ -277,6 +278,7 @@ int pdiff_set_mesh(pdiff_ctx* ctx, size_t n0, size_t n1, const double* ax0, cons
     PD_CUDA(cudaMemsetAsync(ctx->d_par, 0, 4 * NLp * sizeof(double), ctx->stream));
     PD_CUDA(cudaMemsetAsync(ctx->d_J, 0, NLp * sizeof(double), ctx->stream));
     PD_CUDA(cudaMemsetAsync(ctx->d_Ke, 0, 144 * NLp * sizeof(double), ctx->stream));
+    PD_CUDA(cudaMemsetAsync(ctx->d_St, 0, 81 * NLp * sizeof(double), ctx->stream));
     PD_CUDA(cudaMemsetAsync(ctx->d_Mi, 0, 6 * NLp * sizeof(double), ctx->stream));
     PD_CUDA(cudaMemsetAsync(ctx->d_vec, 0, 7 * 3 * NLp * sizeof(double), ctx->stream));
     PD_CUDA(cudaMemsetAsync(ctx->d_Fe, 0, 12 * NLp * sizeof(double), ctx->stream));
@@ -294,7 +296,7 @@ int pdiff_set_mesh(pdiff_ctx* ctx, size_t n0, size_t n1, const double* ax0, cons
     P.A = ctx->d_par; P.B = ctx->d_par + NLp; P.C = ctx->d_par + 2 * NLp; P.D = ctx->d_par + 3 * NLp;
     P.J = ctx->d_J;
     P.nmodes = 0; P.P = P.G = P.dG = nullptr;
-    P.Ke = ctx->d_Ke; P.Mi = ctx->d_Mi;
+    P.Ke = ctx->d_Ke; P.St = ctx->d_St; P.Mi = ctx->d_Mi;
     double* v = ctx->d_vec;
     P.F = v; P.U = v + 3 * NLp; P.r = v + 6 * NLp; P.z = v + 9 * NLp; P.q = v + 12 * NLp; P.p0 = v + 15 * NLp; P.p1 = v + 18 * NLp;
 

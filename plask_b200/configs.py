@@ -410,17 +410,22 @@ def thickness_material_ids(key, thickness):
 
 # ------------------------------------------------------------------------- slab partition
 
-def slab_range(nK, rank, nranks):
-    """Owned node planes [K0, K1) of `rank` along the major axis (balanced, contiguous)."""
+def slab_range(nK, rank, nranks, align=1):
+    """Owned node planes [K0, K1) of `rank` along the major axis (balanced, contiguous).  align > 1: every boundary between two
+    ranks is a multiple of `align` planes (the multilevel preconditioner wants 16: its lateral aggregates must not straddle slabs)."""
+    if align > 1:
+        blocks = -(-nK // align)
+        b0, b1 = slab_range(blocks, rank, nranks)
+        return min(b0 * align, nK), min(b1 * align, nK)
     base, rem = divmod(nK, nranks)
     K0 = rank * base + min(rank, rem)
     return K0, K0 + base + (1 if rank < rem else 0)
 
 
-def slab_local(nK, rank, nranks):
+def slab_local(nK, rank, nranks, align=1):
     """(lo, hi, own_lo, own_hi): local node planes [lo, hi) of the global major axis = owned planes plus one halo
     plane towards each neighbour, and the owned range in LOCAL plane indices."""
-    K0, K1 = slab_range(nK, rank, nranks)
+    K0, K1 = slab_range(nK, rank, nranks, align)
     lo, hi = K0 - (1 if rank > 0 else 0), K1 + (1 if rank < nranks - 1 else 0)
     return lo, hi, K0 - lo, K1 - lo
 
@@ -445,13 +450,15 @@ def slab_order(order, axis):
     return f"{axis}{rest[0]}{rest[1]}"
 
 
-def slab_problem(p, rank, nranks, axis=None):
+def slab_problem(p, rank, nranks, axis=None, align=1):
     """Cut the local problem of `rank` out of a global Problem (thermal or Shockley) — what the solver plugin would do on each
     process before calling the C ABI in slab mode.  `axis`: the physical axis to cut (default: the major axis of the mesh's
-    order; see slab_axis).  Returns (local Problem, own_lo, own_hi, (lo, hi))."""
+    order; see slab_axis); `align`: see slab_range.  Returns (local Problem, own_lo, own_hi, (lo, hi))."""
     major = ORDERS[p.order][0] if axis is None else int(axis)
     n = p.n
-    lo, hi, own_lo, own_hi = slab_local(n[major], rank, nranks)
+    lo, hi, own_lo, own_hi = slab_local(n[major], rank, nranks, align)
+    if hi - lo < 2 or own_hi <= own_lo:
+        raise ValueError(f"slab_problem: rank {rank} of {nranks} gets no planes of the {n[major]}-plane axis with align = {align}")
     axes = [a.copy() for a in p.axes]
     axes[major] = axes[major][lo:hi]
     q = Problem(p.name + f"[{rank}/{nranks}]", p.kind, axes, slab_order(p.order, major), None, p.T0, p.dT, p.tab_lat, p.tab_vert, None, None,

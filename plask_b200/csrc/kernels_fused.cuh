@@ -189,7 +189,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         }
     }
     auto load_zc = [&](const int P) {   // coarse correction of node plane P
-        const int Pc = min(max(P, 0), g.nK - 1);
+        const int Pc = min(max(P, 0), g.nK - 1) + ca.koff;
         const double* const a1 = ca.z1 + (idx_t)(Pc >> ca.sh1) * ca.nJ1 * g.sJ;
         const double* const a2 = ca.z2 + (idx_t)(Pc >> ca.sh2) * ca.nJ2 * g.sJ;
 #pragma unroll
@@ -507,7 +507,7 @@ k_fpcg(const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtenso
         if (tid == 0 && t + NS <= nsteps) issue(t + NS);
         if (MLZ) {   // the next plane lies in another level-1 aggregate: fetch its coarse correction now, use it next step
             const int Pn = min(max(k0 + t, 0), g.nK - 1), Pc = min(max(k0 - 1 + t, 0), g.nK - 1);
-            if ((Pn >> ca.sh1) != (Pc >> ca.sh1)) load_zc(Pn);
+            if (((Pn + ca.koff) >> ca.sh1) != ((Pc + ca.koff) >> ca.sh1)) load_zc(Pn);
         }
 
         // ---------------- phase 2: gather layer L between planes a (registers) and b --------
@@ -905,7 +905,7 @@ static inline cudaError_t launch_fused_vdim(const FusedPlan& f, const Grid& g, i
 template <int MODE>
 static inline cudaError_t launch_fused_dispatch(const FusedPlan& f, const Grid& g, int par, double* r_out, double* q_out,
                                                 double* p_out, double* x, Scalars* sc, double* partials, const PeerOut& po,
-                                                cudaStream_t st, const CoarseAdd ca = CoarseAdd{nullptr, 0, 0, nullptr, 0, 0, nullptr}) {
+                                                cudaStream_t st, const CoarseAdd ca = CoarseAdd{nullptr, 0, 0, nullptr, 0, 0, nullptr, 0}) {
 #define PFEM_FUSED_CASE(TJ, RJ, NS, MINB) \
     if (f.tj == TJ && f.rj == RJ && f.ns == NS && f.minb == MINB) return launch_fused_vdim<TJ, RJ, NS, MINB, MODE>(f, g, par, r_out, q_out, p_out, x, sc, partials, po, st, ca);
     PFEM_FUSED_CASE(8, 2, 2, 3)    // production tile (tools/tune_fused.py); the others are kept for PFEM_FUSED_TILE tuning runs

@@ -35,6 +35,10 @@ namespace pfem {
 struct LineDom {
     int nI, nJ, nK;
     idx_t sJ, sK;
+    // slab mode (fine level only): rows k outside [k0, k1) belong to the neighbours and are skipped; row k lies in the level-1
+    // aggregate (k + koff) >> 2.  koff = 16 - kown0 puts one empty 16-plane aggregate in front of the owned planes, so the halo
+    // planes fall into aggregates of their own whose coarse z stays 0.  Single GPU: k0 = 0, k1 = nK, koff = 0.
+    int k0, k1, koff;
 };
 
 struct MLDev {
@@ -58,11 +62,11 @@ struct MLDev {
 // The diagonal entry itself is taken from the Jacobi diagonal (1/dinv), which includes the convection face terms.
 __global__ void __launch_bounds__(32 * PFEM_ML_C * PFEM_ML_C)
 k_ml_rowsums(const Grid g, const double* __restrict__ cl, const double* __restrict__ cv, const double* __restrict__ dinv,
-             const int nlev, const int nJ1, double* __restrict__ S, const idx_t slen) {
+             const int nlev, const int nJ1, double* __restrict__ S, const idx_t slen, const int koff) {
     __shared__ double sbuf[PFEM_ML_C * PFEM_ML_C][33];
     const int i = blockIdx.x * 32 + threadIdx.x;
-    const int j = blockIdx.y * PFEM_ML_C + threadIdx.y, k = blockIdx.z * PFEM_ML_C + threadIdx.z;
-    const bool valid = i < g.nI && j < g.nJ && k < g.nK;
+    const int j = blockIdx.y * PFEM_ML_C + threadIdx.y, k = blockIdx.z * PFEM_ML_C + threadIdx.z - koff;
+    const bool valid = i < g.nI && j < g.nJ && k >= g.kown0 && k < g.kown1;   // rows of this rank (all rows on one GPU)
     double a0[PFEM_ML_MAXL], a1[PFEM_ML_MAXL];
 #pragma unroll
     for (int l = 0; l < PFEM_ML_MAXL; ++l) a0[l] = a1[l] = 0.;
@@ -93,7 +97,7 @@ k_ml_rowsums(const Grid g, const double* __restrict__ cl, const double* __restri
                         const double v = kv[a ^ b];
                         // first level on which (j, k) and (jj, kk) share an aggregate
                         int l = 1;
-                        while (l < nlev && (((j ^ jj) | (k ^ kk)) >> (PFEM_ML_SHIFT * l)) != 0) ++l;
+                        while (l < nlev && (((j ^ jj) | ((k + koff) ^ (kk + koff))) >> (PFEM_ML_SHIFT * l)) != 0) ++l;
 #pragma unroll
                         for (int m = 0; m < PFEM_ML_MAXL; ++m)
                             if (m == l - 1) { if (di == 0) a0[m] += v; else a1[m] += v; }
@@ -287,7 +291,7 @@ k_line_ml(const LineDom d, const double* __restrict__ r_in, const double* __rest
     const double alpha = (FINE && mode == 0) ? sc->alpha : 0.;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     double* const tb = tbuf[w];
-    const int naJ = (d.nJ + PFEM_ML_C - 1) / PFEM_ML_C, naK = (d.nK + PFEM_ML_C - 1) / PFEM_ML_C;
+    const int naJ = (d.nJ + PFEM_ML_C - 1) / PFEM_ML_C, naK = (d.nK + d.koff + PFEM_ML_C - 1) / PFEM_ML_C;
     double acc[2] = {0., 0.};
     double tot[NE];                    // block total of the residual rows (elements threadIdx.x + 256 e)
 #pragma unroll
@@ -299,8 +303,8 @@ k_line_ml(const LineDom d, const double* __restrict__ r_in, const double* __rest
         for (int c = 0; c < SEG / 2; ++c) rs[c] = make_double2(0., 0.);
 #pragma unroll 1
         for (int t = 0; t < 2; ++t) {
-            const int j = J * PFEM_ML_C + (w & 3), k = K * PFEM_ML_C + 2 * (w >> 2) + t;
-            if (j >= d.nJ || k >= d.nK) continue;     // warp-uniform
+            const int j = J * PFEM_ML_C + (w & 3), k = K * PFEM_ML_C + 2 * (w >> 2) + t - d.koff;
+            if (j >= d.nJ || k < d.k0 || k >= d.k1) continue;     // warp-uniform
             const idx_t base = d.sJ * j + d.sK * (idx_t)k;
             double2 vr[SEG / 2], vl[SEG / 2], vd[SEG / 2], vz[SEG / 2];
 #pragma unroll
@@ -356,6 +360,7 @@ k_line_ml(const LineDom d, const double* __restrict__ r_in, const double* __rest
     }
     if (grid_reduce<2, false>(acc, partials, &sc->ticket[3], sh, &sh_flag)) {
         double rho_top = 0.;
+        bool summed = false;   // acc already holds the totals of all levels and ranks
         if (top.part) {
             // residual of the top level = sum of all rows of this level, block totals added in block order
 #pragma unroll
@@ -369,6 +374,13 @@ k_line_ml(const LineDom d, const double* __restrict__ r_in, const double* __rest
                 }
             }
             __syncthreads();
+            // slab mode: the top level is the 1-D problem of the WHOLE device — its residual is the sum over the ranks, every rank
+            // solves the same line; the scalars of the lower levels travel with it (acc: r.z of this rank's levels, |r'|^2)
+            if (sc->comm) {
+                if (threadIdx.x == 0) { acc[0] += FINE ? 0. : sc->ml_rho; acc[1] = FINE ? acc[1] : sc->ml_rr; }
+                rank_allreduce_vec<2>(acc, tbuf[1], (int)d.sJ, sc->comm, sh);
+                summed = true;
+            }
             if (w == 0) {
                 double2 vr[SEG / 2], vl[SEG / 2], vd[SEG / 2], vz[SEG / 2];
 #pragma unroll
@@ -389,8 +401,8 @@ k_line_ml(const LineDom d, const double* __restrict__ r_in, const double* __rest
             }
         }
         if (threadIdx.x == 0) {
-            const double rho = (FINE ? acc[0] : sc->ml_rho + acc[0]) + rho_top;
-            const double rr = FINE ? acc[1] : sc->ml_rr;
+            const double rho = (FINE || summed ? acc[0] : sc->ml_rho + acc[0]) + rho_top;
+            const double rr = FINE || summed ? acc[1] : sc->ml_rr;
             sc->ml_rho = rho; sc->ml_rr = rr;
             if (top.part) ml_finalize(sc, rho, rr, mode);
         }
@@ -405,7 +417,36 @@ struct CoarseAdd {
     const double* z2;
     int nJ2, sh2;
     const double* zt;    // z_top [sJ]
+    int koff;            // plane k lies in the level-1 aggregate row (k + koff) >> sh1 (slab mode: see LineDom)
 };
+
+// Slab mode: the operator kernel forms p' on its halo planes from z of the neighbour's boundary plane.  z_0 + z_1 + z_2 of the
+// first / last owned plane goes into the neighbour's halo plane of z_0 (whose own coarse aggregates are empty); z_top is the same
+// on all ranks and is added by the receiver like on every other plane.  Followed by k_rank_barrier.
+__global__ void k_ml_halo(const Grid g, const double* __restrict__ z0, const CoarseAdd ca, double* z_lo, double* z_hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= g.nI) return;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        double* dst = side ? z_hi : z_lo;
+        if (!dst) continue;
+        const int k = side ? g.kown1 - 1 : g.kown0, kc = k + ca.koff;
+        const idx_t n = i + g.sJ * j + g.sK * (idx_t)k;
+        dst[g.sJ * j + i] = z0[n] + ca.z1[((idx_t)(kc >> ca.sh1) * ca.nJ1 + (j >> ca.sh1)) * g.sJ + i] +
+                            ca.z2[((idx_t)(kc >> ca.sh2) * ca.nJ2 + (j >> ca.sh2)) * g.sJ + i];
+    }
+}
+
+// Set-up in slab mode: diagonal and coupling of the top line are sums over the ranks (one block, before k_ml_factor of the top level)
+__global__ void k_ml_top_allreduce(double* ld, double* ll, const int n, Scalars* sc) {
+    __shared__ double sh[PFEM_COMM_NV];
+    __shared__ double buf[PFEM_COMM_VEC];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { buf[i] = ld[i]; buf[n + i] = ll[i]; }
+    double v[1] = {0.};
+    rank_allreduce_vec<1>(v, buf, 2 * n, sc->comm, sh);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { ld[i] = buf[i]; ll[i] = buf[n + i]; }
+}
 
 __global__ void k_pupdate_plain(idx_t N, const double* __restrict__ r, const double* __restrict__ dinv, double* __restrict__ z) {
     for (idx_t n = blockIdx.x * (idx_t)blockDim.x + threadIdx.x; n < N; n += (idx_t)gridDim.x * blockDim.x) z[n] = dinv[n] * r[n];
@@ -416,7 +457,8 @@ __global__ void k_ml_prolong_add(const Grid g, const double* __restrict__ z0, co
     const int j = blockIdx.y, k = blockIdx.z;
     if (i >= g.nI) return;
     const idx_t n = i + g.sJ * j + g.sK * (idx_t)k;
-    out[n] = z0[n] + ca.z1[((idx_t)(k >> ca.sh1) * ca.nJ1 + (j >> ca.sh1)) * g.sJ + i] + ca.z2[((idx_t)(k >> ca.sh2) * ca.nJ2 + (j >> ca.sh2)) * g.sJ + i] + ca.zt[i];
+    const int kc = k + ca.koff;
+    out[n] = z0[n] + ca.z1[((idx_t)(kc >> ca.sh1) * ca.nJ1 + (j >> ca.sh1)) * g.sJ + i] + ca.z2[((idx_t)(kc >> ca.sh2) * ca.nJ2 + (j >> ca.sh2)) * g.sJ + i] + ca.zt[i];
 }
 
 }  // namespace pfem

@@ -49,10 +49,12 @@ struct Grid {
 // ---- slab mode (one context per GPU, peers mapped with CUDA IPC over NVLink) ----------------
 #define PFEM_MAX_RANKS 8
 #define PFEM_COMM_NV 8
+#define PFEM_COMM_VEC 1024   // doubles per rank of the vector exchange (multilevel top level: one or two vertical lines of <= 512 nodes)
 // One per rank, in memory the rank exports: peers deposit their partial sums here.
 struct Inbox {
     double data[2][PFEM_MAX_RANKS][PFEM_COMM_NV];
     unsigned long long flag[2][PFEM_MAX_RANKS];
+    double vec[2][PFEM_MAX_RANKS][PFEM_COMM_VEC];
 };
 struct Comm {
     int rank, nranks;
@@ -237,6 +239,31 @@ __device__ __forceinline__ void rank_allreduce(double (&v)[NV], Comm* cm, double
             v[a] = acc;
         }
         *(volatile unsigned long long*)&cm->seq = s + 1ull;
+    }
+    __syncthreads();
+}
+
+// The same exchange carrying a vector of n <= PFEM_COMM_VEC doubles besides the NV scalars: all threads of the block store the vector
+// into every rank's inbox first (the system-scope fence of the scalar exchange publishes those stores, cumulativity through the
+// block barrier), then the scalar exchange runs, then every rank adds the vectors in rank order -> bit-identical sums everywhere.
+// One vector exchange per sequence number, same slot as the scalars of that exchange.
+template <int NV>
+__device__ __forceinline__ void rank_allreduce_vec(double (&v)[NV], double* vec, const int n, Comm* cm, double* sh) {
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const int nt = blockDim.x * blockDim.y * blockDim.z;
+    __syncthreads();
+    const unsigned long long s = *(volatile unsigned long long*)&cm->seq;
+    const int slot = (int)(s & 1ull), me = cm->rank, nr = cm->nranks;
+    for (int r = 0; r < nr; ++r) {
+        double* dst = cm->inbox[r]->vec[slot][me];
+        for (int i = tid; i < n; i += nt) *(volatile double*)&dst[i] = vec[i];
+    }
+    rank_allreduce<NV, false>(v, cm, sh);   // starts and ends with a block barrier; thread 0 advances cm->seq
+    const Inbox* mine = cm->inbox[me];
+    for (int i = tid; i < n; i += nt) {
+        double acc = *(volatile const double*)&mine->vec[slot][0][i];
+        for (int r = 1; r < nr; ++r) acc += *(volatile const double*)&mine->vec[slot][r][i];
+        vec[i] = acc;
     }
     __syncthreads();
 }

@@ -1252,7 +1252,7 @@ __global__ void k_force_running(Scalars* sc) { sc->done = 0; sc->status = 0; }
 // ---- multilevel line preconditioner (kernels_ml.cuh) ----------------------------------------------------------
 static int ml_blocks(const pfem_ctx* ctx, const LineDom& d) {
     const int cap = ctx->sm_count * 2;   // one resident wave of 256-thread blocks, like k_line_I
-    const int na = ((d.nJ + PFEM_ML_C - 1) / PFEM_ML_C) * ((d.nK + PFEM_ML_C - 1) / PFEM_ML_C);
+    const int na = ((d.nJ + PFEM_ML_C - 1) / PFEM_ML_C) * ((d.nK + d.koff + PFEM_ML_C - 1) / PFEM_ML_C);
     if (na <= cap) return na;
     const int per = (na + cap - 1) / cap;   // every block the same number of aggregates (+-1)
     return (na + per - 1) / per;
@@ -1265,20 +1265,30 @@ static int ensure_ml(pfem_ctx* ctx) {
     if (line_seg(g) == 0) FAIL(PFEM_ERR_BAD_INPUT, "the multilevel preconditioner holds at most 512 nodes per vertical line (%d given)", g.nI);
     MLDev ml;
     memset(&ml, 0, sizeof ml);
-    ml.dom[0] = LineDom{g.nI, g.nJ, g.nK, g.sJ, g.sK};
+    // Slab mode: the aggregates of the 4x4 and 16x16 levels must not straddle slabs, so that the hierarchy is the one of the whole
+    // mesh cut into pieces (same aggregates, same line blocks) and only the top level — one column for the whole device — needs
+    // an exchange.  Every rank with an upper neighbour therefore owns a multiple of 16 planes; the aggregate rows are counted from
+    // 16 planes in front of the first owned plane (koff), which puts the halo planes into empty aggregates of their own.
+    const bool slab = ctx->nranks > 1;
+    const int koff = slab ? 16 - g.kown0 : 0;
+    if (slab && ctx->nb_hi.present && (g.kown1 - g.kown0) % 16 != 0)
+        FAIL(PFEM_ERR_BAD_INPUT, "slab mode: the multilevel preconditioner needs a multiple of 16 owned planes on every rank but the last (%d given)",
+             g.kown1 - g.kown0);
+    if (slab && g.sJ * 2 > PFEM_COMM_VEC) FAIL(PFEM_ERR_BAD_INPUT, "slab mode: vertical lines too long for the top-level exchange");
+    ml.dom[0] = LineDom{g.nI, g.nJ, g.nK, g.sJ, g.sK, g.kown0, g.kown1, koff};
     // aggregated levels (4x4, 16x16 lateral columns) as long as they hold more than one column, then the top level = one column
     int L = 0;
-    for (int nJ = g.nJ, nK = g.nK; L < PFEM_ML_MAXL - 1;) {
+    for (int nJ = g.nJ, nK = g.nK + koff; L < PFEM_ML_MAXL - 1;) {
         nJ = (nJ + PFEM_ML_C - 1) / PFEM_ML_C; nK = (nK + PFEM_ML_C - 1) / PFEM_ML_C;
         if (nJ == 1 && nK == 1) break;
         ++L;
-        ml.dom[L] = LineDom{g.nI, nJ, nK, g.sJ, g.sJ * nJ};
+        ml.dom[L] = LineDom{g.nI, nJ, nK, g.sJ, g.sJ * nJ, 0, nK, 0};
     }
     ml.nagg = L;
     ml.nlev = L + 1;
-    ml.dom[ml.nlev] = LineDom{g.nI, 1, 1, g.sJ, g.sJ};
+    ml.dom[ml.nlev] = LineDom{g.nI, 1, 1, g.sJ, g.sJ, 0, 1, 0};
     // set-up partial sums live on the level-1 aggregates whether or not level 1 is a level of its own
-    const int nJ1 = (g.nJ + PFEM_ML_C - 1) / PFEM_ML_C, nK1 = (g.nK + PFEM_ML_C - 1) / PFEM_ML_C;
+    const int nJ1 = (g.nJ + PFEM_ML_C - 1) / PFEM_ML_C, nK1 = (g.nK + koff + PFEM_ML_C - 1) / PFEM_ML_C;
     const idx_t slen = (idx_t)nJ1 * nK1 * g.sJ;
     TRY(dev_alloc(ctx, &ctx->mlS, (size_t)(2 * ml.nlev * slen), 0));
     for (int l = 1; l <= ml.nlev; ++l) {
@@ -1300,15 +1310,20 @@ static int ml_setup(pfem_ctx* ctx) {
     const Grid& g = ctx->g;
     const MLDev& ml = ctx->ml;
     const int L = ml.nlev;
-    const int nJ1 = (g.nJ + PFEM_ML_C - 1) / PFEM_ML_C, nK1 = (g.nK + PFEM_ML_C - 1) / PFEM_ML_C;
-    const LineDom d1{g.nI, nJ1, nK1, g.sJ, g.sJ * nJ1};
+    const int koff = ml.dom[0].koff;
+    const int nJ1 = (g.nJ + PFEM_ML_C - 1) / PFEM_ML_C, nK1 = (g.nK + koff + PFEM_ML_C - 1) / PFEM_ML_C;
+    const LineDom d1{g.nI, nJ1, nK1, g.sJ, g.sJ * nJ1, 0, nK1, 0};
     k_ml_rowsums<<<dim3((unsigned)((g.sJ + 31) / 32), nJ1, nK1), dim3(32, PFEM_ML_C, PFEM_ML_C), 0, ctx->stream>>>(
-        g, ctx->cl, ctx->cv, ctx->dinv, L, nJ1, ctx->mlS, ctx->ml_slen);
+        g, ctx->cl, ctx->cv, ctx->dinv, L, nJ1, ctx->mlS, ctx->ml_slen, koff);
     KCHECK(); LAUNCHED(1);
     for (int l = 2; l <= L; ++l) {
         const int f = (l == L) ? (1 << 30) : PFEM_ML_C;   // the top level gathers everything
         k_ml_gather<<<dim3((unsigned)((g.sJ + 127) / 128), ml.dom[l].nJ, ml.dom[l].nK), 128, 0, ctx->stream>>>(
             d1, ml.dom[l], f, ctx->mlS + (size_t)(2 * (l - 1)) * ctx->ml_slen, ctx->mlS + (size_t)(2 * (l - 1) + 1) * ctx->ml_slen, ml.ld[l], ml.ll[l]);
+        KCHECK(); LAUNCHED(1);
+    }
+    if (ctx->nranks > 1) {   // the top line is the 1-D problem of the whole device: its blocks are sums over the ranks
+        k_ml_top_allreduce<<<1, 256, 0, ctx->stream>>>(ml.ld[L], ml.ll[L], (int)g.sJ, ctx->d_sc);
         KCHECK(); LAUNCHED(1);
     }
     for (int l = 1; l <= L; ++l) {
@@ -1324,9 +1339,10 @@ static CoarseAdd ml_coarse_add(const pfem_ctx* ctx) {
     const MLDev& ml = ctx->ml;
     CoarseAdd ca;
     const double* zt = ml.z[ml.nlev];
-    if (ml.nagg == 0) ca = CoarseAdd{ml.zero, 1, 31, ml.zero, 1, 31, zt};                                   // top level only
-    else if (ml.nagg == 1) ca = CoarseAdd{ml.z[1], ml.dom[1].nJ, PFEM_ML_SHIFT, ml.zero, 1, 31, zt};
-    else ca = CoarseAdd{ml.z[1], ml.dom[1].nJ, PFEM_ML_SHIFT, ml.z[2], ml.dom[2].nJ, 2 * PFEM_ML_SHIFT, zt};
+    const int koff = ml.dom[0].koff;
+    if (ml.nagg == 0) ca = CoarseAdd{ml.zero, 1, 31, ml.zero, 1, 31, zt, koff};                                   // top level only
+    else if (ml.nagg == 1) ca = CoarseAdd{ml.z[1], ml.dom[1].nJ, PFEM_ML_SHIFT, ml.zero, 1, 31, zt, koff};
+    else ca = CoarseAdd{ml.z[1], ml.dom[1].nJ, PFEM_ML_SHIFT, ml.z[2], ml.dom[2].nJ, 2 * PFEM_ML_SHIFT, zt, koff};
     return ca;
 }
 
@@ -1404,8 +1420,12 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
         const bool mlp = ctx->precond == 2;
         if (mlp) launch_ml_chain(ctx, ctx->r, qq[parity], ctx->r, 0);
         else launch_line_solve(ctx, ctx->r, qq[parity], ctx->r, 0);
-        if (ev) cudaEventRecord(ev[1], ctx->stream);
         const PeerOut po = peer_out(ctx, 1 - parity);   // slab mode: p' of the boundary planes goes to the neighbours
+        if (mlp && ctx->nranks > 1) {   // z_0 + z_1 + z_2 of my boundary planes -> the neighbours' halo planes of z_0, then a rank barrier
+            k_ml_halo<<<dim3((unsigned)((g.nI + 127) / 128), g.nJ), 128, 0, ctx->stream>>>(g, ctx->lz, ml_coarse_add(ctx), po.z_lo, po.z_hi);
+            k_rank_barrier<<<1, 32, 0, ctx->stream>>>(ctx->d_sc, 0);
+        }
+        if (ev) cudaEventRecord(ev[1], ctx->stream);
         if (mlp) launch_fused_dispatch<3>(ctx->line_plan, g, parity, nullptr, qq[1 - parity], pp[1 - parity], ctx->x, ctx->d_sc, ctx->partials,
                                           po, ctx->stream, ml_coarse_add(ctx));
         else launch_fused_dispatch<2>(ctx->line_plan, g, parity, nullptr, qq[1 - parity], pp[1 - parity], ctx->x, ctx->d_sc, ctx->partials,
@@ -1458,7 +1478,8 @@ static int launch_iteration(pfem_ctx* ctx, int variant, int parity, cudaEvent_t*
 }
 
 static int kernels_per_iteration(const pfem_ctx* ctx, int variant) {
-    if (variant == 3 && ctx->precond == 2) return 2 + ctx->ml.nagg + ctx->surf_iter;   // level kernels (the top level rides on the last one) + k_fpcg
+    if (variant == 3 && ctx->precond == 2)   // level kernels (the top level rides on the last one) + k_fpcg (+ halo push and barrier in slab mode)
+        return 2 + ctx->ml.nagg + ctx->surf_iter + (ctx->nranks > 1 ? 2 : 0);
     return variant == 1 ? 3 : (variant == 3 ? (ctx->precond == 1 ? 2 + ctx->surf_iter : 1 + ctx->surf_iter) : 2);
 }  // variants 0 (TMA) and 2 (LDG tiled) fuse the p-update
 
@@ -1575,7 +1596,6 @@ static int check_opts(pfem_ctx* ctx, const pfem_opts* o) {
     if (o->maxit <= 0) FAIL(PFEM_ERR_BAD_INPUT, "maxit must be positive");
     if (!(o->lin_tol > 0.)) FAIL(PFEM_ERR_BAD_INPUT, "lin_tol must be positive");
     if (o->precond < 0 || o->precond > 2) FAIL(PFEM_ERR_BAD_INPUT, "preconditioner %d is not implemented (0 = Jacobi, 1 = line-Jacobi, 2 = multilevel line)", o->precond);
-    if (o->precond == 2 && ctx->nranks > 1) FAIL(PFEM_ERR_BAD_INPUT, "the multilevel preconditioner is not available in slab mode");
     if (o->precond >= 1 && o->variant != 3) FAIL(PFEM_ERR_BAD_INPUT, "the line preconditioner runs with kernel variant 3 only");
     if (o->precond >= 1 && ctx->nranks > 1 && ctx->g.vdim == 2)
         FAIL(PFEM_ERR_BAD_INPUT, "slab mode: the line preconditioner needs the vertical axis inside the slabs (a lateral major axis)");

@@ -1,0 +1,110 @@
+"""Worker of the multilevel-preconditioner slab test (one process per GPU, launched by torchrun from tests/test_slab.py):
+the additive multilevel line preconditioner ('mlj') in slab mode against the single-GPU solve.  With slab boundaries at multiples of
+16 planes the hierarchy is the one of the whole mesh (same aggregates, same line blocks, ONE top column for the whole device whose
+residual and blocks are summed over the ranks), so the iteration counts must agree with the single-GPU run, not just the result."""
+import os
+import pickle
+import sys
+
+import numpy as np
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from plask_b200 import configs as cf  # noqa: E402
+from plask_b200.solvers import Shockley3D, Static3D  # noqa: E402
+
+
+def allgather_bytes(b):
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, b)
+    return out
+
+
+def main():
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    import torch
+    local = rank % max(torch.cuda.device_count(), 1)
+
+    def run(cls, name, prob, slab, dev, loops, setup=None):
+        s = cls(name)
+        s.device = dev
+        s.problem = prob
+        s.slab = slab
+        s.iterative.preconditioner = "mlj"
+        s.iterative.maxerr = 1e-11
+        s.iterative.maxit = 50000
+        if setup:
+            setup(s)
+        s.compute(loops)
+        return s
+
+    # ---- Static3D, config B: 32 planes per rank but the last (which gets 37), vertical axis minor
+    n = (32 * world + 5, 20, 24)
+    p = cf.config_B(n)
+    q, own_lo, own_hi, _ = cf.slab_problem(p, rank, world, align=16)
+    slab = dict(rank=rank, nranks=world, own_lo=own_lo, own_hi=own_hi, allgather=allgather_bytes)
+    s = run(Static3D, f"mlslab{rank}", q, slab, local, 0)
+    parts = allgather_bytes((cf.slab_field_owned(q, s.outTemperature(), own_lo, own_hi), s.stats))
+    s.invalidate()
+    assert all(x[1]["lin_iters"] == parts[0][1]["lin_iters"] for x in parts)
+    if rank == 0:
+        T = np.concatenate([x[0] for x in parts], axis=0).ravel()
+        one = run(Static3D, "mlsingle", p, None, 0, 0)
+        d = float(np.abs(T - one.outTemperature()).max())
+        print(f"slab x{world} multilevel: PCG iterations {parts[0][1]['lin_iters']} (single GPU {one.stats['lin_iters']}), "
+              f"max|Tml_slab - Tml_single| = {d:.3e} K")
+        assert parts[0][1]["outer_loops"] == one.stats["outer_loops"]
+        assert abs(parts[0][1]["lin_iters"] - one.stats["lin_iters"]) <= 0.03 * one.stats["lin_iters"] + 3
+        assert d <= 1e-6
+        one.invalidate()
+    dist.barrier()
+
+    # ---- Shockley3D, config C (junction, contacts): lateral axis 0 cut, 16 planes on the first ranks
+    pc = cf.config_C((16 * world + 7, 22, 52), order="012")
+    qc, c_lo, c_hi, _ = cf.slab_problem(pc, rank, world, align=16)
+    slabc = dict(rank=rank, nranks=world, own_lo=c_lo, own_hi=c_hi, allgather=allgather_bytes)
+
+    def shockley_setup(prob):
+        def f(e):
+            e.beta, e.js, e.maxerr = prob.beta, prob.js, prob.maxerr
+        return f
+    e = run(Shockley3D, f"mlshock{rank}", qc, slabc, local, 5, shockley_setup(pc))
+    partsV = allgather_bytes((cf.slab_field_owned(qc, e.outVoltage(), c_lo, c_hi), e.stats))
+    e.invalidate()
+    if rank == 0:
+        V = np.concatenate([x[0] for x in partsV], axis=0).ravel()
+        onev = run(Shockley3D, "mlshock_single", pc, None, 0, 5, shockley_setup(pc))
+        dv = float(np.abs(V - onev.outVoltage()).max())
+        print(f"slab x{world} multilevel Shockley3D: PCG iterations {partsV[0][1]['lin_iters']} (single GPU {onev.stats['lin_iters']}), "
+              f"max|Vml_slab - Vml_single| = {dv:.3e} V")
+        assert abs(partsV[0][1]["lin_iters"] - onev.stats["lin_iters"]) <= 0.03 * onev.stats["lin_iters"] + 5
+        assert dv <= 1e-7
+        onev.invalidate()
+    dist.barrier()
+
+    # ---- a partition that is not aligned is refused with a clear message
+    qb, b_lo, b_hi, _ = cf.slab_problem(p, rank, world)          # 32 w + 5 planes split evenly: not a multiple of 16
+    if (b_hi - b_lo) % 16 != 0:
+        bad = Static3D(f"mlbad{rank}")
+        bad.device = local
+        bad.problem = qb
+        bad.slab = dict(rank=rank, nranks=world, own_lo=b_lo, own_hi=b_hi, allgather=allgather_bytes)
+        bad.iterative.preconditioner = "mlj"
+        failed = False
+        try:
+            bad.compute(1)
+        except Exception as err:       # rank world-1 has no upper neighbour and is not the one that refuses
+            failed = "multiple of 16" in str(err)
+        flags = allgather_bytes(failed)
+        assert any(flags[:-1]), flags
+        bad.invalidate()
+    if rank == 0:
+        print("slab multilevel ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

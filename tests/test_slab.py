@@ -9,9 +9,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = os.path.join(ROOT, "tests", "slab_worker.py")
 
 
-def _torchrun(nproc, port, *args, timeout=600):
+def _torchrun(nproc, port, *args, timeout=600, worker=WORKER):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), WORKER, *args]
+           "--master-port", str(port), worker, *args]
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
 
 
@@ -38,3 +38,14 @@ def test_slab_solve_two_gpus():
     assert "max|V_slab - V_single|" in r.stdout
     assert "max|V201_slab - V201_single|" in r.stdout
     assert "max|Td_slab - Td_single|" in r.stdout          # Dynamic3D in slab mode      # vertical-major mesh: the host cuts a lateral axis
+
+
+@pytest.mark.gpu
+def test_slab_multilevel_two_gpus():
+    """the multilevel preconditioner in slab mode = the single-GPU hierarchy (same iteration counts), Static3D and Shockley3D"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    r = _torchrun(2, 29557, timeout=900, worker=os.path.join(ROOT, "tests", "slab_ml_worker.py"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "max|Tml_slab - Tml_single|" in r.stdout and "max|Vml_slab - Vml_single|" in r.stdout and "slab multilevel ok" in r.stdout

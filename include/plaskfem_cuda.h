@@ -178,7 +178,10 @@ int pfem_set_junctions(pfem_ctx* ctx, uint32_t njunc, const pfem_junction* junc,
  * Per PCG iteration the boundary planes of r, q, p are written straight into the neighbours' halo planes by the
  * iteration kernel and the 7 CG scalars are exchanged once through peer inboxes (no separate collective launch);
  * all ranks obtain bit-identical scalars.  pfem_get_field returns the local field with up-to-date halo planes.
- * Implemented for pfem_solve_thermal and pfem_solve_linear (kernel variant 3). */
+ * Implemented for pfem_solve_thermal, pfem_solve_shockley, pfem_solve_dynamic and pfem_solve_linear (kernel variant 3) with all
+ * three preconditioners.  The multilevel preconditioner (precond = 2) asks for slab boundaries at multiples of 16 planes (every
+ * rank but the last owns a multiple of 16 planes): its lateral aggregates then coincide with those of the undivided mesh and the
+ * iteration counts are those of one GPU; only its top level (one vertical line for the whole device) is summed over the ranks. */
 size_t pfem_slab_blob_size(void);
 int pfem_slab_configure(pfem_ctx* ctx, int rank, int nranks, size_t own_lo, size_t own_hi);
 int pfem_slab_export(pfem_ctx* ctx, void* blob);
@@ -194,7 +197,7 @@ typedef struct {
                        * 2 = additive multilevel line preconditioner (kernels_ml.cuh): line blocks + the line blocks of the Galerkin
                        * operators on 4^l x 4^l lateral aggregates up to one column — the counterpart of the strength of the
                        * reference's default "ic" (iterative_matrix.hpp:73); needs PFEM_LAYOUT_VERTICAL_MINOR (or a mesh order whose
-                       * minor axis is vertical) and at most 512 nodes per vertical line */
+                       * minor axis is vertical) and at most 512 nodes per vertical line; slab mode: boundaries at multiples of 16 planes */
     double outer_tol; /* maxerr of the nonlinear loop: K (thermal) or % (electrical)        */
     int loops;        /* max nonlinear loops in this call, 0 = until converged              */
     int batch;        /* PCG iterations per captured CUDA graph launch (0 = default)        */

@@ -29,7 +29,7 @@ def main():
     ap.add_argument("--boundary", action="store_true")
     ap.add_argument("--lin-tol", type=float, default=1e-8)
     ap.add_argument("--meta-loops", type=int, default=100)
-    ap.add_argument("--precond", default="jac", help="jac | ljac (line-Jacobi along the vertical axis)")
+    ap.add_argument("--precond", default="jac", help="jac | ljac (line-Jacobi along the vertical axis) | mlj (multilevel line preconditioner)")
     ap.add_argument("--order", default="optimal")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -46,7 +46,7 @@ def main():
             return out
 
     def slab_of(n0):
-        lo, hi, own_lo, own_hi = cf.slab_local(n0, rank, world)
+        lo, hi, own_lo, own_hi = cf.slab_local(n0, rank, world, 16 if a.precond == "mlj" else 1)   # mlj: slab boundaries at multiples of 16 planes
         return (lo, hi), dict(rank=rank, nranks=world, own_lo=own_lo, own_hi=own_hi, allgather=allgather)
 
     def tune(s):

@@ -62,12 +62,20 @@ def main():
         p = cf.config_C(n, order=a.order)
         e = Shockley3D("C")
         tune(e)
-        e.problem = p
+        if world > 1:   # the host cuts a lateral axis (the junction and the vertical lines stay inside every slab)
+            axis = cf.slab_axis(p, need_vertical_inside=True)
+            q, own_lo, own_hi, _ = cf.slab_problem(p, rank, world, axis=axis, align=16 if a.precond == "mlj" else 1)
+            e.problem = q
+            e.slab = dict(rank=rank, nranks=world, own_lo=own_lo, own_hi=own_hi, allgather=allgather)
+            e.beta, e.js, e.maxerr = p.beta, p.js, p.maxerr
+            out["slab_axis"] = axis
+        else:
+            e.problem = p
         t1 = time.perf_counter()
         e.compute(0)
         t2 = time.perf_counter()
         st = e.stats
-        I = e.get_total_current()
+        I = e.get_total_current() if world == 1 else float("nan")
         out.update(mesh=n, dof=p.N, order=p.order, outer_loops=st["outer_loops"], pcg_iterations=st["lin_iters"],
                    device_ms=st["t_solve_ms"], wall_s=t2 - t1, setup_s=t1 - t0, err_percent=st["err"], lin_relres=st["lin_relres"],
                    max_j_kAcm2=st["maxval"], total_current_mA=I, dof_iter_per_s=p.N * st["lin_iters"] / (st["t_solve_ms"] * 1e-3))

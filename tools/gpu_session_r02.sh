@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/r02_gpu.txt 2>&1
-timeout 2400 python -m pytest tests/ -x -q -m gpu -p no:cacheprovider > gpurun_out/r02_pytest_gpu.log 2>&1; echo "pytest exit $?" | tee gpurun_out/r02_summary.txt
+timeout -s KILL 1500 python -m pytest tests/ -x -q -m gpu -p no:cacheprovider > gpurun_out/r02_pytest_gpu.log 2>&1; echo "pytest exit $?" | tee gpurun_out/r02_summary.txt
 tail -n 3 gpurun_out/r02_pytest_gpu.log
 timeout 900 python __graft_entry__.py smoke > gpurun_out/r02_smoke.log 2>&1; echo "smoke exit $?" | tee -a gpurun_out/r02_summary.txt
 tail -n 3 gpurun_out/r02_smoke.log
@@ -15,3 +15,8 @@ echo "ncu list exit $?" | tee -a gpurun_out/r02_summary.txt
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_fpcg' -s 40 -c 1 -f -o gpurun_out/r02_prof_fpcg \
    python tools/time_line.py 256 012 > gpurun_out/r02_ncu_fpcg.log 2>&1
 echo "ncu full exit $?" | tee -a gpurun_out/r02_summary.txt
+# Diffusion3D: timing over mesh sizes next to the reference's band-Cholesky loop on the CPU, and one ncu capture of the cooperative kernel
+timeout 600 python tools/time_diffusion.py > gpurun_out/r02_diffusion_timing.jsonl 2> gpurun_out/r02_diffusion_timing.err; echo "diffusion timing exit $?" | tee -a gpurun_out/r02_summary.txt
+timeout 600 ncu --set full --clock-control none --import-source on -k k_diff_compute -c 1 -f -o gpurun_out/r02_prof_diff \
+   python tools/time_diffusion.py --sizes 401 --repeat 1 --cpu-max 0 > gpurun_out/r02_ncu_diff.log 2>&1
+echo "ncu diffusion exit $?" | tee -a gpurun_out/r02_summary.txt

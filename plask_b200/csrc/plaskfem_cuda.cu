@@ -1271,10 +1271,14 @@ static int ensure_ml(pfem_ctx* ctx) {
     // 16 planes in front of the first owned plane (koff), which puts the halo planes into empty aggregates of their own.
     const bool slab = ctx->nranks > 1;
     const int koff = slab ? 16 - g.kown0 : 0;
-    if (slab && ctx->nb_hi.present && (g.kown1 - g.kown0) % 16 != 0)
-        FAIL(PFEM_ERR_BAD_INPUT, "slab mode: the multilevel preconditioner needs a multiple of 16 owned planes on every rank but the last (%d given)",
-             g.kown1 - g.kown0);
-    if (slab && g.sJ * 2 > PFEM_COMM_VEC) FAIL(PFEM_ERR_BAD_INPUT, "slab mode: vertical lines too long for the top-level exchange");
+    if (slab) {   // the refusal must be collective: a rank that went on alone would wait for the others in its first exchange
+        const int mine = (ctx->nb_hi.present && (g.kown1 - g.kown0) % 16 != 0) || g.sJ * 2 > PFEM_COMM_VEC;
+        int any = 0;
+        TRY(rank_barrier(ctx, mine, &any));
+        if (any)
+            FAIL(PFEM_ERR_BAD_INPUT, "slab mode: the multilevel preconditioner needs a multiple of 16 owned planes on every rank but the last "
+                 "(this rank: %d%s) and at most 512 nodes per vertical line", g.kown1 - g.kown0, mine ? ", not accepted" : "");
+    }
     ml.dom[0] = LineDom{g.nI, g.nJ, g.nK, g.sJ, g.sK, g.kown0, g.kown1, koff};
     // aggregated levels (4x4, 16x16 lateral columns) as long as they hold more than one column, then the top level = one column
     int L = 0;

@@ -46,6 +46,6 @@ def test_slab_multilevel_two_gpus():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
-    r = _torchrun(2, 29557, timeout=900, worker=os.path.join(ROOT, "tests", "slab_ml_worker.py"))
+    r = _torchrun(2, 29557, timeout=300, worker=os.path.join(ROOT, "tests", "slab_ml_worker.py"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "max|Tml_slab - Tml_single|" in r.stdout and "max|Vml_slab - Vml_single|" in r.stdout and "slab multilevel ok" in r.stdout

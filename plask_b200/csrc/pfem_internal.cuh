@@ -222,7 +222,9 @@ __device__ __forceinline__ void rank_allreduce(double (&v)[NV], Comm* cm, double
         const Inbox* mine = cm->inbox[me];
         const long long t0 = clock64();
         while (*(volatile const unsigned long long*)&mine->flag[slot][tid] != s + 1ull) {
-            if (clock64() - t0 > 20000000000ll) { cm->timeout = 1; break; }   // ~10 s
+            // ~10 s; once one exchange has given up every later one falls through at once, so that the call ends with
+            // PFEM_ERR_CUDA after seconds instead of 10 s per exchange of the remaining kernels
+            if (*(volatile const int*)&cm->timeout || clock64() - t0 > 20000000000ll) { cm->timeout = 1; break; }
         }
         __threadfence_system();
     }

@@ -16,7 +16,7 @@ struct pdiff_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
-    bool has_mesh = false, has_par = false, has_cur = false, assembled_for_hooks = false;
+    bool has_mesh = false, has_par = false, has_cur = false;
     int order = 0;
     size_t n0 = 0, n1 = 0, nn = 0, ne = 0;
     int guard = 0, grid = 0;
@@ -155,13 +155,13 @@ int need_tmp(pdiff_ctx* ctx, size_t bytes) {
     return PFEM_OK;
 }
 
-int plain_grid(const pdiff_ctx* c, size_t items) { return (int)std::min<size_t>((items + 127) / 128, 148 * 16); }
+int plain_grid(size_t items) { return (int)std::min<size_t>((items + 127) / 128, 148 * 16); }
 
 // Ke, F, M^-1 at the current U (the hooks; the compute kernel does the same inside its loop)
 int assemble_now(pdiff_ctx* ctx, int verbatim) {
     if (!ctx->has_mesh || !ctx->has_par || !ctx->has_cur) return fail(ctx, PFEM_ERR_STATE, "mesh, parameters and current must be set first");
-    k_diff_assemble<<<plain_grid(ctx, 12 * (size_t)ctx->P.NLp), 128, 0, ctx->stream>>>(ctx->P, verbatim, ctx->d_Fe);
-    k_diff_gather<<<plain_grid(ctx, ctx->P.NL), 128, 0, ctx->stream>>>(ctx->P, ctx->d_Fe);
+    k_diff_assemble<<<plain_grid(12 * (size_t)ctx->P.NLp), 128, 0, ctx->stream>>>(ctx->P, verbatim, ctx->d_Fe);
+    k_diff_gather<<<plain_grid(ctx->P.NL), 128, 0, ctx->stream>>>(ctx->P, ctx->d_Fe);
     ctx->launches += 2;
     PD_CUDA(cudaGetLastError());
     return PFEM_OK;
@@ -504,7 +504,7 @@ int pdiff_apply(pdiff_ctx* ctx, int verbatim, const double* v, double* y) {
     to_soa(ctx, v, soa);
     double *dv = ctx->d_tmp, *dy = dv + 3 * NLp;
     PD_CUDA(cudaMemcpyAsync(dv, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    k_diff_apply<<<plain_grid(ctx, ctx->P.NL), 128, 0, ctx->stream>>>(ctx->P, dv, dy);
+    k_diff_apply<<<plain_grid(ctx->P.NL), 128, 0, ctx->stream>>>(ctx->P, dv, dy);
     ctx->launches += 1;
     PD_CUDA(cudaGetLastError());
     PD_CUDA(cudaMemcpyAsync(soa.data(), dy, soa.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

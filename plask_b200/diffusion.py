@@ -287,10 +287,7 @@ class Diffusion3D:
             self.modesP[act] = power
         else:
             d.set_modes()
-        try:
-            st = d.compute(loops, self.maxerr, self.maxit, self.lin_tol, self.verbatim)
-        except L.ComputationError:
-            raise
+        st = d.compute(loops, self.maxerr, self.maxit, self.lin_tol, self.verbatim)
         if st["status"] == L.PFEM_NOT_CONVERGED and self.noconv == "error":
             raise L.ComputationError(f"{self.id}: linear solver did not converge in {self.maxit} iterations")
         self.stats = st

@@ -21,9 +21,45 @@ def allgather_bytes(b):
     return out
 
 
+def host_checks(rank, world):
+    """no GPU: the aligned partition covers the axis, every boundary is a multiple of 16 planes, the local problems are slices of
+    the global one (what the multilevel preconditioner relies on: no lateral aggregate straddles two slabs)"""
+    n = (32 * world + 5, 20, 24)
+    p = cf.config_B(n)
+    q, own_lo, own_hi, (lo, hi) = cf.slab_problem(p, rank, world, align=16)
+    ranges = allgather_bytes((lo, hi, own_lo, own_hi))
+    owned = [(l + a, l + b) for (l, h, a, b) in ranges]
+    assert owned[0][0] == 0 and owned[-1][1] == n[0]
+    assert all(owned[r][1] == owned[r + 1][0] for r in range(world - 1))
+    assert all(owned[r][1] % 16 == 0 for r in range(world - 1)), owned
+    assert own_lo == (1 if rank > 0 else 0) and (hi - lo) - own_hi == (1 if rank < world - 1 else 0)
+    eg = np.broadcast_to(p.elem_index_grid(), tuple(k - 1 for k in n))
+    leg = np.broadcast_to(q.elem_index_grid(), tuple(k - 1 for k in q.n))
+    assert np.array_equal(q.elem_mat[leg], p.elem_mat[eg][lo:hi - 1]) and np.array_equal(q.heat[leg], p.heat[eg][lo:hi - 1])
+    # aggregate rows as the library counts them: (k + koff) >> 2 with koff = 16 - own_lo; halo planes fall into rows of their own
+    koff = 16 - own_lo
+    rows_owned = {(k + koff) >> 2 for k in range(own_lo, own_hi)}
+    halos = [k for k in (own_lo - 1, own_hi) if 0 <= k < hi - lo]
+    assert all(((k + koff) >> 2) not in rows_owned for k in halos)
+    assert all(((k + koff) >> 4) not in {(j + koff) >> 4 for j in range(own_lo, own_hi)} for k in halos)
+    # Shockley problem cut along a lateral axis although its own order has the vertical axis major
+    pc = cf.config_C((16 * world + 7, 22, 52))
+    axis = cf.slab_axis(pc, need_vertical_inside=True)
+    assert axis in (0, 1)
+    qc, c_lo, c_hi, (clo, chi) = cf.slab_problem(pc, rank, world, axis=axis, align=16)
+    assert (clo + c_hi) % 16 == 0 or rank == world - 1
+    if rank == 0:
+        print("slab multilevel host logic ok")
+
+
 def main():
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
+    host_checks(rank, world)
+    if "--host-only" in sys.argv:
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     import torch
     local = rank % max(torch.cuda.device_count(), 1)
 

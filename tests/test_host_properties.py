@@ -58,3 +58,27 @@ def test_slab_local_nodes_is_the_restriction(nranks, extra, order, seed):
             if int(v) in owned_global:
                 seen[int(v)] += 1
     assert np.all(seen[nodes] == 1)           # every listed node is owned by exactly one rank
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.integers(min_value=1, max_value=8), st.integers(min_value=0, max_value=600), st.sampled_from([4, 16]))
+def test_aligned_slab_partition(nranks, extra, align):
+    """slab_range(align): what the multilevel preconditioner asks for — the boundaries between ranks are multiples of `align`
+    planes, the ranges cover the axis once, the blocks of `align` planes are balanced"""
+    nK = align * (nranks - 1) + 1 + extra     # enough planes for one block per rank
+    owned = [cf.slab_range(nK, r, nranks, align) for r in range(nranks)]
+    assert owned[0][0] == 0 and owned[-1][1] == nK
+    assert all(owned[r][1] == owned[r + 1][0] for r in range(nranks - 1))
+    assert all(owned[r][1] % align == 0 for r in range(nranks - 1))
+    assert all(b > a for a, b in owned)
+    blocks = [-(-(b - a) // align) for a, b in owned]
+    assert max(blocks) - min(blocks) <= 1
+    # aggregate rows of the library: no 4x4 / 16x16 aggregate row holds planes of two ranks
+    if align == 16:
+        for r in range(nranks):
+            lo, hi, own_lo, own_hi = cf.slab_local(nK, r, nranks, align)
+            koff = 16 - own_lo
+            for sh in (2, 4):
+                mine = {(k + koff) >> sh for k in range(own_lo, own_hi)}
+                halo = {(k + koff) >> sh for k in (own_lo - 1, own_hi) if 0 <= k < hi - lo}
+                assert not (mine & halo)

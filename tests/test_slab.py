@@ -22,6 +22,13 @@ def test_slab_host_logic_gloo(world):
     assert "slab host logic ok" in r.stdout
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_multilevel_host_logic_gloo(world):
+    r = _torchrun(world, 29546 + world, "--host-only", worker=os.path.join(ROOT, "tests", "slab_ml_worker.py"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "slab multilevel host logic ok" in r.stdout
+
+
 @pytest.mark.gpu
 def test_slab_solve_two_gpus():
     import torch

@@ -87,7 +87,8 @@ int pfem_set_mesh(pfem_ctx* ctx, const size_t n[3], const double* ax0, const dou
  * vector and the heat capacity is multiplied by w[i], i = index of the element along `axis` (n[axis] - 1 values, > 0; NULL
  * removes the weights); gradients (currents, fluxes, Joule heat) keep the geometric spacing.  This is what the cylindrical
  * 2-D solvers need — K_e and f_e carry the midpoint radius r of the element (therm2d.cpp:338-420, electr2d.cpp:219-230) — when
- * a 2-D mesh is handed over as a brick mesh of one element layer.  Not combinable with pfem_set_boundary. */
+ * a 2-D mesh is handed over as a brick mesh of one element layer.  Call it before pfem_set_boundary, which
+ * accepts weights only in its cylindrical 2-D mode (pfem_boundary::mode2d = 2). */
 int pfem_set_axis_weight(pfem_ctx* ctx, int axis, const double* w);
 
 /* Material id per element + per-id conductivity tables c_lat/c_vert[nmat][nT] sampled by the
@@ -126,15 +127,33 @@ int pfem_set_source(pfem_ctx* ctx, const double* heat_per_elem);
  * temperatures[0..7] (:265), and it keeps the convection matrix as written (:255: 0.125e-12, a QUARTER of the
  * consistent face mass matrix, so that the solution relaxes towards 4*ambient).  verbatim == 0 is the corrected
  * form: terms go to the nodes of the wall, radiation reads the wall node, consistent face mass matrix.
- * b == NULL (or no flags) removes all boundary terms. */
+ * b == NULL (or no flags) removes all boundary terms.
+ *
+ * mode2d != 0: the mesh is the one-layer embedding of a 2-D mesh (2 nodes along physical axis 0) and the
+ * conditions are those of ThermalFem2DSolver (therm2d.cpp: setBoundaries :138-172, Cartesian terms :225-265, cylindrical
+ * :371-413, mode2d = 2; the radius is physical axis 1).  An EDGE of a 2-D element carries a condition when both of its nodes
+ * have a value; flags and values are read from the nodes of plane 0 and the terms are added on both planes, scaled like the
+ * embedded operator.  The 2-D solver puts every term on the right node, so verbatim means something else here: the convection
+ * matrix terms are taken as written, WITHOUT the 1e-6 (um -> m) their load terms carry (:241,244 against :238) and,
+ * cylindrical, with the second factor r they pick up in A += r * k11 (:385-397 against :415-426) — the solution is then pinned
+ * to the ambient temperature; verbatim == 0 restores the unit factor and the single r.  mode2d = 2 is the one case that may be
+ * combined with pfem_set_axis_weight (set the weights first). */
 typedef struct {
     const uint8_t* has_flux;  const double* flux;                                     /* W/m^2            */
     const uint8_t* has_conv;  const double* conv_coeff;     const double* conv_ambient; /* W/(m^2 K), K    */
     const uint8_t* has_rad;   const double* rad_emissivity; const double* rad_ambient;  /* -, K            */
     int verbatim;
-    int reserved[3];
+    int mode2d;               /* 0 brick faces (therm3d.cpp), 1 Cartesian 2-D edges, 2 cylindrical 2-D edges (therm2d.cpp) */
+    int reserved[2];
 } pfem_boundary;
 int pfem_set_boundary(pfem_ctx* ctx, const pfem_boundary* b);
+
+/* Host-only view of what the 2-D mode adds (no device, no context): the edge terms of a 2-D mesh x[n1] (tran or r) by y[n2] (vert),
+ * node (i1, i2) -> i1 * n2 + i2, in the 2-D solver's own units (before the embedding scale): load[N] (heat flux + convection),
+ * radiation as load -= rad_coef[n] * (T[n]^4 - rad_amb4[n]), and the convection matrix K[N*N] (dense, row-major).  b->mode2d must
+ * be 1 or 2.  Lets the CPU test suite compare the flattening with the oracle's restatement of therm2d.cpp. */
+int pfem_edges2d_host(size_t n1, const double* x, size_t n2, const double* y, const pfem_boundary* b,
+                      double* load, double* rad_coef, double* rad_amb4, double* K);
 
 /* Unknown field (temperatures [K] / potential [V]): initial guess and warm start
  * (therm3d.cpp:79, electr3d.cpp:190; iterative_matrix.hpp:205-209). */

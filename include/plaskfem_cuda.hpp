@@ -349,9 +349,10 @@ class Context {
         check(pfem_set_materials(ctx_, ids.data(), t.nmat, t.T0, t.dT, t.nT, t.lat.data(), t.vert.data()));
     }
     void set_dirichlet(const Dirichlet& bc) { check(pfem_set_dirichlet(ctx_, bc.node.size(), bc.node.data(), bc.value.data())); }
-    // verbatim = true reproduces setBoundaries to the letter (local slots, quarter mass matrix; plaskfem_cuda.h)
+    // verbatim = true reproduces setBoundaries to the letter (local slots, quarter mass matrix; plaskfem_cuda.h); mode2d = 1 / 2: the
+    // edge conditions of ThermalFem2DSolver<Cartesian / Cylindrical> on the one-layer embedding (therm2d.cpp:138-172)
     void set_boundary(const NodeConditions<1>& heatflux, const NodeConditions<2>& convection, const NodeConditions<2>& radiation,
-                      bool verbatim = true) {
+                      bool verbatim = true, int mode2d = 0) {
         if (heatflux.empty() && convection.empty() && radiation.empty()) { check(pfem_set_boundary(ctx_, nullptr)); return; }
         pfem_boundary b;
         memset(&b, 0, sizeof b);
@@ -359,6 +360,7 @@ class Context {
         if (!convection.empty()) { b.has_conv = convection.has.data(); b.conv_coeff = convection.v[0].data(); b.conv_ambient = convection.v[1].data(); }
         if (!radiation.empty()) { b.has_rad = radiation.has.data(); b.rad_emissivity = radiation.v[0].data(); b.rad_ambient = radiation.v[1].data(); }
         b.verbatim = verbatim ? 1 : 0;
+        b.mode2d = mode2d;
         check(pfem_set_boundary(ctx_, &b));
     }
     void set_source(const double* heat_per_elem) { check(pfem_set_source(ctx_, heat_per_elem)); }

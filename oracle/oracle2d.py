@@ -1,6 +1,7 @@
 """CPU restatement of PLaSK's TWO-DIMENSIONAL FEM solvers — TEST INFRASTRUCTURE, never imported by plask_b200/ (SURVEY.md 8f-4).
 
     Static2D / StaticCyl     thermal.static      solvers/thermal/static/therm2d.cpp
+    Dynamic2D / DynamicCyl   thermal.dynamic     solvers/thermal/dynamic/femT2d.cpp (corrected time loop, see Dynamic2DOracle)
     Shockley2D / ShockleyCyl electrical.shockley solvers/electrical/shockley/electr2d.cpp + beta.hpp
 
 It is written independently of the 3-D code paths (oracle.py, fem3d_oracle.c, the CUDA library): 4-node rectangles assembled
@@ -93,9 +94,82 @@ def solve_dirichlet(A, B, nodes, values):
     return X
 
 
+SB = 5.670373e-8          # W/(m^2 K^4), plask/phys/constants.hpp:41
+
+
+def _first_wins(N, conds, nval):
+    """BoundaryConditionsWithMesh::getValue (plask/mesh/boundary_conditions.hpp:182-186): the first condition naming a node"""
+    has = np.zeros(N, dtype=bool)
+    vals = np.zeros((nval, N))
+    for cond in conds:
+        for n in np.asarray(cond[0], dtype=np.int64):
+            if not has[n]:
+                has[n] = True
+                vals[:, n] = cond[1:1 + nval]
+    return has, vals
+
+
+def edge_terms(mesh, T, heatflux=(), convection=(), radiation=(), cyl=False, verbatim=True):
+    """The boundary conditions of the 2nd / 3rd kind and radiation of ThermalFem2DSolver::setMatrix, element by element and side by
+    side like setBoundaries (therm2d.cpp:138-172) with the lambdas of :225-265 (Cartesian) and :371-413 (cylindrical).
+    Returns (K as coo triplets added to the element matrices, F added to the load vector).
+
+    verbatim: the convection matrix terms exactly as the reference adds them — (c1 + c2) len / 6 and / 12 WITHOUT the 1e-6 that
+    turns the edge length into metres (the load terms carry it: 0.5e-6 len c T_amb), and in the cylindrical solver added to
+    k11 .. k41 BEFORE `A(i, j) += r * kij` (:415-426), i.e. multiplied by the midpoint radius a second time.
+    verbatim = False: with the 1e-6 and the single radial factor."""
+    m = mesh
+    n1 = m.n[1]
+    hf, (qf,) = _first_wins(m.N, heatflux, 1)
+    hc, (cc, ca) = _first_wins(m.N, convection, 2)
+    hr, (re, ra) = _first_wins(m.N, radiation, 2)
+    rows, cols, data = [], [], []
+    F = np.zeros(m.N)
+    kunit = 1. if verbatim else 1e-6
+    for e in np.nonzero((hf | hc | hr)[m.ll] | (hf | hc | hr)[m.lr] | (hf | hc | hr)[m.ur] | (hf | hc | hr)[m.ul])[0]:
+        i1, i2, i3, i4 = int(m.ll[e]), int(m.lr[e]), int(m.ur[e]), int(m.ul[e])
+        w, h, r = float(m.w[e]), float(m.h[e]), float(m.rmid[e])
+        lo0, up0 = r - 0.5 * w, r + 0.5 * w                                     # elem.getLower0(), getUpper0()
+        sides = [("BOTTOM", i1, i2, w), ("RIGHT", i2, i3, h), ("TOP", i3, i4, w), ("LEFT", i4, i1, h)]
+
+        def radial(side, ia, ib, ln, offdiag=False):
+            if not cyl:
+                return 1.
+            if side == "LEFT":
+                return lo0
+            if side == "RIGHT":
+                return up0
+            if offdiag:
+                return r
+            return r + (-ln / 6. if ia < ib else ln / 6.)
+
+        kfac = kunit * (r if (cyl and verbatim) else 1.)
+        for side, ia, ib, ln in sides:
+            if hf[ia] and hf[ib]:
+                for a, b_ in ((ia, ib), (ib, ia)):
+                    F[a] += -0.5e-6 * ln * qf[a] * radial(side, a, b_, ln)
+            if hc[ia] and hc[ib]:
+                for a, b_ in ((ia, ib), (ib, ia)):
+                    if cyl:
+                        F[a] += 0.125e-6 * ln * (cc[a] + cc[b_]) * (ca[a] + ca[b_]) * radial(side, a, b_, ln)
+                    else:
+                        F[a] += 0.5e-6 * ln * cc[a] * ca[a]
+                    rows.append(a); cols.append(a); data.append(kfac * (cc[a] + cc[b_]) * ln / 6. * radial(side, a, b_, ln))
+                koff = kfac * (cc[ia] + cc[ib]) * ln / 12. * radial(side, ia, ib, ln, offdiag=True)
+                rows += [ia, ib]; cols += [ib, ia]; data += [koff, koff]
+            if hr[ia] and hr[ib]:
+                for a, b_ in ((ia, ib), (ib, ia)):
+                    F[a] += -0.5e-6 * ln * re[a] * SB * (T[a] ** 4 - ra[a] ** 4) * radial(side, a, b_, ln)
+    return (np.asarray(rows, dtype=np.int64), np.asarray(cols, dtype=np.int64), np.asarray(data, dtype=np.float64)), F
+
+
 class Static2DOracle:
     """ThermalFem2DSolver<Cartesian / Cylindrical> (therm2d.cpp): nonlinear loop of compute (:438-492) with boundary conditions of
-    the first kind and the volumetric heat source."""
+    the first kind, the volumetric heat source and — heatflux / convection / radiation lists of (nodes, values...) — the
+    conditions of the 2nd / 3rd kind and radiation (edge_terms)."""
+
+    heatflux = convection = radiation = ()
+    verbatim = True
 
     def __init__(self, x, y, elem_mat, T0, dT, tab_lat, tab_vert, bc_nodes, bc_values, heat=None, inittemp=300., maxerr=0.05, cyl=False):
         self.mesh = Mesh2D(x, y)
@@ -125,6 +199,11 @@ class Static2DOracle:
             ky = kv * m.w / m.h
             f = 0.25e-12 * m.w * m.h * self.heat                                                   # :210
             A, B = assemble(m, kx, ky, f, self.cyl)
+            if self.heatflux or self.convection or self.radiation:
+                import scipy.sparse as sp
+                (kr, kc, kd), F = edge_terms(m, self.temperatures, self.heatflux, self.convection, self.radiation, self.cyl, self.verbatim)
+                A = A + sp.coo_matrix((kd, (kr, kc)), shape=(m.N, m.N)).tocsr()
+                B = B + F
             Tn = solve_dirichlet(A, B, self.bc_nodes, self.bc_values)
             err = float(np.abs(Tn - self.temperatures).max())
             self.temperatures = Tn
@@ -143,6 +222,92 @@ class Static2DOracle:
         gx = 0.5e6 * (-T[m.ll] + T[m.lr] - T[m.ul] + T[m.ur]) / m.w
         gy = 0.5e6 * (-T[m.ll] - T[m.lr] + T[m.ul] + T[m.ur]) / m.h
         return np.stack([-kl * gx, -kv * gy], axis=1)
+
+
+class Dynamic2DOracle:
+    """DynamicThermalFem2DSolver<Cartesian / Cylindrical> (solvers/thermal/dynamic/femT2d.cpp) as a CORRECTED specification.
+
+    setMatrix (:127-255 Cartesian, :258-388 cylindrical) to the letter: A = methodparam K + C, B = -(1 - methodparam) K + C with the
+    4-node rectangle K (:176-181; the cylindrical solver multiplies kx, ky, c and f by the midpoint radius, :307-313), the element
+    capacity c = cp dens 0.25e-12 w h / timestep / 1e-9 (:164), lumped (diag c, :186-189) or consistent (4/9, 2/9, 1/9 c,
+    :212-222), F = 0.25e-12 w h heat (:170), conductivities and capacities at the mean of the four node temperatures (:157).
+    The time loop (:415-445) eliminates the Dirichlet rows in A and F only (:247) while B.mult keeps them (:425), so a fixed node
+    would receive value + (B T)_r; here, like the 3-D oracle (oracle.Dynamic3DOracle, which documents the same defect of
+    femT3d.cpp):  A T' = B T + F on the free rows, T' = value on the Dirichlet rows.  cprho: [nmat][nT] table of cp(T) dens(T)."""
+
+    def __init__(self, x, y, elem_mat, T0, dT, tab_lat, tab_vert, cprho, bc_nodes, bc_values, heat=None, inittemp=300., cyl=False,
+                 timestep=0.1, methodparam=0.5, lumping=True, rebuildfreq=0):
+        self.mesh = Mesh2D(x, y)
+        self.elem_mat = np.asarray(elem_mat, dtype=np.int64)
+        self.T0, self.dT, self.tab_lat, self.tab_vert = T0, dT, np.asarray(tab_lat), np.asarray(tab_vert)
+        self.cprho = np.asarray(cprho, dtype=np.float64)
+        self.bc_nodes, self.bc_values = np.asarray(bc_nodes, dtype=np.int64), np.asarray(bc_values, dtype=np.float64)
+        self.heat = np.zeros(self.mesh.E) if heat is None else np.asarray(heat, dtype=np.float64)
+        self.cyl = cyl
+        self.timestep, self.methodparam, self.lumping, self.rebuildfreq = float(timestep), float(methodparam), bool(lumping), int(rebuildfreq)
+        self.temperatures = np.full(self.mesh.N, float(inittemp))
+        self.elapstime = 0.
+        self.physical_time = 0.
+        self.maxT_log = []
+
+    def set_matrix(self):
+        import scipy.sparse as sp
+        m, T = self.mesh, self.temperatures
+        temp = 0.25 * (T[m.ll] + T[m.lr] + T[m.ul] + T[m.ur])
+        kl = table_lookup(self.tab_lat, self.elem_mat, self.T0, self.dT, temp)
+        kv = table_lookup(self.tab_vert, self.elem_mat, self.T0, self.dT, temp)
+        c = table_lookup(self.cprho, self.elem_mat, self.T0, self.dT, temp) * 0.25 * 1e-12 * m.h * m.w / self.timestep / 1e-9
+        if self.cyl:
+            c = c * m.rmid
+        K, F = assemble(m, kl * m.h / m.w, kv * m.w / m.h, 0.25e-12 * m.w * m.h * self.heat, self.cyl)
+        nd = [m.ll, m.lr, m.ur, m.ul]
+        rows, cols, data = [], [], []
+        for a in range(4):
+            for b in range(4):
+                if self.lumping:
+                    wgt = 1. if a == b else 0.
+                else:
+                    wgt = 4. / 9. if a == b else (1. / 9. if (a + b) % 2 == 0 else 2. / 9.)     # opposite corners 1/9, edges 2/9
+                if wgt:
+                    rows.append(nd[a]); cols.append(nd[b]); data.append(wgt * c)
+        Cm = sp.coo_matrix((np.concatenate(data), (np.concatenate(rows), np.concatenate(cols))), shape=(m.N, m.N)).tocsr()
+        th = self.methodparam
+        return (th * K + Cm).tocsr(), (-(1. - th) * K + Cm).tocsr(), F
+
+    def _factor(self):
+        import scipy.sparse.linalg as spl
+        A, B, F = self.set_matrix()
+        fixed = np.zeros(self.mesh.N, dtype=bool)
+        fixed[self.bc_nodes] = True
+        xD = np.zeros(self.mesh.N)
+        xD[self.bc_nodes] = self.bc_values
+        free = ~fixed
+        return dict(solve=spl.factorized(A[free][:, free].tocsc()), B=B, F=F, free=free, fixed=fixed, xD=xD,
+                    lift=A[free][:, fixed] @ xD[fixed])
+
+    def compute(self, time):
+        """compute(time), femT2d.cpp:390-452"""
+        sysm = self._factor()
+        r = self.rebuildfreq
+        tend = time + self.timestep / 2.
+        t = 0.
+        while t < tend:
+            if self.rebuildfreq and r == 0:
+                sysm = self._factor()
+                r = self.rebuildfreq
+            rhs = sysm["B"] @ self.temperatures + sysm["F"]
+            Tn = np.empty_like(self.temperatures)
+            Tn[sysm["free"]] = sysm["solve"](rhs[sysm["free"]] - sysm["lift"])
+            Tn[sysm["fixed"]] = sysm["xD"][sysm["fixed"]]
+            self.temperatures = Tn
+            self.maxT_log.append(float(Tn.max()))
+            r -= 1
+            self.elapstime += self.timestep
+            self.physical_time += self.timestep
+            t += self.timestep
+        self.elapstime -= self.timestep
+        self.maxT = float(self.temperatures.max())
+        return 0.
 
 
 class Shockley2DOracle:

@@ -34,7 +34,7 @@ class Boundary(C.Structure):
     _fields_ = [("has_flux", C.POINTER(C.c_uint8)), ("flux", c_dp),
                 ("has_conv", C.POINTER(C.c_uint8)), ("conv_coeff", c_dp), ("conv_ambient", c_dp),
                 ("has_rad", C.POINTER(C.c_uint8)), ("rad_emissivity", c_dp), ("rad_ambient", c_dp),
-                ("verbatim", C.c_int), ("reserved", C.c_int * 3)]
+                ("verbatim", C.c_int), ("mode2d", C.c_int), ("reserved", C.c_int * 2)]
 
 
 class Opts(C.Structure):
@@ -95,6 +95,7 @@ SYMBOLS = {
     "pfem_set_dirichlet": (C.c_int, [_vp, c_sz, _szp, c_dp]),
     "pfem_set_source": (C.c_int, [_vp, c_dp]),
     "pfem_set_boundary": (C.c_int, [_vp, C.POINTER(Boundary)]),
+    "pfem_edges2d_host": (C.c_int, [c_sz, c_dp, c_sz, c_dp, C.POINTER(Boundary), c_dp, c_dp, c_dp, c_dp]),
     "pfem_set_field": (C.c_int, [_vp, c_dp]),
     "pfem_fill_field": (C.c_int, [_vp, C.c_double]),
     "pfem_set_elem_temperature": (C.c_int, [_vp, c_dp, C.c_double]),

@@ -739,6 +739,87 @@ static void surf_release(pfem_ctx* ctx) {
     if (ctx->graph) { cudaGraphExecDestroy(ctx->graph); ctx->graph = nullptr; }
 }
 
+// Boundary conditions of the 2nd / 3rd kind and radiation of the 2-D thermal solvers (ThermalFem2DSolver::setMatrix, therm2d.cpp) in the
+// reference's own 2-D units: edge by edge like setBoundaries (:138-172) with the terms of :225-265 (Cartesian) and :371-413
+// (cylindrical).  An edge carries a condition when both of its nodes have a value.  Unlike the 3-D solver the 2-D one accumulates
+// into the right nodes (F1..F4 by name) and radiation reads the wall node itself; what b->verbatim reproduces here is (i) the convection
+// MATRIX terms missing the 1e-6 (um -> m) that the load terms carry (:241,244 against :238) and (ii), cylindrical, their second
+// factor r: they are added to k11.. before A(..) += r * k11 (:385-397, :415-426).  Pure host code (pfem_edges2d_host exposes it to
+// the CPU tests).  Node (i1, i2) -> i1 * s1 + i2 * s2 (flags and values are read there), element (e1, e2) -> e1 * es1 + e2 * es2.
+struct Edge2DTerms {
+    std::vector<idx_t> lnode, rnode, krow, kcol;
+    std::vector<double> lval, rcoef, ramb4, kval;    // load; radiation: load = -rcoef (T^4 - ramb4); matrix triplets (both orientations)
+};
+static void edges2d(idx_t n1, idx_t n2, const double* X, const double* Y, idx_t s1, idx_t s2, const uint8_t* excluded, idx_t es1, idx_t es2,
+                    const pfem_boundary* b, bool cyl, Edge2DTerms& t) {
+    const double SB = 5.670373e-8;   // plask/phys/constants.hpp:41
+    const bool quirk = b->verbatim != 0;
+    const double kunit = quirk ? 1. : 1e-6;
+    auto flags = [&](idx_t n) {
+        return (uint8_t)((b->has_flux && b->has_flux[n] ? 1 : 0) | (b->has_conv && b->has_conv[n] ? 2 : 0) | (b->has_rad && b->has_rad[n] ? 4 : 0));
+    };
+    for (idx_t e1 = 0; e1 + 1 < n1; ++e1)
+        for (idx_t e2 = 0; e2 + 1 < n2; ++e2) {
+            if (excluded && excluded[(size_t)(es1 * e1 + es2 * e2)]) continue;                       // :196: elements of the masked mesh only
+            const idx_t c4[4] = {e1 * s1 + e2 * s2, (e1 + 1) * s1 + e2 * s2,                         // lower left, lower right,
+                                 (e1 + 1) * s1 + (e2 + 1) * s2, e1 * s1 + (e2 + 1) * s2};            // upper right, upper left
+            uint8_t mk4[4], any = 0;
+            for (int l = 0; l < 4; ++l) { mk4[l] = flags(c4[l]); any |= mk4[l]; }
+            if (!any) continue;
+            const double width = X[e1 + 1] - X[e1], height = Y[e2 + 1] - Y[e2], rmid = 0.5 * (X[e1] + X[e1 + 1]);
+            const double kr = (cyl && quirk) ? rmid : 1.;
+            for (int kind = 0; kind < 3; ++kind) {           // heat flux, convection, radiation: the order of :225-265
+                const uint8_t bit = (uint8_t)(1 << kind);
+                for (int side = 0; side < 4; ++side) {       // bottom (1,2), right (2,3), top (3,4), left (4,1): :153-172
+                    const int la = side, lb = (side + 1) & 3;
+                    if (!(mk4[la] & mk4[lb] & bit)) continue;
+                    const double len = (side & 1) ? height : width;
+                    for (int pass = 0; pass < 2; ++pass) {   // the terms of node a with partner b, then of b with a
+                        const int l1 = pass ? lb : la, l2 = pass ? la : lb;
+                        const idx_t na = c4[l1], nb = c4[l2];
+                        // radial factors: the radius of a vertical edge; on a horizontal one r -+ len/6 for the node at the lower /
+                        // higher radius (:376-378), r for the off-diagonal entry (:397)
+                        double rf = 1., rf_off = 1.;
+                        if (cyl) {
+                            const bool inner = (l1 == 0 || l1 == 3);
+                            rf = side == 3 ? X[e1] : side == 1 ? X[e1 + 1] : rmid + (inner ? -len / 6. : len / 6.);
+                            rf_off = side == 3 ? X[e1] : side == 1 ? X[e1 + 1] : rmid;
+                        }
+                        if (kind == 0) { t.lnode.push_back(na); t.lval.push_back(-0.5e-6 * len * b->flux[na] * rf); }
+                        else if (kind == 2) {
+                            double a = b->rad_ambient[na]; a = a * a;
+                            t.rnode.push_back(na); t.rcoef.push_back(0.5e-6 * len * b->rad_emissivity[na] * SB * rf); t.ramb4.push_back(a * a);
+                        } else {
+                            const double csum = b->conv_coeff[na] + b->conv_coeff[nb];
+                            t.lnode.push_back(na);
+                            t.lval.push_back(cyl ? 0.125e-6 * len * csum * (b->conv_ambient[na] + b->conv_ambient[nb]) * rf
+                                                 : 0.5e-6 * len * b->conv_coeff[na] * b->conv_ambient[na]);
+                            t.krow.push_back(na); t.kcol.push_back(na); t.kval.push_back(kunit * kr * csum * len / 6. * rf);
+                            t.krow.push_back(na); t.kcol.push_back(nb); t.kval.push_back(kunit * kr * csum * len / 12. * rf_off);
+                        }
+                    }
+                }
+            }
+        }
+}
+
+extern "C" int pfem_edges2d_host(size_t n1, const double* x, size_t n2, const double* y, const pfem_boundary* b,
+                                 double* load, double* rad_coef, double* rad_amb4, double* K) {
+    if (!x || !y || !b || !load || !rad_coef || !rad_amb4 || !K || n1 < 2 || n2 < 2) return PFEM_ERR_BAD_INPUT;
+    if (b->mode2d != 1 && b->mode2d != 2) return PFEM_ERR_BAD_INPUT;
+    if ((b->has_flux && !b->flux) || (b->has_conv && (!b->conv_coeff || !b->conv_ambient)) || (b->has_rad && (!b->rad_emissivity || !b->rad_ambient)))
+        return PFEM_ERR_BAD_INPUT;
+    const size_t N = n1 * n2;
+    Edge2DTerms t;
+    edges2d((idx_t)n1, (idx_t)n2, x, y, (idx_t)n2, 1, nullptr, 0, 0, b, b->mode2d == 2, t);
+    for (size_t k = 0; k < N; ++k) load[k] = rad_coef[k] = rad_amb4[k] = 0.;
+    for (size_t k = 0; k < N * N; ++k) K[k] = 0.;
+    for (size_t k = 0; k < t.lnode.size(); ++k) load[t.lnode[k]] += t.lval[k];
+    for (size_t k = 0; k < t.rnode.size(); ++k) { rad_coef[t.rnode[k]] += t.rcoef[k]; rad_amb4[t.rnode[k]] = t.ramb4[k]; }
+    for (size_t k = 0; k < t.krow.size(); ++k) K[(size_t)t.krow[k] * N + (size_t)t.kcol[k]] += t.kval[k];
+    return PFEM_OK;
+}
+
 extern "C" int pfem_set_boundary(pfem_ctx* ctx, const pfem_boundary* b) {
     NEED_MESH();
     const Grid& g = ctx->g;
@@ -748,8 +829,14 @@ extern "C" int pfem_set_boundary(pfem_ctx* ctx, const pfem_boundary* b) {
     if ((b->has_flux && !b->flux) || (b->has_conv && (!b->conv_coeff || !b->conv_ambient)) ||
         (b->has_rad && (!b->rad_emissivity || !b->rad_ambient)))
         FAIL(PFEM_ERR_BAD_INPUT, "boundary condition flags without values");
-    if (ctx->weighted) FAIL(PFEM_ERR_BAD_INPUT, "element weights (pfem_set_axis_weight) and boundary conditions of the 2nd / 3rd kind cannot be combined");
-    if (b->verbatim && b->has_rad && ctx->nranks > 1)
+    const int mode2d = b->mode2d;
+    if (mode2d < 0 || mode2d > 2) FAIL(PFEM_ERR_BAD_INPUT, "pfem_boundary::mode2d must be 0 (brick), 1 (Cartesian 2-D) or 2 (cylindrical 2-D)");
+    if (ctx->weighted && mode2d != 2)
+        FAIL(PFEM_ERR_BAD_INPUT, "element weights (pfem_set_axis_weight) combine with boundary conditions of the 2nd / 3rd kind only in the cylindrical 2-D mode (mode2d = 2)");
+    if (mode2d && (g.pn[0] != 2 || ctx->nranks > 1))
+        FAIL(PFEM_ERR_BAD_INPUT, "mode2d needs the one-layer embedding of a 2-D mesh (2 nodes along physical axis 0) on a single device");
+    if (mode2d == 2 && !(ctx->hax[1].front() >= 0.)) FAIL(PFEM_ERR_BAD_INPUT, "mode2d = 2: negative radius on physical axis 1");
+    if (b->verbatim && b->has_rad && ctx->nranks > 1 && !mode2d)
         FAIL(PFEM_ERR_BAD_INPUT, "slab mode: verbatim radiation reads temperatures[0..7] of the whole mesh (therm3d.cpp:265); use the corrected form");
     // dense (ABI) and lattice strides of the physical axes; element extents along them
     idx_t dps[3], cnt[3] = {g.nI, g.nJ, g.nK};
@@ -768,6 +855,20 @@ extern "C" int pfem_set_boundary(pfem_ctx* ctx, const pfem_boundary* b) {
     static const int walls[6][4] = {{0, 1, 2, 3}, {4, 5, 6, 7}, {0, 2, 4, 6}, {1, 3, 5, 7}, {0, 1, 4, 5}, {2, 3, 6, 7}};
     const double SB = 5.670373e-8;   // plask/phys/constants.hpp:41
     const int quirk = b->verbatim ? 1 : 0;
+    if (mode2d) {
+        // the brick operator and load restricted to one of the two node planes are  emb = d/2 * 1e-6  times their 2-D counterparts
+        // (INTEGRATION.md 9): the edge terms of the 2-D solver go to both planes, scaled by emb
+        const double emb = 0.5e-6 * (ctx->hax[0][1] - ctx->hax[0][0]);
+        Edge2DTerms t;
+        edges2d(g.pn[1], g.pn[2], ctx->hax[1].data(), ctx->hax[2].data(), dps[1], dps[2],
+                ctx->h_excluded.empty() ? nullptr : ctx->h_excluded.data(), g.es[1], g.es[2], b, mode2d == 2, t);
+        for (int plane = 0; plane < 2; ++plane) {
+            const idx_t o = plane * dps[0];
+            for (size_t k = 0; k < t.lnode.size(); ++k) loads.push_back({lattice(t.lnode[k] + o), emb * t.lval[k]});
+            for (size_t k = 0; k < t.rnode.size(); ++k) rads.push_back({lattice(t.rnode[k] + o), lattice(t.rnode[k] + o), emb * t.rcoef[k], t.ramb4[k]});
+            for (size_t k = 0; k < t.krow.size(); ++k) kts.push_back({lattice(t.krow[k] + o), lattice(t.kcol[k] + o), emb * t.kval[k]});
+        }
+    } else
     for (idx_t ek = 0; ek < cnt[2] - 1; ++ek)
         for (idx_t ej = 0; ej < cnt[1] - 1; ++ej)
             for (idx_t ei = 0; ei < cnt[0] - 1; ++ei) {

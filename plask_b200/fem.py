@@ -93,10 +93,11 @@ class DeviceFem:
             assert h.size == self.E
             self._ck(self.lib.pfem_set_source(self.ctx, _dp(h)))
 
-    def set_boundary(self, heatflux=(), convection=(), radiation=(), verbatim=True):
+    def set_boundary(self, heatflux=(), convection=(), radiation=(), verbatim=True, mode2d=0):
         """heatflux_boundary / convection_boundary / radiation_boundary (therm3d.hpp:79-82) as lists of conditions in
         definition order: (nodes, q) / (nodes, coeff, ambient) / (nodes, emissivity, ambient).  Densified like
-        BoundaryConditionsWithMesh::getValue: the FIRST condition naming a node wins."""
+        BoundaryConditionsWithMesh::getValue: the FIRST condition naming a node wins.  mode2d = 1 / 2: the edge conditions of the 2-D
+        solvers (therm2d.cpp, Cartesian / cylindrical) on the one-layer embedding; nodes are those of plane 0."""
         def dense(conds, nval):
             if not conds:
                 return None, [None] * nval
@@ -122,6 +123,7 @@ class DeviceFem:
         b.has_conv, b.conv_coeff, b.conv_ambient = u8(hc), dp(cc), dp(ca)
         b.has_rad, b.rad_emissivity, b.rad_ambient = u8(hr), dp(re), dp(ra)
         b.verbatim = int(bool(verbatim))
+        b.mode2d = int(mode2d)
         self._ck(self.lib.pfem_set_boundary(self.ctx, C.byref(b)))
 
     def set_field(self, x):

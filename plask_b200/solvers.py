@@ -183,9 +183,12 @@ class Static3D(_FemSolver):
         f.set_materials(self._elem_materials(), p.T0, p.dT, p.tab_lat, p.tab_vert)
         f.set_field(float(self.inittemp))               # temperatures.reset(size, inittemp), :79
         f.set_dirichlet(*self._dirichlet())
-        f.set_boundary(self.heatflux_boundary, self.convection_boundary, self.radiation_boundary, self.boundary_verbatim)
+        self._set_boundary(f)
         self.loopno = 0
         self.initialized = True
+
+    def _set_boundary(self, f):
+        f.set_boundary(self.heatflux_boundary, self.convection_boundary, self.radiation_boundary, self.boundary_verbatim)
 
     def compute(self, loops=0):
         """ThermalFem3DSolver::compute (therm3d.cpp:281-340); returns the max loop error."""

@@ -1,6 +1,6 @@
 """The two-dimensional solvers on the brick kernels: thermal.static.Static2D / StaticCyl
-(solvers/thermal/static/therm2d.cpp) and electrical.shockley.Shockley2D / ShockleyCyl (solvers/electrical/shockley/electr2d.cpp)
-with algorithm='cuda'.
+(solvers/thermal/static/therm2d.cpp), thermal.dynamic.Dynamic2D / DynamicCyl (solvers/thermal/dynamic/femT2d.cpp) and
+electrical.shockley.Shockley2D / ShockleyCyl (solvers/electrical/shockley/electr2d.cpp) with algorithm='cuda'.
 
 A rectangular 2-D mesh (x = tran or r, y = vert) is handed to the library as a brick mesh with ONE element layer along a dummy
 longitudinal axis and z-invariant data.  For a z-invariant field the brick operator of the layer (thickness d) reduces on each of
@@ -12,16 +12,19 @@ midpoint radius r (therm2d.cpp:353,412-426, electr2d.cpp:219-230): pfem_set_axis
 fluxes and Joule heat are element gradients and come out identical (the longitudinal component is zero); the integrals
 (total current, heat, energy, capacitance) use the 2-D formulas with the extrusion length or 2 pi r.
 
-Scope: boundary conditions of the first kind and the volumetric heat source (what the BASELINE-style configurations use).
-The 2-D conditions of the 2nd / 3rd kind and radiation are not mapped: therm2d.cpp:236-246 adds the convection matrix terms
-without the 1e-6 (um -> m) factor its load terms carry, which no brick-face term reproduces."""
+Boundary conditions of the 2nd / 3rd kind and radiation (therm2d.cpp:138-172, :225-265 Cartesian, :371-413 cylindrical) live on
+element EDGES of the 2-D mesh; brick faces do not reproduce them (the cylindrical terms carry r -+ len/6 per node, the
+convection matrix terms lack the 1e-6 of the load terms), so the library flattens them itself in its 2-D mode
+(pfem_boundary::mode2d), plane by plane with the same d/2 * 1e-6 scale: heatflux_boundary / convection_boundary /
+radiation_boundary of Static2D / StaticCyl take 2-D node lists; boundary_verbatim keeps the reference's convection matrix as
+written (no 1e-6, a second factor r in the cylindrical solver), False applies the unit factor and the single r."""
 from dataclasses import dataclass, field
 
 import numpy as np
 
 from . import _lib as L
 from .configs import Problem
-from .solvers import Shockley3D, Static3D
+from .solvers import Dynamic3D, Shockley3D, Static3D
 
 
 @dataclass
@@ -51,6 +54,7 @@ class Problem2D:
     pcond: float = 5.
     ncond: float = 50.
     start_cond: tuple = (0., 5.)
+    tab_cprho: np.ndarray = None   # [nmat][nT] cp(T) * dens(T), J/(m^3 K) (Dynamic2D / DynamicCyl)
     meta: dict = field(default_factory=dict)
 
     @property
@@ -78,6 +82,7 @@ def embed(p2, thickness=1.):
     p.elem_junc = None if p2.elem_junc is None else np.asarray(p2.elem_junc, dtype=np.uint32)
     p.elem_role = None if p2.elem_role is None else np.asarray(p2.elem_role, dtype=np.uint8)
     p.noheat = None if p2.noheat is None else np.asarray(p2.noheat, dtype=np.uint8)
+    p.tab_cprho = p2.tab_cprho
     for k in ("beta", "js", "pcond", "ncond", "start_cond"):
         setattr(p, k, getattr(p2, k))
     p.meta = dict(p2.meta)
@@ -133,6 +138,14 @@ class _Embedded2D:
 class Static2D(_Embedded2D, Static3D):
     """thermal.static.Static2D with algorithm='cuda' (therm2d.cpp, Geometry2DCartesian)"""
 
+    def _set_boundary(self, f):
+        pass                          # after the element weights, in the library's 2-D mode: initialize below
+
+    def initialize(self):
+        super().initialize()          # mesh, materials, Dirichlet, then the radial weights
+        self._fem.set_boundary(self.heatflux_boundary, self.convection_boundary, self.radiation_boundary, self.boundary_verbatim,
+                               mode2d=2 if self.cyl else 1)
+
     def outTemperature(self, mesh=None):
         if mesh is not None:
             raise L.BadInput(f"{self.id}: interpolation onto a foreign 2-D mesh is left to the plugin's own interpolation")
@@ -151,6 +164,28 @@ class Static2D(_Embedded2D, Static3D):
 
 class StaticCyl(Static2D):
     """thermal.static.StaticCyl (therm2d.cpp, Geometry2DCylindrical): x is the radius"""
+    cyl = True
+
+
+class Dynamic2D(_Embedded2D, Dynamic3D):
+    """thermal.dynamic.Dynamic2D with algorithm='cuda' (femT2d.cpp, Geometry2DCartesian): the element capacity
+    cp dens 0.25e-12 w h / timestep / 1e-9 (:164), lumped or consistent (4/9, 2/9, 1/9: the rows of M (x) M (x) M_z of the brick sum
+    to exactly that over the dummy axis), is the brick capacity of the layer times the same d/2 * 1e-6 as K and F; the time loop
+    (:415-445) is the one of femT3d.cpp — pfem_solve_dynamic, corrected theta scheme."""
+
+    def outTemperature(self, mesh=None):
+        if mesh is not None:
+            raise L.BadInput(f"{self.id}: interpolation onto a foreign 2-D mesh is left to the plugin's own interpolation")
+        if not self.initialized:
+            return np.full(self._p2.N, float(self.inittemp))
+        return self._plane(Dynamic3D.outTemperature(self))
+
+    def outHeatFlux(self):
+        return Dynamic3D.outHeatFlux(self)[:, 1:3].copy()
+
+
+class DynamicCyl(Dynamic2D):
+    """thermal.dynamic.DynamicCyl (femT2d.cpp:258-388): kx, ky, c and f carry the midpoint radius"""
     cyl = True
 
 

@@ -301,6 +301,15 @@ def oracle_static2d(p2, **kw):
                                    heat=p2.heat, inittemp=p2.inittemp, maxerr=p2.maxerr, cyl=p2.cyl, **kw)
 
 
+def oracle_dynamic2d(p2, **kw):
+    """Dynamic2DOracle (corrected femT2d.cpp); cp * dens from the problem or the config tables of the thermal ids"""
+    from oracle import oracle2d
+    cprho = p2.tab_cprho if p2.tab_cprho is not None else cf.capacity_tables(p2.T0, p2.dT, p2.tab_lat.shape[1])[:p2.tab_lat.shape[0]]
+    kw.setdefault("inittemp", p2.inittemp)
+    return oracle2d.Dynamic2DOracle(p2.x, p2.y, p2.elem_mat, p2.T0, p2.dT, p2.tab_lat, p2.tab_vert, cprho, p2.bc_nodes, p2.bc_values,
+                                    heat=p2.heat, cyl=p2.cyl, **kw)
+
+
 def thermal2d_problem(n=(33, 41), cyl=False, seed=3):
     """layered GaAs / AlGaAs / Cu block with k(T) tables (the thermal ids of configs.thermal_tables), a hot disc / stripe near the
     axis, 300 K on the bottom edge; graded mesh in both directions"""

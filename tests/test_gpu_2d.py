@@ -5,9 +5,9 @@ against the independent two-dimensional oracle (oracle/oracle2d.py) and the refe
 import numpy as np
 import pytest
 
-from helpers import oracle_shockley2d, oracle_static2d, shockley2d_reference_problem, thermal2d_problem
+from helpers import oracle_dynamic2d, oracle_shockley2d, oracle_static2d, shockley2d_reference_problem, thermal2d_problem
 from plask_b200 import _lib as L
-from plask_b200.solvers2d import Shockley2D, ShockleyCyl, Static2D, StaticCyl
+from plask_b200.solvers2d import Dynamic2D, DynamicCyl, Shockley2D, ShockleyCyl, Static2D, StaticCyl
 
 pytestmark = pytest.mark.gpu
 
@@ -57,6 +57,84 @@ def test_static2d_vs_oracle(cyl, precond, variant):
     F = s.outHeatFlux()
     Fo = o.heat_fluxes()
     assert np.abs(F - Fo).max() <= 1e-6 * np.abs(Fo).max()
+    s.invalidate()
+
+
+def boundary_conditions_2d(p2):
+    """heat flux into the top edge over the hot region, convection on the outer (right) edge and on the rest of the top, radiation
+    towards a hot ambient on the top: node-wise conditions, the corner node shared by two of them (the first definition wins)"""
+    n0, n1 = p2.n
+    ng = np.arange(n0 * n1).reshape(n0, n1)
+    top, right = ng[:, n1 - 1], ng[n0 - 1, :]
+    hot = top[:n0 // 3 + 1]
+    return dict(heatflux=[(hot, -2.0e8)], convection=[(right[4:], 2.0e6, 320.), (top[n0 // 3:], 6.0e5, 295.)],
+                radiation=[(top, 0.8, 2500.)])
+
+
+@pytest.mark.parametrize("cyl", [False, True])
+@pytest.mark.parametrize("verbatim,precond", [(False, "jac"), (False, "ljac"), (False, "mlj"), (True, "jac"), (True, "ljac")])
+def test_static2d_boundary_conditions_vs_oracle(cyl, verbatim, precond):
+    """therm2d.cpp:138-172, :225-265 (Cartesian), :371-413 (cylindrical) through pfem_boundary::mode2d against the 2-D oracle;
+    verbatim = the convection matrix as the reference writes it (no 1e-6, second factor r), corrected = with them"""
+    p2 = thermal2d_problem(cyl=cyl)
+    conds = boundary_conditions_2d(p2)
+    o = oracle_static2d(p2)
+    o.heatflux, o.convection, o.radiation, o.verbatim = conds["heatflux"], conds["convection"], conds["radiation"], verbatim
+    o.compute(0)
+    plain = oracle_static2d(p2)
+    plain.compute(0)
+    assert np.abs(o.temperatures - plain.temperatures).max() > 1.           # the conditions matter
+    s = thermal(p2, precond)
+    s.heatflux_boundary, s.convection_boundary, s.radiation_boundary = conds["heatflux"], conds["convection"], conds["radiation"]
+    s.boundary_verbatim = verbatim
+    s.compute(0)
+    T = s.outTemperature()
+    assert s.stats["outer_loops"] == len(o.history)
+    assert np.abs(T - o.temperatures).max() <= 1e-3
+    assert np.abs(T - o.temperatures).max() <= 1e-5
+    full = s._fem.get_field()
+    assert np.abs(full[:p2.N] - full[p2.N:]).max() <= 1e-6
+    s.invalidate()
+
+
+def test_static2d_boundary_mode_needs_the_embedding():
+    from helpers import face_nodes
+    from plask_b200 import configs
+    from plask_b200.fem import Fem
+    p = configs.config_B((6, 6, 8))
+    f = Fem()
+    f.set_mesh(p.axes, p.strides)
+    with pytest.raises(L.BadInput):
+        f.set_boundary([], [(face_nodes(p, 2, -1), 1e4, 300.)], [], False, mode2d=1)
+    f.close()
+
+
+@pytest.mark.parametrize("cyl", [False, True])
+@pytest.mark.parametrize("precond,variant,lumping", [("jac", 3, True), ("ljac", 3, True), ("jac", 1, True), ("jac", 1, False)])
+def test_dynamic2d_vs_oracle(cyl, precond, variant, lumping):
+    """femT2d.cpp through the one-layer embedding (pfem_solve_dynamic) against the 2-D oracle: k(T), cp(T) rebuilt every 3 steps,
+    two calls of compute continue one trajectory"""
+    p2 = thermal2d_problem((21, 26), cyl=cyl)
+    o = oracle_dynamic2d(p2, timestep=0.5, methodparam=0.5, lumping=lumping, rebuildfreq=3)
+    o.compute(3.)
+    o.compute(2.)
+    s = (DynamicCyl if cyl else Dynamic2D)("dyn2d")
+    s.problem = p2
+    s.variant = variant
+    s.iterative.preconditioner = precond
+    s.iterative.maxerr = 1e-12
+    s.iterative.maxit = 100000
+    s.timestep, s.methodparam, s.lumping, s.rebuildfreq = 0.5, 0.5, lumping, 3
+    s.compute(3.)
+    s.compute(2.)
+    T = s.outTemperature()
+    assert o.temperatures.max() - 300. > 1.
+    assert s.time == pytest.approx(o.elapstime)
+    assert np.abs(T - o.temperatures).max() <= 1e-6
+    assert abs(s.maxT - o.maxT) <= 1e-6
+    full = s._fem.get_field()
+    assert np.abs(full[:p2.N] - full[p2.N:]).max() <= 1e-6
+    assert s.outHeatFlux().shape == (p2.E, 2)
     s.invalidate()
 
 

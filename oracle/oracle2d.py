@@ -471,3 +471,61 @@ class Shockley2DOracle:
         assert len(vals) == 2
         U = float(vals[1] - vals[0])
         return 2e12 * self.get_total_energy() / (U * U)
+
+
+def interp_bilinear(xs, ys, v, xq, yq):
+    """interpolateLinear on a rectangular 2-D mesh (plask/mesh/rectangular2d.hpp: points outside are clamped to the edge):
+    v[len(xs) * len(ys)] in the numbering i0 * n1 + i1 -> values on the product grid xq x yq, same numbering"""
+    xs, ys, xq, yq = (np.asarray(a, dtype=np.float64) for a in (xs, ys, xq, yq))
+    v = np.asarray(v, dtype=np.float64).reshape(len(xs), len(ys))
+
+    def axis(a, q):
+        if len(a) == 1:
+            return np.zeros(len(q), dtype=np.int64), np.zeros(len(q), dtype=np.int64), np.zeros(len(q))
+        q = np.clip(q, a[0], a[-1])
+        hi = np.clip(np.searchsorted(a, q, side="right"), 1, len(a) - 1)
+        lo = hi - 1
+        return lo, hi, (q - a[lo]) / (a[hi] - a[lo])
+    i0, i1, fx = axis(xs, xq)
+    j0, j1, fy = axis(ys, yq)
+    fx, fy = fx[:, None], fy[None, :]
+    out = ((1. - fx) * (1. - fy) * v[i0][:, j0] + fx * (1. - fy) * v[i1][:, j0] +
+           (1. - fx) * fy * v[i0][:, j1] + fx * fy * v[i1][:, j1])
+    return out.ravel()
+
+
+class ThermoElectric2DOracle:
+    """meta.shockley.ThermoElectric2D / ThermoElectricCyl (solvers/meta/shockley/thermoelectric.py:187-211) over Static2DOracle and
+    Shockley2DOracle: electrical.inTemperature = thermal.outTemperature at the electrical element midpoints (electr2d.cpp:330-335),
+    thermal.inHeat = electrical.outHeat — element-mesh data interpolated at the thermal element midpoints, 0 outside the extent of
+    the electrical mesh (getHeatDensities, electr2d.cpp:604-618)."""
+
+    def __init__(self, thermal, electrical, tfreq=6):
+        self.thermal, self.electrical, self.tfreq = thermal, electrical, tfreq
+        self.history = []
+
+    def exchange_temperature(self):
+        t, e = self.thermal.mesh, self.electrical.mesh
+        mid = lambda a: 0.5 * (a[1:] + a[:-1])
+        self.electrical.Te = interp_bilinear(t.x, t.y, self.thermal.temperatures, mid(e.x), mid(e.y))
+
+    def exchange_heat(self):
+        t, e = self.thermal.mesh, self.electrical.mesh
+        mid = lambda a: 0.5 * (a[1:] + a[:-1])
+        xq, yq = mid(t.x), mid(t.y)
+        heat = interp_bilinear(mid(e.x), mid(e.y), self.electrical.heat_densities(), xq, yq)
+        inside = ((xq >= e.x[0]) & (xq <= e.x[-1]))[:, None] & ((yq >= e.y[0]) & (yq <= e.y[-1]))[None, :]
+        self.thermal.heat = np.where(inside.ravel(), heat, 0.)
+
+    def compute(self, max_meta_loops=100):
+        t, e = self.thermal, self.electrical
+        verr, terr = 2. * e.maxerr, 2. * t.maxerr
+        n = 0
+        while (terr > t.maxerr or verr > e.maxerr) and n < max_meta_loops:
+            self.exchange_temperature()
+            verr = e.compute(self.tfreq)
+            self.exchange_heat()
+            terr = t.compute(1)
+            n += 1
+            self.history.append(dict(verr=verr, terr=terr, maxT=t.maxT, current=e.get_total_current()))
+        return n

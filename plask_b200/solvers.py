@@ -541,10 +541,12 @@ class ThermoElectric3D:
             terr = thermal.compute(1)
     """
 
+    thermal_solver, electrical_solver = Static3D, Shockley3D
+
     def __init__(self, name=""):
         self.id = name
-        self.thermal = Static3D(name + "-thermal")
-        self.electrical = Shockley3D(name + "-electrical")
+        self.thermal = self.thermal_solver(name + "-thermal")
+        self.electrical = self.electrical_solver(name + "-electrical")
         self.tfreq = 6                                   # thermoelectric.py:57
         self.thermal.inHeat = self.electrical
         self.electrical.inTemperature = self.thermal

@@ -24,7 +24,7 @@ import numpy as np
 
 from . import _lib as L
 from .configs import Problem
-from .solvers import Dynamic3D, Shockley3D, Static3D
+from .solvers import Dynamic3D, Shockley3D, Static3D, ThermoElectric3D
 
 
 @dataclass
@@ -244,3 +244,15 @@ class Shockley2D(_Embedded2D, Shockley3D):
 class ShockleyCyl(Shockley2D):
     """electrical.shockley.ShockleyCyl (electr2d.cpp, Geometry2DCylindrical): x is the radius"""
     cyl = True
+
+
+class ThermoElectric2D(ThermoElectric3D):
+    """meta.shockley.ThermoElectric2D (solvers/meta/shockley/thermoelectric.py:187-211 with Static2D + Shockley2D): the loop and the
+    device-resident field exchange of ThermoElectric3D — the embedded meshes share the dummy axis, so pfem_transfer_temperature /
+    pfem_transfer_heat interpolate bilinearly in (x, y) exactly like getTemperatures / getHeatDensity on 2-D meshes."""
+    thermal_solver, electrical_solver = Static2D, Shockley2D
+
+
+class ThermoElectricCyl(ThermoElectric3D):
+    """meta.shockley.ThermoElectricCyl: StaticCyl + ShockleyCyl"""
+    thermal_solver, electrical_solver = StaticCyl, ShockleyCyl

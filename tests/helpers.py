@@ -328,3 +328,39 @@ def thermal2d_problem(n=(33, 41), cyl=False, seed=3):
     p = Problem2D("thermal2d", "thermal", x, y, mat.ravel(), T0, dT, lat, vert, ng[:, 0].astype(np.uintp), np.full(n[0], 300.),
                   heat=heat.ravel(), cyl=cyl)
     return p
+
+
+def thermoelectric2d_pair(cyl=False, nx=19, thermal_shape=None, voltage=2.2):
+    """A small mesa diode for the 2-D meta loop (ThermoElectric2D / ThermoElectricCyl): n-GaAs substrate 2 um, junction 0.02 um (two
+    element rows), p-GaAs 1 um, contact on the top over x < 4 um, bottom grounded and held at 300 K.  sigma(T) and k(T) tabulated
+    250..600 K, so that the exchanged temperatures matter.  thermal_shape = (n0, n1): the thermal solver on its own, coarser mesh
+    that extends 1 um deeper (a heat-spreader the electrical mesh does not have: no Joule heat there)."""
+    from plask_b200.solvers2d import Problem2D
+    x = cf.graded_axis(nx, 0.25, 1.2)
+    x = x - x[0]
+    y = np.concatenate([np.linspace(0., 2., 9), [2.01, 2.02], 2.02 + np.linspace(0., 1., 7)[1:]])
+    T0, dT, nT = 250., 0.5, 701
+    Tg = T0 + dT * np.arange(nT)
+    sig = np.stack([5.0e3 * (300. / Tg), np.full(nT, 1.0), 8.0e2 * (300. / Tg) ** 1.5])
+    ym = 0.5 * (y[1:] + y[:-1])
+    row_mat = np.where(ym < 2., 0, np.where(ym < 2.02, 1, 2)).astype(np.uint32)
+    mat = np.tile(row_mat, len(x) - 1)
+    n0, n1 = len(x), len(y)
+    ng = np.arange(n0 * n1).reshape(n0, n1)
+    top = ng[x <= 4.0 + 1e-9, -1]
+    bot = ng[:, 0]
+    pe = Problem2D("mesa-electrical", "shockley", x, y, mat, T0, dT, sig, sig.copy(),
+                   np.concatenate([top, bot]).astype(np.uintp), np.concatenate([np.full(top.size, voltage), np.zeros(bot.size)]), cyl=cyl)
+    pe.elem_junc = (mat == 1).astype(np.uint32)
+    pe.beta, pe.js, pe.maxerr = 11., 1., 0.05
+    if thermal_shape is None:
+        xt, yt = x, y
+    else:
+        xt = np.linspace(0., x[-1], thermal_shape[0])
+        yt = np.concatenate([[-1.0, -0.5], np.linspace(0., y[-1], thermal_shape[1] - 2)])
+    k = np.stack([45. * (300. / Tg) ** 1.28])
+    nt0, nt1 = len(xt), len(yt)
+    ngt = np.arange(nt0 * nt1).reshape(nt0, nt1)
+    pt = Problem2D("mesa-thermal", "thermal", xt, yt, np.zeros((nt0 - 1) * (nt1 - 1), dtype=np.uint32), T0, dT, k, k.copy(),
+                   ngt[:, 0].astype(np.uintp), np.full(nt0, 300.), heat=None, cyl=cyl)
+    return pt, pe

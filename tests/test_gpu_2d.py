@@ -5,9 +5,11 @@ against the independent two-dimensional oracle (oracle/oracle2d.py) and the refe
 import numpy as np
 import pytest
 
-from helpers import oracle_dynamic2d, oracle_shockley2d, oracle_static2d, shockley2d_reference_problem, thermal2d_problem
+from helpers import (oracle_dynamic2d, oracle_shockley2d, oracle_static2d, shockley2d_reference_problem, thermal2d_problem,
+                     thermoelectric2d_pair)
 from plask_b200 import _lib as L
-from plask_b200.solvers2d import Dynamic2D, DynamicCyl, Shockley2D, ShockleyCyl, Static2D, StaticCyl
+from plask_b200.solvers2d import (Dynamic2D, DynamicCyl, Shockley2D, ShockleyCyl, Static2D, StaticCyl, ThermoElectric2D,
+                                  ThermoElectricCyl)
 
 pytestmark = pytest.mark.gpu
 
@@ -203,3 +205,33 @@ def test_axis_weight_rejects_bad_input_and_boundary_terms():
     s._fem.set_axis_weight(1, None)          # weights removed: boundary terms are accepted again
     s._fem.set_boundary([], [], [], False)
     s.invalidate()
+
+
+@pytest.mark.parametrize("cyl", [False, True])
+@pytest.mark.parametrize("thermal_shape", [None, (12, 14)])
+def test_thermoelectric2d_meta_loop_vs_oracles(cyl, thermal_shape):
+    """meta.shockley.ThermoElectric2D / ThermoElectricCyl (thermoelectric.py:187-211): sigma(T), k(T) and a temperature-dependent
+    junction beta(T), the fields exchanged on the device — same mesh, and a coarser thermal mesh that reaches below the electrical one"""
+    from oracle import oracle2d
+    pt, pe = thermoelectric2d_pair(cyl, thermal_shape=thermal_shape)
+    beta = lambda T: 11. * 300. / T
+    te = (ThermoElectricCyl if cyl else ThermoElectric2D)("te2d")
+    te.thermal.problem, te.electrical.problem = pt, pe
+    te.tfreq = 4
+    for s in (te.thermal, te.electrical):
+        s.iterative.maxerr, s.iterative.maxit = 1e-13, 200000
+    te.electrical.beta, te.electrical.js, te.electrical.maxerr = beta, pe.js, pe.maxerr
+    te.thermal.maxerr = pt.maxerr
+    n = te.compute(max_meta_loops=5)
+    o = oracle2d.ThermoElectric2DOracle(oracle_static2d(pt), oracle_shockley2d(pe, beta=beta), tfreq=4)
+    no = o.compute(max_meta_loops=5)
+    assert n == no == 5
+    T, V = te.thermal.outTemperature(), te.electrical.outVoltage()
+    assert o.thermal.maxT > 310.
+    assert np.abs(T - o.thermal.temperatures).max() <= 1e-3
+    assert np.abs(V - o.electrical.potentials).max() <= 1e-6
+    assert te.get_total_current() == pytest.approx(o.electrical.get_total_current(), rel=1e-6)
+    for h, g in zip(te.history, o.history):
+        assert h["terr"] == pytest.approx(g["terr"], abs=1e-3)
+        assert h["verr"] == pytest.approx(g["verr"], rel=1e-3, abs=1e-6)
+    te.invalidate()

@@ -102,9 +102,9 @@ def test_static2d_boundary_conditions_vs_oracle(cyl, verbatim, precond):
 def test_static2d_boundary_mode_needs_the_embedding():
     from helpers import face_nodes
     from plask_b200 import configs
-    from plask_b200.fem import Fem
+    from plask_b200.fem import DeviceFem
     p = configs.config_B((6, 6, 8))
-    f = Fem()
+    f = DeviceFem(0)
     f.set_mesh(p.axes, p.strides)
     with pytest.raises(L.BadInput):
         f.set_boundary([], [(face_nodes(p, 2, -1), 1e4, 300.)], [], False, mode2d=1)

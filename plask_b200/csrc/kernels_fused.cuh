@@ -44,7 +44,9 @@
 #define PFEM_X 45   // experiment mask of k_fpcg: 1 = phase-1 loads hoisted (-1.7 %), 2 = x fetched two planes ahead in registers (+1.5 %: off),
                     // 4 = vertical stiffness per element (-0.5 %), 8 = x of the own tile through the TMA stage instead of a global load (-3 %),
                     // 32 = isotropic coefficient layer from per-thread constants (-0.4 ... -1.0 % inside the power-capped bench);
-                    // tried and dropped: a branch-free phase 2 that guards only the stores (+1.1 %)
+                    // tried and dropped: a branch-free phase 2 that guards only the stores (+1.1 %); TMA L2 prefetch
+                    // (cp.async.bulk.prefetch.tensor) of the boxes 1 / 2 / 4 steps beyond the shared-memory ring: 0.227 -> 0.295 / 0.299 / 0.318 ms
+                    // per iteration in the graph (the prefetches queue in front of the next step's real loads; profiles/r02_prefetch_ab.md)
 #endif
 
 namespace pfem {

@@ -112,7 +112,7 @@ template <int SEG>
 __global__ void __launch_bounds__(256)
 k_line_I(const Grid g, const double* __restrict__ r_in, const double* __restrict__ q_in, const double* __restrict__ ll,
          const double* __restrict__ ld, double* __restrict__ r_out, double* __restrict__ z_out, Scalars* sc, double* partials,
-         const int mode, const PeerOut po) {
+         const int mode, const PeerOut po, const int pf) {
     constexpr int ROW = 32 * SEG, ROWP = ROW + ROW / SEG;   // one pad per segment: conflict-free segment reads
     __shared__ double sh[32 * 3];
     __shared__ int sh_flag;
@@ -147,6 +147,14 @@ k_line_I(const Grid g, const double* __restrict__ r_in, const double* __restrict
                     *reinterpret_cast<double2*>(r_out + base + i) = vr[c];
                 }
             }
+        }
+        if (pf && row + pf * nwarps < rows) {   // the row this warp solves next (pf = 1; 2 = the one after): into L2 while this one is solved
+            const idx_t rn = row + pf * nwarps;
+            const idx_t bn = g.sJ * (idx_t)(rn % g.nJ) + g.sK * (idx_t)(g.kown0 + rn / g.nJ);
+            prefetch_row_l2(r_in + bn, lane, (int)g.sJ);
+            prefetch_row_l2(ll + bn, lane, (int)g.sJ);
+            prefetch_row_l2(ld + bn, lane, (int)g.sJ);
+            if (mode == 0) prefetch_row_l2(q_in + bn, lane, (int)g.sJ);
         }
         // transposition into the segment layout, one array at a time through the padded row buffer
 #pragma unroll

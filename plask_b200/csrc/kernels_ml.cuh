@@ -20,8 +20,8 @@
 //   k_line_ml<FINE>   r' = r - alpha q, z_0 = T_0^-1 r', r_1 = P_1^T r'       (one block per 4x4 aggregate: the restriction
 //                                                                              is a fixed-order sum in shared memory)
 //   k_line_ml (x L)   z_l = T_l^-1 r_l, r_{l+1} = sum of 4x4 level-l lines, rho += r_l.z_l; the last one finalises beta / stop
-//   k_ml_down         z_1 += sum_{l>=2} z_l(parent)                            (levels >= 1 hold 1/16, 1/256 ... of the nodes)
-//   k_fpcg<MODE 2>    p' = mask (z_0 + z_1(parent)) + beta p, x' = x + alpha p, q' = M A p'  (one extra L2-resident gather)
+//   k_fpcg<MODE 3>    p' = mask (z_0 + z_1(parent) + z_2(parent) + z_top) + beta p, x' = x + alpha p, q' = M A p'  (the coarse
+//                     values are gathered by the operator kernel itself, L2-resident; there is no separate prolongation kernel)
 #pragma once
 #include "pfem_internal.cuh"
 
@@ -282,7 +282,7 @@ template <int SEG, bool FINE>
 __global__ void __launch_bounds__(256)
 k_line_ml(const LineDom d, const double* __restrict__ r_in, const double* __restrict__ q_in, const double* __restrict__ ll,
           const double* __restrict__ ld, double* __restrict__ r_out, double* __restrict__ z_out, double* __restrict__ rc_out,
-          const int nJc, Scalars* sc, double* partials, const int mode, const MLTop top) {
+          const int nJc, Scalars* sc, double* partials, const int mode, const MLTop top, const int pf) {
     constexpr int ROW = 32 * SEG, ROWP = ROW + ROW / SEG, NE = (ROW + 255) / 256;
     __shared__ double sh[32 * 2];
     __shared__ int sh_flag;
@@ -321,6 +321,17 @@ k_line_ml(const LineDom d, const double* __restrict__ r_in, const double* __rest
                         *reinterpret_cast<double2*>(r_out + base + i) = vr[c];
                     }
                     rs[c].x += vr[c].x; rs[c].y += vr[c].y;
+                }
+            }
+            if (pf) {   // the row this warp solves next (t = 1 of this aggregate, or t = 0 of the block's next aggregate): into L2 meanwhile
+                const int an = t ? agg + (int)gridDim.x : agg;
+                const int jn = (an % naJ) * PFEM_ML_C + (w & 3), kn = (an / naJ) * PFEM_ML_C + 2 * (w >> 2) + (1 - t) - d.koff;
+                if (an < naJ * naK && jn < d.nJ && kn >= d.k0 && kn < d.k1) {
+                    const idx_t bn = d.sJ * jn + d.sK * (idx_t)kn;
+                    prefetch_row_l2(r_in + bn, lane, (int)d.sJ);
+                    prefetch_row_l2(ll + bn, lane, (int)d.sJ);
+                    prefetch_row_l2(ld + bn, lane, (int)d.sJ);
+                    if (FINE && mode == 0) prefetch_row_l2(q_in + bn, lane, (int)d.sJ);
                 }
             }
             double rr = 0.;

@@ -46,6 +46,13 @@ struct Grid {
     const double *uI, *uJ, *uK;
 };
 
+// L2 prefetch of one lattice row of up to 512 doubles (lane l touches the 128-byte line l): the warp-per-row line kernels issue it for
+// the row they will solve NEXT right after the loads of the current row, so that row's HBM latency passes under the current solve
+// (ncu r02: 61 % of the stall samples of k_line_ml<FINE> were long-scoreboard waits on the first use of a freshly loaded row).
+__device__ __forceinline__ void prefetch_row_l2(const double* row, const int lane, const int n) {
+    if (lane * 16 < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + lane * 16));
+}
+
 // ---- slab mode (one context per GPU, peers mapped with CUDA IPC over NVLink) ----------------
 #define PFEM_MAX_RANKS 8
 #define PFEM_COMM_NV 8

@@ -1320,6 +1320,12 @@ static inline int line_seg(const Grid& g) {   // nodes per lane of the I-line ke
     return 0;
 }
 
+// L2 prefetch of the next row in the warp-per-row line kernels (k_line_I, k_line_ml); PFEM_LINE_PREFETCH=0 turns it off for A/B runs
+static int line_prefetch() {
+    static const int v = getenv("PFEM_LINE_PREFETCH") ? atoi(getenv("PFEM_LINE_PREFETCH")) : 1;
+    return v;
+}
+
 // z = M^-1 (r - alpha q) for the line-Jacobi preconditioner; mode 1: only b.M^-1 b -> sc->bz
 static int launch_line_solve(pfem_ctx* ctx, const double* r_in, const double* q_in, double* r_out, int mode) {
     const Grid& g = ctx->g;
@@ -1332,7 +1338,7 @@ static int launch_line_solve(pfem_ctx* ctx, const double* r_in, const double* q_
         const idx_t rpw = (rows + cap_warps - 1) / cap_warps;
         int blocks = (int)(((rows + rpw - 1) / rpw + 7) / 8);
         if (blocks < 1) blocks = 1;
-#define PFEM_LINE_CASE(S) case S: k_line_I<S><<<blocks, 256, 0, ctx->stream>>>(g, r_in, q_in, ctx->ll, ctx->ld, r_out, ctx->lz, ctx->d_sc, ctx->partials, mode, po); break;
+#define PFEM_LINE_CASE(S) case S: k_line_I<S><<<blocks, 256, 0, ctx->stream>>>(g, r_in, q_in, ctx->ll, ctx->ld, r_out, ctx->lz, ctx->d_sc, ctx->partials, mode, po, line_prefetch()); break;
         switch (line_seg(g)) {
             PFEM_LINE_CASE(2) PFEM_LINE_CASE(4) PFEM_LINE_CASE(8) PFEM_LINE_CASE(16)
             default: FAIL(PFEM_ERR_STATE, "no warp-per-row line kernel for %d nodes per line", g.nI);
@@ -1464,11 +1470,11 @@ static void launch_ml_chain_seg(pfem_ctx* ctx, const double* r_in, const double*
     };
     k_line_ml<SEG, true><<<ml_blocks(ctx, ml.dom[0]), 256, 0, ctx->stream>>>(ml.dom[0], r_in, q_in, ctx->ll, ctx->ld, r_out, ctx->lz,
                                                                            La >= 1 ? ml.r[1] : nullptr, La >= 1 ? ml.dom[1].nJ : 0, ctx->d_sc,
-                                                                           ctx->partials, mode, top_of(0));
+                                                                           ctx->partials, mode, top_of(0), line_prefetch());
     for (int l = 1; l <= La; ++l)
         k_line_ml<SEG, false><<<ml_blocks(ctx, ml.dom[l]), 256, 0, ctx->stream>>>(ml.dom[l], ml.r[l], nullptr, ml.ll[l], ml.ld[l], nullptr, ml.z[l],
                                                                                 l < La ? ml.r[l + 1] : nullptr, l < La ? ml.dom[l + 1].nJ : 0,
-                                                                                ctx->d_sc, ctx->partials, mode, top_of(l));
+                                                                                ctx->d_sc, ctx->partials, mode, top_of(l), line_prefetch());
 }
 
 // z_0 .. z_top and the CG scalars of the multilevel preconditioner; mode 1: only b.M^-1 b -> sc->bz; mode 2: z only

@@ -103,7 +103,7 @@ def test_static2d_boundary_mode_needs_the_embedding():
     from helpers import face_nodes
     from plask_b200 import configs
     from plask_b200.fem import DeviceFem
-    p = configs.config_B((6, 6, 8))
+    p = configs.config_B((6, 6, 20))
     f = DeviceFem(0)
     f.set_mesh(p.axes, p.strides)
     with pytest.raises(L.BadInput):

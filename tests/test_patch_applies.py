@@ -20,6 +20,7 @@ def _files():
 def test_patch_touches_the_documented_files():
     want = {"plask/common/fem/fem_solver.hpp", "python/plask/common/fem/fem.cpp", "plask/common/fem.yml",
             "solvers/thermal/static/therm3d.hpp", "solvers/thermal/static/therm3d.cpp",
+            "solvers/thermal/static/therm2d.hpp", "solvers/thermal/static/therm2d.cpp",
             "solvers/electrical/shockley/electr3d.hpp", "solvers/electrical/shockley/electr3d.cpp",
             "solvers/electrical/shockley/beta.hpp", "solvers/electrical/shockley/python/electr_python.cpp",
             "solvers/thermal/static/CMakeLists.txt", "solvers/electrical/shockley/CMakeLists.txt",
@@ -43,6 +44,9 @@ def test_patch_applies_to_the_reference(tmp_path):
     assert "ALGORITHM_CUDA" in text and '.value("cuda", ALGORITHM_CUDA)' in text
     assert "computeCuda" in open(tmp_path / "solvers/thermal/static/therm3d.cpp").read()
     assert "shockleyParameters" in open(tmp_path / "solvers/electrical/shockley/beta.hpp").read()
+    t2 = open(tmp_path / "solvers/thermal/static/therm2d.cpp").read()
+    assert "cuda->set_axis_weight(1, rmid);" in t2 and "std::is_same<Geometry2DType, Geometry2DCylindrical>::value ? 2 : 1" in t2
+    assert "if (this->algorithm == ALGORITHM_CUDA) return computeCuda(loops, btemperature, bheatflux, bconvection, bradiation);" in t2
     dyn = open(tmp_path / "solvers/thermal/dynamic/femT3d.cpp").read()
     assert "solve_dynamic" in dyn and "set_capacity" in dyn and "if (algorithm == ALGORITHM_CUDA) return computeCuda(time, btemperature);" in dyn
     dif = open(tmp_path / "solvers/electrical/diffusion/diffusion3d.cpp").read()

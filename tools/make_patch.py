@@ -10,6 +10,8 @@ What the patch does (INTEGRATION.md explains every hunk):
     branch that hands the whole nonlinear loop to the library (include/plaskfem_cuda.hpp)
   * BetaSolver / the Python Shockley class expose beta(T), js(T) per junction through one virtual, so that the host can
     evaluate them at the mid-plane temperature of every junction column (electr3d.cpp:261-262)
+  * ThermalFem2DSolver<Cartesian / Cylindrical>: the same through the one-layer embedding of the 2-D mesh (radial element weights,
+    the edge conditions of the 2nd / 3rd kind and radiation in the library's 2-D mode)
   * DynamicThermalFem3DSolver: the same for the time loop of compute(time) (pfem_solve_dynamic, corrected update)
   * Diffusion3DSolver: compute() hands the whole loop of one active region to pdiff_compute (include/plaskdiff_cuda.hpp)
   * the four solver CMakeLists link plaskfem_cuda
@@ -301,6 +303,225 @@ edit(F, """void ThermalFem3DSolver::saveHeatFluxes()
 }
 
 void ThermalFem3DSolver::saveHeatFluxes()
+{""")
+
+# ---------------------------------------------------------------- thermal.static Static2D / StaticCyl (INTEGRATION.md 9)
+F = "solvers/thermal/static/therm2d.hpp"
+edit(F, """#include "common.hpp"
+
+namespace plask { namespace thermal { namespace tstatic {
+
+/**
+ * Solver performing calculations in 2D Cartesian or Cylindrical space using finite element method
+ */
+template <typename Geometry2DType>
+struct PLASK_SOLVER_API ThermalFem2DSolver :""", """#include "common.hpp"
+
+namespace plaskfem { class Context; }   // plaskfem_cuda.hpp: host adapter of libplaskfem_cuda.so (algorithm 'cuda')
+
+namespace plask { namespace thermal { namespace tstatic {
+
+/**
+ * Solver performing calculations in 2D Cartesian or Cylindrical space using finite element method
+ */
+template <typename Geometry2DType>
+struct PLASK_SOLVER_API ThermalFem2DSolver :""")
+edit(F, """    DataVector<Vec<2, double>> fluxes;  ///< Computed (only when needed) heat fluxes on our own mesh
+""", """    DataVector<Vec<2, double>> fluxes;  ///< Computed (only when needed) heat fluxes on our own mesh
+
+    std::shared_ptr<plaskfem::Context> cuda;  ///< Device context, exists only for algorithm 'cuda'
+
+    /// Node of the masked mesh -> node i0 * n1 + i1 of plane 0 of the one-layer brick mesh the device library works on
+    std::vector<size_t> cudaNode;
+
+    /// Create the device context: the 2-D mesh as a brick mesh of one element layer, (material, thickness) ids, thermk(T) tables
+    void setupCuda();
+
+    /// The nonlinear loop of compute() on the device
+    double computeCuda(int loops,
+                       const BoundaryConditionsWithMesh<RectangularMesh<2>::Boundary, double>& btemperature,
+                       const BoundaryConditionsWithMesh<RectangularMesh<2>::Boundary, double>& bheatflux,
+                       const BoundaryConditionsWithMesh<RectangularMesh<2>::Boundary, Convection>& bconvection,
+                       const BoundaryConditionsWithMesh<RectangularMesh<2>::Boundary, Radiation>& bradiation);
+""")
+
+F = "solvers/thermal/static/therm2d.cpp"
+edit(F, """#include "therm2d.hpp"
+""", """#include "therm2d.hpp"
+
+#include <plaskfem_cuda.hpp>
+""")
+edit(F, """            if (idx != RectangularMaskedMesh2D::Element::UNKNOWN_ELEMENT_INDEX)
+                thickness[idx] = h;
+        }
+    }
+}
+
+
+template<typename Geometry2DType> void ThermalFem2DSolver<Geometry2DType>::onInvalidate() {
+    temperatures.reset();
+    fluxes.reset();
+    thickness.reset();
+}
+""", """            if (idx != RectangularMaskedMesh2D::Element::UNKNOWN_ELEMENT_INDEX)
+                thickness[idx] = h;
+        }
+    }
+
+    if (this->algorithm == ALGORITHM_CUDA) setupCuda();
+}
+
+
+template<typename Geometry2DType>
+void ThermalFem2DSolver<Geometry2DType>::setupCuda() {
+    try {
+        cuda.reset(new plaskfem::Context(0, this->getId()));
+        // The library has no 2-D kernels: a brick mesh with ONE element layer along a dummy axis and z-invariant data gives, on each
+        // of its two node planes, 0.5e-6 * d times the 4-node rectangle operator and load of setMatrix (INTEGRATION.md 9).
+        const size_t n0 = this->mesh->axis[0]->size(), n1 = this->mesh->axis[1]->size();
+        plaskfem::Mesh fm;
+        fm.axis[0] = {0., 1.};
+        for (size_t i = 0; i != n0; ++i) fm.axis[1].push_back(this->mesh->axis[0]->at(i));
+        for (size_t i = 0; i != n1; ++i) fm.axis[2].push_back(this->mesh->axis[1]->at(i));
+        fm.order = plaskfem::ORDER_012;   // node (0, i0, i1) = i0 * n1 + i1, element (0, i0, i1) = i0 * (n1 - 1) + i1
+        cuda->set_mesh(fm);
+        if (std::is_same<Geometry2DType, Geometry2DCylindrical>::value) {
+            std::vector<double> rmid(n0 - 1);   // every element matrix and load carries midpoint.rad_r() (setMatrix of the cylindrical solver)
+            for (size_t i = 0; i + 1 < n0; ++i) rmid[i] = 0.5 * (this->mesh->axis[0]->at(i) + this->mesh->axis[0]->at(i + 1));
+            cuda->set_axis_weight(1, rmid);
+        }
+
+        const size_t nfull = (n0 - 1) * (n1 - 1);
+        std::vector<shared_ptr<Material>> materials(nfull);
+        std::vector<const Material*> key(nfull, nullptr);
+        std::vector<double> thick(nfull, 0.);
+        std::vector<uint8_t> included(nfull, 0);
+        cudaNode.assign(this->maskedMesh->size(), 0);
+        for (auto elem: this->maskedMesh->elements()) {
+            const size_t i0 = elem.getIndex0(), i1 = elem.getIndex1(), e = i0 * (n1 - 1) + i1;
+            materials[e] = this->geometry->getMaterial(elem.getMidpoint());
+            key[e] = materials[e].get();
+            thick[e] = thickness[elem.getIndex()];
+            included[e] = 1;
+            cudaNode[elem.getLoLoIndex()] = i0 * n1 + i1;
+            cudaNode[elem.getUpLoIndex()] = (i0 + 1) * n1 + i1;
+            cudaNode[elem.getLoUpIndex()] = i0 * n1 + i1 + 1;
+            cudaNode[elem.getUpUpIndex()] = (i0 + 1) * n1 + i1 + 1;
+        }
+        std::vector<size_t> reps;
+        std::vector<uint32_t> ids = plaskfem::material_ids(key, thick, &reps);
+        plaskfem::Tables tables = plaskfem::sample_tables(reps.size(), [&](uint32_t id, double T) {
+            if (!materials[reps[id]]) return std::make_pair(0., 0.);
+            auto k = materials[reps[id]]->thermk(T, thick[reps[id]]);
+            return std::make_pair(k.c00, k.c11);
+        });
+        if (!this->maskedMesh->full()) ids = plaskfem::MaskedNumbering(fm, included).mark_excluded(ids);
+        cuda->set_materials(ids, tables);
+        cuda->fill_field(inittemp);
+    } catch (const plaskfem::NoDevice& err) {
+        throw ComputationError(this->getId(), "algorithm 'cuda' has no CPU fallback: {}", err.what());
+    } catch (const plaskfem::BadInput& err) {
+        throw BadInput(this->getId(), "{}", err.what());
+    }
+}
+
+
+template<typename Geometry2DType> void ThermalFem2DSolver<Geometry2DType>::onInvalidate() {
+    temperatures.reset();
+    fluxes.reset();
+    thickness.reset();
+    cuda.reset();
+    cudaNode.clear();
+}
+""")
+edit(F, """    this->writelog(LOG_INFO, "Running thermal calculations");
+
+    int loop = 0;
+    size_t size = this->maskedMesh->size();
+
+    std::unique_ptr<FemMatrix> pA(this->getMatrix());
+    FemMatrix& A = *pA.get();
+
+    double err;
+    toterr = 0.;
+""", """    this->writelog(LOG_INFO, "Running thermal calculations");
+
+    if (this->algorithm == ALGORITHM_CUDA) return computeCuda(loops, btemperature, bheatflux, bconvection, bradiation);
+
+    int loop = 0;
+    size_t size = this->maskedMesh->size();
+
+    std::unique_ptr<FemMatrix> pA(this->getMatrix());
+    FemMatrix& A = *pA.get();
+
+    double err;
+    toterr = 0.;
+""")
+edit(F, """template<typename Geometry2DType>
+void ThermalFem2DSolver<Geometry2DType>::saveHeatFluxes()
+{""", """template<typename Geometry2DType>
+double ThermalFem2DSolver<Geometry2DType>::computeCuda(int loops,
+                   const BoundaryConditionsWithMesh<RectangularMesh<2>::Boundary,double>& btemperature,
+                   const BoundaryConditionsWithMesh<RectangularMesh<2>::Boundary,double>& bheatflux,
+                   const BoundaryConditionsWithMesh<RectangularMesh<2>::Boundary,Convection>& bconvection,
+                   const BoundaryConditionsWithMesh<RectangularMesh<2>::Boundary,Radiation>& bradiation)
+{
+    if (!cuda) setupCuda();
+    try {
+        const size_t n0 = this->mesh->axis[0]->size(), n1 = this->mesh->axis[1]->size();
+        const size_t plane = n0 * n1, nfull = 2 * plane;   // the two node planes of the brick mesh hold the same field
+
+        // Edge conditions of the 2nd / 3rd kind and radiation (setBoundaries + the lambdas of setMatrix): per-node getValue() arrays
+        // on plane 0, flattened by the library in its 2-D mode (pfem_boundary::mode2d: 1 Cartesian, 2 cylindrical)
+        plaskfem::NodeConditions<1> hf;
+        plaskfem::NodeConditions<2> cv, rd;
+        for (auto cond: bheatflux) for (auto r: cond.place) hf.add_node(nfull, cudaNode[r], {cond.value});
+        for (auto cond: bconvection) for (auto r: cond.place) cv.add_node(nfull, cudaNode[r], {cond.value.coeff, cond.value.ambient});
+        for (auto cond: bradiation) for (auto r: cond.place) rd.add_node(nfull, cudaNode[r], {cond.value.emissivity, cond.value.ambient});
+        cuda->set_boundary(hf, cv, rd, /*verbatim=*/true, std::is_same<Geometry2DType, Geometry2DCylindrical>::value ? 2 : 1);
+
+        plaskfem::Dirichlet bc;                                   // application order of matrix.hpp:111-118, on both planes
+        for (auto cond: btemperature)
+            for (auto r: cond.place) { bc.add_node(cudaNode[r], cond.value); bc.add_node(cudaNode[r] + plane, cond.value); }
+        cuda->set_dirichlet(bc);
+
+        auto heats = inHeat(this->maskedMesh->getElementMesh());
+        std::vector<double> heat((n0 - 1) * (n1 - 1), 0.);
+        for (auto elem: this->maskedMesh->elements()) heat[elem.getIndex0() * (n1 - 1) + elem.getIndex1()] = heats[elem.getIndex()];
+        cuda->set_source(heat.data());
+
+        temperatures = temperatures.claim();
+        std::vector<double> field(nfull, 0.);
+        for (size_t i = 0; i != temperatures.size(); ++i) field[cudaNode[i]] = field[cudaNode[i] + plane] = temperatures[i];
+        cuda->set_field(field.data());                            // warm start, like iterative_matrix.hpp:205-209
+
+        plaskfem::IterParams ip{this->iter_params.maxit, this->iter_params.maxerr,
+                                plaskfem::IterParams::NoConvergenceBehavior(int(this->iter_params.no_convergence_behavior))};
+        ip.preconditioner = this->iter_params.preconditioner == IterativeMatrixParams::PRECOND_JAC ? plaskfem::IterParams::PRECOND_JAC :
+                            this->iter_params.preconditioner == IterativeMatrixParams::PRECOND_LJAC ? plaskfem::IterParams::PRECOND_LJAC :
+                                                                                                      plaskfem::IterParams::PRECOND_MLJ;
+        auto result = cuda->solve(true, ip, maxerr, loops,
+                                  [this](int level, const std::string& msg) { this->writelog(LogLevel(level), msg); });
+        this->iter_params.converged = ip.converged; this->iter_params.iters = ip.iters; this->iter_params.err = ip.err;
+
+        cuda->get_field(field.data());
+        for (size_t i = 0; i != temperatures.size(); ++i) temperatures[i] = field[cudaNode[i]];
+        loopno = result.loopno; maxT = result.maxval; toterr = result.toterr;
+    } catch (const plaskfem::BadInput& err) {
+        throw BadInput(this->getId(), "{}", err.what());
+    } catch (const std::runtime_error& err) {
+        throw ComputationError(this->getId(), "{}", err.what());
+    }
+
+    outTemperature.fireChanged();
+    outHeatFlux.fireChanged();
+
+    return toterr;
+}
+
+
+template<typename Geometry2DType>
+void ThermalFem2DSolver<Geometry2DType>::saveHeatFluxes()
 {""")
 
 # ---------------------------------------------------------------- electrical.shockley Shockley3D

@@ -153,3 +153,42 @@ def test_oracle_radiation_fixed_point():
     T = o.temperatures[top[0]]
     assert T > 300.
     assert k * (T - 300.) / H == pytest.approx(-eps * oracle2d.SB * (T ** 4 - Ta ** 4), rel=1e-7)
+
+
+def test_host_flattening_properties():
+    """size-independent properties on random meshes and random node sets (hypothesis): the convection matrix is symmetric positive
+    semidefinite with support on flagged nodes only; loads are linear in the flux / in coeff * ambient; an edge needs both nodes"""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.integers(0, 2 ** 31 - 1), st.integers(3, 7), st.integers(3, 7), st.booleans(), st.booleans())
+    def check(seed, n0, n1, cyl, verbatim):
+        rng = np.random.default_rng(seed)
+        x = (0. if cyl else -2.) + np.concatenate([[0.], np.cumsum(rng.uniform(0.2, 2., n0 - 1))])
+        y = np.concatenate([[0.], np.cumsum(rng.uniform(0.2, 2., n1 - 1))])
+        N = n0 * n1
+        nodes = np.nonzero(rng.random(N) < 0.6)[0]
+        if nodes.size == 0:
+            return
+        h, Ta, q = rng.uniform(1., 1e4), rng.uniform(250., 400.), rng.uniform(-1e6, 1e6)
+        load, _, _, K = _host_terms(x, y, [(nodes, q)], [(nodes, h, Ta)], [], cyl, verbatim)
+        assert np.array_equal(K, K.T)
+        off = np.ones(N, dtype=bool)
+        off[nodes] = False
+        assert not K[off].any() and not K[:, off].any() and not load[off].any()
+        if K.any():
+            assert np.linalg.eigvalsh(K).min() >= -1e-12 * np.abs(K).max()
+        load2, _, _, K2 = _host_terms(x, y, [(nodes, 2. * q)], [(nodes, 3. * h, Ta)], [], cyl, verbatim)
+        lq, _, _, _ = _host_terms(x, y, [(nodes, q)], [], [], cyl, verbatim)
+        lc = load - lq
+        assert np.allclose(K2, 3. * K, rtol=1e-13, atol=0.)
+        assert np.allclose(load2, 2. * lq + 3. * lc, rtol=1e-12, atol=1e-12 * (np.abs(load).max() + 1e-300))
+        # a node whose neighbours along both axes are all unflagged contributes nothing
+        g = np.zeros((n0, n1), dtype=bool)
+        g.ravel()[nodes] = True
+        pad = np.pad(g, 1)
+        lonely = g & ~(pad[:-2, 1:-1] | pad[2:, 1:-1] | pad[1:-1, :-2] | pad[1:-1, 2:])
+        assert not load[lonely.ravel()].any() and not K[lonely.ravel()].any()
+
+    check()

@@ -203,6 +203,58 @@ struct MaskedNumbering {
     }
 };
 
+// ---- the 2-D solvers on the brick kernels (therm2d.cpp, electr2d.cpp, femT2d.cpp) --------------------
+//
+// A RectangularMesh<2> (axis 0 = tran or r, axis 1 = vert) is handed to the library as a brick mesh with ONE element layer along
+// a dummy longitudinal axis: for z-invariant data the brick operator, load and capacity restricted to a node plane are
+// 0.5e-6 * thickness times the 4-node rectangle ones, so plane 0 of the result is the 2-D FEM solution.  This helper holds the
+// index bookkeeping every 2-D solver needs: plane-0 numbering node (i0, i1) = i0 * n1 + i1, element (i0, i1) = i0 * (n1 - 1) + i1
+// whatever the iteration order of the plugin's own mesh.
+struct Embedding2D {
+    size_t n0 = 0, n1 = 0;
+    Mesh mesh;   // axis[0] = {0, thickness}, axis[1] = tran / r, axis[2] = vert, ORDER_012
+
+    Embedding2D() {}
+    Embedding2D(const std::vector<double>& x, const std::vector<double>& y, double thickness = 1.) : n0(x.size()), n1(y.size()) {
+        if (n0 < 2 || n1 < 2) throw BadInput("Embedding2D: mesh needs at least 2 points per axis");
+        if (!(thickness > 0.)) throw BadInput("Embedding2D: the dummy layer needs a positive thickness");
+        mesh.axis[0] = {0., thickness};
+        mesh.axis[1] = x;
+        mesh.axis[2] = y;
+        mesh.order = ORDER_012;
+    }
+    size_t plane() const { return n0 * n1; }                          // nodes per plane; the brick mesh has 2 * plane()
+    size_t elements() const { return (n0 - 1) * (n1 - 1); }           // the brick mesh has the same elements
+    size_t node(size_t i0, size_t i1) const { return i0 * n1 + i1; }  // on plane 0; + plane() on plane 1
+    size_t elem(size_t i0, size_t i1) const { return i0 * (n1 - 1) + i1; }
+    // element weights of the cylindrical solvers: midpoint.rad_r() of every element column (therm2d.cpp:353, electr2d.cpp:220),
+    // for Context::set_axis_weight(1, ...)
+    std::vector<double> radial_weights() const {
+        std::vector<double> w(n0 - 1);
+        for (size_t i = 0; i + 1 < n0; ++i) w[i] = 0.5 * (mesh.axis[1][i] + mesh.axis[1][i + 1]);
+        return w;
+    }
+    // a condition of the first kind on a node of the 2-D mesh: both planes, application order kept (matrix.hpp:111-118)
+    void add_dirichlet(Dirichlet& bc, size_t node2d, double value) const {
+        if (node2d >= plane()) throw BadInput("Embedding2D: node outside the 2-D mesh");
+        bc.add_node(node2d, value);
+        bc.add_node(node2d + plane(), value);
+    }
+    // 2-D nodal field -> brick field (the same values on both planes) and back (plane 0)
+    std::vector<double> lift(const double* f2d) const {
+        std::vector<double> f(2 * plane());
+        for (size_t i = 0; i < plane(); ++i) f[i] = f[i + plane()] = f2d[i];
+        return f;
+    }
+    void restrict_to_plane(const double* brick, double* f2d) const { for (size_t i = 0; i < plane(); ++i) f2d[i] = brick[i]; }
+    // element vectors of the library ([E][3], the longitudinal component is zero) -> the (tran / r, vert) pairs of the 2-D solvers
+    void elem_vec2(const double* brick3, double* out2) const {
+        for (size_t e = 0; e < elements(); ++e) { out2[2 * e] = brick3[3 * e + 1]; out2[2 * e + 1] = brick3[3 * e + 2]; }
+    }
+    // pfem_boundary::mode2d for Context::set_boundary: edge conditions of therm2d.cpp, Cartesian or cylindrical
+    static int boundary_mode(bool cylindrical) { return cylindrical ? 2 : 1; }
+};
+
 // ---- row a7: boundary conditions of the 2nd / 3rd kind and radiation ----------------------------------
 //
 // heatflux_boundary / convection_boundary / radiation_boundary (therm3d.hpp:79-82) in the form setBoundaries reads

@@ -13,6 +13,7 @@
 
 using namespace plaskfem;
 
+static bool near(double a, double b) { return std::fabs(a - b) <= 1e-13 * (std::fabs(a) + std::fabs(b)); }
 #define REQUIRE(c) do { if (!(c)) { fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
 
 static Mesh make_mesh(size_t n0, size_t n1, size_t n2, IterationOrder o) {
@@ -108,6 +109,51 @@ static int host_tests() {
 
     Tables t = sample_tables(2, [](uint32_t id, double T) { return std::make_pair(10. * (id + 1) * 300. / T, 5. * (id + 1)); }, 250., 0.5, 701);
     REQUIRE(t.lat.size() == 1402 && std::fabs(t.lat[701 + 100] - 20. * 300. / 300.) < 1e-12);
+
+    // the 2-D solvers' bookkeeping and the library's host-side flattening of the 2-D edge conditions
+    {
+        const std::vector<double> x = {0., 1., 3.}, y = {0., 0.5, 1.0, 2.0};
+        Embedding2D emb(x, y);
+        REQUIRE(emb.plane() == 12 && emb.elements() == 6 && emb.mesh.size() == 24 && emb.mesh.elements() == 6);
+        REQUIRE(emb.mesh.node(0, 2, 1) == emb.node(2, 1) && emb.mesh.node(1, 2, 1) == emb.node(2, 1) + emb.plane());
+        REQUIRE(emb.mesh.elem(0, 1, 2) == emb.elem(1, 2));
+        std::vector<double> w = emb.radial_weights();
+        REQUIRE(w.size() == 2 && w[0] == 0.5 && w[1] == 2.0);
+        Dirichlet bc;
+        emb.add_dirichlet(bc, emb.node(1, 0), 300.);
+        REQUIRE(bc.node.size() == 2 && bc.node[0] == 4 && bc.node[1] == 16 && bc.value[1] == 300.);
+        std::vector<double> f2(12);
+        for (size_t i = 0; i < 12; ++i) f2[i] = double(i);
+        std::vector<double> f3 = emb.lift(f2.data()), back(12);
+        REQUIRE(f3.size() == 24 && f3[5] == 5. && f3[17] == 5.);
+        emb.restrict_to_plane(f3.data(), back.data());
+        REQUIRE(back == f2);
+        bool threw = false;
+        try { Embedding2D bad({0.}, y); } catch (const BadInput&) { threw = true; }
+        REQUIRE(threw);
+        REQUIRE(Embedding2D::boundary_mode(false) == 1 && Embedding2D::boundary_mode(true) == 2);
+
+        // convection on the top edge (nodes (i0, 3)): one edge per element column, therm2d.cpp:236-246 (Cartesian) / :385-397 (cylindrical)
+        const size_t N = emb.plane();
+        NodeConditions<2> cv;
+        for (size_t i0 = 0; i0 < 3; ++i0) cv.add_node(N, emb.node(i0, 3), {100., 300.});
+        pfem_boundary b;
+        memset(&b, 0, sizeof b);
+        b.has_conv = cv.has.data(); b.conv_coeff = cv.v[0].data(); b.conv_ambient = cv.v[1].data();
+        std::vector<double> load(N), rc(N), ra(N), K(N * N);
+        b.verbatim = 0; b.mode2d = 1;
+        REQUIRE(pfem_edges2d_host(3, x.data(), 4, y.data(), &b, load.data(), rc.data(), ra.data(), K.data()) == PFEM_OK);
+        const size_t a = emb.node(0, 3), c = emb.node(1, 3), d = emb.node(2, 3);
+        REQUIRE(near(load[a], 0.5e-6 * 1. * 100. * 300.) && near(load[c], 0.5e-6 * (1. + 2.) * 100. * 300.) && near(load[d], 0.5e-6 * 2. * 100. * 300.));
+        REQUIRE(near(K[a * N + a], 1e-6 * 200. * 1. / 6.) && near(K[a * N + c], 1e-6 * 200. * 1. / 12.) && near(K[c * N + d], 1e-6 * 200. * 2. / 12.));
+        REQUIRE(near(K[c * N + c], 1e-6 * 200. * (1. + 2.) / 6.) && K[a * N + d] == 0. && load[emb.node(1, 2)] == 0.);
+        b.verbatim = 1; b.mode2d = 2;      // cylindrical, as written: no 1e-6, r - len/6 on the inner node, a second factor r_mid
+        REQUIRE(pfem_edges2d_host(3, x.data(), 4, y.data(), &b, load.data(), rc.data(), ra.data(), K.data()) == PFEM_OK);
+        REQUIRE(near(K[a * N + a], 0.5 * (200. * 1. / 6.) * (0.5 - 1. / 6.)) && near(K[a * N + c], 0.5 * (200. * 1. / 12.) * 0.5));
+        REQUIRE(near(load[a], 0.125e-6 * 1. * 200. * 600. * (0.5 - 1. / 6.)));
+        b.mode2d = 0;
+        REQUIRE(pfem_edges2d_host(3, x.data(), 4, y.data(), &b, load.data(), rc.data(), ra.data(), K.data()) == PFEM_ERR_BAD_INPUT);
+    }
 
     if (pfem_device_count() == 0) {
         bool nodev = false;

@@ -25,6 +25,7 @@ def test_patch_touches_the_documented_files():
             "solvers/electrical/shockley/beta.hpp", "solvers/electrical/shockley/python/electr_python.cpp",
             "solvers/thermal/static/CMakeLists.txt", "solvers/electrical/shockley/CMakeLists.txt",
             "solvers/thermal/dynamic/femT3d.hpp", "solvers/thermal/dynamic/femT3d.cpp", "solvers/thermal/dynamic/CMakeLists.txt",
+            "solvers/thermal/dynamic/femT2d.hpp", "solvers/thermal/dynamic/femT2d.cpp",
             "solvers/electrical/diffusion/diffusion3d.hpp", "solvers/electrical/diffusion/diffusion3d.cpp",
             "solvers/electrical/diffusion/CMakeLists.txt"}
     assert set(_files()) == want
@@ -45,10 +46,13 @@ def test_patch_applies_to_the_reference(tmp_path):
     assert "computeCuda" in open(tmp_path / "solvers/thermal/static/therm3d.cpp").read()
     assert "shockleyParameters" in open(tmp_path / "solvers/electrical/shockley/beta.hpp").read()
     t2 = open(tmp_path / "solvers/thermal/static/therm2d.cpp").read()
-    assert "cuda->set_axis_weight(1, rmid);" in t2 and "std::is_same<Geometry2DType, Geometry2DCylindrical>::value ? 2 : 1" in t2
+    assert "cuda->set_axis_weight(1, emb.radial_weights());" in t2 and "plaskfem::Embedding2D::boundary_mode(" in t2
     assert "if (this->algorithm == ALGORITHM_CUDA) return computeCuda(loops, btemperature, bheatflux, bconvection, bradiation);" in t2
     dyn = open(tmp_path / "solvers/thermal/dynamic/femT3d.cpp").read()
     assert "solve_dynamic" in dyn and "set_capacity" in dyn and "if (algorithm == ALGORITHM_CUDA) return computeCuda(time, btemperature);" in dyn
+    d2 = open(tmp_path / "solvers/thermal/dynamic/femT2d.cpp").read()
+    assert "if (this->algorithm == ALGORITHM_CUDA) return computeCuda(time, btemperature);" in d2 and "cuda->set_capacity(tables, cpdens);" in d2
+    assert "emb.add_dirichlet(bc, cudaNode[r], cond.value);" in d2
     dif = open(tmp_path / "solvers/electrical/diffusion/diffusion3d.cpp").read()
     assert "computeCuda(loops, act, active, A, B, C, D, J, nmodes, Ps, nrs);" in dif and "#include <plaskdiff_cuda.hpp>" in dif
 
@@ -62,7 +66,9 @@ def test_every_adapter_call_of_the_patch_exists():
         assert re.search(r"\b%s\(" % name, hdr), f"Context::{name} is not declared in plaskfem_cuda.hpp"
     for name in set(re.findall(r"plaskfem::(\w+)", added)):
         assert re.search(r"\b%s\b" % name, hdr), f"plaskfem::{name} is not declared in plaskfem_cuda.hpp"
-    for name in ("add_node", "node_to_full", "mark_excluded", "PRECOND_MLJ"):
+    for name in set(re.findall(r"\bemb\.(\w+)\(", added)):
+        assert re.search(r"\b%s\(" % name, hdr), f"Embedding2D::{name} is not declared in plaskfem_cuda.hpp"
+    for name in ("add_node", "node_to_full", "mark_excluded", "PRECOND_MLJ", "Embedding2D", "radial_weights", "lift"):
         assert name in added and name in hdr
     dhdr = open(os.path.join(ROOT, "include", "plaskdiff_cuda.hpp")).read()
     for name in set(re.findall(r"region->(\w+)\(", added)):

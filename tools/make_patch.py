@@ -10,8 +10,8 @@ What the patch does (INTEGRATION.md explains every hunk):
     branch that hands the whole nonlinear loop to the library (include/plaskfem_cuda.hpp)
   * BetaSolver / the Python Shockley class expose beta(T), js(T) per junction through one virtual, so that the host can
     evaluate them at the mid-plane temperature of every junction column (electr3d.cpp:261-262)
-  * ThermalFem2DSolver<Cartesian / Cylindrical>: the same through the one-layer embedding of the 2-D mesh (radial element weights,
-    the edge conditions of the 2nd / 3rd kind and radiation in the library's 2-D mode)
+  * ThermalFem2DSolver / DynamicThermalFem2DSolver <Cartesian / Cylindrical>: the same through the one-layer embedding of the 2-D mesh
+    (plaskfem::Embedding2D, radial element weights, the edge conditions of the 2nd / 3rd kind and radiation in the library's 2-D mode)
   * DynamicThermalFem3DSolver: the same for the time loop of compute(time) (pfem_solve_dynamic, corrected update)
   * Diffusion3DSolver: compute() hands the whole loop of one active region to pdiff_compute (include/plaskdiff_cuda.hpp)
   * the four solver CMakeLists link plaskfem_cuda
@@ -310,31 +310,24 @@ F = "solvers/thermal/static/therm2d.hpp"
 edit(F, """#include "common.hpp"
 
 namespace plask { namespace thermal { namespace tstatic {
+""", """#include "common.hpp"
 
-/**
- * Solver performing calculations in 2D Cartesian or Cylindrical space using finite element method
- */
-template <typename Geometry2DType>
-struct PLASK_SOLVER_API ThermalFem2DSolver :""", """#include "common.hpp"
-
-namespace plaskfem { class Context; }   // plaskfem_cuda.hpp: host adapter of libplaskfem_cuda.so (algorithm 'cuda')
+#include <plaskfem_cuda.hpp>   // host adapter of libplaskfem_cuda.so (algorithm 'cuda'): header-only, plain C ABI underneath
 
 namespace plask { namespace thermal { namespace tstatic {
-
-/**
- * Solver performing calculations in 2D Cartesian or Cylindrical space using finite element method
- */
-template <typename Geometry2DType>
-struct PLASK_SOLVER_API ThermalFem2DSolver :""")
+""")
 edit(F, """    DataVector<Vec<2, double>> fluxes;  ///< Computed (only when needed) heat fluxes on our own mesh
 """, """    DataVector<Vec<2, double>> fluxes;  ///< Computed (only when needed) heat fluxes on our own mesh
 
     std::shared_ptr<plaskfem::Context> cuda;  ///< Device context, exists only for algorithm 'cuda'
 
-    /// Node of the masked mesh -> node i0 * n1 + i1 of plane 0 of the one-layer brick mesh the device library works on
+    /// The 2-D mesh as a brick mesh of one element layer (index bookkeeping of the embedding)
+    plaskfem::Embedding2D cudaEmbedding;
+
+    /// Node of the masked mesh -> node of plane 0 of the brick mesh
     std::vector<size_t> cudaNode;
 
-    /// Create the device context: the 2-D mesh as a brick mesh of one element layer, (material, thickness) ids, thermk(T) tables
+    /// Create the device context: embedded mesh, radial weights, (material, thickness) ids, thermk(T) tables
     void setupCuda();
 
     /// The nonlinear loop of compute() on the device
@@ -346,11 +339,6 @@ edit(F, """    DataVector<Vec<2, double>> fluxes;  ///< Computed (only when need
 """)
 
 F = "solvers/thermal/static/therm2d.cpp"
-edit(F, """#include "therm2d.hpp"
-""", """#include "therm2d.hpp"
-
-#include <plaskfem_cuda.hpp>
-""")
 edit(F, """            if (idx != RectangularMaskedMesh2D::Element::UNKNOWN_ELEMENT_INDEX)
                 thickness[idx] = h;
         }
@@ -377,45 +365,41 @@ void ThermalFem2DSolver<Geometry2DType>::setupCuda() {
     try {
         cuda.reset(new plaskfem::Context(0, this->getId()));
         // The library has no 2-D kernels: a brick mesh with ONE element layer along a dummy axis and z-invariant data gives, on each
-        // of its two node planes, 0.5e-6 * d times the 4-node rectangle operator and load of setMatrix (INTEGRATION.md 9).
-        const size_t n0 = this->mesh->axis[0]->size(), n1 = this->mesh->axis[1]->size();
-        plaskfem::Mesh fm;
-        fm.axis[0] = {0., 1.};
-        for (size_t i = 0; i != n0; ++i) fm.axis[1].push_back(this->mesh->axis[0]->at(i));
-        for (size_t i = 0; i != n1; ++i) fm.axis[2].push_back(this->mesh->axis[1]->at(i));
-        fm.order = plaskfem::ORDER_012;   // node (0, i0, i1) = i0 * n1 + i1, element (0, i0, i1) = i0 * (n1 - 1) + i1
-        cuda->set_mesh(fm);
-        if (std::is_same<Geometry2DType, Geometry2DCylindrical>::value) {
-            std::vector<double> rmid(n0 - 1);   // every element matrix and load carries midpoint.rad_r() (setMatrix of the cylindrical solver)
-            for (size_t i = 0; i + 1 < n0; ++i) rmid[i] = 0.5 * (this->mesh->axis[0]->at(i) + this->mesh->axis[0]->at(i + 1));
-            cuda->set_axis_weight(1, rmid);
-        }
+        // of its two node planes, 0.5e-6 * d times the 4-node rectangle operator, load and capacity of setMatrix (INTEGRATION.md 9).
+        std::vector<double> x, y;
+        for (size_t i = 0; i != this->mesh->axis[0]->size(); ++i) x.push_back(this->mesh->axis[0]->at(i));
+        for (size_t i = 0; i != this->mesh->axis[1]->size(); ++i) y.push_back(this->mesh->axis[1]->at(i));
+        cudaEmbedding = plaskfem::Embedding2D(x, y);
+        const plaskfem::Embedding2D& emb = cudaEmbedding;
+        cuda->set_mesh(emb.mesh);
+        // every element matrix and load of the cylindrical solver carries midpoint.rad_r()
+        if (std::is_same<Geometry2DType, Geometry2DCylindrical>::value) cuda->set_axis_weight(1, emb.radial_weights());
 
-        const size_t nfull = (n0 - 1) * (n1 - 1);
+        const size_t nfull = emb.elements();
         std::vector<shared_ptr<Material>> materials(nfull);
         std::vector<const Material*> key(nfull, nullptr);
         std::vector<double> thick(nfull, 0.);
         std::vector<uint8_t> included(nfull, 0);
-        cudaNode.assign(this->maskedMesh->size(), 0);
+        cudaNode.assign(this->maskedMesh->size(), 0);   // node of the masked mesh -> node of plane 0, whatever the mesh's iteration order
         for (auto elem: this->maskedMesh->elements()) {
-            const size_t i0 = elem.getIndex0(), i1 = elem.getIndex1(), e = i0 * (n1 - 1) + i1;
+            const size_t i0 = elem.getIndex0(), i1 = elem.getIndex1(), e = emb.elem(i0, i1);
             materials[e] = this->geometry->getMaterial(elem.getMidpoint());
             key[e] = materials[e].get();
             thick[e] = thickness[elem.getIndex()];
             included[e] = 1;
-            cudaNode[elem.getLoLoIndex()] = i0 * n1 + i1;
-            cudaNode[elem.getUpLoIndex()] = (i0 + 1) * n1 + i1;
-            cudaNode[elem.getLoUpIndex()] = i0 * n1 + i1 + 1;
-            cudaNode[elem.getUpUpIndex()] = (i0 + 1) * n1 + i1 + 1;
+            cudaNode[elem.getLoLoIndex()] = emb.node(i0, i1);
+            cudaNode[elem.getUpLoIndex()] = emb.node(i0 + 1, i1);
+            cudaNode[elem.getLoUpIndex()] = emb.node(i0, i1 + 1);
+            cudaNode[elem.getUpUpIndex()] = emb.node(i0 + 1, i1 + 1);
         }
         std::vector<size_t> reps;
         std::vector<uint32_t> ids = plaskfem::material_ids(key, thick, &reps);
         plaskfem::Tables tables = plaskfem::sample_tables(reps.size(), [&](uint32_t id, double T) {
-            if (!materials[reps[id]]) return std::make_pair(0., 0.);
+            if (!materials[reps[id]]) return std::make_pair(1., 1.);
             auto k = materials[reps[id]]->thermk(T, thick[reps[id]]);
             return std::make_pair(k.c00, k.c11);
         });
-        if (!this->maskedMesh->full()) ids = plaskfem::MaskedNumbering(fm, included).mark_excluded(ids);
+        if (!this->maskedMesh->full()) ids = plaskfem::MaskedNumbering(emb.mesh, included).mark_excluded(ids);
         cuda->set_materials(ids, tables);
         cuda->fill_field(inittemp);
     } catch (const plaskfem::NoDevice& err) {
@@ -468,32 +452,33 @@ double ThermalFem2DSolver<Geometry2DType>::computeCuda(int loops,
 {
     if (!cuda) setupCuda();
     try {
-        const size_t n0 = this->mesh->axis[0]->size(), n1 = this->mesh->axis[1]->size();
-        const size_t plane = n0 * n1, nfull = 2 * plane;   // the two node planes of the brick mesh hold the same field
+        const plaskfem::Embedding2D& emb = cudaEmbedding;
 
-        // Edge conditions of the 2nd / 3rd kind and radiation (setBoundaries + the lambdas of setMatrix): per-node getValue() arrays
-        // on plane 0, flattened by the library in its 2-D mode (pfem_boundary::mode2d: 1 Cartesian, 2 cylindrical)
-        plaskfem::NodeConditions<1> hf;
-        plaskfem::NodeConditions<2> cv, rd;
-        for (auto cond: bheatflux) for (auto r: cond.place) hf.add_node(nfull, cudaNode[r], {cond.value});
-        for (auto cond: bconvection) for (auto r: cond.place) cv.add_node(nfull, cudaNode[r], {cond.value.coeff, cond.value.ambient});
-        for (auto cond: bradiation) for (auto r: cond.place) rd.add_node(nfull, cudaNode[r], {cond.value.emissivity, cond.value.ambient});
-        cuda->set_boundary(hf, cv, rd, /*verbatim=*/true, std::is_same<Geometry2DType, Geometry2DCylindrical>::value ? 2 : 1);
-
-        plaskfem::Dirichlet bc;                                   // application order of matrix.hpp:111-118, on both planes
-        for (auto cond: btemperature)
-            for (auto r: cond.place) { bc.add_node(cudaNode[r], cond.value); bc.add_node(cudaNode[r] + plane, cond.value); }
+        plaskfem::Dirichlet bc;                                   // application order of matrix.hpp:111-118, on both node planes
+        for (auto cond: btemperature) for (auto r: cond.place) emb.add_dirichlet(bc, cudaNode[r], cond.value);
         cuda->set_dirichlet(bc);
 
         auto heats = inHeat(this->maskedMesh->getElementMesh());
-        std::vector<double> heat((n0 - 1) * (n1 - 1), 0.);
-        for (auto elem: this->maskedMesh->elements()) heat[elem.getIndex0() * (n1 - 1) + elem.getIndex1()] = heats[elem.getIndex()];
+        std::vector<double> heat(emb.elements(), 0.);
+        for (auto elem: this->maskedMesh->elements()) heat[emb.elem(elem.getIndex0(), elem.getIndex1())] = heats[elem.getIndex()];
         cuda->set_source(heat.data());
 
         temperatures = temperatures.claim();
-        std::vector<double> field(nfull, 0.);
-        for (size_t i = 0; i != temperatures.size(); ++i) field[cudaNode[i]] = field[cudaNode[i] + plane] = temperatures[i];
+        std::vector<double> plane0(emb.plane(), 0.);
+        for (size_t i = 0; i != temperatures.size(); ++i) plane0[cudaNode[i]] = temperatures[i];
+        std::vector<double> field = emb.lift(plane0.data());
         cuda->set_field(field.data());                            // warm start, like iterative_matrix.hpp:205-209
+
+        // Edge conditions of the 2nd / 3rd kind and radiation (setBoundaries + the lambdas of setMatrix): per-node getValue() arrays
+        // on plane 0, flattened by the library in its 2-D mode (pfem_boundary::mode2d: 1 Cartesian, 2 cylindrical)
+        const size_t nbrick = 2 * emb.plane();
+        plaskfem::NodeConditions<1> hf;
+        plaskfem::NodeConditions<2> cv, rd;
+        for (auto cond: bheatflux) for (auto r: cond.place) hf.add_node(nbrick, cudaNode[r], {cond.value});
+        for (auto cond: bconvection) for (auto r: cond.place) cv.add_node(nbrick, cudaNode[r], {cond.value.coeff, cond.value.ambient});
+        for (auto cond: bradiation) for (auto r: cond.place) rd.add_node(nbrick, cudaNode[r], {cond.value.emissivity, cond.value.ambient});
+        cuda->set_boundary(hf, cv, rd, /*verbatim=*/true,
+                           plaskfem::Embedding2D::boundary_mode(std::is_same<Geometry2DType, Geometry2DCylindrical>::value));
 
         plaskfem::IterParams ip{this->iter_params.maxit, this->iter_params.maxerr,
                                 plaskfem::IterParams::NoConvergenceBehavior(int(this->iter_params.no_convergence_behavior))};
@@ -523,6 +508,199 @@ double ThermalFem2DSolver<Geometry2DType>::computeCuda(int loops,
 template<typename Geometry2DType>
 void ThermalFem2DSolver<Geometry2DType>::saveHeatFluxes()
 {""")
+
+# ---------------------------------------------------------------- thermal.dynamic Dynamic2D / DynamicCyl
+F = "solvers/thermal/dynamic/femT2d.hpp"
+edit(F, """#include <plask/common/fem.hpp>
+
+namespace plask { namespace thermal { namespace dynamic {
+
+/**
+ * Solver performing calculations in 2D Cartesian or Cylindrical space using finite element method
+ */
+template<typename Geometry2DType>""", """#include <plask/common/fem.hpp>
+
+#include <plaskfem_cuda.hpp>   // host adapter of libplaskfem_cuda.so (algorithm 'cuda'): header-only, plain C ABI underneath
+
+namespace plask { namespace thermal { namespace dynamic {
+
+/**
+ * Solver performing calculations in 2D Cartesian or Cylindrical space using finite element method
+ */
+template<typename Geometry2DType>""")
+edit(F, """    DataVector<Vec<2,double>> fluxes;           ///< Computed (only when needed) heat fluxes on our own mesh
+""", """    DataVector<Vec<2,double>> fluxes;           ///< Computed (only when needed) heat fluxes on our own mesh
+
+    std::shared_ptr<plaskfem::Context> cuda;  ///< Device context, exists only for algorithm 'cuda'
+
+    /// The 2-D mesh as a brick mesh of one element layer (index bookkeeping of the embedding)
+    plaskfem::Embedding2D cudaEmbedding;
+
+    /// Node of the masked mesh -> node of plane 0 of the brick mesh
+    std::vector<size_t> cudaNode;
+
+    /// Create the device context: embedded mesh, radial weights, (material, thickness) ids, thermk(T) and cp(T)*dens(T) tables
+    void setupCuda();
+
+    /// The time loop of compute() on the device (pfem_solve_dynamic)
+    double computeCuda(double time, const BoundaryConditionsWithMesh<RectangularMesh<2>::Boundary,double>& btemperature);
+""")
+
+F = "solvers/thermal/dynamic/femT2d.cpp"
+edit(F, """            if (idx != RectangularMaskedMesh2D::Element::UNKNOWN_ELEMENT_INDEX)
+                thickness[idx] = h;
+        }
+    }
+}
+
+
+template<typename Geometry2DType> void DynamicThermalFem2DSolver<Geometry2DType>::onInvalidate() {
+    temperatures.reset();
+    fluxes.reset();
+}
+""", """            if (idx != RectangularMaskedMesh2D::Element::UNKNOWN_ELEMENT_INDEX)
+                thickness[idx] = h;
+        }
+    }
+
+    if (this->algorithm == ALGORITHM_CUDA) setupCuda();
+}
+
+
+template<typename Geometry2DType>
+void DynamicThermalFem2DSolver<Geometry2DType>::setupCuda() {
+    try {
+        cuda.reset(new plaskfem::Context(0, this->getId()));
+        // The library has no 2-D kernels: a brick mesh with ONE element layer along a dummy axis and z-invariant data gives, on each
+        // of its two node planes, 0.5e-6 * d times the 4-node rectangle operator, load and capacity of setMatrix (INTEGRATION.md 9).
+        std::vector<double> x, y;
+        for (size_t i = 0; i != this->mesh->axis[0]->size(); ++i) x.push_back(this->mesh->axis[0]->at(i));
+        for (size_t i = 0; i != this->mesh->axis[1]->size(); ++i) y.push_back(this->mesh->axis[1]->at(i));
+        cudaEmbedding = plaskfem::Embedding2D(x, y);
+        const plaskfem::Embedding2D& emb = cudaEmbedding;
+        cuda->set_mesh(emb.mesh);
+        // every element matrix and load of the cylindrical solver carries midpoint.rad_r()
+        if (std::is_same<Geometry2DType, Geometry2DCylindrical>::value) cuda->set_axis_weight(1, emb.radial_weights());
+
+        const size_t nfull = emb.elements();
+        std::vector<shared_ptr<Material>> materials(nfull);
+        std::vector<const Material*> key(nfull, nullptr);
+        std::vector<double> thick(nfull, 0.);
+        std::vector<uint8_t> included(nfull, 0);
+        cudaNode.assign(this->maskedMesh->size(), 0);   // node of the masked mesh -> node of plane 0, whatever the mesh's iteration order
+        for (auto elem: this->maskedMesh->elements()) {
+            const size_t i0 = elem.getIndex0(), i1 = elem.getIndex1(), e = emb.elem(i0, i1);
+            materials[e] = this->geometry->getMaterial(elem.getMidpoint());
+            key[e] = materials[e].get();
+            thick[e] = thickness[elem.getIndex()];
+            included[e] = 1;
+            cudaNode[elem.getLoLoIndex()] = emb.node(i0, i1);
+            cudaNode[elem.getUpLoIndex()] = emb.node(i0 + 1, i1);
+            cudaNode[elem.getLoUpIndex()] = emb.node(i0, i1 + 1);
+            cudaNode[elem.getUpUpIndex()] = emb.node(i0 + 1, i1 + 1);
+        }
+        std::vector<size_t> reps;
+        std::vector<uint32_t> ids = plaskfem::material_ids(key, thick, &reps);
+        plaskfem::Tables tables = plaskfem::sample_tables(reps.size(), [&](uint32_t id, double T) {
+            if (!materials[reps[id]]) return std::make_pair(1., 1.);
+            auto k = materials[reps[id]]->thermk(T, thick[reps[id]]);
+            return std::make_pair(k.c00, k.c11);
+        });
+        if (!this->maskedMesh->full()) ids = plaskfem::MaskedNumbering(emb.mesh, included).mark_excluded(ids);
+        cuda->set_materials(ids, tables);
+        // one more table per id: cp(T) * dens(T) of the element capacity (setMatrix: cp * dens * 0.25e-12 * w * h / timestep / 1e-9)
+        std::vector<double> cpdens(size_t(tables.nmat) * tables.nT, 1.);
+        for (uint32_t id = 0; id != tables.nmat; ++id)
+            if (materials[reps[id]])
+                for (uint32_t i = 0; i != tables.nT; ++i) {
+                    double T = tables.T0 + i * tables.dT;
+                    cpdens[size_t(id) * tables.nT + i] = materials[reps[id]]->cp(T) * materials[reps[id]]->dens(T);
+                }
+        cuda->set_capacity(tables, cpdens);
+        cuda->fill_field(inittemp);
+    } catch (const plaskfem::NoDevice& err) {
+        throw ComputationError(this->getId(), "algorithm 'cuda' has no CPU fallback: {}", err.what());
+    } catch (const plaskfem::BadInput& err) {
+        throw BadInput(this->getId(), "{}", err.what());
+    }
+}
+
+
+template<typename Geometry2DType>
+double DynamicThermalFem2DSolver<Geometry2DType>::computeCuda(double time,
+                   const BoundaryConditionsWithMesh<RectangularMesh<2>::Boundary,double>& btemperature)
+{
+    if (!cuda) setupCuda();
+    try {
+        const plaskfem::Embedding2D& emb = cudaEmbedding;
+
+        plaskfem::Dirichlet bc;                                   // application order of matrix.hpp:111-118, on both node planes
+        for (auto cond: btemperature) for (auto r: cond.place) emb.add_dirichlet(bc, cudaNode[r], cond.value);
+        cuda->set_dirichlet(bc);
+
+        auto heats = inHeat(this->maskedMesh->getElementMesh());
+        std::vector<double> heat(emb.elements(), 0.);
+        for (auto elem: this->maskedMesh->elements()) heat[emb.elem(elem.getIndex0(), elem.getIndex1())] = heats[elem.getIndex()];
+        cuda->set_source(heat.data());
+
+        temperatures = temperatures.claim();
+        std::vector<double> plane0(emb.plane(), 0.);
+        for (size_t i = 0; i != temperatures.size(); ++i) plane0[cudaNode[i]] = temperatures[i];
+        std::vector<double> field = emb.lift(plane0.data());
+        cuda->set_field(field.data());                            // warm start, like iterative_matrix.hpp:205-209
+
+        plaskfem::IterParams ip{this->iter_params.maxit, this->iter_params.maxerr,
+                                plaskfem::IterParams::NoConvergenceBehavior(int(this->iter_params.no_convergence_behavior))};
+        // jac as named, every other choice -> line-Jacobi (the multilevel preconditioner does not take the capacity diagonal yet)
+        ip.preconditioner = this->iter_params.preconditioner == IterativeMatrixParams::PRECOND_JAC ? plaskfem::IterParams::PRECOND_JAC :
+                                                                                                      plaskfem::IterParams::PRECOND_LJAC;
+        // the corrected theta scheme (plaskfem_cuda.h): Dirichlet rows keep their values (setMatrix eliminates them in A and F only)
+        auto result = cuda->solve_dynamic(ip, time, timestep, methodparam, lumping, int(rebuildfreq), int(logfreq), elapstime,
+                                          [this](int level, const std::string& msg) { this->writelog(LogLevel(level), msg); });
+        this->iter_params.converged = ip.converged; this->iter_params.iters = ip.iters; this->iter_params.err = ip.err;
+
+        cuda->get_field(field.data());
+        for (size_t i = 0; i != temperatures.size(); ++i) temperatures[i] = field[cudaNode[i]];
+        maxT = result.maxT;
+    } catch (const plaskfem::BadInput& err) {
+        throw BadInput(this->getId(), "{}", err.what());
+    } catch (const std::runtime_error& err) {
+        throw ComputationError(this->getId(), "{}", err.what());
+    }
+
+    outTemperature.fireChanged();
+    outHeatFlux.fireChanged();
+
+    return 0.;
+}
+
+
+template<typename Geometry2DType> void DynamicThermalFem2DSolver<Geometry2DType>::onInvalidate() {
+    temperatures.reset();
+    fluxes.reset();
+    cuda.reset();
+    cudaNode.clear();
+}
+""")
+edit(F, """    auto btemperature = temperature_boundary(this->maskedMesh, this->geometry);
+
+    size_t size = this->maskedMesh->size();
+
+    std::unique_ptr<FemMatrix> pA(this->getMatrix());
+    FemMatrix& A = *pA.get();
+    std::unique_ptr<FemMatrix> pB(this->getMatrix());
+    FemMatrix& B = *pB.get();
+""", """    auto btemperature = temperature_boundary(this->maskedMesh, this->geometry);
+
+    if (this->algorithm == ALGORITHM_CUDA) return computeCuda(time, btemperature);
+
+    size_t size = this->maskedMesh->size();
+
+    std::unique_ptr<FemMatrix> pA(this->getMatrix());
+    FemMatrix& A = *pA.get();
+    std::unique_ptr<FemMatrix> pB(this->getMatrix());
+    FemMatrix& B = *pB.get();
+""")
 
 # ---------------------------------------------------------------- electrical.shockley Shockley3D
 F = "solvers/electrical/shockley/electr3d.hpp"

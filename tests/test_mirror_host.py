@@ -53,3 +53,33 @@ def test_masked_nodes_match_the_masked_mesh(order):
     s.empty_elements = "sometimes"
     with pytest.raises(L.BadInput):
         s._elem_materials()
+
+
+@pytest.mark.parametrize("cyl", [False, True])
+def test_2d_mirror_integrals_vs_oracle2d(cyl):
+    """integrateCurrent / getTotalHeat / getTotalEnergy / getCapacitance of the 2-D solvers (electr2d.cpp:466-649) as the mirror computes
+    them from downloaded fields — here the oracle's fields are injected, no device is involved — and the bookkeeping of embed()"""
+    from helpers import oracle_shockley2d, shockley2d_reference_problem
+    from plask_b200.solvers2d import Shockley2D, ShockleyCyl, embed
+    p2 = shockley2d_reference_problem(cyl, nx=3, ny=2)
+    o = oracle_shockley2d(p2)
+    o.compute(30)
+    e = (ShockleyCyl if cyl else Shockley2D)("host2d")
+    e._p2 = p2
+    e._problem = embed(p2)
+    e.outVoltage = lambda mesh=None: o.potentials
+    e.outCurrentDensity = lambda: o.currents
+    e.outHeat = lambda: o.heat_densities()
+    vindex = int(np.nonzero(np.asarray(p2.elem_junc).reshape(p2.n[0] - 1, p2.n[1] - 1).any(axis=0))[0].min())   # bottom row of the junction
+    assert e.integrate_current(vindex, True) == pytest.approx(o.integrate_current(vindex, True), rel=1e-12)
+    assert e.integrate_current(vindex, False) == pytest.approx(o.integrate_current(vindex, False), rel=1e-12)
+    assert e.get_total_heat() == pytest.approx(o.get_total_heat(), rel=1e-12)
+    assert e.get_total_energy() == pytest.approx(o.get_total_energy(), rel=1e-12)
+    assert e.get_capacitance() == pytest.approx(o.get_capacitance(), rel=1e-12)
+    # the embedding: plane 0 keeps the 2-D numbering, plane 1 follows at offset N, every condition of the first kind on both planes
+    p3 = e._problem
+    assert p3.n == (2, p2.n[0], p2.n[1]) and p3.N == 2 * p2.N and p3.E == p2.E
+    assert np.array_equal(p3.bc_nodes[:len(p2.bc_nodes)], p2.bc_nodes) and np.array_equal(p3.bc_nodes[len(p2.bc_nodes):], p2.bc_nodes + p2.N)
+    assert np.array_equal(p3.elem_mat, p2.elem_mat) and np.array_equal(p3.elem_junc, p2.elem_junc)
+    with pytest.raises(L.BadInput):
+        (Shockley2D if cyl else ShockleyCyl)("wrong").problem = p2       # Cartesian problem on the cylindrical solver and vice versa

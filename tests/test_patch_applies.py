@@ -22,6 +22,7 @@ def test_patch_touches_the_documented_files():
             "solvers/thermal/static/therm3d.hpp", "solvers/thermal/static/therm3d.cpp",
             "solvers/thermal/static/therm2d.hpp", "solvers/thermal/static/therm2d.cpp",
             "solvers/electrical/shockley/electr3d.hpp", "solvers/electrical/shockley/electr3d.cpp",
+            "solvers/electrical/shockley/electr2d.hpp", "solvers/electrical/shockley/electr2d.cpp",
             "solvers/electrical/shockley/beta.hpp", "solvers/electrical/shockley/python/electr_python.cpp",
             "solvers/thermal/static/CMakeLists.txt", "solvers/electrical/shockley/CMakeLists.txt",
             "solvers/thermal/dynamic/femT3d.hpp", "solvers/thermal/dynamic/femT3d.cpp", "solvers/thermal/dynamic/CMakeLists.txt",
@@ -53,6 +54,12 @@ def test_patch_applies_to_the_reference(tmp_path):
     d2 = open(tmp_path / "solvers/thermal/dynamic/femT2d.cpp").read()
     assert "if (this->algorithm == ALGORITHM_CUDA) return computeCuda(time, btemperature);" in d2 and "cuda->set_capacity(tables, cpdens);" in d2
     assert "emb.add_dirichlet(bc, cudaNode[r], cond.value);" in d2
+    e2h = open(tmp_path / "solvers/electrical/shockley/electr2d.hpp").read()
+    # BetaSolver<Geometry2D...> overrides shockleyParameters: its 2-D base must declare the virtual as well
+    assert "virtual bool shockleyParameters(" in e2h and "virtual bool shockleyParameters(" in open(tmp_path / "solvers/electrical/shockley/electr3d.hpp").read()
+    e2 = open(tmp_path / "solvers/electrical/shockley/electr2d.cpp").read()
+    assert "if (this->algorithm == ALGORITHM_CUDA) return computeCuda(loops, vconst);" in e2
+    assert "pfem_junction{act.bottom, act.top, act.left, act.right, 0, 1, 1, act.offset, act.height}" in e2
     dif = open(tmp_path / "solvers/electrical/diffusion/diffusion3d.cpp").read()
     assert "computeCuda(loops, act, active, A, B, C, D, J, nmodes, Ps, nrs);" in dif and "#include <plaskdiff_cuda.hpp>" in dif
 

@@ -10,7 +10,7 @@ What the patch does (INTEGRATION.md explains every hunk):
     branch that hands the whole nonlinear loop to the library (include/plaskfem_cuda.hpp)
   * BetaSolver / the Python Shockley class expose beta(T), js(T) per junction through one virtual, so that the host can
     evaluate them at the mid-plane temperature of every junction column (electr3d.cpp:261-262)
-  * ThermalFem2DSolver / DynamicThermalFem2DSolver <Cartesian / Cylindrical>: the same through the one-layer embedding of the 2-D mesh
+  * ThermalFem2DSolver / DynamicThermalFem2DSolver / ElectricalFem2DSolver <Cartesian / Cylindrical>: the same through the one-layer embedding of the 2-D mesh
     (plaskfem::Embedding2D, radial element weights, the edge conditions of the 2nd / 3rd kind and radiation in the library's 2-D mode)
   * DynamicThermalFem3DSolver: the same for the time loop of compute(time) (pfem_solve_dynamic, corrected update)
   * Diffusion3DSolver: compute() hands the whole loop of one active region to pdiff_compute (include/plaskdiff_cuda.hpp)
@@ -975,6 +975,238 @@ edit(F, """void ElectricalFem3DSolver::saveHeatDensity() {""", """double Electri
 }
 
 void ElectricalFem3DSolver::saveHeatDensity() {""")
+
+# ---------------------------------------------------------------- electrical.shockley Shockley2D / ShockleyCyl (INTEGRATION.md 9)
+# BetaSolver<GeometryT> (beta.hpp) derives from ElectricalFem2DSolver<GeometryT> for the 2-D geometries: the shockleyParameters
+# virtual it overrides must exist in that base too.
+F = "solvers/electrical/shockley/electr2d.hpp"
+edit(F, """#include "common.hpp"
+""", """#include "common.hpp"
+
+#include <plaskfem_cuda.hpp>   // host adapter of libplaskfem_cuda.so (algorithm 'cuda'): header-only, plain C ABI underneath
+""")
+edit(F, """    virtual Tensor2<double> activeCond(size_t n, double U, double jy, double T) = 0;
+""", """    virtual Tensor2<double> activeCond(size_t n, double U, double jy, double T) = 0;
+
+    /** Parameters of the Shockley law of junction \\p n at temperature \\p T, for solvers whose activeCond is
+     *  10 |jy| beta h / ln(1e7 |jy| / js + 1) (BetaSolver and its Python subclass).  Algorithm 'cuda' evaluates that law
+     *  on the device and therefore needs the parameters instead of the callback.
+     *  \\return false if this solver has another junction model
+     */
+    virtual bool shockleyParameters(size_t PLASK_UNUSED(n), double PLASK_UNUSED(T), double& PLASK_UNUSED(beta),
+                                    double& PLASK_UNUSED(js)) const { return false; }
+
+    std::shared_ptr<plaskfem::Context> cuda;  ///< Device context, exists only for algorithm 'cuda'
+
+    /// The 2-D mesh as a brick mesh of one element layer (index bookkeeping of the embedding)
+    plaskfem::Embedding2D cudaEmbedding;
+
+    /// Node of the masked mesh -> node of plane 0 of the brick mesh
+    std::vector<size_t> cudaNode;
+
+    /// Create the device context: embedded mesh, radial weights, the cond(T) tables of the materials
+    void setupCuda();
+
+    /// The nonlinear loop of compute() on the device
+    double computeCuda(unsigned loops, const BoundaryConditionsWithMesh<RectangularMesh<2>::Boundary, double>& bvoltage);
+""")
+
+F = "solvers/electrical/shockley/electr2d.cpp"
+edit(F, """    potentials.reset(this->maskedMesh->size(), 0.);
+    currents.reset(this->maskedMesh->getElementsCount(), vec(0., 0.));
+    conds.reset(this->maskedMesh->getElementsCount());
+}
+
+template <typename Geometry2DType> void ElectricalFem2DSolver<Geometry2DType>::onInvalidate() {
+    conds.reset();
+    potentials.reset();
+    currents.reset();
+    heats.reset();
+    junction_conductivity.reset(1, default_junction_conductivity);
+}
+""", """    potentials.reset(this->maskedMesh->size(), 0.);
+    currents.reset(this->maskedMesh->getElementsCount(), vec(0., 0.));
+    conds.reset(this->maskedMesh->getElementsCount());
+    if (this->algorithm == ALGORITHM_CUDA) setupCuda();
+}
+
+template <typename Geometry2DType> void ElectricalFem2DSolver<Geometry2DType>::onInvalidate() {
+    conds.reset();
+    potentials.reset();
+    currents.reset();
+    heats.reset();
+    junction_conductivity.reset(1, default_junction_conductivity);
+    cuda.reset();
+    cudaNode.clear();
+}
+
+template <typename Geometry2DType> void ElectricalFem2DSolver<Geometry2DType>::setupCuda() {
+    try {
+        cuda.reset(new plaskfem::Context(0, this->getId()));
+        // one element layer along a dummy axis: on each node plane the brick operator is 0.5e-6 * d times the rectangle operator of
+        // setMatrix, currents and Joule heat are element gradients and come out identical (INTEGRATION.md 9)
+        std::vector<double> x, y;
+        for (size_t i = 0; i != this->mesh->axis[0]->size(); ++i) x.push_back(this->mesh->axis[0]->at(i));
+        for (size_t i = 0; i != this->mesh->axis[1]->size(); ++i) y.push_back(this->mesh->axis[1]->at(i));
+        cudaEmbedding = plaskfem::Embedding2D(x, y);
+        const plaskfem::Embedding2D& emb = cudaEmbedding;
+        cuda->set_mesh(emb.mesh);
+        // setLocalMatrix of the cylindrical solver multiplies every element matrix by midpoint.rad_r()
+        if (std::is_same<Geometry2DType, Geometry2DCylindrical>::value) cuda->set_axis_weight(1, emb.radial_weights());
+
+        // cond(T) of every distinct material, sampled on the host (loadConductivities)
+        const size_t nfull = emb.elements();
+        std::vector<shared_ptr<Material>> materials(nfull);
+        std::vector<const Material*> key(nfull, nullptr);
+        std::vector<uint8_t> included(nfull, 0);
+        cudaNode.assign(this->maskedMesh->size(), 0);
+        for (auto elem : this->maskedMesh->elements()) {
+            const size_t i0 = elem.getIndex0(), i1 = elem.getIndex1(), e = emb.elem(i0, i1);
+            materials[e] = this->geometry->getMaterial(elem.getMidpoint());
+            key[e] = materials[e].get();
+            included[e] = 1;
+            cudaNode[elem.getLoLoIndex()] = emb.node(i0, i1);
+            cudaNode[elem.getUpLoIndex()] = emb.node(i0 + 1, i1);
+            cudaNode[elem.getLoUpIndex()] = emb.node(i0, i1 + 1);
+            cudaNode[elem.getUpUpIndex()] = emb.node(i0 + 1, i1 + 1);
+        }
+        std::vector<size_t> reps;
+        std::vector<uint32_t> ids = plaskfem::material_ids(key, std::vector<double>(), &reps);
+        plaskfem::Tables tables = plaskfem::sample_tables(reps.size(), [&](uint32_t id, double T) {
+            if (!materials[reps[id]]) return std::make_pair(0., 0.);
+            auto s = materials[reps[id]]->cond(T);
+            return std::make_pair(s.c00, s.c11);
+        });
+        if (!this->maskedMesh->full()) ids = plaskfem::MaskedNumbering(emb.mesh, included).mark_excluded(ids);
+        cuda->set_materials(ids, tables);
+        cuda->fill_field(0.);
+    } catch (const plaskfem::NoDevice& err) {
+        throw ComputationError(this->getId(), "algorithm 'cuda' has no CPU fallback: {}", err.what());
+    } catch (const plaskfem::BadInput& err) {
+        throw BadInput(this->getId(), "{}", err.what());
+    }
+}
+""")
+edit(F, """    this->writelog(LOG_INFO, "Running electrical calculations");
+
+    unsigned loop = 0;
+
+    std::unique_ptr<FemMatrix> pA(this->getMatrix());
+    FemMatrix& A = *pA.get();
+
+    double err = 0.;
+    toterr = 0.;
+""", """    this->writelog(LOG_INFO, "Running electrical calculations");
+
+    if (this->algorithm == ALGORITHM_CUDA) return computeCuda(loops, vconst);
+
+    unsigned loop = 0;
+
+    std::unique_ptr<FemMatrix> pA(this->getMatrix());
+    FemMatrix& A = *pA.get();
+
+    double err = 0.;
+    toterr = 0.;
+""")
+edit(F, """template <typename Geometry2DType> void ElectricalFem2DSolver<Geometry2DType>::saveHeatDensities() {""",
+     """template <typename Geometry2DType>
+double ElectricalFem2DSolver<Geometry2DType>::computeCuda(unsigned loops,
+                                                          const BoundaryConditionsWithMesh<RectangularMesh<2>::Boundary, double>& bvoltage) {
+    if (!cuda) setupCuda();
+    try {
+        const plaskfem::Embedding2D& emb = cudaEmbedding;
+        const size_t efull = emb.elements();
+
+        // what loadConductivities and saveHeatDensities read from the geometry, flattened
+        std::vector<uint32_t> elem_junc(efull, 0);
+        std::vector<uint8_t> elem_role(efull, 0), noheat(efull, 0);
+        std::vector<double> Te(efull, 300.);
+        auto temperature = inTemperature(this->maskedMesh->getElementMesh());
+        for (auto el : this->maskedMesh->elements()) {
+            const size_t e = emb.elem(el.getIndex0(), el.getIndex1());
+            auto mid = el.getMidpoint();
+            auto roles = this->geometry->getRolesAt(mid);
+            elem_junc[e] = uint32_t(isActive(mid));
+            elem_role[e] = roles.find("p-contact") != roles.end() ? 1 : roles.find("n-contact") != roles.end() ? 2 : 0;
+            noheat[e] = this->geometry->getMaterial(mid)->kind() == Material::EMPTY || roles.find("noheat") != roles.end();
+            Te[e] = temperature[el.getIndex()];
+        }
+        cuda->set_elem_temperature(Te.data());
+        cuda->set_noheat(noheat);
+
+        // junctions: a 2-D Active is a pfem_junction one element deep along the dummy axis (back = 0, front = 1, ld = 1), so that the
+        // library's table index offset + ld * tran + lon is the solver's own act.offset + index0 (loadConductivities) and
+        // junction_conductivity travels as it is; beta(T), js(T) at the temperature of the mid-row element of the column (setMatrix)
+        std::vector<pfem_junction> junctions(active.size());
+        const size_t ncol = junction_conductivity.size();
+        std::vector<double> beta_col(ncol, 1.), js_col(ncol, 1.);
+        for (size_t n = 0; n != active.size(); ++n) {
+            const Active& act = active[n];
+            junctions[n] = pfem_junction{act.bottom, act.top, act.left, act.right, 0, 1, 1, act.offset, act.height};
+            const size_t mid = (act.bottom + act.top) / 2;
+            for (size_t t = act.left; t != act.right; ++t) {
+                const size_t tidx = this->maskedMesh->element(t, mid).getIndex();
+                const double T = tidx != RectangularMaskedMesh2D::Element::UNKNOWN_ELEMENT_INDEX ? temperature[tidx] : 300.;
+                const size_t col = act.offset + t;
+                if (!shockleyParameters(n, T, beta_col[col], js_col[col]))
+                    throw BadInput(this->getId(), "algorithm 'cuda' needs a Shockley junction (beta, js); this solver has a custom junction model");
+            }
+        }
+        std::vector<double> jcond(2 * ncol);
+        for (size_t i = 0; i != ncol; ++i) { jcond[2 * i] = junction_conductivity[i].c00; jcond[2 * i + 1] = junction_conductivity[i].c11; }
+        cuda->set_junctions(junctions, elem_junc, elem_role, pcond, ncond, jcond, beta_col, js_col, convergence == CONVERGENCE_STABLE);
+
+        plaskfem::Dirichlet bc;                                   // application order of matrix.hpp:111-118, on both node planes
+        for (auto cond : bvoltage) for (auto r : cond.place) emb.add_dirichlet(bc, cudaNode[r], cond.value);
+        cuda->set_dirichlet(bc);
+        cuda->set_source(nullptr);                                // zero load vector
+
+        potentials = potentials.claim();
+        std::vector<double> plane0(emb.plane(), 0.);
+        for (size_t i = 0; i != potentials.size(); ++i) plane0[cudaNode[i]] = potentials[i];
+        std::vector<double> field = emb.lift(plane0.data());
+        cuda->set_field(field.data());
+
+        plaskfem::IterParams ip{this->iter_params.maxit, this->iter_params.maxerr,
+                                plaskfem::IterParams::NoConvergenceBehavior(int(this->iter_params.no_convergence_behavior))};
+        ip.preconditioner = this->iter_params.preconditioner == IterativeMatrixParams::PRECOND_JAC ? plaskfem::IterParams::PRECOND_JAC :
+                            this->iter_params.preconditioner == IterativeMatrixParams::PRECOND_LJAC ? plaskfem::IterParams::PRECOND_LJAC :
+                                                                                                      plaskfem::IterParams::PRECOND_MLJ;
+        auto result = cuda->solve(false, ip, maxerr, int(loops),
+                                  [this](int level, const std::string& msg) { this->writelog(LogLevel(level), msg); });
+        this->iter_params.converged = ip.converged; this->iter_params.iters = ip.iters; this->iter_params.err = ip.err;
+
+        cuda->get_field(field.data());
+        for (size_t i = 0; i != potentials.size(); ++i) potentials[i] = field[cudaNode[i]];
+        std::vector<double> cur3(3 * efull), cur2(2 * efull), cnd(2 * efull);
+        cuda->get_elem(PFEM_ELEM_CURRENT, cur3.data());
+        emb.elem_vec2(cur3.data(), cur2.data());                  // the longitudinal component is zero
+        cuda->get_elem(PFEM_ELEM_COND, cnd.data());
+        for (auto el : this->maskedMesh->elements()) {
+            const size_t e = emb.elem(el.getIndex0(), el.getIndex1()), i = el.getIndex();
+            currents[i] = vec(cur2[2 * e], cur2[2 * e + 1]);
+            conds[i] = Tensor2<double>(cnd[2 * e], cnd[2 * e + 1]);
+        }
+        cuda->get_junction_cond(jcond.data());                    // saveConductivities happened on the device
+        for (size_t i = 0; i != ncol; ++i) junction_conductivity[i] = Tensor2<double>(jcond[2 * i], jcond[2 * i + 1]);
+        heats.reset();
+        maxcur = vec(result.maxcur[1], result.maxcur[2]);
+        loopno = result.loopno;
+        toterr = result.toterr;
+    } catch (const plaskfem::BadInput& err) {
+        throw BadInput(this->getId(), "{}", err.what());
+    } catch (const std::runtime_error& err) {
+        throw ComputationError(this->getId(), "{}", err.what());
+    }
+
+    outVoltage.fireChanged();
+    outCurrentDensity.fireChanged();
+    outHeat.fireChanged();
+
+    return toterr;
+}
+
+template <typename Geometry2DType> void ElectricalFem2DSolver<Geometry2DType>::saveHeatDensities() {""")
 
 # ---------------------------------------------------------------- thermal.dynamic Dynamic3D
 F = "solvers/thermal/dynamic/femT3d.hpp"

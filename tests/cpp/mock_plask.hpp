@@ -64,6 +64,8 @@ template <typename T> struct DataVector {
     size_t size() const { return v.size(); }
     T& operator[](size_t i) { return v[i]; }
     const T& operator[](size_t i) const { return v[i]; }
+    T* data() { return v.data(); }
+    const T* data() const { return v.data(); }
     DataVector claim() const { return *this; }
     void reset() { v.clear(); }
     void reset(size_t n, const T& x = T()) { v.assign(n, x); }
@@ -98,6 +100,7 @@ template <int D> struct RectangularMesh : MeshD<D> {
 };
 
 struct RectangularMaskedMesh2D : MeshD<2> {
+    static constexpr size_t NOT_INCLUDED = std::numeric_limits<size_t>::max();
     struct Element {
         static constexpr size_t UNKNOWN_ELEMENT_INDEX = std::numeric_limits<size_t>::max();
         size_t i0, i1, idx, n1;
@@ -204,3 +207,50 @@ namespace electrical { namespace shockley {
 }}
 
 }  // namespace plask
+
+// ---- slice of the API used by the Diffusion3DSolver hunks (solvers/electrical/diffusion/diffusion3d.{hpp,cpp}) -------------------
+#include <complex>
+#include <map>
+namespace plask {
+
+typedef std::complex<double> dcomplex;
+using std::real;
+template <typename T> inline Tensor2<T> operator*(double a, const Tensor2<T>& t) { return Tensor2<T>(a * t.c00, a * t.c11); }
+struct InterpolationMethod { enum Value { INTERPOLATION_DEFAULT, INTERPOLATION_LINEAR, INTERPOLATION_SPLINE }; };
+struct Gain { enum EnumType { GAIN, DGDN }; };
+constexpr double inv_hc = 1.0e-9 / (6.62607015e-34 * 299792458.);
+
+struct RectangularMesh2D : RectangularMesh<2> {
+    enum IterationOrder2D { ORDER_10, ORDER_01 };
+    IterationOrder2D getIterationOrder() const { return ORDER_10; }
+};
+struct LateralMaskedModel {
+    static constexpr size_t NOT_INCLUDED = std::numeric_limits<size_t>::max();
+    RectangularMesh2D fullMesh;
+    size_t getElementIndexFromLowIndexes(size_t, size_t) const { return 0; }
+};
+}  // namespace plask
+// the hunk names RectangularMaskedMesh2D::NOT_INCLUDED (plask/mesh/rectangular_masked_common.hpp)
+namespace plask { namespace electrical { namespace diffusion {
+struct SizedMesh { size_t n = 0; size_t size() const { return n; } };
+struct QwMesh2 : SizedMesh { shared_ptr<LateralMaskedModel> lateralMesh = std::make_shared<LateralMaskedModel>(); };
+struct ActiveRegion3D {
+    shared_ptr<QwMesh2> mesh2 = std::make_shared<QwMesh2>();
+    shared_ptr<SizedMesh> emesh2 = std::make_shared<SizedMesh>();
+    DataVector<double> U;
+    std::vector<double> modesP;
+    double QWheight = 0.;
+};
+struct ElementParams3D {
+    double X = 1., Y = 1.;
+    ElementParams3D(const ActiveRegion3D&, size_t) {}
+};
+inline Tensor2<double> integrateBilinear(double, double, const Tensor2<double>*) { return Tensor2<double>(); }
+struct WavelengthReceiverModel { dcomplex operator()(size_t) const { return dcomplex(980., 0.); } };
+struct GainReceiverModel {
+    template <typename MeshPtr> LazyData<Tensor2<double>> operator()(const MeshPtr&, double, InterpolationMethod::Value) const { return LazyData<Tensor2<double>>(); }
+    template <typename MeshPtr> LazyData<Tensor2<double>> operator()(Gain::EnumType, const MeshPtr&, double, InterpolationMethod::Value) const {
+        return LazyData<Tensor2<double>>();
+    }
+};
+}}}  // namespace plask::electrical::diffusion

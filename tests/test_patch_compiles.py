@@ -162,3 +162,33 @@ struct {cls} : public FemSolverWithMaskedMesh<Geometry3D, RectangularMesh<3>> {{
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wno-unused-variable", "-Wno-unused-function", "-I",
                         os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "cpp"), str(gen)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[:6000]
+
+
+def test_added_diffusion3d_code_compiles_against_the_api_model(tmp_path):
+    """Diffusion3DSolver::computeCuda (the loop of one active region handed to pdiff_compute) against include/plaskdiff_cuda.hpp"""
+    stem = "solvers/electrical/diffusion/diffusion3d"
+    for ext in (".hpp", ".cpp"):
+        os.makedirs(os.path.dirname(tmp_path / (stem + ext)), exist_ok=True)
+        shutil.copyfile(os.path.join(REF, stem + ext), tmp_path / (stem + ext))
+    subprocess.run(["patch", "-p1", "--batch", "--forward", "-d", str(tmp_path), "-i", PATCH], capture_output=True, text=True)
+    src = open(tmp_path / (stem + ".cpp")).read()
+    members = "".join(l for l in _added_lines(stem + ".hpp") if not l.startswith(("#include", "namespace plaskdiff")))
+    assert "std::map<size_t, std::unique_ptr<plaskdiff::Region>> cuda;" in members
+    code = f"""#include "mock_plask.hpp"
+#include "plaskdiff_cuda.hpp"
+namespace plask {{ namespace electrical {{ namespace diffusion {{
+struct Diffusion3DSolver : public FemSolverWithMaskedMesh<Geometry3D, RectangularMesh<3>> {{
+    double maxerr, toterr; unsigned loopno;
+    std::map<size_t, ActiveRegion3D> active;
+    WavelengthReceiverModel inWavelength; GainReceiverModel inGain; ProviderModel outCarriersConcentration;
+    void onInvalidate();
+{members}
+}};
+{_function(src, "Diffusion3DSolver", "computeCuda")}
+}}}}}}
+"""
+    gen = tmp_path / "gen.cpp"
+    gen.write_text(code)
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wno-unused-variable", "-I", os.path.join(ROOT, "include"),
+                        "-I", os.path.join(ROOT, "tests", "cpp"), str(gen)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[:6000]

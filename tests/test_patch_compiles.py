@@ -192,3 +192,40 @@ struct Diffusion3DSolver : public FemSolverWithMaskedMesh<Geometry3D, Rectangula
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Wno-unused-variable", "-I", os.path.join(ROOT, "include"),
                         "-I", os.path.join(ROOT, "tests", "cpp"), str(gen)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[:6000]
+
+
+def test_beta_solver_override_matches_every_base(tmp_path):
+    """BetaSolver<GeometryT> (beta.hpp) derives from ElectricalFem3DSolver for Geometry3D and from ElectricalFem2DSolver<GeometryT>
+    otherwise; the `shockleyParameters(...) const override` the patch adds to it only compiles if BOTH bases declare that virtual."""
+    beta = "".join(_added_lines("solvers/electrical/shockley/beta.hpp"))
+    assert "bool shockleyParameters(size_t n, double PLASK_UNUSED(T), double& beta, double& js) const override" in beta
+
+    def virtual_of(path):
+        lines = _added_lines(path)
+        i = next(k for k, l in enumerate(lines) if "virtual bool shockleyParameters(" in l)
+        return lines[i] + lines[i + 1]
+    v3, v2 = virtual_of("solvers/electrical/shockley/electr3d.hpp"), virtual_of("solvers/electrical/shockley/electr2d.hpp")
+    code = f"""#include "mock_plask.hpp"
+namespace plask {{
+struct ElectricalFem3DSolver {{ virtual ~ElectricalFem3DSolver() {{}}
+{v3}
+}};
+template <typename G> struct ElectricalFem2DSolver {{ virtual ~ElectricalFem2DSolver() {{}}
+{v2}
+}};
+template <typename GeometryT>
+struct BetaSolver : public std::conditional<std::is_same<GeometryT, Geometry3D>::value, ElectricalFem3DSolver, ElectricalFem2DSolver<GeometryT>>::type {{
+    double getBeta(size_t) const {{ return 11.; }}
+    double getJs(size_t) const {{ return 1.; }}
+{beta}
+}};
+template struct BetaSolver<Geometry3D>;
+template struct BetaSolver<Geometry2DCartesian>;
+template struct BetaSolver<Geometry2DCylindrical>;
+}}
+"""
+    gen = tmp_path / "gen.cpp"
+    gen.write_text(code)
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "tests", "cpp"), str(gen)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[:4000]

@@ -89,6 +89,24 @@ def embed(p2, thickness=1.):
     return p
 
 
+def interpolate2d(p2, field, xq, yq):
+    """A nodal field of the 2-D mesh on the product mesh xq x yq (numbering i0 * len(yq) + i1), linear like
+    interpolate(mesh, data, dst_mesh, INTERPOLATION_LINEAR) of the 2-D providers (getTemperatures, therm2d.cpp:529-536;
+    getVoltage, electr2d.cpp:507-514): points outside the mesh take the value of the nearest edge.  Host side: the providers of the
+    2-D solvers hand out a few thousand values, the field is already downloaded."""
+    x, y = np.asarray(p2.x, dtype=np.float64), np.asarray(p2.y, dtype=np.float64)
+    v = np.asarray(field, dtype=np.float64).reshape(len(x), len(y))
+
+    def weights(a, q):
+        q = np.clip(np.asarray(q, dtype=np.float64), a[0], a[-1])
+        hi = np.clip(np.searchsorted(a, q, side="right"), 1, len(a) - 1)
+        return hi - 1, hi, (q - a[hi - 1]) / (a[hi] - a[hi - 1])
+    i0, i1, fx = weights(x, xq)
+    j0, j1, fy = weights(y, yq)
+    fx, fy = fx[:, None], fy[None, :]
+    return ((1. - fx) * ((1. - fy) * v[i0][:, j0] + fy * v[i0][:, j1]) + fx * ((1. - fy) * v[i1][:, j0] + fy * v[i1][:, j1])).ravel()
+
+
 class _Embedded2D:
     """shared plumbing of the four solvers: `problem` takes a Problem2D, providers return 2-D arrays"""
     cyl = False
@@ -147,11 +165,11 @@ class Static2D(_Embedded2D, Static3D):
                                mode2d=2 if self.cyl else 1)
 
     def outTemperature(self, mesh=None):
-        if mesh is not None:
-            raise L.BadInput(f"{self.id}: interpolation onto a foreign 2-D mesh is left to the plugin's own interpolation")
+        """temperatures on the solver's own mesh, or (mesh = (xq, yq)) interpolated linearly onto a foreign rectangular 2-D mesh"""
         if not self.initialized:
-            return np.full(self._p2.N, float(self.inittemp))
-        return self._plane(Static3D.outTemperature(self))
+            return np.full(self._p2.N if mesh is None else len(mesh[0]) * len(mesh[1]), float(self.inittemp))
+        T = self._plane(Static3D.outTemperature(self))
+        return T if mesh is None else interpolate2d(self._p2, T, mesh[0], mesh[1])
 
     def outHeatFlux(self):
         """(E, 2): (-k_x dT/dx, -k_y dT/dy) at the element midpoints, W/m^2 (saveHeatFluxes, therm2d.cpp:494-527)"""
@@ -174,11 +192,10 @@ class Dynamic2D(_Embedded2D, Dynamic3D):
     (:415-445) is the one of femT3d.cpp — pfem_solve_dynamic, corrected theta scheme."""
 
     def outTemperature(self, mesh=None):
-        if mesh is not None:
-            raise L.BadInput(f"{self.id}: interpolation onto a foreign 2-D mesh is left to the plugin's own interpolation")
         if not self.initialized:
-            return np.full(self._p2.N, float(self.inittemp))
-        return self._plane(Dynamic3D.outTemperature(self))
+            return np.full(self._p2.N if mesh is None else len(mesh[0]) * len(mesh[1]), float(self.inittemp))
+        T = self._plane(Dynamic3D.outTemperature(self))
+        return T if mesh is None else interpolate2d(self._p2, T, mesh[0], mesh[1])
 
     def outHeatFlux(self):
         return Dynamic3D.outHeatFlux(self)[:, 1:3].copy()
@@ -193,9 +210,9 @@ class Shockley2D(_Embedded2D, Shockley3D):
     """electrical.shockley.Shockley2D with algorithm='cuda' (electr2d.cpp + beta.hpp, Geometry2DCartesian)"""
 
     def outVoltage(self, mesh=None):
-        if mesh is not None:
-            raise L.BadInput(f"{self.id}: interpolation onto a foreign 2-D mesh is left to the plugin's own interpolation")
-        return self._plane(Shockley3D.outVoltage(self))
+        """potentials on the solver's own mesh, or (mesh = (xq, yq)) interpolated linearly onto a foreign rectangular 2-D mesh"""
+        V = self._plane(Shockley3D.outVoltage(self))
+        return V if mesh is None else interpolate2d(self._p2, V, mesh[0], mesh[1])
 
     def outCurrentDensity(self):
         """(E, 2) kA/cm^2 (electr2d.cpp:399-405)"""

@@ -83,3 +83,23 @@ def test_2d_mirror_integrals_vs_oracle2d(cyl):
     assert np.array_equal(p3.elem_mat, p2.elem_mat) and np.array_equal(p3.elem_junc, p2.elem_junc)
     with pytest.raises(L.BadInput):
         (Shockley2D if cyl else ShockleyCyl)("wrong").problem = p2       # Cartesian problem on the cylindrical solver and vice versa
+
+
+def test_2d_provider_interpolation_vs_oracle2d():
+    """outTemperature / outVoltage of the 2-D mirror on a foreign rectangular mesh (host-side bilinear interpolation, clamped outside
+    like interpolateLinear) against the oracle's independent implementation and against scipy"""
+    from scipy.interpolate import RegularGridInterpolator
+    from oracle import oracle2d
+    from helpers import thermal2d_problem
+    from plask_b200.solvers2d import interpolate2d
+    p2 = thermal2d_problem((9, 12))
+    rng = np.random.default_rng(2)
+    f = rng.normal(size=p2.N)
+    xq = np.concatenate([[p2.x[0] - 1.], rng.uniform(p2.x[0], p2.x[-1], 9), [p2.x[-1], p2.x[-1] + 2.]])
+    yq = np.concatenate([[p2.y[0] - 0.3], rng.uniform(p2.y[0], p2.y[-1], 7), [p2.y[0], p2.y[-1] + 1.]])
+    got = interpolate2d(p2, f, xq, yq)
+    assert np.abs(got - oracle2d.interp_bilinear(p2.x, p2.y, f, xq, yq)).max() <= 1e-13
+    X, Y = np.meshgrid(np.clip(xq, p2.x[0], p2.x[-1]), np.clip(yq, p2.y[0], p2.y[-1]), indexing="ij")
+    ref = RegularGridInterpolator((p2.x, p2.y), f.reshape(p2.n))(np.stack([X, Y], axis=-1)).ravel()
+    assert np.abs(got - ref).max() <= 1e-13
+    assert np.abs(interpolate2d(p2, f, p2.x, p2.y) - f).max() == 0.       # the own mesh: identity

@@ -135,9 +135,9 @@ int pfem_set_source(pfem_ctx* ctx, const double* heat_per_elem);
  * have a value; flags and values are read from the nodes of plane 0 and the terms are added on both planes, scaled like the
  * embedded operator.  The 2-D solver puts every term on the right node, so verbatim means something else here: the convection
  * matrix terms are taken as written, WITHOUT the 1e-6 (um -> m) their load terms carry (:241,244 against :238) and,
- * cylindrical, with the second factor r they pick up in A += r * k11 (:385-397 against :415-426) — the solution is then pinned
- * to the ambient temperature; verbatim == 0 restores the unit factor and the single r.  mode2d = 2 is the one case that may be
- * combined with pfem_set_axis_weight (set the weights first). */
+ * cylindrical, with the second factor r they pick up in A += r * k11 (:385-397 against :415-426) — the boundary is then pinned
+ * to about 1e-6 * ambient (its matrix term is 1e6 times its own load term); verbatim == 0 restores the unit factor and the
+ * single r.  mode2d = 2 is the one case that may be combined with pfem_set_axis_weight (set the weights first). */
 typedef struct {
     const uint8_t* has_flux;  const double* flux;                                     /* W/m^2            */
     const uint8_t* has_conv;  const double* conv_coeff;     const double* conv_ambient; /* W/(m^2 K), K    */

@@ -192,3 +192,32 @@ def test_host_flattening_properties():
         assert not load[lonely.ravel()].any() and not K[lonely.ravel()].any()
 
     check()
+
+
+def test_host_flattening_equals_oracle_on_random_cases():
+    """random meshes, random node sets and node-wise random values for all three kinds (several overlapping conditions each: the first
+    one naming a node wins), both geometries, verbatim and corrected: library flattening == oracle restatement"""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=30, deadline=None)
+    @given(st.integers(0, 2 ** 31 - 1), st.integers(2, 8), st.integers(2, 8), st.booleans(), st.booleans())
+    def check(seed, n0, n1, cyl, verbatim):
+        rng = np.random.default_rng(seed)
+        x = (0. if cyl else -1.) + np.concatenate([[0.], np.cumsum(rng.uniform(0.1, 3., n0 - 1))])
+        y = np.concatenate([[0.], np.cumsum(rng.uniform(0.1, 3., n1 - 1))])
+        m = oracle2d.Mesh2D(x, y)
+        pick = lambda frac: np.nonzero(rng.random(m.N) < frac)[0]
+        heatflux = [(pick(0.5), rng.uniform(-1e6, 1e6)), (pick(0.5), rng.uniform(-1e6, 1e6))]
+        convection = [(pick(0.4), rng.uniform(1., 1e5), rng.uniform(250., 350.)), (pick(0.6), rng.uniform(1., 1e5), rng.uniform(250., 350.))]
+        radiation = [(pick(0.5), rng.uniform(0.1, 1.), rng.uniform(250., 350.)), (pick(0.3), rng.uniform(0.1, 1.), rng.uniform(250., 350.))]
+        T = rng.uniform(250., 500., m.N)
+        (kr, kc, kd), F = oracle2d.edge_terms(m, T, heatflux, convection, radiation, cyl=cyl, verbatim=verbatim)
+        Ko = np.zeros((m.N, m.N))
+        np.add.at(Ko, (kr, kc), kd)
+        load, rcoef, ramb4, K = _host_terms(x, y, heatflux, convection, radiation, cyl, verbatim)
+        Fh = load - rcoef * (T ** 4 - ramb4)
+        assert np.abs(K - Ko).max() <= 1e-13 * max(np.abs(Ko).max(), 1e-300)
+        assert np.abs(Fh - F).max() <= 1e-12 * max(np.abs(F).max(), 1e-300)
+
+    check()

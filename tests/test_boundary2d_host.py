@@ -221,3 +221,35 @@ def test_host_flattening_equals_oracle_on_random_cases():
         assert np.abs(Fh - F).max() <= 1e-12 * max(np.abs(F).max(), 1e-300)
 
     check()
+
+
+def test_oracle_cylindrical_side_wall_analytic():
+    """radial conduction through a hollow cylinder: T = T_i on the inner wall (r_i), convection (corrected units) or a heat flux on the
+    outer wall (r_o) — the RIGHT-side terms of the cylindrical solver carry elem.getUpper0() (therm2d.cpp:375-377, :385-397):
+        convection:  T(r) = T_i - (T_i - T_a) ln(r / r_i) / (ln(r_o / r_i) + k / (h r_o))
+        heat flux q leaving the wall:  T(r) = T_i - q r_o ln(r / r_i) / k
+    (lengths in metres in the formulas).  Second-order convergence of the 4-node elements: 1e-4 of the drop on 201 radial nodes."""
+    ri, ro, k = 2.0, 10.0, 30.
+    x = np.linspace(ri, ro, 201)
+    y = np.linspace(0., 1., 3)
+    n0, n1 = len(x), len(y)
+    E = (n0 - 1) * (n1 - 1)
+    tab = np.full((1, 2), k)
+    ng = np.arange(n0 * n1).reshape(n0, n1)
+    inner, outer = ng[0, :], ng[-1, :]
+    Ti, Ta, h, q = 400., 300., 2.0e6, 5.0e7
+    r = np.repeat(x, n1)
+
+    o = oracle2d.Static2DOracle(x, y, np.zeros(E, dtype=np.int64), 300., 1000., tab, tab, inner, np.full(n1, Ti), cyl=True)
+    o.convection, o.verbatim = [(outer, h, Ta)], False
+    o.compute(1)
+    exact = Ti - (Ti - Ta) * np.log(r / ri) / (np.log(ro / ri) + k / (h * ro * 1e-6))
+    assert np.abs(o.temperatures - exact).max() <= 1e-4 * (Ti - exact.min())
+    assert Ti - exact.min() > 20.
+
+    o = oracle2d.Static2DOracle(x, y, np.zeros(E, dtype=np.int64), 300., 1000., tab, tab, inner, np.full(n1, Ti), cyl=True)
+    o.heatflux = [(outer, q)]
+    o.compute(1)
+    exact = Ti - q * (ro * 1e-6) * np.log(r / ri) / k
+    assert np.abs(o.temperatures - exact).max() <= 1e-4 * (Ti - exact.min())
+    assert Ti - exact.min() > 20.

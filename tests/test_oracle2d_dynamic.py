@@ -68,3 +68,30 @@ def test_embedding_agrees_with_the_3d_oracle(cyl, lumping):
         oc = oracle_dynamic2d(pc, timestep=0.5, methodparam=0.5, lumping=lumping, rebuildfreq=3)
         oc.compute(4.)
         assert np.abs(oc.temperatures - o2.temperatures).max() <= 1e-4 * (o2.temperatures.max() - 300.)
+
+
+def test_cylinder_radial_cooling_bessel():
+    """solid cylinder of radius R, wall held at 300 K, T(r, 0) = 300 + a J0(l1 r / R): the exact solution is the same profile times
+    exp(-alpha l1^2 t / R^2) (l1 = first zero of J0).  Exercises the radial weights of K AND of the capacity matrix (c r, femT2d.cpp:
+    307-313) — the slab test above cannot see a wrong weight on c."""
+    from scipy.special import j0, jn_zeros
+    from plask_b200.solvers2d import Problem2D
+    R, k, cprho, a = 3.0, 45., 0.327e3 * 5.31749e3, 40.
+    nx, ny = 121, 3
+    x, y = np.linspace(0., R, nx), np.linspace(0., 0.5, ny)
+    tab = np.full((1, 2), k)
+    ng = np.arange(nx * ny).reshape(nx, ny)
+    p = Problem2D("bessel", "thermal", x, y, np.zeros((nx - 1) * (ny - 1), dtype=np.uint32), 200., 1000., tab, tab.copy(),
+                  ng[-1, :].astype(np.uintp), np.full(ny, 300.), heat=np.zeros((nx - 1) * (ny - 1)), cyl=True)
+    p.tab_cprho = np.full((1, 2), cprho)
+    l1 = jn_zeros(0, 1)[0]
+    alpha = k / cprho * 1e3                       # um^2 / ns
+    profile = np.repeat(j0(l1 * x / R), ny)
+    for lumping in (True, False):
+        o = oracle_dynamic2d(p, timestep=2.0, methodparam=0.5, lumping=lumping)
+        o.temperatures = 300. + a * profile
+        o.compute(60.)
+        exact = 300. + a * profile * np.exp(-alpha * (l1 / R) ** 2 * o.physical_time)
+        left = a * np.exp(-alpha * (l1 / R) ** 2 * o.physical_time)
+        assert 0.2 * a < left < 0.8 * a           # a good part of the transient has happened, a good part is left
+        assert np.abs(o.temperatures - exact).max() <= 2e-3 * left, lumping

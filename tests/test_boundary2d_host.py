@@ -253,3 +253,21 @@ def test_oracle_cylindrical_side_wall_analytic():
     exact = Ti - q * (ro * 1e-6) * np.log(r / ri) / k
     assert np.abs(o.temperatures - exact).max() <= 1e-4 * (Ti - exact.min())
     assert Ti - exact.min() > 20.
+
+
+def test_oracle_cylindrical_inner_wall_analytic():
+    """the LEFT-side terms carry elem.getLower0() (therm2d.cpp:375): heat flux q leaving through the inner wall of a hollow cylinder whose
+    outer wall is held at T_o:  T(r) = T_o + q r_i ln(r / r_o) / k"""
+    ri, ro, k, To, q = 2.0, 10.0, 30., 400., 2.0e8
+    x = np.linspace(ri, ro, 201)
+    y = np.linspace(0., 1., 3)
+    n0, n1 = len(x), len(y)
+    tab = np.full((1, 2), k)
+    ng = np.arange(n0 * n1).reshape(n0, n1)
+    o = oracle2d.Static2DOracle(x, y, np.zeros((n0 - 1) * (n1 - 1), dtype=np.int64), 300., 1000., tab, tab, ng[-1, :], np.full(n1, To), cyl=True)
+    o.heatflux = [(ng[0, :], q)]
+    o.compute(1)
+    r = np.repeat(x, n1)
+    exact = To + q * (ri * 1e-6) * np.log(r / ro) / k
+    assert To - exact.min() > 20.
+    assert np.abs(o.temperatures - exact).max() <= 1e-4 * (To - exact.min())
